@@ -1,0 +1,154 @@
+/*
+ * nf_b200.h -- C ABI of the B200-native coupling-flow hot path.
+ *
+ * Drop-in boundary for the reference's flow (there is no native interface in the reference;
+ * every entry point names the Python symbol it replaces, paths relative to /root/reference):
+ *
+ *   nf_flow_forward   <- RealNVP.forward        il-and-cil/utils/torch_fcnf.py:134-141
+ *                        (MetaBlock.forward :95-106, InvertiblePLU.forward :33-42)
+ *   nf_flow_inverse   <- RealNVP.reverse        il-and-cil/utils/torch_fcnf.py:143-152
+ *                        (MetaBlock.reverse :108-117, InvertiblePLU.reverse :44-58;
+ *                         optional log-det as unsupservised-gcrl/nf.py:131-148)
+ *   nf_flow_backward  <- torch.autograd through the above (loss.backward(),
+ *                        il-and-cil/torch_nfbc_ant.py:269-272; input gradient for the denoise
+ *                        step :212-217)
+ *   nf_flow_prepare   <- the per-call parameter work the reference redoes inside every
+ *                        forward/reverse: W = P L U (:34-38), W^-1 by two triangular solves
+ *                        (:45-54), sum log|s| (:41)
+ *   nf_affine_logdet_{fwd,inv,bwd} <- the affine coupling + log-det lines :101-104 / :112-113
+ *                        as a standalone HBM-bound kernel
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch / ATen types.
+ *   - Every pointer is a DEVICE pointer to caller-owned memory (fp32, row-major, contiguous,
+ *     16-byte aligned) borrowed for the duration of the call; the library allocates nothing on
+ *     the data path.  Scratch and stash buffers are sized by the *_bytes queries.
+ *   - All work is enqueued asynchronously on `stream` (a cudaStream_t passed as void*).
+ *   - Return value: 0 = ok, < 0 = bad argument (NF_E_*), > 0 = cudaError_t.  Nothing throws
+ *     across the ABI; nf_last_error() returns a thread-local message for the last failure.
+ *   - Re-entrant; one process per GPU.
+ */
+#ifndef NF_B200_H
+#define NF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NF_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define NF_API __attribute__((visibility("default")))
+#else
+#define NF_API
+#endif
+
+#define NF_E_BADARG   (-1)
+#define NF_E_ALIGN    (-2)
+#define NF_E_WORKSPACE (-3)
+#define NF_E_UNSUPPORTED (-4)
+
+/* Arithmetic of the conditioner GEMMs. */
+#define NF_PREC_FP32_SIMT 0 /* FFMA, exact fp32 (checker / odd shapes)                         */
+#define NF_PREC_TF32X3    1 /* tcgen05 kind::tf32, 3-pass split operands, fp32 accumulate:     */
+                            /* fp32-parity mode (<= 1e-5 vs the fp64 arbiter)                   */
+#define NF_PREC_BF16      2 /* tcgen05 kind::f16 (bf16 operands), 2e-2 contract                */
+
+typedef struct NfFlowDesc {
+  int32_t D;        /* in_channels: flow dimension                                     */
+  int32_t C;        /* channels: conditioner width (second hidden layer and LN size)    */
+  int32_t H1;       /* first hidden width: C (torch_fcnf.py:75) or C+R (nf.py:94)       */
+  int32_t R;        /* cond_channels                                                    */
+  int32_t n_blocks; /* n_layers                                                         */
+  float   ln_eps;   /* 1e-5 (torch nn.LayerNorm) or 1e-6 (flax nn.LayerNorm)            */
+  int32_t precision;/* NF_PREC_*                                                        */
+  int32_t reserved;
+} NfFlowDesc;
+
+/* Per-block slots of the flat parameter arena, in order.  Offsets are in floats, every slot
+ * starts on a multiple of 4 floats.  Net 0 is `t`, net 1 is `s` (state_dict order). */
+enum {
+  NF_P_S = 0, NF_P_U, NF_P_L, NF_P_P, NF_P_PINV,                 /* blocks.i.l.{s,U,L,P,P_inv} */
+  NF_P_W1, NF_P_B1, NF_P_G1, NF_P_BE1, NF_P_W2, NF_P_B2, NF_P_G2, NF_P_BE2, NF_P_W3, NF_P_B3,
+  NF_P_NET_SLOTS = 10,                                            /* {0,2,3,5,6}.{weight,bias}  */
+  NF_P_SLOTS = 5 + 2 * 10
+};
+
+typedef struct NfParamLayout {
+  int64_t slot_off[NF_P_SLOTS];  /* offset of each slot inside one block (net t then net s) */
+  int64_t slot_numel[NF_P_SLOTS];
+  int64_t block_stride;          /* floats per block                                         */
+  int64_t net_stride;            /* offset(net s slot) - offset(net t slot)                  */
+  int64_t total;                 /* floats in the whole arena = n_blocks * block_stride      */
+} NfParamLayout;
+
+NF_API int nf_abi_version(void);
+NF_API const char* nf_last_error(void);
+
+/* Layout of the flat parameter / gradient arena for `desc` (pure host computation). */
+NF_API int nf_param_layout(const NfFlowDesc* desc, NfParamLayout* out);
+
+/* Buffer sizes (bytes). */
+NF_API int64_t nf_flow_packed_bytes(const NfFlowDesc* desc);
+NF_API int64_t nf_flow_stash_bytes(const NfFlowDesc* desc, int64_t B);
+NF_API int64_t nf_flow_workspace_bytes(const NfFlowDesc* desc, int64_t B);
+
+/* what: bit 0 = forward/backward tables, bit 1 = inverse tables (W^-1). */
+#define NF_PREP_FWD 1
+#define NF_PREP_INV 2
+NF_API int nf_flow_prepare(const NfFlowDesc* desc, const float* params, void* packed, int what,
+                    void* workspace, int64_t ws_bytes, void* stream);
+
+/* z (B,D), logdet (B,), outputs (n_blocks,B,D) or NULL.  `stash` (nf_flow_stash_bytes) receives
+ * what nf_flow_backward needs; pass NULL for an inference-only forward. */
+NF_API int nf_flow_forward(const NfFlowDesc* desc, const float* params, const void* packed,
+                    const float* x, const float* y, int64_t B,
+                    float* z, float* logdet, float* outputs, void* stash,
+                    void* workspace, int64_t ws_bytes, void* stream);
+
+/* x (B,D) from z (B,D); logdet (B,) or NULL (flax-style reverse log-det);
+ * seq (n_blocks+1,B,D) or NULL (return_sequence=True, seq[0] = z). */
+NF_API int nf_flow_inverse(const NfFlowDesc* desc, const float* params, const void* packed,
+                    const float* z, const float* y, int64_t B,
+                    float* x, float* logdet, float* seq,
+                    void* workspace, int64_t ws_bytes, void* stream);
+
+/* Given dz (B,D) and dlogdet (B,) (either may be NULL = zero):  dx (B,D) or NULL, dy (B,R) or
+ * NULL, dparams (flat arena, layout of nf_param_layout, fully overwritten) or NULL. */
+NF_API int nf_flow_backward(const NfFlowDesc* desc, const float* params, const void* packed,
+                     const void* stash, const float* y, int64_t B,
+                     const float* dz, const float* dlogdet,
+                     float* dx, float* dy, float* dparams,
+                     void* workspace, int64_t ws_bytes, void* stream);
+
+/* Standalone affine coupling + log-det kernels (HBM-bound; torch_fcnf.py:101-104, :112-113).
+ *   fwd: z[:, :dc] = xp[:, :dc];  z[:, dc:] = (xp[:, dc:] - t) * exp(-s);  logdet += c - sum_j s
+ *   inv: xp[:, dc:] = z[:, dc:] * exp(s) + t;                              logdet += sum_j s - c
+ *   bwd: ds = -dz_t * z_t - dlogdet; dt = -dz_t * exp(-s); dxp = [dz_c, dz_t * exp(-s)]
+ * s, t are (B, D/2) WITHOUT the last-layer bias; bias_s/bias_t (D/2) are added inside (may be NULL).
+ * logdet may be NULL. */
+NF_API int nf_affine_logdet_fwd(const float* xp, const float* s, const float* t,
+                         const float* bias_s, const float* bias_t, float logdet_const,
+                         int64_t B, int32_t D, float* z, float* logdet, float* s_out, void* stream);
+NF_API int nf_affine_logdet_inv(const float* z, const float* s, const float* t,
+                         const float* bias_s, const float* bias_t, float logdet_const,
+                         int64_t B, int32_t D, float* xp, float* logdet, void* stream);
+NF_API int nf_affine_logdet_bwd(const float* dz, const float* z, const float* s_full, const float* dlogdet,
+                         int64_t B, int32_t D, float* dxp, float* ds, float* dt, void* stream);
+
+/* Standalone PLU build (torch_fcnf.py:34-38, :45-54): W (D,D), optional W_inv (D,D), logdet (1). */
+NF_API int nf_plu_build(const float* s, const float* U, const float* L, const float* P, const float* P_inv,
+                 int32_t D, float* W, float* W_inv, float* logdet, void* workspace, int64_t ws_bytes,
+                 void* stream);
+
+/* Number of kernels this library launched on the calling thread since the last reset
+ * (bench.py's gpu_launches). */
+NF_API int64_t nf_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NF_B200_H */

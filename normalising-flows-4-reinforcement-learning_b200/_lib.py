@@ -1,0 +1,85 @@
+"""ctypes binding of libnf_b200.so (include/nf_b200.h).  No CPU fallback: if the CUDA
+library is missing the import of this module fails loudly."""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libnf_b200.so")
+
+PREC = {"fp32_simt": 0, "fp32": 1, "tf32x3": 1, "bf16": 2}
+
+NF_P_SLOTS = 25
+NF_P_NET_SLOTS = 10
+SLOT_NAMES = ["l.s", "l.U", "l.L", "l.P", "l.P_inv"] + [
+    f"{net}.{k}" for net in ("t", "s")
+    for k in ("0.weight", "0.bias", "2.weight", "2.bias", "3.weight", "3.bias", "5.weight", "5.bias",
+              "6.weight", "6.bias")]
+NF_PREP_FWD, NF_PREP_INV = 1, 2
+
+
+class NfFlowDesc(Structure):
+    _fields_ = [("D", c_int32), ("C", c_int32), ("H1", c_int32), ("R", c_int32), ("n_blocks", c_int32),
+                ("ln_eps", c_float), ("precision", c_int32), ("reserved", c_int32)]
+
+
+class NfParamLayout(Structure):
+    _fields_ = [("slot_off", c_int64 * NF_P_SLOTS), ("slot_numel", c_int64 * NF_P_SLOTS),
+                ("block_stride", c_int64), ("net_stride", c_int64), ("total", c_int64)]
+
+
+class NfError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        # Build in-tree on first use (nvcc cross-compiles for sm_100a without a GPU).
+        from .build import build
+        build()
+    lib = ctypes.CDLL(LIB_PATH)
+    D = POINTER(NfFlowDesc)
+    fp, vp, i64 = c_void_p, c_void_p, c_int64   # device pointers are passed as integers
+    sigs = {
+        "nf_abi_version": (c_int, []),
+        "nf_last_error": (c_char_p, []),
+        "nf_param_layout": (c_int, [D, POINTER(NfParamLayout)]),
+        "nf_flow_packed_bytes": (c_int64, [D]),
+        "nf_flow_stash_bytes": (c_int64, [D, i64]),
+        "nf_flow_workspace_bytes": (c_int64, [D, i64]),
+        "nf_flow_prepare": (c_int, [D, fp, vp, c_int, vp, i64, vp]),
+        "nf_flow_forward": (c_int, [D, fp, vp, fp, fp, i64, fp, fp, fp, vp, vp, i64, vp]),
+        "nf_flow_inverse": (c_int, [D, fp, vp, fp, fp, i64, fp, fp, fp, vp, i64, vp]),
+        "nf_flow_backward": (c_int, [D, fp, vp, vp, fp, i64, fp, fp, fp, fp, fp, vp, i64, vp]),
+        "nf_affine_logdet_fwd": (c_int, [fp, fp, fp, fp, fp, c_float, i64, c_int32, fp, fp, fp, vp]),
+        "nf_affine_logdet_inv": (c_int, [fp, fp, fp, fp, fp, c_float, i64, c_int32, fp, fp, vp]),
+        "nf_affine_logdet_bwd": (c_int, [fp, fp, fp, fp, i64, c_int32, fp, fp, fp, vp]),
+        "nf_plu_build": (c_int, [fp, fp, fp, fp, fp, c_int32, fp, fp, fp, vp, i64, vp]),
+        "nf_launch_count": (c_int64, [c_int]),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib, sorted(sigs)
+
+
+lib, EXPORTS = _load()
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = lib.nf_last_error().decode(errors="replace")
+        raise NfError(f"{what} failed (code {rc}): {msg}")
+
+
+def make_desc(D, C, H1, R, n, ln_eps, precision) -> NfFlowDesc:
+    return NfFlowDesc(int(D), int(C), int(H1), int(R), int(n), float(ln_eps), int(precision), 0)
+
+
+def param_layout(desc: NfFlowDesc) -> NfParamLayout:
+    out = NfParamLayout()
+    check(lib.nf_param_layout(ctypes.byref(desc), ctypes.byref(out)), "nf_param_layout")
+    return out

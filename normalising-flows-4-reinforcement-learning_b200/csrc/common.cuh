@@ -1,0 +1,88 @@
+// Shared host/device helpers for the nf_b200 C-ABI library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/nf_b200.h"
+
+namespace nf {
+
+constexpr float kLeakySlope = 0.01f;  // nn.LeakyReLU() default (torch_fcnf.py:75)
+
+// ---- error plumbing (thread-local message, never throws) --------------------------------
+char* err_buf();
+int set_err(int code, const char* fmt, ...);
+int64_t& launch_counter();
+
+#define NF_CHECK_ARG(cond, code, ...)                    \
+  do {                                                   \
+    if (!(cond)) return nf::set_err((code), __VA_ARGS__); \
+  } while (0)
+
+#define NF_CUDA(expr)                                                                      \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess)                                                                 \
+      return nf::set_err((int)_e, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),  \
+                         __FILE__, __LINE__);                                              \
+  } while (0)
+
+// counts the launch and converts a launch failure to a return code
+#define NF_LAUNCHED()                    \
+  do {                                   \
+    nf::launch_counter()++;              \
+    NF_CUDA(cudaPeekAtLastError());      \
+  } while (0)
+
+static inline int64_t pad4(int64_t v) { return (v + 3) & ~int64_t(3); }
+static inline int64_t pad32(int64_t v) { return (v + 31) & ~int64_t(31); }
+static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+struct Dims {
+  int D, C, H1, R, n, dc, dt, K1;
+  float eps;
+  int prec;
+};
+
+static inline Dims dims_of(const NfFlowDesc* d) {
+  Dims m;
+  m.D = d->D; m.C = d->C; m.H1 = d->H1; m.R = d->R; m.n = d->n_blocks;
+  m.dc = (d->D + 1) / 2;  // torch.tensor_split(x, 2, dim=1): first chunk is the larger one
+  m.dt = d->D / 2;
+  m.K1 = m.dc + d->R;
+  m.eps = d->ln_eps;
+  m.prec = d->precision;
+  return m;
+}
+
+int check_desc(const NfFlowDesc* d);
+void param_layout(const Dims& m, NfParamLayout* out);
+
+// ---- packed (derived) parameter tables -----------------------------------------------------
+// Per block:  W (D*D), Winv (D*D), Lh (D*D), Uh (D*D), PL (D*D) [= P @ Lh], then per net (t, s):
+//             W2f (C*H1), b2f (C), W3f (dt*C), b3f (dt).
+// After all blocks: logdet_c (n floats, sum log|s| per block) and logdet_total (1 float).
+struct PackedLayout {
+  int64_t W, Winv, Lh, Uh, PL;
+  int64_t net0;          // offset of net t tables inside a block
+  int64_t W2f, b2f, W3f, b3f;  // offsets inside a net
+  int64_t net_stride, block_stride;
+  int64_t logdet_c, logdet_total, total;
+};
+PackedLayout packed_layout(const Dims& m);
+
+// ---- stash written by forward for backward ---------------------------------------------------
+// xs: (n+1, B, D) block inputs (xs[0] = x, xs[i+1] = output of block i)
+// ss: (n, B, dt)  log-scales s of every block
+// then per block, per net (t, s):  xh1 (B*H1), xh2 (B*C), r1 (B), r2 (B), m1 (B*W1w), m2 (B*W2w)
+struct StashLayout {
+  int64_t xs, ss, blocks;
+  int64_t xh1, xh2, r1, r2, m1, m2;   // offsets inside a net
+  int64_t net_stride, block_stride, total;
+  int mw1, mw2;                        // mask words per row
+};
+StashLayout stash_layout(const Dims& m, int64_t B);
+
+}  // namespace nf

@@ -1,0 +1,533 @@
+// Row-wise and parameter-sized kernels of the flow (sm_100a).
+#include "elementwise.cuh"
+
+namespace nf {
+
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// LeakyReLU + LayerNorm (no affine: gamma/beta are folded into the next Linear, see fold_ln_affine)
+// one warp per row; three passes over the row (mean, centred variance, normalise) like
+// nn.LayerNorm's two-pass statistics (torch_fcnf.py:75-76).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_lrelu_ln_fwd(LnFwdP p) {
+  const int net = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= p.B) return;
+  const float* u = p.u + net * p.u_net + row * p.N;
+  const float* bias = p.bias ? p.bias + net * p.bias_net : nullptr;
+  float* xh = p.xh + net * p.xh_net + row * p.N;
+  float* xlo = p.xh_lo ? p.xh_lo + net * p.xh_lo_net + row * p.N : nullptr;
+  const int N = p.N;
+
+  float sum = 0.f;
+  for (int c = lane; c < N; c += 32) {
+    float v = u[c] + (bias ? bias[c] : 0.f);
+    v = v > 0.f ? v : kLeakySlope * v;
+    sum += v;
+  }
+  const float mean = warp_sum(sum) / (float)N;
+  float sq = 0.f;
+  for (int c = lane; c < N; c += 32) {
+    float v = u[c] + (bias ? bias[c] : 0.f);
+    v = v > 0.f ? v : kLeakySlope * v;
+    const float d = v - mean;
+    sq = fmaf(d, d, sq);
+  }
+  const float var = warp_sum(sq) / (float)N;
+  const float rstd = rsqrtf(var + p.eps);
+  uint32_t* mask = p.mask ? p.mask + net * p.mask_net + row * p.mw : nullptr;
+  for (int c0 = 0; c0 < N; c0 += 32) {
+    const int c = c0 + lane;
+    float pre = 0.f;
+    if (c < N) {
+      pre = u[c] + (bias ? bias[c] : 0.f);
+      const float v = pre > 0.f ? pre : kLeakySlope * pre;
+      const float o = (v - mean) * rstd;
+      if (xlo) {
+        const float hi = __uint_as_float(__float_as_uint(o) & 0xffffe000u);
+        xh[c] = hi;
+        xlo[c] = o - hi;
+      } else {
+        xh[c] = o;
+      }
+    }
+    const uint32_t bits = __ballot_sync(0xffffffffu, c < N && pre > 0.f);
+    if (mask && lane == 0) mask[c0 >> 5] = bits;
+  }
+  if (p.rstd && lane == 0) p.rstd[net * p.rstd_net + row] = rstd;
+}
+
+// d u = LeakyReLU'(u) * rstd * (g - mean(g) - x_hat * mean(g * x_hat)),  g = d x_hat
+// column sums of d u (bias gradient) are accumulated per CTA in shared memory, then atomically.
+constexpr int kBwdRowsPerWarp = 8;
+__global__ void __launch_bounds__(256) k_ln_lrelu_bwd(LnBwdP p) {
+  extern __shared__ float s_col[];
+  const int net = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int N = p.N;
+  for (int c = threadIdx.x; c < N; c += blockDim.x) s_col[c] = 0.f;
+  __syncthreads();
+  const long long row0 = ((long long)blockIdx.x * nwarps + warp) * kBwdRowsPerWarp;
+  for (int r = 0; r < kBwdRowsPerWarp; ++r) {
+    const long long row = row0 + r;
+    if (row >= p.B) break;
+    float* g = p.g + net * p.g_net + row * N;
+    const float* xh = p.xh + net * p.xh_net + row * N;
+    const uint32_t* mask = p.mask + net * p.mask_net + row * p.mw;
+    const float rstd = p.rstd[net * p.rstd_net + row];
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = lane; c < N; c += 32) {
+      const float gv = g[c];
+      s1 += gv;
+      s2 = fmaf(gv, xh[c], s2);
+    }
+    const float m1 = warp_sum(s1) / (float)N, m2 = warp_sum(s2) / (float)N;
+    for (int c0 = 0; c0 < N; c0 += 32) {
+      const int c = c0 + lane;
+      const uint32_t bits = mask[c0 >> 5];
+      if (c < N) {
+        float dv = rstd * (g[c] - m1 - xh[c] * m2);
+        dv *= ((bits >> lane) & 1u) ? 1.0f : kLeakySlope;
+        g[c] = dv;
+        atomicAdd(&s_col[c], dv);
+      }
+    }
+  }
+  __syncthreads();
+  if (p.colsum) {
+    float* cs = p.colsum + net * p.colsum_net;
+    for (int c = threadIdx.x; c < N; c += blockDim.x) {
+      const float v = s_col[c];
+      if (v != 0.f) atomicAdd(&cs[c], v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Affine coupling + log-det (torch_fcnf.py:101-104 forward, :112-113 inverse).
+// Small D: one thread per row (adjacent threads touch adjacent rows -> coalesced, 128-bit when
+// the halves are multiples of 4).  Large D: one warp per row.
+// ------------------------------------------------------------------------------------------
+template <int VEC, bool INVERSE>
+__global__ void __launch_bounds__(256) k_affine_rowthread(const float* __restrict__ in, const float* __restrict__ s,
+                                                          const float* __restrict__ t, const float* __restrict__ bs,
+                                                          const float* __restrict__ bt, const float* cdev, float chost,
+                                                          long long B, int D, float* __restrict__ out,
+                                                          float* __restrict__ logdet, float* __restrict__ s_out) {
+  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= B) return;
+  const int dc = (D + 1) / 2, dt = D / 2;
+  const float* xi = in + row * D;
+  float* xo = out + row * D;
+  const float* sr = s + row * dt;
+  const float* tr = t + row * dt;
+  float ssum = 0.f;
+  if (VEC == 4) {
+    for (int j = 0; j < dc; j += 4) *reinterpret_cast<float4*>(xo + j) = *reinterpret_cast<const float4*>(xi + j);
+    for (int j = 0; j < dt; j += 4) {
+      float4 sv = *reinterpret_cast<const float4*>(sr + j);
+      float4 tv = *reinterpret_cast<const float4*>(tr + j);
+      const float4 xv = *reinterpret_cast<const float4*>(xi + dc + j);
+      if (bs) { sv.x += bs[j]; sv.y += bs[j + 1]; sv.z += bs[j + 2]; sv.w += bs[j + 3]; }
+      if (bt) { tv.x += bt[j]; tv.y += bt[j + 1]; tv.z += bt[j + 2]; tv.w += bt[j + 3]; }
+      float4 o;
+      if (!INVERSE) {
+        o.x = (xv.x - tv.x) * expf(-sv.x); o.y = (xv.y - tv.y) * expf(-sv.y);
+        o.z = (xv.z - tv.z) * expf(-sv.z); o.w = (xv.w - tv.w) * expf(-sv.w);
+      } else {
+        o.x = fmaf(xv.x, expf(sv.x), tv.x); o.y = fmaf(xv.y, expf(sv.y), tv.y);
+        o.z = fmaf(xv.z, expf(sv.z), tv.z); o.w = fmaf(xv.w, expf(sv.w), tv.w);
+      }
+      ssum += (sv.x + sv.y) + (sv.z + sv.w);
+      *reinterpret_cast<float4*>(xo + dc + j) = o;
+      if (s_out) *reinterpret_cast<float4*>(s_out + row * dt + j) = sv;
+    }
+  } else {
+    for (int j = 0; j < dc; ++j) xo[j] = xi[j];
+    for (int j = 0; j < dt; ++j) {
+      const float sv = sr[j] + (bs ? bs[j] : 0.f);
+      const float tv = tr[j] + (bt ? bt[j] : 0.f);
+      const float xv = xi[dc + j];
+      xo[dc + j] = INVERSE ? fmaf(xv, expf(sv), tv) : (xv - tv) * expf(-sv);
+      ssum += sv;
+      if (s_out) s_out[row * dt + j] = sv;
+    }
+  }
+  if (logdet) {
+    const float c = chost + (cdev ? *cdev : 0.f);
+    logdet[row] += INVERSE ? (ssum - c) : (c - ssum);
+  }
+}
+
+template <bool INVERSE>
+__global__ void __launch_bounds__(256) k_affine_rowwarp(const float* __restrict__ in, const float* __restrict__ s,
+                                                        const float* __restrict__ t, const float* __restrict__ bs,
+                                                        const float* __restrict__ bt, const float* cdev, float chost,
+                                                        long long B, int D, float* __restrict__ out,
+                                                        float* __restrict__ logdet, float* __restrict__ s_out) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= B) return;
+  const int dc = (D + 1) / 2, dt = D / 2;
+  const float* xi = in + row * D;
+  float* xo = out + row * D;
+  for (int j = lane; j < dc; j += 32) xo[j] = xi[j];
+  float ssum = 0.f;
+  for (int j = lane; j < dt; j += 32) {
+    const float sv = s[row * dt + j] + (bs ? bs[j] : 0.f);
+    const float tv = t[row * dt + j] + (bt ? bt[j] : 0.f);
+    const float xv = xi[dc + j];
+    xo[dc + j] = INVERSE ? fmaf(xv, expf(sv), tv) : (xv - tv) * expf(-sv);
+    ssum += sv;
+    if (s_out) s_out[row * dt + j] = sv;
+  }
+  ssum = warp_sum(ssum);
+  if (logdet && lane == 0) {
+    const float c = chost + (cdev ? *cdev : 0.f);
+    logdet[row] += INVERSE ? (ssum - c) : (c - ssum);
+  }
+}
+
+// backward of the affine coupling: per element, plus column sums of ds/dt (last-layer bias grads)
+__global__ void __launch_bounds__(256) k_affine_bwd(const float* __restrict__ dz, const float* __restrict__ z,
+                                                    const float* __restrict__ sfull, const float* __restrict__ dld,
+                                                    long long B, int D, float* __restrict__ dxp,
+                                                    float* __restrict__ ds, float* __restrict__ dtt,
+                                                    float* g3s, float* g3t) {
+  extern __shared__ float sh[];  // 2*dt partial column sums
+  const int dc = (D + 1) / 2, dt = D / 2;
+  for (int i = threadIdx.x; i < 2 * dt; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  const long long total = B * (long long)D;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long row = idx / D;
+    const int j = (int)(idx - row * D);
+    const float g = dz ? dz[idx] : 0.f;
+    if (j < dc) {
+      dxp[idx] = g;
+    } else {
+      const int jt = j - dc;
+      const float sv = sfull[row * dt + jt];
+      const float e = expf(-sv);
+      const float ge = g * e;
+      dxp[idx] = ge;
+      const float dsv = -g * z[idx] - (dld ? dld[row] : 0.f);
+      ds[row * dt + jt] = dsv;
+      dtt[row * dt + jt] = -ge;
+      if (g3s) {
+        atomicAdd(&sh[jt], dsv);
+        atomicAdd(&sh[dt + jt], -ge);
+      }
+    }
+  }
+  __syncthreads();
+  if (g3s) {
+    for (int i = threadIdx.x; i < dt; i += blockDim.x) {
+      atomicAdd(&g3s[i], sh[i]);
+      atomicAdd(&g3t[i], sh[dt + i]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// parameter-sized kernels
+// ------------------------------------------------------------------------------------------
+// Lh = tril(L,-1)+I, Uh = triu(U,1)+diag(s)  (torch_fcnf.py:34-38), logdet_c = sum log|s| (:41)
+__global__ void k_plu_mask(const float* params, NfParamLayout pl, int D, float* packed, PackedLayout kl) {
+  const int b = blockIdx.y;
+  const float* pb = params + (long long)b * pl.block_stride;
+  float* kb = packed + (long long)b * kl.block_stride;
+  const float* L = pb + pl.slot_off[NF_P_L];
+  const float* U = pb + pl.slot_off[NF_P_U];
+  const float* s = pb + pl.slot_off[NF_P_S];
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < D * D; idx += gridDim.x * blockDim.x) {
+    const int i = idx / D, j = idx % D;
+    kb[kl.Lh + idx] = i > j ? L[idx] : (i == j ? 1.f : 0.f);
+    kb[kl.Uh + idx] = i < j ? U[idx] : (i == j ? s[i] : 0.f);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < 32) {
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < D; i += 32) acc += logf(fabsf(s[i]));
+    acc = warp_sum(acc);
+    if (threadIdx.x == 0) packed[kl.logdet_c + b] = acc;
+  }
+}
+
+__global__ void k_logdet_total(float* packed, PackedLayout kl, int n) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    float acc = 0.f;
+    for (int i = 0; i < n; ++i) acc += packed[kl.logdet_c + i];
+    packed[kl.logdet_total] = acc;
+  }
+}
+
+// Triangular inverses by substitution against the identity, one thread per column
+// (torch.linalg.solve_triangular(..., eye), torch_fcnf.py:49-52).
+__global__ void k_tri_inverse(const float* packed, PackedLayout kl, int D, float* uinv, float* linv) {
+  const int b = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;  // column of the inverse
+  if (j >= D) return;
+  const float* Uh = packed + (long long)b * kl.block_stride + kl.Uh;
+  const float* Lh = packed + (long long)b * kl.block_stride + kl.Lh;
+  float* X = uinv + (long long)b * D * D;
+  float* Y = linv + (long long)b * D * D;
+  // upper: U X = I  -> back substitution; X[i][j] = 0 for i > j
+  for (int i = D - 1; i >= 0; --i) {
+    float acc = (i == j) ? 1.f : 0.f;
+    if (i <= j) {
+      for (int k = i + 1; k <= j; ++k) acc = fmaf(-Uh[i * D + k], X[k * D + j], acc);
+      X[i * D + j] = acc / Uh[i * D + i];
+    } else {
+      X[i * D + j] = 0.f;
+    }
+  }
+  // unit lower: L Y = I -> forward substitution; Y[i][j] = 0 for i < j
+  for (int i = 0; i < D; ++i) {
+    if (i < j) { Y[i * D + j] = 0.f; continue; }
+    float acc = (i == j) ? 1.f : 0.f;
+    for (int k = j; k < i; ++k) acc = fmaf(-Lh[i * D + k], Y[k * D + j], acc);
+    Y[i * D + j] = acc;
+  }
+}
+
+// W2f = W2 diag(gamma1), b2f = b2 + W2 beta1 ; W3f = W3 diag(gamma2), b3f = b3 + W3 beta2.
+// LayerNorm's affine part commutes into the next Linear, so the forward only stores x_hat.
+__global__ void k_fold(const float* params, NfParamLayout pl, Dims m, float* packed, PackedLayout kl) {
+  const int b = blockIdx.z, net = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // over C + dt output rows
+  const float* pn = params + (long long)b * pl.block_stride + net * pl.net_stride;
+  float* kn = packed + (long long)b * kl.block_stride + kl.net0 + net * kl.net_stride;
+  const float *W, *bias, *gam, *bet;
+  float *Wf, *bf;
+  int K, r;
+  if (row < m.C) {
+    r = row; K = m.H1;
+    W = pn + pl.slot_off[NF_P_W2]; bias = pn + pl.slot_off[NF_P_B2];
+    gam = pn + pl.slot_off[NF_P_G1]; bet = pn + pl.slot_off[NF_P_BE1];
+    Wf = kn + kl.W2f; bf = kn + kl.b2f;
+  } else if (row < m.C + m.dt) {
+    r = row - m.C; K = m.C;
+    W = pn + pl.slot_off[NF_P_W3]; bias = pn + pl.slot_off[NF_P_B3];
+    gam = pn + pl.slot_off[NF_P_G2]; bet = pn + pl.slot_off[NF_P_BE2];
+    Wf = kn + kl.W3f; bf = kn + kl.b3f;
+  } else {
+    return;
+  }
+  float acc = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float w = W[(long long)r * K + k];
+    Wf[(long long)r * K + k] = w * gam[k];
+    acc = fmaf(w, bet[k], acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) bf[r] = bias[r] + acc;
+}
+
+// Inverse of the folding for gradients (in place on the gradient arena):
+//   slot W{2,3} holds G = du^T x_hat, slot b{2,3} holds g = colsum(du)
+//   dW[n,k] = G[n,k] gamma[k] + g[n] beta[k];  dgamma[k] = sum_n G[n,k] W[n,k];  dbeta[k] = sum_n g[n] W[n,k]
+__global__ void k_unfold(const float* params, NfParamLayout pl, Dims m, float* dparams) {
+  const int b = blockIdx.z, net = blockIdx.y;
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  const float* pn = params + (long long)b * pl.block_stride + net * pl.net_stride;
+  float* dn = dparams + (long long)b * pl.block_stride + net * pl.net_stride;
+  for (int layer = 0; layer < 2; ++layer) {
+    const int rows = layer == 0 ? m.C : m.dt;
+    const int K = layer == 0 ? m.H1 : m.C;
+    if (col >= K) continue;
+    const int sw = layer == 0 ? NF_P_W2 : NF_P_W3, sb = layer == 0 ? NF_P_B2 : NF_P_B3;
+    const int sg = layer == 0 ? NF_P_G1 : NF_P_G2, sbe = layer == 0 ? NF_P_BE1 : NF_P_BE2;
+    const float* W = pn + pl.slot_off[sw];
+    float* G = dn + pl.slot_off[sw];
+    const float* g = dn + pl.slot_off[sb];
+    const float gam = pn[pl.slot_off[sg] + col], bet = pn[pl.slot_off[sbe] + col];
+    float dgam = 0.f, dbet = 0.f;
+    for (int n = 0; n < rows; ++n) {
+      const long long idx = (long long)n * K + col;
+      const float Gv = G[idx], w = W[idx], gn = g[n];
+      dgam = fmaf(Gv, w, dgam);
+      dbet = fmaf(gn, w, dbet);
+      G[idx] = fmaf(Gv, gam, gn * bet);
+    }
+    dn[pl.slot_off[sg] + col] = dgam;
+    dn[pl.slot_off[sbe] + col] = dbet;
+  }
+}
+
+// dL = tril(dLh,-1), dU = triu(dUh,1), ds = diag(dUh) + sum(dlogdet)/s
+__global__ void k_plu_grad_finish(const float* params, NfParamLayout pl, int D, const float* dLh, const float* dUh,
+                                  const float* sum_dld, float* dparams) {
+  const int b = blockIdx.y;
+  const float* pb = params + (long long)b * pl.block_stride;
+  float* db = dparams + (long long)b * pl.block_stride;
+  const float* dl = dLh + (long long)b * D * D;
+  const float* du = dUh + (long long)b * D * D;
+  const float sd = sum_dld ? *sum_dld : 0.f;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < D * D; idx += gridDim.x * blockDim.x) {
+    const int i = idx / D, j = idx % D;
+    db[pl.slot_off[NF_P_L] + idx] = i > j ? dl[idx] : 0.f;
+    db[pl.slot_off[NF_P_U] + idx] = i < j ? du[idx] : 0.f;
+    if (i == j) db[pl.slot_off[NF_P_S] + i] = du[idx] + sd / pb[pl.slot_off[NF_P_S] + i];
+  }
+}
+
+__global__ void k_sum_vector(const float* v, long long n, float* out) {
+  __shared__ float sh[32];
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    acc += v[i];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float a = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.f;
+    a = warp_sum(a);
+    if (threadIdx.x == 0) atomicAdd(out, a);
+  }
+}
+
+__global__ void k_axpy(float* dst, const float* src, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] += src[i];
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// host wrappers
+// ------------------------------------------------------------------------------------------
+int lrelu_ln_fwd(const LnFwdP& p, cudaStream_t st) {
+  if (p.B <= 0) return 0;
+  dim3 grid((unsigned)cdiv(p.B, 8), (unsigned)p.nets);
+  k_lrelu_ln_fwd<<<grid, 256, 0, st>>>(p);
+  NF_LAUNCHED();
+  return 0;
+}
+
+int ln_lrelu_bwd(const LnBwdP& p, cudaStream_t st) {
+  if (p.B <= 0) return 0;
+  dim3 grid((unsigned)cdiv(p.B, 8 * kBwdRowsPerWarp), (unsigned)p.nets);
+  k_ln_lrelu_bwd<<<grid, 256, p.N * sizeof(float), st>>>(p);
+  NF_LAUNCHED();
+  return 0;
+}
+
+template <bool INV>
+static int affine_launch(const float* in, const float* s, const float* t, const float* bs, const float* bt,
+                         const float* cdev, float chost, long long B, int D, float* out, float* logdet, float* s_out,
+                         cudaStream_t st) {
+  if (B <= 0) return 0;
+  if (D <= 64) {
+    const bool vec = (D % 8 == 0);
+    dim3 grid((unsigned)cdiv(B, 256));
+    if (vec) k_affine_rowthread<4, INV><<<grid, 256, 0, st>>>(in, s, t, bs, bt, cdev, chost, B, D, out, logdet, s_out);
+    else k_affine_rowthread<1, INV><<<grid, 256, 0, st>>>(in, s, t, bs, bt, cdev, chost, B, D, out, logdet, s_out);
+  } else {
+    dim3 grid((unsigned)cdiv(B, 8));
+    k_affine_rowwarp<INV><<<grid, 256, 0, st>>>(in, s, t, bs, bt, cdev, chost, B, D, out, logdet, s_out);
+  }
+  NF_LAUNCHED();
+  return 0;
+}
+
+int affine_fwd(const float* xp, const float* s, const float* t, const float* bias_s, const float* bias_t,
+               const float* cdev, float chost, long long B, int D, float* z, float* logdet, float* s_out,
+               cudaStream_t st) {
+  return affine_launch<false>(xp, s, t, bias_s, bias_t, cdev, chost, B, D, z, logdet, s_out, st);
+}
+int affine_inv(const float* z, const float* s, const float* t, const float* bias_s, const float* bias_t,
+               const float* cdev, float chost, long long B, int D, float* xp, float* logdet, cudaStream_t st) {
+  return affine_launch<true>(z, s, t, bias_s, bias_t, cdev, chost, B, D, xp, logdet, nullptr, st);
+}
+
+int affine_bwd(const float* dz, const float* z, const float* s_full, const float* dlogdet, long long B, int D,
+               float* dxp, float* ds, float* dt, float* g3s, float* g3t, cudaStream_t st) {
+  if (B <= 0) return 0;
+  const long long total = B * D;
+  long long blocks = cdiv(total, 256 * 4);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  k_affine_bwd<<<(unsigned)blocks, 256, 2 * (D / 2) * sizeof(float) + 16, st>>>(dz, z, s_full, dlogdet, B, D, dxp,
+                                                                              ds, dt, g3s, g3t);
+  NF_LAUNCHED();
+  return 0;
+}
+
+int plu_mask(const float* params, const NfParamLayout& pl, const Dims& m, float* packed, const PackedLayout& kl,
+             cudaStream_t st) {
+  dim3 grid((unsigned)std::min<int64_t>(cdiv((int64_t)m.D * m.D, 256), 64), (unsigned)m.n);
+  k_plu_mask<<<grid, 256, 0, st>>>(params, pl, m.D, packed, kl);
+  NF_LAUNCHED();
+  k_logdet_total<<<1, 32, 0, st>>>(packed, kl, m.n);
+  NF_LAUNCHED();
+  return 0;
+}
+
+int plu_tri_inverse(const float* packed, const PackedLayout& kl, const Dims& m, float* uinv, float* linv,
+                    cudaStream_t st) {
+  dim3 grid((unsigned)cdiv(m.D, 64), (unsigned)m.n);
+  k_tri_inverse<<<grid, 64, 0, st>>>(packed, kl, m.D, uinv, linv);
+  NF_LAUNCHED();
+  return 0;
+}
+
+int fold_ln_affine(const float* params, const NfParamLayout& pl, const Dims& m, float* packed, const PackedLayout& kl,
+                   cudaStream_t st) {
+  dim3 grid((unsigned)cdiv(m.C + m.dt, 8), 2, (unsigned)m.n);
+  k_fold<<<grid, 256, 0, st>>>(params, pl, m, packed, kl);
+  NF_LAUNCHED();
+  return 0;
+}
+
+int unfold_grads(const float* params, const NfParamLayout& pl, const Dims& m, float* dparams, cudaStream_t st) {
+  const int K = m.H1 > m.C ? m.H1 : m.C;
+  dim3 grid((unsigned)cdiv(K, 128), 2, (unsigned)m.n);
+  k_unfold<<<grid, 128, 0, st>>>(params, pl, m, dparams);
+  NF_LAUNCHED();
+  return 0;
+}
+
+int plu_grad_finish(const float* params, const NfParamLayout& pl, const Dims& m, const float* dLh, const float* dUh,
+                    const float* sum_dld, float* dparams, cudaStream_t st) {
+  dim3 grid((unsigned)std::min<int64_t>(cdiv((int64_t)m.D * m.D, 256), 64), (unsigned)m.n);
+  k_plu_grad_finish<<<grid, 256, 0, st>>>(params, pl, m.D, dLh, dUh, sum_dld, dparams);
+  NF_LAUNCHED();
+  return 0;
+}
+
+int sum_vector(const float* v, long long n, float* out, cudaStream_t st) {
+  NF_CUDA(cudaMemsetAsync(out, 0, sizeof(float), st));
+  if (n <= 0) return 0;
+  long long blocks = cdiv(n, 256 * 8);
+  if (blocks > 296) blocks = 296;
+  k_sum_vector<<<(unsigned)blocks, 256, 0, st>>>(v, n, out);
+  NF_LAUNCHED();
+  return 0;
+}
+
+int fill_zero(float* p, long long n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  NF_CUDA(cudaMemsetAsync(p, 0, n * sizeof(float), st));
+  return 0;
+}
+
+int axpy_rows(float* dst, const float* src, long long n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  long long blocks = cdiv(n, 256 * 4);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k_axpy<<<(unsigned)blocks, 256, 0, st>>>(dst, src, n);
+  NF_LAUNCHED();
+  return 0;
+}
+
+}  // namespace nf

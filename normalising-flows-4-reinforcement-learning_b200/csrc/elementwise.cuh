@@ -1,0 +1,58 @@
+// Row-wise and parameter-sized kernels of the flow (everything that is not a GEMM).
+#pragma once
+#include "common.cuh"
+
+namespace nf {
+
+// x_hat = LayerNorm_noaffine(LeakyReLU(u + bias)); optional rstd (B), sign mask (B, mw words).
+// Batched over `nets` with the given strides (floats / words).
+struct LnFwdP {
+  const float* u; long long u_net;
+  const float* bias; long long bias_net;
+  float* xh; long long xh_net;
+  float* xh_lo; long long xh_lo_net;   // optional low plane (tf32 split); may be null
+  float* rstd; long long rstd_net;     // may be null
+  uint32_t* mask; long long mask_net;  // may be null
+  int mw, N, nets;
+  long long B;
+  float eps;
+};
+int lrelu_ln_fwd(const LnFwdP& p, cudaStream_t st);
+
+// g (in: d x_hat, out: d u) ; colsum[n] += sum_rows du
+struct LnBwdP {
+  float* g; long long g_net;
+  const float* xh; long long xh_net;
+  const float* rstd; long long rstd_net;
+  const uint32_t* mask; long long mask_net;
+  float* colsum; long long colsum_net;   // N floats per net, atomically accumulated
+  int mw, N, nets;
+  long long B;
+};
+int ln_lrelu_bwd(const LnBwdP& p, cudaStream_t st);
+
+int affine_fwd(const float* xp, const float* s, const float* t, const float* bias_s, const float* bias_t,
+               const float* logdet_const_dev, float logdet_const_host, long long B, int D,
+               float* z, float* logdet, float* s_out, cudaStream_t st);
+int affine_inv(const float* z, const float* s, const float* t, const float* bias_s, const float* bias_t,
+               const float* logdet_const_dev, float logdet_const_host, long long B, int D,
+               float* xp, float* logdet, cudaStream_t st);
+// ds/dt are (B,dt) each; g3s/g3t (dt) receive column sums of ds/dt (atomic), may be null.
+int affine_bwd(const float* dz, const float* z, const float* s_full, const float* dlogdet, long long B, int D,
+               float* dxp, float* ds, float* dt, float* g3s, float* g3t, cudaStream_t st);
+
+// ---- parameter-sized kernels ---------------------------------------------------------------
+int plu_mask(const float* params, const NfParamLayout& pl, const Dims& m, float* packed,
+             const PackedLayout& kl, cudaStream_t st);
+int plu_tri_inverse(const float* packed, const PackedLayout& kl, const Dims& m, float* uinv, float* linv,
+                    cudaStream_t st);
+int fold_ln_affine(const float* params, const NfParamLayout& pl, const Dims& m, float* packed,
+                   const PackedLayout& kl, cudaStream_t st);
+int unfold_grads(const float* params, const NfParamLayout& pl, const Dims& m, float* dparams, cudaStream_t st);
+int plu_grad_finish(const float* params, const NfParamLayout& pl, const Dims& m, const float* dLh,
+                    const float* dUh, const float* sum_dld, float* dparams, cudaStream_t st);
+int sum_vector(const float* v, long long n, float* out, cudaStream_t st);  // out[0] = sum(v)
+int fill_zero(float* p, long long n, cudaStream_t st);
+int axpy_rows(float* dst, const float* src, long long n, cudaStream_t st);  // dst += src
+
+}  // namespace nf

@@ -1,0 +1,697 @@
+// Orchestration of the coupling-flow hot path and the C-ABI entry points (include/nf_b200.h).
+#include <stdarg.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "elementwise.cuh"
+#include "simt_gemm.cuh"
+
+namespace nf {
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static thread_local int64_t g_launches = 0;
+char* err_buf() { return g_err; }
+int64_t& launch_counter() { return g_launches; }
+int set_err(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int check_desc(const NfFlowDesc* d) {
+  NF_CHECK_ARG(d != nullptr, NF_E_BADARG, "desc is NULL");
+  NF_CHECK_ARG(d->D >= 2 && d->D <= 4096, NF_E_BADARG, "D=%d out of range [2,4096]", d->D);
+  NF_CHECK_ARG(d->C >= 1 && d->C <= 8192, NF_E_BADARG, "C=%d out of range", d->C);
+  NF_CHECK_ARG(d->H1 >= 1 && d->H1 <= 16384, NF_E_BADARG, "H1=%d out of range", d->H1);
+  NF_CHECK_ARG(d->R >= 0 && d->R <= 65536, NF_E_BADARG, "R=%d out of range", d->R);
+  NF_CHECK_ARG(d->n_blocks >= 1 && d->n_blocks <= 4096, NF_E_BADARG, "n_blocks=%d out of range", d->n_blocks);
+  NF_CHECK_ARG(d->ln_eps > 0.f, NF_E_BADARG, "ln_eps must be > 0");
+  NF_CHECK_ARG(d->precision >= 0 && d->precision <= 2, NF_E_BADARG, "unknown precision %d", d->precision);
+  return 0;
+}
+
+void param_layout(const Dims& m, NfParamLayout* out) {
+  const int64_t DD = (int64_t)m.D * m.D;
+  int64_t numel[NF_P_SLOTS];
+  numel[NF_P_S] = m.D; numel[NF_P_U] = DD; numel[NF_P_L] = DD; numel[NF_P_P] = DD; numel[NF_P_PINV] = DD;
+  for (int net = 0; net < 2; ++net) {
+    const int o = net * NF_P_NET_SLOTS;
+    numel[NF_P_W1 + o] = (int64_t)m.H1 * m.K1; numel[NF_P_B1 + o] = m.H1;
+    numel[NF_P_G1 + o] = m.H1; numel[NF_P_BE1 + o] = m.H1;
+    numel[NF_P_W2 + o] = (int64_t)m.C * m.H1; numel[NF_P_B2 + o] = m.C;
+    numel[NF_P_G2 + o] = m.C; numel[NF_P_BE2 + o] = m.C;
+    numel[NF_P_W3 + o] = (int64_t)m.dt * m.C; numel[NF_P_B3 + o] = m.dt;
+  }
+  int64_t off = 0;
+  for (int s = 0; s < NF_P_SLOTS; ++s) {
+    out->slot_off[s] = off;
+    out->slot_numel[s] = numel[s];
+    off += pad4(numel[s]);
+  }
+  out->block_stride = off;
+  out->net_stride = out->slot_off[NF_P_W1 + NF_P_NET_SLOTS] - out->slot_off[NF_P_W1];
+  out->total = off * m.n;
+}
+
+PackedLayout packed_layout(const Dims& m) {
+  PackedLayout k;
+  const int64_t DD = pad4((int64_t)m.D * m.D);
+  int64_t off = 0;
+  k.W = off; off += DD;
+  k.Winv = off; off += DD;
+  k.Lh = off; off += DD;
+  k.Uh = off; off += DD;
+  k.PL = off; off += DD;
+  k.net0 = off;
+  int64_t n = 0;
+  k.W2f = n; n += pad4((int64_t)m.C * m.H1);
+  k.b2f = n; n += pad4(m.C);
+  k.W3f = n; n += pad4((int64_t)m.dt * m.C);
+  k.b3f = n; n += pad4(m.dt);
+  k.net_stride = n;
+  off += 2 * n;
+  k.block_stride = off;
+  k.logdet_c = off * m.n;
+  k.logdet_total = k.logdet_c + pad4(m.n);
+  k.total = k.logdet_total + 4;
+  return k;
+}
+
+StashLayout stash_layout(const Dims& m, int64_t B) {
+  StashLayout s;
+  s.mw1 = (m.H1 + 31) / 32;
+  s.mw2 = (m.C + 31) / 32;
+  int64_t off = 0;
+  s.xs = off; off += pad4((int64_t)(m.n + 1) * B * m.D);
+  s.ss = off; off += pad4((int64_t)m.n * B * m.dt);
+  s.blocks = off;
+  int64_t n = 0;
+  s.xh1 = n; n += pad4(B * m.H1);
+  s.xh2 = n; n += pad4(B * m.C);
+  s.r1 = n; n += pad4(B);
+  s.r2 = n; n += pad4(B);
+  s.m1 = n; n += pad4(B * s.mw1);
+  s.m2 = n; n += pad4(B * s.mw2);
+  s.net_stride = n;
+  s.block_stride = 2 * n;
+  s.total = off + s.block_stride * m.n;
+  return s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// workspace carving
+// ---------------------------------------------------------------------------------------------
+struct Carver {
+  float* base;
+  int64_t off = 0;
+  explicit Carver(void* p) : base(reinterpret_cast<float*>(p)) {}
+  float* take(int64_t n) {
+    float* r = base ? base + off : nullptr;
+    off += pad32(n);
+    return r;
+  }
+};
+
+struct FwdWs { float *xp, *u, *o, *xh1, *xh2, *pp0, *pp1; int64_t total; };
+static FwdWs carve_fwd(const Dims& m, int64_t B, void* ws) {
+  Carver c(ws);
+  FwdWs w;
+  const int64_t Hm = std::max(m.H1, m.C);
+  w.xp = c.take(B * m.D);
+  w.u = c.take(2 * B * Hm);
+  w.o = c.take(2 * B * m.dt);
+  w.xh1 = c.take(2 * B * m.H1);
+  w.xh2 = c.take(2 * B * m.C);
+  w.pp0 = c.take(B * m.D);
+  w.pp1 = c.take(B * m.D);
+  w.total = c.off;
+  return w;
+}
+
+struct BwdWs { float *d0, *d1, *dxp, *dout, *gA, *gB, *dWs, *T1, *dLh, *dUh, *sumdld; int64_t total; };
+static BwdWs carve_bwd(const Dims& m, int64_t B, void* ws) {
+  Carver c(ws);
+  BwdWs w;
+  const int64_t Hm = std::max(m.H1, m.C);
+  const int64_t DD = (int64_t)m.D * m.D;
+  w.d0 = c.take(B * m.D);
+  w.d1 = c.take(B * m.D);
+  w.dxp = c.take(B * m.D);
+  w.dout = c.take(2 * B * m.dt);
+  w.gA = c.take(2 * B * Hm);
+  w.gB = c.take(2 * B * Hm);
+  w.dWs = c.take(m.n * DD);
+  w.T1 = c.take(m.n * DD);
+  w.dLh = c.take(m.n * DD);
+  w.dUh = c.take(m.n * DD);
+  w.sumdld = c.take(4);
+  w.total = c.off;
+  return w;
+}
+
+struct PrepWs { float *uinv, *linv, *T; int64_t total; };
+static PrepWs carve_prep(const Dims& m, void* ws) {
+  Carver c(ws);
+  PrepWs w;
+  const int64_t DD = (int64_t)m.D * m.D;
+  w.uinv = c.take(m.n * DD);
+  w.linv = c.take(m.n * DD);
+  w.T = c.take(m.n * DD);
+  w.total = c.off;
+  return w;
+}
+
+static int check_ptr(const void* p, const char* name, bool required) {
+  if (!p) {
+    NF_CHECK_ARG(!required, NF_E_BADARG, "%s is NULL", name);
+    return 0;
+  }
+  NF_CHECK_ARG((reinterpret_cast<uintptr_t>(p) & 15u) == 0, NF_E_ALIGN, "%s is not 16-byte aligned", name);
+  return 0;
+}
+#define NF_TRY(expr)            \
+  do {                          \
+    int _r = (expr);            \
+    if (_r != 0) return _r;     \
+  } while (0)
+
+// The two conditioner MLPs (net 0 = t, net 1 = s) up to the last Linear's raw output o (2,B,dt):
+//   u1 = [x_cond | y] W1^T -> LeakyReLU -> LN -> x_hat1 -> W2f -> LeakyReLU -> LN -> x_hat2 -> W3f
+// (torch_fcnf.py:74-78, :85-89, :99-100).  `xc` holds x_cond in its first dc columns (row stride D).
+static int conditioners(const Dims& m, const NfParamLayout& pl, const PackedLayout& kl, const float* pb,
+                        const float* kb, const float* xc, const float* y, int64_t B, const FwdWs& w,
+                        float* xh1, int64_t xh1_net, float* xh2, int64_t xh2_net, float* r1, float* r2,
+                        int64_t r_net, uint32_t* m1, uint32_t* m2, int64_t m_net, int mw1, int mw2,
+                        cudaStream_t st) {
+  const int64_t Hm = std::max(m.H1, m.C);
+  {  // u1
+    GemmP g;
+    g.A0 = xc; g.lda0 = m.D; g.K0 = m.dc;
+    g.A1 = y; g.lda1 = m.R; g.K1 = m.R;
+    g.B0 = pb + pl.slot_off[NF_P_W1]; g.ldb0 = m.K1; g.sB0 = pl.net_stride;
+    g.B1 = g.B0 + m.dc; g.ldb1 = m.K1; g.sB1 = pl.net_stride;
+    g.transB = 1;
+    g.C = w.u; g.ldc = m.H1; g.sC = B * Hm;
+    g.M = (int)B; g.N = m.H1; g.batch = 2;
+    NF_TRY(simt_gemm(g, st));
+  }
+  {
+    LnFwdP p{};
+    p.u = w.u; p.u_net = B * Hm;
+    p.bias = pb + pl.slot_off[NF_P_B1]; p.bias_net = pl.net_stride;
+    p.xh = xh1; p.xh_net = xh1_net;
+    p.rstd = r1; p.rstd_net = r_net;
+    p.mask = m1; p.mask_net = m_net; p.mw = mw1;
+    p.N = m.H1; p.nets = 2; p.B = B; p.eps = m.eps;
+    NF_TRY(lrelu_ln_fwd(p, st));
+  }
+  {  // u2
+    GemmP g;
+    g.A0 = xh1; g.lda0 = m.H1; g.K0 = m.H1; g.sA0 = xh1_net;
+    g.B0 = kb + kl.net0 + kl.W2f; g.ldb0 = m.H1; g.sB0 = kl.net_stride; g.transB = 1;
+    g.C = w.u; g.ldc = m.C; g.sC = B * Hm;
+    g.M = (int)B; g.N = m.C; g.batch = 2;
+    NF_TRY(simt_gemm(g, st));
+  }
+  {
+    LnFwdP p{};
+    p.u = w.u; p.u_net = B * Hm;
+    p.bias = kb + kl.net0 + kl.b2f; p.bias_net = kl.net_stride;
+    p.xh = xh2; p.xh_net = xh2_net;
+    p.rstd = r2; p.rstd_net = r_net;
+    p.mask = m2; p.mask_net = m_net; p.mw = mw2;
+    p.N = m.C; p.nets = 2; p.B = B; p.eps = m.eps;
+    NF_TRY(lrelu_ln_fwd(p, st));
+  }
+  {  // o = x_hat2 W3f^T
+    GemmP g;
+    g.A0 = xh2; g.lda0 = m.C; g.K0 = m.C; g.sA0 = xh2_net;
+    g.B0 = kb + kl.net0 + kl.W3f; g.ldb0 = m.C; g.sB0 = kl.net_stride; g.transB = 1;
+    g.C = w.o; g.ldc = m.dt; g.sC = B * m.dt;
+    g.M = (int)B; g.N = m.dt; g.batch = 2;
+    NF_TRY(simt_gemm(g, st));
+  }
+  return 0;
+}
+
+}  // namespace nf
+
+using namespace nf;
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+int nf_abi_version(void) { return NF_ABI_VERSION; }
+const char* nf_last_error(void) { return err_buf(); }
+int64_t nf_launch_count(int reset) {
+  int64_t v = launch_counter();
+  if (reset) launch_counter() = 0;
+  return v;
+}
+
+int nf_param_layout(const NfFlowDesc* desc, NfParamLayout* out) {
+  NF_TRY(check_desc(desc));
+  NF_CHECK_ARG(out != nullptr, NF_E_BADARG, "out is NULL");
+  param_layout(dims_of(desc), out);
+  return 0;
+}
+
+int64_t nf_flow_packed_bytes(const NfFlowDesc* desc) {
+  if (check_desc(desc)) return -1;
+  return packed_layout(dims_of(desc)).total * (int64_t)sizeof(float);
+}
+
+int64_t nf_flow_stash_bytes(const NfFlowDesc* desc, int64_t B) {
+  if (check_desc(desc) || B < 0) return -1;
+  return stash_layout(dims_of(desc), B).total * (int64_t)sizeof(float);
+}
+
+int64_t nf_flow_workspace_bytes(const NfFlowDesc* desc, int64_t B) {
+  if (check_desc(desc) || B < 0) return -1;
+  const Dims m = dims_of(desc);
+  int64_t t = carve_fwd(m, B, nullptr).total;
+  t = std::max(t, carve_bwd(m, B, nullptr).total);
+  t = std::max(t, carve_prep(m, nullptr).total);
+  return (t + 64) * (int64_t)sizeof(float);
+}
+
+int nf_flow_prepare(const NfFlowDesc* desc, const float* params, void* packed_v, int what, void* workspace,
+                    int64_t ws_bytes, void* stream) {
+  NF_TRY(check_desc(desc));
+  NF_TRY(check_ptr(params, "params", true));
+  NF_TRY(check_ptr(packed_v, "packed", true));
+  const Dims m = dims_of(desc);
+  NfParamLayout pl;
+  param_layout(m, &pl);
+  const PackedLayout kl = packed_layout(m);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  float* packed = reinterpret_cast<float*>(packed_v);
+  const int64_t DD = (int64_t)m.D * m.D;
+
+  NF_TRY(plu_mask(params, pl, m, packed, kl, st));
+  {  // PL = P @ Lh
+    GemmP g;
+    g.A0 = params + pl.slot_off[NF_P_P]; g.lda0 = m.D; g.K0 = m.D; g.sA0 = pl.block_stride;
+    g.B0 = packed + kl.Lh; g.ldb0 = m.D; g.sB0 = kl.block_stride;
+    g.C = packed + kl.PL; g.ldc = m.D; g.sC = kl.block_stride;
+    g.M = m.D; g.N = m.D; g.batch = m.n;
+    NF_TRY(simt_gemm(g, st));
+    // W = PL @ Uh
+    g.A0 = packed + kl.PL; g.sA0 = kl.block_stride;
+    g.B0 = packed + kl.Uh;
+    g.C = packed + kl.W;
+    NF_TRY(simt_gemm(g, st));
+  }
+  NF_TRY(fold_ln_affine(params, pl, m, packed, kl, st));
+  if (what & NF_PREP_INV) {
+    NF_TRY(check_ptr(workspace, "workspace", true));
+    const PrepWs w = carve_prep(m, workspace);
+    NF_CHECK_ARG(ws_bytes >= w.total * (int64_t)sizeof(float), NF_E_WORKSPACE, "workspace too small: %lld < %lld",
+                 (long long)ws_bytes, (long long)(w.total * sizeof(float)));
+    NF_TRY(plu_tri_inverse(packed, kl, m, w.uinv, w.linv, st));
+    GemmP g;  // T = Uinv @ Linv ; Winv = T @ P_inv   (torch_fcnf.py:54)
+    g.A0 = w.uinv; g.lda0 = m.D; g.K0 = m.D; g.sA0 = DD;
+    g.B0 = w.linv; g.ldb0 = m.D; g.sB0 = DD;
+    g.C = w.T; g.ldc = m.D; g.sC = DD;
+    g.M = m.D; g.N = m.D; g.batch = m.n;
+    NF_TRY(simt_gemm(g, st));
+    g.A0 = w.T;
+    g.B0 = params + pl.slot_off[NF_P_PINV]; g.sB0 = pl.block_stride;
+    g.C = packed + kl.Winv; g.sC = kl.block_stride;
+    NF_TRY(simt_gemm(g, st));
+  }
+  return 0;
+}
+
+int nf_flow_forward(const NfFlowDesc* desc, const float* params, const void* packed_v, const float* x,
+                    const float* y, int64_t B, float* z, float* logdet, float* outputs, void* stash_v,
+                    void* workspace, int64_t ws_bytes, void* stream) {
+  NF_TRY(check_desc(desc));
+  NF_CHECK_ARG(B >= 0 && B < (int64_t(1) << 30), NF_E_BADARG, "B=%lld out of range", (long long)B);
+  NF_TRY(check_ptr(params, "params", true));
+  NF_TRY(check_ptr(packed_v, "packed", true));
+  if (B == 0) return 0;
+  NF_TRY(check_ptr(x, "x", true));
+  NF_TRY(check_ptr(y, "y", desc->R > 0));
+  NF_TRY(check_ptr(z, "z", true));
+  NF_TRY(check_ptr(logdet, "logdet", true));
+  NF_TRY(check_ptr(outputs, "outputs", false));
+  NF_TRY(check_ptr(stash_v, "stash", false));
+  NF_TRY(check_ptr(workspace, "workspace", true));
+  const Dims m = dims_of(desc);
+  NfParamLayout pl;
+  param_layout(m, &pl);
+  const PackedLayout kl = packed_layout(m);
+  const FwdWs w = carve_fwd(m, B, workspace);
+  NF_CHECK_ARG(ws_bytes >= w.total * (int64_t)sizeof(float), NF_E_WORKSPACE, "workspace too small: %lld < %lld",
+               (long long)ws_bytes, (long long)(w.total * sizeof(float)));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const float* packed = reinterpret_cast<const float*>(packed_v);
+  float* stash = reinterpret_cast<float*>(stash_v);
+  const StashLayout sl = stash_layout(m, B);
+  const int64_t BD = B * m.D;
+
+  NF_CUDA(cudaMemsetAsync(logdet, 0, B * sizeof(float), st));
+  const float* cur = x;
+  if (stash) {
+    NF_CUDA(cudaMemcpyAsync(stash + sl.xs, x, BD * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    cur = stash + sl.xs;
+  }
+  for (int i = 0; i < m.n; ++i) {
+    const float* pb = params + (int64_t)i * pl.block_stride;
+    const float* kb = packed + (int64_t)i * kl.block_stride;
+    {  // xp = cur @ W   (torch_fcnf.py:40)
+      GemmP g;
+      g.A0 = cur; g.lda0 = m.D; g.K0 = m.D;
+      g.B0 = kb + kl.W; g.ldb0 = m.D;
+      g.C = w.xp; g.ldc = m.D; g.M = (int)B; g.N = m.D;
+      NF_TRY(simt_gemm(g, st));
+    }
+    float *xh1 = w.xh1, *xh2 = w.xh2, *r1 = nullptr, *r2 = nullptr;
+    uint32_t *m1 = nullptr, *m2 = nullptr;
+    int64_t xh1_net = B * m.H1, xh2_net = B * m.C, r_net = 0, m_net = 0;
+    if (stash) {
+      float* sb = stash + sl.blocks + (int64_t)i * sl.block_stride;
+      xh1 = sb + sl.xh1; xh2 = sb + sl.xh2; r1 = sb + sl.r1; r2 = sb + sl.r2;
+      m1 = reinterpret_cast<uint32_t*>(sb + sl.m1); m2 = reinterpret_cast<uint32_t*>(sb + sl.m2);
+      xh1_net = xh2_net = r_net = m_net = sl.net_stride;
+    }
+    NF_TRY(conditioners(m, pl, kl, pb, kb, w.xp, y, B, w, xh1, xh1_net, xh2, xh2_net, r1, r2, r_net, m1, m2, m_net,
+                        sl.mw1, sl.mw2, st));
+    float* next;
+    if (stash) next = stash + sl.xs + (int64_t)(i + 1) * BD;
+    else if (outputs) next = outputs + (int64_t)i * BD;
+    else if (i == m.n - 1) next = z;
+    else next = (i & 1) ? w.pp1 : w.pp0;
+    NF_TRY(affine_fwd(w.xp, w.o + B * m.dt, w.o, kb + kl.net0 + kl.net_stride + kl.b3f, kb + kl.net0 + kl.b3f,
+                      packed + kl.logdet_c + i, 0.f, B, m.D, next, logdet,
+                      stash ? stash + sl.ss + (int64_t)i * B * m.dt : nullptr, st));
+    cur = next;
+  }
+  if (cur != z) NF_CUDA(cudaMemcpyAsync(z, cur, BD * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (stash && outputs)
+    NF_CUDA(cudaMemcpyAsync(outputs, stash + sl.xs + BD, (int64_t)m.n * BD * sizeof(float), cudaMemcpyDeviceToDevice,
+                            st));
+  return 0;
+}
+
+int nf_flow_inverse(const NfFlowDesc* desc, const float* params, const void* packed_v, const float* z,
+                    const float* y, int64_t B, float* x, float* logdet, float* seq, void* workspace,
+                    int64_t ws_bytes, void* stream) {
+  NF_TRY(check_desc(desc));
+  NF_CHECK_ARG(B >= 0 && B < (int64_t(1) << 30), NF_E_BADARG, "B=%lld out of range", (long long)B);
+  NF_TRY(check_ptr(params, "params", true));
+  NF_TRY(check_ptr(packed_v, "packed", true));
+  if (B == 0) return 0;
+  NF_TRY(check_ptr(z, "z", true));
+  NF_TRY(check_ptr(y, "y", desc->R > 0));
+  NF_TRY(check_ptr(x, "x", true));
+  NF_TRY(check_ptr(logdet, "logdet", false));
+  NF_TRY(check_ptr(seq, "seq", false));
+  NF_TRY(check_ptr(workspace, "workspace", true));
+  const Dims m = dims_of(desc);
+  NfParamLayout pl;
+  param_layout(m, &pl);
+  const PackedLayout kl = packed_layout(m);
+  const FwdWs w = carve_fwd(m, B, workspace);
+  NF_CHECK_ARG(ws_bytes >= w.total * (int64_t)sizeof(float), NF_E_WORKSPACE, "workspace too small: %lld < %lld",
+               (long long)ws_bytes, (long long)(w.total * sizeof(float)));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const float* packed = reinterpret_cast<const float*>(packed_v);
+  const int64_t BD = B * m.D;
+
+  if (logdet) NF_CUDA(cudaMemsetAsync(logdet, 0, B * sizeof(float), st));
+  if (seq) NF_CUDA(cudaMemcpyAsync(seq, z, BD * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  const float* cur = z;
+  int step = 0;
+  for (int i = m.n - 1; i >= 0; --i, ++step) {
+    const float* pb = params + (int64_t)i * pl.block_stride;
+    const float* kb = packed + (int64_t)i * kl.block_stride;
+    NF_TRY(conditioners(m, pl, kl, pb, kb, cur, y, B, w, w.xh1, B * m.H1, w.xh2, B * m.C, nullptr, nullptr, 0,
+                        nullptr, nullptr, 0, 0, 0, st));
+    // affine first (torch_fcnf.py:112-113) ...
+    NF_TRY(affine_inv(cur, w.o + B * m.dt, w.o, kb + kl.net0 + kl.net_stride + kl.b3f, kb + kl.net0 + kl.b3f,
+                      packed + kl.logdet_c + i, 0.f, B, m.D, w.xp, logdet, st));
+    // ... then x = xp @ W^-1 (torch_fcnf.py:115 -> :55)
+    float* next;
+    if (seq) next = seq + (int64_t)(step + 1) * BD;
+    else if (i == 0) next = x;
+    else next = (step & 1) ? w.pp1 : w.pp0;
+    GemmP g;
+    g.A0 = w.xp; g.lda0 = m.D; g.K0 = m.D;
+    g.B0 = kb + kl.Winv; g.ldb0 = m.D;
+    g.C = next; g.ldc = m.D; g.M = (int)B; g.N = m.D;
+    NF_TRY(simt_gemm(g, st));
+    cur = next;
+  }
+  if (cur != x) NF_CUDA(cudaMemcpyAsync(x, cur, BD * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+int nf_flow_backward(const NfFlowDesc* desc, const float* params, const void* packed_v, const void* stash_v,
+                     const float* y, int64_t B, const float* dz, const float* dlogdet, float* dx, float* dy,
+                     float* dparams, void* workspace, int64_t ws_bytes, void* stream) {
+  NF_TRY(check_desc(desc));
+  NF_CHECK_ARG(B >= 0 && B < (int64_t(1) << 30), NF_E_BADARG, "B=%lld out of range", (long long)B);
+  NF_TRY(check_ptr(params, "params", true));
+  NF_TRY(check_ptr(packed_v, "packed", true));
+  NF_TRY(check_ptr(dparams, "dparams", false));
+  const Dims m = dims_of(desc);
+  NfParamLayout pl;
+  param_layout(m, &pl);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dparams) NF_TRY(fill_zero(dparams, pl.total, st));
+  if (B == 0) return 0;
+  NF_TRY(check_ptr(stash_v, "stash", true));
+  NF_TRY(check_ptr(y, "y", desc->R > 0));
+  NF_TRY(check_ptr(dz, "dz", false));
+  NF_TRY(check_ptr(dlogdet, "dlogdet", false));
+  NF_TRY(check_ptr(dx, "dx", false));
+  NF_TRY(check_ptr(dy, "dy", false));
+  NF_TRY(check_ptr(workspace, "workspace", true));
+  const PackedLayout kl = packed_layout(m);
+  const StashLayout sl = stash_layout(m, B);
+  const BwdWs w = carve_bwd(m, B, workspace);
+  NF_CHECK_ARG(ws_bytes >= w.total * (int64_t)sizeof(float), NF_E_WORKSPACE, "workspace too small: %lld < %lld",
+               (long long)ws_bytes, (long long)(w.total * sizeof(float)));
+  const float* packed = reinterpret_cast<const float*>(packed_v);
+  const float* stash = reinterpret_cast<const float*>(stash_v);
+  const int64_t BD = B * m.D, Hm = std::max(m.H1, m.C), DD = (int64_t)m.D * m.D;
+
+  if (dy) NF_TRY(fill_zero(dy, B * m.R, st));
+  if (dparams) {
+    NF_TRY(fill_zero(w.dWs, m.n * DD, st));
+    if (dlogdet) NF_TRY(sum_vector(dlogdet, B, w.sumdld, st));
+    else NF_TRY(fill_zero(w.sumdld, 4, st));
+  }
+  const float* gcur = dz;  // NULL means zero (handled inside affine_bwd)
+  int pp = 0;
+  for (int i = m.n - 1; i >= 0; --i) {
+    const float* pb = params + (int64_t)i * pl.block_stride;
+    const float* kb = packed + (int64_t)i * kl.block_stride;
+    float* dn = dparams ? dparams + (int64_t)i * pl.block_stride : nullptr;
+    const float* xin = stash + sl.xs + (int64_t)i * BD;
+    const float* zi = stash + sl.xs + (int64_t)(i + 1) * BD;
+    const float* si = stash + sl.ss + (int64_t)i * B * m.dt;
+    const float* sb = stash + sl.blocks + (int64_t)i * sl.block_stride;
+    const uint32_t* m1 = reinterpret_cast<const uint32_t*>(sb + sl.m1);
+    const uint32_t* m2 = reinterpret_cast<const uint32_t*>(sb + sl.m2);
+
+    // a. affine coupling backward: dout[0] = dt, dout[1] = ds
+    NF_TRY(affine_bwd(gcur, zi, si, dlogdet, B, m.D, w.dxp, w.dout + B * m.dt, w.dout,
+                      dn ? dn + pl.net_stride + pl.slot_off[NF_P_B3] : nullptr,
+                      dn ? dn + pl.slot_off[NF_P_B3] : nullptr, st));
+    if (dn) {  // b. G3 = dout^T x_hat2  -> slot W3 (unfolded at the end)
+      GemmP g;
+      g.transA = 1; g.A0 = w.dout; g.lda0 = m.dt; g.sA0 = B * m.dt; g.K0 = (int)B;
+      g.B0 = sb + sl.xh2; g.ldb0 = m.C; g.sB0 = sl.net_stride;
+      g.C = dn + pl.slot_off[NF_P_W3]; g.ldc = m.C; g.sC = pl.net_stride;
+      g.M = m.dt; g.N = m.C; g.batch = 2; g.splitk = pick_splitk(g.M, g.N, B, 2);
+      NF_TRY(simt_gemm(g, st));
+    }
+    {  // c. d x_hat2 = dout W3f
+      GemmP g;
+      g.A0 = w.dout; g.lda0 = m.dt; g.sA0 = B * m.dt; g.K0 = m.dt;
+      g.B0 = kb + kl.net0 + kl.W3f; g.ldb0 = m.C; g.sB0 = kl.net_stride;
+      g.C = w.gA; g.ldc = m.C; g.sC = B * Hm;
+      g.M = (int)B; g.N = m.C; g.batch = 2;
+      NF_TRY(simt_gemm(g, st));
+    }
+    {  // d. through LayerNorm + LeakyReLU (layer 2); column sums -> slot b2
+      LnBwdP p{};
+      p.g = w.gA; p.g_net = B * Hm;
+      p.xh = sb + sl.xh2; p.xh_net = sl.net_stride;
+      p.rstd = sb + sl.r2; p.rstd_net = sl.net_stride;
+      p.mask = m2; p.mask_net = sl.net_stride; p.mw = sl.mw2;
+      p.colsum = dn ? dn + pl.slot_off[NF_P_B2] : nullptr; p.colsum_net = pl.net_stride;
+      p.N = m.C; p.nets = 2; p.B = B;
+      NF_TRY(ln_lrelu_bwd(p, st));
+    }
+    if (dn) {  // e. G2 = du2^T x_hat1 -> slot W2
+      GemmP g;
+      g.transA = 1; g.A0 = w.gA; g.lda0 = m.C; g.sA0 = B * Hm; g.K0 = (int)B;
+      g.B0 = sb + sl.xh1; g.ldb0 = m.H1; g.sB0 = sl.net_stride;
+      g.C = dn + pl.slot_off[NF_P_W2]; g.ldc = m.H1; g.sC = pl.net_stride;
+      g.M = m.C; g.N = m.H1; g.batch = 2; g.splitk = pick_splitk(g.M, g.N, B, 2);
+      NF_TRY(simt_gemm(g, st));
+    }
+    {  // f. d x_hat1 = du2 W2f
+      GemmP g;
+      g.A0 = w.gA; g.lda0 = m.C; g.sA0 = B * Hm; g.K0 = m.C;
+      g.B0 = kb + kl.net0 + kl.W2f; g.ldb0 = m.H1; g.sB0 = kl.net_stride;
+      g.C = w.gB; g.ldc = m.H1; g.sC = B * Hm;
+      g.M = (int)B; g.N = m.H1; g.batch = 2;
+      NF_TRY(simt_gemm(g, st));
+    }
+    {  // g. through LayerNorm + LeakyReLU (layer 1); column sums -> slot b1
+      LnBwdP p{};
+      p.g = w.gB; p.g_net = B * Hm;
+      p.xh = sb + sl.xh1; p.xh_net = sl.net_stride;
+      p.rstd = sb + sl.r1; p.rstd_net = sl.net_stride;
+      p.mask = m1; p.mask_net = sl.net_stride; p.mw = sl.mw1;
+      p.colsum = dn ? dn + pl.slot_off[NF_P_B1] : nullptr; p.colsum_net = pl.net_stride;
+      p.N = m.H1; p.nets = 2; p.B = B;
+      NF_TRY(ln_lrelu_bwd(p, st));
+    }
+    if (dn) {  // h. dW1 = du1^T [x_cond | y]
+      GemmP g;
+      g.transA = 1; g.A0 = w.gB; g.lda0 = m.H1; g.sA0 = B * Hm; g.K0 = (int)B;
+      g.B0 = zi; g.ldb0 = m.D; g.sB0 = 0;
+      g.C = dn + pl.slot_off[NF_P_W1]; g.ldc = m.K1; g.sC = pl.net_stride;
+      g.M = m.H1; g.N = m.dc; g.batch = 2; g.splitk = pick_splitk(g.M, g.N, B, 2);
+      NF_TRY(simt_gemm(g, st));
+      if (m.R > 0) {
+        g.B0 = y; g.ldb0 = m.R;
+        g.C = dn + pl.slot_off[NF_P_W1] + m.dc; g.N = m.R;
+        g.splitk = pick_splitk(g.M, g.N, B, 2);
+        NF_TRY(simt_gemm(g, st));
+      }
+    }
+    {  // i. d h0 = du1_t W1_t + du1_s W1_s : first dc columns -> dxp, the rest -> dy
+      GemmP g;
+      g.A0 = w.gB; g.lda0 = m.H1; g.K0 = m.H1;
+      g.A1 = w.gB + B * Hm; g.lda1 = m.H1; g.K1 = m.H1;
+      g.B0 = pb + pl.slot_off[NF_P_W1]; g.ldb0 = m.K1;
+      g.B1 = g.B0 + pl.net_stride; g.ldb1 = m.K1;
+      g.C = w.dxp; g.ldc = m.D; g.M = (int)B; g.N = m.dc; g.accumulate = 1;
+      NF_TRY(simt_gemm(g, st));
+      if (dy && m.R > 0) {
+        g.B0 += m.dc; g.B1 += m.dc;
+        g.C = dy; g.ldc = m.R; g.N = m.R;
+        NF_TRY(simt_gemm(g, st));
+      }
+    }
+    if (dn) {  // j. dW = x_in^T dxp
+      GemmP g;
+      g.transA = 1; g.A0 = xin; g.lda0 = m.D; g.K0 = (int)B;
+      g.B0 = w.dxp; g.ldb0 = m.D;
+      g.C = w.dWs + (int64_t)i * DD; g.ldc = m.D; g.M = m.D; g.N = m.D;
+      g.splitk = pick_splitk(g.M, g.N, B, 1);
+      NF_TRY(simt_gemm(g, st));
+    }
+    if (i > 0 || dx) {  // k. d x_in = dxp W^T
+      GemmP g;
+      g.A0 = w.dxp; g.lda0 = m.D; g.K0 = m.D;
+      g.B0 = kb + kl.W; g.ldb0 = m.D; g.transB = 1;
+      float* dst = (i == 0) ? dx : (pp ? w.d1 : w.d0);
+      g.C = dst; g.ldc = m.D; g.M = (int)B; g.N = m.D;
+      NF_TRY(simt_gemm(g, st));
+      gcur = dst;
+      pp ^= 1;
+    }
+  }
+  if (dparams) {
+    GemmP g;  // T1 = P^T dW
+    g.transA = 1; g.A0 = params + pl.slot_off[NF_P_P]; g.lda0 = m.D; g.sA0 = pl.block_stride; g.K0 = m.D;
+    g.B0 = w.dWs; g.ldb0 = m.D; g.sB0 = DD;
+    g.C = w.T1; g.ldc = m.D; g.sC = DD; g.M = m.D; g.N = m.D; g.batch = m.n;
+    NF_TRY(simt_gemm(g, st));
+    GemmP h;  // dLh = T1 Uh^T
+    h.A0 = w.T1; h.lda0 = m.D; h.sA0 = DD; h.K0 = m.D;
+    h.B0 = packed + kl.Uh; h.ldb0 = m.D; h.sB0 = kl.block_stride; h.transB = 1;
+    h.C = w.dLh; h.ldc = m.D; h.sC = DD; h.M = m.D; h.N = m.D; h.batch = m.n;
+    NF_TRY(simt_gemm(h, st));
+    GemmP u;  // dUh = (P Lh)^T dW
+    u.transA = 1; u.A0 = packed + kl.PL; u.lda0 = m.D; u.sA0 = kl.block_stride; u.K0 = m.D;
+    u.B0 = w.dWs; u.ldb0 = m.D; u.sB0 = DD;
+    u.C = w.dUh; u.ldc = m.D; u.sC = DD; u.M = m.D; u.N = m.D; u.batch = m.n;
+    NF_TRY(simt_gemm(u, st));
+    NF_TRY(plu_grad_finish(params, pl, m, w.dLh, w.dUh, w.sumdld, dparams, st));
+    NF_TRY(unfold_grads(params, pl, m, dparams, st));
+  }
+  return 0;
+}
+
+int nf_affine_logdet_fwd(const float* xp, const float* s, const float* t, const float* bias_s, const float* bias_t,
+                         float logdet_const, int64_t B, int32_t D, float* z, float* logdet, float* s_out,
+                         void* stream) {
+  NF_CHECK_ARG(D >= 2 && B >= 0, NF_E_BADARG, "bad shape B=%lld D=%d", (long long)B, D);
+  NF_TRY(check_ptr(xp, "xp", true)); NF_TRY(check_ptr(s, "s", true)); NF_TRY(check_ptr(t, "t", true));
+  NF_TRY(check_ptr(z, "z", true)); NF_TRY(check_ptr(logdet, "logdet", false)); NF_TRY(check_ptr(s_out, "s_out", false));
+  return affine_fwd(xp, s, t, bias_s, bias_t, nullptr, logdet_const, B, D, z, logdet, s_out,
+                    reinterpret_cast<cudaStream_t>(stream));
+}
+
+int nf_affine_logdet_inv(const float* z, const float* s, const float* t, const float* bias_s, const float* bias_t,
+                         float logdet_const, int64_t B, int32_t D, float* xp, float* logdet, void* stream) {
+  NF_CHECK_ARG(D >= 2 && B >= 0, NF_E_BADARG, "bad shape B=%lld D=%d", (long long)B, D);
+  NF_TRY(check_ptr(z, "z", true)); NF_TRY(check_ptr(s, "s", true)); NF_TRY(check_ptr(t, "t", true));
+  NF_TRY(check_ptr(xp, "xp", true)); NF_TRY(check_ptr(logdet, "logdet", false));
+  return affine_inv(z, s, t, bias_s, bias_t, nullptr, logdet_const, B, D, xp, logdet,
+                    reinterpret_cast<cudaStream_t>(stream));
+}
+
+int nf_affine_logdet_bwd(const float* dz, const float* z, const float* s_full, const float* dlogdet, int64_t B,
+                         int32_t D, float* dxp, float* ds, float* dt, void* stream) {
+  NF_CHECK_ARG(D >= 2 && B >= 0, NF_E_BADARG, "bad shape B=%lld D=%d", (long long)B, D);
+  NF_TRY(check_ptr(z, "z", true)); NF_TRY(check_ptr(s_full, "s_full", true));
+  NF_TRY(check_ptr(dxp, "dxp", true)); NF_TRY(check_ptr(ds, "ds", true)); NF_TRY(check_ptr(dt, "dt", true));
+  return affine_bwd(dz, z, s_full, dlogdet, B, D, dxp, ds, dt, nullptr, nullptr,
+                    reinterpret_cast<cudaStream_t>(stream));
+}
+
+int nf_plu_build(const float* s, const float* U, const float* L, const float* P, const float* P_inv, int32_t D,
+                 float* W, float* W_inv, float* logdet, void* workspace, int64_t ws_bytes, void* stream) {
+  // One-block flow with no conditioner: reuse the packed-table machinery on a temporary arena
+  // carved from the workspace.
+  NF_CHECK_ARG(D >= 2 && D <= 4096, NF_E_BADARG, "D=%d out of range", D);
+  NF_TRY(check_ptr(workspace, "workspace", true));
+  NfFlowDesc d{};
+  d.D = D; d.C = 1; d.H1 = 1; d.R = 0; d.n_blocks = 1; d.ln_eps = 1e-5f; d.precision = 0;
+  const Dims m = dims_of(&d);
+  NfParamLayout pl;
+  param_layout(m, &pl);
+  const PackedLayout kl = packed_layout(m);
+  const PrepWs pw = carve_prep(m, nullptr);
+  const int64_t need = (pad32(pl.total) + pad32(kl.total) + pw.total) * (int64_t)sizeof(float);
+  NF_CHECK_ARG(ws_bytes >= need, NF_E_WORKSPACE, "workspace too small: %lld < %lld", (long long)ws_bytes,
+               (long long)need);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  float* arena = reinterpret_cast<float*>(workspace);
+  float* packed = arena + pad32(pl.total);
+  float* rest = packed + pad32(kl.total);
+  const int64_t DD = (int64_t)D * D;
+  NF_CUDA(cudaMemsetAsync(arena, 0, pl.total * sizeof(float), st));
+  NF_CUDA(cudaMemcpyAsync(arena + pl.slot_off[NF_P_S], s, D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  NF_CUDA(cudaMemcpyAsync(arena + pl.slot_off[NF_P_U], U, DD * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  NF_CUDA(cudaMemcpyAsync(arena + pl.slot_off[NF_P_L], L, DD * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  NF_CUDA(cudaMemcpyAsync(arena + pl.slot_off[NF_P_P], P, DD * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (P_inv)
+    NF_CUDA(cudaMemcpyAsync(arena + pl.slot_off[NF_P_PINV], P_inv, DD * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  NF_TRY(nf_flow_prepare(&d, arena, packed, NF_PREP_FWD | (W_inv ? NF_PREP_INV : 0), rest,
+                         pw.total * (int64_t)sizeof(float), stream));
+  if (W) NF_CUDA(cudaMemcpyAsync(W, packed + kl.W, DD * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (W_inv) NF_CUDA(cudaMemcpyAsync(W_inv, packed + kl.Winv, DD * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (logdet) NF_CUDA(cudaMemcpyAsync(logdet, packed + kl.logdet_c, sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+}  // extern "C"

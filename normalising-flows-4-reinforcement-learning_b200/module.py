@@ -1,0 +1,350 @@
+"""torch.nn.Module front of the B200-native coupling flow.
+
+Mirrors the reference's operator interface for the hot path so the training scripts only
+change their import (`from nf_b200 import RealNVP` instead of
+`from utils.torch_fcnf import RealNVP`, /root/reference/il-and-cil/torch_nfbc_ant.py:30):
+
+* ``RealNVP(in_channels, channels, cond_channels, n_layers, prior)``      torch_fcnf.py:119-132
+* ``forward(x, y) -> (z, outputs, log_dets)``                               torch_fcnf.py:134-141
+* ``reverse(x, y, return_sequence=False)``                                  torch_fcnf.py:143-152
+* ``.prior``, ``.blocks[i].{l,t,s}``, identical ``state_dict`` keys          torch_fcnf.py:14-31, 61-93
+
+All arithmetic runs in libnf_b200.so (hand-written sm_100a CUDA) through the C ABI of
+include/nf_b200.h; there is no CPU or PyTorch-eager fallback -- CPU tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import List, Optional
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _lib
+from ._lib import lib
+
+
+def count_parameters(model):
+    """torch_fcnf.py:11."""
+    return sum(p.numel() for p in model.parameters())
+
+
+class InvertiblePLU(nn.Module):
+    """Parameter container of the invertible linear layer W = P L (U + diag s)
+    (torch_fcnf.py:14-31: same initialiser, same parameter names, P/P_inv frozen)."""
+
+    def __init__(self, features: int):
+        super().__init__()
+        self.features = features
+        w = torch.empty((features, features))
+        nn.init.orthogonal_(w)
+        P, L, U = torch.linalg.lu(w)
+        self.s = nn.Parameter(torch.diag(U))
+        self.U = nn.Parameter(U - torch.diag(self.s))
+        self.L = nn.Parameter(L)
+        self.P = nn.Parameter(P, requires_grad=False)
+        self.P_inv = nn.Parameter(torch.linalg.inv(P), requires_grad=False)
+
+
+def _conditioner(in_features: int, first_hidden: int, channels: int, out_features: int, ln_eps: float):
+    """Linear-LeakyReLU-LayerNorm x2 + Linear with a zero-initialised head (torch_fcnf.py:74-93)."""
+    net = nn.Sequential(
+        nn.Linear(in_features, first_hidden), nn.LeakyReLU(), nn.LayerNorm(first_hidden, eps=ln_eps),
+        nn.Linear(first_hidden, channels), nn.LeakyReLU(), nn.LayerNorm(channels, eps=ln_eps),
+        nn.Linear(channels, out_features),
+    )
+    nn.init.zeros_(net[-1].weight)
+    nn.init.zeros_(net[-1].bias)
+    return net
+
+
+class MetaBlock(nn.Module):
+    """Parameter container of one flow block (torch_fcnf.py:60-93); the arithmetic of
+    forward/reverse (:95-117) is done for the whole stack by RealNVP."""
+
+    def __init__(self, in_channels: int, channels: int, cond_channels: int,
+                 first_hidden: Optional[int] = None, ln_eps: float = 1e-5):
+        super().__init__()
+        k1 = int(np.ceil(in_channels / 2)) + cond_channels
+        h1 = channels if first_hidden is None else first_hidden
+        self.l = InvertiblePLU(in_channels)
+        self.t = _conditioner(k1, h1, channels, in_channels // 2, ln_eps)
+        self.s = _conditioner(k1, h1, channels, in_channels // 2, ln_eps)
+
+
+class _Flow(torch.autograd.Function):
+    """autograd bridge: forward = nf_flow_forward, backward = nf_flow_backward."""
+
+    @staticmethod
+    def forward(ctx, model: "RealNVP", want_stash: bool, x, y, *params):
+        z, logdet, outs, stash, packed = model._run_forward(x, y, want_stash)
+        ctx.model = model
+        ctx.stash = stash
+        ctx.packed = packed
+        ctx.pver = model._params_version()
+        ctx.B = x.shape[0]
+        ctx.save_for_backward(y)
+        ctx.mark_non_differentiable(outs)
+        return z, logdet, outs
+
+    @staticmethod
+    def backward(ctx, dz, dld, _douts):
+        model = ctx.model
+        if ctx.stash is None:
+            raise RuntimeError("nf_b200: backward called on a forward that ran without a stash")
+        if ctx.pver != model._params_version():
+            raise RuntimeError("nf_b200: parameters were modified between forward and backward")
+        (y,) = ctx.saved_tensors
+        need_x = ctx.needs_input_grad[2]
+        need_y = ctx.needs_input_grad[3]
+        need_p = any(ctx.needs_input_grad[4:])
+        dx, dy, dflat = model._run_backward(ctx.stash, ctx.packed, y, ctx.B, dz, dld, need_x, need_y, need_p)
+        if need_p:
+            views = model._grad_views(dflat)
+            pg = tuple(v if need else None for v, need in zip(views, ctx.needs_input_grad[4:]))
+        else:
+            pg = (None,) * (len(ctx.needs_input_grad) - 4)
+        ctx.stash = None
+        return (None, None, dx, dy) + pg
+
+
+class RealNVP(nn.Module):
+    """Drop-in for the reference ``RealNVP`` (torch_fcnf.py:119-152).
+
+    Extra keyword arguments select the flax twin's semantics
+    (/root/reference/unsupservised-gcrl/nf.py): ``first_hidden=channels+cond_channels`` (:94,101),
+    ``ln_eps=1e-6`` (flax LayerNorm default), and ``precision``:
+    ``"fp32"`` (tcgen05 3xTF32, fp32-parity), ``"fp32_simt"`` (FFMA), ``"bf16"``.
+    """
+
+    def __init__(self, in_channels, channels, cond_channels, n_layers, prior, *,
+                 first_hidden: Optional[int] = None, ln_eps: float = 1e-5, precision: str = "fp32_simt"):
+        super().__init__()
+        self.in_channels = int(in_channels)
+        self.channels = int(channels)
+        self.cond_channels = int(cond_channels)
+        self.n_layers = int(n_layers)
+        self.first_hidden = int(channels if first_hidden is None else first_hidden)
+        self.ln_eps = float(ln_eps)
+        if precision not in _lib.PREC:
+            raise ValueError(f"precision must be one of {sorted(_lib.PREC)}")
+        self.precision = precision
+        self.blocks = nn.ModuleList(
+            [MetaBlock(in_channels, channels, cond_channels, first_hidden, ln_eps) for _ in range(n_layers)])
+        self.prior = prior
+
+        self._desc = _lib.make_desc(self.in_channels, self.channels, self.first_hidden, self.cond_channels,
+                                    self.n_layers, self.ln_eps, _lib.PREC[precision])
+        self._layout = _lib.param_layout(self._desc)
+        self._flat: Optional[torch.Tensor] = None
+        self._packed: Optional[torch.Tensor] = None
+        self._packed_key = None
+        self._ws: Optional[torch.Tensor] = None
+        self._dp_group = None
+        self._dp_world = 1
+        self._flatten()
+        self.register_load_state_dict_post_hook(lambda module, keys: module._flatten())
+
+    # ------------------------------------------------------------------ parameter arena
+    def _slot_params(self):
+        """[(param, offset_in_floats)] in arena order (include/nf_b200.h NF_P_*)."""
+        lay = self._layout
+        out = []
+        for i, blk in enumerate(self.blocks):
+            base = i * lay.block_stride
+            plist = [blk.l.s, blk.l.U, blk.l.L, blk.l.P, blk.l.P_inv]
+            for net in (blk.t, blk.s):
+                plist += [net[0].weight, net[0].bias, net[2].weight, net[2].bias, net[3].weight, net[3].bias,
+                          net[5].weight, net[5].bias, net[6].weight, net[6].bias]
+            for slot, p in enumerate(plist):
+                assert p.numel() == lay.slot_numel[slot], (slot, tuple(p.shape), lay.slot_numel[slot])
+                out.append((p, base + lay.slot_off[slot]))
+        return out
+
+    def _flatten(self):
+        """(Re)pack every parameter into one flat fp32 arena and make the nn.Parameters views of it.
+        The arena layout is the one the C library computes (nf_param_layout)."""
+        sp = self._slot_params()
+        dev = sp[0][0].device
+        dtype = sp[0][0].dtype
+        flat = torch.zeros(self._layout.total, dtype=dtype, device=dev)
+        with torch.no_grad():
+            for p, off in sp:
+                view = flat[off:off + p.numel()].view(p.shape)
+                view.copy_(p.detach())
+                p.data = view
+        self._flat = flat
+        self._slots = sp
+        self._trainable = [(p, off) for p, off in sp if p.requires_grad]
+        self._packed = None
+        self._packed_key = None
+
+    def _apply(self, fn, recurse=True):
+        out = super()._apply(fn, recurse)
+        self._flatten()
+        self._ws = None
+        return out
+
+    def _is_flat(self):
+        p0, off0 = self._slots[0]
+        p1, off1 = self._slots[-1]
+        base = self._flat.data_ptr()
+        return (p0.data_ptr() == base + 4 * off0 and p1.data_ptr() == base + 4 * off1
+                and p0.device == self._flat.device)
+
+    def _params_version(self):
+        return sum(p._version for p, _ in self._slots)
+
+    def _grad_views(self, dflat):
+        return [dflat[off:off + p.numel()].view(p.shape) for p, off in self._trainable]
+
+    # ------------------------------------------------------------------ plumbing
+    def _check_inputs(self, x, y):
+        if not (x.is_cuda and y.is_cuda):
+            raise RuntimeError("nf_b200.RealNVP runs on CUDA only (sm_100a kernels, no CPU fallback); "
+                               "move the module and its inputs to a B200")
+        if x.dim() != 2 or x.shape[1] != self.in_channels:
+            raise ValueError(f"x must be (B, {self.in_channels}), got {tuple(x.shape)}")
+        if y.dim() != 2 or y.shape[1] != self.cond_channels or y.shape[0] != x.shape[0]:
+            raise ValueError(f"y must be ({x.shape[0]}, {self.cond_channels}), got {tuple(y.shape)}")
+        if x.dtype != torch.float32 or y.dtype != torch.float32:
+            raise TypeError("nf_b200 computes in float32: x and y must be float32")
+        if not self._is_flat():
+            self._flatten()
+        if self._flat.device != x.device or self._flat.dtype != torch.float32:
+            raise RuntimeError("module parameters must be float32 on the same device as the inputs")
+
+    def _stream(self, device):
+        return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+    def _workspace(self, B, device):
+        need = lib.nf_flow_workspace_bytes(ctypes.byref(self._desc), B)
+        if self._ws is None or self._ws.numel() < need or self._ws.device != device:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=device)
+        return self._ws
+
+    def _prepared(self, what, device):
+        """Derived parameter tables (W, W^-1, folded LayerNorm affine, log|det|), rebuilt whenever a
+        parameter changed (torch_fcnf.py:34-38, 45-54 redo this in every call)."""
+        key = (self._params_version(), self._flat.data_ptr())
+        have = self._packed_key
+        if self._packed is not None and have is not None and have[0] == key and (have[1] & what) == what:
+            return self._packed
+        nbytes = lib.nf_flow_packed_bytes(ctypes.byref(self._desc))
+        packed = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        ws = self._workspace(1, device)
+        if have is not None and have[0] == key:
+            what |= have[1]
+        _lib.check(lib.nf_flow_prepare(ctypes.byref(self._desc), self._flat.data_ptr(), packed.data_ptr(), what,
+                                       ws.data_ptr(), ws.numel(), self._stream(device)), "nf_flow_prepare")
+        self._packed, self._packed_key = packed, (key, what)
+        return packed
+
+    def _run_forward(self, x, y, want_stash):
+        dev = x.device
+        B, D, n = x.shape[0], self.in_channels, self.n_layers
+        x = x.contiguous()
+        y = y.contiguous()
+        with torch.cuda.device(dev):
+            packed = self._prepared(_lib.NF_PREP_FWD, dev)
+            ws = self._workspace(B, dev)
+            z = torch.empty((B, D), dtype=torch.float32, device=dev)
+            logdet = torch.empty((B,), dtype=torch.float32, device=dev)
+            stash = None
+            if want_stash:
+                nbytes = lib.nf_flow_stash_bytes(ctypes.byref(self._desc), B)
+                stash = torch.empty(nbytes // 4, dtype=torch.float32, device=dev)
+                # outputs alias the block-input region of the stash: xs[1:], (n, B, D)
+                outs = stash[B * D:(n + 1) * B * D].view(n, B, D)
+                outs_ptr = None
+            else:
+                outs = torch.empty((n, B, D), dtype=torch.float32, device=dev)
+                outs_ptr = outs.data_ptr()
+            _lib.check(lib.nf_flow_forward(
+                ctypes.byref(self._desc), self._flat.data_ptr(), packed.data_ptr(), x.data_ptr(), y.data_ptr(), B,
+                z.data_ptr(), logdet.data_ptr(), outs_ptr, stash.data_ptr() if stash is not None else None,
+                ws.data_ptr(), ws.numel(), self._stream(dev)), "nf_flow_forward")
+        return z, logdet, outs, stash, packed
+
+    def _run_backward(self, stash, packed, y, B, dz, dld, need_x, need_y, need_p):
+        dev = y.device
+        D, R = self.in_channels, self.cond_channels
+        with torch.cuda.device(dev):
+            ws = self._workspace(B, dev)
+            dz = dz.contiguous() if dz is not None else None
+            dld = dld.contiguous() if dld is not None else None
+            dx = torch.empty((B, D), dtype=torch.float32, device=dev) if need_x else None
+            dy = torch.empty((B, R), dtype=torch.float32, device=dev) if need_y else None
+            dflat = torch.empty(self._layout.total, dtype=torch.float32, device=dev) if need_p else None
+            ptr = lambda t: t.data_ptr() if t is not None else None
+            _lib.check(lib.nf_flow_backward(
+                ctypes.byref(self._desc), self._flat.data_ptr(), packed.data_ptr(), stash.data_ptr(), y.data_ptr(), B,
+                ptr(dz), ptr(dld), ptr(dx), ptr(dy), ptr(dflat), ws.data_ptr(), ws.numel(), self._stream(dev)),
+                "nf_flow_backward")
+            if need_p and self._dp_world > 1:
+                self._allreduce_grads(dflat)
+        return dx, dy, dflat
+
+    # ------------------------------------------------------------------ data parallel
+    def enable_data_parallel(self, process_group=None):
+        """Batch-sharded data parallel training: gradients of the flat arena are averaged over the
+        ranks of `process_group` (NCCL over NVLink on the GPU box) inside backward."""
+        import torch.distributed as dist
+        self._dp_group = process_group
+        self._dp_world = dist.get_world_size(process_group)
+        return self
+
+    def _allreduce_grads(self, dflat):
+        import torch.distributed as dist
+        dist.all_reduce(dflat, op=dist.ReduceOp.SUM, group=self._dp_group)
+        dflat.mul_(1.0 / self._dp_world)
+
+    # ------------------------------------------------------------------ reference API
+    def forward(self, x, y):
+        """-> (z, outputs, log_dets): torch_fcnf.py:134-141.  ``outputs`` (list of n_layers (B, D)
+        tensors, the block outputs logged at torch_nfbc_ant.py:286-287) are not differentiable."""
+        self._check_inputs(x, y)
+        params = [p for p, _ in self._trainable]
+        need_grad = torch.is_grad_enabled() and (
+            x.requires_grad or y.requires_grad or any(p.requires_grad for p in params))
+        if need_grad:
+            z, logdet, outs = _Flow.apply(self, True, x, y, *params)
+        else:
+            z, logdet, outs, _, _ = self._run_forward(x, y, False)
+        return z, list(outs.unbind(0)), logdet
+
+    def reverse(self, x, y, return_sequence=False, return_logdet=False):
+        """torch_fcnf.py:143-152 (sampling direction; not differentiable).  With
+        ``return_logdet=True`` also returns the flax-style reverse log-det (nf.py:131-148)."""
+        self._check_inputs(x, y)
+        dev = x.device
+        B, D, n = x.shape[0], self.in_channels, self.n_layers
+        x = x.detach().contiguous()
+        y = y.detach().contiguous()
+        with torch.cuda.device(dev):
+            packed = self._prepared(_lib.NF_PREP_FWD | _lib.NF_PREP_INV, dev)
+            ws = self._workspace(B, dev)
+            out = torch.empty((B, D), dtype=torch.float32, device=dev)
+            logdet = torch.empty((B,), dtype=torch.float32, device=dev) if return_logdet else None
+            seq = torch.empty((n + 1, B, D), dtype=torch.float32, device=dev) if return_sequence else None
+            _lib.check(lib.nf_flow_inverse(
+                ctypes.byref(self._desc), self._flat.data_ptr(), packed.data_ptr(), x.data_ptr(), y.data_ptr(), B,
+                out.data_ptr(), logdet.data_ptr() if logdet is not None else None,
+                seq.data_ptr() if seq is not None else None, ws.data_ptr(), ws.numel(), self._stream(dev)),
+                "nf_flow_inverse")
+        res = list(seq.unbind(0)) if return_sequence else out
+        return (res, logdet) if return_logdet else res
+
+    # ------------------------------------------------------------------ extras
+    def log_prob(self, x, y):
+        """log N(z; 0, I) + log_dets -- what the callers assemble from ``prior.log_prob(z) + logdets``
+        (torch_nfbc_ant.py:269) for the standard-normal prior, without the O(D^2) Mahalanobis path."""
+        z, _, logdet = self.forward(x, y)
+        return -0.5 * (z * z).sum(dim=1) - 0.5 * self.in_channels * math.log(2.0 * math.pi) + logdet
+
+    def sample(self, y, generator=None):
+        """reverse(prior sample, y) with a standard-normal prior (torch_nfbc_ant.py:209-210)."""
+        eps = torch.randn((y.shape[0], self.in_channels), dtype=torch.float32, device=y.device, generator=generator)
+        return self.reverse(eps, y)

@@ -1,0 +1,115 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/nf_b200.h declares,
+argument validation works without a GPU, and the host-side module mirrors the reference's
+parameter tree (no compute calls here)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import nf_b200
+from nf_b200 import _lib
+from oracle import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "nf_b200.h")).read()
+    return sorted(set(re.findall(r"NF_API\s+[\w\s\*]+?\b(nf_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    syms = header_symbols()
+    assert len(syms) >= 14
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for s in syms:
+        assert hasattr(lib, s), s
+    assert sorted(_lib.EXPORTS) == syms, "ctypes binding and header disagree"
+    assert _lib.lib.nf_abi_version() == 1
+
+
+def test_bad_descriptor_is_rejected_with_message():
+    d = _lib.make_desc(1, 32, 32, 4, 2, 1e-5, 0)   # D=1 has nothing to transform
+    out = _lib.NfParamLayout()
+    rc = _lib.lib.nf_param_layout(ctypes.byref(d), ctypes.byref(out))
+    assert rc == -1
+    assert b"D=1" in _lib.lib.nf_last_error()
+    assert _lib.lib.nf_flow_packed_bytes(ctypes.byref(d)) == -1
+    d2 = _lib.make_desc(8, 32, 32, 4, 2, 1e-5, 7)
+    assert _lib.lib.nf_param_layout(ctypes.byref(d2), ctypes.byref(out)) == -1
+
+
+@pytest.mark.parametrize("D,C,R,n,H1", [(9, 32, 16, 3, None), (2, 16, 8, 2, 24), (8, 64, 0, 1, None)])
+def test_param_layout_matches_state_dict(D, C, R, n, H1):
+    m = nf_b200.RealNVP(D, C, R, n, None, first_hidden=H1)
+    lay = m._layout
+    sd = m.state_dict()
+    keys = list(sd.keys())
+    ref_sd = synth.make_state_dict(D, C, R, n, H1=H1)
+    assert keys == list(ref_sd.keys())
+    for k in keys:
+        assert tuple(sd[k].shape) == ref_sd[k].shape, k
+    # slot order == state_dict order inside a block, offsets 16-byte aligned and non-overlapping
+    per_block = len(keys) // n
+    assert per_block == _lib.NF_P_SLOTS
+    end = 0
+    for slot in range(_lib.NF_P_SLOTS):
+        assert keys[slot] == "blocks.0." + _lib.SLOT_NAMES[slot]
+        assert lay.slot_off[slot] % 4 == 0 and lay.slot_off[slot] >= end
+        assert lay.slot_numel[slot] == sd[keys[slot]].numel()
+        end = lay.slot_off[slot] + lay.slot_numel[slot]
+    assert lay.block_stride >= end and lay.total == n * lay.block_stride
+    assert nf_b200.count_parameters(m) == sum(v.size for v in ref_sd.values())
+
+
+def test_parameters_are_views_of_one_arena_and_survive_load_state_dict():
+    D, C, R, n = 9, 32, 16, 2
+    m = nf_b200.RealNVP(D, C, R, n, None)
+    assert m._is_flat()
+    sd = {k: torch.tensor(v) for k, v in synth.make_state_dict(D, C, R, n, seed=7).items()}
+    m.load_state_dict(sd)
+    assert m._is_flat()
+    lay = m._layout
+    flat = m._flat
+    w = m.blocks[1].s[3].weight
+    off = lay.block_stride + lay.slot_off[5 + 10 + 4]
+    assert torch.equal(flat[off:off + w.numel()].view_as(w), sd["blocks.1.s.3.weight"])
+    # frozen permutation factors, trainable everything else (torch_fcnf.py:30-31)
+    assert not m.blocks[0].l.P.requires_grad and not m.blocks[0].l.P_inv.requires_grad
+    assert m.blocks[0].l.L.requires_grad
+    # in-place optimiser-style update is visible through the arena and bumps the version
+    v0 = m._params_version()
+    with torch.no_grad():
+        w.add_(1.0)
+    assert m._params_version() != v0
+    assert torch.equal(flat[off:off + w.numel()].view_as(w), sd["blocks.1.s.3.weight"] + 1.0)
+
+
+def test_same_seed_gives_the_reference_initialisation():
+    """The containers are built with the same torch calls in the same order as
+    torch_fcnf.py:15-31,61-93, so a seed reproduces the reference's initial weights; the heads are
+    zero (s = t = 0 at init)."""
+    torch.manual_seed(0)
+    m = nf_b200.RealNVP(8, 32, 16, 2, None)
+    for blk in m.blocks:
+        assert float(blk.s[6].weight.abs().max()) == 0.0 and float(blk.t[6].bias.abs().max()) == 0.0
+        W = blk.l.P @ (torch.tril(blk.l.L, -1) + torch.eye(8)) @ (torch.triu(blk.l.U, 1) + torch.diag(blk.l.s))
+        assert torch.allclose(W @ W.T, torch.eye(8), atol=1e-5)   # orthogonal init
+
+
+def test_cpu_tensors_are_refused():
+    m = nf_b200.RealNVP(8, 32, 16, 2, None)
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        m(torch.zeros(4, 8), torch.zeros(4, 16))
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        m.reverse(torch.zeros(4, 8), torch.zeros(4, 16))
+
+
+def test_flops_formula():
+    # SURVEY.md section 8(d) table
+    assert abs(synth.flops_fwd_per_sample(**synth.CONFIGS["C2a"]) / 1e6 - 2.016) < 0.01
+    assert abs(synth.flops_fwd_per_sample(**synth.CONFIGS["C4"]) / 1e6 - 37.97) < 0.05
+    assert abs(synth.flops_fwd_per_sample(**synth.CONFIGS["C5"]) / 1e6 - 129.02) < 0.05

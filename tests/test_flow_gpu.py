@@ -1,0 +1,276 @@
+"""GPU parity tests (run on the B200 box with `-m gpu`): the CUDA path called through the
+nn.Module / C-ABI is compared with the golden fixtures generated from the real reference and
+with the numpy oracle on seeded inputs.  Nothing here reads /root/reference."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import nf_b200
+from nf_b200 import _lib
+from oracle import flow_oracle as fo
+from oracle import synth
+from tests.helpers import golden_files, grad_probe, load_case, probe_err, rel_err, tol_vs_arbiter
+
+pytestmark = pytest.mark.gpu
+CASES = golden_files()
+PRECISIONS = ["fp32_simt"]
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def build_model(cfg, sd, precision, **kw):
+    m = nf_b200.RealNVP(cfg["D"], cfg["C"], cfg["R"], cfg["n"], None, precision=precision, **kw)
+    m.load_state_dict({k: torch.tensor(np.asarray(v, dtype=np.float32)) for k, v in sd.items()})
+    return m.to(dev())
+
+
+def t(a):
+    return torch.tensor(np.asarray(a, dtype=np.float32), device=dev())
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[:-4] for p in CASES])
+def test_golden_forward_reverse_backward(path, precision):
+    cfg, sd, x, y, dz, dld, g = load_case(path)
+    model = build_model(cfg, sd, precision)
+    xt, yt = t(x).requires_grad_(True), t(y).requires_grad_(True)
+    z, outputs, log_dets = model(xt, yt)
+    assert len(outputs) == cfg["n"] and z.shape == xt.shape and log_dets.shape == (cfg["B"],)
+
+    def check(name, ours, floor=1e-5):
+        ref64 = g[f"f64/{name}"]
+        tol = tol_vs_arbiter(g[f"f32/{name}"], ref64, floor)
+        e = rel_err(ours.detach().cpu().numpy(), ref64)
+        assert e <= tol, (name, e, tol)
+
+    check("z", z)
+    check("log_dets", log_dets)
+    check("outputs", torch.stack(outputs))
+    assert torch.equal(outputs[-1], z.detach())
+
+    (z * t(dz)).sum().add((log_dets * t(dld)).sum()).backward()
+    check("dx", xt.grad)
+    check("dy", yt.grad)
+    errs, noise = {}, [0.0]
+    for k, p in model.named_parameters():
+        if not p.requires_grad:
+            assert p.grad is None
+            continue
+        gr = p.grad.detach().cpu().numpy()
+        if f"f64/grad/{k}" in g.files:
+            errs[k] = rel_err(gr, g[f"f64/grad/{k}"])
+            noise.append(rel_err(g[f"f32/grad/{k}"], g[f"f64/grad/{k}"]))
+        else:
+            errs[k] = probe_err(grad_probe(gr, k), g[f"f64/gprobe/{k}"], gr.size)
+            noise.append(probe_err(g[f"f32/gprobe/{k}"], g[f"f64/gprobe/{k}"], gr.size))
+    tol = max(5e-5, 2.0 * max(noise))
+    bad = {k: e for k, e in errs.items() if e > tol}
+    assert not bad, (sorted(bad.items(), key=lambda kv: -kv[1])[:5], tol)
+
+    # reverse of the reference's own z, against the reference's own reverse
+    with torch.no_grad():
+        rev = model.reverse(t(g["f32/z"]), t(y))
+    tol = max(10 * tol_vs_arbiter(g["f32/rev"], g["f64/rev"]), 1e-4)
+    assert rel_err(rev.cpu().numpy(), g["f32/rev"]) <= tol
+    # NLL of torch_nfbc_ant.py:269 through the log_prob extra
+    with torch.no_grad():
+        nll = -model.log_prob(t(x), t(y)).mean().item()
+    assert abs(nll - float(g["f64/nll"])) <= 1e-5 * max(1.0, abs(float(g["f64/nll"]))) + 2 * abs(
+        float(g["f32/nll"]) - float(g["f64/nll"]))
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("B", [1, 20, 50, 257])
+@pytest.mark.parametrize("D,C,R,n,H1,eps", [(9, 64, 24, 3, None, 1e-5), (2, 32, 8, 2, 40, 1e-6), (8, 48, 16, 2, None, 1e-5)])
+def test_oracle_parity_ragged_batches(B, D, C, R, n, H1, eps, precision):
+    """Odd D (9 -> 5/4 split), batch sizes that are not tile multiples, the flax twin's widths
+    (first hidden C+R, eps 1e-6) -- against the numpy oracle in float64."""
+    sd = synth.make_state_dict(D, C, R, n, seed=11, H1=H1)
+    x, y = synth.make_inputs(B, D, R, seed=B)
+    dz, dld = synth.make_cotangents(B, D, seed=B + 1)
+    cfg = dict(D=D, C=C, R=R, n=n, B=B)
+    model = build_model(cfg, sd, precision, first_hidden=H1, ln_eps=eps)
+    sd64 = fo.cast_state_dict(sd, np.float64)
+    ref = fo.flow_backward(sd64, n, x.astype(np.float64), y.astype(np.float64), dz.astype(np.float64),
+                           dld.astype(np.float64), eps=eps)
+    xt, yt = t(x).requires_grad_(True), t(y).requires_grad_(True)
+    z, outputs, ld = model(xt, yt)
+    (z * t(dz)).sum().add((ld * t(dld)).sum()).backward()
+    tol = 2e-5
+    assert rel_err(z.detach().cpu().numpy(), ref["z"]) <= tol
+    assert rel_err(ld.detach().cpu().numpy(), ref["log_dets"]) <= tol
+    assert rel_err(xt.grad.cpu().numpy(), ref["dx"]) <= tol
+    assert rel_err(yt.grad.cpu().numpy(), ref["dy"]) <= tol
+    for k, p in model.named_parameters():
+        if p.requires_grad:
+            assert rel_err(p.grad.cpu().numpy(), ref["grads"][k]) <= 5e-5, k
+    with torch.no_grad():
+        seq, rld = model.reverse(z.detach(), yt.detach(), return_sequence=True, return_logdet=True)
+    ref_seq, ref_rld = fo.flow_reverse(sd64, n, ref["z"], y.astype(np.float64), eps=eps, return_sequence=True,
+                                       return_logdet=True)
+    assert len(seq) == n + 1
+    for a, b in zip(seq, ref_seq):
+        assert rel_err(a.cpu().numpy(), b) <= 1e-4
+    assert rel_err(rld.cpu().numpy(), ref_rld) <= 1e-4
+    # inverse(forward(x)) == x and reverse log-det == -forward log-det
+    assert rel_err(seq[-1].cpu().numpy(), x) <= 1e-4
+    assert rel_err(rld.cpu().numpy(), -ref["log_dets"]) <= 1e-4
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("cfgname,B", [("C2a", 4096), ("C4", 8192), ("C3", 16384)])
+def test_full_size_properties(cfgname, B, precision):
+    """BASELINE.json sizes: size-independent properties (round trip, log-det antisymmetry,
+    shard-invariance of outputs and of data-parallel gradients)."""
+    cfg = dict(synth.CONFIGS[cfgname])
+    eps, H1 = cfg.pop("ln_eps"), cfg.pop("H1")
+    sd = synth.make_state_dict(cfg["D"], cfg["C"], cfg["R"], cfg["n"], seed=0, H1=H1)
+    model = build_model(dict(cfg, B=B), sd, precision, first_hidden=H1, ln_eps=eps)
+    x, y = synth.make_inputs(B, cfg["D"], cfg["R"], seed=99)
+    xt, yt = t(x), t(y)
+    with torch.no_grad():
+        z, outs, ld = model(xt, yt)
+        xr, rld = model.reverse(z, yt, return_logdet=True)
+    assert torch.isfinite(z).all() and torch.isfinite(ld).all()
+    assert rel_err(xr.cpu().numpy(), x) <= 2e-4
+    assert rel_err(rld.cpu().numpy(), -ld.cpu().numpy()) <= 2e-5
+    # rows are independent: a shard gives the same rows as the full batch
+    h = B // 2 + 3
+    with torch.no_grad():
+        z2, _, ld2 = model(xt[h:].contiguous(), yt[h:].contiguous())
+    assert rel_err(z2.cpu().numpy(), z[h:].cpu().numpy()) <= 1e-6
+    assert rel_err(ld2.cpu().numpy(), ld[h:].cpu().numpy()) <= 1e-6
+    if cfgname == "C4":
+        return   # sampling-only config
+    # data parallel invariant: mean of shard gradients == full-batch gradient of the mean loss
+    def grads(xs, ys, scale):
+        for p in model.parameters():
+            p.grad = None
+        (-model.log_prob(xs, ys).sum() * scale).backward()
+        return torch.cat([p.grad.reshape(-1) for p in model.parameters() if p.requires_grad])
+    full = grads(xt, yt, 1.0 / B)
+    half = B // 2
+    parts = 0.5 * (grads(xt[:half].contiguous(), yt[:half].contiguous(), 1.0 / half)
+                   + grads(xt[half:].contiguous(), yt[half:].contiguous(), 1.0 / half))
+    assert rel_err(parts.cpu().numpy(), full.cpu().numpy()) <= 2e-5
+
+
+def test_denoise_step_input_gradient_only():
+    """torch_nfbc_ant.py:212-217: autograd.grad of the log-prob w.r.t. the action only."""
+    cfg = dict(D=8, C=64, R=32, n=3, B=20)
+    sd = synth.make_state_dict(8, 64, 32, 3, seed=2)
+    model = build_model(cfg, sd, PRECISIONS[0])
+    for p in model.parameters():
+        p.requires_grad_(False)
+    x, y = synth.make_inputs(20, 8, 32, seed=3)
+    action = t(x).requires_grad_(True)
+    z, _, ld = model(action, t(y))
+    logprob = -0.5 * (z * z).sum(1) + ld
+    (grad,) = torch.autograd.grad(logprob.sum(), [action])
+    sd64 = fo.cast_state_dict(sd, np.float64)
+    z64, _, _ = fo.flow_forward(sd64, 3, x.astype(np.float64), y.astype(np.float64))
+    ref = fo.flow_backward(sd64, 3, x.astype(np.float64), y.astype(np.float64), -z64, np.ones(20))
+    assert rel_err(grad.cpu().numpy(), ref["dx"]) <= 2e-5
+
+
+def test_standalone_affine_and_plu_kernels():
+    lib = _lib.lib
+    rs = np.random.RandomState(0)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for D, B in [(8, 1000), (9, 257), (400, 64), (2, 5000)]:
+        dc, dt = (D + 1) // 2, D // 2
+        xp, s, tt = rs.randn(B, D), 0.3 * rs.randn(B, dt), rs.randn(B, dt)
+        bs, bt = 0.1 * rs.randn(dt), 0.1 * rs.randn(dt)
+        ld0 = rs.randn(B)
+        z = torch.empty(B, D, device=dev())
+        ld = t(ld0)
+        sout = torch.empty(B, dt, device=dev())
+        _lib.check(lib.nf_affine_logdet_fwd(t(xp).data_ptr(), t(s).data_ptr(), t(tt).data_ptr(), t(bs).data_ptr(),
+                                            t(bt).data_ptr(), 0.25, B, D, z.data_ptr(), ld.data_ptr(),
+                                            sout.data_ptr(), st), "affine_fwd")
+        sf, tf = s + bs, tt + bt
+        zref = np.concatenate([xp[:, :dc], (xp[:, dc:] - tf) * np.exp(-sf)], axis=1)
+        assert rel_err(z.cpu().numpy(), zref) <= 1e-6
+        assert rel_err(ld.cpu().numpy(), ld0 + 0.25 - sf.sum(1)) <= 1e-6
+        assert rel_err(sout.cpu().numpy(), sf) <= 1e-6
+        # inverse undoes forward
+        back = torch.empty(B, D, device=dev())
+        ld2 = ld.clone()
+        _lib.check(lib.nf_affine_logdet_inv(z.data_ptr(), t(s).data_ptr(), t(tt).data_ptr(), t(bs).data_ptr(),
+                                            t(bt).data_ptr(), 0.25, B, D, back.data_ptr(), ld2.data_ptr(), st),
+                   "affine_inv")
+        assert rel_err(back.cpu().numpy(), xp) <= 1e-5
+        assert rel_err(ld2.cpu().numpy(), ld0) <= 1e-5
+        # backward
+        dzv, dldv = rs.randn(B, D), rs.randn(B)
+        dxp = torch.empty(B, D, device=dev()); ds = torch.empty(B, dt, device=dev()); dtt = torch.empty(B, dt, device=dev())
+        _lib.check(lib.nf_affine_logdet_bwd(t(dzv).data_ptr(), z.data_ptr(), sout.data_ptr(), t(dldv).data_ptr(), B, D,
+                                            dxp.data_ptr(), ds.data_ptr(), dtt.data_ptr(), st), "affine_bwd")
+        e = np.exp(-sf)
+        assert rel_err(dxp.cpu().numpy(), np.concatenate([dzv[:, :dc], dzv[:, dc:] * e], 1)) <= 1e-6
+        assert rel_err(ds.cpu().numpy(), -dzv[:, dc:] * zref[:, dc:] - dldv[:, None]) <= 1e-5
+        assert rel_err(dtt.cpu().numpy(), -dzv[:, dc:] * e) <= 1e-6
+    for D in (2, 9, 64, 400):
+        sd = synth.make_state_dict(D, 4, 2, 1, seed=D)
+        W = torch.empty(D, D, device=dev()); Wi = torch.empty(D, D, device=dev()); ldt = torch.empty(1, device=dev())
+        ws = torch.empty(64 * D * D + 4096, dtype=torch.float32, device=dev())
+        _lib.check(lib.nf_plu_build(t(sd["blocks.0.l.s"]).data_ptr(), t(sd["blocks.0.l.U"]).data_ptr(),
+                                    t(sd["blocks.0.l.L"]).data_ptr(), t(sd["blocks.0.l.P"]).data_ptr(),
+                                    t(sd["blocks.0.l.P_inv"]).data_ptr(), D, W.data_ptr(), Wi.data_ptr(),
+                                    ldt.data_ptr(), ws.data_ptr(), ws.numel() * 4, st), "plu_build")
+        sd64 = fo.cast_state_dict(sd, np.float64)
+        assert rel_err(W.cpu().numpy(), fo.plu_weight(sd64, 0)[0]) <= 1e-5
+        assert rel_err(Wi.cpu().numpy(), fo.plu_weight_inv(sd64, 0)) <= 1e-4
+        assert abs(ldt.item() - fo.plu_logdet(sd64, 0)) <= 1e-4
+
+
+def test_abi_argument_errors_on_device():
+    lib = _lib.lib
+    d = _lib.make_desc(8, 32, 32, 4, 2, 1e-5, 0)
+    buf = torch.zeros(1 << 16, device=dev())
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    # misaligned pointer
+    rc = lib.nf_flow_forward(ctypes.byref(d), buf.data_ptr() + 4, buf.data_ptr(), buf.data_ptr(), buf.data_ptr(), 4,
+                             buf.data_ptr(), buf.data_ptr(), None, None, buf.data_ptr(), buf.numel() * 4, st)
+    assert rc == -2 and b"aligned" in lib.nf_last_error()
+    # workspace too small
+    rc = lib.nf_flow_forward(ctypes.byref(d), buf.data_ptr(), buf.data_ptr(), buf.data_ptr(), buf.data_ptr(), 4096,
+                             buf.data_ptr(), buf.data_ptr(), None, None, buf.data_ptr(), 64, st)
+    assert rc == -3
+    # empty batch is a no-op
+    rc = lib.nf_flow_forward(ctypes.byref(d), buf.data_ptr(), buf.data_ptr(), None, None, 0, None, None, None, None,
+                             None, 0, st)
+    assert rc == 0
+    m = nf_b200.RealNVP(8, 32, 4, 2, None).to(dev())
+    z, outs, ld = m(torch.zeros(0, 8, device=dev()), torch.zeros(0, 4, device=dev()))
+    assert z.shape == (0, 8) and ld.shape == (0,)
+
+
+def test_fresh_model_is_identity_coupling_and_state_dict_roundtrip(tmp_path):
+    """Zero-initialised heads (torch_fcnf.py:79-82): a fresh model has s = t = 0, so
+    log_dets == sum_i sum log|s_plu| for every row; checkpoints keep the reference's keys
+    (il-and-cil/utils/torch_utils.py:5-16)."""
+    torch.manual_seed(0)
+    m = nf_b200.RealNVP(8, 64, 16, 4, None).to(dev())
+    x, y = synth.make_inputs(33, 8, 16)
+    z, outs, ld = m(t(x), t(y))
+    expect = sum(float(torch.log(torch.abs(b.l.s)).sum()) for b in m.blocks)
+    assert torch.allclose(ld, torch.full_like(ld, expect), atol=1e-5)
+    path = os.path.join(tmp_path, "params.pth")
+    torch.save({"model": m.state_dict()}, path)
+    m2 = nf_b200.RealNVP(8, 64, 16, 4, None).to(dev())
+    m2.load_state_dict(torch.load(path)["model"])
+    z2, _, _ = m2(t(x), t(y))
+    assert torch.equal(z, z2)
+    # one optimiser step changes the output (prepared tables are refreshed)
+    opt = torch.optim.AdamW(m2.parameters(), lr=1e-2)
+    loss = -m2.log_prob(t(x), t(y)).mean()
+    loss.backward()
+    opt.step()
+    z3, _, _ = m2(t(x), t(y))
+    assert not torch.equal(z2, z3)
