@@ -13,7 +13,7 @@ namespace nf {
 // error plumbing
 // ---------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
-static thread_local int64_t g_launches = 0;
+static int64_t g_launches = 0;  // process-wide (autograd runs backward on its own thread)
 char* err_buf() { return g_err; }
 int64_t& launch_counter() { return g_launches; }
 int set_err(int code, const char* fmt, ...) {

@@ -26,6 +26,17 @@ from . import _lib
 from ._lib import lib
 
 
+def _dense(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    """Contiguous and 16-byte aligned (the C ABI's contract); row slices of a tensor are contiguous
+    but can start at any float, so those are copied."""
+    if t is None:
+        return None
+    t = t.contiguous()
+    if t.data_ptr() % 16 != 0:
+        t = t.clone()
+    return t
+
+
 def count_parameters(model):
     """torch_fcnf.py:11."""
     return sum(p.numel() for p in model.parameters())
@@ -245,8 +256,8 @@ class RealNVP(nn.Module):
     def _run_forward(self, x, y, want_stash):
         dev = x.device
         B, D, n = x.shape[0], self.in_channels, self.n_layers
-        x = x.contiguous()
-        y = y.contiguous()
+        x = _dense(x)
+        y = _dense(y)
         with torch.cuda.device(dev):
             packed = self._prepared(_lib.NF_PREP_FWD, dev)
             ws = self._workspace(B, dev)
@@ -273,8 +284,7 @@ class RealNVP(nn.Module):
         D, R = self.in_channels, self.cond_channels
         with torch.cuda.device(dev):
             ws = self._workspace(B, dev)
-            dz = dz.contiguous() if dz is not None else None
-            dld = dld.contiguous() if dld is not None else None
+            dz, dld, y = _dense(dz), _dense(dld), _dense(y)
             dx = torch.empty((B, D), dtype=torch.float32, device=dev) if need_x else None
             dy = torch.empty((B, R), dtype=torch.float32, device=dev) if need_y else None
             dflat = torch.empty(self._layout.total, dtype=torch.float32, device=dev) if need_p else None
@@ -321,8 +331,8 @@ class RealNVP(nn.Module):
         self._check_inputs(x, y)
         dev = x.device
         B, D, n = x.shape[0], self.in_channels, self.n_layers
-        x = x.detach().contiguous()
-        y = y.detach().contiguous()
+        x = _dense(x.detach())
+        y = _dense(y.detach())
         with torch.cuda.device(dev):
             packed = self._prepared(_lib.NF_PREP_FWD | _lib.NF_PREP_INV, dev)
             ws = self._workspace(B, dev)

@@ -241,3 +241,16 @@ def flow_backward(sd, n, x, y, dz, dld, eps=1e-5):
 
 def cast_state_dict(sd, dtype):
     return OrderedDict((k, np.asarray(v, dtype=dtype)) for k, v in sd.items())
+
+
+def min_abs_preactivation(sd, n, x, y, eps=1e-5):
+    """Smallest |u| over every LeakyReLU input of the stack (float64 recommended).  LeakyReLU is
+    not differentiable at 0: when some |u| is within float32 rounding of zero, two correct float32
+    implementations can pick different slopes and their gradients differ by O(1e-3).  Parity cases
+    are therefore drawn so that this margin is comfortably above float32 noise."""
+    _, _, _, caches = flow_forward(sd, n, x, y, eps, keep=True)
+    m = np.inf
+    for c in caches:
+        for key in ("cs", "ct"):
+            m = min(m, float(np.abs(c[key]["u1"]).min()), float(np.abs(c[key]["u2"]).min()))
+    return m

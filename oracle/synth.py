@@ -107,3 +107,18 @@ def flops_fwd_per_sample(D, C, R, n, H1=None, **_):
     """F_fwd = n [2 D^2 + 4((dc+R) H1 + H1 C + C dt)]."""
     dc, dt, H1 = dims(D, C, R, H1)
     return n * (2 * D * D + 4 * ((dc + R) * H1 + H1 * C + C * dt))
+
+
+KINK_MARGIN = 2e-6
+
+
+def make_safe_inputs(sd, n, B, D, R, seed=1234, eps=1e-5, max_tries=400):
+    """make_inputs with the first seed >= `seed` whose LeakyReLU inputs all stay KINK_MARGIN away
+    from zero (see flow_oracle.min_abs_preactivation).  Returns (x, y, seed_used)."""
+    from . import flow_oracle as fo
+    sd64 = fo.cast_state_dict(sd, np.float64)
+    for s in range(seed, seed + max_tries):
+        x, y = make_inputs(B, D, R, seed=s)
+        if fo.min_abs_preactivation(sd64, n, x.astype(np.float64), y.astype(np.float64), eps) > KINK_MARGIN:
+            return x, y, s
+    raise RuntimeError("no kink-free input seed found")

@@ -93,9 +93,9 @@ def make_refinit(name, D, C, R, n, B):
                 net[5].weight.add_(0.1 * torch.randn_like(net[5].weight))
                 net[5].bias.add_(0.1 * torch.randn_like(net[5].bias))
     sd32 = {k: v.detach().numpy().copy() for k, v in model.state_dict().items()}
-    x, y = synth.make_inputs(B, D, R, seed=1234)
+    x, y, xseed = synth.make_safe_inputs(sd32, n, B, D, R, seed=1234)
     dz, dld = synth.make_cotangents(B, D, seed=4321)
-    out = dict(cfg=np.asarray([D, C, R, n, B]))
+    out = dict(cfg=np.asarray([D, C, R, n, B, 0, xseed]))
     for k, v in sd32.items():
         out["sd/" + k] = v
     for tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
@@ -108,7 +108,7 @@ def make_refinit(name, D, C, R, n, B):
         for k, g in grads.items():
             out[f"{tag}/grad/{k}"] = g
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
-    print(name, "ok", sum(v.nbytes for v in out.values()) // 1024, "KiB raw")
+    print(name, "ok, input seed", xseed)
 
 
 def make_synth(name, cfgname, B, n_override=None, seed=0):
@@ -120,9 +120,9 @@ def make_synth(name, cfgname, B, n_override=None, seed=0):
         cfg["n"] = n_override
     D, C, R, n = cfg["D"], cfg["C"], cfg["R"], cfg["n"]
     sd = synth.make_state_dict(D, C, R, n, seed=seed)
-    x, y = synth.make_inputs(B, D, R, seed=1234)
+    x, y, xseed = synth.make_safe_inputs(sd, n, B, D, R, seed=1234)
     dz, dld = synth.make_cotangents(B, D, seed=4321)
-    out = dict(cfg=np.asarray([D, C, R, n, B, seed]))
+    out = dict(cfg=np.asarray([D, C, R, n, B, seed, xseed]))
     for tag, dt, npdt in (("f32", torch.float32, np.float32), ("f64", torch.float64, np.float64)):
         m = build(D, C, R, n)
         m.load_state_dict({k: torch.tensor(v) for k, v in sd.items()})
@@ -136,7 +136,7 @@ def make_synth(name, cfgname, B, n_override=None, seed=0):
             out[f"{tag}/gprobe/{k}"] = np.concatenate(
                 [[g.sum(dtype=np.float64), (g.astype(np.float64) ** 2).sum()], g.reshape(-1)[idx].astype(np.float64)])
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
-    print(name, "ok", sum(v.nbytes for v in out.values()) // 1024, "KiB raw")
+    print(name, "ok, input seed", xseed)
 
 
 if __name__ == "__main__":

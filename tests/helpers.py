@@ -52,13 +52,12 @@ def load_case(path):
     """Returns (cfg dict, sd, x, y, dz, dld, golden npz)."""
     g = np.load(path)
     name = os.path.basename(path)
+    D, C, R, n, B, seed, xseed = [int(v) for v in g["cfg"]]
     if name.startswith("refinit"):
-        D, C, R, n, B = [int(v) for v in g["cfg"]]
         sd = {k[3:]: g[k] for k in g.files if k.startswith("sd/")}
     else:
-        D, C, R, n, B, seed = [int(v) for v in g["cfg"]]
         sd = synth.make_state_dict(D, C, R, n, seed=seed)
-    x, y = synth.make_inputs(B, D, R, seed=1234)
+    x, y = synth.make_inputs(B, D, R, seed=xseed)   # kink-free seed chosen by make_golden.py
     dz, dld = synth.make_cotangents(B, D, seed=4321)
     return dict(D=D, C=C, R=R, n=n, B=B), sd, x, y, dz, dld, g
 
