@@ -144,6 +144,12 @@ NF_API int nf_plu_build(const float* s, const float* U, const float* L, const fl
                  int32_t D, float* W, float* W_inv, float* logdet, void* workspace, int64_t ws_bytes,
                  void* stream);
 
+/* One conditioner Linear  C (M,N) = A (M,K) @ W (N,K)^T + bias  (torch_fcnf.py:75-77; nn.Linear weight
+ * layout).  Row pitches lda/ldw/ldc in floats.  engine: NF_PREC_FP32_SIMT (FFMA), NF_PREC_TF32X3 (tcgen05,
+ * fp32 parity), 3 = tcgen05 single TF32 pass, 4 = tcgen05 3xTF32 feeding raw fp32 as the hi operand. */
+NF_API int nf_linear(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, float* C,
+                     int64_t ldc, int64_t M, int32_t N, int32_t K, int32_t engine, void* stream);
+
 /* Number of kernels this library launched on the calling thread since the last reset
  * (bench.py's gpu_launches). */
 NF_API int64_t nf_launch_count(int reset);

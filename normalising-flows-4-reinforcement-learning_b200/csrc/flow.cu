@@ -6,6 +6,7 @@
 #include "common.cuh"
 #include "elementwise.cuh"
 #include "simt_gemm.cuh"
+#include "tc_gemm.cuh"
 
 namespace nf {
 
@@ -628,6 +629,26 @@ int nf_flow_backward(const NfFlowDesc* desc, const float* params, const void* pa
     NF_TRY(unfold_grads(params, pl, m, dparams, st));
   }
   return 0;
+}
+
+int nf_linear(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, float* C, int64_t ldc,
+              int64_t M, int32_t N, int32_t K, int32_t engine, void* stream) {
+  NF_CHECK_ARG(M >= 0 && N >= 1 && K >= 1 && M < (int64_t(1) << 30), NF_E_BADARG, "bad shape M=%lld N=%d K=%d",
+               (long long)M, N, K);
+  NF_CHECK_ARG(lda >= K && ldw >= K && ldc >= N, NF_E_BADARG, "row pitch smaller than the row");
+  NF_TRY(check_ptr(A, "A", true)); NF_TRY(check_ptr(W, "W", true)); NF_TRY(check_ptr(C, "C", true));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (engine == NF_PREC_FP32_SIMT) {
+    GemmP g;
+    g.A0 = A; g.lda0 = (int)lda; g.K0 = K; g.B0 = W; g.ldb0 = (int)ldw; g.transB = 1;
+    g.C = C; g.ldc = (int)ldc; g.bias = bias; g.M = (int)M; g.N = N;
+    return simt_gemm(g, st);
+  }
+  NF_CHECK_ARG(engine == NF_PREC_TF32X3 || engine == 3 || engine == 4, NF_E_UNSUPPORTED, "unknown engine %d", engine);
+  TcGemmP t;
+  t.A0 = A; t.lda0 = lda; t.K0 = K; t.B0 = W; t.ldb0 = ldw; t.C = C; t.ldc = ldc; t.bias = bias;
+  t.M = (int)M; t.N = N; t.passes = engine == 3 ? 1 : 3; t.raw_hi = engine == 4;
+  return tc_gemm(t, st);
 }
 
 int nf_affine_logdet_fwd(const float* xp, const float* s, const float* t, const float* bias_s, const float* bias_t,

@@ -1,0 +1,362 @@
+// tcgen05 / TMEM / TMA GEMM for the conditioner layers (sm_100a).  See tc_gemm.cuh.
+//
+// Roles inside one CTA (192 threads), one 128 x BN output tile per CTA:
+//   warp 0      TMA producer: fp32 operand tiles (128 B rows, SWIZZLE_128B) -> shared memory ring
+//   warps 2..5  splitters: hi = cvt.rna.tf32(x) written in place, lo = x - hi written to a twin
+//               buffer (same swizzled positions), then the epilogue (TMEM -> registers -> global)
+//   warp 1      MMA issuer: one thread issues tcgen05.mma kind::tf32 (lo*hi, hi*lo, hi*hi) with
+//               the fp32 accumulator in TMEM; owns tcgen05.alloc/dealloc
+// Pipelines: full[s] (TMA -> splitters), split[s] (splitters -> MMA), empty[s] (MMA commit ->
+// producer), acc (MMA commit -> epilogue).
+#include <cuda.h>
+
+#include "tc_gemm.cuh"
+
+namespace nf {
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 32;  // 32 fp32 = 128 bytes = one swizzle row
+constexpr int A_BYTES = BM * 128;
+constexpr int NTHREADS = 192;
+
+struct KArgs {
+  float* C;
+  const float* bias;
+  int M, N, K0, K1;
+  long long ldc, sC, sBias;
+  int zA0, zA1, zB0, zB1;  // 1: operand is batched over blockIdx.z, 0: shared
+  int accumulate, passes, raw_hi;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must end in a trap (reported as a launch failure), never a hang.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  for (uint32_t spins = 0; !mbar_try(bar, parity); ++spins) {
+    if (spins > (1u << 24)) {
+      printf("nf_b200 tc_gemm: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y,
+             blockIdx.z, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+// K-major SWIZZLE_128B operand descriptor: rows of 128 B, 8-row groups 1024 B apart (SBO),
+// descriptor version 1 (Blackwell), layout type 2 (cute::UMMA::LayoutType::SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;             // LBO (unused for swizzled K-major), 16 B units
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;     // SBO
+  d |= static_cast<uint64_t>(1) << 46;             // version
+  d |= static_cast<uint64_t>(2) << 61;             // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float rna_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+template <int BN, int STAGES>
+struct Smem {
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int HALF = A_BYTES + B_BYTES;   // raw/hi tiles; the lo twins follow
+  static constexpr int STAGE = 2 * HALF;
+  static constexpr int BARS = STAGES * STAGE;      // byte offset of the barrier block
+  static constexpr int TOTAL = BARS + 256 + 1024;  // + alignment slack
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUtensorMap mA1,
+          const __grid_constant__ CUtensorMap mB0, const __grid_constant__ CUtensorMap mB1, const KArgs a) {
+  using S = Smem<BN, STAGES>;
+  extern __shared__ uint8_t smem_dyn[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::BARS);
+  uint64_t* full = bars;
+  uint64_t* split = bars + STAGES;
+  uint64_t* empty = bars + 2 * STAGES;
+  uint64_t* accbar = bars + 3 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN, z = blockIdx.z;
+  const int nk0 = (a.K0 + BK - 1) / BK, nk1 = (a.K1 + BK - 1) / BK, nk = nk0 + nk1;
+  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&mA0); prefetch_tmap(&mB0);
+    if (nk1) { prefetch_tmap(&mA1); prefetch_tmap(&mB1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&split[s], 4); mbar_init(&empty[s], 1); }
+    mbar_init(accbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      for (int it = 0; it < nk; ++it) {
+        const int s = it % STAGES, use = it / STAGES;
+        mbar_wait(&empty[s], (use & 1) ^ 1);
+        mbar_expect_tx(&full[s], S::HALF);
+        uint8_t* st = smem + s * S::STAGE;
+        const bool seg1 = it >= nk0;
+        const int kk = (seg1 ? it - nk0 : it) * BK;
+        tma_load_3d(st, seg1 ? &mA1 : &mA0, &full[s], kk, m0, (seg1 ? a.zA1 : a.zA0) ? z : 0);
+        tma_load_3d(st + A_BYTES, seg1 ? &mB1 : &mB0, &full[s], kk, n0, (seg1 ? a.zB1 : a.zB0) ? z : 0);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      // kind::tf32, fp32 accumulate, K-major A and B, M = 128, N = BN  (cute::UMMA::InstrDescriptor)
+      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(BN >> 3) << 17) | (uint32_t(BM >> 4) << 24);
+      uint32_t acc = 0;
+      for (int it = 0; it < nk; ++it) {
+        const int s = it % STAGES, use = it / STAGES;
+        mbar_wait(&split[s], use & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = smem_u32(smem + s * S::STAGE);
+        const uint64_t a_hi = make_sdesc(sa), b_hi = make_sdesc(sa + A_BYTES);
+        const uint64_t a_lo = make_sdesc(sa + S::HALF), b_lo = make_sdesc(sa + S::HALF + A_BYTES);
+        const bool seg1 = it >= nk0;
+        const int kleft = (seg1 ? a.K1 - (it - nk0) * BK : a.K0 - it * BK);
+        const int nks = kleft >= BK ? BK / 8 : (kleft + 7) / 8;
+        for (int ks = 0; ks < nks; ++ks) {
+          const uint64_t adv = static_cast<uint64_t>(ks * 2);   // 8 fp32 = 32 B = 2 x 16 B units
+          if (a.passes == 3) {
+            umma_tf32(tmem_base, a_lo + adv, b_hi + adv, idesc, acc); acc = 1;
+            umma_tf32(tmem_base, a_hi + adv, b_lo + adv, idesc, acc);
+          }
+          umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, acc); acc = 1;
+        }
+        umma_commit(&empty[s]);   // frees the stage once the MMAs above have read it
+      }
+      umma_commit(accbar);        // accumulator complete
+    }
+  } else {
+    // ------------------------------------------------------------------ splitters, then epilogue
+    const int t = threadIdx.x - 64;  // 0..127
+    for (int it = 0; it < nk; ++it) {
+      const int s = it % STAGES, use = it / STAGES;
+      mbar_wait(&full[s], use & 1);
+      float4* raw = reinterpret_cast<float4*>(smem + s * S::STAGE);
+      float4* lo = reinterpret_cast<float4*>(smem + s * S::STAGE + S::HALF);
+#pragma unroll 4
+      for (int i = t; i < S::HALF / 16; i += 128) {
+        const float4 v = raw[i];
+        float4 h, l;
+        if (a.raw_hi) {
+          h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+          h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+        } else {
+          h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
+          raw[i] = h;
+        }
+        l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+        lo[i] = l;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> UMMA reads
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&split[s]);
+    }
+    // epilogue: this warp may only touch TMEM lanes 32*(warp%4) .. +31; thread = one output row
+    mbar_wait(accbar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int q = warp & 3;
+    const int row = m0 + q * 32 + lane;
+    float* crow = a.C + (long long)z * a.sC + (long long)row * a.ldc;
+    const float* bias = a.bias ? a.bias + (long long)z * a.sBias : nullptr;
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (n0 + c0 >= a.N) break;   // warp-uniform
+      uint32_t r[32];
+      tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c0), r);
+      if (row < a.M) {
+        const int cbase = n0 + c0;
+        if (cbase + 32 <= a.N && (a.ldc & 3) == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                   __uint_as_float(r[j + 3]));
+            if (bias) { v.x += bias[cbase + j]; v.y += bias[cbase + j + 1]; v.z += bias[cbase + j + 2]; v.w += bias[cbase + j + 3]; }
+            float4* dst = reinterpret_cast<float4*>(crow + cbase + j);
+            if (a.accumulate) { const float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+            *dst = v;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (cbase + j < a.N) {
+              float v = __uint_as_float(r[j]) + (bias ? bias[cbase + j] : 0.f);
+              if (a.accumulate) v += crow[cbase + j];
+              crow[cbase + j] = v;
+            }
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: tensor maps
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// fp32 K-major matrix (rows x K, row pitch `ld` floats), optionally batched; box = 32 x box_rows x 1
+int make_map(CUtensorMap* map, const float* base, long long K, long long rows, long long ld, long long batch,
+             long long bstride, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  NF_CHECK_ARG(fn != nullptr, NF_E_UNSUPPORTED, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)(bstride ? batch : 1)};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)(bstride ? bstride : ld * rows) * 4};
+  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  NF_CHECK_ARG(r == CUDA_SUCCESS, NF_E_BADARG, "cuTensorMapEncodeTiled failed (%d): K=%lld rows=%lld ld=%lld", (int)r,
+               K, rows, ld);
+  return 0;
+}
+
+bool ok_operand(const float* p, long long ld, long long bstride) {
+  return p && (reinterpret_cast<uintptr_t>(p) & 15u) == 0 && (ld & 3) == 0 && (bstride & 3) == 0;
+}
+
+template <int BN, int STAGES>
+int launch(const TcGemmP& p, cudaStream_t st) {
+  using S = Smem<BN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    NF_CUDA(cudaFuncSetAttribute(k_tc_gemm<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    configured = true;
+  }
+  CUtensorMap mA0, mA1, mB0, mB1;
+  int r;
+  if ((r = make_map(&mA0, p.A0, p.K0, p.M, p.lda0, p.batch, p.sA0, BM))) return r;
+  if ((r = make_map(&mB0, p.B0, p.K0, p.N, p.ldb0, p.batch, p.sB0, BN))) return r;
+  if (p.K1 > 0) {
+    if ((r = make_map(&mA1, p.A1, p.K1, p.M, p.lda1, p.batch, p.sA1, BM))) return r;
+    if ((r = make_map(&mB1, p.B1, p.K1, p.N, p.ldb1, p.batch, p.sB1, BN))) return r;
+  } else {
+    mA1 = mA0; mB1 = mB0;
+  }
+  KArgs a;
+  a.C = p.C; a.bias = p.bias; a.M = p.M; a.N = p.N; a.K0 = p.K0; a.K1 = p.K1;
+  a.ldc = p.ldc; a.sC = p.sC; a.sBias = p.sBias;
+  a.zA0 = p.sA0 != 0; a.zA1 = p.sA1 != 0; a.zB0 = p.sB0 != 0; a.zB1 = p.sB1 != 0;
+  a.accumulate = p.accumulate; a.passes = p.passes; a.raw_hi = p.raw_hi;
+  dim3 grid((unsigned)cdiv(p.M, BM), (unsigned)cdiv(p.N, BN), (unsigned)p.batch);
+  k_tc_gemm<BN, STAGES><<<grid, NTHREADS, S::TOTAL, st>>>(mA0, mA1, mB0, mB1, a);
+  NF_LAUNCHED();
+  return 0;
+}
+
+}  // namespace
+
+bool tc_gemm_supported(const TcGemmP& p) {
+  if (p.M <= 0 || p.N <= 0 || p.K0 <= 0 || p.batch <= 0 || p.batch > 65535) return false;
+  if (!ok_operand(p.A0, p.lda0, p.sA0) || !ok_operand(p.B0, p.ldb0, p.sB0)) return false;
+  if (p.K1 > 0 && (!ok_operand(p.A1, p.lda1, p.sA1) || !ok_operand(p.B1, p.ldb1, p.sB1))) return false;
+  if (!p.C || cdiv(p.N, 64) > 65535) return false;
+  return encode_fn() != nullptr;
+}
+
+int tc_gemm(const TcGemmP& p, cudaStream_t st) {
+  if (p.M <= 0 || p.N <= 0 || p.batch <= 0) return 0;
+  NF_CHECK_ARG(tc_gemm_supported(p), NF_E_UNSUPPORTED,
+               "tc_gemm: operands must be 16-byte aligned with row pitches that are multiples of 4 floats");
+  if (p.N > 128) return launch<256, 2>(p, st);
+  if (p.N > 64) return launch<128, 3>(p, st);
+  return launch<64, 4>(p, st);
+}
+
+}  // namespace nf

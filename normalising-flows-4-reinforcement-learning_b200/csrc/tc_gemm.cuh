@@ -1,0 +1,32 @@
+// tcgen05 (5th-gen tensor core) GEMM for the conditioner layers, sm_100a only.
+//
+//   C[z][m, n] (+)= sum_k A[z][m, k] * B[z][n, k]   (+ bias[z][n])
+//
+// Both operands are K-major fp32 in global memory.  fp32 parity is obtained with the 3xTF32
+// split: every operand tile is split inside the kernel into hi = rna_tf32(x) and lo = x - hi and
+// three kind::tf32 MMAs (lo*hi, hi*lo, hi*hi) accumulate in fp32 in TMEM.
+#pragma once
+#include "common.cuh"
+
+namespace nf {
+
+struct TcGemmP {
+  // K-major operands; the reduction may be two segments (A0|A1) x (B0|B1)
+  const float* A0 = nullptr; const float* A1 = nullptr;
+  const float* B0 = nullptr; const float* B1 = nullptr;
+  float* C = nullptr;
+  const float* bias = nullptr;
+  int M = 0, N = 0, K0 = 0, K1 = 0;
+  long long lda0 = 0, lda1 = 0, ldb0 = 0, ldb1 = 0, ldc = 0;     // row pitches in floats (multiples of 4)
+  long long sA0 = 0, sA1 = 0, sB0 = 0, sB1 = 0, sC = 0, sBias = 0;  // batch strides in floats (0 = shared)
+  int batch = 1;
+  int accumulate = 0;
+  int passes = 3;       // 3 = 3xTF32 (fp32 parity), 1 = single TF32 pass
+  int raw_hi = 0;       // experiment: feed the raw fp32 tile as the hi operand (hardware truncation)
+};
+
+// returns 0, or NF_E_UNSUPPORTED when the shape/alignment cannot be handled by TMA (caller decides)
+int tc_gemm(const TcGemmP& p, cudaStream_t st);
+bool tc_gemm_supported(const TcGemmP& p);
+
+}  // namespace nf
