@@ -150,6 +150,12 @@ NF_API int nf_plu_build(const float* s, const float* U, const float* L, const fl
 NF_API int nf_linear(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, float* C,
                      int64_t ldc, int64_t M, int32_t N, int32_t K, int32_t engine, void* stream);
 
+/* Weight gradient of one Linear: dW (n_out, n_in) += dY (B, n_out)^T @ X (B, n_in); the reduction runs over
+ * the batch rows (what autograd computes for nn.Linear.weight, torch_fcnf.py:75-77).  engine as nf_linear
+ * (0 = FFMA, 1 = tcgen05 3xTF32, 3 = single TF32 pass). */
+NF_API int nf_linear_wgrad(const float* dY, int64_t lddy, const float* X, int64_t ldx, float* dW, int64_t lddw,
+                           int64_t B, int32_t n_out, int32_t n_in, int32_t engine, void* stream);
+
 /* Number of kernels this library launched on the calling thread since the last reset
  * (bench.py's gpu_launches). */
 NF_API int64_t nf_launch_count(int reset);

@@ -58,6 +58,7 @@ def _load():
         "nf_affine_logdet_bwd": (c_int, [fp, fp, fp, fp, i64, c_int32, fp, fp, fp, vp]),
         "nf_plu_build": (c_int, [fp, fp, fp, fp, fp, c_int32, fp, fp, fp, vp, i64, vp]),
         "nf_linear": (c_int, [fp, i64, fp, i64, fp, fp, i64, i64, c_int32, c_int32, c_int32, vp]),
+        "nf_linear_wgrad": (c_int, [fp, i64, fp, i64, fp, i64, i64, c_int32, c_int32, c_int32, vp]),
         "nf_launch_count": (c_int64, [c_int]),
     }
     for name, (res, args) in sigs.items():

@@ -62,12 +62,14 @@ void param_layout(const Dims& m, NfParamLayout* out);
 
 // ---- packed (derived) parameter tables -----------------------------------------------------
 // Per block:  W (D*D), Winv (D*D), Lh (D*D), Uh (D*D), PL (D*D) [= P @ Lh], then per net (t, s):
-//             W2f (C*H1), b2f (C), W3f (dt*C), b3f (dt).
+//             W2f (C*H1), b2f (C), W3f (dt*C), b3f (dt), W2fT (H1*C), W1T (K1*H1), W1p (H1*K1p)
+//             (the transposes are the K-major B operands of the data-gradient GEMMs).
 // After all blocks: logdet_c (n floats, sum log|s| per block) and logdet_total (1 float).
 struct PackedLayout {
   int64_t W, Winv, Lh, Uh, PL;
   int64_t net0;          // offset of net t tables inside a block
-  int64_t W2f, b2f, W3f, b3f;  // offsets inside a net
+  int64_t W2f, b2f, W3f, b3f, W2fT, W1T, W1p;  // offsets inside a net
+  int dcp, K1p;  // W1p: (H1, K1p) copy of W1 whose y columns start at the 16-byte aligned column dcp
   int64_t net_stride, block_stride;
   int64_t logdet_c, logdet_total, total;
 };

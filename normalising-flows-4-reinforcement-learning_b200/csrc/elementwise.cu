@@ -120,13 +120,13 @@ template <int VEC, bool INVERSE>
 __global__ void __launch_bounds__(256) k_affine_rowthread(const float* __restrict__ in, const float* __restrict__ s,
                                                           const float* __restrict__ t, const float* __restrict__ bs,
                                                           const float* __restrict__ bt, const float* cdev, float chost,
-                                                          long long B, int D, float* __restrict__ out,
+                                                          long long B, int D, int ldi, int ldo, float* __restrict__ out,
                                                           float* __restrict__ logdet, float* __restrict__ s_out) {
   const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= B) return;
   const int dc = (D + 1) / 2, dt = D / 2;
-  const float* xi = in + row * D;
-  float* xo = out + row * D;
+  const float* xi = in + row * ldi;
+  float* xo = out + row * ldo;
   const float* sr = s + row * dt;
   const float* tr = t + row * dt;
   float ssum = 0.f;
@@ -171,14 +171,14 @@ template <bool INVERSE>
 __global__ void __launch_bounds__(256) k_affine_rowwarp(const float* __restrict__ in, const float* __restrict__ s,
                                                         const float* __restrict__ t, const float* __restrict__ bs,
                                                         const float* __restrict__ bt, const float* cdev, float chost,
-                                                        long long B, int D, float* __restrict__ out,
+                                                        long long B, int D, int ldi, int ldo, float* __restrict__ out,
                                                         float* __restrict__ logdet, float* __restrict__ s_out) {
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= B) return;
   const int dc = (D + 1) / 2, dt = D / 2;
-  const float* xi = in + row * D;
-  float* xo = out + row * D;
+  const float* xi = in + row * ldi;
+  float* xo = out + row * ldo;
   for (int j = lane; j < dc; j += 32) xo[j] = xi[j];
   float ssum = 0.f;
   for (int j = lane; j < dt; j += 32) {
@@ -333,6 +333,21 @@ __global__ void k_fold(const float* params, NfParamLayout pl, Dims m, float* pac
   if (lane == 0) bf[r] = bias[r] + acc;
 }
 
+// W1p[r][c] = W1[r][c] for the x_cond columns c < dc, W1p[r][dcp + j] = W1[r][dc + j] for the y
+// columns, zero elsewhere.
+__global__ void k_pack_w1(const float* params, NfParamLayout pl, Dims m, float* packed, PackedLayout kl) {
+  const int b = blockIdx.z, net = blockIdx.y, r = blockIdx.x;
+  const float* W = params + (long long)b * pl.block_stride + net * pl.net_stride + pl.slot_off[NF_P_W1] +
+                   (long long)r * m.K1;
+  float* Wp = packed + (long long)b * kl.block_stride + kl.net0 + net * kl.net_stride + kl.W1p + (long long)r * kl.K1p;
+  for (int c = threadIdx.x; c < kl.K1p; c += blockDim.x) {
+    float v = 0.f;
+    if (c < m.dc) v = W[c];
+    else if (c >= kl.dcp && c - kl.dcp < m.R) v = W[m.dc + c - kl.dcp];
+    Wp[c] = v;
+  }
+}
+
 // Inverse of the folding for gradients (in place on the gradient arena):
 //   slot W{2,3} holds G = du^T x_hat, slot b{2,3} holds g = colsum(du)
 //   dW[n,k] = G[n,k] gamma[k] + g[n] beta[k];  dgamma[k] = sum_n G[n,k] W[n,k];  dbeta[k] = sum_n g[n] W[n,k]
@@ -401,6 +416,33 @@ __global__ void k_axpy(float* dst, const float* src, long long n) {
     dst[i] += src[i];
 }
 
+__global__ void k_copy2d(float* dst, long long ldd, const float* src, long long lds, long long rows, int cols) {
+  const long long total = rows * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols;
+    const int c = (int)(i - r * cols);
+    dst[r * ldd + c] = src[r * lds + c];
+  }
+}
+
+__global__ void k_transpose2d(float* dst, long long ldd, long long sd0, long long sd1, const float* src, long long lds,
+                              long long ss0, long long ss1, int rows, int cols, int batch0) {
+  __shared__ float tile[32][33];
+  const int b0 = blockIdx.z % batch0, b1 = blockIdx.z / batch0;
+  const float* s = src + b0 * ss0 + b1 * ss1;
+  float* d = dst + b0 * sd0 + b1 * sd1;
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? s[(long long)r * lds + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) d[(long long)c * ldd + r] = tile[threadIdx.x][i];
+  }
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
@@ -423,31 +465,34 @@ int ln_lrelu_bwd(const LnBwdP& p, cudaStream_t st) {
 }
 
 template <bool INV>
-static int affine_launch(const float* in, const float* s, const float* t, const float* bs, const float* bt,
-                         const float* cdev, float chost, long long B, int D, float* out, float* logdet, float* s_out,
-                         cudaStream_t st) {
+static int affine_launch(const float* in, int ldi, const float* s, const float* t, const float* bs, const float* bt,
+                         const float* cdev, float chost, long long B, int D, float* out, int ldo, float* logdet,
+                         float* s_out, cudaStream_t st) {
   if (B <= 0) return 0;
   if (D <= 64) {
-    const bool vec = (D % 8 == 0);
+    const bool vec = (D % 8 == 0) && (ldi % 4 == 0) && (ldo % 4 == 0);
     dim3 grid((unsigned)cdiv(B, 256));
-    if (vec) k_affine_rowthread<4, INV><<<grid, 256, 0, st>>>(in, s, t, bs, bt, cdev, chost, B, D, out, logdet, s_out);
-    else k_affine_rowthread<1, INV><<<grid, 256, 0, st>>>(in, s, t, bs, bt, cdev, chost, B, D, out, logdet, s_out);
+    if (vec)
+      k_affine_rowthread<4, INV><<<grid, 256, 0, st>>>(in, s, t, bs, bt, cdev, chost, B, D, ldi, ldo, out, logdet, s_out);
+    else
+      k_affine_rowthread<1, INV><<<grid, 256, 0, st>>>(in, s, t, bs, bt, cdev, chost, B, D, ldi, ldo, out, logdet, s_out);
   } else {
     dim3 grid((unsigned)cdiv(B, 8));
-    k_affine_rowwarp<INV><<<grid, 256, 0, st>>>(in, s, t, bs, bt, cdev, chost, B, D, out, logdet, s_out);
+    k_affine_rowwarp<INV><<<grid, 256, 0, st>>>(in, s, t, bs, bt, cdev, chost, B, D, ldi, ldo, out, logdet, s_out);
   }
   NF_LAUNCHED();
   return 0;
 }
 
-int affine_fwd(const float* xp, const float* s, const float* t, const float* bias_s, const float* bias_t,
-               const float* cdev, float chost, long long B, int D, float* z, float* logdet, float* s_out,
+int affine_fwd(const float* xp, int ld_in, const float* s, const float* t, const float* bias_s, const float* bias_t,
+               const float* cdev, float chost, long long B, int D, float* z, int ld_out, float* logdet, float* s_out,
                cudaStream_t st) {
-  return affine_launch<false>(xp, s, t, bias_s, bias_t, cdev, chost, B, D, z, logdet, s_out, st);
+  return affine_launch<false>(xp, ld_in, s, t, bias_s, bias_t, cdev, chost, B, D, z, ld_out, logdet, s_out, st);
 }
-int affine_inv(const float* z, const float* s, const float* t, const float* bias_s, const float* bias_t,
-               const float* cdev, float chost, long long B, int D, float* xp, float* logdet, cudaStream_t st) {
-  return affine_launch<true>(z, s, t, bias_s, bias_t, cdev, chost, B, D, xp, logdet, nullptr, st);
+int affine_inv(const float* z, int ld_in, const float* s, const float* t, const float* bias_s, const float* bias_t,
+               const float* cdev, float chost, long long B, int D, float* xp, int ld_out, float* logdet,
+               cudaStream_t st) {
+  return affine_launch<true>(z, ld_in, s, t, bias_s, bias_t, cdev, chost, B, D, xp, ld_out, logdet, nullptr, st);
 }
 
 int affine_bwd(const float* dz, const float* z, const float* s_full, const float* dlogdet, long long B, int D,
@@ -489,6 +534,14 @@ int fold_ln_affine(const float* params, const NfParamLayout& pl, const Dims& m, 
   return 0;
 }
 
+int pack_w1(const float* params, const NfParamLayout& pl, const Dims& m, float* packed, const PackedLayout& kl,
+            cudaStream_t st) {
+  dim3 grid((unsigned)m.H1, 2, (unsigned)m.n);
+  k_pack_w1<<<grid, 128, 0, st>>>(params, pl, m, packed, kl);
+  NF_LAUNCHED();
+  return 0;
+}
+
 int unfold_grads(const float* params, const NfParamLayout& pl, const Dims& m, float* dparams, cudaStream_t st) {
   const int K = m.H1 > m.C ? m.H1 : m.C;
   dim3 grid((unsigned)cdiv(K, 128), 2, (unsigned)m.n);
@@ -518,6 +571,24 @@ int sum_vector(const float* v, long long n, float* out, cudaStream_t st) {
 int fill_zero(float* p, long long n, cudaStream_t st) {
   if (n <= 0) return 0;
   NF_CUDA(cudaMemsetAsync(p, 0, n * sizeof(float), st));
+  return 0;
+}
+
+int copy2d(float* dst, long long ldd, const float* src, long long lds, long long rows, int cols, cudaStream_t st) {
+  if (rows <= 0 || cols <= 0) return 0;
+  long long blocks = cdiv(rows * cols, 256 * 4);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k_copy2d<<<(unsigned)blocks, 256, 0, st>>>(dst, ldd, src, lds, rows, cols);
+  NF_LAUNCHED();
+  return 0;
+}
+
+int transpose2d(float* dst, long long ldd, long long sdst0, long long sdst1, const float* src, long long lds,
+                long long ssrc0, long long ssrc1, int rows, int cols, int batch0, int batch1, cudaStream_t st) {
+  if (rows <= 0 || cols <= 0) return 0;
+  dim3 grid((unsigned)cdiv(cols, 32), (unsigned)cdiv(rows, 32), (unsigned)(batch0 * batch1));
+  k_transpose2d<<<grid, dim3(32, 8), 0, st>>>(dst, ldd, sdst0, sdst1, src, lds, ssrc0, ssrc1, rows, cols, batch0);
+  NF_LAUNCHED();
   return 0;
 }
 

@@ -31,12 +31,13 @@ struct LnBwdP {
 };
 int ln_lrelu_bwd(const LnBwdP& p, cudaStream_t st);
 
-int affine_fwd(const float* xp, const float* s, const float* t, const float* bias_s, const float* bias_t,
+// ld_in / ld_out: row pitches (floats) of the (B,D) input and output
+int affine_fwd(const float* xp, int ld_in, const float* s, const float* t, const float* bias_s, const float* bias_t,
                const float* logdet_const_dev, float logdet_const_host, long long B, int D,
-               float* z, float* logdet, float* s_out, cudaStream_t st);
-int affine_inv(const float* z, const float* s, const float* t, const float* bias_s, const float* bias_t,
+               float* z, int ld_out, float* logdet, float* s_out, cudaStream_t st);
+int affine_inv(const float* z, int ld_in, const float* s, const float* t, const float* bias_s, const float* bias_t,
                const float* logdet_const_dev, float logdet_const_host, long long B, int D,
-               float* xp, float* logdet, cudaStream_t st);
+               float* xp, int ld_out, float* logdet, cudaStream_t st);
 // ds/dt are (B,dt) each; g3s/g3t (dt) receive column sums of ds/dt (atomic), may be null.
 int affine_bwd(const float* dz, const float* z, const float* s_full, const float* dlogdet, long long B, int D,
                float* dxp, float* ds, float* dt, float* g3s, float* g3t, cudaStream_t st);
@@ -48,11 +49,17 @@ int plu_tri_inverse(const float* packed, const PackedLayout& kl, const Dims& m, 
                     cudaStream_t st);
 int fold_ln_affine(const float* params, const NfParamLayout& pl, const Dims& m, float* packed,
                    const PackedLayout& kl, cudaStream_t st);
+int pack_w1(const float* params, const NfParamLayout& pl, const Dims& m, float* packed, const PackedLayout& kl,
+            cudaStream_t st);
 int unfold_grads(const float* params, const NfParamLayout& pl, const Dims& m, float* dparams, cudaStream_t st);
 int plu_grad_finish(const float* params, const NfParamLayout& pl, const Dims& m, const float* dLh,
                     const float* dUh, const float* sum_dld, float* dparams, cudaStream_t st);
 int sum_vector(const float* v, long long n, float* out, cudaStream_t st);  // out[0] = sum(v)
 int fill_zero(float* p, long long n, cudaStream_t st);
 int axpy_rows(float* dst, const float* src, long long n, cudaStream_t st);  // dst += src
+int copy2d(float* dst, long long ldd, const float* src, long long lds, long long rows, int cols, cudaStream_t st);
+// dst[b][c][r] = src[b][r][c]  (rows x cols -> cols x rows), batched with strides in floats
+int transpose2d(float* dst, long long ldd, long long sdst0, long long sdst1, const float* src, long long lds,
+                long long ssrc0, long long ssrc1, int rows, int cols, int batch0, int batch1, cudaStream_t st);
 
 }  // namespace nf

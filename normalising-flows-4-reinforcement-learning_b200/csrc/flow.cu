@@ -75,6 +75,11 @@ PackedLayout packed_layout(const Dims& m) {
   k.b2f = n; n += pad4(m.C);
   k.W3f = n; n += pad4((int64_t)m.dt * m.C);
   k.b3f = n; n += pad4(m.dt);
+  k.W2fT = n; n += pad4((int64_t)m.H1 * m.C);
+  k.W1T = n; n += pad4((int64_t)m.K1 * m.H1);
+  k.dcp = (int)pad4(m.dc);
+  k.K1p = (int)pad4(k.dcp + m.R);
+  k.W1p = n; n += pad4((int64_t)m.H1 * k.K1p);
   k.net_stride = n;
   off += 2 * n;
   k.block_stride = off;
@@ -119,18 +124,19 @@ struct Carver {
   }
 };
 
-struct FwdWs { float *xp, *u, *o, *xh1, *xh2, *pp0, *pp1; int64_t total; };
+struct FwdWs { float *xp, *u, *o, *xh1, *xh2, *pp0, *pp1; int64_t total; int Dp; };
 static FwdWs carve_fwd(const Dims& m, int64_t B, void* ws) {
   Carver c(ws);
   FwdWs w;
   const int64_t Hm = std::max(m.H1, m.C);
-  w.xp = c.take(B * m.D);
+  w.Dp = (int)pad4(m.D);   // internal (B,D) buffers use a 16-byte row pitch so TMA can read x_cond
+  w.xp = c.take(B * w.Dp);
   w.u = c.take(2 * B * Hm);
   w.o = c.take(2 * B * m.dt);
   w.xh1 = c.take(2 * B * m.H1);
   w.xh2 = c.take(2 * B * m.C);
-  w.pp0 = c.take(B * m.D);
-  w.pp1 = c.take(B * m.D);
+  w.pp0 = c.take(B * w.Dp);
+  w.pp1 = c.take(B * w.Dp);
   w.total = c.off;
   return w;
 }
@@ -182,25 +188,53 @@ static int check_ptr(const void* p, const char* name, bool required) {
     if (_r != 0) return _r;     \
   } while (0)
 
+// C[z] (M,N) (+)= [A0 | A1][z] (M,K0+K1) @ [B0 | B1][z] (N,K0+K1)^T : the Linear layers and their data
+// gradients.  precision 1 (3xTF32) runs on tcgen05 when the tile shapes make sense and TMA can
+// address the operands; everything else (tiny N or K, odd pitches) is exact-fp32 FFMA.
+static int linear_nt(int prec, const TcGemmP& t, cudaStream_t st) {
+  if (prec == NF_PREC_TF32X3 && t.N >= 32 && (t.K0 + t.K1) >= 32 && tc_gemm_supported(t)) return tc_gemm(t, st);
+  GemmP g;
+  g.A0 = t.A0; g.A1 = t.A1; g.B0 = t.B0; g.B1 = t.B1; g.C = t.C; g.bias = t.bias;
+  g.M = t.M; g.N = t.N; g.K0 = t.K0; g.K1 = t.K1;
+  g.lda0 = (int)t.lda0; g.lda1 = (int)t.lda1; g.ldb0 = (int)t.ldb0; g.ldb1 = (int)t.ldb1; g.ldc = (int)t.ldc;
+  g.sA0 = t.sA0; g.sA1 = t.sA1; g.sB0 = t.sB0; g.sB1 = t.sB1; g.sC = t.sC; g.sBias = t.sBias;
+  g.batch = t.batch; g.transB = 1; g.accumulate = t.accumulate;
+  return simt_gemm(g, st);
+}
+
+// C[z] (M,N) += A[z] (K,M)^T @ B[z] (K,N): weight gradients (reduction over the K = batch rows).
+// C must already hold the base value (the gradient arena is zero-filled first).
+static int wgrad_tn(int prec, const TcGemmTnP& t, cudaStream_t st) {
+  if (prec == NF_PREC_TF32X3 && t.M >= 32 && t.N >= 32 && tc_gemm_tn_supported(t)) return tc_gemm_tn(t, st);
+  GemmP g;
+  g.transA = 1; g.A0 = t.A; g.lda0 = (int)t.lda; g.sA0 = t.sA; g.K0 = (int)t.K;
+  g.B0 = t.B; g.ldb0 = (int)t.ldb; g.sB0 = t.sB;
+  g.C = t.C; g.ldc = (int)t.ldc; g.sC = t.sC;
+  g.M = t.M; g.N = t.N; g.batch = t.batch;
+  g.splitk = pick_splitk(g.M, g.N, t.K, t.batch);
+  if (g.splitk == 1) g.accumulate = 1;
+  return simt_gemm(g, st);
+}
+
 // The two conditioner MLPs (net 0 = t, net 1 = s) up to the last Linear's raw output o (2,B,dt):
 //   u1 = [x_cond | y] W1^T -> LeakyReLU -> LN -> x_hat1 -> W2f -> LeakyReLU -> LN -> x_hat2 -> W3f
-// (torch_fcnf.py:74-78, :85-89, :99-100).  `xc` holds x_cond in its first dc columns (row stride D).
+// (torch_fcnf.py:74-78, :85-89, :99-100).  `xc` holds x_cond in its first dc columns (row pitch ldxc).
 static int conditioners(const Dims& m, const NfParamLayout& pl, const PackedLayout& kl, const float* pb,
-                        const float* kb, const float* xc, const float* y, int64_t B, const FwdWs& w,
+                        const float* kb, const float* xc, int ldxc, const float* y, int64_t B, const FwdWs& w,
                         float* xh1, int64_t xh1_net, float* xh2, int64_t xh2_net, float* r1, float* r2,
                         int64_t r_net, uint32_t* m1, uint32_t* m2, int64_t m_net, int mw1, int mw2,
                         cudaStream_t st) {
   const int64_t Hm = std::max(m.H1, m.C);
   {  // u1
-    GemmP g;
-    g.A0 = xc; g.lda0 = m.D; g.K0 = m.dc;
-    g.A1 = y; g.lda1 = m.R; g.K1 = m.R;
-    g.B0 = pb + pl.slot_off[NF_P_W1]; g.ldb0 = m.K1; g.sB0 = pl.net_stride;
-    g.B1 = g.B0 + m.dc; g.ldb1 = m.K1; g.sB1 = pl.net_stride;
-    g.transB = 1;
+    TcGemmP g;
+    g.A0 = xc; g.lda0 = ldxc; g.K0 = m.dc;
+    if (m.R > 0) { g.A1 = y; g.lda1 = m.R; g.K1 = m.R; }
+    // W1p: W1 with the y columns moved to the 16-byte aligned column dcp (TMA operand)
+    g.B0 = kb + kl.net0 + kl.W1p; g.ldb0 = kl.K1p; g.sB0 = kl.net_stride;
+    if (m.R > 0) { g.B1 = g.B0 + kl.dcp; g.ldb1 = kl.K1p; g.sB1 = kl.net_stride; }
     g.C = w.u; g.ldc = m.H1; g.sC = B * Hm;
     g.M = (int)B; g.N = m.H1; g.batch = 2;
-    NF_TRY(simt_gemm(g, st));
+    NF_TRY(linear_nt(m.prec, g, st));
   }
   {
     LnFwdP p{};
@@ -213,12 +247,12 @@ static int conditioners(const Dims& m, const NfParamLayout& pl, const PackedLayo
     NF_TRY(lrelu_ln_fwd(p, st));
   }
   {  // u2
-    GemmP g;
+    TcGemmP g;
     g.A0 = xh1; g.lda0 = m.H1; g.K0 = m.H1; g.sA0 = xh1_net;
-    g.B0 = kb + kl.net0 + kl.W2f; g.ldb0 = m.H1; g.sB0 = kl.net_stride; g.transB = 1;
+    g.B0 = kb + kl.net0 + kl.W2f; g.ldb0 = m.H1; g.sB0 = kl.net_stride;
     g.C = w.u; g.ldc = m.C; g.sC = B * Hm;
     g.M = (int)B; g.N = m.C; g.batch = 2;
-    NF_TRY(simt_gemm(g, st));
+    NF_TRY(linear_nt(m.prec, g, st));
   }
   {
     LnFwdP p{};
@@ -230,13 +264,13 @@ static int conditioners(const Dims& m, const NfParamLayout& pl, const PackedLayo
     p.N = m.C; p.nets = 2; p.B = B; p.eps = m.eps;
     NF_TRY(lrelu_ln_fwd(p, st));
   }
-  {  // o = x_hat2 W3f^T
-    GemmP g;
+  {  // o = x_hat2 W3f^T  (N = D/2: FFMA unless the flow is wide)
+    TcGemmP g;
     g.A0 = xh2; g.lda0 = m.C; g.K0 = m.C; g.sA0 = xh2_net;
-    g.B0 = kb + kl.net0 + kl.W3f; g.ldb0 = m.C; g.sB0 = kl.net_stride; g.transB = 1;
+    g.B0 = kb + kl.net0 + kl.W3f; g.ldb0 = m.C; g.sB0 = kl.net_stride;
     g.C = w.o; g.ldc = m.dt; g.sC = B * m.dt;
     g.M = (int)B; g.N = m.dt; g.batch = 2;
-    NF_TRY(simt_gemm(g, st));
+    NF_TRY(linear_nt(m.prec, g, st));
   }
   return 0;
 }
@@ -312,6 +346,12 @@ int nf_flow_prepare(const NfFlowDesc* desc, const float* params, void* packed_v,
     NF_TRY(simt_gemm(g, st));
   }
   NF_TRY(fold_ln_affine(params, pl, m, packed, kl, st));
+  // K-major B operands of the data-gradient GEMMs: W2f^T (H1,C) and W1^T (K1,H1), per net and block
+  NF_TRY(transpose2d(packed + kl.net0 + kl.W2fT, m.C, kl.net_stride, kl.block_stride, packed + kl.net0 + kl.W2f,
+                     m.H1, kl.net_stride, kl.block_stride, m.C, m.H1, 2, m.n, st));
+  NF_TRY(transpose2d(packed + kl.net0 + kl.W1T, m.H1, kl.net_stride, kl.block_stride,
+                     params + pl.slot_off[NF_P_W1], m.K1, pl.net_stride, pl.block_stride, m.H1, m.K1, 2, m.n, st));
+  NF_TRY(pack_w1(params, pl, m, packed, kl, st));
   if (what & NF_PREP_INV) {
     NF_TRY(check_ptr(workspace, "workspace", true));
     const PrepWs w = carve_prep(m, workspace);
@@ -373,7 +413,7 @@ int nf_flow_forward(const NfFlowDesc* desc, const float* params, const void* pac
       GemmP g;
       g.A0 = cur; g.lda0 = m.D; g.K0 = m.D;
       g.B0 = kb + kl.W; g.ldb0 = m.D;
-      g.C = w.xp; g.ldc = m.D; g.M = (int)B; g.N = m.D;
+      g.C = w.xp; g.ldc = w.Dp; g.M = (int)B; g.N = m.D;
       NF_TRY(simt_gemm(g, st));
     }
     float *xh1 = w.xh1, *xh2 = w.xh2, *r1 = nullptr, *r2 = nullptr;
@@ -385,15 +425,15 @@ int nf_flow_forward(const NfFlowDesc* desc, const float* params, const void* pac
       m1 = reinterpret_cast<uint32_t*>(sb + sl.m1); m2 = reinterpret_cast<uint32_t*>(sb + sl.m2);
       xh1_net = xh2_net = r_net = m_net = sl.net_stride;
     }
-    NF_TRY(conditioners(m, pl, kl, pb, kb, w.xp, y, B, w, xh1, xh1_net, xh2, xh2_net, r1, r2, r_net, m1, m2, m_net,
-                        sl.mw1, sl.mw2, st));
+    NF_TRY(conditioners(m, pl, kl, pb, kb, w.xp, w.Dp, y, B, w, xh1, xh1_net, xh2, xh2_net, r1, r2, r_net, m1, m2,
+                        m_net, sl.mw1, sl.mw2, st));
     float* next;
     if (stash) next = stash + sl.xs + (int64_t)(i + 1) * BD;
     else if (outputs) next = outputs + (int64_t)i * BD;
     else if (i == m.n - 1) next = z;
-    else next = (i & 1) ? w.pp1 : w.pp0;
-    NF_TRY(affine_fwd(w.xp, w.o + B * m.dt, w.o, kb + kl.net0 + kl.net_stride + kl.b3f, kb + kl.net0 + kl.b3f,
-                      packed + kl.logdet_c + i, 0.f, B, m.D, next, logdet,
+    else next = (i & 1) ? w.pp1 : w.pp0;   // dense (B,D): only the PLU matmul reads it
+    NF_TRY(affine_fwd(w.xp, w.Dp, w.o + B * m.dt, w.o, kb + kl.net0 + kl.net_stride + kl.b3f, kb + kl.net0 + kl.b3f,
+                      packed + kl.logdet_c + i, 0.f, B, m.D, next, m.D, logdet,
                       stash ? stash + sl.ss + (int64_t)i * B * m.dt : nullptr, st));
     cur = next;
   }
@@ -431,29 +471,37 @@ int nf_flow_inverse(const NfFlowDesc* desc, const float* params, const void* pac
 
   if (logdet) NF_CUDA(cudaMemsetAsync(logdet, 0, B * sizeof(float), st));
   if (seq) NF_CUDA(cudaMemcpyAsync(seq, z, BD * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  // running buffer with a 16-byte row pitch (x_cond is a TMA operand of the first Linear)
   const float* cur = z;
+  int ldcur = m.D;
+  if (w.Dp != m.D) {
+    NF_TRY(copy2d(w.pp1, w.Dp, z, m.D, B, m.D, st));
+    cur = w.pp1; ldcur = w.Dp;
+  }
   int step = 0;
   for (int i = m.n - 1; i >= 0; --i, ++step) {
     const float* pb = params + (int64_t)i * pl.block_stride;
     const float* kb = packed + (int64_t)i * kl.block_stride;
-    NF_TRY(conditioners(m, pl, kl, pb, kb, cur, y, B, w, w.xh1, B * m.H1, w.xh2, B * m.C, nullptr, nullptr, 0,
+    NF_TRY(conditioners(m, pl, kl, pb, kb, cur, ldcur, y, B, w, w.xh1, B * m.H1, w.xh2, B * m.C, nullptr, nullptr, 0,
                         nullptr, nullptr, 0, 0, 0, st));
     // affine first (torch_fcnf.py:112-113) ...
-    NF_TRY(affine_inv(cur, w.o + B * m.dt, w.o, kb + kl.net0 + kl.net_stride + kl.b3f, kb + kl.net0 + kl.b3f,
-                      packed + kl.logdet_c + i, 0.f, B, m.D, w.xp, logdet, st));
+    NF_TRY(affine_inv(cur, ldcur, w.o + B * m.dt, w.o, kb + kl.net0 + kl.net_stride + kl.b3f, kb + kl.net0 + kl.b3f,
+                      packed + kl.logdet_c + i, 0.f, B, m.D, w.xp, w.Dp, logdet, st));
     // ... then x = xp @ W^-1 (torch_fcnf.py:115 -> :55)
     float* next;
-    if (seq) next = seq + (int64_t)(step + 1) * BD;
-    else if (i == 0) next = x;
-    else next = (step & 1) ? w.pp1 : w.pp0;
+    int ldnext;
+    if (i == 0 && !seq) { next = x; ldnext = m.D; }
+    else if (seq && w.Dp == m.D) { next = seq + (int64_t)(step + 1) * BD; ldnext = m.D; }
+    else { next = (step & 1) ? w.pp1 : w.pp0; ldnext = w.Dp; }
     GemmP g;
-    g.A0 = w.xp; g.lda0 = m.D; g.K0 = m.D;
+    g.A0 = w.xp; g.lda0 = w.Dp; g.K0 = m.D;
     g.B0 = kb + kl.Winv; g.ldb0 = m.D;
-    g.C = next; g.ldc = m.D; g.M = (int)B; g.N = m.D;
+    g.C = next; g.ldc = ldnext; g.M = (int)B; g.N = m.D;
     NF_TRY(simt_gemm(g, st));
-    cur = next;
+    if (seq && w.Dp != m.D) NF_TRY(copy2d(seq + (int64_t)(step + 1) * BD, m.D, next, ldnext, B, m.D, st));
+    cur = next; ldcur = ldnext;
   }
-  if (cur != x) NF_CUDA(cudaMemcpyAsync(x, cur, BD * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (seq) NF_CUDA(cudaMemcpyAsync(x, seq + (int64_t)m.n * BD, BD * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return 0;
 }
 
@@ -511,12 +559,12 @@ int nf_flow_backward(const NfFlowDesc* desc, const float* params, const void* pa
                       dn ? dn + pl.net_stride + pl.slot_off[NF_P_B3] : nullptr,
                       dn ? dn + pl.slot_off[NF_P_B3] : nullptr, st));
     if (dn) {  // b. G3 = dout^T x_hat2  -> slot W3 (unfolded at the end)
-      GemmP g;
-      g.transA = 1; g.A0 = w.dout; g.lda0 = m.dt; g.sA0 = B * m.dt; g.K0 = (int)B;
-      g.B0 = sb + sl.xh2; g.ldb0 = m.C; g.sB0 = sl.net_stride;
+      TcGemmTnP g;
+      g.A = w.dout; g.lda = m.dt; g.sA = B * m.dt;
+      g.B = sb + sl.xh2; g.ldb = m.C; g.sB = sl.net_stride;
       g.C = dn + pl.slot_off[NF_P_W3]; g.ldc = m.C; g.sC = pl.net_stride;
-      g.M = m.dt; g.N = m.C; g.batch = 2; g.splitk = pick_splitk(g.M, g.N, B, 2);
-      NF_TRY(simt_gemm(g, st));
+      g.M = m.dt; g.N = m.C; g.K = B; g.batch = 2;
+      NF_TRY(wgrad_tn(m.prec, g, st));
     }
     {  // c. d x_hat2 = dout W3f
       GemmP g;
@@ -537,20 +585,20 @@ int nf_flow_backward(const NfFlowDesc* desc, const float* params, const void* pa
       NF_TRY(ln_lrelu_bwd(p, st));
     }
     if (dn) {  // e. G2 = du2^T x_hat1 -> slot W2
-      GemmP g;
-      g.transA = 1; g.A0 = w.gA; g.lda0 = m.C; g.sA0 = B * Hm; g.K0 = (int)B;
-      g.B0 = sb + sl.xh1; g.ldb0 = m.H1; g.sB0 = sl.net_stride;
+      TcGemmTnP g;
+      g.A = w.gA; g.lda = m.C; g.sA = B * Hm;
+      g.B = sb + sl.xh1; g.ldb = m.H1; g.sB = sl.net_stride;
       g.C = dn + pl.slot_off[NF_P_W2]; g.ldc = m.H1; g.sC = pl.net_stride;
-      g.M = m.C; g.N = m.H1; g.batch = 2; g.splitk = pick_splitk(g.M, g.N, B, 2);
-      NF_TRY(simt_gemm(g, st));
+      g.M = m.C; g.N = m.H1; g.K = B; g.batch = 2;
+      NF_TRY(wgrad_tn(m.prec, g, st));
     }
-    {  // f. d x_hat1 = du2 W2f
-      GemmP g;
+    {  // f. d x_hat1 = du2 W2f   (K-major B operand = W2f^T)
+      TcGemmP g;
       g.A0 = w.gA; g.lda0 = m.C; g.sA0 = B * Hm; g.K0 = m.C;
-      g.B0 = kb + kl.net0 + kl.W2f; g.ldb0 = m.H1; g.sB0 = kl.net_stride;
+      g.B0 = kb + kl.net0 + kl.W2fT; g.ldb0 = m.C; g.sB0 = kl.net_stride;
       g.C = w.gB; g.ldc = m.H1; g.sC = B * Hm;
       g.M = (int)B; g.N = m.H1; g.batch = 2;
-      NF_TRY(simt_gemm(g, st));
+      NF_TRY(linear_nt(m.prec, g, st));
     }
     {  // g. through LayerNorm + LeakyReLU (layer 1); column sums -> slot b1
       LnBwdP p{};
@@ -563,31 +611,30 @@ int nf_flow_backward(const NfFlowDesc* desc, const float* params, const void* pa
       NF_TRY(ln_lrelu_bwd(p, st));
     }
     if (dn) {  // h. dW1 = du1^T [x_cond | y]
-      GemmP g;
-      g.transA = 1; g.A0 = w.gB; g.lda0 = m.H1; g.sA0 = B * Hm; g.K0 = (int)B;
-      g.B0 = zi; g.ldb0 = m.D; g.sB0 = 0;
+      TcGemmTnP g;
+      g.A = w.gB; g.lda = m.H1; g.sA = B * Hm;
+      g.B = zi; g.ldb = m.D; g.sB = 0;
       g.C = dn + pl.slot_off[NF_P_W1]; g.ldc = m.K1; g.sC = pl.net_stride;
-      g.M = m.H1; g.N = m.dc; g.batch = 2; g.splitk = pick_splitk(g.M, g.N, B, 2);
-      NF_TRY(simt_gemm(g, st));
+      g.M = m.H1; g.N = m.dc; g.K = B; g.batch = 2;
+      NF_TRY(wgrad_tn(m.prec, g, st));
       if (m.R > 0) {
-        g.B0 = y; g.ldb0 = m.R;
+        g.B = y; g.ldb = m.R;
         g.C = dn + pl.slot_off[NF_P_W1] + m.dc; g.N = m.R;
-        g.splitk = pick_splitk(g.M, g.N, B, 2);
-        NF_TRY(simt_gemm(g, st));
+        NF_TRY(wgrad_tn(m.prec, g, st));
       }
     }
-    {  // i. d h0 = du1_t W1_t + du1_s W1_s : first dc columns -> dxp, the rest -> dy
-      GemmP g;
+    {  // i. d h0 = du1_t W1_t + du1_s W1_s : first dc columns -> dxp, the rest -> dy  (B operand = W1^T)
+      TcGemmP g;
       g.A0 = w.gB; g.lda0 = m.H1; g.K0 = m.H1;
       g.A1 = w.gB + B * Hm; g.lda1 = m.H1; g.K1 = m.H1;
-      g.B0 = pb + pl.slot_off[NF_P_W1]; g.ldb0 = m.K1;
-      g.B1 = g.B0 + pl.net_stride; g.ldb1 = m.K1;
+      g.B0 = kb + kl.net0 + kl.W1T; g.ldb0 = m.H1;
+      g.B1 = g.B0 + kl.net_stride; g.ldb1 = m.H1;
       g.C = w.dxp; g.ldc = m.D; g.M = (int)B; g.N = m.dc; g.accumulate = 1;
-      NF_TRY(simt_gemm(g, st));
+      NF_TRY(linear_nt(m.prec, g, st));
       if (dy && m.R > 0) {
-        g.B0 += m.dc; g.B1 += m.dc;
+        g.B0 += (int64_t)m.dc * m.H1; g.B1 += (int64_t)m.dc * m.H1;
         g.C = dy; g.ldc = m.R; g.N = m.R;
-        NF_TRY(simt_gemm(g, st));
+        NF_TRY(linear_nt(m.prec, g, st));
       }
     }
     if (dn) {  // j. dW = x_in^T dxp
@@ -651,13 +698,33 @@ int nf_linear(const float* A, int64_t lda, const float* W, int64_t ldw, const fl
   return tc_gemm(t, st);
 }
 
+int nf_linear_wgrad(const float* dY, int64_t lddy, const float* X, int64_t ldx, float* dW, int64_t lddw, int64_t B,
+                    int32_t n_out, int32_t n_in, int32_t engine, void* stream) {
+  NF_CHECK_ARG(B >= 0 && n_out >= 1 && n_in >= 1, NF_E_BADARG, "bad shape");
+  NF_TRY(check_ptr(dY, "dY", true)); NF_TRY(check_ptr(X, "X", true)); NF_TRY(check_ptr(dW, "dW", true));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (engine == NF_PREC_FP32_SIMT) {
+    GemmP g;
+    g.transA = 1; g.A0 = dY; g.lda0 = (int)lddy; g.K0 = (int)B;
+    g.B0 = X; g.ldb0 = (int)ldx;
+    g.C = dW; g.ldc = (int)lddw; g.M = n_out; g.N = n_in;
+    g.splitk = pick_splitk(n_out, n_in, B, 1);
+    if (g.splitk == 1) g.accumulate = 1;
+    return simt_gemm(g, st);
+  }
+  TcGemmTnP t;
+  t.A = dY; t.lda = lddy; t.B = X; t.ldb = ldx; t.C = dW; t.ldc = lddw;
+  t.M = n_out; t.N = n_in; t.K = B; t.passes = engine == 3 ? 1 : 3;
+  return tc_gemm_tn(t, st);
+}
+
 int nf_affine_logdet_fwd(const float* xp, const float* s, const float* t, const float* bias_s, const float* bias_t,
                          float logdet_const, int64_t B, int32_t D, float* z, float* logdet, float* s_out,
                          void* stream) {
   NF_CHECK_ARG(D >= 2 && B >= 0, NF_E_BADARG, "bad shape B=%lld D=%d", (long long)B, D);
   NF_TRY(check_ptr(xp, "xp", true)); NF_TRY(check_ptr(s, "s", true)); NF_TRY(check_ptr(t, "t", true));
   NF_TRY(check_ptr(z, "z", true)); NF_TRY(check_ptr(logdet, "logdet", false)); NF_TRY(check_ptr(s_out, "s_out", false));
-  return affine_fwd(xp, s, t, bias_s, bias_t, nullptr, logdet_const, B, D, z, logdet, s_out,
+  return affine_fwd(xp, D, s, t, bias_s, bias_t, nullptr, logdet_const, B, D, z, D, logdet, s_out,
                     reinterpret_cast<cudaStream_t>(stream));
 }
 
@@ -666,7 +733,7 @@ int nf_affine_logdet_inv(const float* z, const float* s, const float* t, const f
   NF_CHECK_ARG(D >= 2 && B >= 0, NF_E_BADARG, "bad shape B=%lld D=%d", (long long)B, D);
   NF_TRY(check_ptr(z, "z", true)); NF_TRY(check_ptr(s, "s", true)); NF_TRY(check_ptr(t, "t", true));
   NF_TRY(check_ptr(xp, "xp", true)); NF_TRY(check_ptr(logdet, "logdet", false));
-  return affine_inv(z, s, t, bias_s, bias_t, nullptr, logdet_const, B, D, xp, logdet,
+  return affine_inv(z, D, s, t, bias_s, bias_t, nullptr, logdet_const, B, D, xp, D, logdet,
                     reinterpret_cast<cudaStream_t>(stream));
 }
 

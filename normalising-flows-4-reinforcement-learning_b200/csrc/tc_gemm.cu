@@ -8,6 +8,12 @@
 //               the fp32 accumulator in TMEM; owns tcgen05.alloc/dealloc
 // Pipelines: full[s] (TMA -> splitters), split[s] (splitters -> MMA), empty[s] (MMA commit ->
 // producer), acc (MMA commit -> epilogue).
+// Two fp32 accumulators live in TMEM: `main` takes only the hi*hi products, `corr` the two small
+// cross terms; the tensor core's accumulate step truncates, so keeping the 2^-11-sized terms out
+// of the main accumulator cuts the rounding drift of a long reduction by 3x.  They are summed in
+// the epilogue.
+// MNMAJOR = true is the weight-gradient form (both operands MN-major, reduction over batch rows,
+// split-K with red.global.add).
 #include <cuda.h>
 
 #include "tc_gemm.cuh"
@@ -27,6 +33,7 @@ struct KArgs {
   long long ldc, sC, sBias;
   int zA0, zA1, zB0, zB1;  // 1: operand is batched over blockIdx.z, 0: shared
   int accumulate, passes, raw_hi;
+  int splitk, chunks_per_split;   // MN-major form only
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -82,6 +89,25 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
   d |= static_cast<uint64_t>(2) << 61;             // SWIZZLE_128B
   return d;
 }
+// MN-major fp32/tf32 operands must use the 128B-swizzle-with-32B-atom layout (cute
+// Layout_MN_SW128_32B_Atom, UMMA layout type 1, TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): canonical
+// form ((T,8,m),(4,k)):((1,T,LBO),(8T,SBO)) in elements, T = 4 fp32 -- 32 fp32 contiguous along M/N
+// per 128 B row, 4 k-rows per 512 B swizzle atom.  Here every 32 x 32 TMA box is 4096 B, so
+// LBO (distance between 32-element M/N groups) = 4096 B and SBO (distance between 4-row k groups)
+// = 512 B.
+__device__ __forceinline__ uint64_t make_sdesc_mn(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(4096 >> 4) << 16;     // LBO
+  d |= static_cast<uint64_t>(512 >> 4) << 32;      // SBO
+  d |= static_cast<uint64_t>(1) << 46;             // version
+  d |= static_cast<uint64_t>(1) << 61;             // SWIZZLE_128B_BASE32B
+  return d;
+}
+__device__ __forceinline__ void red_add_v4(float* dst, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
   asm volatile(
@@ -122,7 +148,7 @@ struct Smem {
   static constexpr int TOTAL = BARS + 256 + 1024;  // + alignment slack
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool MNMAJOR>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUtensorMap mA1,
           const __grid_constant__ CUtensorMap mB0, const __grid_constant__ CUtensorMap mB1, const KArgs a) {
@@ -137,9 +163,13 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN, z = blockIdx.z;
-  const int nk0 = (a.K0 + BK - 1) / BK, nk1 = (a.K1 + BK - 1) / BK, nk = nk0 + nk1;
-  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int z = MNMAJOR ? blockIdx.z / a.splitk : blockIdx.z;
+  const int nk0 = (a.K0 + BK - 1) / BK, nk1 = (a.K1 + BK - 1) / BK;
+  // chunk range of this CTA: everything (K-major form) or one split of the batch rows (MN-major form)
+  const int kc_begin = MNMAJOR ? (blockIdx.z % a.splitk) * a.chunks_per_split : 0;
+  const int nk = MNMAJOR ? min(nk0 - kc_begin, a.chunks_per_split) : nk0 + nk1;
+  constexpr uint32_t TMEM_COLS = 2 * BN;   // main + corr accumulators
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&mA0); prefetch_tmap(&mB0);
@@ -166,35 +196,59 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
         mbar_wait(&empty[s], (use & 1) ^ 1);
         mbar_expect_tx(&full[s], S::HALF);
         uint8_t* st = smem + s * S::STAGE;
-        const bool seg1 = it >= nk0;
-        const int kk = (seg1 ? it - nk0 : it) * BK;
-        tma_load_3d(st, seg1 ? &mA1 : &mA0, &full[s], kk, m0, (seg1 ? a.zA1 : a.zA0) ? z : 0);
-        tma_load_3d(st + A_BYTES, seg1 ? &mB1 : &mB0, &full[s], kk, n0, (seg1 ? a.zB1 : a.zB0) ? z : 0);
+        if (MNMAJOR) {
+          // operands are (K rows, M|N columns): one 32 x 32 box per 32-column group
+          const int k0 = (kc_begin + it) * BK;
+#pragma unroll
+          for (int g = 0; g < BM / 32; ++g) tma_load_3d(st + g * 4096, &mA0, &full[s], m0 + g * 32, k0, a.zA0 ? z : 0);
+#pragma unroll
+          for (int g = 0; g < BN / 32; ++g)
+            tma_load_3d(st + A_BYTES + g * 4096, &mB0, &full[s], n0 + g * 32, k0, a.zB0 ? z : 0);
+        } else {
+          const bool seg1 = it >= nk0;
+          const int kk = (seg1 ? it - nk0 : it) * BK;
+          tma_load_3d(st, seg1 ? &mA1 : &mA0, &full[s], kk, m0, (seg1 ? a.zA1 : a.zA0) ? z : 0);
+          tma_load_3d(st + A_BYTES, seg1 ? &mB1 : &mB0, &full[s], kk, n0, (seg1 ? a.zB1 : a.zB0) ? z : 0);
+        }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      // kind::tf32, fp32 accumulate, K-major A and B, M = 128, N = BN  (cute::UMMA::InstrDescriptor)
-      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(BN >> 3) << 17) | (uint32_t(BM >> 4) << 24);
-      uint32_t acc = 0;
+      // kind::tf32, fp32 accumulate, M = 128, N = BN; bits 15/16 = MN-major A/B (cute::UMMA::InstrDescriptor)
+      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (MNMAJOR ? (3u << 15) : 0u) |
+                                 (uint32_t(BN >> 3) << 17) | (uint32_t(BM >> 4) << 24);
+      const uint32_t tmem_main = tmem_base, tmem_corr = tmem_base + BN;
+      uint32_t acc_m = 0, acc_c = 0;
       for (int it = 0; it < nk; ++it) {
         const int s = it % STAGES, use = it / STAGES;
         mbar_wait(&split[s], use & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t sa = smem_u32(smem + s * S::STAGE);
-        const uint64_t a_hi = make_sdesc(sa), b_hi = make_sdesc(sa + A_BYTES);
-        const uint64_t a_lo = make_sdesc(sa + S::HALF), b_lo = make_sdesc(sa + S::HALF + A_BYTES);
-        const bool seg1 = it >= nk0;
-        const int kleft = (seg1 ? a.K1 - (it - nk0) * BK : a.K0 - it * BK);
-        const int nks = kleft >= BK ? BK / 8 : (kleft + 7) / 8;
+        uint64_t a_hi, b_hi, a_lo, b_lo;
+        int nks;
+        uint64_t step;
+        if (MNMAJOR) {
+          a_hi = make_sdesc_mn(sa); b_hi = make_sdesc_mn(sa + A_BYTES);
+          a_lo = make_sdesc_mn(sa + S::HALF); b_lo = make_sdesc_mn(sa + S::HALF + A_BYTES);
+          const long long kleft = (long long)a.K0 - (long long)(kc_begin + it) * BK;
+          nks = kleft >= BK ? BK / 8 : (int)((kleft + 7) / 8);
+          step = 1024 >> 4;   // next 8 k-rows = next 1024 B swizzle atom
+        } else {
+          a_hi = make_sdesc(sa); b_hi = make_sdesc(sa + A_BYTES);
+          a_lo = make_sdesc(sa + S::HALF); b_lo = make_sdesc(sa + S::HALF + A_BYTES);
+          const bool seg1 = it >= nk0;
+          const int kleft = (seg1 ? a.K1 - (it - nk0) * BK : a.K0 - it * BK);
+          nks = kleft >= BK ? BK / 8 : (kleft + 7) / 8;
+          step = 32 >> 4;     // next 8 fp32 along the 128 B row
+        }
         for (int ks = 0; ks < nks; ++ks) {
-          const uint64_t adv = static_cast<uint64_t>(ks * 2);   // 8 fp32 = 32 B = 2 x 16 B units
+          const uint64_t adv = step * static_cast<uint64_t>(ks);
           if (a.passes == 3) {
-            umma_tf32(tmem_base, a_lo + adv, b_hi + adv, idesc, acc); acc = 1;
-            umma_tf32(tmem_base, a_hi + adv, b_lo + adv, idesc, acc);
+            umma_tf32(tmem_corr, a_lo + adv, b_hi + adv, idesc, acc_c); acc_c = 1;
+            umma_tf32(tmem_corr, a_hi + adv, b_lo + adv, idesc, acc_c);
           }
-          umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, acc); acc = 1;
+          umma_tf32(tmem_main, a_hi + adv, b_hi + adv, idesc, acc_m); acc_m = 1;
         }
         umma_commit(&empty[s]);   // frees the stage once the MMAs above have read it
       }
@@ -233,29 +287,45 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
     const int row = m0 + q * 32 + lane;
     float* crow = a.C + (long long)z * a.sC + (long long)row * a.ldc;
     const float* bias = a.bias ? a.bias + (long long)z * a.sBias : nullptr;
+    const bool vec_ok = (a.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.C) + (size_t)z * a.sC * 4) & 15) == 0;
     for (int c0 = 0; c0 < BN; c0 += 32) {
       if (n0 + c0 >= a.N) break;   // warp-uniform
       uint32_t r[32];
-      tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c0), r);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c0);
+      tmem_ld32(taddr, r);
+      if (a.passes == 3) {
+        uint32_t rc[32];
+        tmem_ld32(taddr + BN, rc);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(rc[j]));
+      }
       if (row < a.M) {
         const int cbase = n0 + c0;
-        if (cbase + 32 <= a.N && (a.ldc & 3) == 0) {
+        if (cbase + 32 <= a.N && vec_ok) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
                                    __uint_as_float(r[j + 3]));
-            if (bias) { v.x += bias[cbase + j]; v.y += bias[cbase + j + 1]; v.z += bias[cbase + j + 2]; v.w += bias[cbase + j + 3]; }
             float4* dst = reinterpret_cast<float4*>(crow + cbase + j);
-            if (a.accumulate) { const float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
-            *dst = v;
+            if (MNMAJOR) {
+              red_add_v4(crow + cbase + j, v);
+            } else {
+              if (bias) { v.x += bias[cbase + j]; v.y += bias[cbase + j + 1]; v.z += bias[cbase + j + 2]; v.w += bias[cbase + j + 3]; }
+              if (a.accumulate) { const float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+              *dst = v;
+            }
           }
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             if (cbase + j < a.N) {
-              float v = __uint_as_float(r[j]) + (bias ? bias[cbase + j] : 0.f);
-              if (a.accumulate) v += crow[cbase + j];
-              crow[cbase + j] = v;
+              if (MNMAJOR) {
+                atomicAdd(crow + cbase + j, __uint_as_float(r[j]));
+              } else {
+                float v = __uint_as_float(r[j]) + (bias ? bias[cbase + j] : 0.f);
+                if (a.accumulate) v += crow[cbase + j];
+                crow[cbase + j] = v;
+              }
             }
           }
         }
@@ -290,20 +360,23 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// fp32 K-major matrix (rows x K, row pitch `ld` floats), optionally batched; box = 32 x box_rows x 1
-int make_map(CUtensorMap* map, const float* base, long long K, long long rows, long long ld, long long batch,
-             long long bstride, int box_rows) {
+// fp32 matrix with `inner` contiguous floats per row and `rows` rows (row pitch `ld` floats), optionally
+// batched; box = 32 x box_rows x 1, SWIZZLE_128B, zero fill out of bounds.
+int make_map(CUtensorMap* map, const float* base, long long inner, long long rows, long long ld, long long batch,
+             long long bstride, int box_rows, bool atom32 = false) {
   EncodeTiledFn fn = encode_fn();
   NF_CHECK_ARG(fn != nullptr, NF_E_UNSUPPORTED, "cuTensorMapEncodeTiled is not available from this driver");
-  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)(bstride ? batch : 1)};
+  cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)(bstride ? batch : 1)};
   cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)(bstride ? bstride : ld * rows) * 4};
   cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  NF_CHECK_ARG(r == CUDA_SUCCESS, NF_E_BADARG, "cuTensorMapEncodeTiled failed (%d): K=%lld rows=%lld ld=%lld", (int)r,
-               K, rows, ld);
+  NF_CHECK_ARG(r == CUDA_SUCCESS, NF_E_BADARG, "cuTensorMapEncodeTiled failed (%d): inner=%lld rows=%lld ld=%lld",
+               (int)r, inner, rows, ld);
   return 0;
 }
 
@@ -311,16 +384,23 @@ bool ok_operand(const float* p, long long ld, long long bstride) {
   return p && (reinterpret_cast<uintptr_t>(p) & 15u) == 0 && (ld & 3) == 0 && (bstride & 3) == 0;
 }
 
+template <int BN, int STAGES, bool MN>
+int set_smem() {
+  static bool configured = false;
+  if (!configured) {
+    NF_CUDA(cudaFuncSetAttribute(k_tc_gemm<BN, STAGES, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 Smem<BN, STAGES>::TOTAL));
+    configured = true;
+  }
+  return 0;
+}
+
 template <int BN, int STAGES>
 int launch(const TcGemmP& p, cudaStream_t st) {
   using S = Smem<BN, STAGES>;
-  static bool configured = false;
-  if (!configured) {
-    NF_CUDA(cudaFuncSetAttribute(k_tc_gemm<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-    configured = true;
-  }
-  CUtensorMap mA0, mA1, mB0, mB1;
   int r;
+  if ((r = set_smem<BN, STAGES, false>())) return r;
+  CUtensorMap mA0, mA1, mB0, mB1;
   if ((r = make_map(&mA0, p.A0, p.K0, p.M, p.lda0, p.batch, p.sA0, BM))) return r;
   if ((r = make_map(&mB0, p.B0, p.K0, p.N, p.ldb0, p.batch, p.sB0, BN))) return r;
   if (p.K1 > 0) {
@@ -329,13 +409,44 @@ int launch(const TcGemmP& p, cudaStream_t st) {
   } else {
     mA1 = mA0; mB1 = mB0;
   }
-  KArgs a;
+  KArgs a{};
   a.C = p.C; a.bias = p.bias; a.M = p.M; a.N = p.N; a.K0 = p.K0; a.K1 = p.K1;
   a.ldc = p.ldc; a.sC = p.sC; a.sBias = p.sBias;
   a.zA0 = p.sA0 != 0; a.zA1 = p.sA1 != 0; a.zB0 = p.sB0 != 0; a.zB1 = p.sB1 != 0;
   a.accumulate = p.accumulate; a.passes = p.passes; a.raw_hi = p.raw_hi;
+  a.splitk = 1; a.chunks_per_split = 0;
   dim3 grid((unsigned)cdiv(p.M, BM), (unsigned)cdiv(p.N, BN), (unsigned)p.batch);
-  k_tc_gemm<BN, STAGES><<<grid, NTHREADS, S::TOTAL, st>>>(mA0, mA1, mB0, mB1, a);
+  k_tc_gemm<BN, STAGES, false><<<grid, NTHREADS, S::TOTAL, st>>>(mA0, mA1, mB0, mB1, a);
+  NF_LAUNCHED();
+  return 0;
+}
+
+template <int BN, int STAGES>
+int launch_tn(const TcGemmTnP& p, cudaStream_t st) {
+  using S = Smem<BN, STAGES>;
+  int r;
+  if ((r = set_smem<BN, STAGES, true>())) return r;
+  CUtensorMap mA, mB;
+  // operands are (K rows, M|N contiguous): inner = M|N, rows = K, 32 x 32 boxes
+  if ((r = make_map(&mA, p.A, p.M, p.K, p.lda, p.batch, p.sA, 32, true))) return r;
+  if ((r = make_map(&mB, p.B, p.N, p.K, p.ldb, p.batch, p.sB, 32, true))) return r;
+  const long long nk = cdiv(p.K, BK);
+  const long long tiles = cdiv(p.M, BM) * cdiv(p.N, BN) * p.batch;
+  long long splitk = p.splitk > 0 ? p.splitk : cdiv(148, tiles);
+  if (splitk > nk) splitk = nk;
+  if (splitk < 1) splitk = 1;
+  const long long per = cdiv(nk, splitk);
+  splitk = cdiv(nk, per);                       // no empty split
+  NF_CHECK_ARG(splitk * p.batch <= 65535, NF_E_BADARG, "tc_gemm_tn: grid too large");
+  KArgs a{};
+  a.C = p.C; a.bias = nullptr; a.M = p.M; a.N = p.N;
+  a.K0 = (int)p.K; a.K1 = 0;
+  a.ldc = p.ldc; a.sC = p.sC; a.sBias = 0;
+  a.zA0 = p.sA != 0; a.zB0 = p.sB != 0; a.zA1 = a.zB1 = 0;
+  a.accumulate = 1; a.passes = p.passes; a.raw_hi = 0;
+  a.splitk = (int)splitk; a.chunks_per_split = (int)per;
+  dim3 grid((unsigned)cdiv(p.M, BM), (unsigned)cdiv(p.N, BN), (unsigned)(splitk * p.batch));
+  k_tc_gemm<BN, STAGES, true><<<grid, NTHREADS, S::TOTAL, st>>>(mA, mA, mB, mB, a);
   NF_LAUNCHED();
   return 0;
 }
@@ -357,6 +468,21 @@ int tc_gemm(const TcGemmP& p, cudaStream_t st) {
   if (p.N > 128) return launch<256, 2>(p, st);
   if (p.N > 64) return launch<128, 3>(p, st);
   return launch<64, 4>(p, st);
+}
+
+bool tc_gemm_tn_supported(const TcGemmTnP& p) {
+  if (p.M <= 0 || p.N <= 0 || p.K <= 0 || p.K >= (1ll << 31) || p.batch <= 0) return false;
+  if (!ok_operand(p.A, p.lda, p.sA) || !ok_operand(p.B, p.ldb, p.sB) || !p.C) return false;
+  return encode_fn() != nullptr;
+}
+
+int tc_gemm_tn(const TcGemmTnP& p, cudaStream_t st) {
+  if (p.M <= 0 || p.N <= 0 || p.batch <= 0 || p.K <= 0) return 0;
+  NF_CHECK_ARG(tc_gemm_tn_supported(p), NF_E_UNSUPPORTED,
+               "tc_gemm_tn: operands must be 16-byte aligned with row pitches that are multiples of 4 floats");
+  if (p.N > 128) return launch_tn<256, 2>(p, st);
+  if (p.N > 64) return launch_tn<128, 3>(p, st);
+  return launch_tn<64, 4>(p, st);
 }
 
 }  // namespace nf

@@ -25,6 +25,21 @@ struct TcGemmP {
   int raw_hi = 0;       // experiment: feed the raw fp32 tile as the hi operand (hardware truncation)
 };
 
+// Weight-gradient form: C[z][m, n] += sum_k A[z][k, m] * B[z][k, n]  (both operands MN-major: the
+// reduction runs over the batch rows).  The reduction is split over `splitk` CTAs whose partial
+// tiles are combined with red.global.add, so C must hold the base value (zeros) on entry.
+struct TcGemmTnP {
+  const float* A = nullptr; const float* B = nullptr; float* C = nullptr;
+  int M = 0, N = 0; long long K = 0;
+  long long lda = 0, ldb = 0, ldc = 0;       // pitches in floats (lda, ldb multiples of 4)
+  long long sA = 0, sB = 0, sC = 0;          // batch strides in floats (0 = shared operand)
+  int batch = 1;
+  int splitk = 0;                            // 0 = choose
+  int passes = 3;
+};
+int tc_gemm_tn(const TcGemmTnP& p, cudaStream_t st);
+bool tc_gemm_tn_supported(const TcGemmTnP& p);
+
 // returns 0, or NF_E_UNSUPPORTED when the shape/alignment cannot be handled by TMA (caller decides)
 int tc_gemm(const TcGemmP& p, cudaStream_t st);
 bool tc_gemm_supported(const TcGemmP& p);

@@ -16,7 +16,7 @@ from tests.helpers import golden_files, grad_probe, load_case, probe_err, rel_er
 
 pytestmark = pytest.mark.gpu
 CASES = golden_files()
-PRECISIONS = ["fp32_simt"]
+PRECISIONS = ["fp32_simt", "fp32"]
 
 
 def dev():
