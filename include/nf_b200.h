@@ -156,6 +156,14 @@ NF_API int nf_linear(const float* A, int64_t lda, const float* W, int64_t ldw, c
 NF_API int nf_linear_wgrad(const float* dY, int64_t lddy, const float* X, int64_t ldx, float* dW, int64_t lddw,
                            int64_t B, int32_t n_out, int32_t n_in, int32_t engine, void* stream);
 
+/* Optional per-kernel-class timing (CUDA events on the launching stream; off by default).  Kinds:
+ * 0 tcgen05 GEMM, 1 tcgen05 weight-gradient GEMM, 2 FFMA GEMM, 3 LeakyReLU+LayerNorm fwd, 4 its backward,
+ * 5 affine coupling kernels, 6 parameter-sized kernels.  nf_prof_collect sums and clears the records:
+ * ms[k] total milliseconds, work[k] algorithmic FLOPs (GEMMs) or bytes (row kernels), launches[k]. */
+#define NF_PROF_KINDS 7
+NF_API int nf_prof_enable(int on);
+NF_API int nf_prof_collect(double* ms, double* work, int64_t* launches, int nkinds);
+
 /* Number of kernels this library launched on the calling thread since the last reset
  * (bench.py's gpu_launches). */
 NF_API int64_t nf_launch_count(int reset);

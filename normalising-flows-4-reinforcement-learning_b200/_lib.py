@@ -59,6 +59,8 @@ def _load():
         "nf_plu_build": (c_int, [fp, fp, fp, fp, fp, c_int32, fp, fp, fp, vp, i64, vp]),
         "nf_linear": (c_int, [fp, i64, fp, i64, fp, fp, i64, i64, c_int32, c_int32, c_int32, vp]),
         "nf_linear_wgrad": (c_int, [fp, i64, fp, i64, fp, i64, i64, c_int32, c_int32, c_int32, vp]),
+        "nf_prof_enable": (c_int, [c_int]),
+        "nf_prof_collect": (c_int, [POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(c_int64), c_int]),
         "nf_launch_count": (c_int64, [c_int]),
     }
     for name, (res, args) in sigs.items():
@@ -85,3 +87,16 @@ def param_layout(desc: NfFlowDesc) -> NfParamLayout:
     out = NfParamLayout()
     check(lib.nf_param_layout(ctypes.byref(desc), ctypes.byref(out)), "nf_param_layout")
     return out
+
+
+PROF_KINDS = ["tc_gemm", "tc_wgrad", "simt_gemm", "ln_fwd", "ln_bwd", "affine", "param"]
+
+
+def prof_collect():
+    """{kind: (ms, work, launches)} since the last call (see nf_prof_collect)."""
+    n = len(PROF_KINDS)
+    ms = (ctypes.c_double * n)()
+    work = (ctypes.c_double * n)()
+    cnt = (c_int64 * n)()
+    lib.nf_prof_collect(ms, work, cnt, n)
+    return {k: (ms[i], work[i], cnt[i]) for i, k in enumerate(PROF_KINDS)}

@@ -1,5 +1,6 @@
 // Row-wise and parameter-sized kernels of the flow (sm_100a).
 #include "elementwise.cuh"
+#include "prof.cuh"
 
 namespace nf {
 
@@ -66,47 +67,70 @@ __global__ void __launch_bounds__(256) k_lrelu_ln_fwd(LnFwdP p) {
 }
 
 // d u = LeakyReLU'(u) * rstd * (g - mean(g) - x_hat * mean(g * x_hat)),  g = d x_hat
-// column sums of d u (bias gradient) are accumulated per CTA in shared memory, then atomically.
+// One warp owns kBwdRowsPerWarp rows: a statistics pass, then per 256-column chunk a pass that
+// writes d u and keeps the column sums (bias gradient) in registers; the warps of a CTA are
+// summed through shared memory and added to global memory with one atomic per column and CTA.
 constexpr int kBwdRowsPerWarp = 8;
-__global__ void __launch_bounds__(256) k_ln_lrelu_bwd(LnBwdP p) {
-  extern __shared__ float s_col[];
+constexpr int kBwdWarps = 8;
+__global__ void __launch_bounds__(kBwdWarps * 32) k_ln_lrelu_bwd(LnBwdP p, int rpw) {
+  __shared__ float s_col[kBwdWarps][256];
   const int net = blockIdx.y;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int N = p.N;
-  for (int c = threadIdx.x; c < N; c += blockDim.x) s_col[c] = 0.f;
-  __syncthreads();
-  const long long row0 = ((long long)blockIdx.x * nwarps + warp) * kBwdRowsPerWarp;
+  const long long row0 = ((long long)blockIdx.x * kBwdWarps + warp) * rpw;
+  float m1[kBwdRowsPerWarp], m2[kBwdRowsPerWarp];
+#pragma unroll
   for (int r = 0; r < kBwdRowsPerWarp; ++r) {
     const long long row = row0 + r;
-    if (row >= p.B) break;
-    float* g = p.g + net * p.g_net + row * N;
-    const float* xh = p.xh + net * p.xh_net + row * N;
-    const uint32_t* mask = p.mask + net * p.mask_net + row * p.mw;
-    const float rstd = p.rstd[net * p.rstd_net + row];
     float s1 = 0.f, s2 = 0.f;
-    for (int c = lane; c < N; c += 32) {
-      const float gv = g[c];
-      s1 += gv;
-      s2 = fmaf(gv, xh[c], s2);
-    }
-    const float m1 = warp_sum(s1) / (float)N, m2 = warp_sum(s2) / (float)N;
-    for (int c0 = 0; c0 < N; c0 += 32) {
-      const int c = c0 + lane;
-      const uint32_t bits = mask[c0 >> 5];
-      if (c < N) {
-        float dv = rstd * (g[c] - m1 - xh[c] * m2);
-        dv *= ((bits >> lane) & 1u) ? 1.0f : kLeakySlope;
-        g[c] = dv;
-        atomicAdd(&s_col[c], dv);
+    if (r < rpw && row < p.B) {
+      const float* g = p.g + net * p.g_net + row * N;
+      const float* xh = p.xh + net * p.xh_net + row * N;
+      for (int c = lane; c < N; c += 32) {
+        const float gv = g[c];
+        s1 += gv;
+        s2 = fmaf(gv, xh[c], s2);
       }
     }
+    m1[r] = warp_sum(s1) / (float)N;
+    m2[r] = warp_sum(s2) / (float)N;
   }
-  __syncthreads();
-  if (p.colsum) {
-    float* cs = p.colsum + net * p.colsum_net;
-    for (int c = threadIdx.x; c < N; c += blockDim.x) {
-      const float v = s_col[c];
-      if (v != 0.f) atomicAdd(&cs[c], v);
+  for (int ch = 0; ch * 256 < N; ++ch) {
+    float cs[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) cs[k] = 0.f;
+#pragma unroll
+    for (int r = 0; r < kBwdRowsPerWarp; ++r) {
+      const long long row = row0 + r;
+      if (r < rpw && row < p.B) {
+        float* g = p.g + net * p.g_net + row * N;
+        const float* xh = p.xh + net * p.xh_net + row * N;
+        const uint32_t* mask = p.mask + net * p.mask_net + row * p.mw;
+        const float rstd = p.rstd[net * p.rstd_net + row];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int c = ch * 256 + k * 32 + lane;
+          if (c < N) {
+            float dv = rstd * (g[c] - m1[r] - xh[c] * m2[r]);
+            dv *= ((mask[c >> 5] >> lane) & 1u) ? 1.0f : kLeakySlope;
+            g[c] = dv;
+            cs[k] += dv;
+          }
+        }
+      }
+    }
+    if (p.colsum) {   // uniform across the CTA
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s_col[warp][k * 32 + lane] = cs[k];
+      __syncthreads();
+      const int c = ch * 256 + threadIdx.x;
+      if (threadIdx.x < 256 && c < N) {
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < kBwdWarps; ++w) v += s_col[w][threadIdx.x];
+        if (v != 0.f) atomicAdd(&p.colsum[net * p.colsum_net + c], v);
+      }
+      __syncthreads();
     }
   }
 }
@@ -351,32 +375,33 @@ __global__ void k_pack_w1(const float* params, NfParamLayout pl, Dims m, float* 
 // Inverse of the folding for gradients (in place on the gradient arena):
 //   slot W{2,3} holds G = du^T x_hat, slot b{2,3} holds g = colsum(du)
 //   dW[n,k] = G[n,k] gamma[k] + g[n] beta[k];  dgamma[k] = sum_n G[n,k] W[n,k];  dbeta[k] = sum_n g[n] W[n,k]
+constexpr int kUnfoldRows = 16;
 __global__ void k_unfold(const float* params, NfParamLayout pl, Dims m, float* dparams) {
-  const int b = blockIdx.z, net = blockIdx.y;
+  const int layer = blockIdx.z & 1, net = (blockIdx.z >> 1) & 1, b = blockIdx.z >> 2;
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  const int rows = layer == 0 ? m.C : m.dt;
+  const int K = layer == 0 ? m.H1 : m.C;
+  const int n0 = blockIdx.y * kUnfoldRows;
+  if (col >= K || n0 >= rows) return;
   const float* pn = params + (long long)b * pl.block_stride + net * pl.net_stride;
   float* dn = dparams + (long long)b * pl.block_stride + net * pl.net_stride;
-  for (int layer = 0; layer < 2; ++layer) {
-    const int rows = layer == 0 ? m.C : m.dt;
-    const int K = layer == 0 ? m.H1 : m.C;
-    if (col >= K) continue;
-    const int sw = layer == 0 ? NF_P_W2 : NF_P_W3, sb = layer == 0 ? NF_P_B2 : NF_P_B3;
-    const int sg = layer == 0 ? NF_P_G1 : NF_P_G2, sbe = layer == 0 ? NF_P_BE1 : NF_P_BE2;
-    const float* W = pn + pl.slot_off[sw];
-    float* G = dn + pl.slot_off[sw];
-    const float* g = dn + pl.slot_off[sb];
-    const float gam = pn[pl.slot_off[sg] + col], bet = pn[pl.slot_off[sbe] + col];
-    float dgam = 0.f, dbet = 0.f;
-    for (int n = 0; n < rows; ++n) {
-      const long long idx = (long long)n * K + col;
-      const float Gv = G[idx], w = W[idx], gn = g[n];
-      dgam = fmaf(Gv, w, dgam);
-      dbet = fmaf(gn, w, dbet);
-      G[idx] = fmaf(Gv, gam, gn * bet);
-    }
-    dn[pl.slot_off[sg] + col] = dgam;
-    dn[pl.slot_off[sbe] + col] = dbet;
+  const int sw = layer == 0 ? NF_P_W2 : NF_P_W3, sb = layer == 0 ? NF_P_B2 : NF_P_B3;
+  const int sg = layer == 0 ? NF_P_G1 : NF_P_G2, sbe = layer == 0 ? NF_P_BE1 : NF_P_BE2;
+  const float* W = pn + pl.slot_off[sw];
+  float* G = dn + pl.slot_off[sw];
+  const float* g = dn + pl.slot_off[sb];
+  const float gam = pn[pl.slot_off[sg] + col], bet = pn[pl.slot_off[sbe] + col];
+  float dgam = 0.f, dbet = 0.f;
+  const int n1 = min(rows, n0 + kUnfoldRows);
+  for (int n = n0; n < n1; ++n) {
+    const long long idx = (long long)n * K + col;
+    const float Gv = G[idx], w = W[idx], gn = g[n];
+    dgam = fmaf(Gv, w, dgam);
+    dbet = fmaf(gn, w, dbet);
+    G[idx] = fmaf(Gv, gam, gn * bet);
   }
+  atomicAdd(&dn[pl.slot_off[sg] + col], dgam);    // the gamma / beta slots are zero on entry
+  atomicAdd(&dn[pl.slot_off[sbe] + col], dbet);
 }
 
 // dL = tril(dLh,-1), dU = triu(dUh,1), ds = diag(dUh) + sum(dlogdet)/s
@@ -451,6 +476,7 @@ __global__ void k_transpose2d(float* dst, long long ldd, long long sd0, long lon
 int lrelu_ln_fwd(const LnFwdP& p, cudaStream_t st) {
   if (p.B <= 0) return 0;
   dim3 grid((unsigned)cdiv(p.B, 8), (unsigned)p.nets);
+  ProfScope prof(st, PROF_LN_FWD, 8.0 * p.B * p.N * p.nets);   // read u, write x_hat
   k_lrelu_ln_fwd<<<grid, 256, 0, st>>>(p);
   NF_LAUNCHED();
   return 0;
@@ -458,8 +484,13 @@ int lrelu_ln_fwd(const LnFwdP& p, cudaStream_t st) {
 
 int ln_lrelu_bwd(const LnBwdP& p, cudaStream_t st) {
   if (p.B <= 0) return 0;
-  dim3 grid((unsigned)cdiv(p.B, 8 * kBwdRowsPerWarp), (unsigned)p.nets);
-  k_ln_lrelu_bwd<<<grid, 256, p.N * sizeof(float), st>>>(p);
+  // latency-bound: fill the GPU with warps first, then give each warp several rows
+  long long rpw = p.B * p.nets / (148 * 24);
+  if (rpw < 1) rpw = 1;
+  if (rpw > kBwdRowsPerWarp) rpw = kBwdRowsPerWarp;
+  dim3 grid((unsigned)cdiv(p.B, kBwdWarps * rpw), (unsigned)p.nets);
+  ProfScope prof(st, PROF_LN_BWD, 12.0 * p.B * p.N * p.nets);  // read g, x_hat; write du
+  k_ln_lrelu_bwd<<<grid, kBwdWarps * 32, 0, st>>>(p, (int)rpw);
   NF_LAUNCHED();
   return 0;
 }
@@ -469,6 +500,8 @@ static int affine_launch(const float* in, int ldi, const float* s, const float* 
                          const float* cdev, float chost, long long B, int D, float* out, int ldo, float* logdet,
                          float* s_out, cudaStream_t st) {
   if (B <= 0) return 0;
+  // algorithmic bytes: read xp (D), s, t (D/2 each), logdet; write z (D), logdet  
+  ProfScope prof(st, PROF_AFFINE, 4.0 * B * (2.0 * D + 2.0 * (D / 2) + 2.0));
   if (D <= 64) {
     const bool vec = (D % 8 == 0) && (ldi % 4 == 0) && (ldo % 4 == 0);
     dim3 grid((unsigned)cdiv(B, 256));
@@ -502,6 +535,7 @@ int affine_bwd(const float* dz, const float* z, const float* s_full, const float
   long long blocks = cdiv(total, 256 * 4);
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
+  ProfScope prof(st, PROF_AFFINE, 4.0 * B * (3.0 * D + 3.0 * (D / 2) + 1.0));
   k_affine_bwd<<<(unsigned)blocks, 256, 2 * (D / 2) * sizeof(float) + 16, st>>>(dz, z, s_full, dlogdet, B, D, dxp,
                                                                               ds, dt, g3s, g3t);
   NF_LAUNCHED();
@@ -544,7 +578,9 @@ int pack_w1(const float* params, const NfParamLayout& pl, const Dims& m, float* 
 
 int unfold_grads(const float* params, const NfParamLayout& pl, const Dims& m, float* dparams, cudaStream_t st) {
   const int K = m.H1 > m.C ? m.H1 : m.C;
-  dim3 grid((unsigned)cdiv(K, 128), 2, (unsigned)m.n);
+  const int rows = m.C > m.dt ? m.C : m.dt;
+  dim3 grid((unsigned)cdiv(K, 128), (unsigned)cdiv(rows, kUnfoldRows), (unsigned)(4 * m.n));
+  ProfScope prof(st, PROF_PARAM, 0.0);
   k_unfold<<<grid, 128, 0, st>>>(params, pl, m, dparams);
   NF_LAUNCHED();
   return 0;

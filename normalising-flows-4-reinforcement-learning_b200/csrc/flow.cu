@@ -5,6 +5,7 @@
 
 #include "common.cuh"
 #include "elementwise.cuh"
+#include "rowfused.cuh"
 #include "simt_gemm.cuh"
 #include "tc_gemm.cuh"
 
@@ -192,7 +193,7 @@ static int check_ptr(const void* p, const char* name, bool required) {
 // gradients.  precision 1 (3xTF32) runs on tcgen05 when the tile shapes make sense and TMA can
 // address the operands; everything else (tiny N or K, odd pitches) is exact-fp32 FFMA.
 static int linear_nt(int prec, const TcGemmP& t, cudaStream_t st) {
-  if (prec == NF_PREC_TF32X3 && t.N >= 32 && (t.K0 + t.K1) >= 32 && tc_gemm_supported(t)) return tc_gemm(t, st);
+  if (prec == NF_PREC_TF32X3 && t.N >= 16 && (t.K0 + t.K1) >= 32 && tc_gemm_supported(t)) return tc_gemm(t, st);
   GemmP g;
   g.A0 = t.A0; g.A1 = t.A1; g.B0 = t.B0; g.B1 = t.B1; g.C = t.C; g.bias = t.bias;
   g.M = t.M; g.N = t.N; g.K0 = t.K0; g.K1 = t.K1;
@@ -216,6 +217,12 @@ static int wgrad_tn(int prec, const TcGemmTnP& t, cudaStream_t st) {
   return simt_gemm(g, st);
 }
 
+// Small flow dimensions use the row-fused kernels of rowfused.cuh for everything around the wide GEMMs.
+static bool use_row_fused(const Dims& m) {
+  return m.D <= kRowFusedMaxD && row_bwd_head_smem(m.D, m.C) <= kRowFusedSmemLimit &&
+         row_bwd_tail_smem(m.D, m.H1) <= kRowFusedSmemLimit;
+}
+
 // The two conditioner MLPs (net 0 = t, net 1 = s) up to the last Linear's raw output o (2,B,dt):
 //   u1 = [x_cond | y] W1^T -> LeakyReLU -> LN -> x_hat1 -> W2f -> LeakyReLU -> LN -> x_hat2 -> W3f
 // (torch_fcnf.py:74-78, :85-89, :99-100).  `xc` holds x_cond in its first dc columns (row pitch ldxc).
@@ -223,7 +230,7 @@ static int conditioners(const Dims& m, const NfParamLayout& pl, const PackedLayo
                         const float* kb, const float* xc, int ldxc, const float* y, int64_t B, const FwdWs& w,
                         float* xh1, int64_t xh1_net, float* xh2, int64_t xh2_net, float* r1, float* r2,
                         int64_t r_net, uint32_t* m1, uint32_t* m2, int64_t m_net, int mw1, int mw2,
-                        cudaStream_t st) {
+                        bool with_last, cudaStream_t st) {
   const int64_t Hm = std::max(m.H1, m.C);
   {  // u1
     TcGemmP g;
@@ -264,7 +271,7 @@ static int conditioners(const Dims& m, const NfParamLayout& pl, const PackedLayo
     p.N = m.C; p.nets = 2; p.B = B; p.eps = m.eps;
     NF_TRY(lrelu_ln_fwd(p, st));
   }
-  {  // o = x_hat2 W3f^T  (N = D/2: FFMA unless the flow is wide)
+  if (with_last) {  // o = x_hat2 W3f^T  (N = D/2: FFMA unless the flow is wide)
     TcGemmP g;
     g.A0 = xh2; g.lda0 = m.C; g.K0 = m.C; g.sA0 = xh2_net;
     g.B0 = kb + kl.net0 + kl.W3f; g.ldb0 = m.C; g.sB0 = kl.net_stride;
@@ -406,10 +413,11 @@ int nf_flow_forward(const NfFlowDesc* desc, const float* params, const void* pac
     NF_CUDA(cudaMemcpyAsync(stash + sl.xs, x, BD * sizeof(float), cudaMemcpyDeviceToDevice, st));
     cur = stash + sl.xs;
   }
+  const bool fused = use_row_fused(m);
   for (int i = 0; i < m.n; ++i) {
     const float* pb = params + (int64_t)i * pl.block_stride;
     const float* kb = packed + (int64_t)i * kl.block_stride;
-    {  // xp = cur @ W   (torch_fcnf.py:40)
+    if (!fused || i == 0) {  // xp = cur @ W   (torch_fcnf.py:40); fused: done by the previous block's tail
       GemmP g;
       g.A0 = cur; g.lda0 = m.D; g.K0 = m.D;
       g.B0 = kb + kl.W; g.ldb0 = m.D;
@@ -426,15 +434,30 @@ int nf_flow_forward(const NfFlowDesc* desc, const float* params, const void* pac
       xh1_net = xh2_net = r_net = m_net = sl.net_stride;
     }
     NF_TRY(conditioners(m, pl, kl, pb, kb, w.xp, w.Dp, y, B, w, xh1, xh1_net, xh2, xh2_net, r1, r2, r_net, m1, m2,
-                        m_net, sl.mw1, sl.mw2, st));
+                        m_net, sl.mw1, sl.mw2, !fused, st));
     float* next;
     if (stash) next = stash + sl.xs + (int64_t)(i + 1) * BD;
     else if (outputs) next = outputs + (int64_t)i * BD;
     else if (i == m.n - 1) next = z;
     else next = (i & 1) ? w.pp1 : w.pp0;   // dense (B,D): only the PLU matmul reads it
-    NF_TRY(affine_fwd(w.xp, w.Dp, w.o + B * m.dt, w.o, kb + kl.net0 + kl.net_stride + kl.b3f, kb + kl.net0 + kl.b3f,
-                      packed + kl.logdet_c + i, 0.f, B, m.D, next, m.D, logdet,
-                      stash ? stash + sl.ss + (int64_t)i * B * m.dt : nullptr, st));
+    float* s_out = stash ? stash + sl.ss + (int64_t)i * B * m.dt : nullptr;
+    if (fused) {
+      TailP t{};
+      t.xh2 = xh2; t.xh2_net = xh2_net;
+      t.W3f = kb + kl.net0 + kl.W3f; t.w_net = kl.net_stride;
+      t.b3f = kb + kl.net0 + kl.b3f; t.b_net = kl.net_stride;
+      t.in = w.xp; t.ld_in = w.Dp;
+      t.cdev = packed + kl.logdet_c + i;
+      t.Wmat = (i + 1 < m.n) ? kb + kl.block_stride + kl.W : nullptr;   // next block's W
+      t.out = next; t.ld_out = m.D;
+      t.out2 = w.xp; t.ld_out2 = w.Dp;                                   // in place: a warp owns its row
+      t.logdet = logdet; t.s_out = s_out;
+      t.B = B; t.D = m.D; t.C = m.C; t.inverse = 0;
+      NF_TRY(row_tail(t, st));
+    } else {
+      NF_TRY(affine_fwd(w.xp, w.Dp, w.o + B * m.dt, w.o, kb + kl.net0 + kl.net_stride + kl.b3f,
+                        kb + kl.net0 + kl.b3f, packed + kl.logdet_c + i, 0.f, B, m.D, next, m.D, logdet, s_out, st));
+    }
     cur = next;
   }
   if (cur != z) NF_CUDA(cudaMemcpyAsync(z, cur, BD * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -479,25 +502,39 @@ int nf_flow_inverse(const NfFlowDesc* desc, const float* params, const void* pac
     cur = w.pp1; ldcur = w.Dp;
   }
   int step = 0;
+  const bool fused = use_row_fused(m);
   for (int i = m.n - 1; i >= 0; --i, ++step) {
     const float* pb = params + (int64_t)i * pl.block_stride;
     const float* kb = packed + (int64_t)i * kl.block_stride;
     NF_TRY(conditioners(m, pl, kl, pb, kb, cur, ldcur, y, B, w, w.xh1, B * m.H1, w.xh2, B * m.C, nullptr, nullptr, 0,
-                        nullptr, nullptr, 0, 0, 0, st));
-    // affine first (torch_fcnf.py:112-113) ...
-    NF_TRY(affine_inv(cur, ldcur, w.o + B * m.dt, w.o, kb + kl.net0 + kl.net_stride + kl.b3f, kb + kl.net0 + kl.b3f,
-                      packed + kl.logdet_c + i, 0.f, B, m.D, w.xp, w.Dp, logdet, st));
-    // ... then x = xp @ W^-1 (torch_fcnf.py:115 -> :55)
+                        nullptr, nullptr, 0, 0, 0, !fused, st));
     float* next;
     int ldnext;
     if (i == 0 && !seq) { next = x; ldnext = m.D; }
     else if (seq && w.Dp == m.D) { next = seq + (int64_t)(step + 1) * BD; ldnext = m.D; }
     else { next = (step & 1) ? w.pp1 : w.pp0; ldnext = w.Dp; }
-    GemmP g;
-    g.A0 = w.xp; g.lda0 = w.Dp; g.K0 = m.D;
-    g.B0 = kb + kl.Winv; g.ldb0 = m.D;
-    g.C = next; g.ldc = ldnext; g.M = (int)B; g.N = m.D;
-    NF_TRY(simt_gemm(g, st));
+    if (fused) {
+      // affine first (torch_fcnf.py:112-113), then x = xp @ W^-1 (:115 -> :55), one kernel
+      TailP t{};
+      t.xh2 = w.xh2; t.xh2_net = B * m.C;
+      t.W3f = kb + kl.net0 + kl.W3f; t.w_net = kl.net_stride;
+      t.b3f = kb + kl.net0 + kl.b3f; t.b_net = kl.net_stride;
+      t.in = cur; t.ld_in = ldcur;
+      t.cdev = packed + kl.logdet_c + i;
+      t.Wmat = kb + kl.Winv;
+      t.out2 = next; t.ld_out2 = ldnext;
+      t.logdet = logdet;
+      t.B = B; t.D = m.D; t.C = m.C; t.inverse = 1;
+      NF_TRY(row_tail(t, st));
+    } else {
+      NF_TRY(affine_inv(cur, ldcur, w.o + B * m.dt, w.o, kb + kl.net0 + kl.net_stride + kl.b3f, kb + kl.net0 + kl.b3f,
+                        packed + kl.logdet_c + i, 0.f, B, m.D, w.xp, w.Dp, logdet, st));
+      GemmP g;
+      g.A0 = w.xp; g.lda0 = w.Dp; g.K0 = m.D;
+      g.B0 = kb + kl.Winv; g.ldb0 = m.D;
+      g.C = next; g.ldc = ldnext; g.M = (int)B; g.N = m.D;
+      NF_TRY(simt_gemm(g, st));
+    }
     if (seq && w.Dp != m.D) NF_TRY(copy2d(seq + (int64_t)(step + 1) * BD, m.D, next, ldnext, B, m.D, st));
     cur = next; ldcur = ldnext;
   }
@@ -541,8 +578,9 @@ int nf_flow_backward(const NfFlowDesc* desc, const float* params, const void* pa
     if (dlogdet) NF_TRY(sum_vector(dlogdet, B, w.sumdld, st));
     else NF_TRY(fill_zero(w.sumdld, 4, st));
   }
-  const float* gcur = dz;  // NULL means zero (handled inside affine_bwd)
+  const float* gcur = dz;  // NULL means zero (handled inside the kernels)
   int pp = 0;
+  const bool fused = use_row_fused(m);
   for (int i = m.n - 1; i >= 0; --i) {
     const float* pb = params + (int64_t)i * pl.block_stride;
     const float* kb = packed + (int64_t)i * kl.block_stride;
@@ -554,35 +592,53 @@ int nf_flow_backward(const NfFlowDesc* desc, const float* params, const void* pa
     const uint32_t* m1 = reinterpret_cast<const uint32_t*>(sb + sl.m1);
     const uint32_t* m2 = reinterpret_cast<const uint32_t*>(sb + sl.m2);
 
-    // a. affine coupling backward: dout[0] = dt, dout[1] = ds
-    NF_TRY(affine_bwd(gcur, zi, si, dlogdet, B, m.D, w.dxp, w.dout + B * m.dt, w.dout,
-                      dn ? dn + pl.net_stride + pl.slot_off[NF_P_B3] : nullptr,
-                      dn ? dn + pl.slot_off[NF_P_B3] : nullptr, st));
-    if (dn) {  // b. G3 = dout^T x_hat2  -> slot W3 (unfolded at the end)
-      TcGemmTnP g;
-      g.A = w.dout; g.lda = m.dt; g.sA = B * m.dt;
-      g.B = sb + sl.xh2; g.ldb = m.C; g.sB = sl.net_stride;
-      g.C = dn + pl.slot_off[NF_P_W3]; g.ldc = m.C; g.sC = pl.net_stride;
-      g.M = m.dt; g.N = m.C; g.K = B; g.batch = 2;
-      NF_TRY(wgrad_tn(m.prec, g, st));
-    }
-    {  // c. d x_hat2 = dout W3f
-      GemmP g;
-      g.A0 = w.dout; g.lda0 = m.dt; g.sA0 = B * m.dt; g.K0 = m.dt;
-      g.B0 = kb + kl.net0 + kl.W3f; g.ldb0 = m.C; g.sB0 = kl.net_stride;
-      g.C = w.gA; g.ldc = m.C; g.sC = B * Hm;
-      g.M = (int)B; g.N = m.C; g.batch = 2;
-      NF_TRY(simt_gemm(g, st));
-    }
-    {  // d. through LayerNorm + LeakyReLU (layer 2); column sums -> slot b2
-      LnBwdP p{};
-      p.g = w.gA; p.g_net = B * Hm;
-      p.xh = sb + sl.xh2; p.xh_net = sl.net_stride;
-      p.rstd = sb + sl.r2; p.rstd_net = sl.net_stride;
-      p.mask = m2; p.mask_net = sl.net_stride; p.mw = sl.mw2;
-      p.colsum = dn ? dn + pl.slot_off[NF_P_B2] : nullptr; p.colsum_net = pl.net_stride;
-      p.N = m.C; p.nets = 2; p.B = B;
-      NF_TRY(ln_lrelu_bwd(p, st));
+    if (fused) {
+      // a-d in one kernel: affine backward, last-Linear gradients, data gradient through the last
+      // Linear and through LayerNorm + LeakyReLU of layer 2
+      BwdHeadP h{};
+      h.dz = gcur; h.ld_dz = m.D; h.z = zi; h.s = si; h.dld = dlogdet;
+      h.xh2 = sb + sl.xh2; h.xh2_net = sl.net_stride;
+      h.rstd = sb + sl.r2; h.rstd_net = sl.net_stride;
+      h.mask = m2; h.mask_net = sl.net_stride; h.mw = sl.mw2;
+      h.W3f = kb + kl.net0 + kl.W3f; h.w_net = kl.net_stride;
+      h.dxp = w.dxp; h.du2 = w.gA; h.du2_net = B * Hm;
+      h.G3 = dn ? dn + pl.slot_off[NF_P_W3] : nullptr;
+      h.g3 = dn ? dn + pl.slot_off[NF_P_B3] : nullptr;
+      h.gb2 = dn ? dn + pl.slot_off[NF_P_B2] : nullptr;
+      h.g_net = pl.net_stride;
+      h.B = B; h.D = m.D; h.C = m.C;
+      NF_TRY(row_bwd_head(h, st));
+    } else {
+      // a. affine coupling backward: dout[0] = dt, dout[1] = ds
+      NF_TRY(affine_bwd(gcur, zi, si, dlogdet, B, m.D, w.dxp, w.dout + B * m.dt, w.dout,
+                        dn ? dn + pl.net_stride + pl.slot_off[NF_P_B3] : nullptr,
+                        dn ? dn + pl.slot_off[NF_P_B3] : nullptr, st));
+      if (dn) {  // b. G3 = dout^T x_hat2  -> slot W3 (unfolded at the end)
+        TcGemmTnP g;
+        g.A = w.dout; g.lda = m.dt; g.sA = B * m.dt;
+        g.B = sb + sl.xh2; g.ldb = m.C; g.sB = sl.net_stride;
+        g.C = dn + pl.slot_off[NF_P_W3]; g.ldc = m.C; g.sC = pl.net_stride;
+        g.M = m.dt; g.N = m.C; g.K = B; g.batch = 2;
+        NF_TRY(wgrad_tn(m.prec, g, st));
+      }
+      {  // c. d x_hat2 = dout W3f
+        GemmP g;
+        g.A0 = w.dout; g.lda0 = m.dt; g.sA0 = B * m.dt; g.K0 = m.dt;
+        g.B0 = kb + kl.net0 + kl.W3f; g.ldb0 = m.C; g.sB0 = kl.net_stride;
+        g.C = w.gA; g.ldc = m.C; g.sC = B * Hm;
+        g.M = (int)B; g.N = m.C; g.batch = 2;
+        NF_TRY(simt_gemm(g, st));
+      }
+      {  // d. through LayerNorm + LeakyReLU (layer 2); column sums -> slot b2
+        LnBwdP p{};
+        p.g = w.gA; p.g_net = B * Hm;
+        p.xh = sb + sl.xh2; p.xh_net = sl.net_stride;
+        p.rstd = sb + sl.r2; p.rstd_net = sl.net_stride;
+        p.mask = m2; p.mask_net = sl.net_stride; p.mw = sl.mw2;
+        p.colsum = dn ? dn + pl.slot_off[NF_P_B2] : nullptr; p.colsum_net = pl.net_stride;
+        p.N = m.C; p.nets = 2; p.B = B;
+        NF_TRY(ln_lrelu_bwd(p, st));
+      }
     }
     if (dn) {  // e. G2 = du2^T x_hat1 -> slot W2
       TcGemmTnP g;
@@ -610,13 +666,13 @@ int nf_flow_backward(const NfFlowDesc* desc, const float* params, const void* pa
       p.N = m.H1; p.nets = 2; p.B = B;
       NF_TRY(ln_lrelu_bwd(p, st));
     }
-    if (dn) {  // h. dW1 = du1^T [x_cond | y]
+    if (dn) {  // h. dW1 = du1^T [x_cond | y]   (fused path: the x_cond columns come from the tail kernel)
       TcGemmTnP g;
       g.A = w.gB; g.lda = m.H1; g.sA = B * Hm;
       g.B = zi; g.ldb = m.D; g.sB = 0;
       g.C = dn + pl.slot_off[NF_P_W1]; g.ldc = m.K1; g.sC = pl.net_stride;
       g.M = m.H1; g.N = m.dc; g.K = B; g.batch = 2;
-      NF_TRY(wgrad_tn(m.prec, g, st));
+      if (!fused) NF_TRY(wgrad_tn(m.prec, g, st));
       if (m.R > 0) {
         g.B = y; g.ldb = m.R;
         g.C = dn + pl.slot_off[NF_P_W1] + m.dc; g.N = m.R;
@@ -630,31 +686,43 @@ int nf_flow_backward(const NfFlowDesc* desc, const float* params, const void* pa
       g.B0 = kb + kl.net0 + kl.W1T; g.ldb0 = m.H1;
       g.B1 = g.B0 + kl.net_stride; g.ldb1 = m.H1;
       g.C = w.dxp; g.ldc = m.D; g.M = (int)B; g.N = m.dc; g.accumulate = 1;
-      NF_TRY(linear_nt(m.prec, g, st));
+      if (!fused) NF_TRY(linear_nt(m.prec, g, st));
       if (dy && m.R > 0) {
         g.B0 += (int64_t)m.dc * m.H1; g.B1 += (int64_t)m.dc * m.H1;
         g.C = dy; g.ldc = m.R; g.N = m.R;
         NF_TRY(linear_nt(m.prec, g, st));
       }
     }
-    if (dn) {  // j. dW = x_in^T dxp
-      GemmP g;
-      g.transA = 1; g.A0 = xin; g.lda0 = m.D; g.K0 = (int)B;
-      g.B0 = w.dxp; g.ldb0 = m.D;
-      g.C = w.dWs + (int64_t)i * DD; g.ldc = m.D; g.M = m.D; g.N = m.D;
-      g.splitk = pick_splitk(g.M, g.N, B, 1);
-      NF_TRY(simt_gemm(g, st));
+    float* dst = (i > 0 || dx) ? ((i == 0) ? dx : (pp ? w.d1 : w.d0)) : nullptr;
+    if (fused) {
+      // i (x_cond part), j, k in one kernel
+      BwdTailP t{};
+      t.du1 = w.gB; t.du1_net = B * Hm;
+      t.W1T = kb + kl.net0 + kl.W1T; t.w_net = kl.net_stride;
+      t.z = zi; t.xin = xin; t.W = kb + kl.W;
+      t.dxp = w.dxp; t.dxin = dst; t.ld_dxin = m.D;
+      t.G1 = dn ? dn + pl.slot_off[NF_P_W1] : nullptr; t.g_net = pl.net_stride; t.ldg = m.K1;
+      t.dW = dn ? w.dWs + (int64_t)i * DD : nullptr;
+      t.B = B; t.D = m.D; t.H1 = m.H1;
+      NF_TRY(row_bwd_tail(t, st));
+    } else {
+      if (dn) {  // j. dW = x_in^T dxp
+        GemmP g;
+        g.transA = 1; g.A0 = xin; g.lda0 = m.D; g.K0 = (int)B;
+        g.B0 = w.dxp; g.ldb0 = m.D;
+        g.C = w.dWs + (int64_t)i * DD; g.ldc = m.D; g.M = m.D; g.N = m.D;
+        g.splitk = pick_splitk(g.M, g.N, B, 1);
+        NF_TRY(simt_gemm(g, st));
+      }
+      if (dst) {  // k. d x_in = dxp W^T
+        GemmP g;
+        g.A0 = w.dxp; g.lda0 = m.D; g.K0 = m.D;
+        g.B0 = kb + kl.W; g.ldb0 = m.D; g.transB = 1;
+        g.C = dst; g.ldc = m.D; g.M = (int)B; g.N = m.D;
+        NF_TRY(simt_gemm(g, st));
+      }
     }
-    if (i > 0 || dx) {  // k. d x_in = dxp W^T
-      GemmP g;
-      g.A0 = w.dxp; g.lda0 = m.D; g.K0 = m.D;
-      g.B0 = kb + kl.W; g.ldb0 = m.D; g.transB = 1;
-      float* dst = (i == 0) ? dx : (pp ? w.d1 : w.d0);
-      g.C = dst; g.ldc = m.D; g.M = (int)B; g.N = m.D;
-      NF_TRY(simt_gemm(g, st));
-      gcur = dst;
-      pp ^= 1;
-    }
+    if (dst) { gcur = dst; pp ^= 1; }
   }
   if (dparams) {
     GemmP g;  // T1 = P^T dW

@@ -1,4 +1,5 @@
 // Exact-fp32 FFMA GEMM (64x64x16 tiles, 256 threads, 4x4 register tiles).
+#include "prof.cuh"
 #include "simt_gemm.cuh"
 
 namespace nf {
@@ -137,6 +138,7 @@ int simt_gemm(const GemmP& p, cudaStream_t st) {
   NF_CHECK_ARG(p.K1 == 0 || (p.A1 && p.B1), NF_E_BADARG, "simt_gemm: segment 1 without pointers");
   dim3 grid((unsigned)(cdiv(p.M, BM) * cdiv(p.N, BN)), (unsigned)p.splitk, (unsigned)p.batch);
   NF_CHECK_ARG(p.splitk >= 1 && p.splitk <= 65535 && p.batch <= 65535, NF_E_BADARG, "simt_gemm: grid");
+  ProfScope prof(st, PROF_SIMT_GEMM, 2.0 * p.M * p.N * (double)(p.K0 + p.K1) * p.batch);
   if (!p.transA && !p.transB) k_gemm<false, false><<<grid, 256, 0, st>>>(p);
   else if (!p.transA && p.transB) k_gemm<false, true><<<grid, 256, 0, st>>>(p);
   else if (p.transA && !p.transB) k_gemm<true, false><<<grid, 256, 0, st>>>(p);

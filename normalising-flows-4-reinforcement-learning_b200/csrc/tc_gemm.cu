@@ -16,6 +16,7 @@
 // split-K with red.global.add).
 #include <cuda.h>
 
+#include "prof.cuh"
 #include "tc_gemm.cuh"
 
 namespace nf {
@@ -416,6 +417,7 @@ int launch(const TcGemmP& p, cudaStream_t st) {
   a.accumulate = p.accumulate; a.passes = p.passes; a.raw_hi = p.raw_hi;
   a.splitk = 1; a.chunks_per_split = 0;
   dim3 grid((unsigned)cdiv(p.M, BM), (unsigned)cdiv(p.N, BN), (unsigned)p.batch);
+  ProfScope prof(st, PROF_TC_GEMM, 2.0 * p.M * p.N * (double)(p.K0 + p.K1) * p.batch);
   k_tc_gemm<BN, STAGES, false><<<grid, NTHREADS, S::TOTAL, st>>>(mA0, mA1, mB0, mB1, a);
   NF_LAUNCHED();
   return 0;
@@ -446,6 +448,7 @@ int launch_tn(const TcGemmTnP& p, cudaStream_t st) {
   a.accumulate = 1; a.passes = p.passes; a.raw_hi = 0;
   a.splitk = (int)splitk; a.chunks_per_split = (int)per;
   dim3 grid((unsigned)cdiv(p.M, BM), (unsigned)cdiv(p.N, BN), (unsigned)(splitk * p.batch));
+  ProfScope prof(st, PROF_TC_WGRAD, 2.0 * p.M * p.N * (double)p.K * p.batch);
   k_tc_gemm<BN, STAGES, true><<<grid, NTHREADS, S::TOTAL, st>>>(mA, mA, mB, mB, a);
   NF_LAUNCHED();
   return 0;
@@ -465,7 +468,9 @@ int tc_gemm(const TcGemmP& p, cudaStream_t st) {
   if (p.M <= 0 || p.N <= 0 || p.batch <= 0) return 0;
   NF_CHECK_ARG(tc_gemm_supported(p), NF_E_UNSUPPORTED,
                "tc_gemm: operands must be 16-byte aligned with row pitches that are multiples of 4 floats");
-  if (p.N > 128) return launch<256, 2>(p, st);
+  // small problems: prefer more, smaller CTAs (3 pipeline stages) over filling TMEM
+  const long long ctas256 = cdiv(p.M, BM) * cdiv(p.N, 256) * p.batch;
+  if (p.N > 128 && ctas256 >= 120) return launch<256, 2>(p, st);
   if (p.N > 64) return launch<128, 3>(p, st);
   return launch<64, 4>(p, st);
 }

@@ -189,6 +189,18 @@ class RealNVP(nn.Module):
         self._flat = flat
         self._slots = sp
         self._trainable = [(p, off) for p, off in sp if p.requires_grad]
+        # one split_with_sizes call yields a 1-D view per arena segment (slots and the gaps between them)
+        sizes, picks, pos = [], [], 0
+        for p, off in sp:
+            if off > pos:
+                sizes.append(off - pos)
+            if p.requires_grad:
+                picks.append((len(sizes), tuple(p.shape) if p.dim() != 1 else None))
+            sizes.append(p.numel())
+            pos = off + p.numel()
+        if pos < self._layout.total:
+            sizes.append(self._layout.total - pos)
+        self._split_sizes, self._split_picks = sizes, picks
         self._packed = None
         self._packed_key = None
 
@@ -209,7 +221,8 @@ class RealNVP(nn.Module):
         return sum(p._version for p, _ in self._slots)
 
     def _grad_views(self, dflat):
-        return [dflat[off:off + p.numel()].view(p.shape) for p, off in self._trainable]
+        chunks = dflat.split_with_sizes(self._split_sizes)
+        return [chunks[i] if shape is None else chunks[i].view(shape) for i, shape in self._split_picks]
 
     # ------------------------------------------------------------------ plumbing
     def _check_inputs(self, x, y):

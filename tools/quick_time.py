@@ -14,8 +14,9 @@ def run(name, B, precision, iters=10):
     m.load_state_dict({k: torch.tensor(v) for k, v in sd.items()}); m = m.to(dev)
     x, y = synth.make_inputs(B, cfg["D"], cfg["R"])
     x = torch.tensor(x, device=dev); y = torch.tensor(y, device=dev)
+    plist = [p for p in m.parameters() if p.requires_grad]
     def train():
-        for p in m.parameters(): p.grad = None
+        for p in plist: p.grad = None
         loss = -m.log_prob(x, y).mean(); loss.backward()
     def fwd():
         with torch.no_grad(): m(x, y)
