@@ -146,7 +146,8 @@ NF_API int nf_plu_build(const float* s, const float* U, const float* L, const fl
 
 /* One conditioner Linear  C (M,N) = A (M,K) @ W (N,K)^T + bias  (torch_fcnf.py:75-77; nn.Linear weight
  * layout).  Row pitches lda/ldw/ldc in floats.  engine: NF_PREC_FP32_SIMT (FFMA), NF_PREC_TF32X3 (tcgen05,
- * fp32 parity), 3 = tcgen05 single TF32 pass, 4 = tcgen05 3xTF32 feeding raw fp32 as the hi operand. */
+ * fp32 parity), 3 = tcgen05 single TF32 pass, 4 = 3xTF32 feeding raw fp32 as the hi operand; 5 / 6 = as 1 / 4
+ * with 32-element (128 B) pipeline stages instead of 16-element ones. */
 NF_API int nf_linear(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, float* C,
                      int64_t ldc, int64_t M, int32_t N, int32_t K, int32_t engine, void* stream);
 
@@ -158,9 +159,10 @@ NF_API int nf_linear_wgrad(const float* dY, int64_t lddy, const float* X, int64_
 
 /* Optional per-kernel-class timing (CUDA events on the launching stream; off by default).  Kinds:
  * 0 tcgen05 GEMM, 1 tcgen05 weight-gradient GEMM, 2 FFMA GEMM, 3 LeakyReLU+LayerNorm fwd, 4 its backward,
- * 5 affine coupling kernels, 6 parameter-sized kernels.  nf_prof_collect sums and clears the records:
+ * 5 affine coupling kernels, 6 parameter-sized kernels, 7 row-fused forward/inverse tail, 8 row-fused
+ * backward head, 9 row-fused backward tail.  nf_prof_collect sums and clears the records:
  * ms[k] total milliseconds, work[k] algorithmic FLOPs (GEMMs) or bytes (row kernels), launches[k]. */
-#define NF_PROF_KINDS 7
+#define NF_PROF_KINDS 10
 NF_API int nf_prof_enable(int on);
 NF_API int nf_prof_collect(double* ms, double* work, int64_t* launches, int nkinds);
 

@@ -89,7 +89,8 @@ def param_layout(desc: NfFlowDesc) -> NfParamLayout:
     return out
 
 
-PROF_KINDS = ["tc_gemm", "tc_wgrad", "simt_gemm", "ln_fwd", "ln_bwd", "affine", "param"]
+PROF_KINDS = ["tc_gemm", "tc_wgrad", "simt_gemm", "ln_fwd", "ln_bwd", "affine", "param", "row_tail", "row_bwd_head",
+              "row_bwd_tail"]
 
 
 def prof_collect():

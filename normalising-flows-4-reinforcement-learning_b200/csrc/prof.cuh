@@ -15,7 +15,10 @@ enum ProfKind {
   PROF_LN_BWD = 4,      // LayerNorm + LeakyReLU backward
   PROF_AFFINE = 5,      // affine coupling + log-det (fwd / inv / bwd)
   PROF_PARAM = 6,       // parameter-sized kernels (PLU build, folding, transposes, unfolding)
-  PROF_NKINDS = 7
+  PROF_ROW_TAIL = 7,    // row-fused forward / inverse tail
+  PROF_ROW_HEAD = 8,    // row-fused backward head
+  PROF_ROW_BTAIL = 9,   // row-fused backward tail
+  PROF_NKINDS = 10
 };
 
 bool prof_enabled();

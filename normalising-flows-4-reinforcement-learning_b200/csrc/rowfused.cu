@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(kWarps * 32) k_row_bwd_head(BwdHeadP p, int ro
   float* stats = smem + kWarps * SLICE + warp * rows_per_warp * 2;
   const long long row0 = ((long long)blockIdx.x * kWarps + warp) * rows_per_warp;
   const bool want_param = p.G3 != nullptr;
+  float acc_g3t = 0.f, acc_g3s = 0.f;   // lane dc + i: column sums of dt_i, ds_i over this warp's rows
 
   for (int net = 0; net < 2; ++net) {
     const float* W3 = p.W3f + net * p.w_net;
@@ -114,10 +115,8 @@ __global__ void __launch_bounds__(kWarps * 32) k_row_bwd_head(BwdHeadP p, int ro
       }
       if (net == 0) {
         if (lane < D) p.dxp[row * D + lane] = dxpv;
-        if (want_param && lane >= dc && lane < D) {
-          atomicAdd(&p.g3[lane - dc], dt_);
-          atomicAdd(&p.g3[p.g_net + (lane - dc)], ds_);
-        }
+        acc_g3t += dt_;
+        acc_g3s += ds_;
       }
       const float mine = net == 0 ? dt_ : ds_;
       float dout[MAXDT];
@@ -202,6 +201,20 @@ __global__ void __launch_bounds__(kWarps * 32) k_row_bwd_head(BwdHeadP p, int ro
           }
         }
         __syncthreads();
+      }
+    }
+  }
+  if (want_param) {   // last-Linear bias gradients: one atomic per CTA and element
+    slice[lane] = acc_g3t;
+    slice[32 + lane] = acc_g3s;
+    __syncthreads();
+    if (threadIdx.x < 64) {
+      const int which = threadIdx.x >> 5, j = threadIdx.x & 31;   // 0: t, 1: s
+      if (j >= dc && j < D) {
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) v += smem[w * SLICE + which * 32 + j];
+        atomicAdd(&p.g3[which * p.g_net + (j - dc)], v);
       }
     }
   }
@@ -346,7 +359,7 @@ int row_tail(const TailP& p, cudaStream_t st) {
   NF_CHECK_ARG(p.D >= 2 && p.D <= kRowFusedMaxD, NF_E_UNSUPPORTED, "row_tail: D=%d", p.D);
   const int dt = p.D / 2;
   dim3 grid((unsigned)cdiv(p.B, kWarps));
-  ProfScope prof(st, PROF_AFFINE, 4.0 * p.B * (2.0 * p.C + 3.0 * p.D));
+  ProfScope prof(st, PROF_ROW_TAIL, 4.0 * p.B * (2.0 * p.C + 3.0 * p.D));
   if (dt <= 4) k_row_tail<4><<<grid, kWarps * 32, 0, st>>>(p);
   else k_row_tail<16><<<grid, kWarps * 32, 0, st>>>(p);
   NF_LAUNCHED();
@@ -365,7 +378,7 @@ int row_bwd_head(const BwdHeadP& p, cudaStream_t st) {
   const int rpw = rows_per_warp_for(p.B);
   dim3 grid((unsigned)cdiv(p.B, (long long)kWarps * rpw));
   const size_t smem = row_bwd_head_smem(p.D, p.C);
-  ProfScope prof(st, PROF_LN_BWD, 4.0 * p.B * (4.0 * p.C + 4.0 * p.D));
+  ProfScope prof(st, PROF_ROW_HEAD, 4.0 * p.B * (4.0 * p.C + 4.0 * p.D));
   if (dt <= 4) {
     static bool cfg = false;
     if (!cfg) { NF_CUDA(cudaFuncSetAttribute(k_row_bwd_head<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cfg = true; }
@@ -392,7 +405,7 @@ int row_bwd_tail(const BwdTailP& p, cudaStream_t st) {
   const int rpw = rows_per_warp_for(p.B);
   dim3 grid((unsigned)cdiv(p.B, (long long)kWarps * rpw));
   const size_t smem = row_bwd_tail_smem(p.D, p.H1);
-  ProfScope prof(st, PROF_AFFINE, 4.0 * p.B * (4.0 * p.H1 + 4.0 * p.D));
+  ProfScope prof(st, PROF_ROW_BTAIL, 4.0 * p.B * (4.0 * p.H1 + 4.0 * p.D));
   if (dc <= 8) {
     static bool cfg = false;
     if (!cfg) { NF_CUDA(cudaFuncSetAttribute(k_row_bwd_tail<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cfg = true; }

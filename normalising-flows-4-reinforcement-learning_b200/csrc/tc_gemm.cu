@@ -23,9 +23,9 @@ namespace nf {
 namespace {
 
 constexpr int BM = 128;
-constexpr int BK = 32;  // 32 fp32 = 128 bytes = one swizzle row
-constexpr int A_BYTES = BM * 128;
 constexpr int NTHREADS = 192;
+// BK = fp32 elements of the reduction per pipeline stage: 32 (128 B rows, SWIZZLE_128B) or 16 (64 B rows,
+// SWIZZLE_64B; twice the stages in the same shared memory, which hides the TMA + split latency better).
 
 struct KArgs {
   float* C;
@@ -79,30 +79,32 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
-// K-major SWIZZLE_128B operand descriptor: rows of 128 B, 8-row groups 1024 B apart (SBO),
-// descriptor version 1 (Blackwell), layout type 2 (cute::UMMA::LayoutType::SWIZZLE_128B).
+// K-major operand descriptor: rows of BK*4 bytes (128 B -> SWIZZLE_128B, 64 B -> SWIZZLE_64B), 8-row
+// groups SBO bytes apart, descriptor version 1 (Blackwell); layout codes of cute::UMMA::LayoutType.
+template <int BK>
 __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
-  d |= static_cast<uint64_t>(1) << 16;             // LBO (unused for swizzled K-major), 16 B units
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;     // SBO
-  d |= static_cast<uint64_t>(1) << 46;             // version
-  d |= static_cast<uint64_t>(2) << 61;             // SWIZZLE_128B
+  d |= static_cast<uint64_t>(1) << 16;                       // LBO (unused for swizzled K-major), 16 B units
+  d |= static_cast<uint64_t>((8 * BK * 4) >> 4) << 32;       // SBO: 8 rows
+  d |= static_cast<uint64_t>(1) << 46;                       // version
+  d |= static_cast<uint64_t>(BK == 32 ? 2 : 4) << 61;        // SWIZZLE_128B : SWIZZLE_64B
   return d;
 }
 // MN-major fp32/tf32 operands must use the 128B-swizzle-with-32B-atom layout (cute
 // Layout_MN_SW128_32B_Atom, UMMA layout type 1, TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): canonical
 // form ((T,8,m),(4,k)):((1,T,LBO),(8T,SBO)) in elements, T = 4 fp32 -- 32 fp32 contiguous along M/N
-// per 128 B row, 4 k-rows per 512 B swizzle atom.  Here every 32 x 32 TMA box is 4096 B, so
-// LBO (distance between 32-element M/N groups) = 4096 B and SBO (distance between 4-row k groups)
+// per 128 B row, 4 k-rows per 512 B swizzle atom.  Every 32 x BK TMA box is BK*128 B, so
+// LBO (distance between 32-element M/N groups) = BK*128 B and SBO (distance between 4-row k groups)
 // = 512 B.
+template <int BK>
 __device__ __forceinline__ uint64_t make_sdesc_mn(uint32_t saddr) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
-  d |= static_cast<uint64_t>(4096 >> 4) << 16;     // LBO
-  d |= static_cast<uint64_t>(512 >> 4) << 32;      // SBO
-  d |= static_cast<uint64_t>(1) << 46;             // version
-  d |= static_cast<uint64_t>(1) << 61;             // SWIZZLE_128B_BASE32B
+  d |= static_cast<uint64_t>((BK * 128) >> 4) << 16;         // LBO
+  d |= static_cast<uint64_t>(512 >> 4) << 32;                // SBO
+  d |= static_cast<uint64_t>(1) << 46;                       // version
+  d |= static_cast<uint64_t>(1) << 61;                       // SWIZZLE_128B_BASE32B
   return d;
 }
 __device__ __forceinline__ void red_add_v4(float* dst, float4 v) {
@@ -140,20 +142,23 @@ __device__ __forceinline__ float rna_tf32(float x) {
   return __uint_as_float(r);
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int BK>
 struct Smem {
-  static constexpr int B_BYTES = BN * 128;
+  static constexpr int A_BYTES = BM * BK * 4;
+  static constexpr int B_BYTES = BN * BK * 4;
   static constexpr int HALF = A_BYTES + B_BYTES;   // raw/hi tiles; the lo twins follow
   static constexpr int STAGE = 2 * HALF;
   static constexpr int BARS = STAGES * STAGE;      // byte offset of the barrier block
   static constexpr int TOTAL = BARS + 256 + 1024;  // + alignment slack
 };
 
-template <int BN, int STAGES, bool MNMAJOR>
+template <int BN, int STAGES, bool MNMAJOR, int BK>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUtensorMap mA1,
           const __grid_constant__ CUtensorMap mB0, const __grid_constant__ CUtensorMap mB1, const KArgs a) {
-  using S = Smem<BN, STAGES>;
+  using S = Smem<BN, STAGES, BK>;
+  constexpr int A_BYTES = S::A_BYTES;
+  constexpr int BOX = 32 * BK * 4;   // bytes of one 32-column MN-major TMA box
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::BARS);
@@ -201,10 +206,10 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
           // operands are (K rows, M|N columns): one 32 x 32 box per 32-column group
           const int k0 = (kc_begin + it) * BK;
 #pragma unroll
-          for (int g = 0; g < BM / 32; ++g) tma_load_3d(st + g * 4096, &mA0, &full[s], m0 + g * 32, k0, a.zA0 ? z : 0);
+          for (int g = 0; g < BM / 32; ++g) tma_load_3d(st + g * BOX, &mA0, &full[s], m0 + g * 32, k0, a.zA0 ? z : 0);
 #pragma unroll
           for (int g = 0; g < BN / 32; ++g)
-            tma_load_3d(st + A_BYTES + g * 4096, &mB0, &full[s], n0 + g * 32, k0, a.zB0 ? z : 0);
+            tma_load_3d(st + A_BYTES + g * BOX, &mB0, &full[s], n0 + g * 32, k0, a.zB0 ? z : 0);
         } else {
           const bool seg1 = it >= nk0;
           const int kk = (seg1 ? it - nk0 : it) * BK;
@@ -230,14 +235,14 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
         int nks;
         uint64_t step;
         if (MNMAJOR) {
-          a_hi = make_sdesc_mn(sa); b_hi = make_sdesc_mn(sa + A_BYTES);
-          a_lo = make_sdesc_mn(sa + S::HALF); b_lo = make_sdesc_mn(sa + S::HALF + A_BYTES);
+          a_hi = make_sdesc_mn<BK>(sa); b_hi = make_sdesc_mn<BK>(sa + A_BYTES);
+          a_lo = make_sdesc_mn<BK>(sa + S::HALF); b_lo = make_sdesc_mn<BK>(sa + S::HALF + A_BYTES);
           const long long kleft = (long long)a.K0 - (long long)(kc_begin + it) * BK;
           nks = kleft >= BK ? BK / 8 : (int)((kleft + 7) / 8);
           step = 1024 >> 4;   // next 8 k-rows = next 1024 B swizzle atom
         } else {
-          a_hi = make_sdesc(sa); b_hi = make_sdesc(sa + A_BYTES);
-          a_lo = make_sdesc(sa + S::HALF); b_lo = make_sdesc(sa + S::HALF + A_BYTES);
+          a_hi = make_sdesc<BK>(sa); b_hi = make_sdesc<BK>(sa + A_BYTES);
+          a_lo = make_sdesc<BK>(sa + S::HALF); b_lo = make_sdesc<BK>(sa + S::HALF + A_BYTES);
           const bool seg1 = it >= nk0;
           const int kleft = (seg1 ? a.K1 - (it - nk0) * BK : a.K0 - it * BK);
           nks = kleft >= BK ? BK / 8 : (kleft + 7) / 8;
@@ -364,17 +369,15 @@ EncodeTiledFn encode_fn() {
 // fp32 matrix with `inner` contiguous floats per row and `rows` rows (row pitch `ld` floats), optionally
 // batched; box = 32 x box_rows x 1, SWIZZLE_128B, zero fill out of bounds.
 int make_map(CUtensorMap* map, const float* base, long long inner, long long rows, long long ld, long long batch,
-             long long bstride, int box_rows, bool atom32 = false) {
+             long long bstride, int box_inner, int box_rows, CUtensorMapSwizzle swz) {
   EncodeTiledFn fn = encode_fn();
   NF_CHECK_ARG(fn != nullptr, NF_E_UNSUPPORTED, "cuTensorMapEncodeTiled is not available from this driver");
   cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)(bstride ? batch : 1)};
   cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)(bstride ? bstride : ld * rows) * 4};
-  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1};
+  cuuint32_t box[3] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   NF_CHECK_ARG(r == CUDA_SUCCESS, NF_E_BADARG, "cuTensorMapEncodeTiled failed (%d): inner=%lld rows=%lld ld=%lld",
                (int)r, inner, rows, ld);
@@ -385,28 +388,29 @@ bool ok_operand(const float* p, long long ld, long long bstride) {
   return p && (reinterpret_cast<uintptr_t>(p) & 15u) == 0 && (ld & 3) == 0 && (bstride & 3) == 0;
 }
 
-template <int BN, int STAGES, bool MN>
+template <int BN, int STAGES, bool MN, int BK>
 int set_smem() {
   static bool configured = false;
   if (!configured) {
-    NF_CUDA(cudaFuncSetAttribute(k_tc_gemm<BN, STAGES, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 Smem<BN, STAGES>::TOTAL));
+    NF_CUDA(cudaFuncSetAttribute(k_tc_gemm<BN, STAGES, MN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 Smem<BN, STAGES, BK>::TOTAL));
     configured = true;
   }
   return 0;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int BK>
 int launch(const TcGemmP& p, cudaStream_t st) {
-  using S = Smem<BN, STAGES>;
+  using S = Smem<BN, STAGES, BK>;
   int r;
-  if ((r = set_smem<BN, STAGES, false>())) return r;
+  if ((r = set_smem<BN, STAGES, false, BK>())) return r;
   CUtensorMap mA0, mA1, mB0, mB1;
-  if ((r = make_map(&mA0, p.A0, p.K0, p.M, p.lda0, p.batch, p.sA0, BM))) return r;
-  if ((r = make_map(&mB0, p.B0, p.K0, p.N, p.ldb0, p.batch, p.sB0, BN))) return r;
+  const CUtensorMapSwizzle swz = BK == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  if ((r = make_map(&mA0, p.A0, p.K0, p.M, p.lda0, p.batch, p.sA0, BK, BM, swz))) return r;
+  if ((r = make_map(&mB0, p.B0, p.K0, p.N, p.ldb0, p.batch, p.sB0, BK, BN, swz))) return r;
   if (p.K1 > 0) {
-    if ((r = make_map(&mA1, p.A1, p.K1, p.M, p.lda1, p.batch, p.sA1, BM))) return r;
-    if ((r = make_map(&mB1, p.B1, p.K1, p.N, p.ldb1, p.batch, p.sB1, BN))) return r;
+    if ((r = make_map(&mA1, p.A1, p.K1, p.M, p.lda1, p.batch, p.sA1, BK, BM, swz))) return r;
+    if ((r = make_map(&mB1, p.B1, p.K1, p.N, p.ldb1, p.batch, p.sB1, BK, BN, swz))) return r;
   } else {
     mA1 = mA0; mB1 = mB0;
   }
@@ -418,23 +422,24 @@ int launch(const TcGemmP& p, cudaStream_t st) {
   a.splitk = 1; a.chunks_per_split = 0;
   dim3 grid((unsigned)cdiv(p.M, BM), (unsigned)cdiv(p.N, BN), (unsigned)p.batch);
   ProfScope prof(st, PROF_TC_GEMM, 2.0 * p.M * p.N * (double)(p.K0 + p.K1) * p.batch);
-  k_tc_gemm<BN, STAGES, false><<<grid, NTHREADS, S::TOTAL, st>>>(mA0, mA1, mB0, mB1, a);
+  k_tc_gemm<BN, STAGES, false, BK><<<grid, NTHREADS, S::TOTAL, st>>>(mA0, mA1, mB0, mB1, a);
   NF_LAUNCHED();
   return 0;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int BK>
 int launch_tn(const TcGemmTnP& p, cudaStream_t st) {
-  using S = Smem<BN, STAGES>;
+  using S = Smem<BN, STAGES, BK>;
   int r;
-  if ((r = set_smem<BN, STAGES, true>())) return r;
+  if ((r = set_smem<BN, STAGES, true, BK>())) return r;
   CUtensorMap mA, mB;
-  // operands are (K rows, M|N contiguous): inner = M|N, rows = K, 32 x 32 boxes
-  if ((r = make_map(&mA, p.A, p.M, p.K, p.lda, p.batch, p.sA, 32, true))) return r;
-  if ((r = make_map(&mB, p.B, p.N, p.K, p.ldb, p.batch, p.sB, 32, true))) return r;
+  // operands are (K rows, M|N contiguous): inner = M|N, rows = K, 32 x BK boxes
+  if ((r = make_map(&mA, p.A, p.M, p.K, p.lda, p.batch, p.sA, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return r;
+  if ((r = make_map(&mB, p.B, p.N, p.K, p.ldb, p.batch, p.sB, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return r;
   const long long nk = cdiv(p.K, BK);
   const long long tiles = cdiv(p.M, BM) * cdiv(p.N, BN) * p.batch;
-  long long splitk = p.splitk > 0 ? p.splitk : cdiv(148, tiles);
+  // one wave: as many splits as fit on the 148 SMs without spilling into a second, nearly empty wave
+  long long splitk = p.splitk > 0 ? p.splitk : (tiles >= 148 ? 1 : 148 / tiles);
   if (splitk > nk) splitk = nk;
   if (splitk < 1) splitk = 1;
   const long long per = cdiv(nk, splitk);
@@ -449,7 +454,7 @@ int launch_tn(const TcGemmTnP& p, cudaStream_t st) {
   a.splitk = (int)splitk; a.chunks_per_split = (int)per;
   dim3 grid((unsigned)cdiv(p.M, BM), (unsigned)cdiv(p.N, BN), (unsigned)(splitk * p.batch));
   ProfScope prof(st, PROF_TC_WGRAD, 2.0 * p.M * p.N * (double)p.K * p.batch);
-  k_tc_gemm<BN, STAGES, true><<<grid, NTHREADS, S::TOTAL, st>>>(mA, mA, mB, mB, a);
+  k_tc_gemm<BN, STAGES, true, BK><<<grid, NTHREADS, S::TOTAL, st>>>(mA, mA, mB, mB, a);
   NF_LAUNCHED();
   return 0;
 }
@@ -470,9 +475,14 @@ int tc_gemm(const TcGemmP& p, cudaStream_t st) {
                "tc_gemm: operands must be 16-byte aligned with row pitches that are multiples of 4 floats");
   // small problems: prefer more, smaller CTAs (3 pipeline stages) over filling TMEM
   const long long ctas256 = cdiv(p.M, BM) * cdiv(p.N, 256) * p.batch;
-  if (p.N > 128 && ctas256 >= 120) return launch<256, 2>(p, st);
-  if (p.N > 64) return launch<128, 3>(p, st);
-  return launch<64, 4>(p, st);
+  if (p.bk == 32) {
+    if (p.N > 128 && ctas256 >= 120) return launch<256, 2, 32>(p, st);
+    if (p.N > 64) return launch<128, 3, 32>(p, st);
+    return launch<64, 4, 32>(p, st);
+  }
+  if (p.N > 128 && ctas256 >= 120) return launch<256, 4, 16>(p, st);
+  if (p.N > 64) return launch<128, 6, 16>(p, st);
+  return launch<64, 8, 16>(p, st);
 }
 
 bool tc_gemm_tn_supported(const TcGemmTnP& p) {
@@ -485,9 +495,14 @@ int tc_gemm_tn(const TcGemmTnP& p, cudaStream_t st) {
   if (p.M <= 0 || p.N <= 0 || p.batch <= 0 || p.K <= 0) return 0;
   NF_CHECK_ARG(tc_gemm_tn_supported(p), NF_E_UNSUPPORTED,
                "tc_gemm_tn: operands must be 16-byte aligned with row pitches that are multiples of 4 floats");
-  if (p.N > 128) return launch_tn<256, 2>(p, st);
-  if (p.N > 64) return launch_tn<128, 3>(p, st);
-  return launch_tn<64, 4>(p, st);
+  if (p.bk == 32) {
+    if (p.N > 128) return launch_tn<256, 2, 32>(p, st);
+    if (p.N > 64) return launch_tn<128, 3, 32>(p, st);
+    return launch_tn<64, 4, 32>(p, st);
+  }
+  if (p.N > 128) return launch_tn<256, 4, 16>(p, st);
+  if (p.N > 64) return launch_tn<128, 6, 16>(p, st);
+  return launch_tn<64, 8, 16>(p, st);
 }
 
 }  // namespace nf

@@ -22,7 +22,9 @@ struct TcGemmP {
   int batch = 1;
   int accumulate = 0;
   int passes = 3;       // 3 = 3xTF32 (fp32 parity), 1 = single TF32 pass
-  int raw_hi = 0;       // experiment: feed the raw fp32 tile as the hi operand (hardware truncation)
+  int raw_hi = 1;       // feed the raw fp32 tile as the hi operand (the tensor core ignores the low 13 bits):
+                        // lo = x - trunc_tf32(x); saves one shared-memory store per element (measured +10%)
+  int bk = 16;          // reduction elements per pipeline stage: 16 or 32
 };
 
 // Weight-gradient form: C[z][m, n] += sum_k A[z][k, m] * B[z][k, n]  (both operands MN-major: the
@@ -36,6 +38,7 @@ struct TcGemmTnP {
   int batch = 1;
   int splitk = 0;                            // 0 = choose
   int passes = 3;
+  int bk = 16;
 };
 int tc_gemm_tn(const TcGemmTnP& p, cudaStream_t st);
 bool tc_gemm_tn_supported(const TcGemmTnP& p);

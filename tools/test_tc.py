@@ -24,12 +24,12 @@ def run(M, N, K, engine, pad=0, bias=True, seed=0):
     return C
 
 if __name__ == "__main__":
-    for eng in (0, 1, 3, 4):
+    for eng in (0, 1, 3, 4, 5, 6):
         run(128, 256, 32, eng)
-    for eng in (1, 3, 4):
+    for eng in (1, 3, 4, 5):
         run(128, 256, 256, eng)
         run(4096, 512, 260, eng)
-    for eng in (0, 1):
+    for eng in (1, 5):
         run(257, 200, 36, eng)
         run(1000, 64, 512, eng, pad=4)
         run(300, 136, 100, eng)
@@ -41,7 +41,7 @@ if __name__ == "__main__":
     # timing
     M, N, K = 16384, 512, 512
     A = torch.randn(M, K, device=dev); W = torch.randn(N, K, device=dev); C = torch.empty(M, N, device=dev)
-    for eng in (0, 1, 3):
+    for eng in (0, 1, 3, 4, 5, 6):
         for _ in range(3): lib.nf_linear(A.data_ptr(), K, W.data_ptr(), K, None, C.data_ptr(), N, M, N, K, eng, st)
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record()

@@ -21,14 +21,14 @@ def run(B, n_out, n_in, engine, seed=0):
     print(f"B={B} n_out={n_out} n_in={n_in} engine={engine}: rel err {err:.3e}", flush=True)
 
 if __name__ == "__main__":
-    for eng in (0, 1, 3):
+    for eng in (0, 1, 3, 5):
         run(32, 128, 256, eng)
-    for eng in (0, 1):
+    for eng in (1, 5):
         run(256, 128, 256, eng); run(4096, 512, 512, eng); run(1000, 200, 260, eng); run(8192, 1024, 1024, eng)
         run(300, 64, 36, eng); run(5000, 512, 1024, eng)
     B, n_out, n_in = 16384, 512, 512
     dY = torch.randn(B, n_out, device=dev); X = torch.randn(B, n_in, device=dev); dW = torch.zeros(n_out, n_in, device=dev)
-    for eng in (0, 1, 3):
+    for eng in (0, 1, 3, 5):
         for _ in range(3): lib.nf_linear_wgrad(dY.data_ptr(), n_out, X.data_ptr(), n_in, dW.data_ptr(), n_in, B, n_out, n_in, eng, st)
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
