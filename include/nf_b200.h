@@ -160,11 +160,19 @@ NF_API int nf_linear_wgrad(const float* dY, int64_t lddy, const float* X, int64_
 /* Optional per-kernel-class timing (CUDA events on the launching stream; off by default).  Kinds:
  * 0 tcgen05 GEMM, 1 tcgen05 weight-gradient GEMM, 2 FFMA GEMM, 3 LeakyReLU+LayerNorm fwd, 4 its backward,
  * 5 affine coupling kernels, 6 parameter-sized kernels, 7 row-fused forward/inverse tail, 8 row-fused
- * backward head, 9 row-fused backward tail.  nf_prof_collect sums and clears the records:
+ * backward head, 9 row-fused backward tail, 10 column reductions over the batch rows.  nf_prof_collect sums and clears the records:
  * ms[k] total milliseconds, work[k] algorithmic FLOPs (GEMMs) or bytes (row kernels), launches[k]. */
-#define NF_PROF_KINDS 10
+#define NF_PROF_KINDS 11
 NF_API int nf_prof_enable(int on);
 NF_API int nf_prof_collect(double* ms, double* work, int64_t* launches, int nkinds);
+
+/* Launch-sequence replay (on by default; NF_B200_GRAPHS=0 disables): prepare / forward / inverse /
+ * backward capture their kernel sequence into a CUDA graph the second time the same (descriptor, B,
+ * pointers) come back and replay it with one cudaGraphLaunch on the caller's stream afterwards.  Buffers
+ * are still caller-owned; a cached graph only refers to the pointers it was keyed on. */
+NF_API int nf_graphs_enable(int on);
+NF_API int nf_graphs_clear(void);
+NF_API int nf_graphs_stats(int64_t* replays, int64_t* captures, int64_t* eager);
 
 /* Number of kernels this library launched on the calling thread since the last reset
  * (bench.py's gpu_launches). */

@@ -62,6 +62,9 @@ def _load():
         "nf_prof_enable": (c_int, [c_int]),
         "nf_prof_collect": (c_int, [POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(c_int64), c_int]),
         "nf_launch_count": (c_int64, [c_int]),
+        "nf_graphs_enable": (c_int, [c_int]),
+        "nf_graphs_clear": (c_int, []),
+        "nf_graphs_stats": (c_int, [POINTER(c_int64), POINTER(c_int64), POINTER(c_int64)]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)
@@ -89,8 +92,15 @@ def param_layout(desc: NfFlowDesc) -> NfParamLayout:
     return out
 
 
+def graph_stats():
+    """(replays, captures, eager runs) of the library's launch-sequence cache."""
+    a, b, c = c_int64(), c_int64(), c_int64()
+    lib.nf_graphs_stats(ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
+    return a.value, b.value, c.value
+
+
 PROF_KINDS = ["tc_gemm", "tc_wgrad", "simt_gemm", "ln_fwd", "ln_bwd", "affine", "param", "row_tail", "row_bwd_head",
-              "row_bwd_tail"]
+              "row_bwd_tail", "col_reduce"]
 
 
 def prof_collect():

@@ -5,7 +5,9 @@
 
 #include "common.cuh"
 #include "elementwise.cuh"
+#include "graphs.cuh"
 #include "rowfused.cuh"
+#include "rowlocal.cuh"
 #include "simt_gemm.cuh"
 #include "tc_gemm.cuh"
 
@@ -339,10 +341,19 @@ int nf_flow_prepare(const NfFlowDesc* desc, const float* params, void* packed_v,
   NfParamLayout pl;
   param_layout(m, &pl);
   const PackedLayout kl = packed_layout(m);
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  cudaStream_t user_st = reinterpret_cast<cudaStream_t>(stream);
   float* packed = reinterpret_cast<float*>(packed_v);
   const int64_t DD = (int64_t)m.D * m.D;
-
+  if (what & NF_PREP_INV) {
+    NF_TRY(check_ptr(workspace, "workspace", true));
+    const PrepWs w = carve_prep(m, workspace);
+    NF_CHECK_ARG(ws_bytes >= w.total * (int64_t)sizeof(float), NF_E_WORKSPACE, "workspace too small: %lld < %lld",
+                 (long long)ws_bytes, (long long)(w.total * sizeof(float)));
+  }
+  GraphKey key;
+  key.op = 1; key.desc = *desc; key.flags = what; key.ws_bytes = ws_bytes;
+  key.ptr[0] = params; key.ptr[1] = packed_v; key.ptr[2] = workspace;
+  auto body = [&](cudaStream_t st) -> int {
   NF_TRY(plu_mask(params, pl, m, packed, kl, st));
   {  // PL = P @ Lh
     GemmP g;
@@ -365,10 +376,7 @@ int nf_flow_prepare(const NfFlowDesc* desc, const float* params, void* packed_v,
                      params + pl.slot_off[NF_P_W1], m.K1, pl.net_stride, pl.block_stride, m.H1, m.K1, 2, m.n, st));
   NF_TRY(pack_w1(params, pl, m, packed, kl, st));
   if (what & NF_PREP_INV) {
-    NF_TRY(check_ptr(workspace, "workspace", true));
     const PrepWs w = carve_prep(m, workspace);
-    NF_CHECK_ARG(ws_bytes >= w.total * (int64_t)sizeof(float), NF_E_WORKSPACE, "workspace too small: %lld < %lld",
-                 (long long)ws_bytes, (long long)(w.total * sizeof(float)));
     NF_TRY(plu_tri_inverse(packed, kl, m, w.uinv, w.linv, st));
     GemmP g;  // T = Uinv @ Linv ; Winv = T @ P_inv   (torch_fcnf.py:54)
     g.A0 = w.uinv; g.lda0 = m.D; g.K0 = m.D; g.sA0 = DD;
@@ -382,6 +390,8 @@ int nf_flow_prepare(const NfFlowDesc* desc, const float* params, void* packed_v,
     NF_TRY(simt_gemm(g, st));
   }
   return 0;
+  };
+  return run_graphed(key, user_st, body);
 }
 
 int nf_flow_forward(const NfFlowDesc* desc, const float* params, const void* packed_v, const float* x,
@@ -406,12 +416,17 @@ int nf_flow_forward(const NfFlowDesc* desc, const float* params, const void* pac
   const FwdWs w = carve_fwd(m, B, workspace);
   NF_CHECK_ARG(ws_bytes >= w.total * (int64_t)sizeof(float), NF_E_WORKSPACE, "workspace too small: %lld < %lld",
                (long long)ws_bytes, (long long)(w.total * sizeof(float)));
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  cudaStream_t user_st = reinterpret_cast<cudaStream_t>(stream);
   const float* packed = reinterpret_cast<const float*>(packed_v);
   float* stash = reinterpret_cast<float*>(stash_v);
   const StashLayout sl = stash_layout(m, B);
   const int64_t BD = B * m.D;
 
+  GraphKey key;
+  key.op = 2; key.desc = *desc; key.B = B; key.ws_bytes = ws_bytes;
+  key.ptr[0] = params; key.ptr[1] = packed_v; key.ptr[2] = x; key.ptr[3] = y; key.ptr[4] = z; key.ptr[5] = logdet;
+  key.ptr[6] = outputs; key.ptr[7] = stash_v; key.ptr[8] = workspace;
+  auto body = [&](cudaStream_t st) -> int {
   NF_CUDA(cudaMemsetAsync(logdet, 0, B * sizeof(float), st));
   const float* cur = x;
   if (stash) {
@@ -458,7 +473,7 @@ int nf_flow_forward(const NfFlowDesc* desc, const float* params, const void* pac
       t.out2 = w.xp; t.ld_out2 = w.Dp;                                   // in place: a warp owns its row
       t.logdet = logdet; t.s_out = s_out;
       t.B = B; t.D = m.D; t.C = m.C; t.inverse = 0;
-      NF_TRY(row_tail(t, st));
+      NF_TRY(row_v2_supported(m.D, m.C, 4) ? row_tail2(t, st) : row_tail(t, st));
     } else {
       NF_TRY(affine_fwd(w.xp, w.Dp, w.o + B * m.dt, w.o, kb + kl.net0 + kl.net_stride + kl.b3f,
                         kb + kl.net0 + kl.b3f, packed + kl.logdet_c + i, 0.f, B, m.D, next, m.D, logdet, s_out, st));
@@ -470,6 +485,8 @@ int nf_flow_forward(const NfFlowDesc* desc, const float* params, const void* pac
     NF_CUDA(cudaMemcpyAsync(outputs, stash + sl.xs + BD, (int64_t)m.n * BD * sizeof(float), cudaMemcpyDeviceToDevice,
                             st));
   return 0;
+  };
+  return run_graphed(key, user_st, body);
 }
 
 int nf_flow_inverse(const NfFlowDesc* desc, const float* params, const void* packed_v, const float* z,
@@ -493,10 +510,15 @@ int nf_flow_inverse(const NfFlowDesc* desc, const float* params, const void* pac
   const FwdWs w = carve_fwd(m, B, workspace);
   NF_CHECK_ARG(ws_bytes >= w.total * (int64_t)sizeof(float), NF_E_WORKSPACE, "workspace too small: %lld < %lld",
                (long long)ws_bytes, (long long)(w.total * sizeof(float)));
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  cudaStream_t user_st = reinterpret_cast<cudaStream_t>(stream);
   const float* packed = reinterpret_cast<const float*>(packed_v);
   const int64_t BD = B * m.D;
 
+  GraphKey key;
+  key.op = 3; key.desc = *desc; key.B = B; key.ws_bytes = ws_bytes;
+  key.ptr[0] = params; key.ptr[1] = packed_v; key.ptr[2] = z; key.ptr[3] = y; key.ptr[4] = x; key.ptr[5] = logdet;
+  key.ptr[6] = seq; key.ptr[7] = workspace;
+  auto body = [&](cudaStream_t st) -> int {
   if (logdet) NF_CUDA(cudaMemsetAsync(logdet, 0, B * sizeof(float), st));
   if (seq) NF_CUDA(cudaMemcpyAsync(seq, z, BD * sizeof(float), cudaMemcpyDeviceToDevice, st));
   // running buffer with a 16-byte row pitch (x_cond is a TMA operand of the first Linear)
@@ -530,7 +552,7 @@ int nf_flow_inverse(const NfFlowDesc* desc, const float* params, const void* pac
       t.out2 = next; t.ld_out2 = ldnext;
       t.logdet = logdet;
       t.B = B; t.D = m.D; t.C = m.C; t.inverse = 1;
-      NF_TRY(row_tail(t, st));
+      NF_TRY(row_v2_supported(m.D, m.C, 4) ? row_tail2(t, st) : row_tail(t, st));
     } else {
       NF_TRY(affine_inv(cur, ldcur, w.o + B * m.dt, w.o, kb + kl.net0 + kl.net_stride + kl.b3f, kb + kl.net0 + kl.b3f,
                         packed + kl.logdet_c + i, 0.f, B, m.D, w.xp, w.Dp, logdet, st));
@@ -545,6 +567,8 @@ int nf_flow_inverse(const NfFlowDesc* desc, const float* params, const void* pac
   }
   if (seq) NF_CUDA(cudaMemcpyAsync(x, seq + (int64_t)m.n * BD, BD * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return 0;
+  };
+  return run_graphed(key, user_st, body);
 }
 
 int nf_flow_backward(const NfFlowDesc* desc, const float* params, const void* packed_v, const void* stash_v,
@@ -558,9 +582,11 @@ int nf_flow_backward(const NfFlowDesc* desc, const float* params, const void* pa
   const Dims m = dims_of(desc);
   NfParamLayout pl;
   param_layout(m, &pl);
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (dparams) NF_TRY(fill_zero(dparams, pl.total, st));
-  if (B == 0) return 0;
+  cudaStream_t user_st = reinterpret_cast<cudaStream_t>(stream);
+  if (B == 0) {
+    if (dparams) NF_TRY(fill_zero(dparams, pl.total, user_st));
+    return 0;
+  }
   NF_TRY(check_ptr(stash_v, "stash", true));
   NF_TRY(check_ptr(y, "y", desc->R > 0));
   NF_TRY(check_ptr(dz, "dz", false));
@@ -577,6 +603,12 @@ int nf_flow_backward(const NfFlowDesc* desc, const float* params, const void* pa
   const float* stash = reinterpret_cast<const float*>(stash_v);
   const int64_t BD = B * m.D, Hm = std::max(m.H1, m.C), DD = (int64_t)m.D * m.D;
 
+  GraphKey key;
+  key.op = 4; key.desc = *desc; key.B = B; key.ws_bytes = ws_bytes;
+  key.ptr[0] = params; key.ptr[1] = packed_v; key.ptr[2] = stash_v; key.ptr[3] = y; key.ptr[4] = dz; key.ptr[5] = dlogdet;
+  key.ptr[6] = dx; key.ptr[7] = dy; key.ptr[8] = dparams; key.ptr[9] = workspace;
+  auto body = [&](cudaStream_t st) -> int {
+  if (dparams) NF_TRY(fill_zero(dparams, pl.total, st));
   if (dy) NF_TRY(fill_zero(dy, B * m.R, st));
   if (dparams) {
     NF_TRY(fill_zero(w.dWs, m.n * DD, st));
@@ -586,6 +618,7 @@ int nf_flow_backward(const NfFlowDesc* desc, const float* params, const void* pa
   const float* gcur = dz;  // NULL means zero (handled inside the kernels)
   int pp = 0;
   const bool fused = use_row_fused(m);
+  const bool v2 = fused && row_v2_supported(m.D, m.C, m.H1);
   for (int i = m.n - 1; i >= 0; --i) {
     const float* pb = params + (int64_t)i * pl.block_stride;
     const float* kb = packed + (int64_t)i * kl.block_stride;
@@ -597,7 +630,20 @@ int nf_flow_backward(const NfFlowDesc* desc, const float* params, const void* pa
     const uint32_t* m1 = reinterpret_cast<const uint32_t*>(sb + sl.m1);
     const uint32_t* m2 = reinterpret_cast<const uint32_t*>(sb + sl.m2);
 
-    if (fused) {
+    if (fused && v2) {
+      // a-d in one row-local kernel: affine backward, data gradient through the last Linear and through
+      // LayerNorm + LeakyReLU of layer 2; the skinny parameter gradients are reduced at the end of the block
+      BwdHead2P h{};
+      h.dz = gcur; h.ld_dz = m.D; h.z = zi; h.s = si; h.dld = dlogdet;
+      h.xh2 = sb + sl.xh2; h.xh2_net = sl.net_stride;
+      h.rstd = sb + sl.r2; h.rstd_net = sl.net_stride;
+      h.mask = m2; h.mask_net = sl.net_stride; h.mw = sl.mw2;
+      h.W3f = kb + kl.net0 + kl.W3f; h.w_net = kl.net_stride;
+      h.dxp = w.dxp; h.dout = w.dout; h.dout_net = B * m.dt;
+      h.du2 = w.gA; h.du2_net = B * Hm;
+      h.B = B; h.D = m.D; h.C = m.C;
+      NF_TRY(row_bwd_head2(h, st));
+    } else if (fused) {
       // a-d in one kernel: affine backward, last-Linear gradients, data gradient through the last
       // Linear and through LayerNorm + LeakyReLU of layer 2
       BwdHeadP h{};
@@ -699,7 +745,38 @@ int nf_flow_backward(const NfFlowDesc* desc, const float* params, const void* pa
       }
     }
     float* dst = (i > 0 || dx) ? ((i == 0) ? dx : (pp ? w.d1 : w.d0)) : nullptr;
-    if (fused) {
+    if (fused && v2) {
+      // i (x_cond part) and k per row, then every reduction over the batch rows of this block in one launch
+      BwdTail2P t{};
+      t.du1 = w.gB; t.du1_net = B * Hm;
+      t.W1T = kb + kl.net0 + kl.W1T; t.w_net = kl.net_stride;
+      t.W = kb + kl.W;
+      t.dxp = w.dxp; t.dxin = dst; t.ld_dxin = m.D;
+      t.B = B; t.D = m.D; t.H1 = m.H1;
+      NF_TRY(row_bwd_tail2(t, st));
+      if (dn) {
+        ColJob jobs[3];
+        // G3 = dout^T x_hat2 (folded last Linear), gb2 = colsum(du2), g3 = colsum(dout)
+        jobs[0].A = sb + sl.xh2; jobs[0].lda = m.C; jobs[0].sA = sl.net_stride; jobs[0].N = m.C;
+        jobs[0].coef = w.dout; jobs[0].ldcf = m.dt; jobs[0].sCf = B * m.dt; jobs[0].m = m.dt;
+        jobs[0].out = dn + pl.slot_off[NF_P_W3]; jobs[0].so_i = m.C; jobs[0].so_c = 1; jobs[0].sOut = pl.net_stride;
+        jobs[0].A2 = w.gA; jobs[0].lda2 = m.C; jobs[0].sA2 = B * Hm;
+        jobs[0].out2 = dn + pl.slot_off[NF_P_B2]; jobs[0].sOut2 = pl.net_stride;
+        jobs[0].out3 = dn + pl.slot_off[NF_P_B3]; jobs[0].sOut3 = pl.net_stride;
+        jobs[0].batch = 2;
+        // G1[:, :dc] = du1^T x_cond   (x_cond = z[:, :dc])
+        jobs[1].A = w.gB; jobs[1].lda = m.H1; jobs[1].sA = B * Hm; jobs[1].N = m.H1;
+        jobs[1].coef = zi; jobs[1].ldcf = m.D; jobs[1].sCf = 0; jobs[1].m = m.dc;
+        jobs[1].out = dn + pl.slot_off[NF_P_W1]; jobs[1].so_i = 1; jobs[1].so_c = m.K1; jobs[1].sOut = pl.net_stride;
+        jobs[1].batch = 2;
+        // dW = x_in^T dxp
+        jobs[2].A = w.dxp; jobs[2].lda = m.D; jobs[2].N = m.D;
+        jobs[2].coef = xin; jobs[2].ldcf = m.D; jobs[2].m = m.D;
+        jobs[2].out = w.dWs + (int64_t)i * DD; jobs[2].so_i = m.D; jobs[2].so_c = 1;
+        jobs[2].batch = 1;
+        NF_TRY(col_reduce(jobs, 3, B, st));
+      }
+    } else if (fused) {
       // i (x_cond part), j, k in one kernel
       BwdTailP t{};
       t.du1 = w.gB; t.du1_net = B * Hm;
@@ -749,6 +826,8 @@ int nf_flow_backward(const NfFlowDesc* desc, const float* params, const void* pa
     NF_TRY(unfold_grads(params, pl, m, dparams, st));
   }
   return 0;
+  };
+  return run_graphed(key, user_st, body);
 }
 
 int nf_linear(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, float* C, int64_t ldc,
@@ -764,11 +843,13 @@ int nf_linear(const float* A, int64_t lda, const float* W, int64_t ldw, const fl
     g.C = C; g.ldc = (int)ldc; g.bias = bias; g.M = (int)M; g.N = N;
     return simt_gemm(g, st);
   }
-  NF_CHECK_ARG(engine == NF_PREC_TF32X3 || (engine >= 3 && engine <= 6), NF_E_UNSUPPORTED, "unknown engine %d", engine);
+  NF_CHECK_ARG(engine == NF_PREC_TF32X3 || (engine >= 3 && engine <= 8), NF_E_UNSUPPORTED, "unknown engine %d", engine);
   TcGemmP t;
   t.A0 = A; t.lda0 = lda; t.K0 = K; t.B0 = W; t.ldb0 = ldw; t.C = C; t.ldc = ldc; t.bias = bias;
   t.M = (int)M; t.N = N; t.passes = engine == 3 ? 1 : 3; t.raw_hi = (engine == 4 || engine == 6 || engine == 3);
   t.bk = (engine == 5 || engine == 6) ? 32 : 16;
+  if (engine == 7) { t.raw_hi = 0; t.lo_round = 1; }   // experiments: rounded lo
+  if (engine == 8) { t.raw_hi = 1; t.lo_round = 1; }
   return tc_gemm(t, st);
 }
 

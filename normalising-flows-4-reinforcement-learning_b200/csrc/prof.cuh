@@ -18,7 +18,8 @@ enum ProfKind {
   PROF_ROW_TAIL = 7,    // row-fused forward / inverse tail
   PROF_ROW_HEAD = 8,    // row-fused backward head
   PROF_ROW_BTAIL = 9,   // row-fused backward tail
-  PROF_NKINDS = 10
+  PROF_COL_REDUCE = 10, // multi-job column reduction over the batch rows (skinny weight/bias gradients)
+  PROF_NKINDS = 11
 };
 
 bool prof_enabled();

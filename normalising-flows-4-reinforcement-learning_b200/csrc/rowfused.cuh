@@ -63,46 +63,6 @@ struct BwdTailP {
 int row_bwd_tail(const BwdTailP& p, cudaStream_t st);
 size_t row_bwd_tail_smem(int D, int H1);
 
-// Column reduction over the batch rows (the skinny weight/bias gradients around the row kernels):
-//   out[i*so_i + c*so_c] += sum_rows coef[row][i] * A[row][c]      (i < m <= 16, coef may be null when m == 0)
-//   out2[c]              += sum_rows A2[row][c]                     (optional plain column sums)
-// One thread owns a column and streams down a chunk of rows (coalesced), partial sums are combined
-// with one atomic per element and row chunk.  Batched over blockIdx.z (nets).
-struct ColRedP {
-  const float* A = nullptr; long long lda = 0, sA = 0;
-  const float* coef = nullptr; long long ldcf = 0, sCf = 0; int m = 0;
-  float* out = nullptr; long long so_i = 0, so_c = 1, sOut = 0;
-  const float* A2 = nullptr; long long lda2 = 0, sA2 = 0;
-  float* out2 = nullptr; long long sOut2 = 0;
-  long long B = 0; int N = 0; int batch = 1;
-};
-int col_reduce(const ColRedP& p, cudaStream_t st);
-
-// v2 row-local kernels (C % 4 == 0, C <= 1024): no cross-row accumulation inside, float4 accesses
-struct BwdHead2P {
-  const float* dz; int ld_dz; const float* z; const float* s; const float* dld;
-  const float* xh2; long long xh2_net;
-  const float* rstd; long long rstd_net;
-  const uint32_t* mask; long long mask_net; int mw;
-  const float* W3f; long long w_net;
-  float* dxp;                            // (B, D)
-  float* dout; long long dout_net;       // (2, B, dt): net 0 = dt, net 1 = ds
-  float* du2; long long du2_net;         // (2, B, C)
-  long long B; int D, C;
-};
-int row_bwd_head2(const BwdHead2P& p, cudaStream_t st);
-bool row_v2_supported(int D, int C, int H1);
-
-struct BwdTail2P {
-  const float* du1; long long du1_net;   // (2, B, H1)
-  const float* W1T; long long w_net;     // (2, K1, H1)
-  const float* xin; const float* W;
-  float* dxp; float* dxin; int ld_dxin;
-  float* dW;                             // (D, D) += x_in^T dxp (null: skip)
-  long long B; int D, H1;
-};
-int row_bwd_tail2(const BwdTail2P& p, cudaStream_t st);
-
 constexpr size_t kRowFusedSmemLimit = 96 * 1024;   // keeps >= 2 CTAs per SM; wider flows use the generic path
 
 }  // namespace nf

@@ -15,6 +15,7 @@
 // MNMAJOR = true is the weight-gradient form (both operands MN-major, reduction over batch rows,
 // split-K with red.global.add).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "prof.cuh"
 #include "tc_gemm.cuh"
@@ -33,7 +34,7 @@ struct KArgs {
   int M, N, K0, K1;
   long long ldc, sC, sBias;
   int zA0, zA1, zB0, zB1;  // 1: operand is batched over blockIdx.z, 0: shared
-  int accumulate, passes, raw_hi;
+  int accumulate, passes, raw_hi, lo_round;
   int splitk, chunks_per_split;   // MN-major form only
 };
 
@@ -175,7 +176,23 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
   // chunk range of this CTA: everything (K-major form) or one split of the batch rows (MN-major form)
   const int kc_begin = MNMAJOR ? (blockIdx.z % a.splitk) * a.chunks_per_split : 0;
   const int nk = MNMAJOR ? min(nk0 - kc_begin, a.chunks_per_split) : nk0 + nk1;
-  constexpr uint32_t TMEM_COLS = 2 * BN;   // main + corr accumulators
+  // The tensor core TRUNCATES (toward zero) when it adds products into the fp32 accumulator (measured with
+  // tools/tc_precision.py: all-positive operands lose 5.4e-8 of the sum per k8 step, mirrored for negative
+  // ones; random-sign data sees zero-mean noise that also grows linearly with the reduction length -- a
+  // multiplicative correction therefore does not help, it was tried).  The hi*hi products therefore rotate over NACC independent
+  // accumulators that are summed with round-to-nearest adds in the epilogue (bias / NACC), and the
+  // weight-gradient form additionally caps the rows per CTA (launch_tn).
+  constexpr int NACC = BN <= 128 ? 3 : 1;
+  constexpr uint32_t TMEM_COLS = (NACC + 1) * BN;   // NACC main + 1 corr accumulator
+  // k8 steps this CTA issues (the epilogue must know how many main accumulators were written)
+  int total_k8;
+  if (MNMAJOR) {
+    const long long len = min((long long)a.K0, (long long)(kc_begin + nk) * BK) - (long long)kc_begin * BK;
+    total_k8 = (int)((len + 7) / 8);
+  } else {
+    total_k8 = (a.K0 + 7) / 8 + (a.K1 + 7) / 8;
+  }
+  const int nacc_used = total_k8 < NACC ? total_k8 : NACC;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&mA0); prefetch_tmap(&mB0);
@@ -224,8 +241,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
       // kind::tf32, fp32 accumulate, M = 128, N = BN; bits 15/16 = MN-major A/B (cute::UMMA::InstrDescriptor)
       constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (MNMAJOR ? (3u << 15) : 0u) |
                                  (uint32_t(BN >> 3) << 17) | (uint32_t(BM >> 4) << 24);
-      const uint32_t tmem_main = tmem_base, tmem_corr = tmem_base + BN;
-      uint32_t acc_m = 0, acc_c = 0;
+      const uint32_t tmem_corr = tmem_base + NACC * BN;
+      uint32_t acc_c = 0;
+      int k8 = 0;
       for (int it = 0; it < nk; ++it) {
         const int s = it % STAGES, use = it / STAGES;
         mbar_wait(&split[s], use & 1);
@@ -254,7 +272,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
             umma_tf32(tmem_corr, a_lo + adv, b_hi + adv, idesc, acc_c); acc_c = 1;
             umma_tf32(tmem_corr, a_hi + adv, b_lo + adv, idesc, acc_c);
           }
-          umma_tf32(tmem_main, a_hi + adv, b_hi + adv, idesc, acc_m); acc_m = 1;
+          umma_tf32(tmem_base + (k8 % NACC) * BN, a_hi + adv, b_hi + adv, idesc, k8 >= NACC ? 1u : 0u);
+          ++k8;
         }
         umma_commit(&empty[s]);   // frees the stage once the MMAs above have read it
       }
@@ -280,6 +299,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
           raw[i] = h;
         }
         l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+        if (a.lo_round) { l.x = rna_tf32(l.x); l.y = rna_tf32(l.y); l.z = rna_tf32(l.z); l.w = rna_tf32(l.w); }
         lo[i] = l;
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> UMMA reads
@@ -299,11 +319,14 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
       uint32_t r[32];
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c0);
       tmem_ld32(taddr, r);
-      if (a.passes == 3) {
-        uint32_t rc[32];
-        tmem_ld32(taddr + BN, rc);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(rc[j]));
+      for (int ac = 1; ac <= NACC; ++ac) {   // remaining main accumulators, then corr (slot NACC)
+        if (ac < NACC ? ac < nacc_used : a.passes == 3) {
+          uint32_t rc[32];
+          tmem_ld32(taddr + ac * BN, rc);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(rc[j]));
+        }
       }
       if (row < a.M) {
         const int cbase = n0 + c0;
@@ -418,7 +441,7 @@ int launch(const TcGemmP& p, cudaStream_t st) {
   a.C = p.C; a.bias = p.bias; a.M = p.M; a.N = p.N; a.K0 = p.K0; a.K1 = p.K1;
   a.ldc = p.ldc; a.sC = p.sC; a.sBias = p.sBias;
   a.zA0 = p.sA0 != 0; a.zA1 = p.sA1 != 0; a.zB0 = p.sB0 != 0; a.zB1 = p.sB1 != 0;
-  a.accumulate = p.accumulate; a.passes = p.passes; a.raw_hi = p.raw_hi;
+  a.accumulate = p.accumulate; a.passes = p.passes; a.raw_hi = p.raw_hi; a.lo_round = p.lo_round;
   a.splitk = 1; a.chunks_per_split = 0;
   dim3 grid((unsigned)cdiv(p.M, BM), (unsigned)cdiv(p.N, BN), (unsigned)p.batch);
   ProfScope prof(st, PROF_TC_GEMM, 2.0 * p.M * p.N * (double)(p.K0 + p.K1) * p.batch);
@@ -440,6 +463,9 @@ int launch_tn(const TcGemmTnP& p, cudaStream_t st) {
   const long long tiles = cdiv(p.M, BM) * cdiv(p.N, BN) * p.batch;
   // one wave: as many splits as fit on the 148 SMs without spilling into a second, nearly empty wave
   long long splitk = p.splitk > 0 ? p.splitk : (tiles >= 148 ? 1 : 148 / tiles);
+  // accumulate-truncation bound (see the kernel): at most kMaxRowsPerSplit batch rows per CTA
+  constexpr long long kMaxRowsPerSplit = 1536;
+  if (p.splitk <= 0 && splitk < cdiv(p.K, kMaxRowsPerSplit)) splitk = cdiv(p.K, kMaxRowsPerSplit);
   if (splitk > nk) splitk = nk;
   if (splitk < 1) splitk = 1;
   const long long per = cdiv(nk, splitk);
@@ -450,7 +476,7 @@ int launch_tn(const TcGemmTnP& p, cudaStream_t st) {
   a.K0 = (int)p.K; a.K1 = 0;
   a.ldc = p.ldc; a.sC = p.sC; a.sBias = 0;
   a.zA0 = p.sA != 0; a.zB0 = p.sB != 0; a.zA1 = a.zB1 = 0;
-  a.accumulate = 1; a.passes = p.passes; a.raw_hi = 0;
+  a.accumulate = 1; a.passes = p.passes; a.raw_hi = 0; a.lo_round = p.lo_round;
   a.splitk = (int)splitk; a.chunks_per_split = (int)per;
   dim3 grid((unsigned)cdiv(p.M, BM), (unsigned)cdiv(p.N, BN), (unsigned)(splitk * p.batch));
   ProfScope prof(st, PROF_TC_WGRAD, 2.0 * p.M * p.N * (double)p.K * p.batch);
@@ -474,7 +500,11 @@ int tc_gemm(const TcGemmP& p, cudaStream_t st) {
   NF_CHECK_ARG(tc_gemm_supported(p), NF_E_UNSUPPORTED,
                "tc_gemm: operands must be 16-byte aligned with row pitches that are multiples of 4 floats");
   // small problems: prefer more, smaller CTAs (3 pipeline stages) over filling TMEM
-  const long long ctas256 = cdiv(p.M, BM) * cdiv(p.N, 256) * p.batch;
+  // BN = 256 fills TMEM with one main + one corr accumulator; BN <= 128 leaves room for the three rotating
+  // main accumulators that keep long reductions inside fp32 parity, so 256 is only used for short ones.
+  static const int wide_ok = [] { const char* e = getenv("NF_B200_BN256"); return e ? atoi(e) : 0; }();
+  const long long ctas256 = (wide_ok == 1 || (wide_ok == 0 && p.K0 + p.K1 <= 128))
+                                ? cdiv(p.M, BM) * cdiv(p.N, 256) * p.batch : 0;
   if (p.bk == 32) {
     if (p.N > 128 && ctas256 >= 120) return launch<256, 2, 32>(p, st);
     if (p.N > 64) return launch<128, 3, 32>(p, st);
@@ -495,6 +525,11 @@ int tc_gemm_tn(const TcGemmTnP& p, cudaStream_t st) {
   if (p.M <= 0 || p.N <= 0 || p.batch <= 0 || p.K <= 0) return 0;
   NF_CHECK_ARG(tc_gemm_tn_supported(p), NF_E_UNSUPPORTED,
                "tc_gemm_tn: operands must be 16-byte aligned with row pitches that are multiples of 4 floats");
+  static const int wide_ok = [] { const char* e = getenv("NF_B200_BN256"); return e ? atoi(e) : 0; }();
+  if (wide_ok != 1) {
+    if (p.bk == 32) return p.N > 64 ? launch_tn<128, 3, 32>(p, st) : launch_tn<64, 4, 32>(p, st);
+    return p.N > 64 ? launch_tn<128, 6, 16>(p, st) : launch_tn<64, 8, 16>(p, st);
+  }
   if (p.bk == 32) {
     if (p.N > 128) return launch_tn<256, 2, 32>(p, st);
     if (p.N > 64) return launch_tn<128, 3, 32>(p, st);

@@ -86,12 +86,17 @@ class MetaBlock(nn.Module):
 
 
 class _Flow(torch.autograd.Function):
-    """autograd bridge: forward = nf_flow_forward, backward = nf_flow_backward."""
+    """autograd bridge: forward = nf_flow_forward, backward = nf_flow_backward.
+
+    ``params`` is either every trainable parameter (``fast_param_grads=False``: gradients are returned
+    to autograd, one AccumulateGrad node per parameter) or a single carrier parameter
+    (``fast_param_grads=True``: backward writes the flat gradient arena and sets ``p.grad`` views itself)."""
 
     @staticmethod
-    def forward(ctx, model: "RealNVP", want_stash: bool, x, y, *params):
-        z, logdet, outs, stash, packed = model._run_forward(x, y, want_stash)
+    def forward(ctx, model: "RealNVP", fast: bool, x, y, *params):
+        z, logdet, outs, stash, packed = model._run_forward(x, y, True)
         ctx.model = model
+        ctx.fast = fast
         ctx.stash = stash
         ctx.packed = packed
         ctx.pver = model._params_version()
@@ -104,19 +109,24 @@ class _Flow(torch.autograd.Function):
     def backward(ctx, dz, dld, _douts):
         model = ctx.model
         if ctx.stash is None:
-            raise RuntimeError("nf_b200: backward called on a forward that ran without a stash")
+            raise RuntimeError("nf_b200: backward called twice on the same forward (the stash is freed after use)")
         if ctx.pver != model._params_version():
             raise RuntimeError("nf_b200: parameters were modified between forward and backward")
         (y,) = ctx.saved_tensors
         need_x = ctx.needs_input_grad[2]
         need_y = ctx.needs_input_grad[3]
         need_p = any(ctx.needs_input_grad[4:])
-        dx, dy, dflat = model._run_backward(ctx.stash, ctx.packed, y, ctx.B, dz, dld, need_x, need_y, need_p)
-        if need_p:
-            views = model._grad_views(dflat)
-            pg = tuple(v if need else None for v, need in zip(views, ctx.needs_input_grad[4:]))
+        nparams = len(ctx.needs_input_grad) - 4
+        if ctx.fast:
+            dx, dy = model._run_backward_fast(ctx.stash, ctx.packed, y, ctx.B, dz, dld, need_x, need_y, need_p)
+            pg = (None,) * nparams
         else:
-            pg = (None,) * (len(ctx.needs_input_grad) - 4)
+            dx, dy, dflat = model._run_backward(ctx.stash, ctx.packed, y, ctx.B, dz, dld, need_x, need_y, need_p)
+            if need_p:
+                views = model._grad_views(dflat)
+                pg = tuple(v if need else None for v, need in zip(views, ctx.needs_input_grad[4:]))
+            else:
+                pg = (None,) * nparams
         ctx.stash = None
         return (None, None, dx, dy) + pg
 
@@ -128,11 +138,20 @@ class RealNVP(nn.Module):
     (/root/reference/unsupservised-gcrl/nf.py): ``first_hidden=channels+cond_channels`` (:94,101),
     ``ln_eps=1e-6`` (flax LayerNorm default), and ``precision``:
     ``"fp32"`` (tcgen05 3xTF32, fp32-parity), ``"fp32_simt"`` (FFMA), ``"bf16"``.
+
+    ``fast_param_grads`` (default on): ``loss.backward()`` writes all parameter gradients into one
+    persistent flat arena with a single library call and points every ``p.grad`` at its view of that
+    arena (accumulating if gradients are already present), instead of handing ~24 tensors per block
+    to autograd one AccumulateGrad node at a time -- the same trade DistributedDataParallel's
+    ``gradient_as_bucket_view`` makes.  Gradients w.r.t. ``x`` and ``y`` always flow through autograd.
+    Turn it off for ``torch.autograd.grad(..., model.parameters())`` or parameter hooks.
     """
 
     def __init__(self, in_channels, channels, cond_channels, n_layers, prior, *,
-                 first_hidden: Optional[int] = None, ln_eps: float = 1e-5, precision: str = "fp32_simt"):
+                 first_hidden: Optional[int] = None, ln_eps: float = 1e-5, precision: str = "fp32_simt",
+                 fast_param_grads: bool = True):
         super().__init__()
+        self.fast_param_grads = bool(fast_param_grads)
         self.in_channels = int(in_channels)
         self.channels = int(channels)
         self.cond_channels = int(cond_channels)
@@ -153,6 +172,8 @@ class RealNVP(nn.Module):
         self._packed: Optional[torch.Tensor] = None
         self._packed_key = None
         self._ws: Optional[torch.Tensor] = None
+        self._gflat: Optional[torch.Tensor] = None
+        self._gviews = None
         self._dp_group = None
         self._dp_world = 1
         self._flatten()
@@ -201,8 +222,11 @@ class RealNVP(nn.Module):
         if pos < self._layout.total:
             sizes.append(self._layout.total - pos)
         self._split_sizes, self._split_picks = sizes, picks
+        self._tparams = [p for p, _ in self._trainable]
         self._packed = None
         self._packed_key = None
+        self._gflat = None
+        self._gviews = None
 
     def _apply(self, fn, recurse=True):
         out = super()._apply(fn, recurse)
@@ -218,7 +242,10 @@ class RealNVP(nn.Module):
                 and p0.device == self._flat.device)
 
     def _params_version(self):
-        return sum(p._version for p, _ in self._slots)
+        v = 0
+        for p in self._tparams:
+            v += p._version
+        return v
 
     def _grad_views(self, dflat):
         chunks = dflat.split_with_sizes(self._split_sizes)
@@ -251,19 +278,22 @@ class RealNVP(nn.Module):
 
     def _prepared(self, what, device):
         """Derived parameter tables (W, W^-1, folded LayerNorm affine, log|det|), rebuilt whenever a
-        parameter changed (torch_fcnf.py:34-38, 45-54 redo this in every call)."""
+        parameter changed (torch_fcnf.py:34-38, 45-54 redo this in every call).  The buffer is
+        persistent, so the library's cached launch graphs keep seeing the same pointer."""
         key = (self._params_version(), self._flat.data_ptr())
         have = self._packed_key
         if self._packed is not None and have is not None and have[0] == key and (have[1] & what) == what:
             return self._packed
-        nbytes = lib.nf_flow_packed_bytes(ctypes.byref(self._desc))
-        packed = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        if self._packed is None or self._packed.device != device:
+            nbytes = lib.nf_flow_packed_bytes(ctypes.byref(self._desc))
+            self._packed = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        packed = self._packed
         ws = self._workspace(1, device)
         if have is not None and have[0] == key:
             what |= have[1]
         _lib.check(lib.nf_flow_prepare(ctypes.byref(self._desc), self._flat.data_ptr(), packed.data_ptr(), what,
                                        ws.data_ptr(), ws.numel(), self._stream(device)), "nf_flow_prepare")
-        self._packed, self._packed_key = packed, (key, what)
+        self._packed_key = (key, what)
         return packed
 
     def _run_forward(self, x, y, want_stash):
@@ -292,7 +322,7 @@ class RealNVP(nn.Module):
                 ws.data_ptr(), ws.numel(), self._stream(dev)), "nf_flow_forward")
         return z, logdet, outs, stash, packed
 
-    def _run_backward(self, stash, packed, y, B, dz, dld, need_x, need_y, need_p):
+    def _run_backward(self, stash, packed, y, B, dz, dld, need_x, need_y, need_p, out=None):
         dev = y.device
         D, R = self.in_channels, self.cond_channels
         with torch.cuda.device(dev):
@@ -300,7 +330,9 @@ class RealNVP(nn.Module):
             dz, dld, y = _dense(dz), _dense(dld), _dense(y)
             dx = torch.empty((B, D), dtype=torch.float32, device=dev) if need_x else None
             dy = torch.empty((B, R), dtype=torch.float32, device=dev) if need_y else None
-            dflat = torch.empty(self._layout.total, dtype=torch.float32, device=dev) if need_p else None
+            dflat = None
+            if need_p:
+                dflat = out if out is not None else torch.empty(self._layout.total, dtype=torch.float32, device=dev)
             ptr = lambda t: t.data_ptr() if t is not None else None
             _lib.check(lib.nf_flow_backward(
                 ctypes.byref(self._desc), self._flat.data_ptr(), packed.data_ptr(), stash.data_ptr(), y.data_ptr(), B,
@@ -309,6 +341,47 @@ class RealNVP(nn.Module):
             if need_p and self._dp_world > 1:
                 self._allreduce_grads(dflat)
         return dx, dy, dflat
+
+    def _run_backward_fast(self, stash, packed, y, B, dz, dld, need_x, need_y, need_p):
+        """Backward with the parameter gradients written straight into the persistent flat arena."""
+        dev = y.device
+        tp = self._tparams
+        if not need_p:
+            dx, dy, _ = self._run_backward(stash, packed, y, B, dz, dld, need_x, need_y, False)
+            return dx, dy
+        if self._gflat is None or self._gflat.device != dev:
+            self._gflat = torch.zeros(self._layout.total, dtype=torch.float32, device=dev)
+            self._gviews = self._grad_views(self._gflat)
+        views = self._gviews
+        fresh = True          # every p.grad is None: write the arena in place and hand out the views
+        ours = True           # every p.grad already is our view: accumulate with one flat add
+        for p, v in zip(tp, views):
+            if not p.requires_grad:
+                continue
+            g = p.grad
+            if g is not None:
+                fresh = False
+                if g.data_ptr() != v.data_ptr() or g.shape != v.shape:
+                    ours = False
+            else:
+                ours = False
+        target = self._gflat if fresh else None
+        dx, dy, dflat = self._run_backward(stash, packed, y, B, dz, dld, need_x, need_y, True, out=target)
+        if fresh:
+            for p, v in zip(tp, views):
+                if p.requires_grad:
+                    p.grad = v
+        elif ours:
+            self._gflat.add_(dflat)
+        else:
+            for p, v in zip(tp, self._grad_views(dflat)):
+                if not p.requires_grad:
+                    continue
+                if p.grad is None:
+                    p.grad = v.clone()
+                else:
+                    p.grad.add_(v)
+        return dx, dy
 
     # ------------------------------------------------------------------ data parallel
     def enable_data_parallel(self, process_group=None):
@@ -329,11 +402,13 @@ class RealNVP(nn.Module):
         """-> (z, outputs, log_dets): torch_fcnf.py:134-141.  ``outputs`` (list of n_layers (B, D)
         tensors, the block outputs logged at torch_nfbc_ant.py:286-287) are not differentiable."""
         self._check_inputs(x, y)
-        params = [p for p, _ in self._trainable]
-        need_grad = torch.is_grad_enabled() and (
-            x.requires_grad or y.requires_grad or any(p.requires_grad for p in params))
+        params = [p for p in self._tparams if p.requires_grad] if torch.is_grad_enabled() else []
+        need_grad = torch.is_grad_enabled() and (x.requires_grad or y.requires_grad or len(params) > 0)
         if need_grad:
-            z, logdet, outs = _Flow.apply(self, True, x, y, *params)
+            if self.fast_param_grads:
+                z, logdet, outs = _Flow.apply(self, True, x, y, *params[:1])
+            else:
+                z, logdet, outs = _Flow.apply(self, False, x, y, *params)
         else:
             z, logdet, outs, _, _ = self._run_forward(x, y, False)
         return z, list(outs.unbind(0)), logdet

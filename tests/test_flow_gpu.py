@@ -277,3 +277,96 @@ def test_fresh_model_is_identity_coupling_and_state_dict_roundtrip(tmp_path):
     opt.step()
     z3, _, _ = m2(t(x), t(y))
     assert not torch.equal(z2, z3)
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_fast_param_grads_match_autograd_path_and_accumulate(precision):
+    """fast_param_grads (flat gradient arena + p.grad views) gives the gradients the plain autograd
+    path returns, accumulates like autograd when gradients are already present, and respects
+    frozen parameters."""
+    D, C, R, n, B = 8, 64, 16, 3, 130
+    sd = synth.make_state_dict(D, C, R, n, seed=21)
+    x, y, _ = synth.make_safe_inputs(sd, n, B, D, R, seed=22)
+    cfg = dict(D=D, C=C, R=R, n=n, B=B)
+    slow = build_model(cfg, sd, precision, fast_param_grads=False)
+    fast = build_model(cfg, sd, precision, fast_param_grads=True)
+
+    def run(m):
+        xt = t(x).requires_grad_(True)
+        (-m.log_prob(xt, t(y)).mean()).backward()
+        return xt.grad
+
+    gx_s, gx_f = run(slow), run(fast)
+    tol = 0.0 if precision == "fp32_simt" else 1e-6      # atomics order differs between calls on the tensor path
+    assert rel_err(gx_f.cpu().numpy(), gx_s.cpu().numpy()) <= 1e-6
+    ref = {k: p.grad.clone() for k, p in slow.named_parameters() if p.requires_grad}
+    for k, p in fast.named_parameters():
+        if p.requires_grad:
+            assert p.grad is not None and p.grad.shape == p.shape
+            assert rel_err(p.grad.cpu().numpy(), ref[k].cpu().numpy()) <= max(tol, 2e-6), k
+        else:
+            assert p.grad is None
+    # second backward without zero_grad accumulates (autograd semantics), in both modes
+    run(slow); run(fast)
+    for k, p in fast.named_parameters():
+        if p.requires_grad:
+            assert rel_err(p.grad.cpu().numpy(), 2 * ref[k].cpu().numpy()) <= 5e-6, k
+            assert rel_err(dict(slow.named_parameters())[k].grad.cpu().numpy(), 2 * ref[k].cpu().numpy()) <= 5e-6, k
+    # zero_grad(set_to_none=True) then a third backward: back to a single gradient
+    fast.zero_grad(set_to_none=True)
+    run(fast)
+    for k, p in fast.named_parameters():
+        if p.requires_grad:
+            assert rel_err(p.grad.cpu().numpy(), ref[k].cpu().numpy()) <= 5e-6, k
+    # a foreign gradient tensor (not our view) is accumulated into, not replaced
+    fast.zero_grad(set_to_none=True)
+    w = fast.blocks[0].t[0].weight
+    w.grad = torch.ones_like(w)
+    run(fast)
+    assert rel_err((w.grad - 1).cpu().numpy(), ref["blocks.0.t.0.weight"].cpu().numpy()) <= 5e-6
+    # frozen parameters get no gradient and do not block the others
+    fast.zero_grad(set_to_none=True)
+    fast.blocks[0].t[0].weight.requires_grad_(False)
+    run(fast)
+    assert fast.blocks[0].t[0].weight.grad is None
+    assert rel_err(fast.blocks[1].s[3].weight.grad.cpu().numpy(), ref["blocks.1.s.3.weight"].cpu().numpy()) <= 5e-6
+    # optimizer step through the views changes the arena the kernels read
+    opt = torch.optim.SGD([p for p in fast.parameters() if p.requires_grad], lr=0.1)
+    before = fast._flat.clone()
+    opt.step()
+    assert not torch.equal(before, fast._flat)
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_launch_graph_replay_is_bit_identical(precision):
+    """The library replays a cached CUDA graph when the same (descriptor, B, pointers) come back: the
+    replayed forward / inverse give bit-identical results to the eager first call, also after the
+    parameters changed in place (the graph reads the arena, it does not bake values in)."""
+    D, C, R, n, B = 9, 64, 24, 3, 200
+    sd = synth.make_state_dict(D, C, R, n, seed=31)
+    x, y, _ = synth.make_safe_inputs(sd, n, B, D, R, seed=32)
+    model = build_model(dict(D=D, C=C, R=R, n=n, B=B), sd, precision)
+    xt, yt = t(x), t(y)
+    r0 = _lib.graph_stats()
+    outs = []
+    with torch.no_grad():
+        for _ in range(4):
+            z, _, ld = model(xt, yt)
+            outs.append((z.clone(), ld.clone()))
+            del z, ld                                   # same addresses come back from the caching allocator
+    r1 = _lib.graph_stats()
+    assert r1[0] > r0[0], "no graph replay happened"
+    for z, ld in outs[1:]:
+        assert torch.equal(z, outs[0][0]) and torch.equal(ld, outs[0][1])
+    with torch.no_grad():
+        for p in model.parameters():
+            if p.requires_grad:
+                p.mul_(1.01)
+        z2, _, ld2 = model(xt, yt)
+        _lib.lib.nf_graphs_enable(0)
+        try:
+            z3, _, ld3 = model(xt, yt)
+        finally:
+            _lib.lib.nf_graphs_enable(1)
+    assert not torch.equal(z2, outs[0][0])
+    assert torch.equal(z2, z3) and torch.equal(ld2, ld3)
