@@ -239,44 +239,42 @@ static int conditioners(const Dims& m, const NfParamLayout& pl, const PackedLayo
                         int64_t r_net, uint32_t* m1, uint32_t* m2, int64_t m_net, int mw1, int mw2,
                         bool with_last, cudaStream_t st) {
   const int64_t Hm = std::max(m.H1, m.C);
-  {  // u1
+  // Linear + LeakyReLU + LayerNorm as ONE tcgen05 kernel (row statistics exchanged across the CTA cluster
+  // that spans the row) when the width allows it; otherwise GEMM -> u, then the row-wise kernel.
+  auto linear_lrelu_ln = [&](TcGemmP g, int N, const float* bias, int64_t bias_net, float* xh, int64_t xh_net,
+                             float* r, uint32_t* mk, int mw) -> int {
+    g.M = (int)B; g.N = N; g.batch = 2;
+    if (g.K0 + g.K1 >= 512) g.raw_hi = 0;
+    TcGemmP f = g;
+    f.C = xh; f.ldc = N; f.sC = xh_net; f.bias = bias; f.sBias = bias_net;
+    f.epi.kind = TC_EPI_LN_FWD; f.epi.eps = m.eps;
+    f.epi.rstd = r; f.epi.sRstd = r_net; f.epi.mask = mk; f.epi.sMask = m_net; f.epi.mw = mk ? mw : 0;
+    if (m.prec == NF_PREC_TF32X3 && (g.K0 + g.K1) >= 32 && tc_gemm_epi_supported(f)) return tc_gemm(f, st);
+    g.C = w.u; g.ldc = N; g.sC = B * Hm;
+    NF_TRY(linear_nt(m.prec, g, st));
+    LnFwdP p{};
+    p.u = w.u; p.u_net = B * Hm;
+    p.bias = bias; p.bias_net = bias_net;
+    p.xh = xh; p.xh_net = xh_net;
+    p.rstd = r; p.rstd_net = r_net;
+    p.mask = mk; p.mask_net = m_net; p.mw = mw;
+    p.N = N; p.nets = 2; p.B = B; p.eps = m.eps;
+    return lrelu_ln_fwd(p, st);
+  };
+  {  // layer 1: [x_cond | y] W1^T + b1
     TcGemmP g;
     g.A0 = xc; g.lda0 = ldxc; g.K0 = m.dc;
     if (m.R > 0) { g.A1 = y; g.lda1 = m.R; g.K1 = m.R; }
     // W1p: W1 with the y columns moved to the 16-byte aligned column dcp (TMA operand)
     g.B0 = kb + kl.net0 + kl.W1p; g.ldb0 = kl.K1p; g.sB0 = kl.net_stride;
     if (m.R > 0) { g.B1 = g.B0 + kl.dcp; g.ldb1 = kl.K1p; g.sB1 = kl.net_stride; }
-    g.C = w.u; g.ldc = m.H1; g.sC = B * Hm;
-    g.M = (int)B; g.N = m.H1; g.batch = 2;
-    NF_TRY(linear_nt(m.prec, g, st));
+    NF_TRY(linear_lrelu_ln(g, m.H1, pb + pl.slot_off[NF_P_B1], pl.net_stride, xh1, xh1_net, r1, m1, mw1));
   }
-  {
-    LnFwdP p{};
-    p.u = w.u; p.u_net = B * Hm;
-    p.bias = pb + pl.slot_off[NF_P_B1]; p.bias_net = pl.net_stride;
-    p.xh = xh1; p.xh_net = xh1_net;
-    p.rstd = r1; p.rstd_net = r_net;
-    p.mask = m1; p.mask_net = m_net; p.mw = mw1;
-    p.N = m.H1; p.nets = 2; p.B = B; p.eps = m.eps;
-    NF_TRY(lrelu_ln_fwd(p, st));
-  }
-  {  // u2
+  {  // layer 2: x_hat1 W2f^T + b2f
     TcGemmP g;
     g.A0 = xh1; g.lda0 = m.H1; g.K0 = m.H1; g.sA0 = xh1_net;
     g.B0 = kb + kl.net0 + kl.W2f; g.ldb0 = m.H1; g.sB0 = kl.net_stride;
-    g.C = w.u; g.ldc = m.C; g.sC = B * Hm;
-    g.M = (int)B; g.N = m.C; g.batch = 2;
-    NF_TRY(linear_nt(m.prec, g, st));
-  }
-  {
-    LnFwdP p{};
-    p.u = w.u; p.u_net = B * Hm;
-    p.bias = kb + kl.net0 + kl.b2f; p.bias_net = kl.net_stride;
-    p.xh = xh2; p.xh_net = xh2_net;
-    p.rstd = r2; p.rstd_net = r_net;
-    p.mask = m2; p.mask_net = m_net; p.mw = mw2;
-    p.N = m.C; p.nets = 2; p.B = B; p.eps = m.eps;
-    NF_TRY(lrelu_ln_fwd(p, st));
+    NF_TRY(linear_lrelu_ln(g, m.C, kb + kl.net0 + kl.b2f, kl.net_stride, xh2, xh2_net, r2, m2, mw2));
   }
   if (with_last) {  // o = x_hat2 W3f^T  (N = D/2: FFMA unless the flow is wide)
     TcGemmP g;
@@ -699,15 +697,30 @@ int nf_flow_backward(const NfFlowDesc* desc, const float* params, const void* pa
       g.M = m.C; g.N = m.H1; g.K = B; g.batch = 2;
       NF_TRY(wgrad_tn(m.prec, g, st));
     }
+    bool ln1_fused = false;
     {  // f. d x_hat1 = du2 W2f   (K-major B operand = W2f^T)
       TcGemmP g;
       g.A0 = w.gA; g.lda0 = m.C; g.sA0 = B * Hm; g.K0 = m.C;
       g.B0 = kb + kl.net0 + kl.W2fT; g.ldb0 = m.C; g.sB0 = kl.net_stride;
       g.C = w.gB; g.ldc = m.H1; g.sC = B * Hm;
       g.M = (int)B; g.N = m.H1; g.batch = 2;
-      NF_TRY(linear_nt(m.prec, g, st));
+      if (v2 && m.prec == NF_PREC_TF32X3 && m.C >= 32) {
+        // f + g in one kernel: LayerNorm-1 / LeakyReLU-1 backward as the GEMM's row-wise epilogue; the bias
+        // gradient (column sums of du1) is taken by the block's column-reduction launch
+        TcGemmP f = g;
+        if (f.K0 >= 512) f.raw_hi = 0;
+        f.epi.kind = TC_EPI_LN_BWD;
+        f.epi.xh = sb + sl.xh1; f.epi.ldxh = m.H1; f.epi.sXh = sl.net_stride;
+        f.epi.rstd = const_cast<float*>(sb + sl.r1); f.epi.sRstd = sl.net_stride;
+        f.epi.mask = const_cast<uint32_t*>(m1); f.epi.sMask = sl.net_stride; f.epi.mw = sl.mw1;
+        if (tc_gemm_epi_supported(f)) {
+          NF_TRY(tc_gemm(f, st));
+          ln1_fused = true;
+        }
+      }
+      if (!ln1_fused) NF_TRY(linear_nt(m.prec, g, st));
     }
-    {  // g. through LayerNorm + LeakyReLU (layer 1); column sums -> slot b1
+    if (!ln1_fused) {  // g. through LayerNorm + LeakyReLU (layer 1); column sums -> slot b1
       LnBwdP p{};
       p.g = w.gB; p.g_net = B * Hm;
       p.xh = sb + sl.xh1; p.xh_net = sl.net_stride;
@@ -768,6 +781,10 @@ int nf_flow_backward(const NfFlowDesc* desc, const float* params, const void* pa
         jobs[1].A = w.gB; jobs[1].lda = m.H1; jobs[1].sA = B * Hm; jobs[1].N = m.H1;
         jobs[1].coef = zi; jobs[1].ldcf = m.D; jobs[1].sCf = 0; jobs[1].m = m.dc;
         jobs[1].out = dn + pl.slot_off[NF_P_W1]; jobs[1].so_i = 1; jobs[1].so_c = m.K1; jobs[1].sOut = pl.net_stride;
+        if (ln1_fused) {   // gb1 = colsum(du1): same array as A, loaded once
+          jobs[1].A2 = w.gB; jobs[1].lda2 = m.H1; jobs[1].sA2 = B * Hm;
+          jobs[1].out2 = dn + pl.slot_off[NF_P_B1]; jobs[1].sOut2 = pl.net_stride;
+        }
         jobs[1].batch = 2;
         // dW = x_in^T dxp
         jobs[2].A = w.dxp; jobs[2].lda = m.D; jobs[2].N = m.D;

@@ -274,8 +274,14 @@ int rows_per_warp_for(long long B) {
 // ---------------------------------------------------------------------------------------------
 // multi-job column reduction
 // ---------------------------------------------------------------------------------------------
-constexpr int kColU = 8;     // rows per warp and load batch
-constexpr int kColSub = 256;   // rows per shared-memory coefficient sub-chunk
+// A warp covers 128 columns of one row (lane = 4 adjacent columns, one 128-bit load), the 8 warps of a
+// CTA take rows w, w + 8, ... of the CTA's row chunk; coefficients of the chunk sit in shared memory
+// (zero-padded to MAXM so the FMA loop needs no predicates).  Loads of kColU rows are issued before
+// the first use.  History (ncu, C2a): one column per lane + one row per dependent load = 40 us; batched
+// loads = 31 us, instruction-bound (11 M warp instructions); this layout issues ~3x fewer.
+constexpr int kColU = 4;       // rows per warp and load batch
+constexpr int kColSub = 128;   // rows per shared-memory coefficient sub-chunk
+constexpr int kColTile = 128;  // columns per CTA
 struct ColArgs {
   ColJob j[kColMaxJobs];
   int njobs;
@@ -283,75 +289,99 @@ struct ColArgs {
   int rows_per_cta;
 };
 
+__device__ __forceinline__ float4 ld4(const float* base, long long off, int nvalid, bool vec) {
+  if (nvalid <= 0) return make_float4(0.f, 0.f, 0.f, 0.f);
+  if (vec) return __ldg(reinterpret_cast<const float4*>(base + off));
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  v.x = __ldg(base + off);
+  if (nvalid > 1) v.y = __ldg(base + off + 1);
+  if (nvalid > 2) v.z = __ldg(base + off + 2);
+  if (nvalid > 3) v.w = __ldg(base + off + 3);
+  return v;
+}
+
 template <int MAXM>
-__global__ void __launch_bounds__(256) k_col_reduce(const __grid_constant__ ColArgs a) {
-  __shared__ float s_coef[kColSub * MAXM];
-  __shared__ float s_acc[(MAXM + 2) * 32];
-  int job = 0, z = blockIdx.z;
-  while (job < a.njobs - 1 && z >= a.j[job].batch) { z -= a.j[job].batch; ++job; }
-  const ColJob& J = a.j[job];
-  if ((int)blockIdx.y * 32 >= J.N) return;   // CTA-uniform
-  const int tx = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int c = blockIdx.y * 32 + tx, m = J.m;
-  const bool colok = c < J.N;
+__device__ __forceinline__ void col_body(const ColJob& J, int z, long long B, int rows_per_cta, float* s_coef,
+                                         float* s_acc) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = blockIdx.y * kColTile + lane * 4, m = J.m;
+  const int nvalid = min(4, J.N - c);
   const float* A = J.out ? J.A + z * J.sA : nullptr;
   const float* A2 = (J.out2 && J.A2) ? J.A2 + z * J.sA2 : nullptr;
   const float* coef = m ? J.coef + z * J.sCf : nullptr;
+  const bool same2 = A2 != nullptr && A2 == A && J.lda2 == J.lda;   // column sums of the weighted matrix itself
+  const bool vecA = A && (J.lda & 3) == 0 && (reinterpret_cast<uintptr_t>(A) & 15u) == 0 && nvalid == 4;
+  const bool vecA2 = A2 && (J.lda2 & 3) == 0 && (reinterpret_cast<uintptr_t>(A2) & 15u) == 0 && nvalid == 4;
   const bool do3 = J.out3 != nullptr && blockIdx.y == 0 && m > 0;
-  const long long row_begin = (long long)blockIdx.x * a.rows_per_cta;
-  const long long row_end = min(a.B, row_begin + (long long)a.rows_per_cta);
-  float acc[MAXM], acc2 = 0.f, acc3 = 0.f;
+  const long long row_begin = (long long)blockIdx.x * rows_per_cta;
+  const long long row_end = min(B, row_begin + (long long)rows_per_cta);
+  float4 acc[MAXM], acc2 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float acc3 = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAXM; ++i) acc[i] = 0.f;
-  for (int e = threadIdx.x; e < (MAXM + 2) * 32; e += blockDim.x) s_acc[e] = 0.f;
+  for (int i = 0; i < MAXM; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int e = threadIdx.x; e < (MAXM + 2) * kColTile; e += blockDim.x) s_acc[e] = 0.f;
 
   for (long long sub = row_begin; sub < row_end; sub += kColSub) {
     const int nsub = (int)min((long long)kColSub, row_end - sub);
     if (m) {
-      for (int e = threadIdx.x; e < nsub * m; e += blockDim.x) {
-        const int r = e / m, i = e - r * m;
-        s_coef[r * MAXM + i] = coef[(sub + r) * J.ldcf + i];
+#pragma unroll 4
+      for (int e = threadIdx.x; e < nsub * MAXM; e += blockDim.x) {
+        const int r = e / MAXM, i = e % MAXM;
+        s_coef[e] = i < m ? __ldg(coef + (sub + r) * J.ldcf + i) : 0.f;
       }
     }
     __syncthreads();
-    // batches of kColU rows per warp: all global loads of a batch are issued before the first use (the
-    // straightforward loop made one dependent DRAM/L2 round trip per row: 32 per warp, ncu 40 us)
     for (int r0 = w; r0 < nsub; r0 += 8 * kColU) {
-      float av[kColU], a2[kColU];
+      float4 av[kColU], a2[kColU];
 #pragma unroll
       for (int u = 0; u < kColU; ++u) {
         const int r = r0 + 8 * u;
-        const bool ok = colok && r < nsub;
-        av[u] = (ok && A) ? __ldg(A + (sub + r) * J.lda + c) : 0.f;
-        a2[u] = (ok && A2) ? __ldg(A2 + (sub + r) * J.lda2 + c) : 0.f;
+        const int nv = r < nsub ? nvalid : 0;
+        av[u] = A ? ld4(A, (sub + r) * J.lda + c, nv, vecA) : make_float4(0.f, 0.f, 0.f, 0.f);
+        a2[u] = A2 ? (same2 ? av[u] : ld4(A2, (sub + r) * J.lda2 + c, nv, vecA2)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
       for (int u = 0; u < kColU; ++u) {
         const int r = r0 + 8 * u;
         if (r < nsub) {
+          if (A) {
 #pragma unroll
-          for (int i = 0; i < MAXM; ++i)
-            if (i < m) acc[i] = fmaf(s_coef[r * MAXM + i], av[u], acc[i]);
-          acc2 += a2[u];
-          if (do3 && tx < m) acc3 += s_coef[r * MAXM + tx];
+            for (int i4 = 0; i4 < MAXM; i4 += 4) {
+              const float4 cf = *reinterpret_cast<const float4*>(s_coef + r * MAXM + i4);
+              const float cfv[4] = {cf.x, cf.y, cf.z, cf.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                acc[i4 + k].x = fmaf(cfv[k], av[u].x, acc[i4 + k].x); acc[i4 + k].y = fmaf(cfv[k], av[u].y, acc[i4 + k].y);
+                acc[i4 + k].z = fmaf(cfv[k], av[u].z, acc[i4 + k].z); acc[i4 + k].w = fmaf(cfv[k], av[u].w, acc[i4 + k].w);
+              }
+            }
+          }
+          acc2.x += a2[u].x; acc2.y += a2[u].y; acc2.z += a2[u].z; acc2.w += a2[u].w;
+          if (do3 && lane < m) acc3 += s_coef[r * MAXM + lane];
         }
       }
     }
     __syncthreads();
   }
   // combine the 8 warps through shared memory, then one global atomic per element and CTA
-  if (colok) {
+  if (nvalid > 0) {
     if (A) {
 #pragma unroll
       for (int i = 0; i < MAXM; ++i)
-        if (i < m) atomicAdd(&s_acc[i * 32 + tx], acc[i]);
+        if (i < m) {
+          float* d = s_acc + i * kColTile + lane * 4;
+          atomicAdd(d, acc[i].x); atomicAdd(d + 1, acc[i].y); atomicAdd(d + 2, acc[i].z); atomicAdd(d + 3, acc[i].w);
+        }
     }
-    if (A2) atomicAdd(&s_acc[MAXM * 32 + tx], acc2);
+    if (A2) {
+      float* d = s_acc + MAXM * kColTile + lane * 4;
+      atomicAdd(d, acc2.x); atomicAdd(d + 1, acc2.y); atomicAdd(d + 2, acc2.z); atomicAdd(d + 3, acc2.w);
+    }
   }
-  if (do3 && tx < m) atomicAdd(&s_acc[(MAXM + 1) * 32 + tx], acc3);
+  if (do3 && lane < m) atomicAdd(&s_acc[(MAXM + 1) * kColTile + lane], acc3);
   __syncthreads();
-  for (int e = threadIdx.x; e < (MAXM + 2) * 32; e += blockDim.x) {
-    const int i = e >> 5, t = e & 31, cc = blockIdx.y * 32 + t;
+  for (int e = threadIdx.x; e < (MAXM + 2) * kColTile; e += blockDim.x) {
+    const int i = e / kColTile, t = e % kColTile, cc = blockIdx.y * kColTile + t;
     const float v = s_acc[e];
     if (v == 0.f) continue;
     if (i < MAXM) {
@@ -364,11 +394,23 @@ __global__ void __launch_bounds__(256) k_col_reduce(const __grid_constant__ ColA
   }
 }
 
-template <int MAXM>
-int launch_col(const ColArgs& a, dim3 grid, cudaStream_t st) {
-  k_col_reduce<MAXM><<<grid, 256, 0, st>>>(a);
-  NF_LAUNCHED();
-  return 0;
+// KMAX = largest m over the jobs of the launch (bounds the register budget of the kernel)
+template <int KMAX>
+__global__ void __launch_bounds__(256) k_col_reduce(const __grid_constant__ ColArgs a) {
+  __shared__ __align__(16) float s_coef[kColSub * KMAX];
+  __shared__ float s_acc[(KMAX + 2) * kColTile];
+  int job = 0, z = blockIdx.z;
+  while (job < a.njobs - 1 && z >= a.j[job].batch) { z -= a.j[job].batch; ++job; }
+  const ColJob& J = a.j[job];
+  if ((int)blockIdx.y * kColTile >= J.N) return;   // CTA-uniform
+  if (J.m <= 4) { col_body<4>(J, z, a.B, a.rows_per_cta, s_coef, s_acc); return; }
+  if constexpr (KMAX >= 8) {
+    if (J.m <= 8) { col_body<8>(J, z, a.B, a.rows_per_cta, s_coef, s_acc); return; }
+  }
+  if constexpr (KMAX >= 16) {
+    if (J.m <= 16) { col_body<16>(J, z, a.B, a.rows_per_cta, s_coef, s_acc); return; }
+  }
+  if constexpr (KMAX >= 32) col_body<32>(J, z, a.B, a.rows_per_cta, s_coef, s_acc);
 }
 
 }  // namespace
@@ -444,26 +486,28 @@ int col_reduce(const ColJob* jobs, int njobs, long long B, cudaStream_t st) {
   if (B <= 0 || njobs <= 0) return 0;
   NF_CHECK_ARG(njobs <= kColMaxJobs, NF_E_BADARG, "col_reduce: too many jobs (%d)", njobs);
   ColArgs a{};
-  int maxm = 0, tiles = 0, zs = 0;
+  int tiles = 0, zs = 0, maxm = 0;
   double bytes = 0;
   for (int j = 0; j < njobs; ++j) {
     a.j[j] = jobs[j];
     NF_CHECK_ARG(jobs[j].m >= 0 && jobs[j].m <= 32 && jobs[j].N >= 1 && jobs[j].batch >= 1, NF_E_BADARG,
                  "col_reduce: job %d has m=%d N=%d", j, jobs[j].m, jobs[j].N);
+    tiles = std::max(tiles, (int)cdiv(jobs[j].N, kColTile));
     maxm = std::max(maxm, jobs[j].m);
-    tiles = std::max(tiles, (int)cdiv(jobs[j].N, 32));
     zs += jobs[j].batch;
     bytes += 4.0 * B * jobs[j].batch * ((jobs[j].out ? jobs[j].N : 0) + (jobs[j].out2 ? jobs[j].N : 0) + jobs[j].m);
   }
   a.njobs = njobs;
   a.B = B;
-  a.rows_per_cta = B <= 16384 ? 256 : 1024;
+  a.rows_per_cta = B <= 16384 ? 128 : 1024;
   dim3 grid((unsigned)cdiv(B, a.rows_per_cta), (unsigned)tiles, (unsigned)zs);
   ProfScope prof(st, PROF_COL_REDUCE, bytes);
-  if (maxm <= 4) return launch_col<4>(a, grid, st);
-  if (maxm <= 8) return launch_col<8>(a, grid, st);
-  if (maxm <= 16) return launch_col<16>(a, grid, st);
-  return launch_col<32>(a, grid, st);
+  if (maxm <= 4) k_col_reduce<4><<<grid, 256, 0, st>>>(a);
+  else if (maxm <= 8) k_col_reduce<8><<<grid, 256, 0, st>>>(a);
+  else if (maxm <= 16) k_col_reduce<16><<<grid, 256, 0, st>>>(a);
+  else k_col_reduce<32><<<grid, 256, 0, st>>>(a);
+  NF_LAUNCHED();
+  return 0;
 }
 
 }  // namespace nf

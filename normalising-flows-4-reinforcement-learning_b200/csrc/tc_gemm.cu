@@ -36,7 +36,15 @@ struct KArgs {
   int zA0, zA1, zB0, zB1;  // 1: operand is batched over blockIdx.z, 0: shared
   int accumulate, passes, raw_hi, lo_round;
   int splitk, chunks_per_split;   // MN-major form only
+  // row-wise epilogues over the cluster (EPI_LN_FWD / EPI_LN_BWD)
+  float* rstd; long long sRstd;          // fwd: out (row), bwd: in
+  uint32_t* mask; long long sMask; int mw;   // fwd: out, bwd: in; mw words per row
+  const float* xh; long long ldxh, sXh;  // bwd: normalised activations of the layer (stash)
+  float eps;
+  int ncl;                               // CTAs per cluster = N / BN (the cluster spans the whole row)
 };
+constexpr int EPI_NONE = 0, EPI_LN_FWD = 1, EPI_LN_BWD = 2;
+constexpr int kMaxCluster = 8;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -137,6 +145,44 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_v2(uint32_t raddr, float a, float b) {
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(raddr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t raddr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  for (uint32_t spins = 0;; ++spins) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (spins > (1u << 24)) {
+      printf("nf_b200 tc_gemm: cluster exchange timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y,
+             blockIdx.z, threadIdx.x);
+      __trap();
+    }
+  }
+}
 __device__ __forceinline__ float rna_tf32(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -150,10 +196,12 @@ struct Smem {
   static constexpr int HALF = A_BYTES + B_BYTES;   // raw/hi tiles; the lo twins follow
   static constexpr int STAGE = 2 * HALF;
   static constexpr int BARS = STAGES * STAGE;      // byte offset of the barrier block
-  static constexpr int TOTAL = BARS + 256 + 1024;  // + alignment slack
+  static constexpr int XCHG = BARS + 512;          // [kMaxCluster][128] float2 partial row statistics (epilogue kernels)
+  static constexpr int TOTAL = BARS + 512 + 1024;  // + alignment slack
+  static constexpr int TOTAL_EPI = XCHG + 8 * 128 * 8 + 1024;
 };
 
-template <int BN, int STAGES, bool MNMAJOR, int BK>
+template <int BN, int STAGES, bool MNMAJOR, int BK, int EPI = EPI_NONE>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUtensorMap mA1,
           const __grid_constant__ CUtensorMap mB0, const __grid_constant__ CUtensorMap mB1, const KArgs a) {
@@ -167,7 +215,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
   uint64_t* split = bars + STAGES;
   uint64_t* empty = bars + 2 * STAGES;
   uint64_t* accbar = bars + 3 * STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
+  uint64_t* xbar = bars + 3 * STAGES + 1;      // cluster exchange barrier (epilogue kernels)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
@@ -199,6 +248,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
     if (nk1) { prefetch_tmap(&mA1); prefetch_tmap(&mB1); }
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&split[s], 4); mbar_init(&empty[s], 1); }
     mbar_init(accbar, 1);
+    if (EPI != EPI_NONE) mbar_init(xbar, (uint32_t)a.ncl * 128u);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -208,6 +258,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (EPI != EPI_NONE) cluster_sync_all();   // every CTA's exchange barrier is initialised before a peer arrives on it
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
@@ -311,6 +362,126 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int q = warp & 3;
     const int row = m0 + q * 32 + lane;
+    if constexpr (EPI != EPI_NONE) {
+      // ------------------------------------------------------------------ row-wise epilogue over the cluster
+      // The cluster (1, ncl, 1) spans the whole output row: this thread holds its row's BN columns in
+      // registers, exchanges two partial statistics with the ncl - 1 peer CTAs through distributed
+      // shared memory (push + remote mbarrier arrive, one round) and finishes the row-wise operation:
+      //   EPI_LN_FWD: x_hat = LayerNorm_noaffine(LeakyReLU(acc + bias)), rstd, sign mask   (torch_fcnf.py:75-76)
+      //   EPI_LN_BWD: du = LeakyReLU'(mask) rstd (g - mean(g) - x_hat mean(g x_hat)),  g = acc
+      const int rit = q * 32 + lane;
+      const bool rowok = row < a.M;
+      float v[BN];
+#pragma unroll
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c0);
+        tmem_ld32(taddr, r);
+#pragma unroll
+        for (int ac = 1; ac <= NACC; ++ac) {
+          if (ac < NACC ? ac < nacc_used : a.passes == 3) {
+            uint32_t rc[32];
+            tmem_ld32(taddr + ac * BN, rc);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(rc[j]));
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[c0 + j] = __uint_as_float(r[j]);
+      }
+      float2* xchg = reinterpret_cast<float2*>(smem + S::XCHG);   // [rank][row in tile]
+      const uint32_t my_rank = cluster_ctarank();
+      const int ncl = a.ncl;
+      float p0, p1;            // the two partial statistics of this CTA's BN columns
+      uint32_t mbits[BN / 32];
+      if constexpr (EPI == EPI_LN_FWD) {
+        const float* bias = a.bias ? a.bias + (long long)z * a.sBias + n0 : nullptr;
+        float sum = 0.f;
+#pragma unroll
+        for (int c = 0; c < BN; ++c) {
+          const float pre = v[c] + (bias ? __ldg(bias + c) : 0.f);
+          if ((c & 31) == 0) mbits[c >> 5] = 0u;
+          if (pre > 0.f) mbits[c >> 5] |= 1u << (c & 31);
+          v[c] = pre > 0.f ? pre : kLeakySlope * pre;
+          sum += v[c];
+        }
+        p0 = sum * (1.0f / BN);                     // local mean
+        float m2 = 0.f;
+#pragma unroll
+        for (int c = 0; c < BN; ++c) { const float d = v[c] - p0; m2 = fmaf(d, d, m2); }
+        p1 = m2;                                    // local centred sum of squares
+      } else {
+        const float* xh = a.xh + (long long)z * a.sXh + (long long)row * a.ldxh + n0;
+        float s1 = 0.f, s2 = 0.f;
+        if (rowok) {
+#pragma unroll
+          for (int c = 0; c < BN; c += 4) {
+            const float4 x = *reinterpret_cast<const float4*>(xh + c);
+            s1 += (v[c] + v[c + 1]) + (v[c + 2] + v[c + 3]);
+            s2 = fmaf(v[c], x.x, fmaf(v[c + 1], x.y, fmaf(v[c + 2], x.z, fmaf(v[c + 3], x.w, s2))));
+          }
+        }
+        p0 = s1; p1 = s2;
+      }
+      // push to every CTA of the cluster (own included), then wait for everyone's partials
+      const uint32_t slot = smem_u32(&xchg[my_rank * 128 + rit]);
+      const uint32_t xb = smem_u32(xbar);
+      for (int pr = 0; pr < ncl; ++pr) {
+        st_cluster_v2(mapa_u32(slot, (uint32_t)pr), p0, p1);
+        mbar_arrive_remote(mapa_u32(xb, (uint32_t)pr));
+      }
+      mbar_wait_cluster(xbar, 0);
+      float* crow = a.C + (long long)z * a.sC + (long long)row * a.ldc + n0;
+      if constexpr (EPI == EPI_LN_FWD) {
+        // combine equal-sized groups (Chan et al.): mean = avg(mean_i), M2 = sum M2_i + BN sum (mean_i - mean)^2
+        float mean = 0.f;
+        for (int pr = 0; pr < ncl; ++pr) mean += xchg[pr * 128 + rit].x;
+        mean /= (float)ncl;
+        float m2 = 0.f;
+        for (int pr = 0; pr < ncl; ++pr) {
+          const float2 s = xchg[pr * 128 + rit];
+          const float d = s.x - mean;
+          m2 += s.y + (float)BN * d * d;
+        }
+        const float rstd = rsqrtf(m2 / (float)(ncl * BN) + a.eps);
+        if (rowok) {
+#pragma unroll
+          for (int c = 0; c < BN; c += 4) {
+            float4 o;
+            o.x = (v[c] - mean) * rstd; o.y = (v[c + 1] - mean) * rstd;
+            o.z = (v[c + 2] - mean) * rstd; o.w = (v[c + 3] - mean) * rstd;
+            *reinterpret_cast<float4*>(crow + c) = o;
+          }
+          if (a.mask) {
+            uint32_t* mk = a.mask + (long long)z * a.sMask + (long long)row * a.mw + (n0 >> 5);
+#pragma unroll
+            for (int w = 0; w < BN / 32; ++w) mk[w] = mbits[w];
+          }
+          if (a.rstd && my_rank == 0) a.rstd[(long long)z * a.sRstd + row] = rstd;
+        }
+      } else {
+        float s1 = 0.f, s2 = 0.f;
+        for (int pr = 0; pr < ncl; ++pr) { const float2 s = xchg[pr * 128 + rit]; s1 += s.x; s2 += s.y; }
+        const float inv = 1.0f / (float)(ncl * BN);
+        s1 *= inv; s2 *= inv;
+        if (rowok) {
+          const float rs = a.rstd[(long long)z * a.sRstd + row];
+          const float* xh = a.xh + (long long)z * a.sXh + (long long)row * a.ldxh + n0;
+          const uint32_t* mk = a.mask + (long long)z * a.sMask + (long long)row * a.mw + (n0 >> 5);
+#pragma unroll
+          for (int c = 0; c < BN; c += 4) {
+            const float4 x = *reinterpret_cast<const float4*>(xh + c);
+            const uint32_t bits = mk[c >> 5] >> (c & 31);
+            float4 o;
+            o.x = rs * (v[c] - s1 - x.x * s2) * ((bits & 1u) ? 1.0f : kLeakySlope);
+            o.y = rs * (v[c + 1] - s1 - x.y * s2) * ((bits & 2u) ? 1.0f : kLeakySlope);
+            o.z = rs * (v[c + 2] - s1 - x.z * s2) * ((bits & 4u) ? 1.0f : kLeakySlope);
+            o.w = rs * (v[c + 3] - s1 - x.w * s2) * ((bits & 8u) ? 1.0f : kLeakySlope);
+            *reinterpret_cast<float4*>(crow + c) = o;
+          }
+        }
+      }
+    } else {
     float* crow = a.C + (long long)z * a.sC + (long long)row * a.ldc;
     const float* bias = a.bias ? a.bias + (long long)z * a.sBias : nullptr;
     const bool vec_ok = (a.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.C) + (size_t)z * a.sC * 4) & 15) == 0;
@@ -360,6 +531,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
         }
       }
     }
+    }  // plain epilogue
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -450,6 +622,56 @@ int launch(const TcGemmP& p, cudaStream_t st) {
   return 0;
 }
 
+template <int BN, int STAGES, int BK, int EPI>
+int launch_epi(const TcGemmP& p, cudaStream_t st) {
+  using S = Smem<BN, STAGES, BK>;
+  static bool configured = false;
+  if (!configured) {
+    NF_CUDA(cudaFuncSetAttribute(k_tc_gemm<BN, STAGES, false, BK, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 S::TOTAL_EPI));
+    configured = true;
+  }
+  int r;
+  CUtensorMap mA0, mA1, mB0, mB1;
+  const CUtensorMapSwizzle swz = BK == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  if ((r = make_map(&mA0, p.A0, p.K0, p.M, p.lda0, p.batch, p.sA0, BK, BM, swz))) return r;
+  if ((r = make_map(&mB0, p.B0, p.K0, p.N, p.ldb0, p.batch, p.sB0, BK, BN, swz))) return r;
+  if (p.K1 > 0) {
+    if ((r = make_map(&mA1, p.A1, p.K1, p.M, p.lda1, p.batch, p.sA1, BK, BM, swz))) return r;
+    if ((r = make_map(&mB1, p.B1, p.K1, p.N, p.ldb1, p.batch, p.sB1, BK, BN, swz))) return r;
+  } else {
+    mA1 = mA0; mB1 = mB0;
+  }
+  KArgs a{};
+  a.C = p.C; a.bias = p.bias; a.M = p.M; a.N = p.N; a.K0 = p.K0; a.K1 = p.K1;
+  a.ldc = p.ldc; a.sC = p.sC; a.sBias = p.sBias;
+  a.zA0 = p.sA0 != 0; a.zA1 = p.sA1 != 0; a.zB0 = p.sB0 != 0; a.zB1 = p.sB1 != 0;
+  a.accumulate = 0; a.passes = p.passes; a.raw_hi = p.raw_hi; a.lo_round = p.lo_round;
+  a.splitk = 1; a.chunks_per_split = 0;
+  a.rstd = p.epi.rstd; a.sRstd = p.epi.sRstd; a.mask = p.epi.mask; a.sMask = p.epi.sMask; a.mw = p.epi.mw;
+  a.xh = p.epi.xh; a.ldxh = p.epi.ldxh; a.sXh = p.epi.sXh; a.eps = p.epi.eps;
+  a.ncl = p.N / BN;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)cdiv(p.M, BM), (unsigned)a.ncl, (unsigned)p.batch);
+  cfg.blockDim = dim3(NTHREADS);
+  cfg.dynamicSmemBytes = S::TOTAL_EPI;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = (unsigned)a.ncl; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  ProfScope prof(st, PROF_TC_GEMM, 2.0 * p.M * p.N * (double)(p.K0 + p.K1) * p.batch);
+  NF_CUDA(cudaLaunchKernelEx(&cfg, k_tc_gemm<BN, STAGES, false, BK, EPI>, mA0, mA1, mB0, mB1, a));
+  NF_LAUNCHED();
+  return 0;
+}
+
+template <int EPI>
+int launch_epi_pick(const TcGemmP& p, cudaStream_t st) {
+  if (p.N % 128 == 0 && p.N / 128 <= kMaxCluster) return launch_epi<128, 6, 16, EPI>(p, st);
+  return launch_epi<64, 8, 16, EPI>(p, st);
+}
+
 template <int BN, int STAGES, int BK>
 int launch_tn(const TcGemmTnP& p, cudaStream_t st) {
   using S = Smem<BN, STAGES, BK>;
@@ -495,8 +717,31 @@ bool tc_gemm_supported(const TcGemmP& p) {
   return encode_fn() != nullptr;
 }
 
+bool tc_gemm_epi_supported(const TcGemmP& p) {
+  if (!tc_gemm_supported(p) || p.accumulate) return false;
+  // One output tile per CTA: the row-wise epilogue is not overlapped with another tile's MMAs, so it only
+  // pays while the launch is latency-bound (at most ~2 waves of CTAs); measured on C3/C4/C5 at B >= 8192 the
+  // separate row kernel is 15-35 % faster, on C2a (B = 4096) the fused one wins.
+  static const int force = [] { const char* e = getenv("NF_B200_FUSED_LN"); return e ? atoi(e) : -1; }();
+  if (force == 0) return false;
+  if (force != 1 && cdiv(p.M, BM) * cdiv(p.N, 128) * p.batch > 2 * 148) return false;
+  const bool n128 = p.N % 128 == 0 && p.N / 128 <= kMaxCluster;
+  const bool n64 = p.N % 64 == 0 && p.N / 64 <= kMaxCluster;
+  if (!n128 && !n64) return false;
+  if ((p.ldc & 3) != 0 || (reinterpret_cast<uintptr_t>(p.C) & 15u) != 0 || (p.sC & 3) != 0) return false;
+  if (p.epi.kind == TC_EPI_LN_FWD) return p.epi.mask == nullptr || p.epi.mw * 32 >= p.N;
+  if (p.epi.kind == TC_EPI_LN_BWD)
+    return p.epi.xh && p.epi.rstd && p.epi.mask && (p.epi.ldxh & 3) == 0 && (p.epi.sXh & 3) == 0 &&
+           (reinterpret_cast<uintptr_t>(p.epi.xh) & 15u) == 0 && p.epi.mw * 32 >= p.N;
+  return false;
+}
+
 int tc_gemm(const TcGemmP& p, cudaStream_t st) {
   if (p.M <= 0 || p.N <= 0 || p.batch <= 0) return 0;
+  if (p.epi.kind != TC_EPI_NONE) {
+    NF_CHECK_ARG(tc_gemm_epi_supported(p), NF_E_UNSUPPORTED, "tc_gemm: fused row epilogue needs N = k * 64 (k <= 8), N=%d", p.N);
+    return p.epi.kind == TC_EPI_LN_FWD ? launch_epi_pick<EPI_LN_FWD>(p, st) : launch_epi_pick<EPI_LN_BWD>(p, st);
+  }
   NF_CHECK_ARG(tc_gemm_supported(p), NF_E_UNSUPPORTED,
                "tc_gemm: operands must be 16-byte aligned with row pitches that are multiples of 4 floats");
   // small problems: prefer more, smaller CTAs (3 pipeline stages) over filling TMEM

@@ -10,6 +10,18 @@
 
 namespace nf {
 
+// Row-wise epilogues fused into the GEMM (the cluster of CTAs along N spans the whole output row):
+//   TC_EPI_LN_FWD: C = LayerNorm_noaffine(LeakyReLU(acc + bias)), rstd (M) and sign mask (M, mw words) written
+//   TC_EPI_LN_BWD: C = LeakyReLU'(mask) rstd (acc - mean(acc) - xh mean(acc xh))   (xh, rstd, mask read)
+enum { TC_EPI_NONE = 0, TC_EPI_LN_FWD = 1, TC_EPI_LN_BWD = 2 };
+struct TcEpi {
+  int kind = TC_EPI_NONE;
+  float* rstd = nullptr; long long sRstd = 0;
+  uint32_t* mask = nullptr; long long sMask = 0; int mw = 0;
+  const float* xh = nullptr; long long ldxh = 0, sXh = 0;
+  float eps = 1e-5f;
+};
+
 struct TcGemmP {
   // K-major operands; the reduction may be two segments (A0|A1) x (B0|B1)
   const float* A0 = nullptr; const float* A1 = nullptr;
@@ -26,6 +38,7 @@ struct TcGemmP {
                         // lo = x - trunc_tf32(x); saves one shared-memory store per element (measured +10%)
   int lo_round = 0;     // round lo to tf32 (nearest) instead of letting the tensor core truncate it
   int bk = 16;          // reduction elements per pipeline stage: 16 or 32
+  TcEpi epi;            // optional fused row-wise epilogue (see tc_gemm_epi_supported)
 };
 
 // Weight-gradient form: C[z][m, n] += sum_k A[z][k, m] * B[z][k, n]  (both operands MN-major: the
@@ -48,5 +61,7 @@ bool tc_gemm_tn_supported(const TcGemmTnP& p);
 // returns 0, or NF_E_UNSUPPORTED when the shape/alignment cannot be handled by TMA (caller decides)
 int tc_gemm(const TcGemmP& p, cudaStream_t st);
 bool tc_gemm_supported(const TcGemmP& p);
+// the fused epilogues need N = ncl * BN with BN in {64, 128} and ncl <= 8 (one cluster per 128-row tile)
+bool tc_gemm_epi_supported(const TcGemmP& p);
 
 }  // namespace nf

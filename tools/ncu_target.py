@@ -16,6 +16,7 @@ x, y = synth.make_inputs(B, cfg["D"], cfg["R"])
 x = torch.tensor(x, device=dev); y = torch.tensor(y, device=dev)
 plist = [p for p in m.parameters() if p.requires_grad]
 for _ in range(steps):
+    m._packed_key = None
     for p in plist: p.grad = None
     loss = -m.log_prob(x, y).mean(); loss.backward()
 torch.cuda.synchronize()
