@@ -35,6 +35,7 @@ struct KArgs {
   long long ldc, sC, sBias;
   int zA0, zA1, zB0, zB1;  // 1: operand is batched over blockIdx.z, 0: shared
   int accumulate, passes, raw_hi, lo_round;
+  int nacc, merge_corr;           // main accumulators in rotation (1..NACC); cross terms share the main accumulator
   int splitk, chunks_per_split;   // MN-major form only
   // row-wise epilogues over the cluster (EPI_LN_FWD / EPI_LN_BWD)
   float* rstd; long long sRstd;          // fwd: out (row), bwd: in
@@ -42,6 +43,7 @@ struct KArgs {
   const float* xh; long long ldxh, sXh;  // bwd: normalised activations of the layer (stash)
   float eps;
   int ncl;                               // CTAs per cluster = N / BN (the cluster spans the whole row)
+  long long* dbg;                        // optional: 8 clock64 timestamps per CTA (nf_debug_tc_timeline)
 };
 constexpr int EPI_NONE = 0, EPI_LN_FWD = 1, EPI_LN_BWD = 2;
 constexpr int kMaxCluster = 8;
@@ -143,7 +145,39 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// Sum of the NACC main accumulators (only `nacc_used` were written) and the corr accumulator of one 32-column
+// chunk: all TMEM loads are issued before the single wait (one TMEM round trip per chunk instead of four).
+template <int BN, int NACC>
+__device__ __forceinline__ void tmem_ld_sum(uint32_t taddr, int nacc_used, bool with_corr, float (&out)[32]) {
+  uint32_t r[NACC + 1][32];
+  tmem_ld32(taddr, r[0]);
+#pragma unroll
+  for (int ac = 1; ac <= NACC; ++ac)
+    if (ac < NACC ? ac < nacc_used : with_corr) tmem_ld32(taddr + ac * BN, r[ac]);
+  tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < 32; ++j) out[j] = __uint_as_float(r[0][j]);
+#pragma unroll
+  for (int ac = 1; ac <= NACC; ++ac)
+    if (ac < NACC ? ac < nacc_used : with_corr) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) out[j] += __uint_as_float(r[ac][j]);
+    }
+}
+// One elected lane of a fully converged warp.  The producer and MMA warps run their loops with ALL lanes
+// (so every operand stays warp-uniform and lives in uniform registers) and only the instruction issue is
+// elected; under `if (lane == 0)` the compiler wrapped every UTCHMMA / UTMALDG in an ELECT + R2UR.BROADCAST
+// + BRA.U.ANY waterfall loop, which made the single issuing thread the bottleneck of the tensor pipe.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -183,6 +217,34 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
     }
   }
 }
+// Warp-level 32 x 32 transposition through shared memory (pitch 36 floats: conflict-free for the 128-bit
+// row-per-lane accesses and for the 128-byte row segments).  In the TMEM layout a lane owns a ROW; global
+// memory wants a warp on one row segment.  A row-per-lane float4 store touches 32 different 128-byte
+// lines (measured: the epilogue was LSU-bound at 4800 cycles per 128 x 128 tile); after the transposition
+// every store instruction writes four full lines.
+constexpr int kXPitch = 36;
+constexpr int kXWarpFloats = 32 * kXPitch;
+__device__ __forceinline__ void xpose_put(float* sbuf, int lane, const float (&v)[32]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<float4*>(sbuf + lane * kXPitch + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  __syncwarp();
+}
+// i-th of 8 pieces: rows (lane >> 3) + 4 i, columns 4 (lane & 7) .. +3
+__device__ __forceinline__ float4 xpose_get(const float* sbuf, int lane, int i) {
+  return *reinterpret_cast<const float4*>(sbuf + ((lane >> 3) + 4 * i) * kXPitch + 4 * (lane & 7));
+}
+// the reverse direction: coalesced pieces in, row-per-lane out
+__device__ __forceinline__ void xpose_put_piece(float* sbuf, int lane, int i, float4 v) {
+  *reinterpret_cast<float4*>(sbuf + ((lane >> 3) + 4 * i) * kXPitch + 4 * (lane & 7)) = v;
+}
+__device__ __forceinline__ void xpose_get_row(const float* sbuf, int lane, float (&v)[32]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 t = *reinterpret_cast<const float4*>(sbuf + lane * kXPitch + 4 * j);
+    v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+  }
+}
 __device__ __forceinline__ float rna_tf32(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -220,6 +282,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  long long* dbg = a.dbg ? a.dbg + 8ll * (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * (long long)blockIdx.z)) : nullptr;
+#define NF_TS(i) do { if (dbg) dbg[i] = clock64(); } while (0)
+  if (threadIdx.x == 64) NF_TS(0);
   const int z = MNMAJOR ? blockIdx.z / a.splitk : blockIdx.z;
   const int nk0 = (a.K0 + BK - 1) / BK, nk1 = (a.K1 + BK - 1) / BK;
   // chunk range of this CTA: everything (K-major form) or one split of the batch rows (MN-major form)
@@ -241,7 +306,12 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
   } else {
     total_k8 = (a.K0 + 7) / 8 + (a.K1 + 7) / 8;
   }
-  const int nacc_used = total_k8 < NACC ? total_k8 : NACC;
+  // Rotating over all NACC accumulators is also FASTER than using fewer (measured: 840 vs 940-1100 cycles per
+  // 16-deep stage): back-to-back MMAs into one accumulator serialise on it.  a.nacc / a.merge_corr stay as
+  // experiment knobs (NF_B200_NACC); the default is the full rotation with a separate corr accumulator.
+  const int nacc_rt = a.nacc < 1 ? NACC : (a.nacc > NACC ? NACC : a.nacc);
+  const int nacc_used = total_k8 < nacc_rt ? total_k8 : nacc_rt;
+  const bool with_corr = a.passes == 3 && !a.merge_corr;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&mA0); prefetch_tmap(&mB0);
@@ -261,74 +331,101 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
   if (EPI != EPI_NONE) cluster_sync_all();   // every CTA's exchange barrier is initialised before a peer arrives on it
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 64) NF_TS(1);   // prologue done
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    {
       for (int it = 0; it < nk; ++it) {
         const int s = it % STAGES, use = it / STAGES;
-        mbar_wait(&empty[s], (use & 1) ^ 1);
-        mbar_expect_tx(&full[s], S::HALF);
+        if (lane == 0) mbar_wait(&empty[s], (use & 1) ^ 1);   // one poller per warp: 32 spinning lanes steal smem cycles
+        __syncwarp();
         uint8_t* st = smem + s * S::STAGE;
-        if (MNMAJOR) {
-          // operands are (K rows, M|N columns): one 32 x 32 box per 32-column group
-          const int k0 = (kc_begin + it) * BK;
+        if (elect_one()) {
+          mbar_expect_tx(&full[s], S::HALF);
+          if (MNMAJOR) {
+            // operands are (K rows, M|N columns): one 32 x 32 box per 32-column group
+            const int k0 = (kc_begin + it) * BK;
 #pragma unroll
-          for (int g = 0; g < BM / 32; ++g) tma_load_3d(st + g * BOX, &mA0, &full[s], m0 + g * 32, k0, a.zA0 ? z : 0);
+            for (int g = 0; g < BM / 32; ++g) tma_load_3d(st + g * BOX, &mA0, &full[s], m0 + g * 32, k0, a.zA0 ? z : 0);
 #pragma unroll
-          for (int g = 0; g < BN / 32; ++g)
-            tma_load_3d(st + A_BYTES + g * BOX, &mB0, &full[s], n0 + g * 32, k0, a.zB0 ? z : 0);
-        } else {
-          const bool seg1 = it >= nk0;
-          const int kk = (seg1 ? it - nk0 : it) * BK;
-          tma_load_3d(st, seg1 ? &mA1 : &mA0, &full[s], kk, m0, (seg1 ? a.zA1 : a.zA0) ? z : 0);
-          tma_load_3d(st + A_BYTES, seg1 ? &mB1 : &mB0, &full[s], kk, n0, (seg1 ? a.zB1 : a.zB0) ? z : 0);
+            for (int g = 0; g < BN / 32; ++g)
+              tma_load_3d(st + A_BYTES + g * BOX, &mB0, &full[s], n0 + g * 32, k0, a.zB0 ? z : 0);
+          } else {
+            const bool seg1 = it >= nk0;
+            const int kk = (seg1 ? it - nk0 : it) * BK;
+            tma_load_3d(st, seg1 ? &mA1 : &mA0, &full[s], kk, m0, (seg1 ? a.zA1 : a.zA0) ? z : 0);
+            tma_load_3d(st + A_BYTES, seg1 ? &mB1 : &mB0, &full[s], kk, n0, (seg1 ? a.zB1 : a.zB0) ? z : 0);
+          }
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    {
       // kind::tf32, fp32 accumulate, M = 128, N = BN; bits 15/16 = MN-major A/B (cute::UMMA::InstrDescriptor)
       constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (MNMAJOR ? (3u << 15) : 0u) |
                                  (uint32_t(BN >> 3) << 17) | (uint32_t(BM >> 4) << 24);
+      // One thread issues every MMA, so the instruction latency of THIS loop paces the tensor pipe (a
+      // runtime modulo for the accumulator rotation alone cost 30 % of the mainloop): descriptors are a
+      // constant high word plus a 14-bit address in the low word, the rotation is a wrapping counter.
       const uint32_t tmem_corr = tmem_base + NACC * BN;
-      uint32_t acc_c = 0;
-      int k8 = 0;
+      const uint64_t d0 = MNMAJOR ? make_sdesc_mn<BK>(0u) : make_sdesc<BK>(0u);
+      const uint32_t dhi = static_cast<uint32_t>(d0 >> 32), dlo = static_cast<uint32_t>(d0);
+      constexpr uint32_t kStep = MNMAJOR ? (1024u >> 4) : (32u >> 4);   // next k8 block inside a stage
+      const uint32_t rot_end = tmem_base + (uint32_t)nacc_rt * BN;
+      uint32_t tmem_main = tmem_base, acc_c = 0, fresh = (uint32_t)nacc_rt;   // `fresh` mains not written yet
+      const bool merge = a.merge_corr != 0, three = a.passes == 3;
       for (int it = 0; it < nk; ++it) {
         const int s = it % STAGES, use = it / STAGES;
-        mbar_wait(&split[s], use & 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sa = smem_u32(smem + s * S::STAGE);
-        uint64_t a_hi, b_hi, a_lo, b_lo;
         int nks;
-        uint64_t step;
         if (MNMAJOR) {
-          a_hi = make_sdesc_mn<BK>(sa); b_hi = make_sdesc_mn<BK>(sa + A_BYTES);
-          a_lo = make_sdesc_mn<BK>(sa + S::HALF); b_lo = make_sdesc_mn<BK>(sa + S::HALF + A_BYTES);
           const long long kleft = (long long)a.K0 - (long long)(kc_begin + it) * BK;
           nks = kleft >= BK ? BK / 8 : (int)((kleft + 7) / 8);
-          step = 1024 >> 4;   // next 8 k-rows = next 1024 B swizzle atom
         } else {
-          a_hi = make_sdesc<BK>(sa); b_hi = make_sdesc<BK>(sa + A_BYTES);
-          a_lo = make_sdesc<BK>(sa + S::HALF); b_lo = make_sdesc<BK>(sa + S::HALF + A_BYTES);
           const bool seg1 = it >= nk0;
           const int kleft = (seg1 ? a.K1 - (it - nk0) * BK : a.K0 - it * BK);
           nks = kleft >= BK ? BK / 8 : (kleft + 7) / 8;
-          step = 32 >> 4;     // next 8 fp32 along the 128 B row
         }
-        for (int ks = 0; ks < nks; ++ks) {
-          const uint64_t adv = step * static_cast<uint64_t>(ks);
-          if (a.passes == 3) {
-            umma_tf32(tmem_corr, a_lo + adv, b_hi + adv, idesc, acc_c); acc_c = 1;
-            umma_tf32(tmem_corr, a_hi + adv, b_lo + adv, idesc, acc_c);
+        const uint32_t sa = (smem_u32(smem + s * S::STAGE) & 0x3FFFFu) >> 4;
+        uint32_t la_hi = dlo + sa, lb_hi = la_hi + (A_BYTES >> 4), la_lo = la_hi + (S::HALF >> 4),
+                 lb_lo = lb_hi + (S::HALF >> 4);
+        if (lane == 0) mbar_wait(&split[s], use & 1);
+        __syncwarp();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const bool leader = elect_one();
+#pragma unroll
+        for (int ks = 0; ks < BK / 8; ++ks) {
+          if (ks < nks) {
+            const uint64_t a_hi = (static_cast<uint64_t>(dhi) << 32) | la_hi, b_hi = (static_cast<uint64_t>(dhi) << 32) | lb_hi;
+            const uint64_t a_lo = (static_cast<uint64_t>(dhi) << 32) | la_lo, b_lo = (static_cast<uint64_t>(dhi) << 32) | lb_lo;
+            uint32_t acc_m = fresh == 0 ? 1u : 0u;
+            if (leader) {
+              if (three) {
+                if (merge) {
+                  umma_tf32(tmem_main, a_lo, b_hi, idesc, acc_m);
+                  umma_tf32(tmem_main, a_hi, b_lo, idesc, 1u);
+                  acc_m = 1;
+                } else {
+                  umma_tf32(tmem_corr, a_lo, b_hi, idesc, acc_c);
+                  umma_tf32(tmem_corr, a_hi, b_lo, idesc, 1u);
+                }
+              }
+              umma_tf32(tmem_main, a_hi, b_hi, idesc, acc_m);
+            }
+            acc_c = 1;
+            if (fresh) --fresh;
+            tmem_main += BN;
+            if (tmem_main == rot_end) tmem_main = tmem_base;
+            la_hi += kStep; lb_hi += kStep; la_lo += kStep; lb_lo += kStep;
           }
-          umma_tf32(tmem_base + (k8 % NACC) * BN, a_hi + adv, b_hi + adv, idesc, k8 >= NACC ? 1u : 0u);
-          ++k8;
         }
-        umma_commit(&empty[s]);   // frees the stage once the MMAs above have read it
+        if (leader) umma_commit(&empty[s]);   // frees the stage once the MMAs above have read it
+        __syncwarp();
       }
-      umma_commit(accbar);        // accumulator complete
+      if (elect_one()) umma_commit(accbar);        // accumulator complete
+      __syncwarp();
     }
   } else {
     // ------------------------------------------------------------------ splitters, then epilogue
@@ -336,20 +433,29 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
     for (int it = 0; it < nk; ++it) {
       const int s = it % STAGES, use = it / STAGES;
       mbar_wait(&full[s], use & 1);
+      if (threadIdx.x == 64 && it == 0) NF_TS(2);   // first operand tile landed
       float4* raw = reinterpret_cast<float4*>(smem + s * S::STAGE);
       float4* lo = reinterpret_cast<float4*>(smem + s * S::STAGE + S::HALF);
-#pragma unroll 4
-      for (int i = t; i < S::HALF / 16; i += 128) {
-        const float4 v = raw[i];
+      // every load of the stage is issued before the first store: the in-place/aliased stores otherwise
+      // serialise load -> store -> load and the splitters pace the MMAs (measured 800 cycles per stage
+      // against a 384-cycle MMA floor, tools/tc_timeline.py)
+      constexpr int PER = S::HALF / 16 / 128;
+      static_assert(S::HALF % (16 * 128) == 0, "tile bytes must be a multiple of 2 KB");
+      float4 v[PER];
+#pragma unroll
+      for (int k = 0; k < PER; ++k) v[k] = raw[t + 128 * k];
+#pragma unroll
+      for (int k = 0; k < PER; ++k) {
+        const int i = t + 128 * k;
         float4 h, l;
         if (a.raw_hi) {
-          h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
-          h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+          h.x = __uint_as_float(__float_as_uint(v[k].x) & 0xffffe000u); h.y = __uint_as_float(__float_as_uint(v[k].y) & 0xffffe000u);
+          h.z = __uint_as_float(__float_as_uint(v[k].z) & 0xffffe000u); h.w = __uint_as_float(__float_as_uint(v[k].w) & 0xffffe000u);
         } else {
-          h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
+          h.x = rna_tf32(v[k].x); h.y = rna_tf32(v[k].y); h.z = rna_tf32(v[k].z); h.w = rna_tf32(v[k].w);
           raw[i] = h;
         }
-        l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+        l.x = v[k].x - h.x; l.y = v[k].y - h.y; l.z = v[k].z - h.z; l.w = v[k].w - h.w;
         if (a.lo_round) { l.x = rna_tf32(l.x); l.y = rna_tf32(l.y); l.z = rna_tf32(l.z); l.w = rna_tf32(l.w); }
         lo[i] = l;
       }
@@ -358,7 +464,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
       if (lane == 0) mbar_arrive(&split[s]);
     }
     // epilogue: this warp may only touch TMEM lanes 32*(warp%4) .. +31; thread = one output row
+    if (threadIdx.x == 64) NF_TS(3);   // last tile split
     mbar_wait(accbar, 0);
+    if (threadIdx.x == 64) NF_TS(4);   // accumulators complete
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int q = warp & 3;
     const int row = m0 + q * 32 + lane;
@@ -374,24 +482,20 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
       float v[BN];
 #pragma unroll
       for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
+        float r[32];
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c0);
-        tmem_ld32(taddr, r);
+        tmem_ld_sum<BN, NACC>(taddr, nacc_used, with_corr, r);
 #pragma unroll
-        for (int ac = 1; ac <= NACC; ++ac) {
-          if (ac < NACC ? ac < nacc_used : a.passes == 3) {
-            uint32_t rc[32];
-            tmem_ld32(taddr + ac * BN, rc);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(rc[j]));
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[c0 + j] = __uint_as_float(r[j]);
+        for (int j = 0; j < 32; ++j) v[c0 + j] = r[j];
       }
+      if (threadIdx.x == 64) NF_TS(5);   // row in registers
       float2* xchg = reinterpret_cast<float2*>(smem + S::XCHG);   // [rank][row in tile]
       const uint32_t my_rank = cluster_ctarank();
       const int ncl = a.ncl;
+      float* sxh = reinterpret_cast<float*>(smem) + q * (32 * (BN + 4));              // bwd: this warp's x_hat tile
+      float* sx = reinterpret_cast<float*>(smem) + 4 * 32 * (BN + 4) + q * kXWarpFloats;   // 32 x 32 transposition buffer
+      float* cwarp = a.C + (long long)z * a.sC + (long long)(m0 + q * 32) * a.ldc + n0;
+      const int rows_valid_w = a.M - (m0 + q * 32);
       float p0, p1;            // the two partial statistics of this CTA's BN columns
       uint32_t mbits[BN / 32];
       if constexpr (EPI == EPI_LN_FWD) {
@@ -411,15 +515,24 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
         for (int c = 0; c < BN; ++c) { const float d = v[c] - p0; m2 = fmaf(d, d, m2); }
         p1 = m2;                                    // local centred sum of squares
       } else {
-        const float* xh = a.xh + (long long)z * a.sXh + (long long)row * a.ldxh + n0;
+        // x_hat tile of this warp's 32 rows -> shared memory with coalesced 128-bit loads (the operand
+        // stages are free now); both passes then read the lane's own row from there
+        const float* xw = a.xh + (long long)z * a.sXh + (long long)(m0 + q * 32) * a.ldxh + n0;
+        const int rows_valid = a.M - (m0 + q * 32);
+#pragma unroll 8
+        for (int idx = lane; idx < 32 * (BN / 4); idx += 32) {
+          const int r = idx / (BN / 4), c4 = idx % (BN / 4);
+          const float4 t = r < rows_valid ? __ldg(reinterpret_cast<const float4*>(xw + (long long)r * a.ldxh) + c4)
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(sxh + r * (BN + 4) + 4 * c4) = t;
+        }
+        __syncwarp();
         float s1 = 0.f, s2 = 0.f;
-        if (rowok) {
 #pragma unroll
-          for (int c = 0; c < BN; c += 4) {
-            const float4 x = *reinterpret_cast<const float4*>(xh + c);
-            s1 += (v[c] + v[c + 1]) + (v[c + 2] + v[c + 3]);
-            s2 = fmaf(v[c], x.x, fmaf(v[c + 1], x.y, fmaf(v[c + 2], x.z, fmaf(v[c + 3], x.w, s2))));
-          }
+        for (int c = 0; c < BN; c += 4) {
+          const float4 x = *reinterpret_cast<const float4*>(sxh + lane * (BN + 4) + c);
+          s1 += (v[c] + v[c + 1]) + (v[c + 2] + v[c + 3]);
+          s2 = fmaf(v[c], x.x, fmaf(v[c + 1], x.y, fmaf(v[c + 2], x.z, fmaf(v[c + 3], x.w, s2))));
         }
         p0 = s1; p1 = s2;
       }
@@ -431,6 +544,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
         mbar_arrive_remote(mapa_u32(xb, (uint32_t)pr));
       }
       mbar_wait_cluster(xbar, 0);
+      if (threadIdx.x == 64) NF_TS(6);   // statistics exchanged
       float* crow = a.C + (long long)z * a.sC + (long long)row * a.ldc + n0;
       if constexpr (EPI == EPI_LN_FWD) {
         // combine equal-sized groups (Chan et al.): mean = avg(mean_i), M2 = sum M2_i + BN sum (mean_i - mean)^2
@@ -444,14 +558,21 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
           m2 += s.y + (float)BN * d * d;
         }
         const float rstd = rsqrtf(m2 / (float)(ncl * BN) + a.eps);
-        if (rowok) {
 #pragma unroll
-          for (int c = 0; c < BN; c += 4) {
-            float4 o;
-            o.x = (v[c] - mean) * rstd; o.y = (v[c + 1] - mean) * rstd;
-            o.z = (v[c + 2] - mean) * rstd; o.w = (v[c + 3] - mean) * rstd;
-            *reinterpret_cast<float4*>(crow + c) = o;
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          float o[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) o[j] = (v[c0 + j] - mean) * rstd;
+          xpose_put(sx, lane, o);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = (lane >> 3) + 4 * i;
+            if (rr < rows_valid_w)
+              *reinterpret_cast<float4*>(cwarp + (long long)rr * a.ldc + c0 + 4 * (lane & 7)) = xpose_get(sx, lane, i);
           }
+          __syncwarp();
+        }
+        if (rowok) {
           if (a.mask) {
             uint32_t* mk = a.mask + (long long)z * a.sMask + (long long)row * a.mw + (n0 >> 5);
 #pragma unroll
@@ -464,48 +585,53 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
         for (int pr = 0; pr < ncl; ++pr) { const float2 s = xchg[pr * 128 + rit]; s1 += s.x; s2 += s.y; }
         const float inv = 1.0f / (float)(ncl * BN);
         s1 *= inv; s2 *= inv;
+        float rs_row = 0.f;
         if (rowok) {
-          const float rs = a.rstd[(long long)z * a.sRstd + row];
-          const float* xh = a.xh + (long long)z * a.sXh + (long long)row * a.ldxh + n0;
+          rs_row = a.rstd[(long long)z * a.sRstd + row];
           const uint32_t* mk = a.mask + (long long)z * a.sMask + (long long)row * a.mw + (n0 >> 5);
 #pragma unroll
-          for (int c = 0; c < BN; c += 4) {
-            const float4 x = *reinterpret_cast<const float4*>(xh + c);
-            const uint32_t bits = mk[c >> 5] >> (c & 31);
-            float4 o;
-            o.x = rs * (v[c] - s1 - x.x * s2) * ((bits & 1u) ? 1.0f : kLeakySlope);
-            o.y = rs * (v[c + 1] - s1 - x.y * s2) * ((bits & 2u) ? 1.0f : kLeakySlope);
-            o.z = rs * (v[c + 2] - s1 - x.z * s2) * ((bits & 4u) ? 1.0f : kLeakySlope);
-            o.w = rs * (v[c + 3] - s1 - x.w * s2) * ((bits & 8u) ? 1.0f : kLeakySlope);
-            *reinterpret_cast<float4*>(crow + c) = o;
+          for (int w = 0; w < BN / 32; ++w) mbits[w] = mk[w];
+        }
+#pragma unroll
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          float o[32];
+          const uint32_t bits = mbits[c0 >> 5];
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 x = *reinterpret_cast<const float4*>(sxh + lane * (BN + 4) + c0 + j);
+            o[j] = rs_row * (v[c0 + j] - s1 - x.x * s2) * (((bits >> j) & 1u) ? 1.0f : kLeakySlope);
+            o[j + 1] = rs_row * (v[c0 + j + 1] - s1 - x.y * s2) * (((bits >> (j + 1)) & 1u) ? 1.0f : kLeakySlope);
+            o[j + 2] = rs_row * (v[c0 + j + 2] - s1 - x.z * s2) * (((bits >> (j + 2)) & 1u) ? 1.0f : kLeakySlope);
+            o[j + 3] = rs_row * (v[c0 + j + 3] - s1 - x.w * s2) * (((bits >> (j + 3)) & 1u) ? 1.0f : kLeakySlope);
           }
+          xpose_put(sx, lane, o);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = (lane >> 3) + 4 * i;
+            if (rr < rows_valid_w)
+              *reinterpret_cast<float4*>(cwarp + (long long)rr * a.ldc + c0 + 4 * (lane & 7)) = xpose_get(sx, lane, i);
+          }
+          __syncwarp();
         }
       }
     } else {
-    float* crow = a.C + (long long)z * a.sC + (long long)row * a.ldc;
     const float* bias = a.bias ? a.bias + (long long)z * a.sBias : nullptr;
     const bool vec_ok = (a.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.C) + (size_t)z * a.sC * 4) & 15) == 0;
+    float* crow = a.C + (long long)z * a.sC + (long long)row * a.ldc;
+    // (a shared-memory transposition for fully coalesced stores was measured SLOWER here: this epilogue is
+    // bound by the 64 B/clk TMEM read path, not by the LSU; the fused epilogues keep the transposition)
     for (int c0 = 0; c0 < BN; c0 += 32) {
       if (n0 + c0 >= a.N) break;   // warp-uniform
-      uint32_t r[32];
+      float rf[32];
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c0);
-      tmem_ld32(taddr, r);
-#pragma unroll
-      for (int ac = 1; ac <= NACC; ++ac) {   // remaining main accumulators, then corr (slot NACC)
-        if (ac < NACC ? ac < nacc_used : a.passes == 3) {
-          uint32_t rc[32];
-          tmem_ld32(taddr + ac * BN, rc);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(rc[j]));
-        }
-      }
+      tmem_ld_sum<BN, NACC>(taddr, nacc_used, with_corr, rf);
+      if (threadIdx.x == 64 && c0 == 0) NF_TS(5);
       if (row < a.M) {
         const int cbase = n0 + c0;
         if (cbase + 32 <= a.N && vec_ok) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                   __uint_as_float(r[j + 3]));
+            float4 v = make_float4(rf[j], rf[j + 1], rf[j + 2], rf[j + 3]);
             float4* dst = reinterpret_cast<float4*>(crow + cbase + j);
             if (MNMAJOR) {
               red_add_v4(crow + cbase + j, v);
@@ -520,9 +646,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
           for (int j = 0; j < 32; ++j) {
             if (cbase + j < a.N) {
               if (MNMAJOR) {
-                atomicAdd(crow + cbase + j, __uint_as_float(r[j]));
+                atomicAdd(crow + cbase + j, rf[j]);
               } else {
-                float v = __uint_as_float(r[j]) + (bias ? bias[cbase + j] : 0.f);
+                float v = rf[j] + (bias ? bias[cbase + j] : 0.f);
                 if (a.accumulate) v += crow[cbase + j];
                 crow[cbase + j] = v;
               }
@@ -530,9 +656,12 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
           }
         }
       }
+      if (threadIdx.x == 64 && c0 == 0) NF_TS(6);
     }
     }  // plain epilogue
   }
+  if (threadIdx.x == 64) NF_TS(7);     // outputs stored
+#undef NF_TS
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
@@ -543,6 +672,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
 // ---------------------------------------------------------------------------------------------
 // host side: tensor maps
 // ---------------------------------------------------------------------------------------------
+long long* g_tc_dbg = nullptr;   // set by nf_debug_tc_timeline
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -594,6 +725,15 @@ int set_smem() {
   return 0;
 }
 
+// accumulate-truncation budget: one main accumulator per 32 k8 steps (K = 256), at most 3; reductions of up to
+// 12 k8 steps (K <= 96) keep the cross terms in the main accumulator (3 truncations per step, still < 40)
+constexpr int kMergeCorrK8 = 12;
+int pick_nacc(int total_k8) {
+  static const int forced = [] { const char* e = getenv("NF_B200_NACC"); return e ? atoi(e) : 0; }();
+  (void)total_k8;
+  return forced;   // 0 = kernel default (all NACC accumulators)
+}
+
 template <int BN, int STAGES, int BK>
 int launch(const TcGemmP& p, cudaStream_t st) {
   using S = Smem<BN, STAGES, BK>;
@@ -615,6 +755,11 @@ int launch(const TcGemmP& p, cudaStream_t st) {
   a.zA0 = p.sA0 != 0; a.zA1 = p.sA1 != 0; a.zB0 = p.sB0 != 0; a.zB1 = p.sB1 != 0;
   a.accumulate = p.accumulate; a.passes = p.passes; a.raw_hi = p.raw_hi; a.lo_round = p.lo_round;
   a.splitk = 1; a.chunks_per_split = 0;
+  a.dbg = g_tc_dbg;
+  {
+    const int total_k8 = (p.K0 + 7) / 8 + (p.K1 + 7) / 8;
+    a.nacc = pick_nacc(total_k8); a.merge_corr = 0 * (total_k8 <= kMergeCorrK8);
+  }
   dim3 grid((unsigned)cdiv(p.M, BM), (unsigned)cdiv(p.N, BN), (unsigned)p.batch);
   ProfScope prof(st, PROF_TC_GEMM, 2.0 * p.M * p.N * (double)(p.K0 + p.K1) * p.batch);
   k_tc_gemm<BN, STAGES, false, BK><<<grid, NTHREADS, S::TOTAL, st>>>(mA0, mA1, mB0, mB1, a);
@@ -648,6 +793,11 @@ int launch_epi(const TcGemmP& p, cudaStream_t st) {
   a.zA0 = p.sA0 != 0; a.zA1 = p.sA1 != 0; a.zB0 = p.sB0 != 0; a.zB1 = p.sB1 != 0;
   a.accumulate = 0; a.passes = p.passes; a.raw_hi = p.raw_hi; a.lo_round = p.lo_round;
   a.splitk = 1; a.chunks_per_split = 0;
+  a.dbg = g_tc_dbg;
+  {
+    const int total_k8 = (p.K0 + 7) / 8 + (p.K1 + 7) / 8;
+    a.nacc = pick_nacc(total_k8); a.merge_corr = 0 * (total_k8 <= kMergeCorrK8);
+  }
   a.rstd = p.epi.rstd; a.sRstd = p.epi.sRstd; a.mask = p.epi.mask; a.sMask = p.epi.sMask; a.mw = p.epi.mw;
   a.xh = p.epi.xh; a.ldxh = p.epi.ldxh; a.sXh = p.epi.sXh; a.eps = p.epi.eps;
   a.ncl = p.N / BN;
@@ -700,6 +850,11 @@ int launch_tn(const TcGemmTnP& p, cudaStream_t st) {
   a.zA0 = p.sA != 0; a.zB0 = p.sB != 0; a.zA1 = a.zB1 = 0;
   a.accumulate = 1; a.passes = p.passes; a.raw_hi = 0; a.lo_round = p.lo_round;
   a.splitk = (int)splitk; a.chunks_per_split = (int)per;
+  a.dbg = g_tc_dbg;
+  {
+    const int total_k8 = (int)(per * BK / 8);
+    a.nacc = pick_nacc(total_k8); a.merge_corr = 0 * (total_k8 <= kMergeCorrK8);
+  }
   dim3 grid((unsigned)cdiv(p.M, BM), (unsigned)cdiv(p.N, BN), (unsigned)(splitk * p.batch));
   ProfScope prof(st, PROF_TC_WGRAD, 2.0 * p.M * p.N * (double)p.K * p.batch);
   k_tc_gemm<BN, STAGES, true, BK><<<grid, NTHREADS, S::TOTAL, st>>>(mA, mA, mB, mB, a);
@@ -708,6 +863,8 @@ int launch_tn(const TcGemmTnP& p, cudaStream_t st) {
 }
 
 }  // namespace
+
+void g_tc_dbg_set(long long* p) { g_tc_dbg = p; }
 
 bool tc_gemm_supported(const TcGemmP& p) {
   if (p.M <= 0 || p.N <= 0 || p.K0 <= 0 || p.batch <= 0 || p.batch > 65535) return false;
@@ -746,9 +903,9 @@ int tc_gemm(const TcGemmP& p, cudaStream_t st) {
                "tc_gemm: operands must be 16-byte aligned with row pitches that are multiples of 4 floats");
   // small problems: prefer more, smaller CTAs (3 pipeline stages) over filling TMEM
   // BN = 256 fills TMEM with one main + one corr accumulator; BN <= 128 leaves room for the three rotating
-  // main accumulators that keep long reductions inside fp32 parity, so 256 is only used for short ones.
+  // main accumulators that keep long reductions inside fp32 parity, so 256 is only used while one accumulator is enough (K <= 256, pick_nacc).
   static const int wide_ok = [] { const char* e = getenv("NF_B200_BN256"); return e ? atoi(e) : 0; }();
-  const long long ctas256 = (wide_ok == 1 || (wide_ok == 0 && p.K0 + p.K1 <= 128))
+  const long long ctas256 = (wide_ok == 1 || (wide_ok == 0 && p.K0 + p.K1 <= 256))
                                 ? cdiv(p.M, BM) * cdiv(p.N, 256) * p.batch : 0;
   if (p.bk == 32) {
     if (p.N > 128 && ctas256 >= 120) return launch<256, 2, 32>(p, st);
@@ -786,3 +943,11 @@ int tc_gemm_tn(const TcGemmTnP& p, cudaStream_t st) {
 }
 
 }  // namespace nf
+
+// Debug aid: when `buf` is non-null every following tcgen05 GEMM launch writes 8 clock64 timestamps per
+// CTA into it (start, prologue done, first tile landed, last tile split, accumulators complete, row in
+// registers, statistics exchanged, outputs stored); tools/tc_timeline.py prints the phase durations.
+extern "C" __attribute__((visibility("default"))) int nf_debug_tc_timeline(long long* buf) {
+  nf::g_tc_dbg_set(buf);
+  return 0;
+}
