@@ -36,6 +36,36 @@ int64_t& launch_counter();
     NF_CUDA(cudaPeekAtLastError());      \
   } while (0)
 
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------
+// Every kernel of the library is launched with cudaLaunchAttributeProgrammaticStreamSerialization and
+// starts with NF_PDL_ENTRY(): it blocks until the kernel before it in the stream has completed and
+// flushed (griddepcontrol.wait), then lets the kernel after it be scheduled (launch_dependents), so
+// that launch latency and prologue of kernel N+1 overlap the execution of kernel N -- the flow is a
+// chain of 60-500 short dependent kernels.  Because every kernel waits before its first global
+// access, completion is transitive and no RAW/WAR hazard is exposed.  NF_B200_PDL=0 turns it off.
+#if defined(__CUDACC__)
+#define NF_PDL_ENTRY()                                          \
+  do {                                                          \
+    asm volatile("griddepcontrol.wait;" ::: "memory");          \
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); \
+  } while (0)
+
+bool pdl_enabled();
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#define NF_LAUNCH(kernel, grid, block, smem, st, ...) \
+  (void)nf::launch_pdl(kernel, dim3(grid), dim3(block), (size_t)(smem), st, __VA_ARGS__)
+#endif
+
 static inline int64_t pad4(int64_t v) { return (v + 3) & ~int64_t(3); }
 static inline int64_t pad32(int64_t v) { return (v + 31) & ~int64_t(31); }
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -18,6 +18,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 // nn.LayerNorm's two-pass statistics (torch_fcnf.py:75-76).
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_lrelu_ln_fwd(LnFwdP p) {
+  NF_PDL_ENTRY();
   const int net = blockIdx.y;
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -73,6 +74,7 @@ __global__ void __launch_bounds__(256) k_lrelu_ln_fwd(LnFwdP p) {
 constexpr int kBwdRowsPerWarp = 8;
 constexpr int kBwdWarps = 8;
 __global__ void __launch_bounds__(kBwdWarps * 32) k_ln_lrelu_bwd(LnBwdP p, int rpw) {
+  NF_PDL_ENTRY();
   __shared__ float s_col[kBwdWarps][256];
   const int net = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -146,6 +148,7 @@ __global__ void __launch_bounds__(256) k_affine_rowthread(const float* __restric
                                                           const float* __restrict__ bt, const float* cdev, float chost,
                                                           long long B, int D, int ldi, int ldo, float* __restrict__ out,
                                                           float* __restrict__ logdet, float* __restrict__ s_out) {
+  NF_PDL_ENTRY();
   const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= B) return;
   const int dc = (D + 1) / 2, dt = D / 2;
@@ -197,6 +200,7 @@ __global__ void __launch_bounds__(256) k_affine_rowwarp(const float* __restrict_
                                                         const float* __restrict__ bt, const float* cdev, float chost,
                                                         long long B, int D, int ldi, int ldo, float* __restrict__ out,
                                                         float* __restrict__ logdet, float* __restrict__ s_out) {
+  NF_PDL_ENTRY();
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= B) return;
@@ -226,6 +230,7 @@ __global__ void __launch_bounds__(256) k_affine_bwd(const float* __restrict__ dz
                                                     long long B, int D, float* __restrict__ dxp,
                                                     float* __restrict__ ds, float* __restrict__ dtt,
                                                     float* g3s, float* g3t) {
+  NF_PDL_ENTRY();
   extern __shared__ float sh[];  // 2*dt partial column sums
   const int dc = (D + 1) / 2, dt = D / 2;
   for (int i = threadIdx.x; i < 2 * dt; i += blockDim.x) sh[i] = 0.f;
@@ -267,6 +272,7 @@ __global__ void __launch_bounds__(256) k_affine_bwd(const float* __restrict__ dz
 // ------------------------------------------------------------------------------------------
 // Lh = tril(L,-1)+I, Uh = triu(U,1)+diag(s)  (torch_fcnf.py:34-38), logdet_c = sum log|s| (:41)
 __global__ void k_plu_mask(const float* params, NfParamLayout pl, int D, float* packed, PackedLayout kl) {
+  NF_PDL_ENTRY();
   const int b = blockIdx.y;
   const float* pb = params + (long long)b * pl.block_stride;
   float* kb = packed + (long long)b * kl.block_stride;
@@ -287,6 +293,7 @@ __global__ void k_plu_mask(const float* params, NfParamLayout pl, int D, float* 
 }
 
 __global__ void k_logdet_total(float* packed, PackedLayout kl, int n) {
+  NF_PDL_ENTRY();
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     float acc = 0.f;
     for (int i = 0; i < n; ++i) acc += packed[kl.logdet_c + i];
@@ -297,6 +304,7 @@ __global__ void k_logdet_total(float* packed, PackedLayout kl, int n) {
 // Triangular inverses by substitution against the identity, one thread per column
 // (torch.linalg.solve_triangular(..., eye), torch_fcnf.py:49-52).
 __global__ void k_tri_inverse(const float* packed, PackedLayout kl, int D, float* uinv, float* linv) {
+  NF_PDL_ENTRY();
   const int b = blockIdx.y;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;  // column of the inverse
   if (j >= D) return;
@@ -326,6 +334,7 @@ __global__ void k_tri_inverse(const float* packed, PackedLayout kl, int D, float
 // W2f = W2 diag(gamma1), b2f = b2 + W2 beta1 ; W3f = W3 diag(gamma2), b3f = b3 + W3 beta2.
 // LayerNorm's affine part commutes into the next Linear, so the forward only stores x_hat.
 __global__ void k_fold(const float* params, NfParamLayout pl, Dims m, float* packed, PackedLayout kl) {
+  NF_PDL_ENTRY();
   const int b = blockIdx.z, net = blockIdx.y;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // over C + dt output rows
@@ -360,6 +369,7 @@ __global__ void k_fold(const float* params, NfParamLayout pl, Dims m, float* pac
 // W1p[r][c] = W1[r][c] for the x_cond columns c < dc, W1p[r][dcp + j] = W1[r][dc + j] for the y
 // columns, zero elsewhere.
 __global__ void k_pack_w1(const float* params, NfParamLayout pl, Dims m, float* packed, PackedLayout kl) {
+  NF_PDL_ENTRY();
   const int b = blockIdx.z, net = blockIdx.y, r = blockIdx.x;
   const float* W = params + (long long)b * pl.block_stride + net * pl.net_stride + pl.slot_off[NF_P_W1] +
                    (long long)r * m.K1;
@@ -377,6 +387,7 @@ __global__ void k_pack_w1(const float* params, NfParamLayout pl, Dims m, float* 
 //   dW[n,k] = G[n,k] gamma[k] + g[n] beta[k];  dgamma[k] = sum_n G[n,k] W[n,k];  dbeta[k] = sum_n g[n] W[n,k]
 constexpr int kUnfoldRows = 16;
 __global__ void k_unfold(const float* params, NfParamLayout pl, Dims m, float* dparams) {
+  NF_PDL_ENTRY();
   const int layer = blockIdx.z & 1, net = (blockIdx.z >> 1) & 1, b = blockIdx.z >> 2;
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   const int rows = layer == 0 ? m.C : m.dt;
@@ -407,6 +418,7 @@ __global__ void k_unfold(const float* params, NfParamLayout pl, Dims m, float* d
 // dL = tril(dLh,-1), dU = triu(dUh,1), ds = diag(dUh) + sum(dlogdet)/s
 __global__ void k_plu_grad_finish(const float* params, NfParamLayout pl, int D, const float* dLh, const float* dUh,
                                   const float* sum_dld, float* dparams) {
+  NF_PDL_ENTRY();
   const int b = blockIdx.y;
   const float* pb = params + (long long)b * pl.block_stride;
   float* db = dparams + (long long)b * pl.block_stride;
@@ -422,6 +434,7 @@ __global__ void k_plu_grad_finish(const float* params, NfParamLayout pl, int D, 
 }
 
 __global__ void k_sum_vector(const float* v, long long n, float* out) {
+  NF_PDL_ENTRY();
   __shared__ float sh[32];
   float acc = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -437,11 +450,13 @@ __global__ void k_sum_vector(const float* v, long long n, float* out) {
 }
 
 __global__ void k_axpy(float* dst, const float* src, long long n) {
+  NF_PDL_ENTRY();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     dst[i] += src[i];
 }
 
 __global__ void k_copy2d(float* dst, long long ldd, const float* src, long long lds, long long rows, int cols) {
+  NF_PDL_ENTRY();
   const long long total = rows * cols;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / cols;
@@ -452,6 +467,7 @@ __global__ void k_copy2d(float* dst, long long ldd, const float* src, long long 
 
 __global__ void k_transpose2d(float* dst, long long ldd, long long sd0, long long sd1, const float* src, long long lds,
                               long long ss0, long long ss1, int rows, int cols, int batch0) {
+  NF_PDL_ENTRY();
   __shared__ float tile[32][33];
   const int b0 = blockIdx.z % batch0, b1 = blockIdx.z / batch0;
   const float* s = src + b0 * ss0 + b1 * ss1;
@@ -477,7 +493,7 @@ int lrelu_ln_fwd(const LnFwdP& p, cudaStream_t st) {
   if (p.B <= 0) return 0;
   dim3 grid((unsigned)cdiv(p.B, 8), (unsigned)p.nets);
   ProfScope prof(st, PROF_LN_FWD, 8.0 * p.B * p.N * p.nets);   // read u, write x_hat
-  k_lrelu_ln_fwd<<<grid, 256, 0, st>>>(p);
+  NF_LAUNCH((k_lrelu_ln_fwd), grid, 256, 0, st, p);
   NF_LAUNCHED();
   return 0;
 }
@@ -490,7 +506,7 @@ int ln_lrelu_bwd(const LnBwdP& p, cudaStream_t st) {
   if (rpw > kBwdRowsPerWarp) rpw = kBwdRowsPerWarp;
   dim3 grid((unsigned)cdiv(p.B, kBwdWarps * rpw), (unsigned)p.nets);
   ProfScope prof(st, PROF_LN_BWD, 12.0 * p.B * p.N * p.nets);  // read g, x_hat; write du
-  k_ln_lrelu_bwd<<<grid, kBwdWarps * 32, 0, st>>>(p, (int)rpw);
+  NF_LAUNCH((k_ln_lrelu_bwd), grid, kBwdWarps * 32, 0, st, p, (int)rpw);
   NF_LAUNCHED();
   return 0;
 }
@@ -506,12 +522,12 @@ static int affine_launch(const float* in, int ldi, const float* s, const float* 
     const bool vec = (D % 8 == 0) && (ldi % 4 == 0) && (ldo % 4 == 0);
     dim3 grid((unsigned)cdiv(B, 256));
     if (vec)
-      k_affine_rowthread<4, INV><<<grid, 256, 0, st>>>(in, s, t, bs, bt, cdev, chost, B, D, ldi, ldo, out, logdet, s_out);
+      NF_LAUNCH((k_affine_rowthread<4, INV>), grid, 256, 0, st, in, s, t, bs, bt, cdev, chost, B, D, ldi, ldo, out, logdet, s_out);
     else
-      k_affine_rowthread<1, INV><<<grid, 256, 0, st>>>(in, s, t, bs, bt, cdev, chost, B, D, ldi, ldo, out, logdet, s_out);
+      NF_LAUNCH((k_affine_rowthread<1, INV>), grid, 256, 0, st, in, s, t, bs, bt, cdev, chost, B, D, ldi, ldo, out, logdet, s_out);
   } else {
     dim3 grid((unsigned)cdiv(B, 8));
-    k_affine_rowwarp<INV><<<grid, 256, 0, st>>>(in, s, t, bs, bt, cdev, chost, B, D, ldi, ldo, out, logdet, s_out);
+    NF_LAUNCH((k_affine_rowwarp<INV>), grid, 256, 0, st, in, s, t, bs, bt, cdev, chost, B, D, ldi, ldo, out, logdet, s_out);
   }
   NF_LAUNCHED();
   return 0;
@@ -536,8 +552,7 @@ int affine_bwd(const float* dz, const float* z, const float* s_full, const float
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
   ProfScope prof(st, PROF_AFFINE, 4.0 * B * (3.0 * D + 3.0 * (D / 2) + 1.0));
-  k_affine_bwd<<<(unsigned)blocks, 256, 2 * (D / 2) * sizeof(float) + 16, st>>>(dz, z, s_full, dlogdet, B, D, dxp,
-                                                                              ds, dt, g3s, g3t);
+  NF_LAUNCH((k_affine_bwd), (unsigned)blocks, 256, 2 * (D / 2) * sizeof(float) + 16, st, dz, z, s_full, dlogdet, B, D, dxp,                                                                               ds, dt, g3s, g3t);
   NF_LAUNCHED();
   return 0;
 }
@@ -545,9 +560,9 @@ int affine_bwd(const float* dz, const float* z, const float* s_full, const float
 int plu_mask(const float* params, const NfParamLayout& pl, const Dims& m, float* packed, const PackedLayout& kl,
              cudaStream_t st) {
   dim3 grid((unsigned)std::min<int64_t>(cdiv((int64_t)m.D * m.D, 256), 64), (unsigned)m.n);
-  k_plu_mask<<<grid, 256, 0, st>>>(params, pl, m.D, packed, kl);
+  NF_LAUNCH((k_plu_mask), grid, 256, 0, st, params, pl, m.D, packed, kl);
   NF_LAUNCHED();
-  k_logdet_total<<<1, 32, 0, st>>>(packed, kl, m.n);
+  NF_LAUNCH((k_logdet_total), 1, 32, 0, st, packed, kl, m.n);
   NF_LAUNCHED();
   return 0;
 }
@@ -555,7 +570,7 @@ int plu_mask(const float* params, const NfParamLayout& pl, const Dims& m, float*
 int plu_tri_inverse(const float* packed, const PackedLayout& kl, const Dims& m, float* uinv, float* linv,
                     cudaStream_t st) {
   dim3 grid((unsigned)cdiv(m.D, 64), (unsigned)m.n);
-  k_tri_inverse<<<grid, 64, 0, st>>>(packed, kl, m.D, uinv, linv);
+  NF_LAUNCH((k_tri_inverse), grid, 64, 0, st, packed, kl, m.D, uinv, linv);
   NF_LAUNCHED();
   return 0;
 }
@@ -563,7 +578,7 @@ int plu_tri_inverse(const float* packed, const PackedLayout& kl, const Dims& m, 
 int fold_ln_affine(const float* params, const NfParamLayout& pl, const Dims& m, float* packed, const PackedLayout& kl,
                    cudaStream_t st) {
   dim3 grid((unsigned)cdiv(m.C + m.dt, 8), 2, (unsigned)m.n);
-  k_fold<<<grid, 256, 0, st>>>(params, pl, m, packed, kl);
+  NF_LAUNCH((k_fold), grid, 256, 0, st, params, pl, m, packed, kl);
   NF_LAUNCHED();
   return 0;
 }
@@ -571,7 +586,7 @@ int fold_ln_affine(const float* params, const NfParamLayout& pl, const Dims& m, 
 int pack_w1(const float* params, const NfParamLayout& pl, const Dims& m, float* packed, const PackedLayout& kl,
             cudaStream_t st) {
   dim3 grid((unsigned)m.H1, 2, (unsigned)m.n);
-  k_pack_w1<<<grid, 128, 0, st>>>(params, pl, m, packed, kl);
+  NF_LAUNCH((k_pack_w1), grid, 128, 0, st, params, pl, m, packed, kl);
   NF_LAUNCHED();
   return 0;
 }
@@ -581,7 +596,7 @@ int unfold_grads(const float* params, const NfParamLayout& pl, const Dims& m, fl
   const int rows = m.C > m.dt ? m.C : m.dt;
   dim3 grid((unsigned)cdiv(K, 128), (unsigned)cdiv(rows, kUnfoldRows), (unsigned)(4 * m.n));
   ProfScope prof(st, PROF_PARAM, 0.0);
-  k_unfold<<<grid, 128, 0, st>>>(params, pl, m, dparams);
+  NF_LAUNCH((k_unfold), grid, 128, 0, st, params, pl, m, dparams);
   NF_LAUNCHED();
   return 0;
 }
@@ -589,7 +604,7 @@ int unfold_grads(const float* params, const NfParamLayout& pl, const Dims& m, fl
 int plu_grad_finish(const float* params, const NfParamLayout& pl, const Dims& m, const float* dLh, const float* dUh,
                     const float* sum_dld, float* dparams, cudaStream_t st) {
   dim3 grid((unsigned)std::min<int64_t>(cdiv((int64_t)m.D * m.D, 256), 64), (unsigned)m.n);
-  k_plu_grad_finish<<<grid, 256, 0, st>>>(params, pl, m.D, dLh, dUh, sum_dld, dparams);
+  NF_LAUNCH((k_plu_grad_finish), grid, 256, 0, st, params, pl, m.D, dLh, dUh, sum_dld, dparams);
   NF_LAUNCHED();
   return 0;
 }
@@ -599,7 +614,7 @@ int sum_vector(const float* v, long long n, float* out, cudaStream_t st) {
   if (n <= 0) return 0;
   long long blocks = cdiv(n, 256 * 8);
   if (blocks > 296) blocks = 296;
-  k_sum_vector<<<(unsigned)blocks, 256, 0, st>>>(v, n, out);
+  NF_LAUNCH((k_sum_vector), (unsigned)blocks, 256, 0, st, v, n, out);
   NF_LAUNCHED();
   return 0;
 }
@@ -614,7 +629,7 @@ int copy2d(float* dst, long long ldd, const float* src, long long lds, long long
   if (rows <= 0 || cols <= 0) return 0;
   long long blocks = cdiv(rows * cols, 256 * 4);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  k_copy2d<<<(unsigned)blocks, 256, 0, st>>>(dst, ldd, src, lds, rows, cols);
+  NF_LAUNCH((k_copy2d), (unsigned)blocks, 256, 0, st, dst, ldd, src, lds, rows, cols);
   NF_LAUNCHED();
   return 0;
 }
@@ -623,7 +638,7 @@ int transpose2d(float* dst, long long ldd, long long sdst0, long long sdst1, con
                 long long ssrc0, long long ssrc1, int rows, int cols, int batch0, int batch1, cudaStream_t st) {
   if (rows <= 0 || cols <= 0) return 0;
   dim3 grid((unsigned)cdiv(cols, 32), (unsigned)cdiv(rows, 32), (unsigned)(batch0 * batch1));
-  k_transpose2d<<<grid, dim3(32, 8), 0, st>>>(dst, ldd, sdst0, sdst1, src, lds, ssrc0, ssrc1, rows, cols, batch0);
+  NF_LAUNCH((k_transpose2d), grid, dim3(32, 8), 0, st, dst, ldd, sdst0, sdst1, src, lds, ssrc0, ssrc1, rows, cols, batch0);
   NF_LAUNCHED();
   return 0;
 }
@@ -632,7 +647,7 @@ int axpy_rows(float* dst, const float* src, long long n, cudaStream_t st) {
   if (n <= 0) return 0;
   long long blocks = cdiv(n, 256 * 4);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  k_axpy<<<(unsigned)blocks, 256, 0, st>>>(dst, src, n);
+  NF_LAUNCH((k_axpy), (unsigned)blocks, 256, 0, st, dst, src, n);
   NF_LAUNCHED();
   return 0;
 }

@@ -1,5 +1,6 @@
 // Orchestration of the coupling-flow hot path and the C-ABI entry points (include/nf_b200.h).
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -26,6 +27,11 @@ int set_err(int code, const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
   return code;
+}
+
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("NF_B200_PDL"); return !(e && e[0] == '0'); }();
+  return on;
 }
 
 int check_desc(const NfFlowDesc* d) {

@@ -24,6 +24,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 // ---------------------------------------------------------------------------------------------
 template <int MAXDT>
 __global__ void __launch_bounds__(kWarps * 32) k_row_tail(TailP p) {
+  NF_PDL_ENTRY();
   __shared__ float sW[kRowFusedMaxD * kRowFusedMaxD];
   const int D = p.D, C = p.C, dc = (D + 1) / 2, dt = D / 2;
   if (p.Wmat)
@@ -88,6 +89,7 @@ __global__ void __launch_bounds__(kWarps * 32) k_row_tail(TailP p) {
 // added to global memory with one atomic per element and CTA.
 template <int MAXDT>
 __global__ void __launch_bounds__(kWarps * 32) k_row_bwd_head(BwdHeadP p, int rows_per_warp) {
+  NF_PDL_ENTRY();
   extern __shared__ float smem[];   // [kWarps][(1 + MAXDT) * 256] reduction slices, then [kWarps][rows_per_warp][2] stats
   const int D = p.D, C = p.C, dc = (D + 1) / 2, dt = D / 2;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -225,6 +227,7 @@ __global__ void __launch_bounds__(kWarps * 32) k_row_bwd_head(BwdHeadP p, int ro
 // ---------------------------------------------------------------------------------------------
 template <int MAXDC>
 __global__ void __launch_bounds__(kWarps * 32) k_row_bwd_tail(BwdTailP p, int rows_per_warp) {
+  NF_PDL_ENTRY();
   extern __shared__ float smem[];   // [kWarps][max(D*D, MAXDC*256)] reduction slices, then sW[D*D]
   const int D = p.D, H1 = p.H1, dc = (D + 1) / 2;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -360,8 +363,8 @@ int row_tail(const TailP& p, cudaStream_t st) {
   const int dt = p.D / 2;
   dim3 grid((unsigned)cdiv(p.B, kWarps));
   ProfScope prof(st, PROF_ROW_TAIL, 4.0 * p.B * (2.0 * p.C + 3.0 * p.D));
-  if (dt <= 4) k_row_tail<4><<<grid, kWarps * 32, 0, st>>>(p);
-  else k_row_tail<16><<<grid, kWarps * 32, 0, st>>>(p);
+  if (dt <= 4) NF_LAUNCH((k_row_tail<4>), grid, kWarps * 32, 0, st, p);
+  else NF_LAUNCH((k_row_tail<16>), grid, kWarps * 32, 0, st, p);
   NF_LAUNCHED();
   return 0;
 }
@@ -382,11 +385,11 @@ int row_bwd_head(const BwdHeadP& p, cudaStream_t st) {
   if (dt <= 4) {
     static bool cfg = false;
     if (!cfg) { NF_CUDA(cudaFuncSetAttribute(k_row_bwd_head<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cfg = true; }
-    k_row_bwd_head<4><<<grid, kWarps * 32, smem, st>>>(p, rpw);
+    NF_LAUNCH((k_row_bwd_head<4>), grid, kWarps * 32, smem, st, p, rpw);
   } else {
     static bool cfg = false;
     if (!cfg) { NF_CUDA(cudaFuncSetAttribute(k_row_bwd_head<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cfg = true; }
-    k_row_bwd_head<16><<<grid, kWarps * 32, smem, st>>>(p, rpw);
+    NF_LAUNCH((k_row_bwd_head<16>), grid, kWarps * 32, smem, st, p, rpw);
   }
   NF_LAUNCHED();
   return 0;
@@ -409,11 +412,11 @@ int row_bwd_tail(const BwdTailP& p, cudaStream_t st) {
   if (dc <= 8) {
     static bool cfg = false;
     if (!cfg) { NF_CUDA(cudaFuncSetAttribute(k_row_bwd_tail<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cfg = true; }
-    k_row_bwd_tail<8><<<grid, kWarps * 32, smem, st>>>(p, rpw);
+    NF_LAUNCH((k_row_bwd_tail<8>), grid, kWarps * 32, smem, st, p, rpw);
   } else {
     static bool cfg = false;
     if (!cfg) { NF_CUDA(cudaFuncSetAttribute(k_row_bwd_tail<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cfg = true; }
-    k_row_bwd_tail<16><<<grid, kWarps * 32, smem, st>>>(p, rpw);
+    NF_LAUNCH((k_row_bwd_tail<16>), grid, kWarps * 32, smem, st, p, rpw);
   }
   NF_LAUNCHED();
   return 0;

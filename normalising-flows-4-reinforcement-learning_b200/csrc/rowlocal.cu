@@ -26,6 +26,7 @@ __device__ __forceinline__ float dot4(const float4 a, const float4 b) {
 // ---------------------------------------------------------------------------------------------
 template <int NV>
 __global__ void __launch_bounds__(kWarps * 32) k_row_bwd_head2(BwdHead2P p, int w_smem, int rpw) {
+  NF_PDL_ENTRY();
   extern __shared__ float4 sW4[];   // [2][dt][C/4] when w_smem
   const int D = p.D, C = p.C, dc = (D + 1) / 2, dt = D / 2, C4 = C >> 2;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -125,6 +126,7 @@ __global__ void __launch_bounds__(kWarps * 32) k_row_bwd_head2(BwdHead2P p, int 
 // ---------------------------------------------------------------------------------------------
 template <int NV, int MAXDC>
 __global__ void __launch_bounds__(kWarps * 32) k_row_bwd_tail2(BwdTail2P p, int w_smem, int rpw) {
+  NF_PDL_ENTRY();
   extern __shared__ float4 sW4[];   // [2][dc][H1/4] when w_smem
   __shared__ float sW[32 * 32];
   const int D = p.D, H1 = p.H1, dc = (D + 1) / 2, H4 = H1 >> 2;
@@ -196,6 +198,7 @@ __global__ void __launch_bounds__(kWarps * 32) k_row_bwd_tail2(BwdTail2P p, int 
 // ---------------------------------------------------------------------------------------------
 template <int NV, int MAXDT>
 __global__ void __launch_bounds__(kWarps * 32) k_row_tail2(TailP p, int w_smem, int rpw) {
+  NF_PDL_ENTRY();
   extern __shared__ float4 sW4[];   // [2][dt][C/4] when w_smem
   __shared__ float sW[32 * 32];
   const int D = p.D, C = p.C, dc = (D + 1) / 2, dt = D / 2, C4 = C >> 2;
@@ -397,6 +400,7 @@ __device__ __forceinline__ void col_body(const ColJob& J, int z, long long B, in
 // KMAX = largest m over the jobs of the launch (bounds the register budget of the kernel)
 template <int KMAX>
 __global__ void __launch_bounds__(256) k_col_reduce(const __grid_constant__ ColArgs a) {
+  NF_PDL_ENTRY();
   __shared__ __align__(16) float s_coef[kColSub * KMAX];
   __shared__ float s_acc[(KMAX + 2) * kColTile];
   int job = 0, z = blockIdx.z;
@@ -429,9 +433,9 @@ int row_bwd_head2(const BwdHead2P& p, cudaStream_t st) {
   dim3 grid((unsigned)cdiv(p.B, (long long)kWarps * rpw));
   const size_t smem = w_smem ? wbytes : 0;
   ProfScope prof(st, PROF_ROW_HEAD, 4.0 * p.B * (4.0 * p.C + 4.0 * p.D));
-  if (p.C <= 256) k_row_bwd_head2<2><<<grid, kWarps * 32, smem, st>>>(p, w_smem, rpw);
-  else if (p.C <= 512) k_row_bwd_head2<4><<<grid, kWarps * 32, smem, st>>>(p, w_smem, rpw);
-  else k_row_bwd_head2<8><<<grid, kWarps * 32, smem, st>>>(p, w_smem, rpw);
+  if (p.C <= 256) NF_LAUNCH((k_row_bwd_head2<2>), grid, kWarps * 32, smem, st, p, w_smem, rpw);
+  else if (p.C <= 512) NF_LAUNCH((k_row_bwd_head2<4>), grid, kWarps * 32, smem, st, p, w_smem, rpw);
+  else NF_LAUNCH((k_row_bwd_head2<8>), grid, kWarps * 32, smem, st, p, w_smem, rpw);
   NF_LAUNCHED();
   return 0;
 }
@@ -448,8 +452,8 @@ int row_bwd_tail2(const BwdTail2P& p, cudaStream_t st) {
   ProfScope prof(st, PROF_ROW_BTAIL, 4.0 * p.B * (2.0 * p.H1 + 3.0 * p.D));
 #define NF_TAIL2(NV)                                                                              \
   do {                                                                                            \
-    if (dc <= 8) k_row_bwd_tail2<NV, 8><<<grid, kWarps * 32, smem, st>>>(p, w_smem, rpw);         \
-    else k_row_bwd_tail2<NV, 16><<<grid, kWarps * 32, smem, st>>>(p, w_smem, rpw);                \
+    if (dc <= 8) NF_LAUNCH((k_row_bwd_tail2<NV, 8>), grid, kWarps * 32, smem, st, p, w_smem, rpw);         \
+    else NF_LAUNCH((k_row_bwd_tail2<NV, 16>), grid, kWarps * 32, smem, st, p, w_smem, rpw);                \
   } while (0)
   if (p.H1 <= 256) NF_TAIL2(2);
   else if (p.H1 <= 512) NF_TAIL2(4);
@@ -471,8 +475,8 @@ int row_tail2(const TailP& p, cudaStream_t st) {
   ProfScope prof(st, PROF_ROW_TAIL, 4.0 * p.B * (2.0 * p.C + 3.0 * p.D));
 #define NF_TAILF(NV)                                                                           \
   do {                                                                                         \
-    if (dt <= 4) k_row_tail2<NV, 4><<<grid, kWarps * 32, smem, st>>>(p, w_smem, rpw);          \
-    else k_row_tail2<NV, 16><<<grid, kWarps * 32, smem, st>>>(p, w_smem, rpw);                 \
+    if (dt <= 4) NF_LAUNCH((k_row_tail2<NV, 4>), grid, kWarps * 32, smem, st, p, w_smem, rpw);          \
+    else NF_LAUNCH((k_row_tail2<NV, 16>), grid, kWarps * 32, smem, st, p, w_smem, rpw);                 \
   } while (0)
   if (p.C <= 256) NF_TAILF(2);
   else if (p.C <= 512) NF_TAILF(4);
@@ -502,10 +506,10 @@ int col_reduce(const ColJob* jobs, int njobs, long long B, cudaStream_t st) {
   a.rows_per_cta = B <= 16384 ? 128 : 1024;
   dim3 grid((unsigned)cdiv(B, a.rows_per_cta), (unsigned)tiles, (unsigned)zs);
   ProfScope prof(st, PROF_COL_REDUCE, bytes);
-  if (maxm <= 4) k_col_reduce<4><<<grid, 256, 0, st>>>(a);
-  else if (maxm <= 8) k_col_reduce<8><<<grid, 256, 0, st>>>(a);
-  else if (maxm <= 16) k_col_reduce<16><<<grid, 256, 0, st>>>(a);
-  else k_col_reduce<32><<<grid, 256, 0, st>>>(a);
+  if (maxm <= 4) NF_LAUNCH((k_col_reduce<4>), grid, 256, 0, st, a);
+  else if (maxm <= 8) NF_LAUNCH((k_col_reduce<8>), grid, 256, 0, st, a);
+  else if (maxm <= 16) NF_LAUNCH((k_col_reduce<16>), grid, 256, 0, st, a);
+  else NF_LAUNCH((k_col_reduce<32>), grid, 256, 0, st, a);
   NF_LAUNCHED();
   return 0;
 }

@@ -9,6 +9,7 @@ constexpr int BM = 64, BN = 64, BK = 16, PADM = 4;
 
 template <bool TA, bool TB>
 __global__ void __launch_bounds__(256) k_gemm(GemmP p) {
+  NF_PDL_ENTRY();
   __shared__ __align__(16) float As[BK][BM + PADM];
   __shared__ __align__(16) float Bs[BK][BN + PADM];
 
@@ -139,10 +140,10 @@ int simt_gemm(const GemmP& p, cudaStream_t st) {
   dim3 grid((unsigned)(cdiv(p.M, BM) * cdiv(p.N, BN)), (unsigned)p.splitk, (unsigned)p.batch);
   NF_CHECK_ARG(p.splitk >= 1 && p.splitk <= 65535 && p.batch <= 65535, NF_E_BADARG, "simt_gemm: grid");
   ProfScope prof(st, PROF_SIMT_GEMM, 2.0 * p.M * p.N * (double)(p.K0 + p.K1) * p.batch);
-  if (!p.transA && !p.transB) k_gemm<false, false><<<grid, 256, 0, st>>>(p);
-  else if (!p.transA && p.transB) k_gemm<false, true><<<grid, 256, 0, st>>>(p);
-  else if (p.transA && !p.transB) k_gemm<true, false><<<grid, 256, 0, st>>>(p);
-  else k_gemm<true, true><<<grid, 256, 0, st>>>(p);
+  if (!p.transA && !p.transB) NF_LAUNCH((k_gemm<false, false>), grid, 256, 0, st, p);
+  else if (!p.transA && p.transB) NF_LAUNCH((k_gemm<false, true>), grid, 256, 0, st, p);
+  else if (p.transA && !p.transB) NF_LAUNCH((k_gemm<true, false>), grid, 256, 0, st, p);
+  else NF_LAUNCH((k_gemm<true, true>), grid, 256, 0, st, p);
   NF_LAUNCHED();
   return 0;
 }

@@ -17,6 +17,8 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "prof.cuh"
 #include "tc_gemm.cuh"
 
@@ -285,11 +287,13 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
   long long* dbg = a.dbg ? a.dbg + 8ll * (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * (long long)blockIdx.z)) : nullptr;
 #define NF_TS(i) do { if (dbg) dbg[i] = clock64(); } while (0)
   if (threadIdx.x == 64) NF_TS(0);
-  const int z = MNMAJOR ? blockIdx.z / a.splitk : blockIdx.z;
+  const int z = blockIdx.z / a.splitk;
   const int nk0 = (a.K0 + BK - 1) / BK, nk1 = (a.K1 + BK - 1) / BK;
   // chunk range of this CTA: everything (K-major form) or one split of the batch rows (MN-major form)
-  const int kc_begin = MNMAJOR ? (blockIdx.z % a.splitk) * a.chunks_per_split : 0;
-  const int nk = MNMAJOR ? min(nk0 - kc_begin, a.chunks_per_split) : nk0 + nk1;
+  // both forms can split the reduction over CTAs (partial tiles are combined with red.global.add)
+  const int kc_begin = a.splitk > 1 ? (blockIdx.z % a.splitk) * a.chunks_per_split : 0;
+  const int nk = a.splitk > 1 ? min((MNMAJOR ? nk0 : nk0 + nk1) - kc_begin, a.chunks_per_split)
+                              : (MNMAJOR ? nk0 : nk0 + nk1);
   // The tensor core TRUNCATES (toward zero) when it adds products into the fp32 accumulator (measured with
   // tools/tc_precision.py: all-positive operands lose 5.4e-8 of the sum per k8 step, mirrored for negative
   // ones; random-sign data sees zero-mean noise that also grows linearly with the reduction length -- a
@@ -304,7 +308,11 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
     const long long len = min((long long)a.K0, (long long)(kc_begin + nk) * BK) - (long long)kc_begin * BK;
     total_k8 = (int)((len + 7) / 8);
   } else {
-    total_k8 = (a.K0 + 7) / 8 + (a.K1 + 7) / 8;
+    total_k8 = 0;
+    for (int g = kc_begin; g < kc_begin + nk; ++g) {
+      const int kleft = g >= nk0 ? a.K1 - (g - nk0) * BK : a.K0 - g * BK;
+      total_k8 += kleft >= BK ? BK / 8 : (kleft + 7) / 8;
+    }
   }
   // Rotating over all NACC accumulators is also FASTER than using fewer (measured: 840 vs 940-1100 cycles per
   // 16-deep stage): back-to-back MMAs into one accumulator serialise on it.  a.nacc / a.merge_corr stay as
@@ -331,6 +339,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
   if (EPI != EPI_NONE) cluster_sync_all();   // every CTA's exchange barrier is initialised before a peer arrives on it
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  // everything above (barrier init, TMEM allocation, tensor-map prefetch) overlaps the previous kernel
+  NF_PDL_ENTRY();
   if (threadIdx.x == 64) NF_TS(1);   // prologue done
 
   if (warp == 0) {
@@ -352,8 +362,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
             for (int g = 0; g < BN / 32; ++g)
               tma_load_3d(st + A_BYTES + g * BOX, &mB0, &full[s], n0 + g * 32, k0, a.zB0 ? z : 0);
           } else {
-            const bool seg1 = it >= nk0;
-            const int kk = (seg1 ? it - nk0 : it) * BK;
+            const int g = kc_begin + it;
+            const bool seg1 = g >= nk0;
+            const int kk = (seg1 ? g - nk0 : g) * BK;
             tma_load_3d(st, seg1 ? &mA1 : &mA0, &full[s], kk, m0, (seg1 ? a.zA1 : a.zA0) ? z : 0);
             tma_load_3d(st + A_BYTES, seg1 ? &mB1 : &mB0, &full[s], kk, n0, (seg1 ? a.zB1 : a.zB0) ? z : 0);
           }
@@ -384,8 +395,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
           const long long kleft = (long long)a.K0 - (long long)(kc_begin + it) * BK;
           nks = kleft >= BK ? BK / 8 : (int)((kleft + 7) / 8);
         } else {
-          const bool seg1 = it >= nk0;
-          const int kleft = (seg1 ? a.K1 - (it - nk0) * BK : a.K0 - it * BK);
+          const int g = kc_begin + it;
+          const bool seg1 = g >= nk0;
+          const int kleft = (seg1 ? a.K1 - (g - nk0) * BK : a.K0 - g * BK);
           nks = kleft >= BK ? BK / 8 : (kleft + 7) / 8;
         }
         const uint32_t sa = (smem_u32(smem + s * S::STAGE) & 0x3FFFFu) >> 4;
@@ -615,7 +627,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
         }
       }
     } else {
-    const float* bias = a.bias ? a.bias + (long long)z * a.sBias : nullptr;
+    const bool red = MNMAJOR || a.splitk > 1;   // partial tile: combine with red.global.add
+    const float* bias = (a.bias && kc_begin == 0) ? a.bias + (long long)z * a.sBias : nullptr;
     const bool vec_ok = (a.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.C) + (size_t)z * a.sC * 4) & 15) == 0;
     float* crow = a.C + (long long)z * a.sC + (long long)row * a.ldc;
     // (a shared-memory transposition for fully coalesced stores was measured SLOWER here: this epilogue is
@@ -633,7 +646,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
           for (int j = 0; j < 32; j += 4) {
             float4 v = make_float4(rf[j], rf[j + 1], rf[j + 2], rf[j + 3]);
             float4* dst = reinterpret_cast<float4*>(crow + cbase + j);
-            if (MNMAJOR) {
+            if (red) {
+              if (!MNMAJOR && bias) { v.x += bias[cbase + j]; v.y += bias[cbase + j + 1]; v.z += bias[cbase + j + 2]; v.w += bias[cbase + j + 3]; }
               red_add_v4(crow + cbase + j, v);
             } else {
               if (bias) { v.x += bias[cbase + j]; v.y += bias[cbase + j + 1]; v.z += bias[cbase + j + 2]; v.w += bias[cbase + j + 3]; }
@@ -645,8 +659,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             if (cbase + j < a.N) {
-              if (MNMAJOR) {
-                atomicAdd(crow + cbase + j, rf[j]);
+              if (red) {
+                atomicAdd(crow + cbase + j, rf[j] + ((!MNMAJOR && bias) ? bias[cbase + j] : 0.f));
               } else {
                 float v = rf[j] + (bias ? bias[cbase + j] : 0.f);
                 if (a.accumulate) v += crow[cbase + j];
@@ -754,15 +768,24 @@ int launch(const TcGemmP& p, cudaStream_t st) {
   a.ldc = p.ldc; a.sC = p.sC; a.sBias = p.sBias;
   a.zA0 = p.sA0 != 0; a.zA1 = p.sA1 != 0; a.zB0 = p.sB0 != 0; a.zB1 = p.sB1 != 0;
   a.accumulate = p.accumulate; a.passes = p.passes; a.raw_hi = p.raw_hi; a.lo_round = p.lo_round;
-  a.splitk = 1; a.chunks_per_split = 0;
-  a.dbg = g_tc_dbg;
-  {
-    const int total_k8 = (p.K0 + 7) / 8 + (p.K1 + 7) / 8;
-    a.nacc = pick_nacc(total_k8); a.merge_corr = 0 * (total_k8 <= kMergeCorrK8);
+  // split the reduction over CTAs when the output is accumulated anyway (C already holds the base value) and
+  // the tile grid leaves most of the 148 SMs idle: the dy GEMM of C2a (M = 4096, N = 64, K = 512) ran on 32
+  // CTAs for 37 us
+  const long long nchunks = cdiv(p.K0, BK) + cdiv(p.K1, BK);
+  const long long tiles = cdiv(p.M, BM) * cdiv(p.N, BN) * p.batch;
+  long long splitk = 1;
+  if (p.accumulate && tiles * 2 <= 148 && nchunks >= 8) {
+    splitk = std::min<long long>(148 / tiles, nchunks / 4);
+    if (splitk < 1) splitk = 1;
   }
-  dim3 grid((unsigned)cdiv(p.M, BM), (unsigned)cdiv(p.N, BN), (unsigned)p.batch);
+  const long long per = cdiv(nchunks, splitk);
+  splitk = cdiv(nchunks, per);
+  a.splitk = (int)splitk; a.chunks_per_split = (int)per;
+  a.dbg = g_tc_dbg;
+  a.nacc = pick_nacc(0); a.merge_corr = 0;
+  dim3 grid((unsigned)cdiv(p.M, BM), (unsigned)cdiv(p.N, BN), (unsigned)(p.batch * splitk));
   ProfScope prof(st, PROF_TC_GEMM, 2.0 * p.M * p.N * (double)(p.K0 + p.K1) * p.batch);
-  k_tc_gemm<BN, STAGES, false, BK><<<grid, NTHREADS, S::TOTAL, st>>>(mA0, mA1, mB0, mB1, a);
+  NF_LAUNCH((k_tc_gemm<BN, STAGES, false, BK>), grid, NTHREADS, S::TOTAL, st, mA0, mA1, mB0, mB1, a);
   NF_LAUNCHED();
   return 0;
 }
@@ -806,10 +829,12 @@ int launch_epi(const TcGemmP& p, cudaStream_t st) {
   cfg.blockDim = dim3(NTHREADS);
   cfg.dynamicSmemBytes = S::TOTAL_EPI;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = (unsigned)a.ncl; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
   ProfScope prof(st, PROF_TC_GEMM, 2.0 * p.M * p.N * (double)(p.K0 + p.K1) * p.batch);
   NF_CUDA(cudaLaunchKernelEx(&cfg, k_tc_gemm<BN, STAGES, false, BK, EPI>, mA0, mA1, mB0, mB1, a));
   NF_LAUNCHED();
@@ -857,7 +882,7 @@ int launch_tn(const TcGemmTnP& p, cudaStream_t st) {
   }
   dim3 grid((unsigned)cdiv(p.M, BM), (unsigned)cdiv(p.N, BN), (unsigned)(splitk * p.batch));
   ProfScope prof(st, PROF_TC_WGRAD, 2.0 * p.M * p.N * (double)p.K * p.batch);
-  k_tc_gemm<BN, STAGES, true, BK><<<grid, NTHREADS, S::TOTAL, st>>>(mA, mA, mB, mB, a);
+  NF_LAUNCH((k_tc_gemm<BN, STAGES, true, BK>), grid, NTHREADS, S::TOTAL, st, mA, mA, mB, mB, a);
   NF_LAUNCHED();
   return 0;
 }
