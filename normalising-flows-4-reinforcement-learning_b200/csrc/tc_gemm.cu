@@ -46,6 +46,7 @@ struct KArgs {
   float eps;
   int ncl;                               // CTAs per cluster = N / BN (the cluster spans the whole row)
   long long* dbg;                        // optional: 8 clock64 timestamps per CTA (nf_debug_tc_timeline)
+  int tma_store;                         // mC is valid: write the output tile with bulk tensor stores
 };
 constexpr int EPI_NONE = 0, EPI_LN_FWD = 1, EPI_LN_BWD = 2;
 constexpr int kMaxCluster = 8;
@@ -88,6 +89,31 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
+}
+// Output tile -> global memory through the TMA: the epilogue thread (one row of the TMEM layout) writes its
+// 32 columns into a 32 x 32 fp32 box in shared memory (128-byte rows, SWIZZLE_128B so the row-per-lane
+// 128-bit stores are conflict-free), one elected lane issues a bulk tensor store or reduce-add.  Rows and
+// columns outside the matrix are clipped by the tensor map.  Replaces row-per-lane global stores that
+// were LSU-bound (1 000 cycles per 32-column chunk, tools/tc_timeline.py).
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// the shared-memory source has been read (it may be released); the global writes complete with the grid
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// lane = row of the box; v = its 32 columns
+__device__ __forceinline__ void box_put(uint8_t* box, int lane, const float (&v)[32]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<float4*>(box + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+        make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
@@ -268,7 +294,8 @@ struct Smem {
 template <int BN, int STAGES, bool MNMAJOR, int BK, int EPI = EPI_NONE>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUtensorMap mA1,
-          const __grid_constant__ CUtensorMap mB0, const __grid_constant__ CUtensorMap mB1, const KArgs a) {
+          const __grid_constant__ CUtensorMap mB0, const __grid_constant__ CUtensorMap mB1,
+          const __grid_constant__ CUtensorMap mC, const KArgs a) {
   using S = Smem<BN, STAGES, BK>;
   constexpr int A_BYTES = S::A_BYTES;
   constexpr int BOX = 32 * BK * 4;   // bytes of one 32-column MN-major TMA box
@@ -323,6 +350,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&mA0); prefetch_tmap(&mB0);
+    if (a.tma_store) prefetch_tmap(&mC);
     if (nk1) { prefetch_tmap(&mA1); prefetch_tmap(&mB1); }
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&split[s], 4); mbar_init(&empty[s], 1); }
     mbar_init(accbar, 1);
@@ -508,6 +536,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
       float* sx = reinterpret_cast<float*>(smem) + 4 * 32 * (BN + 4) + q * kXWarpFloats;   // 32 x 32 transposition buffer
       float* cwarp = a.C + (long long)z * a.sC + (long long)(m0 + q * 32) * a.ldc + n0;
       const int rows_valid_w = a.M - (m0 + q * 32);
+      // TMA-store boxes (4 KB each, 1024-byte aligned): after the x_hat tiles / transposition buffers
+      uint8_t* boxes = smem + ((4 * 32 * (BN + 4) * 4 + 4 * kXWarpFloats * 4 + 1023) & ~1023) + q * (BN / 32) * 4096;
       float p0, p1;            // the two partial statistics of this CTA's BN columns
       uint32_t mbits[BN / 32];
       if constexpr (EPI == EPI_LN_FWD) {
@@ -575,14 +605,23 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
           float o[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) o[j] = (v[c0 + j] - mean) * rstd;
-          xpose_put(sx, lane, o);
+          if (a.tma_store) {
+            uint8_t* box = boxes + (c0 >> 5) * 4096;
+            box_put(box, lane, o);
+            // one store per 32-column chunk: the TMA drains the box while the next chunk is computed (issuing
+            // all stores of the tile at the end behind a single proxy fence measured 20 % slower)
+            if (elect_one()) { tma_store_3d(&mC, box, n0 + c0, m0 + q * 32, z); tma_store_commit(); }
+            __syncwarp();
+          } else {
+            xpose_put(sx, lane, o);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rr = (lane >> 3) + 4 * i;
-            if (rr < rows_valid_w)
-              *reinterpret_cast<float4*>(cwarp + (long long)rr * a.ldc + c0 + 4 * (lane & 7)) = xpose_get(sx, lane, i);
+            for (int i = 0; i < 8; ++i) {
+              const int rr = (lane >> 3) + 4 * i;
+              if (rr < rows_valid_w)
+                *reinterpret_cast<float4*>(cwarp + (long long)rr * a.ldc + c0 + 4 * (lane & 7)) = xpose_get(sx, lane, i);
+            }
+            __syncwarp();
           }
-          __syncwarp();
         }
         if (rowok) {
           if (a.mask) {
@@ -616,16 +655,26 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
             o[j + 2] = rs_row * (v[c0 + j + 2] - s1 - x.z * s2) * (((bits >> (j + 2)) & 1u) ? 1.0f : kLeakySlope);
             o[j + 3] = rs_row * (v[c0 + j + 3] - s1 - x.w * s2) * (((bits >> (j + 3)) & 1u) ? 1.0f : kLeakySlope);
           }
-          xpose_put(sx, lane, o);
+          if (a.tma_store) {
+            uint8_t* box = boxes + (c0 >> 5) * 4096;
+            box_put(box, lane, o);
+            // one store per 32-column chunk: the TMA drains the box while the next chunk is computed (issuing
+            // all stores of the tile at the end behind a single proxy fence measured 20 % slower)
+            if (elect_one()) { tma_store_3d(&mC, box, n0 + c0, m0 + q * 32, z); tma_store_commit(); }
+            __syncwarp();
+          } else {
+            xpose_put(sx, lane, o);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rr = (lane >> 3) + 4 * i;
-            if (rr < rows_valid_w)
-              *reinterpret_cast<float4*>(cwarp + (long long)rr * a.ldc + c0 + 4 * (lane & 7)) = xpose_get(sx, lane, i);
+            for (int i = 0; i < 8; ++i) {
+              const int rr = (lane >> 3) + 4 * i;
+              if (rr < rows_valid_w)
+                *reinterpret_cast<float4*>(cwarp + (long long)rr * a.ldc + c0 + 4 * (lane & 7)) = xpose_get(sx, lane, i);
+            }
+            __syncwarp();
           }
-          __syncwarp();
         }
       }
+      if (a.tma_store) tma_store_wait_all();   // (only the electing lanes have groups in flight)
     } else {
     const bool red = MNMAJOR || a.splitk > 1;   // partial tile: combine with red.global.add
     const float* bias = (a.bias && kc_begin == 0) ? a.bias + (long long)z * a.sBias : nullptr;
@@ -639,6 +688,22 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c0);
       tmem_ld_sum<BN, NACC>(taddr, nacc_used, with_corr, rf);
       if (threadIdx.x == 64 && c0 == 0) NF_TS(5);
+      if (a.tma_store) {
+        if (bias) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) rf[j] += (n0 + c0 + j < a.N) ? __ldg(bias + n0 + c0 + j) : 0.f;
+        }
+        uint8_t* box = smem + (q * (BN / 32) + (c0 >> 5)) * 4096;
+        box_put(box, lane, rf);
+        if (elect_one()) {
+          if (red || a.accumulate) tma_reduce_add_3d(&mC, box, n0 + c0, m0 + q * 32, z);
+          else tma_store_3d(&mC, box, n0 + c0, m0 + q * 32, z);
+          tma_store_commit();
+        }
+        __syncwarp();
+        if (threadIdx.x == 64 && c0 == 0) NF_TS(6);
+        continue;
+      }
       if (row < a.M) {
         const int cbase = n0 + c0;
         if (cbase + 32 <= a.N && vec_ok) {
@@ -672,6 +737,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
       }
       if (threadIdx.x == 64 && c0 == 0) NF_TS(6);
     }
+    if (a.tma_store) tma_store_wait_all();
     }  // plain epilogue
   }
   if (threadIdx.x == 64) NF_TS(7);     // outputs stored
@@ -722,6 +788,14 @@ int make_map(CUtensorMap* map, const float* base, long long inner, long long row
   NF_CHECK_ARG(r == CUDA_SUCCESS, NF_E_BADARG, "cuTensorMapEncodeTiled failed (%d): inner=%lld rows=%lld ld=%lld",
                (int)r, inner, rows, ld);
   return 0;
+}
+
+// output tensor map for the TMA-store epilogue: 32 x 32 fp32 boxes, SWIZZLE_128B; returns false when TMA cannot
+// address C (the direct-store epilogue is used then)
+bool make_c_map(CUtensorMap* map, float* C, long long N, long long M, long long ldc, long long batch, long long sC) {
+  static const bool on = [] { const char* e = getenv("NF_B200_TMA_STORE"); return !(e && e[0] == '0'); }();
+  if (!on || !C || (reinterpret_cast<uintptr_t>(C) & 15u) != 0 || (ldc & 3) != 0 || (sC & 3) != 0) return false;
+  return make_map(map, C, N, M, ldc, batch, sC, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B) == 0;
 }
 
 bool ok_operand(const float* p, long long ld, long long bstride) {
@@ -785,7 +859,9 @@ int launch(const TcGemmP& p, cudaStream_t st) {
   a.nacc = pick_nacc(0); a.merge_corr = 0;
   dim3 grid((unsigned)cdiv(p.M, BM), (unsigned)cdiv(p.N, BN), (unsigned)(p.batch * splitk));
   ProfScope prof(st, PROF_TC_GEMM, 2.0 * p.M * p.N * (double)(p.K0 + p.K1) * p.batch);
-  NF_LAUNCH((k_tc_gemm<BN, STAGES, false, BK>), grid, NTHREADS, S::TOTAL, st, mA0, mA1, mB0, mB1, a);
+  CUtensorMap mC = mA0;
+  a.tma_store = make_c_map(&mC, p.C, p.N, p.M, p.ldc, p.batch, p.sC) ? 1 : 0;
+  NF_LAUNCH((k_tc_gemm<BN, STAGES, false, BK>), grid, NTHREADS, S::TOTAL, st, mA0, mA1, mB0, mB1, mC, a);
   NF_LAUNCHED();
   return 0;
 }
@@ -836,7 +912,9 @@ int launch_epi(const TcGemmP& p, cudaStream_t st) {
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
   ProfScope prof(st, PROF_TC_GEMM, 2.0 * p.M * p.N * (double)(p.K0 + p.K1) * p.batch);
-  NF_CUDA(cudaLaunchKernelEx(&cfg, k_tc_gemm<BN, STAGES, false, BK, EPI>, mA0, mA1, mB0, mB1, a));
+  CUtensorMap mC = mA0;
+  a.tma_store = make_c_map(&mC, p.C, p.N, p.M, p.ldc, p.batch, p.sC) ? 1 : 0;
+  NF_CUDA(cudaLaunchKernelEx(&cfg, k_tc_gemm<BN, STAGES, false, BK, EPI>, mA0, mA1, mB0, mB1, mC, a));
   NF_LAUNCHED();
   return 0;
 }
@@ -882,7 +960,9 @@ int launch_tn(const TcGemmTnP& p, cudaStream_t st) {
   }
   dim3 grid((unsigned)cdiv(p.M, BM), (unsigned)cdiv(p.N, BN), (unsigned)(splitk * p.batch));
   ProfScope prof(st, PROF_TC_WGRAD, 2.0 * p.M * p.N * (double)p.K * p.batch);
-  NF_LAUNCH((k_tc_gemm<BN, STAGES, true, BK>), grid, NTHREADS, S::TOTAL, st, mA, mA, mB, mB, a);
+  CUtensorMap mC = mA;
+  a.tma_store = make_c_map(&mC, p.C, p.N, p.M, p.ldc, p.batch, p.sC) ? 1 : 0;
+  NF_LAUNCH((k_tc_gemm<BN, STAGES, true, BK>), grid, NTHREADS, S::TOTAL, st, mA, mA, mB, mB, mC, a);
   NF_LAUNCHED();
   return 0;
 }
