@@ -224,14 +224,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def timed(fn, steps, warmup, e2e=False):
-        for _ in range(warmup):
-            fn(x, y)
-        barrier()
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        wall0 = time.perf_counter()
-        for a, b in ev:
-            flush.zero_()                               # evict L2 between timed iterations (outside the events)
-            a.record()
+        def one():
             if e2e:
                 xd = x_pin.to(dev, non_blocking=True)   # H2D of this step's inputs from pinned memory
                 yd = y_pin.to(dev, non_blocking=True)
@@ -239,6 +232,16 @@ def run_ours(args):
                 _ = float(out.reshape(-1)[0].item()) if out.dim() else float(out.item())   # D2H of the result
             else:
                 fn(x, y)
+        for _ in range(warmup):                         # same code path as the timed steps
+            flush.zero_()
+            one()
+        barrier()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        wall0 = time.perf_counter()
+        for a, b in ev:
+            flush.zero_()                               # evict L2 between timed iterations (outside the events)
+            a.record()
+            one()
             b.record()
         barrier()
         wall = time.perf_counter() - wall0
@@ -248,6 +251,8 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)    # max over ranks
         step_stats.append((float(np.median(per)), float(max(per))))
+        if os.environ.get("BENCH_DEBUG"):
+            print("per-step ms:", " ".join(f"{v:.3f}" for v in per), file=sys.stderr, flush=True)
         return t.item() / steps, wall
 
     step_stats = []
@@ -255,11 +260,18 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     _lib.lib.nf_launch_count(1)
+    gstats = [_lib.graph_stats()]
     ms_train, _ = timed(train_step, args.steps, args.warmup)
     launches = _lib.lib.nf_launch_count(1) // (args.steps + args.warmup)
+    gstats.append(_lib.graph_stats())
     ms_sample, _ = timed(sample_step, args.steps, args.warmup)
+    gstats.append(_lib.graph_stats())
     ms_e2e, _ = timed(train_step, args.steps, args.warmup, e2e=True)
+    gstats.append(_lib.graph_stats())
     ms_e2e_sample, _ = timed(sample_step, args.steps, args.warmup, e2e=True)
+    gstats.append(_lib.graph_stats())
+    leg_graphs = {name: dict(zip(("replays", "captures", "eager_calls"), (b[i] - a[i] for i in range(3))))
+                  for name, a, b in zip(("train", "sample", "e2e_train", "e2e_sample"), gstats[:-1], gstats[1:])}
     # the four timed legs above are short (tens of ms at the default K): keep the same kernels running until
     # nvidia-smi (100 ms period) has seen them under load; these extra steps are not part of any reported time
     t_end = time.perf_counter() + 1.5
@@ -336,10 +348,10 @@ def run_ours(args):
         "e2e": {"value": total_B / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": bytes_in,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e, "ms_median_max": list(step_stats[2]),
                 "sampling": {"value": total_B / (ms_e2e_sample * 1e-3), "unit": "actions/s",
-                             "d2h_bytes_per_step": 4}},
+                             "d2h_bytes_per_step": 4, "ms_median_max": list(step_stats[3])}},
         "gpu_launches": int(launches * args.steps),
         "gpu_launches_per_step": int(launches),
-        "launch_graphs": {"replays": replays, "captures": captures, "eager_calls": eager,
+        "launch_graphs": {"replays": replays, "captures": captures, "eager_calls": eager, "per_leg": leg_graphs,
                           "note": "the library replays its kernel sequence as a cached CUDA graph; gpu_launches "
                                   "counts the library's kernels inside the replayed graphs"},
         "train_ms_median_max": list(step_stats[0]),

@@ -117,7 +117,11 @@ NF_API int nf_flow_inverse(const NfFlowDesc* desc, const float* params, const vo
                     void* workspace, int64_t ws_bytes, void* stream);
 
 /* Given dz (B,D) and dlogdet (B,) (either may be NULL = zero):  dx (B,D) or NULL, dy (B,R) or
- * NULL, dparams (flat arena, layout of nf_param_layout, fully overwritten) or NULL. */
+ * NULL, dparams (flat arena, layout of nf_param_layout, fully overwritten) or NULL.  `y` must be the
+ * tensor given to nf_flow_forward; the kernels read the copy forward left in the stash.
+ * All entry points copy the caller's inputs into / outputs out of the workspace and stash with stream-ordered
+ * copies around the kernel sequence: the kernels themselves only touch params, packed, stash and workspace,
+ * so keeping THOSE buffers persistent is what makes the cached launch graphs replay (see below). */
 NF_API int nf_flow_backward(const NfFlowDesc* desc, const float* params, const void* packed,
                      const void* stash, const float* y, int64_t B,
                      const float* dz, const float* dlogdet,

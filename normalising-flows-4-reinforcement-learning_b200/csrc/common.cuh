@@ -107,10 +107,10 @@ PackedLayout packed_layout(const Dims& m);
 
 // ---- stash written by forward for backward ---------------------------------------------------
 // xs: (n+1, B, D) block inputs (xs[0] = x, xs[i+1] = output of block i)
-// ss: (n, B, dt)  log-scales s of every block
+// ss: (n, B, dt)  log-scales s of every block ; y: (B, R) conditioning input
 // then per block, per net (t, s):  xh1 (B*H1), xh2 (B*C), r1 (B), r2 (B), m1 (B*W1w), m2 (B*W2w)
 struct StashLayout {
-  int64_t xs, ss, blocks;
+  int64_t xs, ss, y, blocks;   // y: (B, R) copy of the conditioning input (backward reads it from here)
   int64_t xh1, xh2, r1, r2, m1, m2;   // offsets inside a net
   int64_t net_stride, block_stride, total;
   int mw1, mw2;                        // mask words per row

@@ -1,5 +1,7 @@
 // Row-wise and parameter-sized kernels of the flow (sm_100a).
 #include "elementwise.cuh"
+
+#include <algorithm>
 #include "prof.cuh"
 
 namespace nf {
@@ -648,6 +650,35 @@ int axpy_rows(float* dst, const float* src, long long n, cudaStream_t st) {
   long long blocks = cdiv(n, 256 * 4);
   if (blocks > 148 * 8) blocks = 148 * 8;
   NF_LAUNCH((k_axpy), (unsigned)blocks, 256, 0, st, dst, src, n);
+  NF_LAUNCHED();
+  return 0;
+}
+
+namespace {
+__global__ void __launch_bounds__(256) k_copy_segments(CopySegs c) {
+  NF_PDL_ENTRY();
+  const int seg = blockIdx.y;
+  const long long n = c.n[seg];
+  const float* __restrict__ src = c.src[seg];
+  float* __restrict__ dst = c.dst[seg];
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15u) == 0) {
+    const long long n4 = n >> 2;
+    for (long long k = i; k < n4; k += stride) reinterpret_cast<float4*>(dst)[k] = __ldg(reinterpret_cast<const float4*>(src) + k);
+    for (long long k = (n4 << 2) + i; k < n; k += stride) dst[k] = src[k];
+  } else {
+    for (long long k = i; k < n; k += stride) dst[k] = src[k];
+  }
+}
+}  // namespace
+
+int copy_segments(const CopySegs& c, cudaStream_t st) {
+  if (c.count == 0) return 0;
+  long long mx = 0;
+  for (int i = 0; i < c.count; ++i) mx = std::max(mx, c.n[i]);
+  const long long blocks = std::min<long long>(std::max<long long>(cdiv(mx, 4 * 256), 1), 148 * 4);
+  NF_LAUNCH((k_copy_segments), dim3((unsigned)blocks, (unsigned)c.count), 256, 0, st, c);
   NF_LAUNCHED();
   return 0;
 }

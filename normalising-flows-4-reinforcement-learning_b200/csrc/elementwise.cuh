@@ -56,6 +56,10 @@ int plu_grad_finish(const float* params, const NfParamLayout& pl, const Dims& m,
                     const float* dUh, const float* sum_dld, float* dparams, cudaStream_t st);
 int sum_vector(const float* v, long long n, float* out, cudaStream_t st);  // out[0] = sum(v)
 int fill_zero(float* p, long long n, cudaStream_t st);
+// up to 4 contiguous device-to-device copies in one launch (the I/O staging around the cached launch graphs)
+struct CopySegs { float* dst[4]; const float* src[4]; long long n[4]; int count = 0;
+                  void add(float* d, const float* s, long long k) { if (d && s && k > 0 && d != s) { dst[count] = d; src[count] = s; n[count] = k; ++count; } } };
+int copy_segments(const CopySegs& c, cudaStream_t st);
 int axpy_rows(float* dst, const float* src, long long n, cudaStream_t st);  // dst += src
 int copy2d(float* dst, long long ldd, const float* src, long long lds, long long rows, int cols, cudaStream_t st);
 // dst[b][c][r] = src[b][r][c]  (rows x cols -> cols x rows), batched with strides in floats

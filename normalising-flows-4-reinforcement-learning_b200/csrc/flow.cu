@@ -105,6 +105,7 @@ StashLayout stash_layout(const Dims& m, int64_t B) {
   int64_t off = 0;
   s.xs = off; off += pad4((int64_t)(m.n + 1) * B * m.D);
   s.ss = off; off += pad4((int64_t)m.n * B * m.dt);
+  s.y = off; off += pad4(B * m.R);
   s.blocks = off;
   int64_t n = 0;
   s.xh1 = n; n += pad4(B * m.H1);
@@ -133,7 +134,11 @@ struct Carver {
   }
 };
 
-struct FwdWs { float *xp, *u, *o, *xh1, *xh2, *pp0, *pp1; int64_t total; int Dp; };
+// io_*: staging copies of the caller's inputs / outputs.  The kernels only ever touch caller-owned PERSISTENT
+// buffers (workspace, stash, packed, params); the caller's x / y / z / logdet / ... are copied in and out with
+// plain stream-ordered copies around the kernel sequence, so the cached launch graph does not depend on
+// the I/O pointers (fresh tensors every step would otherwise force a new capture each time).
+struct FwdWs { float *xp, *u, *o, *xh1, *xh2, *pp0, *pp1, *io_x, *io_y, *io_z, *io_ld, *io_outs; int64_t total; int Dp; };
 static FwdWs carve_fwd(const Dims& m, int64_t B, void* ws) {
   Carver c(ws);
   FwdWs w;
@@ -146,11 +151,19 @@ static FwdWs carve_fwd(const Dims& m, int64_t B, void* ws) {
   w.xh2 = c.take(2 * B * m.C);
   w.pp0 = c.take(B * w.Dp);
   w.pp1 = c.take(B * w.Dp);
+  w.io_x = c.take(B * w.Dp);
+  w.io_y = c.take(B * m.R);
+  w.io_z = c.take(B * w.Dp);
+  w.io_ld = c.take(B);
+  w.io_outs = c.take((int64_t)m.n * B * m.D);
   w.total = c.off;
   return w;
 }
 
-struct BwdWs { float *d0, *d1, *dxp, *dout, *gA, *gB, *dWs, *T1, *dLh, *dUh, *sumdld; int64_t total; };
+struct BwdWs { float *d0, *d1, *dxp, *dout, *gA, *gB, *dWs, *T1, *dLh, *dUh, *sumdld;
+               float *dxp2, *dout2, *gA2, *gB2;   // second set: blocks alternate so side streams can lag one block
+               float *io_dz, *io_dld, *io_dy, *io_dx;   // staging of the caller's cotangents and of dx / dy (see FwdWs)
+               int64_t total; };
 static BwdWs carve_bwd(const Dims& m, int64_t B, void* ws) {
   Carver c(ws);
   BwdWs w;
@@ -167,8 +180,46 @@ static BwdWs carve_bwd(const Dims& m, int64_t B, void* ws) {
   w.dLh = c.take(m.n * DD);
   w.dUh = c.take(m.n * DD);
   w.sumdld = c.take(4);
+  w.dxp2 = c.take(B * m.D);
+  w.dout2 = c.take(2 * B * m.dt);
+  w.gA2 = c.take(2 * B * Hm);
+  w.gB2 = c.take(2 * B * Hm);
+  w.io_dz = c.take(B * m.D);
+  w.io_dld = c.take(B);
+  w.io_dy = c.take(B * m.R);
+  w.io_dx = c.take(B * m.D);
   w.total = c.off;
   return w;
+}
+
+// ---------------------------------------------------------------------------------------------
+// side streams of the backward pass
+// ---------------------------------------------------------------------------------------------
+// Per block only  head -> data gradient through layer 2/1 -> tail  is a dependent chain; the two weight-
+// gradient GEMMs, the dy GEMM and the column reductions only consume its intermediates.  They run on two
+// library-owned side streams (fork/join with events, which also become parallel branches of the captured
+// graph), so the critical path per block is 3 kernels instead of 8.  Blocks alternate between two sets of
+// intermediate buffers and the main stream waits for the side work of block i+2 before it overwrites them.
+struct SideStreams {
+  cudaStream_t s1 = nullptr, s2 = nullptr;
+  cudaEvent_t evA = nullptr, evB = nullptr, evC = nullptr, done1[2] = {nullptr, nullptr}, done2[2] = {nullptr, nullptr};
+  bool ok = false;
+};
+static SideStreams* side_streams() {
+  static SideStreams per_dev[64];
+  static const bool on = [] { const char* e = getenv("NF_B200_STREAMS"); return !(e && e[0] == '0'); }();
+  int dev = 0;
+  if (!on || cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  SideStreams& s = per_dev[dev];
+  if (!s.ok) {
+    bool good = cudaStreamCreateWithFlags(&s.s1, cudaStreamNonBlocking) == cudaSuccess &&
+                cudaStreamCreateWithFlags(&s.s2, cudaStreamNonBlocking) == cudaSuccess;
+    cudaEvent_t* evs[] = {&s.evA, &s.evB, &s.evC, &s.done1[0], &s.done1[1], &s.done2[0], &s.done2[1]};
+    for (cudaEvent_t* e : evs) good = good && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess;
+    if (!good) { cudaGetLastError(); return nullptr; }
+    s.ok = true;
+  }
+  return &s;
 }
 
 struct PrepWs { float *uinv, *linv, *T; int64_t total; };
@@ -232,8 +283,12 @@ static int wgrad_tn(int prec, const TcGemmTnP& t, cudaStream_t st) {
 
 // Small flow dimensions use the row-fused kernels of rowfused.cuh for everything around the wide GEMMs.
 static bool use_row_fused(const Dims& m) {
-  return m.D <= kRowFusedMaxD && row_bwd_head_smem(m.D, m.C) <= kRowFusedSmemLimit &&
-         row_bwd_tail_smem(m.D, m.H1) <= kRowFusedSmemLimit;
+  if (m.D > kRowFusedMaxD) return false;
+  // row-local kernels: worth it while the skinny weight matrices fit in shared memory (measured: C5 with
+  // dt = 16, C = 1024 is 45 % slower on this path than on the GEMM + row-kernel path)
+  if (row_v2_supported(m.D, m.C, m.H1))
+    return (size_t)2 * m.dt * m.C * 4 <= 40 * 1024 && (size_t)2 * m.dc * m.H1 * 4 <= 40 * 1024;
+  return row_bwd_head_smem(m.D, m.C) <= kRowFusedSmemLimit && row_bwd_tail_smem(m.D, m.H1) <= kRowFusedSmemLimit;
 }
 
 // The two conditioner MLPs (net 0 = t, net 1 = s) up to the last Linear's raw output o (2,B,dt):
@@ -428,15 +483,28 @@ int nf_flow_forward(const NfFlowDesc* desc, const float* params, const void* pac
 
   GraphKey key;
   key.op = 2; key.desc = *desc; key.B = B; key.ws_bytes = ws_bytes;
-  key.ptr[0] = params; key.ptr[1] = packed_v; key.ptr[2] = x; key.ptr[3] = y; key.ptr[4] = z; key.ptr[5] = logdet;
-  key.ptr[6] = outputs; key.ptr[7] = stash_v; key.ptr[8] = workspace;
+  key.ptr[0] = params; key.ptr[1] = packed_v; key.ptr[7] = stash_v; key.ptr[8] = workspace;
+  key.flags = (outputs ? 1 : 0) | (stash ? 2 : 0);
+  // inputs -> persistent staging (the stash keeps x and y for backward anyway)
+  float* x_in = stash ? stash + sl.xs : w.io_x;
+  float* y_in = stash ? stash + sl.y : w.io_y;
+  float* const logdet_user = logdet;
+  float* const z_user = z;
+  float* const outputs_user = outputs;
+  {
+    CopySegs c;
+    c.add(x_in, x, BD);
+    c.add(y_in, y, B * m.R);
+    NF_TRY(copy_segments(c, user_st));
+  }
+  y = y_in;
+  logdet = w.io_ld;
+  z = w.io_z;
+  if (outputs && !stash) outputs = w.io_outs;
+  const float* z_src = nullptr;
   auto body = [&](cudaStream_t st) -> int {
   NF_CUDA(cudaMemsetAsync(logdet, 0, B * sizeof(float), st));
-  const float* cur = x;
-  if (stash) {
-    NF_CUDA(cudaMemcpyAsync(stash + sl.xs, x, BD * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    cur = stash + sl.xs;
-  }
+  const float* cur = x_in;
   const bool fused = use_row_fused(m);
   for (int i = 0; i < m.n; ++i) {
     const float* pb = params + (int64_t)i * pl.block_stride;
@@ -484,14 +552,23 @@ int nf_flow_forward(const NfFlowDesc* desc, const float* params, const void* pac
     }
     cur = next;
   }
-  if (cur != z) NF_CUDA(cudaMemcpyAsync(z, cur, BD * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  if (stash && outputs)
-    NF_CUDA(cudaMemcpyAsync(outputs, stash + sl.xs + BD, (int64_t)m.n * BD * sizeof(float), cudaMemcpyDeviceToDevice,
-                            st));
   return 0;
   };
-  return run_graphed(key, user_st, body);
+  NF_TRY(run_graphed(key, user_st, body));
+  // outputs -> the caller's buffers (the last block wrote z into the stash, the outputs array or io_z)
+  if (stash) z_src = stash + sl.xs + (int64_t)m.n * BD;
+  else if (outputs) z_src = outputs + (int64_t)(m.n - 1) * BD;
+  else z_src = z;
+  {
+    CopySegs c;
+    c.add(z_user, z_src, BD);
+    c.add(logdet_user, logdet, B);
+    if (outputs_user) c.add(outputs_user, stash ? stash + sl.xs + BD : outputs, (int64_t)m.n * BD);
+    NF_TRY(copy_segments(c, user_st));
+  }
+  return 0;
 }
+
 
 int nf_flow_inverse(const NfFlowDesc* desc, const float* params, const void* packed_v, const float* z,
                     const float* y, int64_t B, float* x, float* logdet, float* seq, void* workspace,
@@ -520,8 +597,18 @@ int nf_flow_inverse(const NfFlowDesc* desc, const float* params, const void* pac
 
   GraphKey key;
   key.op = 3; key.desc = *desc; key.B = B; key.ws_bytes = ws_bytes;
-  key.ptr[0] = params; key.ptr[1] = packed_v; key.ptr[2] = z; key.ptr[3] = y; key.ptr[4] = x; key.ptr[5] = logdet;
-  key.ptr[6] = seq; key.ptr[7] = workspace;
+  key.ptr[0] = params; key.ptr[1] = packed_v; key.ptr[6] = seq; key.ptr[7] = workspace;
+  key.flags = logdet ? 1 : 0;
+  float* const x_user = x;
+  float* const logdet_user = logdet;
+  {
+    CopySegs c;
+    c.add(w.io_x, z, BD);
+    c.add(w.io_y, y, B * m.R);
+    NF_TRY(copy_segments(c, user_st));
+  }
+  z = w.io_x; y = w.io_y; x = w.io_z;
+  if (logdet) logdet = w.io_ld;
   auto body = [&](cudaStream_t st) -> int {
   if (logdet) NF_CUDA(cudaMemsetAsync(logdet, 0, B * sizeof(float), st));
   if (seq) NF_CUDA(cudaMemcpyAsync(seq, z, BD * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -572,7 +659,14 @@ int nf_flow_inverse(const NfFlowDesc* desc, const float* params, const void* pac
   if (seq) NF_CUDA(cudaMemcpyAsync(x, seq + (int64_t)m.n * BD, BD * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return 0;
   };
-  return run_graphed(key, user_st, body);
+  NF_TRY(run_graphed(key, user_st, body));
+  {
+    CopySegs c;
+    c.add(x_user, x, BD);
+    c.add(logdet_user, logdet, B);
+    NF_TRY(copy_segments(c, user_st));
+  }
+  return 0;
 }
 
 int nf_flow_backward(const NfFlowDesc* desc, const float* params, const void* packed_v, const void* stash_v,
@@ -609,8 +703,22 @@ int nf_flow_backward(const NfFlowDesc* desc, const float* params, const void* pa
 
   GraphKey key;
   key.op = 4; key.desc = *desc; key.B = B; key.ws_bytes = ws_bytes;
-  key.ptr[0] = params; key.ptr[1] = packed_v; key.ptr[2] = stash_v; key.ptr[3] = y; key.ptr[4] = dz; key.ptr[5] = dlogdet;
-  key.ptr[6] = dx; key.ptr[7] = dy; key.ptr[8] = dparams; key.ptr[9] = workspace;
+  key.ptr[0] = params; key.ptr[1] = packed_v; key.ptr[2] = stash_v; key.ptr[8] = dparams; key.ptr[9] = workspace;
+  key.flags = (dz ? 1 : 0) | (dlogdet ? 2 : 0) | (dx ? 4 : 0) | (dy ? 8 : 0);
+  // cotangents in, dx / dy out through the workspace; y is the copy forward left in the stash
+  float* const dx_user = dx;
+  float* const dy_user = dy;
+  {
+    CopySegs c;
+    c.add(w.io_dz, dz, BD);
+    c.add(w.io_dld, dlogdet, B);
+    NF_TRY(copy_segments(c, user_st));
+  }
+  if (dz) dz = w.io_dz;
+  if (dlogdet) dlogdet = w.io_dld;
+  if (dx) dx = w.io_dx;
+  if (dy) dy = w.io_dy;
+  y = stash + sl.y;
   auto body = [&](cudaStream_t st) -> int {
   if (dparams) NF_TRY(fill_zero(dparams, pl.total, st));
   if (dy) NF_TRY(fill_zero(dy, B * m.R, st));
@@ -623,8 +731,17 @@ int nf_flow_backward(const NfFlowDesc* desc, const float* params, const void* pa
   int pp = 0;
   const bool fused = use_row_fused(m);
   const bool v2 = fused && row_v2_supported(m.D, m.C, m.H1);
+  SideStreams* ss = (v2 && (dparams || dy)) ? side_streams() : nullptr;
+  cudaStream_t s1 = ss ? ss->s1 : st, s2 = ss ? ss->s2 : st;
+  bool used1[2] = {false, false}, used2[2] = {false, false};
+  struct { float *dxp, *dout, *gA, *gB; } w2[2] = {{w.dxp, w.dout, w.gA, w.gB}, {w.dxp2, w.dout2, w.gA2, w.gB2}};
   for (int i = m.n - 1; i >= 0; --i) {
-    const float* pb = params + (int64_t)i * pl.block_stride;
+    const int par = ss ? ((m.n - 1 - i) & 1) : 0;
+    const auto& wb = w2[par];   // this block's intermediate buffers
+    if (ss) {   // the side work of block i+2 read this buffer set
+      if (used1[par]) NF_CUDA(cudaStreamWaitEvent(st, ss->done1[par], 0));
+      if (used2[par]) NF_CUDA(cudaStreamWaitEvent(st, ss->done2[par], 0));
+    }
     const float* kb = packed + (int64_t)i * kl.block_stride;
     float* dn = dparams ? dparams + (int64_t)i * pl.block_stride : nullptr;
     const float* xin = stash + sl.xs + (int64_t)i * BD;
@@ -643,10 +760,11 @@ int nf_flow_backward(const NfFlowDesc* desc, const float* params, const void* pa
       h.rstd = sb + sl.r2; h.rstd_net = sl.net_stride;
       h.mask = m2; h.mask_net = sl.net_stride; h.mw = sl.mw2;
       h.W3f = kb + kl.net0 + kl.W3f; h.w_net = kl.net_stride;
-      h.dxp = w.dxp; h.dout = w.dout; h.dout_net = B * m.dt;
-      h.du2 = w.gA; h.du2_net = B * Hm;
+      h.dxp = wb.dxp; h.dout = wb.dout; h.dout_net = B * m.dt;
+      h.du2 = wb.gA; h.du2_net = B * Hm;
       h.B = B; h.D = m.D; h.C = m.C;
       NF_TRY(row_bwd_head2(h, st));
+      if (ss) { NF_CUDA(cudaEventRecord(ss->evA, st)); NF_CUDA(cudaStreamWaitEvent(s1, ss->evA, 0)); }
     } else if (fused) {
       // a-d in one kernel: affine backward, last-Linear gradients, data gradient through the last
       // Linear and through LayerNorm + LeakyReLU of layer 2
@@ -656,7 +774,7 @@ int nf_flow_backward(const NfFlowDesc* desc, const float* params, const void* pa
       h.rstd = sb + sl.r2; h.rstd_net = sl.net_stride;
       h.mask = m2; h.mask_net = sl.net_stride; h.mw = sl.mw2;
       h.W3f = kb + kl.net0 + kl.W3f; h.w_net = kl.net_stride;
-      h.dxp = w.dxp; h.du2 = w.gA; h.du2_net = B * Hm;
+      h.dxp = wb.dxp; h.du2 = wb.gA; h.du2_net = B * Hm;
       h.G3 = dn ? dn + pl.slot_off[NF_P_W3] : nullptr;
       h.g3 = dn ? dn + pl.slot_off[NF_P_B3] : nullptr;
       h.gb2 = dn ? dn + pl.slot_off[NF_P_B2] : nullptr;
@@ -665,12 +783,12 @@ int nf_flow_backward(const NfFlowDesc* desc, const float* params, const void* pa
       NF_TRY(row_bwd_head(h, st));
     } else {
       // a. affine coupling backward: dout[0] = dt, dout[1] = ds
-      NF_TRY(affine_bwd(gcur, zi, si, dlogdet, B, m.D, w.dxp, w.dout + B * m.dt, w.dout,
+      NF_TRY(affine_bwd(gcur, zi, si, dlogdet, B, m.D, wb.dxp, wb.dout + B * m.dt, wb.dout,
                         dn ? dn + pl.net_stride + pl.slot_off[NF_P_B3] : nullptr,
                         dn ? dn + pl.slot_off[NF_P_B3] : nullptr, st));
       if (dn) {  // b. G3 = dout^T x_hat2  -> slot W3 (unfolded at the end)
         TcGemmTnP g;
-        g.A = w.dout; g.lda = m.dt; g.sA = B * m.dt;
+        g.A = wb.dout; g.lda = m.dt; g.sA = B * m.dt;
         g.B = sb + sl.xh2; g.ldb = m.C; g.sB = sl.net_stride;
         g.C = dn + pl.slot_off[NF_P_W3]; g.ldc = m.C; g.sC = pl.net_stride;
         g.M = m.dt; g.N = m.C; g.K = B; g.batch = 2;
@@ -678,15 +796,15 @@ int nf_flow_backward(const NfFlowDesc* desc, const float* params, const void* pa
       }
       {  // c. d x_hat2 = dout W3f
         GemmP g;
-        g.A0 = w.dout; g.lda0 = m.dt; g.sA0 = B * m.dt; g.K0 = m.dt;
+        g.A0 = wb.dout; g.lda0 = m.dt; g.sA0 = B * m.dt; g.K0 = m.dt;
         g.B0 = kb + kl.net0 + kl.W3f; g.ldb0 = m.C; g.sB0 = kl.net_stride;
-        g.C = w.gA; g.ldc = m.C; g.sC = B * Hm;
+        g.C = wb.gA; g.ldc = m.C; g.sC = B * Hm;
         g.M = (int)B; g.N = m.C; g.batch = 2;
         NF_TRY(simt_gemm(g, st));
       }
       {  // d. through LayerNorm + LeakyReLU (layer 2); column sums -> slot b2
         LnBwdP p{};
-        p.g = w.gA; p.g_net = B * Hm;
+        p.g = wb.gA; p.g_net = B * Hm;
         p.xh = sb + sl.xh2; p.xh_net = sl.net_stride;
         p.rstd = sb + sl.r2; p.rstd_net = sl.net_stride;
         p.mask = m2; p.mask_net = sl.net_stride; p.mw = sl.mw2;
@@ -697,18 +815,18 @@ int nf_flow_backward(const NfFlowDesc* desc, const float* params, const void* pa
     }
     if (dn) {  // e. G2 = du2^T x_hat1 -> slot W2
       TcGemmTnP g;
-      g.A = w.gA; g.lda = m.C; g.sA = B * Hm;
+      g.A = wb.gA; g.lda = m.C; g.sA = B * Hm;
       g.B = sb + sl.xh1; g.ldb = m.H1; g.sB = sl.net_stride;
       g.C = dn + pl.slot_off[NF_P_W2]; g.ldc = m.H1; g.sC = pl.net_stride;
       g.M = m.C; g.N = m.H1; g.K = B; g.batch = 2;
-      NF_TRY(wgrad_tn(m.prec, g, st));
+      NF_TRY(wgrad_tn(m.prec, g, s1));
     }
     bool ln1_fused = false;
     {  // f. d x_hat1 = du2 W2f   (K-major B operand = W2f^T)
       TcGemmP g;
-      g.A0 = w.gA; g.lda0 = m.C; g.sA0 = B * Hm; g.K0 = m.C;
+      g.A0 = wb.gA; g.lda0 = m.C; g.sA0 = B * Hm; g.K0 = m.C;
       g.B0 = kb + kl.net0 + kl.W2fT; g.ldb0 = m.C; g.sB0 = kl.net_stride;
-      g.C = w.gB; g.ldc = m.H1; g.sC = B * Hm;
+      g.C = wb.gB; g.ldc = m.H1; g.sC = B * Hm;
       g.M = (int)B; g.N = m.H1; g.batch = 2;
       if (v2 && m.prec == NF_PREC_TF32X3 && m.C >= 32) {
         // f + g in one kernel: LayerNorm-1 / LeakyReLU-1 backward as the GEMM's row-wise epilogue; the bias
@@ -728,7 +846,7 @@ int nf_flow_backward(const NfFlowDesc* desc, const float* params, const void* pa
     }
     if (!ln1_fused) {  // g. through LayerNorm + LeakyReLU (layer 1); column sums -> slot b1
       LnBwdP p{};
-      p.g = w.gB; p.g_net = B * Hm;
+      p.g = wb.gB; p.g_net = B * Hm;
       p.xh = sb + sl.xh1; p.xh_net = sl.net_stride;
       p.rstd = sb + sl.r1; p.rstd_net = sl.net_stride;
       p.mask = m1; p.mask_net = sl.net_stride; p.mw = sl.mw1;
@@ -736,9 +854,10 @@ int nf_flow_backward(const NfFlowDesc* desc, const float* params, const void* pa
       p.N = m.H1; p.nets = 2; p.B = B;
       NF_TRY(ln_lrelu_bwd(p, st));
     }
+    if (ss) { NF_CUDA(cudaEventRecord(ss->evB, st)); NF_CUDA(cudaStreamWaitEvent(s2, ss->evB, 0)); }
     if (dn) {  // h. dW1 = du1^T [x_cond | y]   (fused path: the x_cond columns come from the tail kernel)
       TcGemmTnP g;
-      g.A = w.gB; g.lda = m.H1; g.sA = B * Hm;
+      g.A = wb.gB; g.lda = m.H1; g.sA = B * Hm;
       g.B = zi; g.ldb = m.D; g.sB = 0;
       g.C = dn + pl.slot_off[NF_P_W1]; g.ldc = m.K1; g.sC = pl.net_stride;
       g.M = m.H1; g.N = m.dc; g.K = B; g.batch = 2;
@@ -746,66 +865,79 @@ int nf_flow_backward(const NfFlowDesc* desc, const float* params, const void* pa
       if (m.R > 0) {
         g.B = y; g.ldb = m.R;
         g.C = dn + pl.slot_off[NF_P_W1] + m.dc; g.N = m.R;
-        NF_TRY(wgrad_tn(m.prec, g, st));
+        NF_TRY(wgrad_tn(m.prec, g, s2));
       }
     }
     {  // i. d h0 = du1_t W1_t + du1_s W1_s : first dc columns -> dxp, the rest -> dy  (B operand = W1^T)
       TcGemmP g;
-      g.A0 = w.gB; g.lda0 = m.H1; g.K0 = m.H1;
-      g.A1 = w.gB + B * Hm; g.lda1 = m.H1; g.K1 = m.H1;
+      g.A0 = wb.gB; g.lda0 = m.H1; g.K0 = m.H1;
+      g.A1 = wb.gB + B * Hm; g.lda1 = m.H1; g.K1 = m.H1;
       g.B0 = kb + kl.net0 + kl.W1T; g.ldb0 = m.H1;
       g.B1 = g.B0 + kl.net_stride; g.ldb1 = m.H1;
-      g.C = w.dxp; g.ldc = m.D; g.M = (int)B; g.N = m.dc; g.accumulate = 1;
+      g.C = wb.dxp; g.ldc = m.D; g.M = (int)B; g.N = m.dc; g.accumulate = 1;
       if (!fused) NF_TRY(linear_nt(m.prec, g, st));
       if (dy && m.R > 0) {
         g.B0 += (int64_t)m.dc * m.H1; g.B1 += (int64_t)m.dc * m.H1;
         g.C = dy; g.ldc = m.R; g.N = m.R;
-        NF_TRY(linear_nt(m.prec, g, st));
+        NF_TRY(linear_nt(m.prec, g, s2));
       }
     }
     float* dst = (i > 0 || dx) ? ((i == 0) ? dx : (pp ? w.d1 : w.d0)) : nullptr;
     if (fused && v2) {
       // i (x_cond part) and k per row, then every reduction over the batch rows of this block in one launch
       BwdTail2P t{};
-      t.du1 = w.gB; t.du1_net = B * Hm;
+      t.du1 = wb.gB; t.du1_net = B * Hm;
       t.W1T = kb + kl.net0 + kl.W1T; t.w_net = kl.net_stride;
       t.W = kb + kl.W;
-      t.dxp = w.dxp; t.dxin = dst; t.ld_dxin = m.D;
+      t.dxp = wb.dxp; t.dxin = dst; t.ld_dxin = m.D;
       t.B = B; t.D = m.D; t.H1 = m.H1;
       NF_TRY(row_bwd_tail2(t, st));
       if (dn) {
         ColJob jobs[3];
         // G3 = dout^T x_hat2 (folded last Linear), gb2 = colsum(du2), g3 = colsum(dout)
         jobs[0].A = sb + sl.xh2; jobs[0].lda = m.C; jobs[0].sA = sl.net_stride; jobs[0].N = m.C;
-        jobs[0].coef = w.dout; jobs[0].ldcf = m.dt; jobs[0].sCf = B * m.dt; jobs[0].m = m.dt;
+        jobs[0].coef = wb.dout; jobs[0].ldcf = m.dt; jobs[0].sCf = B * m.dt; jobs[0].m = m.dt;
         jobs[0].out = dn + pl.slot_off[NF_P_W3]; jobs[0].so_i = m.C; jobs[0].so_c = 1; jobs[0].sOut = pl.net_stride;
-        jobs[0].A2 = w.gA; jobs[0].lda2 = m.C; jobs[0].sA2 = B * Hm;
+        jobs[0].A2 = wb.gA; jobs[0].lda2 = m.C; jobs[0].sA2 = B * Hm;
         jobs[0].out2 = dn + pl.slot_off[NF_P_B2]; jobs[0].sOut2 = pl.net_stride;
         jobs[0].out3 = dn + pl.slot_off[NF_P_B3]; jobs[0].sOut3 = pl.net_stride;
         jobs[0].batch = 2;
         // G1[:, :dc] = du1^T x_cond   (x_cond = z[:, :dc])
-        jobs[1].A = w.gB; jobs[1].lda = m.H1; jobs[1].sA = B * Hm; jobs[1].N = m.H1;
+        jobs[1].A = wb.gB; jobs[1].lda = m.H1; jobs[1].sA = B * Hm; jobs[1].N = m.H1;
         jobs[1].coef = zi; jobs[1].ldcf = m.D; jobs[1].sCf = 0; jobs[1].m = m.dc;
         jobs[1].out = dn + pl.slot_off[NF_P_W1]; jobs[1].so_i = 1; jobs[1].so_c = m.K1; jobs[1].sOut = pl.net_stride;
         if (ln1_fused) {   // gb1 = colsum(du1): same array as A, loaded once
-          jobs[1].A2 = w.gB; jobs[1].lda2 = m.H1; jobs[1].sA2 = B * Hm;
+          jobs[1].A2 = wb.gB; jobs[1].lda2 = m.H1; jobs[1].sA2 = B * Hm;
           jobs[1].out2 = dn + pl.slot_off[NF_P_B1]; jobs[1].sOut2 = pl.net_stride;
         }
         jobs[1].batch = 2;
         // dW = x_in^T dxp
-        jobs[2].A = w.dxp; jobs[2].lda = m.D; jobs[2].N = m.D;
+        jobs[2].A = wb.dxp; jobs[2].lda = m.D; jobs[2].N = m.D;
         jobs[2].coef = xin; jobs[2].ldcf = m.D; jobs[2].m = m.D;
         jobs[2].out = w.dWs + (int64_t)i * DD; jobs[2].so_i = m.D; jobs[2].so_c = 1;
         jobs[2].batch = 1;
-        NF_TRY(col_reduce(jobs, 3, B, st));
+        if (ss) {
+          NF_CUDA(cudaEventRecord(ss->evC, st));
+          NF_TRY(col_reduce(&jobs[0], 1, B, s1));
+          NF_CUDA(cudaStreamWaitEvent(s1, ss->evC, 0));   // dxp is final after the tail kernel
+          NF_TRY(col_reduce(&jobs[2], 1, B, s1));
+          NF_TRY(col_reduce(&jobs[1], 1, B, s2));
+        } else {
+          NF_TRY(col_reduce(jobs, 3, B, st));
+        }
+      }
+      if (ss) {
+        NF_CUDA(cudaEventRecord(ss->done1[par], s1));
+        NF_CUDA(cudaEventRecord(ss->done2[par], s2));
+        used1[par] = used2[par] = true;
       }
     } else if (fused) {
       // i (x_cond part), j, k in one kernel
       BwdTailP t{};
-      t.du1 = w.gB; t.du1_net = B * Hm;
+      t.du1 = wb.gB; t.du1_net = B * Hm;
       t.W1T = kb + kl.net0 + kl.W1T; t.w_net = kl.net_stride;
       t.z = zi; t.xin = xin; t.W = kb + kl.W;
-      t.dxp = w.dxp; t.dxin = dst; t.ld_dxin = m.D;
+      t.dxp = wb.dxp; t.dxin = dst; t.ld_dxin = m.D;
       t.G1 = dn ? dn + pl.slot_off[NF_P_W1] : nullptr; t.g_net = pl.net_stride; t.ldg = m.K1;
       t.dW = dn ? w.dWs + (int64_t)i * DD : nullptr;
       t.B = B; t.D = m.D; t.H1 = m.H1;
@@ -814,20 +946,26 @@ int nf_flow_backward(const NfFlowDesc* desc, const float* params, const void* pa
       if (dn) {  // j. dW = x_in^T dxp
         GemmP g;
         g.transA = 1; g.A0 = xin; g.lda0 = m.D; g.K0 = (int)B;
-        g.B0 = w.dxp; g.ldb0 = m.D;
+        g.B0 = wb.dxp; g.ldb0 = m.D;
         g.C = w.dWs + (int64_t)i * DD; g.ldc = m.D; g.M = m.D; g.N = m.D;
         g.splitk = pick_splitk(g.M, g.N, B, 1);
         NF_TRY(simt_gemm(g, st));
       }
       if (dst) {  // k. d x_in = dxp W^T
         GemmP g;
-        g.A0 = w.dxp; g.lda0 = m.D; g.K0 = m.D;
+        g.A0 = wb.dxp; g.lda0 = m.D; g.K0 = m.D;
         g.B0 = kb + kl.W; g.ldb0 = m.D; g.transB = 1;
         g.C = dst; g.ldc = m.D; g.M = (int)B; g.N = m.D;
         NF_TRY(simt_gemm(g, st));
       }
     }
     if (dst) { gcur = dst; pp ^= 1; }
+  }
+  if (ss) {   // join the side streams
+    for (int par = 0; par < 2; ++par) {
+      if (used1[par]) NF_CUDA(cudaStreamWaitEvent(st, ss->done1[par], 0));
+      if (used2[par]) NF_CUDA(cudaStreamWaitEvent(st, ss->done2[par], 0));
+    }
   }
   if (dparams) {
     GemmP g;  // T1 = P^T dW
@@ -850,7 +988,14 @@ int nf_flow_backward(const NfFlowDesc* desc, const float* params, const void* pa
   }
   return 0;
   };
-  return run_graphed(key, user_st, body);
+  NF_TRY(run_graphed(key, user_st, body));
+  {
+    CopySegs c;
+    c.add(dx_user, dx, BD);
+    c.add(dy_user, dy, B * m.R);
+    NF_TRY(copy_segments(c, user_st));
+  }
+  return 0;
 }
 
 int nf_linear(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, float* C, int64_t ldc,

@@ -85,6 +85,33 @@ class MetaBlock(nn.Module):
         self.s = _conditioner(k1, h1, channels, in_channels // 2, ln_eps)
 
 
+class _StashSlot:
+    """One persistent forward->backward stash buffer.  The library's launch graphs are keyed on the
+    buffers the kernels touch, so training keeps reusing the same few stashes instead of allocating a
+    fresh one per forward; a slot is busy from its forward until its backward ran (or its autograd
+    graph was dropped)."""
+    __slots__ = ("tensor", "busy", "__weakref__")
+
+    def __init__(self, tensor):
+        self.tensor = tensor
+        self.busy = False
+
+
+class _SlotGuard:
+    """Releases the slot when the autograd context that owns it goes away without a backward."""
+
+    def __init__(self, slot):
+        self.slot = slot
+
+    def release(self):
+        if self.slot is not None:
+            self.slot.busy = False
+            self.slot = None
+
+    def __del__(self):
+        self.release()
+
+
 class _Flow(torch.autograd.Function):
     """autograd bridge: forward = nf_flow_forward, backward = nf_flow_backward.
 
@@ -94,10 +121,11 @@ class _Flow(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, model: "RealNVP", fast: bool, x, y, *params):
-        z, logdet, outs, stash, packed = model._run_forward(x, y, True)
+        z, logdet, outs, stash, packed, slot = model._run_forward(x, y, True)
         ctx.model = model
         ctx.fast = fast
         ctx.stash = stash
+        ctx.guard = _SlotGuard(slot) if slot is not None else None
         ctx.packed = packed
         ctx.pver = model._params_version()
         ctx.B = x.shape[0]
@@ -128,6 +156,8 @@ class _Flow(torch.autograd.Function):
             else:
                 pg = (None,) * nparams
         ctx.stash = None
+        if ctx.guard is not None:
+            ctx.guard.release()      # the stash may be reused by the next forward
         return (None, None, dx, dy) + pg
 
 
@@ -174,6 +204,7 @@ class RealNVP(nn.Module):
         self._ws: Optional[torch.Tensor] = None
         self._gflat: Optional[torch.Tensor] = None
         self._gviews = None
+        self._stash_pool = {}
         self._dp_group = None
         self._dp_world = 1
         self._flatten()
@@ -232,6 +263,7 @@ class RealNVP(nn.Module):
         out = super()._apply(fn, recurse)
         self._flatten()
         self._ws = None
+        self._stash_pool = {}
         return out
 
     def _is_flat(self):
@@ -306,11 +338,11 @@ class RealNVP(nn.Module):
             ws = self._workspace(B, dev)
             z = torch.empty((B, D), dtype=torch.float32, device=dev)
             logdet = torch.empty((B,), dtype=torch.float32, device=dev)
-            stash = None
+            stash, slot = None, None
             if want_stash:
-                nbytes = lib.nf_flow_stash_bytes(ctypes.byref(self._desc), B)
-                stash = torch.empty(nbytes // 4, dtype=torch.float32, device=dev)
-                # outputs alias the block-input region of the stash: xs[1:], (n, B, D)
+                stash, slot = self._acquire_stash(B, dev)
+                # outputs alias the block-input region of the stash: xs[1:], (n, B, D); they stay valid until
+                # the backward of this forward has run (then the stash may be reused)
                 outs = stash[B * D:(n + 1) * B * D].view(n, B, D)
                 outs_ptr = None
             else:
@@ -320,7 +352,25 @@ class RealNVP(nn.Module):
                 ctypes.byref(self._desc), self._flat.data_ptr(), packed.data_ptr(), x.data_ptr(), y.data_ptr(), B,
                 z.data_ptr(), logdet.data_ptr(), outs_ptr, stash.data_ptr() if stash is not None else None,
                 ws.data_ptr(), ws.numel(), self._stream(dev)), "nf_flow_forward")
-        return z, logdet, outs, stash, packed
+        return z, logdet, outs, stash, packed, slot
+
+    _MAX_STASH_SLOTS = 4
+
+    def _acquire_stash(self, B, dev):
+        """A free persistent stash for batch size B (or a fresh, unpooled one when all are in flight)."""
+        pool = self._stash_pool.setdefault((B, dev), [])
+        for slot in pool:
+            if not slot.busy:
+                slot.busy = True
+                return slot.tensor, slot
+        nbytes = lib.nf_flow_stash_bytes(ctypes.byref(self._desc), B)
+        t = torch.empty(nbytes // 4, dtype=torch.float32, device=dev)
+        if len(pool) < self._MAX_STASH_SLOTS:
+            slot = _StashSlot(t)
+            slot.busy = True
+            pool.append(slot)
+            return t, slot
+        return t, None
 
     def _run_backward(self, stash, packed, y, B, dz, dld, need_x, need_y, need_p, out=None):
         dev = y.device
@@ -410,7 +460,7 @@ class RealNVP(nn.Module):
             else:
                 z, logdet, outs = _Flow.apply(self, False, x, y, *params)
         else:
-            z, logdet, outs, _, _ = self._run_forward(x, y, False)
+            z, logdet, outs, _, _, _ = self._run_forward(x, y, False)
         return z, list(outs.unbind(0)), logdet
 
     def reverse(self, x, y, return_sequence=False, return_logdet=False):
