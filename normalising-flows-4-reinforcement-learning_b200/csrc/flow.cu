@@ -298,19 +298,34 @@ static int conditioners(const Dims& m, const NfParamLayout& pl, const PackedLayo
                         const float* kb, const float* xc, int ldxc, const float* y, int64_t B, const FwdWs& w,
                         float* xh1, int64_t xh1_net, float* xh2, int64_t xh2_net, float* r1, float* r2,
                         int64_t r_net, uint32_t* m1, uint32_t* m2, int64_t m_net, int mw1, int mw2,
-                        bool with_last, cudaStream_t st) {
+                        bool with_last, cudaStream_t st, const TailP* tail = nullptr, bool* tail_done = nullptr,
+                        bool store_xh2 = true) {
   const int64_t Hm = std::max(m.H1, m.C);
   // Linear + LeakyReLU + LayerNorm as ONE tcgen05 kernel (row statistics exchanged across the CTA cluster
   // that spans the row) when the width allows it; otherwise GEMM -> u, then the row-wise kernel.
+  if (tail_done) *tail_done = false;
   auto linear_lrelu_ln = [&](TcGemmP g, int N, const float* bias, int64_t bias_net, float* xh, int64_t xh_net,
-                             float* r, uint32_t* mk, int mw) -> int {
+                             float* r, uint32_t* mk, int mw, const TailP* tl) -> int {
     g.M = (int)B; g.N = N; g.batch = 2;
     if (g.K0 + g.K1 >= 512) g.raw_hi = 0;
     TcGemmP f = g;
     f.C = xh; f.ldc = N; f.sC = xh_net; f.bias = bias; f.sBias = bias_net;
     f.epi.kind = TC_EPI_LN_FWD; f.epi.eps = m.eps;
     f.epi.rstd = r; f.epi.sRstd = r_net; f.epi.mask = mk; f.epi.sMask = m_net; f.epi.mw = mk ? mw : 0;
-    if (m.prec == NF_PREC_TF32X3 && (g.K0 + g.K1) >= 32 && tc_gemm_epi_supported(f)) return tc_gemm(f, st);
+    if (m.prec == NF_PREC_TF32X3 && (g.K0 + g.K1) >= 32 && tc_gemm_epi_supported(f)) {
+      if (tl && tc_gemm_tail_supported(f, tl->D)) {
+        // the whole rest of the block (last Linear, affine coupling, log-det, neighbouring PLU matmul) rides on
+        // this launch: the cluster holds both nets, its leader CTA finishes the rows
+        TcEpi::Tail& t = f.epi.tail;
+        t.on = 1; t.store_c = store_xh2 ? 1 : 0; t.D = tl->D; t.inverse = tl->inverse;
+        t.ld_in = tl->ld_in; t.ld_out = tl->ld_out; t.ld_out2 = tl->ld_out2;
+        t.W3f = tl->W3f; t.w_net = tl->w_net; t.b3f = tl->b3f; t.b_net = tl->b_net;
+        t.in = tl->in; t.cdev = tl->cdev; t.Wmat = tl->Wmat;
+        t.out = tl->out; t.out2 = tl->out2; t.logdet = tl->logdet; t.s_out = tl->s_out;
+        if (tail_done) *tail_done = true;
+      }
+      return tc_gemm(f, st);
+    }
     g.C = w.u; g.ldc = N; g.sC = B * Hm;
     NF_TRY(linear_nt(m.prec, g, st));
     LnFwdP p{};
@@ -329,13 +344,13 @@ static int conditioners(const Dims& m, const NfParamLayout& pl, const PackedLayo
     // W1p: W1 with the y columns moved to the 16-byte aligned column dcp (TMA operand)
     g.B0 = kb + kl.net0 + kl.W1p; g.ldb0 = kl.K1p; g.sB0 = kl.net_stride;
     if (m.R > 0) { g.B1 = g.B0 + kl.dcp; g.ldb1 = kl.K1p; g.sB1 = kl.net_stride; }
-    NF_TRY(linear_lrelu_ln(g, m.H1, pb + pl.slot_off[NF_P_B1], pl.net_stride, xh1, xh1_net, r1, m1, mw1));
+    NF_TRY(linear_lrelu_ln(g, m.H1, pb + pl.slot_off[NF_P_B1], pl.net_stride, xh1, xh1_net, r1, m1, mw1, nullptr));
   }
   {  // layer 2: x_hat1 W2f^T + b2f
     TcGemmP g;
     g.A0 = xh1; g.lda0 = m.H1; g.K0 = m.H1; g.sA0 = xh1_net;
     g.B0 = kb + kl.net0 + kl.W2f; g.ldb0 = m.H1; g.sB0 = kl.net_stride;
-    NF_TRY(linear_lrelu_ln(g, m.C, kb + kl.net0 + kl.b2f, kl.net_stride, xh2, xh2_net, r2, m2, mw2));
+    NF_TRY(linear_lrelu_ln(g, m.C, kb + kl.net0 + kl.b2f, kl.net_stride, xh2, xh2_net, r2, m2, mw2, tail));
   }
   if (with_last) {  // o = x_hat2 W3f^T  (N = D/2: FFMA unless the flow is wide)
     TcGemmP g;
@@ -525,27 +540,28 @@ int nf_flow_forward(const NfFlowDesc* desc, const float* params, const void* pac
       m1 = reinterpret_cast<uint32_t*>(sb + sl.m1); m2 = reinterpret_cast<uint32_t*>(sb + sl.m2);
       xh1_net = xh2_net = r_net = m_net = sl.net_stride;
     }
-    NF_TRY(conditioners(m, pl, kl, pb, kb, w.xp, w.Dp, y, B, w, xh1, xh1_net, xh2, xh2_net, r1, r2, r_net, m1, m2,
-                        m_net, sl.mw1, sl.mw2, !fused, st));
     float* next;
     if (stash) next = stash + sl.xs + (int64_t)(i + 1) * BD;
     else if (outputs) next = outputs + (int64_t)i * BD;
     else if (i == m.n - 1) next = z;
     else next = (i & 1) ? w.pp1 : w.pp0;   // dense (B,D): only the PLU matmul reads it
     float* s_out = stash ? stash + sl.ss + (int64_t)i * B * m.dt : nullptr;
+    TailP t{};
+    t.xh2 = xh2; t.xh2_net = xh2_net;
+    t.W3f = kb + kl.net0 + kl.W3f; t.w_net = kl.net_stride;
+    t.b3f = kb + kl.net0 + kl.b3f; t.b_net = kl.net_stride;
+    t.in = w.xp; t.ld_in = w.Dp;
+    t.cdev = packed + kl.logdet_c + i;
+    t.Wmat = (i + 1 < m.n) ? kb + kl.block_stride + kl.W : nullptr;   // next block's W
+    t.out = next; t.ld_out = m.D;
+    t.out2 = w.xp; t.ld_out2 = w.Dp;                                   // in place: a warp owns its row
+    t.logdet = logdet; t.s_out = s_out;
+    t.B = B; t.D = m.D; t.C = m.C; t.inverse = 0;
+    bool tail_done = false;
+    NF_TRY(conditioners(m, pl, kl, pb, kb, w.xp, w.Dp, y, B, w, xh1, xh1_net, xh2, xh2_net, r1, r2, r_net, m1, m2,
+                        m_net, sl.mw1, sl.mw2, !fused, st, fused ? &t : nullptr, &tail_done, stash != nullptr));
     if (fused) {
-      TailP t{};
-      t.xh2 = xh2; t.xh2_net = xh2_net;
-      t.W3f = kb + kl.net0 + kl.W3f; t.w_net = kl.net_stride;
-      t.b3f = kb + kl.net0 + kl.b3f; t.b_net = kl.net_stride;
-      t.in = w.xp; t.ld_in = w.Dp;
-      t.cdev = packed + kl.logdet_c + i;
-      t.Wmat = (i + 1 < m.n) ? kb + kl.block_stride + kl.W : nullptr;   // next block's W
-      t.out = next; t.ld_out = m.D;
-      t.out2 = w.xp; t.ld_out2 = w.Dp;                                   // in place: a warp owns its row
-      t.logdet = logdet; t.s_out = s_out;
-      t.B = B; t.D = m.D; t.C = m.C; t.inverse = 0;
-      NF_TRY(row_v2_supported(m.D, m.C, 4) ? row_tail2(t, st) : row_tail(t, st));
+      if (!tail_done) NF_TRY(row_v2_supported(m.D, m.C, 4) ? row_tail2(t, st) : row_tail(t, st));
     } else {
       NF_TRY(affine_fwd(w.xp, w.Dp, w.o + B * m.dt, w.o, kb + kl.net0 + kl.net_stride + kl.b3f,
                         kb + kl.net0 + kl.b3f, packed + kl.logdet_c + i, 0.f, B, m.D, next, m.D, logdet, s_out, st));
@@ -624,26 +640,27 @@ int nf_flow_inverse(const NfFlowDesc* desc, const float* params, const void* pac
   for (int i = m.n - 1; i >= 0; --i, ++step) {
     const float* pb = params + (int64_t)i * pl.block_stride;
     const float* kb = packed + (int64_t)i * kl.block_stride;
-    NF_TRY(conditioners(m, pl, kl, pb, kb, cur, ldcur, y, B, w, w.xh1, B * m.H1, w.xh2, B * m.C, nullptr, nullptr, 0,
-                        nullptr, nullptr, 0, 0, 0, !fused, st));
     float* next;
     int ldnext;
     if (i == 0 && !seq) { next = x; ldnext = m.D; }
     else if (seq && w.Dp == m.D) { next = seq + (int64_t)(step + 1) * BD; ldnext = m.D; }
     else { next = (step & 1) ? w.pp1 : w.pp0; ldnext = w.Dp; }
+    // affine first (torch_fcnf.py:112-113), then x = xp @ W^-1 (:115 -> :55)
+    TailP t{};
+    t.xh2 = w.xh2; t.xh2_net = B * m.C;
+    t.W3f = kb + kl.net0 + kl.W3f; t.w_net = kl.net_stride;
+    t.b3f = kb + kl.net0 + kl.b3f; t.b_net = kl.net_stride;
+    t.in = cur; t.ld_in = ldcur;
+    t.cdev = packed + kl.logdet_c + i;
+    t.Wmat = kb + kl.Winv;
+    t.out2 = next; t.ld_out2 = ldnext;
+    t.logdet = logdet;
+    t.B = B; t.D = m.D; t.C = m.C; t.inverse = 1;
+    bool tail_done = false;
+    NF_TRY(conditioners(m, pl, kl, pb, kb, cur, ldcur, y, B, w, w.xh1, B * m.H1, w.xh2, B * m.C, nullptr, nullptr, 0,
+                        nullptr, nullptr, 0, 0, 0, !fused, st, fused ? &t : nullptr, &tail_done, false));
     if (fused) {
-      // affine first (torch_fcnf.py:112-113), then x = xp @ W^-1 (:115 -> :55), one kernel
-      TailP t{};
-      t.xh2 = w.xh2; t.xh2_net = B * m.C;
-      t.W3f = kb + kl.net0 + kl.W3f; t.w_net = kl.net_stride;
-      t.b3f = kb + kl.net0 + kl.b3f; t.b_net = kl.net_stride;
-      t.in = cur; t.ld_in = ldcur;
-      t.cdev = packed + kl.logdet_c + i;
-      t.Wmat = kb + kl.Winv;
-      t.out2 = next; t.ld_out2 = ldnext;
-      t.logdet = logdet;
-      t.B = B; t.D = m.D; t.C = m.C; t.inverse = 1;
-      NF_TRY(row_v2_supported(m.D, m.C, 4) ? row_tail2(t, st) : row_tail(t, st));
+      if (!tail_done) NF_TRY(row_v2_supported(m.D, m.C, 4) ? row_tail2(t, st) : row_tail(t, st));
     } else {
       NF_TRY(affine_inv(cur, ldcur, w.o + B * m.dt, w.o, kb + kl.net0 + kl.net_stride + kl.b3f, kb + kl.net0 + kl.b3f,
                         packed + kl.logdet_c + i, 0.f, B, m.D, w.xp, w.Dp, logdet, st));

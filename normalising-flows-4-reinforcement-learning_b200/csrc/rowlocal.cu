@@ -282,7 +282,7 @@ int rows_per_warp_for(long long B) {
 // (zero-padded to MAXM so the FMA loop needs no predicates).  Loads of kColU rows are issued before
 // the first use.  History (ncu, C2a): one column per lane + one row per dependent load = 40 us; batched
 // loads = 31 us, instruction-bound (11 M warp instructions); this layout issues ~3x fewer.
-constexpr int kColU = 4;       // rows per warp and load batch
+constexpr int kColU = 4;       // rows per warp and load batch (8 rows / 64-row CTAs measured slower: twice the atomics)
 constexpr int kColSub = 128;   // rows per shared-memory coefficient sub-chunk
 constexpr int kColTile = 128;  // columns per CTA
 struct ColArgs {

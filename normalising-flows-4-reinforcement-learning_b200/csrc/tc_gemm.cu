@@ -47,6 +47,14 @@ struct KArgs {
   int ncl;                               // CTAs per cluster = N / BN (the cluster spans the whole row)
   long long* dbg;                        // optional: 8 clock64 timestamps per CTA (nf_debug_tc_timeline)
   int tma_store;                         // mC is valid: write the output tile with bulk tensor stores
+  // fused flow tail (EPI_LN_FWD on layer 2, D/2 <= 4, cluster (1, ncl, 2) = both nets): last Linear, affine
+  // coupling, log-det and the neighbouring PLU matmul finished by the cluster's leader CTA (rowfused.cuh TailP)
+  int tail, store_c;                     // store_c = 0: x_hat is not written (inference: nothing else reads it)
+  int t_D, t_inverse, t_ld_in, t_ld_out, t_ld_out2;
+  const float* t_W3f; long long t_w_net;
+  const float* t_b3f; long long t_b_net;
+  const float* t_in; const float* t_cdev; const float* t_Wmat;
+  float* t_out; float* t_out2; float* t_logdet; float* t_s_out;
 };
 constexpr int EPI_NONE = 0, EPI_LN_FWD = 1, EPI_LN_BWD = 2;
 constexpr int kMaxCluster = 8;
@@ -288,7 +296,8 @@ struct Smem {
   static constexpr int BARS = STAGES * STAGE;      // byte offset of the barrier block
   static constexpr int XCHG = BARS + 512;          // [kMaxCluster][128] float2 partial row statistics (epilogue kernels)
   static constexpr int TOTAL = BARS + 512 + 1024;  // + alignment slack
-  static constexpr int TOTAL_EPI = XCHG + 8 * 128 * 8 + 1024;
+  static constexpr int TPART = XCHG + 8 * 128 * 8;                 // [8 ranks][128] float4 partial last-Linear outputs (leader CTA)
+  static constexpr int TOTAL_EPI = TPART + 8 * 128 * 16 + 1024;
 };
 
 template <int BN, int STAGES, bool MNMAJOR, int BK, int EPI = EPI_NONE>
@@ -307,7 +316,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
   uint64_t* empty = bars + 2 * STAGES;
   uint64_t* accbar = bars + 3 * STAGES;
   uint64_t* xbar = bars + 3 * STAGES + 1;      // cluster exchange barrier (epilogue kernels)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 2);
+  uint64_t* tbar = bars + 3 * STAGES + 2;      // fused tail: partials have arrived at the leader CTA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 3);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
@@ -355,6 +365,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&split[s], 4); mbar_init(&empty[s], 1); }
     mbar_init(accbar, 1);
     if (EPI != EPI_NONE) mbar_init(xbar, (uint32_t)a.ncl * 128u);
+    if (EPI == EPI_LN_FWD) mbar_init(tbar, 2u * (uint32_t)a.ncl * 128u);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -530,8 +541,11 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
       }
       if (threadIdx.x == 64) NF_TS(5);   // row in registers
       float2* xchg = reinterpret_cast<float2*>(smem + S::XCHG);   // [rank][row in tile]
-      const uint32_t my_rank = cluster_ctarank();
       const int ncl = a.ncl;
+      // cluster (1, ncl, 1): rank = N tile; with the fused tail (1, ncl, 2): rank = N tile + ncl * net, and the
+      // LayerNorm exchange stays inside the net's ncl CTAs
+      const uint32_t rank_base = (EPI == EPI_LN_FWD && a.tail) ? (uint32_t)z * (uint32_t)ncl : 0u;
+      const uint32_t my_rank = cluster_ctarank() - rank_base;
       float* sxh = reinterpret_cast<float*>(smem) + q * (32 * (BN + 4));              // bwd: this warp's x_hat tile
       float* sx = reinterpret_cast<float*>(smem) + 4 * 32 * (BN + 4) + q * kXWarpFloats;   // 32 x 32 transposition buffer
       float* cwarp = a.C + (long long)z * a.sC + (long long)(m0 + q * 32) * a.ldc + n0;
@@ -582,8 +596,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
       const uint32_t slot = smem_u32(&xchg[my_rank * 128 + rit]);
       const uint32_t xb = smem_u32(xbar);
       for (int pr = 0; pr < ncl; ++pr) {
-        st_cluster_v2(mapa_u32(slot, (uint32_t)pr), p0, p1);
-        mbar_arrive_remote(mapa_u32(xb, (uint32_t)pr));
+        st_cluster_v2(mapa_u32(slot, rank_base + (uint32_t)pr), p0, p1);
+        mbar_arrive_remote(mapa_u32(xb, rank_base + (uint32_t)pr));
       }
       mbar_wait_cluster(xbar, 0);
       if (threadIdx.x == 64) NF_TS(6);   // statistics exchanged
@@ -600,11 +614,37 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
           m2 += s.y + (float)BN * d * d;
         }
         const float rstd = rsqrtf(m2 / (float)(ncl * BN) + a.eps);
+        // fused tail: this CTA's slice of the folded last Linear, W3f[net][i][n0 .. n0 + BN), in shared memory
+        const int dt = a.t_D >> 1;
+        float* sW3 = reinterpret_cast<float*>(smem + 160 * 1024);          // [4][BN]
+        float* sWm = sW3 + 4 * BN;                                          // [D][D] (leader)
+        float part[4] = {0.f, 0.f, 0.f, 0.f};
+        if (a.tail) {
+          const int te = threadIdx.x - 64;
+          for (int idx = te; idx < 4 * BN; idx += 128) {
+            const int i = idx / BN, c = idx - i * BN;
+            sW3[idx] = i < dt ? __ldg(a.t_W3f + (long long)z * a.t_w_net + (long long)i * a.N + n0 + c) : 0.f;
+          }
+          if (cluster_ctarank() == 0 && a.t_Wmat)
+            for (int idx = te; idx < a.t_D * a.t_D; idx += 128) sWm[idx] = __ldg(a.t_Wmat + idx);
+          asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps
+        }
 #pragma unroll
         for (int c0 = 0; c0 < BN; c0 += 32) {
           float o[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) o[j] = (v[c0 + j] - mean) * rstd;
+          if (a.tail) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 w4 = *reinterpret_cast<const float4*>(sW3 + i * BN + c0 + j);
+                part[i] = fmaf(o[j], w4.x, fmaf(o[j + 1], w4.y, fmaf(o[j + 2], w4.z, fmaf(o[j + 3], w4.w, part[i]))));
+              }
+            }
+          }
+          if (!a.store_c) continue;
           if (a.tma_store) {
             uint8_t* box = boxes + (c0 >> 5) * 4096;
             box_put(box, lane, o);
@@ -630,6 +670,72 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
             for (int w = 0; w < BN / 32; ++w) mk[w] = mbits[w];
           }
           if (a.rstd && my_rank == 0) a.rstd[(long long)z * a.sRstd + row] = rstd;
+        }
+        if (a.tail) {
+          // partial last-Linear outputs of this CTA's columns -> the cluster's leader CTA (rank 0)
+          float4* tpart = reinterpret_cast<float4*>(smem + S::TPART);     // [rank][row in tile]
+          const uint32_t crank = cluster_ctarank();
+          const uint32_t dst = mapa_u32(smem_u32(&tpart[crank * 128 + rit]), 0u);
+          asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(part[0]), "f"(part[1]),
+                       "f"(part[2]), "f"(part[3]) : "memory");
+          mbar_arrive_remote(mapa_u32(smem_u32(tbar), 0u));
+          if (crank == 0) {
+            mbar_wait_cluster(tbar, 0);
+            // t = net 0 (ranks 0 .. ncl-1), s = net 1 (ranks ncl .. 2 ncl - 1)     (torch_fcnf.py:99-104 / :110-115)
+            float tv[4] = {0.f, 0.f, 0.f, 0.f}, sv[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int pr = 0; pr < ncl; ++pr) {
+              const float4 pt = tpart[pr * 128 + rit], ps = tpart[(ncl + pr) * 128 + rit];
+              tv[0] += pt.x; tv[1] += pt.y; tv[2] += pt.z; tv[3] += pt.w;
+              sv[0] += ps.x; sv[1] += ps.y; sv[2] += ps.z; sv[3] += ps.w;
+            }
+            if (rowok) {
+              const int D = a.t_D, dc = (D + 1) >> 1;
+              constexpr int MAXD = 9;
+              float xin[MAXD], zv[MAXD];
+#pragma unroll
+              for (int j = 0; j < MAXD; ++j) xin[j] = j < D ? a.t_in[(long long)row * a.t_ld_in + j] : 0.f;
+              float ssum = 0.f;
+#pragma unroll
+              for (int j = 0; j < MAXD; ++j) zv[j] = xin[j];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                if (i < dt) {
+                  const float tt = tv[i] + a.t_b3f[i], ss = sv[i] + a.t_b3f[a.t_b_net + i];
+                  sv[i] = ss;
+                  ssum += ss;
+#pragma unroll
+                  for (int j = 0; j < MAXD; ++j)
+                    if (j == dc + i) zv[j] = a.t_inverse ? fmaf(xin[j], expf(ss), tt) : (xin[j] - tt) * expf(-ss);
+                }
+              }
+              if (!a.t_inverse) {
+#pragma unroll
+                for (int j = 0; j < MAXD; ++j)
+                  if (j < D) a.t_out[(long long)row * a.t_ld_out + j] = zv[j];
+                if (a.t_s_out) {
+#pragma unroll
+                  for (int i = 0; i < 4; ++i)
+                    if (i < dt) a.t_s_out[(long long)row * dt + i] = sv[i];
+                }
+              }
+              if (a.t_logdet) {
+                const float cst = a.t_cdev ? *a.t_cdev : 0.f;
+                a.t_logdet[row] += a.t_inverse ? (ssum - cst) : (cst - ssum);
+              }
+              if (a.t_Wmat) {
+#pragma unroll
+                for (int j = 0; j < MAXD; ++j) {
+                  if (j < D) {
+                    float o2 = 0.f;
+#pragma unroll
+                    for (int k = 0; k < MAXD; ++k)
+                      if (k < D) o2 = fmaf(zv[k], sWm[k * D + j], o2);
+                    a.t_out2[(long long)row * a.t_ld_out2 + j] = o2;
+                  }
+                }
+              }
+            }
+          }
         }
       } else {
         float s1 = 0.f, s2 = 0.f;
@@ -900,6 +1006,13 @@ int launch_epi(const TcGemmP& p, cudaStream_t st) {
   a.rstd = p.epi.rstd; a.sRstd = p.epi.sRstd; a.mask = p.epi.mask; a.sMask = p.epi.sMask; a.mw = p.epi.mw;
   a.xh = p.epi.xh; a.ldxh = p.epi.ldxh; a.sXh = p.epi.sXh; a.eps = p.epi.eps;
   a.ncl = p.N / BN;
+  const TcEpi::Tail& t = p.epi.tail;
+  a.tail = (EPI == EPI_LN_FWD && t.on) ? 1 : 0;
+  a.store_c = a.tail ? t.store_c : 1;
+  a.t_D = t.D; a.t_inverse = t.inverse; a.t_ld_in = t.ld_in; a.t_ld_out = t.ld_out; a.t_ld_out2 = t.ld_out2;
+  a.t_W3f = t.W3f; a.t_w_net = t.w_net; a.t_b3f = t.b3f; a.t_b_net = t.b_net;
+  a.t_in = t.in; a.t_cdev = t.cdev; a.t_Wmat = t.Wmat;
+  a.t_out = t.out; a.t_out2 = t.out2; a.t_logdet = t.logdet; a.t_s_out = t.s_out;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)cdiv(p.M, BM), (unsigned)a.ncl, (unsigned)p.batch);
   cfg.blockDim = dim3(NTHREADS);
@@ -907,7 +1020,7 @@ int launch_epi(const TcGemmP& p, cudaStream_t st) {
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = (unsigned)a.ncl; attr[0].val.clusterDim.z = 1;
+  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = (unsigned)a.ncl; attr[0].val.clusterDim.z = a.tail ? 2u : 1u;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
@@ -996,6 +1109,16 @@ bool tc_gemm_epi_supported(const TcGemmP& p) {
     return p.epi.xh && p.epi.rstd && p.epi.mask && (p.epi.ldxh & 3) == 0 && (p.epi.sXh & 3) == 0 &&
            (reinterpret_cast<uintptr_t>(p.epi.xh) & 15u) == 0 && p.epi.mw * 32 >= p.N;
   return false;
+}
+
+bool tc_gemm_tail_supported(const TcGemmP& p, int D) {
+  // Off by default: measured on C2a (B = 4096) the fused kernel saves the 6 tail launches of a forward pass
+  // but not time (0.227 vs 0.221 ms): with graph replay + PDL a launch costs little, and the leader CTA's
+  // serial finish is no faster than 512 CTAs of k_row_tail2.  NF_B200_FUSED_TAIL=1 turns it on.
+  static const bool on = [] { const char* e = getenv("NF_B200_FUSED_TAIL"); return e && e[0] == '1'; }();
+  if (!on || p.epi.kind != TC_EPI_LN_FWD || p.batch != 2 || D < 2 || D > 9 || !tc_gemm_epi_supported(p)) return false;
+  const int bn = (p.N % 128 == 0 && p.N / 128 <= kMaxCluster) ? 128 : 64;
+  return 2 * (p.N / bn) <= kMaxCluster;
 }
 
 int tc_gemm(const TcGemmP& p, cudaStream_t st) {

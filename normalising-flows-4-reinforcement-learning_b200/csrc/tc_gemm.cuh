@@ -20,6 +20,15 @@ struct TcEpi {
   uint32_t* mask = nullptr; long long sMask = 0; int mw = 0;
   const float* xh = nullptr; long long ldxh = 0, sXh = 0;
   float eps = 1e-5f;
+  // TC_EPI_LN_FWD only: finish the flow block inside the same kernel (see tc_gemm_tail_supported).  Same
+  // contract as TailP / row_tail2 (rowfused.cuh); store_c = 0 skips writing C (x_hat) altogether.
+  struct Tail {
+    int on = 0, store_c = 1, D = 0, inverse = 0, ld_in = 0, ld_out = 0, ld_out2 = 0;
+    const float* W3f = nullptr; long long w_net = 0;
+    const float* b3f = nullptr; long long b_net = 0;
+    const float* in = nullptr; const float* cdev = nullptr; const float* Wmat = nullptr;
+    float* out = nullptr; float* out2 = nullptr; float* logdet = nullptr; float* s_out = nullptr;
+  } tail;
 };
 
 struct TcGemmP {
@@ -63,5 +72,7 @@ int tc_gemm(const TcGemmP& p, cudaStream_t st);
 bool tc_gemm_supported(const TcGemmP& p);
 // the fused epilogues need N = ncl * BN with BN in {64, 128} and ncl <= 8 (one cluster per 128-row tile)
 bool tc_gemm_epi_supported(const TcGemmP& p);
+// fused tail: both nets in one cluster (batch == 2, 2 * N / BN <= 8 CTAs) and D / 2 <= 4
+bool tc_gemm_tail_supported(const TcGemmP& p, int D);
 
 }  // namespace nf
