@@ -178,6 +178,14 @@ NF_API int nf_graphs_enable(int on);
 NF_API int nf_graphs_clear(void);
 NF_API int nf_graphs_stats(int64_t* replays, int64_t* captures, int64_t* eager);
 
+/* Run-time options, by name (also NF_B200_<NAME> in the environment, read once): "pdl" (programmatic dependent
+ * launch, 1), "streams" (backward on three streams, 1), "tma_store" (bulk-tensor-store epilogues, 1), "nacc" (main
+ * accumulators in rotation, 0 = 3), "fused_ln" (LayerNorm in the GEMM epilogue: -1 auto / 0 / 1), "fused_tail"
+ * (flow tail in the layer-2 GEMM, 0), "bn256" (256-wide tiles: 0 auto / 1 / 2 never).  Every setting computes the
+ * same function (tests/test_flow_gpu.py::test_options_are_equivalent); setting one clears the launch graphs. */
+NF_API int nf_set_option(const char* name, int value);
+NF_API int nf_get_option(const char* name);
+
 /* Number of kernels this library launched on the calling thread since the last reset
  * (bench.py's gpu_launches). */
 NF_API int64_t nf_launch_count(int reset);

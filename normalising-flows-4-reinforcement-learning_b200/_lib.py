@@ -62,6 +62,8 @@ def _load():
         "nf_prof_enable": (c_int, [c_int]),
         "nf_prof_collect": (c_int, [POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(c_int64), c_int]),
         "nf_launch_count": (c_int64, [c_int]),
+        "nf_set_option": (c_int, [c_char_p, c_int]),
+        "nf_get_option": (c_int, [c_char_p]),
         "nf_graphs_enable": (c_int, [c_int]),
         "nf_graphs_clear": (c_int, []),
         "nf_graphs_stats": (c_int, [POINTER(c_int64), POINTER(c_int64), POINTER(c_int64)]),
@@ -90,6 +92,14 @@ def param_layout(desc: NfFlowDesc) -> NfParamLayout:
     out = NfParamLayout()
     check(lib.nf_param_layout(ctypes.byref(desc), ctypes.byref(out)), "nf_param_layout")
     return out
+
+
+def set_option(name: str, value: int):
+    check(lib.nf_set_option(name.encode(), int(value)), "nf_set_option")
+
+
+def get_option(name: str) -> int:
+    return lib.nf_get_option(name.encode())
 
 
 def graph_stats():

@@ -36,6 +36,19 @@ int64_t& launch_counter();
     NF_CUDA(cudaPeekAtLastError());      \
   } while (0)
 
+// ---- run-time options (nf_set_option / NF_B200_<NAME> environment variables) ------------------------------
+enum NfOpt {
+  NF_OPT_PDL = 0,        // programmatic dependent launch on every kernel                       (default 1)
+  NF_OPT_STREAMS,        // backward on three streams                                           (default 1)
+  NF_OPT_TMA_STORE,      // GEMM epilogues write through bulk tensor stores                     (default 1)
+  NF_OPT_NACC,           // main accumulators in rotation, 0 = kernel default (3)               (default 0)
+  NF_OPT_FUSED_LN,       // LayerNorm fused into the GEMM epilogue: -1 auto, 0 never, 1 always  (default -1)
+  NF_OPT_FUSED_TAIL,     // flow tail fused into the layer-2 GEMM                               (default 0)
+  NF_OPT_BN256,          // 256-wide GEMM tiles: 0 auto (K <= 256), 1 always, 2 never           (default 0)
+  NF_OPT_COUNT
+};
+int option(int id);
+
 // ---- programmatic dependent launch (PDL) -------------------------------------------------------
 // Every kernel of the library is launched with cudaLaunchAttributeProgrammaticStreamSerialization and
 // starts with NF_PDL_ENTRY(): it blocks until the kernel before it in the stream has completed and
@@ -50,7 +63,7 @@ int64_t& launch_counter();
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); \
   } while (0)
 
-bool pdl_enabled();
+inline bool pdl_enabled() { return option(NF_OPT_PDL) != 0; }
 template <class... KArgs, class... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                               Args&&... args) {

@@ -29,9 +29,28 @@ int set_err(int code, const char* fmt, ...) {
   return code;
 }
 
-bool pdl_enabled() {
-  static const bool on = [] { const char* e = getenv("NF_B200_PDL"); return !(e && e[0] == '0'); }();
-  return on;
+namespace {
+struct OptDef { const char* name; const char* env; int def; };
+const OptDef kOpts[NF_OPT_COUNT] = {
+    {"pdl", "NF_B200_PDL", 1},           {"streams", "NF_B200_STREAMS", 1},       {"tma_store", "NF_B200_TMA_STORE", 1},
+    {"nacc", "NF_B200_NACC", 0},         {"fused_ln", "NF_B200_FUSED_LN", -1},    {"fused_tail", "NF_B200_FUSED_TAIL", 0},
+    {"bn256", "NF_B200_BN256", 0},
+};
+int g_opt[NF_OPT_COUNT];
+bool g_opt_init = false;
+void opt_init() {
+  if (g_opt_init) return;
+  for (int i = 0; i < NF_OPT_COUNT; ++i) {
+    const char* e = getenv(kOpts[i].env);
+    g_opt[i] = e ? atoi(e) : kOpts[i].def;
+  }
+  g_opt_init = true;
+}
+}  // namespace
+
+int option(int id) {
+  opt_init();
+  return (id >= 0 && id < NF_OPT_COUNT) ? g_opt[id] : 0;
 }
 
 int check_desc(const NfFlowDesc* d) {
@@ -207,9 +226,8 @@ struct SideStreams {
 };
 static SideStreams* side_streams() {
   static SideStreams per_dev[64];
-  static const bool on = [] { const char* e = getenv("NF_B200_STREAMS"); return !(e && e[0] == '0'); }();
   int dev = 0;
-  if (!on || cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (!option(NF_OPT_STREAMS) || cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
   SideStreams& s = per_dev[dev];
   if (!s.ok) {
     bool good = cudaStreamCreateWithFlags(&s.s1, cudaStreamNonBlocking) == cudaSuccess &&
@@ -373,6 +391,25 @@ using namespace nf;
 extern "C" {
 
 int nf_abi_version(void) { return NF_ABI_VERSION; }
+
+int nf_set_option(const char* name, int value) {
+  NF_CHECK_ARG(name != nullptr, NF_E_BADARG, "option name is NULL");
+  opt_init();
+  for (int i = 0; i < NF_OPT_COUNT; ++i) {
+    if (strcmp(name, kOpts[i].name) == 0) {
+      g_opt[i] = value;
+      return nf_graphs_clear();   // cached launch graphs embed the old choice
+    }
+  }
+  return set_err(NF_E_BADARG, "unknown option '%s'", name);
+}
+
+int nf_get_option(const char* name) {
+  opt_init();
+  for (int i = 0; name && i < NF_OPT_COUNT; ++i)
+    if (strcmp(name, kOpts[i].name) == 0) return g_opt[i];
+  return -9999;
+}
 const char* nf_last_error(void) { return err_buf(); }
 int64_t nf_launch_count(int reset) {
   int64_t v = launch_counter();

@@ -899,8 +899,7 @@ int make_map(CUtensorMap* map, const float* base, long long inner, long long row
 // output tensor map for the TMA-store epilogue: 32 x 32 fp32 boxes, SWIZZLE_128B; returns false when TMA cannot
 // address C (the direct-store epilogue is used then)
 bool make_c_map(CUtensorMap* map, float* C, long long N, long long M, long long ldc, long long batch, long long sC) {
-  static const bool on = [] { const char* e = getenv("NF_B200_TMA_STORE"); return !(e && e[0] == '0'); }();
-  if (!on || !C || (reinterpret_cast<uintptr_t>(C) & 15u) != 0 || (ldc & 3) != 0 || (sC & 3) != 0) return false;
+  if (!option(NF_OPT_TMA_STORE) || !C || (reinterpret_cast<uintptr_t>(C) & 15u) != 0 || (ldc & 3) != 0 || (sC & 3) != 0) return false;
   return make_map(map, C, N, M, ldc, batch, sC, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B) == 0;
 }
 
@@ -923,9 +922,8 @@ int set_smem() {
 // 12 k8 steps (K <= 96) keep the cross terms in the main accumulator (3 truncations per step, still < 40)
 constexpr int kMergeCorrK8 = 12;
 int pick_nacc(int total_k8) {
-  static const int forced = [] { const char* e = getenv("NF_B200_NACC"); return e ? atoi(e) : 0; }();
   (void)total_k8;
-  return forced;   // 0 = kernel default (all NACC accumulators)
+  return option(NF_OPT_NACC);   // 0 = kernel default (all NACC accumulators)
 }
 
 template <int BN, int STAGES, int BK>
@@ -1097,7 +1095,7 @@ bool tc_gemm_epi_supported(const TcGemmP& p) {
   // One output tile per CTA: the row-wise epilogue is not overlapped with another tile's MMAs, so it only
   // pays while the launch is latency-bound (at most ~2 waves of CTAs); measured on C3/C4/C5 at B >= 8192 the
   // separate row kernel is 15-35 % faster, on C2a (B = 4096) the fused one wins.
-  static const int force = [] { const char* e = getenv("NF_B200_FUSED_LN"); return e ? atoi(e) : -1; }();
+  const int force = option(NF_OPT_FUSED_LN);
   if (force == 0) return false;
   if (force != 1 && cdiv(p.M, BM) * cdiv(p.N, 128) * p.batch > 2 * 148) return false;
   const bool n128 = p.N % 128 == 0 && p.N / 128 <= kMaxCluster;
@@ -1115,8 +1113,7 @@ bool tc_gemm_tail_supported(const TcGemmP& p, int D) {
   // Off by default: measured on C2a (B = 4096) the fused kernel saves the 6 tail launches of a forward pass
   // but not time (0.227 vs 0.221 ms): with graph replay + PDL a launch costs little, and the leader CTA's
   // serial finish is no faster than 512 CTAs of k_row_tail2.  NF_B200_FUSED_TAIL=1 turns it on.
-  static const bool on = [] { const char* e = getenv("NF_B200_FUSED_TAIL"); return e && e[0] == '1'; }();
-  if (!on || p.epi.kind != TC_EPI_LN_FWD || p.batch != 2 || D < 2 || D > 9 || !tc_gemm_epi_supported(p)) return false;
+  if (option(NF_OPT_FUSED_TAIL) != 1 || p.epi.kind != TC_EPI_LN_FWD || p.batch != 2 || D < 2 || D > 9 || !tc_gemm_epi_supported(p)) return false;
   const int bn = (p.N % 128 == 0 && p.N / 128 <= kMaxCluster) ? 128 : 64;
   return 2 * (p.N / bn) <= kMaxCluster;
 }
@@ -1132,7 +1129,7 @@ int tc_gemm(const TcGemmP& p, cudaStream_t st) {
   // small problems: prefer more, smaller CTAs (3 pipeline stages) over filling TMEM
   // BN = 256 fills TMEM with one main + one corr accumulator; BN <= 128 leaves room for the three rotating
   // main accumulators that keep long reductions inside fp32 parity, so 256 is only used while one accumulator is enough (K <= 256, pick_nacc).
-  static const int wide_ok = [] { const char* e = getenv("NF_B200_BN256"); return e ? atoi(e) : 0; }();
+  const int wide_ok = option(NF_OPT_BN256);
   const long long ctas256 = (wide_ok == 1 || (wide_ok == 0 && p.K0 + p.K1 <= 256))
                                 ? cdiv(p.M, BM) * cdiv(p.N, 256) * p.batch : 0;
   if (p.bk == 32) {
@@ -1155,7 +1152,7 @@ int tc_gemm_tn(const TcGemmTnP& p, cudaStream_t st) {
   if (p.M <= 0 || p.N <= 0 || p.batch <= 0 || p.K <= 0) return 0;
   NF_CHECK_ARG(tc_gemm_tn_supported(p), NF_E_UNSUPPORTED,
                "tc_gemm_tn: operands must be 16-byte aligned with row pitches that are multiples of 4 floats");
-  static const int wide_ok = [] { const char* e = getenv("NF_B200_BN256"); return e ? atoi(e) : 0; }();
+  const int wide_ok = option(NF_OPT_BN256);
   if (wide_ok != 1) {
     if (p.bk == 32) return p.N > 64 ? launch_tn<128, 3, 32>(p, st) : launch_tn<64, 4, 32>(p, st);
     return p.N > 64 ? launch_tn<128, 6, 16>(p, st) : launch_tn<64, 8, 16>(p, st);

@@ -370,3 +370,48 @@ def test_launch_graph_replay_is_bit_identical(precision):
             _lib.lib.nf_graphs_enable(1)
     assert not torch.equal(z2, outs[0][0])
     assert torch.equal(z2, z3) and torch.equal(ld2, ld3)
+
+
+OPTION_SETTINGS = [("pdl", 0), ("streams", 0), ("tma_store", 0), ("fused_ln", 0), ("fused_ln", 1), ("fused_tail", 1),
+                   ("nacc", 1), ("bn256", 2), ("bn256", 1)]
+
+
+@pytest.mark.parametrize("name,value", OPTION_SETTINGS, ids=[f"{n}={v}" for n, v in OPTION_SETTINGS])
+def test_options_are_equivalent(name, value):
+    """Every execution option (PDL, side streams, TMA-store epilogue, fused LayerNorm / tail epilogues,
+    accumulator rotation, tile width) computes the same function: forward, inverse and all gradients agree
+    with the default configuration to fp32 rounding, eagerly and through the replayed launch graph."""
+    D, C, R, n, B = 8, 256, 64, 2, 300
+    sd = synth.make_state_dict(D, C, R, n, seed=41)
+    x, y, _ = synth.make_safe_inputs(sd, n, B, D, R, seed=42)
+    dz, dld = synth.make_cotangents(B, D, seed=43)
+
+    def run():
+        model = build_model(dict(D=D, C=C, R=R, n=n, B=B), sd, "fp32")
+        outs = None
+        for _ in range(3):          # eager, capture, replay
+            model.zero_grad(set_to_none=True)
+            xt, yt = t(x).requires_grad_(True), t(y).requires_grad_(True)
+            z, _, ld = model(xt, yt)
+            (z * t(dz)).sum().add((ld * t(dld)).sum()).backward()
+            with torch.no_grad():
+                xr = model.reverse(z.detach(), t(y))
+            g = torch.cat([p.grad.reshape(-1) for p in model.parameters() if p.requires_grad])
+            cur = [v.detach().cpu().numpy().copy() for v in (z, ld, xt.grad, yt.grad, g, xr)]
+            if outs is not None:
+                for a, b, nm in zip(outs, cur, ("z", "ld", "dx", "dy", "dparams", "rev")):
+                    assert rel_err(b, a) <= 2e-6, ("replay differs from the eager run", nm)
+            outs = cur
+        return outs
+
+    default = _lib.get_option(name)
+    ref = run()
+    _lib.set_option(name, value)
+    try:
+        assert _lib.get_option(name) == value
+        got = run()
+    finally:
+        _lib.set_option(name, default)
+    tol = 1e-5 if name == "nacc" else 3e-6   # one accumulator instead of three: the truncation noise itself changes
+    for a, b, nm in zip(ref, got, ("z", "ld", "dx", "dy", "dparams", "rev")):
+        assert rel_err(b, a) <= tol, (name, value, nm, rel_err(b, a))
