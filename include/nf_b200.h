@@ -161,6 +161,18 @@ NF_API int nf_linear(const float* A, int64_t lda, const float* W, int64_t ldw, c
 NF_API int nf_linear_wgrad(const float* dY, int64_t lddy, const float* X, int64_t ldx, float* dW, int64_t lddw,
                            int64_t B, int32_t n_out, int32_t n_in, int32_t engine, void* stream);
 
+/* The steps either side of the flow in the reference's training loop:
+ *   nf_nll_forward    loss[0] = -mean_b(-0.5 |z_b|^2 - D/2 log 2 pi + logdet_b)   (torch_nfbc_ant.py:269, N(0, I) prior)
+ *   nf_nll_cotangents dz = g z / B, dlogdet = -g / B  with the upstream gradient g[0] (g may be NULL = 1)
+ *   nf_adamw_step     one torch.optim.AdamW step (torch_nfbc_ant.py:150-155) over the flat parameter arena in one
+ *                     launch; exp_avg / exp_avg_sq are arenas of the same layout, slot_mask (n_blocks * NF_P_SLOTS
+ *                     bytes on the device, 1 = update) leaves P / P_inv and frozen parameters alone; step >= 1. */
+NF_API int nf_nll_forward(const float* z, const float* logdet, int64_t B, int32_t D, float* loss, void* stream);
+NF_API int nf_nll_cotangents(const float* z, const float* g, int64_t B, int32_t D, float* dz, float* dld, void* stream);
+NF_API int nf_adamw_step(const NfFlowDesc* desc, float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                         const unsigned char* slot_mask, float lr, float beta1, float beta2, float eps,
+                         float weight_decay, int64_t step, void* stream);
+
 /* Optional per-kernel-class timing (CUDA events on the launching stream; off by default).  Kinds:
  * 0 tcgen05 GEMM, 1 tcgen05 weight-gradient GEMM, 2 FFMA GEMM, 3 LeakyReLU+LayerNorm fwd, 4 its backward,
  * 5 affine coupling kernels, 6 parameter-sized kernels, 7 row-fused forward/inverse tail, 8 row-fused

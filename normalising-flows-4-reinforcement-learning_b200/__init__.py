@@ -5,5 +5,6 @@ include/nf_b200.h), ``_lib`` (ctypes binding) and ``module`` (the host-side mirr
 reference's ``RealNVP`` / ``MetaBlock`` / ``InvertiblePLU`` interface).
 """
 from .module import InvertiblePLU, MetaBlock, RealNVP, count_parameters  # noqa: F401
+from .optim import CosineLRSchedule, FlatAdamW  # noqa: F401
 
-__all__ = ["RealNVP", "MetaBlock", "InvertiblePLU", "count_parameters"]
+__all__ = ["RealNVP", "MetaBlock", "InvertiblePLU", "count_parameters", "FlatAdamW", "CosineLRSchedule"]

@@ -62,6 +62,9 @@ def _load():
         "nf_prof_enable": (c_int, [c_int]),
         "nf_prof_collect": (c_int, [POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(c_int64), c_int]),
         "nf_launch_count": (c_int64, [c_int]),
+        "nf_nll_forward": (c_int, [fp, fp, i64, c_int32, fp, vp]),
+        "nf_nll_cotangents": (c_int, [fp, fp, i64, c_int32, fp, fp, vp]),
+        "nf_adamw_step": (c_int, [D, fp, fp, fp, fp, fp, c_float, c_float, c_float, c_float, c_float, i64, vp]),
         "nf_set_option": (c_int, [c_char_p, c_int]),
         "nf_get_option": (c_int, [c_char_p]),
         "nf_graphs_enable": (c_int, [c_int]),

@@ -655,6 +655,89 @@ int axpy_rows(float* dst, const float* src, long long n, cudaStream_t st) {
 }
 
 namespace {
+// ------------------------------------------------------------------------------------------
+// fused negative log-likelihood and its cotangents; fused AdamW over the flat arena
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_nll_fwd(const float* __restrict__ z, const float* __restrict__ logdet,
+                                                 long long B, int D, float* loss) {
+  NF_PDL_ENTRY();
+  __shared__ float s_part[8];
+  const float kHalfLog2Pi = 0.918938533204672742f;
+  float acc = 0.f;
+  for (long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x; row < B; row += (long long)gridDim.x * blockDim.x) {
+    float sq = 0.f;
+    for (int j = 0; j < D; ++j) { const float v = z[row * D + j]; sq = fmaf(v, v, sq); }
+    acc += 0.5f * sq + (float)D * kHalfLog2Pi - logdet[row];
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float v = s_part[threadIdx.x];
+    for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffu, v, o);
+    if (threadIdx.x == 0) atomicAdd(loss, v / (float)B);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_nll_cot(const float* __restrict__ z, const float* __restrict__ g, long long B,
+                                                 int D, float* __restrict__ dz, float* __restrict__ dld) {
+  NF_PDL_ENTRY();
+  const float scale = (g ? g[0] : 1.0f) / (float)B;
+  const long long n = B * D;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    dz[i] = scale * z[i];
+    if (i < B) dld[i] = -scale;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_adamw(AdamWP p, NfParamLayout pl) {
+  NF_PDL_ENTRY();
+  const int blk = blockIdx.y / NF_P_SLOTS, slot = blockIdx.y % NF_P_SLOTS;
+  if (!p.slot_mask[blockIdx.y]) return;
+  const long long base = (long long)blk * pl.block_stride + pl.slot_off[slot];
+  const long long n = pl.slot_numel[slot];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long e = base + i;
+    const float g = p.grads[e];
+    float w = p.params[e] * p.lr_wd_factor;                       // param.mul_(1 - lr * weight_decay)
+    float m = p.exp_avg[e];
+    m = fmaf(p.one_minus_beta1, g - m, m);                        // exp_avg.lerp_(grad, 1 - beta1)
+    float v = p.exp_avg_sq[e] * p.beta2;                          // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+    v = fmaf(p.one_minus_beta2 * g, g, v);
+    const float denom = sqrtf(v) / p.bc2_sqrt + p.eps;
+    w -= p.step_size * (m / denom);                               // param.addcdiv_(exp_avg, denom, value=-step_size)
+    p.params[e] = w; p.exp_avg[e] = m; p.exp_avg_sq[e] = v;
+  }
+}
+}  // namespace
+
+int nll_forward(const float* z, const float* logdet, long long B, int D, float* loss, cudaStream_t st) {
+  NF_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
+  if (B <= 0) return 0;
+  const long long blocks = std::min<long long>(cdiv(B, 256), 148 * 4);
+  NF_LAUNCH((k_nll_fwd), (unsigned)blocks, 256, 0, st, z, logdet, B, D, loss);
+  NF_LAUNCHED();
+  return 0;
+}
+
+int nll_cotangents(const float* z, const float* g, long long B, int D, float* dz, float* dld, cudaStream_t st) {
+  if (B <= 0) return 0;
+  const long long blocks = std::min<long long>(cdiv(B * D, 256), 148 * 8);
+  NF_LAUNCH((k_nll_cot), (unsigned)blocks, 256, 0, st, z, g, B, D, dz, dld);
+  NF_LAUNCHED();
+  return 0;
+}
+
+int adamw_step(const AdamWP& p, const NfParamLayout& pl, int n_blocks, cudaStream_t st) {
+  long long mx = 0;
+  for (int s = 0; s < NF_P_SLOTS; ++s) mx = std::max<long long>(mx, pl.slot_numel[s]);
+  const long long bx = std::min<long long>(std::max<long long>(cdiv(mx, 256 * 4), 1), 64);
+  NF_LAUNCH((k_adamw), dim3((unsigned)bx, (unsigned)(n_blocks * NF_P_SLOTS)), 256, 0, st, p, pl);
+  NF_LAUNCHED();
+  return 0;
+}
+
+namespace {
 __global__ void __launch_bounds__(256) k_copy_segments(CopySegs c) {
   NF_PDL_ENTRY();
   const int seg = blockIdx.y;

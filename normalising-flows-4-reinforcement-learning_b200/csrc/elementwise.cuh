@@ -56,6 +56,21 @@ int plu_grad_finish(const float* params, const NfParamLayout& pl, const Dims& m,
                     const float* dUh, const float* sum_dld, float* dparams, cudaStream_t st);
 int sum_vector(const float* v, long long n, float* out, cudaStream_t st);  // out[0] = sum(v)
 int fill_zero(float* p, long long n, cudaStream_t st);
+// ---- the steps either side of the flow in the training loop -----------------------
+// loss[0] = -mean_b( -0.5 |z_b|^2 - D/2 log(2 pi) + logdet_b )      (torch_nfbc_ant.py:269 with a standard-normal prior)
+int nll_forward(const float* z, const float* logdet, long long B, int D, float* loss, cudaStream_t st);
+// cotangents of that loss scaled by the upstream gradient g[0] (g may be null = 1): dz = g z / B, dld = -g / B
+int nll_cotangents(const float* z, const float* g, long long B, int D, float* dz, float* dld, cudaStream_t st);
+// one AdamW step (torch.optim.AdamW semantics, torch_nfbc_ant.py:150-155) over the flat parameter arena; slot_mask
+// (n_blocks * NF_P_SLOTS bytes on the device) selects the trainable slots
+struct AdamWP {
+  float* params; const float* grads; float* exp_avg; float* exp_avg_sq;
+  const unsigned char* slot_mask;
+  float lr_wd_factor;      // 1 - lr * weight_decay
+  float one_minus_beta1, beta2, one_minus_beta2, step_size, bc2_sqrt, eps;
+};
+int adamw_step(const AdamWP& p, const NfParamLayout& pl, int n_blocks, cudaStream_t st);
+
 // up to 4 contiguous device-to-device copies in one launch (the I/O staging around the cached launch graphs)
 struct CopySegs { float* dst[4]; const float* src[4]; long long n[4]; int count = 0;
                   void add(float* d, const float* s, long long k) { if (d && s && k > 0 && d != s) { dst[count] = d; src[count] = s; n[count] = k; ++count; } } };

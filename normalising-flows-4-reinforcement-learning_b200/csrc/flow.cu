@@ -1,4 +1,5 @@
 // Orchestration of the coupling-flow hot path and the C-ABI entry points (include/nf_b200.h).
+#include <math.h>
 #include <stdarg.h>
 #include <stdlib.h>
 
@@ -1122,6 +1123,37 @@ int nf_affine_logdet_bwd(const float* dz, const float* z, const float* s_full, c
   NF_TRY(check_ptr(dxp, "dxp", true)); NF_TRY(check_ptr(ds, "ds", true)); NF_TRY(check_ptr(dt, "dt", true));
   return affine_bwd(dz, z, s_full, dlogdet, B, D, dxp, ds, dt, nullptr, nullptr,
                     reinterpret_cast<cudaStream_t>(stream));
+}
+
+int nf_nll_forward(const float* z, const float* logdet, int64_t B, int32_t D, float* loss, void* stream) {
+  NF_CHECK_ARG(D >= 1 && B >= 0, NF_E_BADARG, "bad shape B=%lld D=%d", (long long)B, D);
+  NF_TRY(check_ptr(z, "z", B > 0)); NF_TRY(check_ptr(logdet, "logdet", B > 0)); NF_TRY(check_ptr(loss, "loss", true));
+  return nll_forward(z, logdet, B, D, loss, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int nf_nll_cotangents(const float* z, const float* g, int64_t B, int32_t D, float* dz, float* dld, void* stream) {
+  NF_CHECK_ARG(D >= 1 && B >= 0, NF_E_BADARG, "bad shape B=%lld D=%d", (long long)B, D);
+  NF_TRY(check_ptr(z, "z", B > 0)); NF_TRY(check_ptr(dz, "dz", B > 0)); NF_TRY(check_ptr(dld, "dld", B > 0));
+  return nll_cotangents(z, g, B, D, dz, dld, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int nf_adamw_step(const NfFlowDesc* desc, float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                  const unsigned char* slot_mask, float lr, float beta1, float beta2, float eps, float weight_decay,
+                  int64_t step, void* stream) {
+  NF_TRY(check_desc(desc));
+  NF_TRY(check_ptr(params, "params", true)); NF_TRY(check_ptr(grads, "grads", true));
+  NF_TRY(check_ptr(exp_avg, "exp_avg", true)); NF_TRY(check_ptr(exp_avg_sq, "exp_avg_sq", true));
+  NF_CHECK_ARG(slot_mask != nullptr && step >= 1, NF_E_BADARG, "slot_mask is NULL or step < 1");
+  const Dims m = dims_of(desc);
+  NfParamLayout pl;
+  param_layout(m, &pl);
+  AdamWP p{};
+  p.params = params; p.grads = grads; p.exp_avg = exp_avg; p.exp_avg_sq = exp_avg_sq; p.slot_mask = slot_mask;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+  p.lr_wd_factor = (float)(1.0 - (double)lr * (double)weight_decay);
+  p.one_minus_beta1 = (float)(1.0 - (double)beta1); p.beta2 = beta2; p.one_minus_beta2 = (float)(1.0 - (double)beta2);
+  p.step_size = (float)((double)lr / bc1); p.bc2_sqrt = (float)sqrt(bc2); p.eps = eps;
+  return adamw_step(p, pl, m.n, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int nf_plu_build(const float* s, const float* U, const float* L, const float* P, const float* P_inv, int32_t D,

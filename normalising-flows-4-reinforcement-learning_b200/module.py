@@ -161,6 +161,46 @@ class _Flow(torch.autograd.Function):
         return (None, None, dx, dy) + pg
 
 
+class _FlowNLL(torch.autograd.Function):
+    """loss = -mean(log N(z; 0, I) + log_dets) with the loss and its cotangents computed by the library
+    (nf_nll_forward / nf_nll_cotangents) instead of ~8 elementwise torch kernels either side of the flow."""
+
+    @staticmethod
+    def forward(ctx, model: "RealNVP", x, y, *params):
+        z, logdet, _, stash, packed, slot = model._run_forward(x, y, True)
+        loss = torch.empty((), dtype=torch.float32, device=x.device)
+        _lib.check(lib.nf_nll_forward(z.data_ptr(), logdet.data_ptr(), x.shape[0], model.in_channels,
+                                      loss.data_ptr(), model._stream(x.device)), "nf_nll_forward")
+        ctx.model, ctx.stash, ctx.packed = model, stash, packed
+        ctx.guard = _SlotGuard(slot) if slot is not None else None
+        ctx.pver = model._params_version()
+        ctx.B = x.shape[0]
+        ctx.save_for_backward(y, z)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        model = ctx.model
+        if ctx.stash is None:
+            raise RuntimeError("nf_b200: backward called twice on the same forward (the stash is freed after use)")
+        if ctx.pver != model._params_version():
+            raise RuntimeError("nf_b200: parameters were modified between forward and backward")
+        y, z = ctx.saved_tensors
+        B, D = ctx.B, model.in_channels
+        dz = torch.empty_like(z)
+        dld = torch.empty((B,), dtype=torch.float32, device=z.device)
+        g = _dense(g.reshape(1).to(torch.float32))
+        _lib.check(lib.nf_nll_cotangents(z.data_ptr(), g.data_ptr(), B, D, dz.data_ptr(), dld.data_ptr(),
+                                         model._stream(z.device)), "nf_nll_cotangents")
+        need_x, need_y = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        need_p = any(ctx.needs_input_grad[3:])
+        dx, dy = model._run_backward_fast(ctx.stash, ctx.packed, y, B, dz, dld, need_x, need_y, need_p)
+        ctx.stash = None
+        if ctx.guard is not None:
+            ctx.guard.release()
+        return (None, dx, dy) + (None,) * (len(ctx.needs_input_grad) - 3)
+
+
 class RealNVP(nn.Module):
     """Drop-in for the reference ``RealNVP`` (torch_fcnf.py:119-152).
 
@@ -205,6 +245,7 @@ class RealNVP(nn.Module):
         self._gflat: Optional[torch.Tensor] = None
         self._gviews = None
         self._stash_pool = {}
+        self._xver = 0
         self._dp_group = None
         self._dp_world = 1
         self._flatten()
@@ -273,8 +314,12 @@ class RealNVP(nn.Module):
         return (p0.data_ptr() == base + 4 * off0 and p1.data_ptr() == base + 4 * off1
                 and p0.device == self._flat.device)
 
+    def _bump_version(self):
+        """Called by code that updates the arena outside torch's version counters (FlatAdamW)."""
+        self._xver += 1
+
     def _params_version(self):
-        v = 0
+        v = self._xver
         for p in self._tparams:
             v += p._version
         return v
@@ -491,6 +536,16 @@ class RealNVP(nn.Module):
         (torch_nfbc_ant.py:269) for the standard-normal prior, without the O(D^2) Mahalanobis path."""
         z, _, logdet = self.forward(x, y)
         return -0.5 * (z * z).sum(dim=1) - 0.5 * self.in_channels * math.log(2.0 * math.pi) + logdet
+
+    def nll(self, x, y):
+        """-mean(log N(z; 0, I) + log_dets): the training loss of torch_nfbc_ant.py:269-270 for the standard-normal
+        prior, with the loss reduction and its cotangents fused into two library kernels.  Parameter gradients
+        go to the flat gradient arena (``fast_param_grads`` semantics)."""
+        self._check_inputs(x, y)
+        params = [p for p in self._tparams if p.requires_grad] if torch.is_grad_enabled() else []
+        if torch.is_grad_enabled() and (x.requires_grad or y.requires_grad or params):
+            return _FlowNLL.apply(self, x, y, *params[:1])
+        return -self.log_prob(x, y).mean()
 
     def sample(self, y, generator=None):
         """reverse(prior sample, y) with a standard-normal prior (torch_nfbc_ant.py:209-210)."""

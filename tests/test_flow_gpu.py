@@ -415,3 +415,46 @@ def test_options_are_equivalent(name, value):
     tol = 1e-5 if name == "nacc" else 3e-6   # one accumulator instead of three: the truncation noise itself changes
     for a, b, nm in zip(ref, got, ("z", "ld", "dx", "dy", "dparams", "rev")):
         assert rel_err(b, a) <= tol, (name, value, nm, rel_err(b, a))
+
+
+def test_fused_nll_and_flat_adamw_match_the_torch_training_step():
+    """model.nll() (fused loss + cotangents) and FlatAdamW (one kernel over the arena)
+    reproduce `loss = -(log N(z) + logdets).mean(); loss.backward(); torch.optim.AdamW.step()` of
+    torch_nfbc_ant.py:269-273 for a few steps, with an extra (encoder-like) parameter in the same optimizer and
+    the reference-style cosine schedule driving the learning rate."""
+    D, C, R, n, B = 8, 64, 16, 3, 96
+    sd = synth.make_state_dict(D, C, R, n, seed=51)
+    cfg = dict(D=D, C=C, R=R, n=n, B=B)
+    a = build_model(cfg, sd, "fp32_simt", fast_param_grads=False)      # plain torch training step
+    b = build_model(cfg, sd, "fp32_simt")                              # fused loss + fused optimizer
+    torch.manual_seed(0)
+    enc_a = torch.nn.Linear(5, R).to(dev())
+    enc_b = torch.nn.Linear(5, R).to(dev())
+    enc_b.load_state_dict(enc_a.state_dict())
+    kw = dict(lr=3e-3, betas=(0.9, 0.95), eps=1e-8, weight_decay=1e-2)
+    opt_a = torch.optim.AdamW(list(a.parameters()) + list(enc_a.parameters()), **kw)
+    opt_b = nf_b200.FlatAdamW(list(b.parameters()) + list(enc_b.parameters()), flows=[b], **kw)
+    sch_a = nf_b200.CosineLRSchedule(opt_a, warmup_steps=2, total_steps=6, min_lr=1e-4, max_lr=3e-3)
+    sch_b = nf_b200.CosineLRSchedule(opt_b, warmup_steps=2, total_steps=6, min_lr=1e-4, max_lr=3e-3)
+    LOG2PI = float(np.log(2 * np.pi))
+    for it in range(4):
+        x, _ = synth.make_inputs(B, D, R, seed=60 + it)
+        obs = torch.randn(B, 5, generator=torch.Generator().manual_seed(it)).to(dev())
+        opt_a.zero_grad(set_to_none=True)
+        z, _, ld = a(t(x), enc_a(obs))
+        loss_a = -((-0.5 * (z * z).sum(1) - 0.5 * D * LOG2PI) + ld).mean()
+        loss_a.backward()
+        opt_a.step(); sch_a.step()
+        opt_b.zero_grad(set_to_none=True)
+        loss_b = b.nll(t(x), enc_b(obs))
+        loss_b.backward()
+        opt_b.step(); sch_b.step()
+        assert abs(loss_a.item() - loss_b.item()) <= 2e-6 * max(1.0, abs(loss_a.item())), it
+        assert opt_a.param_groups[0]["lr"] == opt_b.param_groups[0]["lr"]
+    pa, pb = dict(a.named_parameters()), dict(b.named_parameters())
+    for k in pa:
+        assert rel_err(pb[k].detach().cpu().numpy(), pa[k].detach().cpu().numpy()) <= 5e-6, k
+    for k, v in enc_a.state_dict().items():
+        assert rel_err(enc_b.state_dict()[k].cpu().numpy(), v.cpu().numpy()) <= 5e-6, k
+    # frozen PLU permutations are untouched by the optimizer (they carry weight decay otherwise)
+    assert torch.equal(b.blocks[0].l.P, t(sd["blocks.0.l.P"]))
