@@ -45,6 +45,7 @@ enum NfOpt {
   NF_OPT_FUSED_LN,       // LayerNorm fused into the GEMM epilogue: -1 auto, 0 never, 1 always  (default -1)
   NF_OPT_FUSED_TAIL,     // flow tail fused into the layer-2 GEMM                               (default 0)
   NF_OPT_BN256,          // 256-wide GEMM tiles: 0 auto (K <= 256), 1 always, 2 never           (default 0)
+  NF_OPT_TS,             // A operand of the K-major GEMMs from tensor memory                   (default 1)
   NF_OPT_COUNT
 };
 int option(int id);

@@ -35,7 +35,7 @@ struct OptDef { const char* name; const char* env; int def; };
 const OptDef kOpts[NF_OPT_COUNT] = {
     {"pdl", "NF_B200_PDL", 1},           {"streams", "NF_B200_STREAMS", 1},       {"tma_store", "NF_B200_TMA_STORE", 1},
     {"nacc", "NF_B200_NACC", 0},         {"fused_ln", "NF_B200_FUSED_LN", -1},    {"fused_tail", "NF_B200_FUSED_TAIL", 0},
-    {"bn256", "NF_B200_BN256", 0},
+    {"bn256", "NF_B200_BN256", 0},       {"ts", "NF_B200_TS", 1},
 };
 int g_opt[NF_OPT_COUNT];
 bool g_opt_init = false;

@@ -167,6 +167,24 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// A operand from tensor memory (M x K, one 32-bit element per column, row = lane)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
@@ -300,7 +318,14 @@ struct Smem {
   static constexpr int TOTAL_EPI = TPART + 8 * 128 * 16 + 1024;
 };
 
-template <int BN, int STAGES, bool MNMAJOR, int BK, int EPI = EPI_NONE>
+// TS = true: the A operand (the 128 activation rows of the tile) is fed to the MMAs from TENSOR MEMORY instead of
+// shared memory.  The main loop of the SS form is bound by shared-memory bandwidth (96 KB of traffic per
+// 16-deep stage): each k8 step reads the A tile three times.  Here the splitter threads
+// (thread = tile row, the TMEM lane it may access) read their row of the TMA tile once, split it and write hi / lo
+// with tcgen05.st into a 4-slot ring of 32 TMEM columns; the MMAs read A from there ([a_tmem] operand form) and
+// only the B operand comes from shared memory (64 KB per stage).  The ring takes 128 TMEM columns, so 128-wide
+// tiles rotate over two main accumulators instead of three and the form is used for K <= 512 there.
+template <int BN, int STAGES, bool MNMAJOR, int BK, int EPI = EPI_NONE, bool TS = false>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUtensorMap mA1,
           const __grid_constant__ CUtensorMap mB0, const __grid_constant__ CUtensorMap mB1,
@@ -317,7 +342,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
   uint64_t* accbar = bars + 3 * STAGES;
   uint64_t* xbar = bars + 3 * STAGES + 1;      // cluster exchange barrier (epilogue kernels)
   uint64_t* tbar = bars + 3 * STAGES + 2;      // fused tail: partials have arrived at the leader CTA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 3);
+  uint64_t* aempty = bars + 3 * STAGES + 3;    // TS: the MMAs have read TMEM A slot i (4 slots)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 7);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
@@ -337,8 +363,12 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
   // multiplicative correction therefore does not help, it was tried).  The hi*hi products therefore rotate over NACC independent
   // accumulators that are summed with round-to-nearest adds in the epilogue (bias / NACC), and the
   // weight-gradient form additionally caps the rows per CTA (launch_tn).
-  constexpr int NACC = BN <= 128 ? 3 : 1;
-  constexpr uint32_t TMEM_COLS = (NACC + 1) * BN;   // NACC main + 1 corr accumulator
+  static_assert(!TS || (!MNMAJOR && BK == 16 && BN <= 128), "TS form: K-major operands, 16-deep stages, BN <= 128");
+  constexpr int NACC = TS ? (BN <= 64 ? 3 : 2) : (BN <= 128 ? 3 : 1);
+  constexpr int kASlots = 4;                                          // TS: TMEM A ring (hi 16 + lo 16 columns per slot)
+  constexpr uint32_t A_BASE = (NACC + 1) * BN;                        // first TMEM column of the A ring
+  constexpr uint32_t TMEM_NEED = (NACC + 1) * BN + (TS ? kASlots * 2 * BK : 0);
+  constexpr uint32_t TMEM_COLS = TMEM_NEED <= 256 ? 256 : 512;        // NACC main + 1 corr accumulator (+ A ring)
   // k8 steps this CTA issues (the epilogue must know how many main accumulators were written)
   int total_k8;
   if (MNMAJOR) {
@@ -364,6 +394,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
     if (nk1) { prefetch_tmap(&mA1); prefetch_tmap(&mB1); }
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&split[s], 4); mbar_init(&empty[s], 1); }
     mbar_init(accbar, 1);
+    if (TS) for (int i = 0; i < kASlots; ++i) mbar_init(&aempty[i], 1);
     if (EPI != EPI_NONE) mbar_init(xbar, (uint32_t)a.ncl * 128u);
     if (EPI == EPI_LN_FWD) mbar_init(tbar, 2u * (uint32_t)a.ncl * 128u);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -452,6 +483,16 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
             const uint64_t a_hi = (static_cast<uint64_t>(dhi) << 32) | la_hi, b_hi = (static_cast<uint64_t>(dhi) << 32) | lb_hi;
             const uint64_t a_lo = (static_cast<uint64_t>(dhi) << 32) | la_lo, b_lo = (static_cast<uint64_t>(dhi) << 32) | lb_lo;
             uint32_t acc_m = fresh == 0 ? 1u : 0u;
+            if constexpr (TS) {
+              const uint32_t ta_hi = tmem_base + A_BASE + (uint32_t)(it % kASlots) * 2 * BK + (uint32_t)ks * 8, ta_lo = ta_hi + BK;
+              if (leader) {
+                if (three) {
+                  umma_tf32_ts(tmem_corr, ta_lo, b_hi, idesc, acc_c);
+                  umma_tf32_ts(tmem_corr, ta_hi, b_lo, idesc, 1u);
+                }
+                umma_tf32_ts(tmem_main, ta_hi, b_hi, idesc, acc_m);
+              }
+            } else
             if (leader) {
               if (three) {
                 if (merge) {
@@ -472,7 +513,10 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
             la_hi += kStep; lb_hi += kStep; la_lo += kStep; lb_lo += kStep;
           }
         }
-        if (leader) umma_commit(&empty[s]);   // frees the stage once the MMAs above have read it
+        if (leader) {
+          umma_commit(&empty[s]);   // frees the stage once the MMAs above have read it
+          if (TS) umma_commit(&aempty[it % kASlots]);
+        }
         __syncwarp();
       }
       if (elect_one()) umma_commit(accbar);        // accumulator complete
@@ -487,6 +531,53 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
       if (threadIdx.x == 64 && it == 0) NF_TS(2);   // first operand tile landed
       float4* raw = reinterpret_cast<float4*>(smem + s * S::STAGE);
       float4* lo = reinterpret_cast<float4*>(smem + s * S::STAGE + S::HALF);
+      if constexpr (TS) {
+        // B tile: split in shared memory as in the SS form; A tile: this thread's row -> tensor memory
+        constexpr int A4 = A_BYTES / 16, PERB = S::B_BYTES / 16 / 128;
+        const int r = (warp & 3) * 32 + lane;                        // tile row = TMEM lane of this thread
+        const int sw = (r >> 1) & 3;                                 // SWIZZLE_64B: 16-byte chunk c sits at c ^ ((row >> 1) & 3)
+        float4 av[4], bv[PERB];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) av[c] = raw[r * 4 + (c ^ sw)];
+#pragma unroll
+        for (int k = 0; k < PERB; ++k) bv[k] = raw[A4 + t + 128 * k];
+#pragma unroll
+        for (int k = 0; k < PERB; ++k) {
+          const int i = A4 + t + 128 * k;
+          float4 h, l;
+          if (a.raw_hi) {
+            h.x = __uint_as_float(__float_as_uint(bv[k].x) & 0xffffe000u); h.y = __uint_as_float(__float_as_uint(bv[k].y) & 0xffffe000u);
+            h.z = __uint_as_float(__float_as_uint(bv[k].z) & 0xffffe000u); h.w = __uint_as_float(__float_as_uint(bv[k].w) & 0xffffe000u);
+          } else {
+            h.x = rna_tf32(bv[k].x); h.y = rna_tf32(bv[k].y); h.z = rna_tf32(bv[k].z); h.w = rna_tf32(bv[k].w);
+            raw[i] = h;
+          }
+          l.x = bv[k].x - h.x; l.y = bv[k].y - h.y; l.z = bv[k].z - h.z; l.w = bv[k].w - h.w;
+          lo[i] = l;
+        }
+        uint32_t hi16[16], lo16[16];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float xs[4] = {av[c].x, av[c].y, av[c].z, av[c].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float h = a.raw_hi ? __uint_as_float(__float_as_uint(xs[e]) & 0xffffe000u) : rna_tf32(xs[e]);
+            hi16[4 * c + e] = __float_as_uint(h);
+            lo16[4 * c + e] = __float_as_uint(xs[e] - h);
+          }
+        }
+        const int slot = it % kASlots;
+        if (it >= kASlots) {                                         // the MMAs of iteration it - 4 have read this slot
+          if (lane == 0) mbar_wait(&aempty[slot], ((it / kASlots) & 1) ^ 1);
+          __syncwarp();
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        const uint32_t ta = tmem_base + A_BASE + (uint32_t)slot * 2 * BK + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+        tmem_st16(ta, hi16);
+        tmem_st16(ta + BK, lo16);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      } else {
       // every load of the stage is issued before the first store: the in-place/aliased stores otherwise
       // serialise load -> store -> load and the splitters pace the MMAs (measured 800 cycles per stage
       // against a 384-cycle MMA floor, tools/tc_timeline.py)
@@ -509,6 +600,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
         l.x = v[k].x - h.x; l.y = v[k].y - h.y; l.z = v[k].z - h.z; l.w = v[k].w - h.w;
         if (a.lo_round) { l.x = rna_tf32(l.x); l.y = rna_tf32(l.y); l.z = rna_tf32(l.z); l.w = rna_tf32(l.w); }
         lo[i] = l;
+      }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> UMMA reads
       __syncwarp();
@@ -921,16 +1013,25 @@ int set_smem() {
 // accumulate-truncation budget: one main accumulator per 32 k8 steps (K = 256), at most 3; reductions of up to
 // 12 k8 steps (K <= 96) keep the cross terms in the main accumulator (3 truncations per step, still < 40)
 constexpr int kMergeCorrK8 = 12;
+// TS form with 128-wide tiles rotates over two main accumulators: keep its reductions short enough
+constexpr int kTsMaxK128 = 512;
 int pick_nacc(int total_k8) {
   (void)total_k8;
   return option(NF_OPT_NACC);   // 0 = kernel default (all NACC accumulators)
 }
 
-template <int BN, int STAGES, int BK>
+template <int BN, int STAGES, int BK, bool TS = false>
 int launch(const TcGemmP& p, cudaStream_t st) {
   using S = Smem<BN, STAGES, BK>;
   int r;
-  if ((r = set_smem<BN, STAGES, false, BK>())) return r;
+  {
+    static bool configured = false;
+    if (!configured) {
+      NF_CUDA(cudaFuncSetAttribute(k_tc_gemm<BN, STAGES, false, BK, EPI_NONE, TS>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+      configured = true;
+    }
+  }
   CUtensorMap mA0, mA1, mB0, mB1;
   const CUtensorMapSwizzle swz = BK == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   if ((r = make_map(&mA0, p.A0, p.K0, p.M, p.lda0, p.batch, p.sA0, BK, BM, swz))) return r;
@@ -965,17 +1066,17 @@ int launch(const TcGemmP& p, cudaStream_t st) {
   ProfScope prof(st, PROF_TC_GEMM, 2.0 * p.M * p.N * (double)(p.K0 + p.K1) * p.batch);
   CUtensorMap mC = mA0;
   a.tma_store = make_c_map(&mC, p.C, p.N, p.M, p.ldc, p.batch, p.sC) ? 1 : 0;
-  NF_LAUNCH((k_tc_gemm<BN, STAGES, false, BK>), grid, NTHREADS, S::TOTAL, st, mA0, mA1, mB0, mB1, mC, a);
+  NF_LAUNCH((k_tc_gemm<BN, STAGES, false, BK, EPI_NONE, TS>), grid, NTHREADS, S::TOTAL, st, mA0, mA1, mB0, mB1, mC, a);
   NF_LAUNCHED();
   return 0;
 }
 
-template <int BN, int STAGES, int BK, int EPI>
+template <int BN, int STAGES, int BK, int EPI, bool TS = false>
 int launch_epi(const TcGemmP& p, cudaStream_t st) {
   using S = Smem<BN, STAGES, BK>;
   static bool configured = false;
   if (!configured) {
-    NF_CUDA(cudaFuncSetAttribute(k_tc_gemm<BN, STAGES, false, BK, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    NF_CUDA(cudaFuncSetAttribute(k_tc_gemm<BN, STAGES, false, BK, EPI, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  S::TOTAL_EPI));
     configured = true;
   }
@@ -1025,15 +1126,19 @@ int launch_epi(const TcGemmP& p, cudaStream_t st) {
   ProfScope prof(st, PROF_TC_GEMM, 2.0 * p.M * p.N * (double)(p.K0 + p.K1) * p.batch);
   CUtensorMap mC = mA0;
   a.tma_store = make_c_map(&mC, p.C, p.N, p.M, p.ldc, p.batch, p.sC) ? 1 : 0;
-  NF_CUDA(cudaLaunchKernelEx(&cfg, k_tc_gemm<BN, STAGES, false, BK, EPI>, mA0, mA1, mB0, mB1, mC, a));
+  NF_CUDA(cudaLaunchKernelEx(&cfg, k_tc_gemm<BN, STAGES, false, BK, EPI, TS>, mA0, mA1, mB0, mB1, mC, a));
   NF_LAUNCHED();
   return 0;
 }
 
 template <int EPI>
 int launch_epi_pick(const TcGemmP& p, cudaStream_t st) {
-  if (p.N % 128 == 0 && p.N / 128 <= kMaxCluster) return launch_epi<128, 6, 16, EPI>(p, st);
-  return launch_epi<64, 8, 16, EPI>(p, st);
+  const bool ts = option(NF_OPT_TS) != 0;
+  if (p.N % 128 == 0 && p.N / 128 <= kMaxCluster) {
+    if (ts && p.K0 + p.K1 <= kTsMaxK128) return launch_epi<128, 6, 16, EPI, true>(p, st);
+    return launch_epi<128, 6, 16, EPI>(p, st);
+  }
+  return ts ? launch_epi<64, 8, 16, EPI, true>(p, st) : launch_epi<64, 8, 16, EPI>(p, st);
 }
 
 template <int BN, int STAGES, int BK>
@@ -1138,8 +1243,12 @@ int tc_gemm(const TcGemmP& p, cudaStream_t st) {
     return launch<64, 4, 32>(p, st);
   }
   if (p.N > 128 && ctas256 >= 120) return launch<256, 4, 16>(p, st);
-  if (p.N > 64) return launch<128, 6, 16>(p, st);
-  return launch<64, 8, 16>(p, st);
+  const bool ts = option(NF_OPT_TS) != 0;
+  if (p.N > 64) {
+    if (ts && p.K0 + p.K1 <= kTsMaxK128) return launch<128, 6, 16, true>(p, st);
+    return launch<128, 6, 16>(p, st);
+  }
+  return ts ? launch<64, 8, 16, true>(p, st) : launch<64, 8, 16>(p, st);
 }
 
 bool tc_gemm_tn_supported(const TcGemmTnP& p) {
