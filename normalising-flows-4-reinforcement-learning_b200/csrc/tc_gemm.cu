@@ -364,7 +364,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
   // multiplicative correction therefore does not help, it was tried).  The hi*hi products therefore rotate over NACC independent
   // accumulators that are summed with round-to-nearest adds in the epilogue (bias / NACC), and the
   // weight-gradient form additionally caps the rows per CTA (launch_tn).
-  static_assert(!TS || (!MNMAJOR && BK == 16 && BN <= 128), "TS form: K-major operands, 16-deep stages, BN <= 128");
+  static_assert(!TS || (BK == 16 && BN <= 128), "TS form: 16-deep stages, BN <= 128");
   constexpr int NACC = TS ? (BN <= 64 ? 3 : 2) : (BN <= 128 ? 3 : 1);
   constexpr int kASlots = 4;                                          // TS: TMEM A ring (hi 16 + lo 16 columns per slot)
   constexpr uint32_t A_BASE = (NACC + 1) * BN;                        // first TMEM column of the A ring
@@ -447,7 +447,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
     // ------------------------------------------------------------------ MMA issuer
     {
       // kind::tf32, fp32 accumulate, M = 128, N = BN; bits 15/16 = MN-major A/B (cute::UMMA::InstrDescriptor)
-      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (MNMAJOR ? (3u << 15) : 0u) |
+      // (an A operand in tensor memory is always rows x K: only B keeps the MN-major bit in the TS weight-gradient form)
+      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (MNMAJOR ? ((TS ? 2u : 3u) << 15) : 0u) |
                                  (uint32_t(BN >> 3) << 17) | (uint32_t(BM >> 4) << 24);
       // One thread issues every MMA, so the instruction latency of THIS loop paces the tensor pipe (a
       // runtime modulo for the accumulator rotation alone cost 30 % of the mainloop): descriptors are a
@@ -536,10 +537,19 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
         // B tile: split in shared memory as in the SS form; A tile: this thread's row -> tensor memory
         constexpr int A4 = A_BYTES / 16, PERB = S::B_BYTES / 16 / 128;
         const int r = (warp & 3) * 32 + lane;                        // tile row = TMEM lane of this thread
-        const int sw = (r >> 1) & 3;                                 // SWIZZLE_64B: 16-byte chunk c sits at c ^ ((row >> 1) & 3)
         float4 av[4], bv[PERB];
+        if constexpr (MNMAJOR) {
+          // weight-gradient form: the A tile is four unswizzled [BK rows][32 columns] boxes; this thread's tile row is
+          // column `lane` of box (warp & 3): element k at box + k * 32 + lane (consecutive lanes, no bank conflicts)
+          const float* boxf = reinterpret_cast<const float*>(raw) + (warp & 3) * (BOX / 4) + lane;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) av[c] = raw[r * 4 + (c ^ sw)];
+          for (int c = 0; c < 4; ++c)
+            av[c] = make_float4(boxf[(4 * c) * 32], boxf[(4 * c + 1) * 32], boxf[(4 * c + 2) * 32], boxf[(4 * c + 3) * 32]);
+        } else {
+          const int sw = (r >> 1) & 3;                               // SWIZZLE_64B: 16-byte chunk c sits at c ^ ((row >> 1) & 3)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) av[c] = raw[r * 4 + (c ^ sw)];
+        }
 #pragma unroll
         for (int k = 0; k < PERB; ++k) bv[k] = raw[A4 + t + 128 * k];
 #pragma unroll
@@ -1140,21 +1150,30 @@ int launch_epi_pick(const TcGemmP& p, cudaStream_t st) {
   return ts ? launch_epi<64, 8, 16, EPI, true>(p, st) : launch_epi<64, 8, 16, EPI>(p, st);
 }
 
-template <int BN, int STAGES, int BK>
+template <int BN, int STAGES, int BK, bool TS = false>
 int launch_tn(const TcGemmTnP& p, cudaStream_t st) {
   using S = Smem<BN, STAGES, BK>;
   int r;
-  if ((r = set_smem<BN, STAGES, true, BK>())) return r;
+  {
+    static bool configured = false;
+    if (!configured) {
+      NF_CUDA(cudaFuncSetAttribute(k_tc_gemm<BN, STAGES, true, BK, EPI_NONE, TS>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+      configured = true;
+    }
+  }
   CUtensorMap mA, mB;
-  // operands are (K rows, M|N contiguous): inner = M|N, rows = K, 32 x BK boxes
-  if ((r = make_map(&mA, p.A, p.M, p.K, p.lda, p.batch, p.sA, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return r;
+  // operands are (K rows, M|N contiguous): inner = M|N, rows = K, 32 x BK boxes (TS: the A boxes are read by the
+  // splitter threads, not by the tensor core, and stay unswizzled)
+  if ((r = make_map(&mA, p.A, p.M, p.K, p.lda, p.batch, p.sA, 32, BK,
+                    TS ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return r;
   if ((r = make_map(&mB, p.B, p.N, p.K, p.ldb, p.batch, p.sB, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return r;
   const long long nk = cdiv(p.K, BK);
   const long long tiles = cdiv(p.M, BM) * cdiv(p.N, BN) * p.batch;
   // one wave: as many splits as fit on the 148 SMs without spilling into a second, nearly empty wave
   long long splitk = p.splitk > 0 ? p.splitk : (tiles >= 148 ? 1 : 148 / tiles);
   // accumulate-truncation bound (see the kernel): at most kMaxRowsPerSplit batch rows per CTA
-  constexpr long long kMaxRowsPerSplit = 1536;
+  constexpr long long kMaxRowsPerSplit = TS ? 1024 : 1536;   // two rotating accumulators in the TS form
   if (p.splitk <= 0 && splitk < cdiv(p.K, kMaxRowsPerSplit)) splitk = cdiv(p.K, kMaxRowsPerSplit);
   if (splitk > nk) splitk = nk;
   if (splitk < 1) splitk = 1;
@@ -1177,7 +1196,7 @@ int launch_tn(const TcGemmTnP& p, cudaStream_t st) {
   ProfScope prof(st, PROF_TC_WGRAD, 2.0 * p.M * p.N * (double)p.K * p.batch);
   CUtensorMap mC = mA;
   a.tma_store = make_c_map(&mC, p.C, p.N, p.M, p.ldc, p.batch, p.sC) ? 1 : 0;
-  NF_LAUNCH((k_tc_gemm<BN, STAGES, true, BK>), grid, NTHREADS, S::TOTAL, st, mA, mA, mB, mB, mC, a);
+  NF_LAUNCH((k_tc_gemm<BN, STAGES, true, BK, EPI_NONE, TS>), grid, NTHREADS, S::TOTAL, st, mA, mA, mB, mB, mC, a);
   NF_LAUNCHED();
   return 0;
 }
@@ -1263,6 +1282,7 @@ int tc_gemm_tn(const TcGemmTnP& p, cudaStream_t st) {
   const int wide_ok = option(NF_OPT_BN256);
   if (wide_ok != 1) {
     if (p.bk == 32) return p.N > 64 ? launch_tn<128, 3, 32>(p, st) : launch_tn<64, 4, 32>(p, st);
+    if (option(NF_OPT_TS) != 0) return p.N > 64 ? launch_tn<128, 6, 16, true>(p, st) : launch_tn<64, 8, 16, true>(p, st);
     return p.N > 64 ? launch_tn<128, 6, 16>(p, st) : launch_tn<64, 8, 16>(p, st);
   }
   if (p.bk == 32) {
