@@ -46,6 +46,7 @@ enum NfOpt {
   NF_OPT_FUSED_TAIL,     // flow tail fused into the layer-2 GEMM                               (default 0)
   NF_OPT_BN256,          // 256-wide GEMM tiles: 0 auto (K <= 256), 1 always, 2 never           (default 0)
   NF_OPT_TS,             // A operand of the K-major GEMMs from tensor memory                   (default 1)
+  NF_OPT_PRESPLIT,       // weight operands split into hi / lo once per parameter update        (default 1)
   NF_OPT_COUNT
 };
 int option(int id);
@@ -116,6 +117,9 @@ struct PackedLayout {
   int dcp, K1p;  // W1p: (H1, K1p) copy of W1 whose y columns start at the 16-byte aligned column dcp
   int64_t net_stride, block_stride;
   int64_t logdet_c, logdet_total, total;
+  // tensor-core precision only: rounded-to-tf32 `hi` and residual `lo` copies of every table above, at
+  // table + hi_off / table + lo_off (the GEMMs' B operands arrive pre-split; 0 = absent)
+  int64_t hi_off, lo_off;
 };
 PackedLayout packed_layout(const Dims& m);
 

@@ -711,6 +711,34 @@ __global__ void __launch_bounds__(256) k_adamw(AdamWP p, NfParamLayout pl) {
 }
 }  // namespace
 
+namespace {
+__global__ void __launch_bounds__(256) k_split_tables(const float4* __restrict__ t, float4* __restrict__ hi,
+                                                      float4* __restrict__ lo, long long n4) {
+  NF_PDL_ENTRY();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = t[i];
+    float4 h, l;
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v.x)); h.x = __uint_as_float(r);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v.y)); h.y = __uint_as_float(r);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v.z)); h.z = __uint_as_float(r);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v.w)); h.w = __uint_as_float(r);
+    l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+    hi[i] = h; lo[i] = l;
+  }
+}
+}  // namespace
+
+int split_tables(float* tables, long long hi_off, long long lo_off, long long n, cudaStream_t st) {
+  const long long n4 = (n + 3) / 4;
+  const long long blocks = std::min<long long>(std::max<long long>(cdiv(n4, 256), 1), 148 * 8);
+  ProfScope prof(st, PROF_PARAM, 0.0);
+  NF_LAUNCH((k_split_tables), (unsigned)blocks, 256, 0, st, reinterpret_cast<const float4*>(tables),
+            reinterpret_cast<float4*>(tables + hi_off), reinterpret_cast<float4*>(tables + lo_off), n4);
+  NF_LAUNCHED();
+  return 0;
+}
+
 int nll_forward(const float* z, const float* logdet, long long B, int D, float* loss, cudaStream_t st) {
   NF_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
   if (B <= 0) return 0;

@@ -56,6 +56,8 @@ int plu_grad_finish(const float* params, const NfParamLayout& pl, const Dims& m,
                     const float* dUh, const float* sum_dld, float* dparams, cudaStream_t st);
 int sum_vector(const float* v, long long n, float* out, cudaStream_t st);  // out[0] = sum(v)
 int fill_zero(float* p, long long n, cudaStream_t st);
+// hi[i] = rna_tf32(t[i]), lo[i] = t[i] - hi[i] for the first n floats of the packed tables (hi = t + hi_off, ...)
+int split_tables(float* tables, long long hi_off, long long lo_off, long long n, cudaStream_t st);
 // ---- the steps either side of the flow in the training loop -----------------------
 // loss[0] = -mean_b( -0.5 |z_b|^2 - D/2 log(2 pi) + logdet_b )      (torch_nfbc_ant.py:269 with a standard-normal prior)
 int nll_forward(const float* z, const float* logdet, long long B, int D, float* loss, cudaStream_t st);

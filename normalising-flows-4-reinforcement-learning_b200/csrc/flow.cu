@@ -35,7 +35,7 @@ struct OptDef { const char* name; const char* env; int def; };
 const OptDef kOpts[NF_OPT_COUNT] = {
     {"pdl", "NF_B200_PDL", 1},           {"streams", "NF_B200_STREAMS", 1},       {"tma_store", "NF_B200_TMA_STORE", 1},
     {"nacc", "NF_B200_NACC", 0},         {"fused_ln", "NF_B200_FUSED_LN", -1},    {"fused_tail", "NF_B200_FUSED_TAIL", 0},
-    {"bn256", "NF_B200_BN256", 0},       {"ts", "NF_B200_TS", 1},
+    {"bn256", "NF_B200_BN256", 0},       {"ts", "NF_B200_TS", 1},                 {"presplit", "NF_B200_PRESPLIT", 1},
 };
 int g_opt[NF_OPT_COUNT];
 bool g_opt_init = false;
@@ -115,6 +115,12 @@ PackedLayout packed_layout(const Dims& m) {
   k.logdet_c = off * m.n;
   k.logdet_total = k.logdet_c + pad4(m.n);
   k.total = k.logdet_total + 4;
+  k.hi_off = k.lo_off = 0;
+  if (m.prec == NF_PREC_TF32X3) {
+    const int64_t base = pad32(k.total);
+    k.hi_off = base; k.lo_off = 2 * base;
+    k.total = 3 * base;
+  }
   return k;
 }
 
@@ -363,12 +369,14 @@ static int conditioners(const Dims& m, const NfParamLayout& pl, const PackedLayo
     // W1p: W1 with the y columns moved to the 16-byte aligned column dcp (TMA operand)
     g.B0 = kb + kl.net0 + kl.W1p; g.ldb0 = kl.K1p; g.sB0 = kl.net_stride;
     if (m.R > 0) { g.B1 = g.B0 + kl.dcp; g.ldb1 = kl.K1p; g.sB1 = kl.net_stride; }
+    if (kl.hi_off) { g.B0hi = g.B0 + kl.hi_off; g.B0lo = g.B0 + kl.lo_off; if (m.R > 0) { g.B1hi = g.B1 + kl.hi_off; g.B1lo = g.B1 + kl.lo_off; } }
     NF_TRY(linear_lrelu_ln(g, m.H1, pb + pl.slot_off[NF_P_B1], pl.net_stride, xh1, xh1_net, r1, m1, mw1, nullptr));
   }
   {  // layer 2: x_hat1 W2f^T + b2f
     TcGemmP g;
     g.A0 = xh1; g.lda0 = m.H1; g.K0 = m.H1; g.sA0 = xh1_net;
     g.B0 = kb + kl.net0 + kl.W2f; g.ldb0 = m.H1; g.sB0 = kl.net_stride;
+    if (kl.hi_off) { g.B0hi = g.B0 + kl.hi_off; g.B0lo = g.B0 + kl.lo_off; }
     NF_TRY(linear_lrelu_ln(g, m.C, kb + kl.net0 + kl.b2f, kl.net_stride, xh2, xh2_net, r2, m2, mw2, tail));
   }
   if (with_last) {  // o = x_hat2 W3f^T  (N = D/2: FFMA unless the flow is wide)
@@ -501,6 +509,7 @@ int nf_flow_prepare(const NfFlowDesc* desc, const float* params, void* packed_v,
     g.C = packed + kl.Winv; g.sC = kl.block_stride;
     NF_TRY(simt_gemm(g, st));
   }
+  if (kl.hi_off) NF_TRY(split_tables(packed, kl.hi_off, kl.lo_off, (int64_t)m.n * kl.block_stride, st));
   return 0;
   };
   return run_graphed(key, user_st, body);
@@ -883,6 +892,7 @@ int nf_flow_backward(const NfFlowDesc* desc, const float* params, const void* pa
       g.B0 = kb + kl.net0 + kl.W2fT; g.ldb0 = m.C; g.sB0 = kl.net_stride;
       g.C = wb.gB; g.ldc = m.H1; g.sC = B * Hm;
       g.M = (int)B; g.N = m.H1; g.batch = 2;
+      if (kl.hi_off) { g.B0hi = g.B0 + kl.hi_off; g.B0lo = g.B0 + kl.lo_off; }
       if (v2 && m.prec == NF_PREC_TF32X3 && m.C >= 32) {
         // f + g in one kernel: LayerNorm-1 / LeakyReLU-1 backward as the GEMM's row-wise epilogue; the bias
         // gradient (column sums of du1) is taken by the block's column-reduction launch
@@ -933,6 +943,7 @@ int nf_flow_backward(const NfFlowDesc* desc, const float* params, const void* pa
       if (!fused) NF_TRY(linear_nt(m.prec, g, st));
       if (dy && m.R > 0) {
         g.B0 += (int64_t)m.dc * m.H1; g.B1 += (int64_t)m.dc * m.H1;
+        if (kl.hi_off) { g.B0hi = g.B0 + kl.hi_off; g.B0lo = g.B0 + kl.lo_off; g.B1hi = g.B1 + kl.hi_off; g.B1lo = g.B1 + kl.lo_off; }
         g.C = dy; g.ldc = m.R; g.N = m.R;
         NF_TRY(linear_nt(m.prec, g, s2));
       }

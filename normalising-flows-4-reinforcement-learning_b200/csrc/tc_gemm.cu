@@ -47,6 +47,7 @@ struct KArgs {
   int ncl;                               // CTAs per cluster = N / BN (the cluster spans the whole row)
   long long* dbg;                        // optional: 8 clock64 timestamps per CTA (nf_debug_tc_timeline)
   int tma_store;                         // mC is valid: write the output tile with bulk tensor stores
+  int b_presplit;                        // TS form: mB0 / mB1 are the hi tables and mB0l / mB1l the lo tables of B
   // fused flow tail (EPI_LN_FWD on layer 2, D/2 <= 4, cluster (1, ncl, 2) = both nets): last Linear, affine
   // coupling, log-det and the neighbouring PLU matmul finished by the cluster's leader CTA (rowfused.cuh TailP)
   int tail, store_c;                     // store_c = 0: x_hat is not written (inference: nothing else reads it)
@@ -330,6 +331,7 @@ template <int BN, int STAGES, bool MNMAJOR, int BK, int EPI = EPI_NONE, bool TS 
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUtensorMap mA1,
           const __grid_constant__ CUtensorMap mB0, const __grid_constant__ CUtensorMap mB1,
+          const __grid_constant__ CUtensorMap mB0l, const __grid_constant__ CUtensorMap mB1l,
           const __grid_constant__ CUtensorMap mC, const KArgs a) {
   using S = Smem<BN, STAGES, BK>;
   constexpr int A_BYTES = S::A_BYTES;
@@ -392,6 +394,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
   if (threadIdx.x == 0) {
     prefetch_tmap(&mA0); prefetch_tmap(&mB0);
     if (a.tma_store) prefetch_tmap(&mC);
+    if (TS && a.b_presplit) { prefetch_tmap(&mB0l); if (nk1) prefetch_tmap(&mB1l); }
     if (nk1) { prefetch_tmap(&mA1); prefetch_tmap(&mB1); }
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&split[s], 4); mbar_init(&empty[s], 1); }
     mbar_init(accbar, 1);
@@ -423,7 +426,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
         __syncwarp();
         uint8_t* st = smem + s * S::STAGE;
         if (elect_one()) {
-          mbar_expect_tx(&full[s], S::HALF);
+          mbar_expect_tx(&full[s], S::HALF + ((TS && !MNMAJOR && a.b_presplit) ? S::B_BYTES : 0));
           if (MNMAJOR) {
             // operands are (K rows, M|N columns): one 32 x 32 box per 32-column group
             const int k0 = (kc_begin + it) * BK;
@@ -438,6 +441,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
             const int kk = (seg1 ? g - nk0 : g) * BK;
             tma_load_3d(st, seg1 ? &mA1 : &mA0, &full[s], kk, m0, (seg1 ? a.zA1 : a.zA0) ? z : 0);
             tma_load_3d(st + A_BYTES, seg1 ? &mB1 : &mB0, &full[s], kk, n0, (seg1 ? a.zB1 : a.zB0) ? z : 0);
+            if (TS && a.b_presplit)   // the lo tile lands where the in-kernel split would have put it
+              tma_load_3d(st + S::HALF + A_BYTES, seg1 ? &mB1l : &mB0l, &full[s], kk, n0, (seg1 ? a.zB1 : a.zB0) ? z : 0);
           }
         }
         __syncwarp();
@@ -550,10 +555,12 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
 #pragma unroll
           for (int c = 0; c < 4; ++c) av[c] = raw[r * 4 + (c ^ sw)];
         }
+        const bool split_b = MNMAJOR || !a.b_presplit;              // pre-split weights arrive as two TMA tiles
 #pragma unroll
-        for (int k = 0; k < PERB; ++k) bv[k] = raw[A4 + t + 128 * k];
+        for (int k = 0; k < PERB; ++k) bv[k] = split_b ? raw[A4 + t + 128 * k] : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int k = 0; k < PERB; ++k) {
+          if (!split_b) break;
           const int i = A4 + t + 128 * k;
           float4 h, l;
           if (a.raw_hi) {
@@ -588,6 +595,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
         tmem_st16(ta + BK, lo16);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        if (split_b) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> UMMA reads
       } else {
       // every load of the stage is issued before the first store: the in-place/aliased stores otherwise
       // serialise load -> store -> load and the splitters pace the MMAs (measured 800 cycles per stage
@@ -612,8 +620,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
         if (a.lo_round) { l.x = rna_tf32(l.x); l.y = rna_tf32(l.y); l.z = rna_tf32(l.z); l.w = rna_tf32(l.w); }
         lo[i] = l;
       }
-      }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> UMMA reads
+      }
       __syncwarp();
       if (lane == 0) mbar_arrive(&split[s]);
     }
@@ -1041,15 +1049,21 @@ int launch(const TcGemmP& p, cudaStream_t st) {
       configured = true;
     }
   }
-  CUtensorMap mA0, mA1, mB0, mB1;
+  CUtensorMap mA0, mA1, mB0, mB1, mB0l, mB1l;
   const CUtensorMapSwizzle swz = BK == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  // pre-split weight tables (hi / lo) feed the TS form directly
+  const bool pre = TS && option(NF_OPT_PRESPLIT) != 0 && p.B0hi && p.B0lo && (p.K1 <= 0 || (p.B1hi && p.B1lo));
   if ((r = make_map(&mA0, p.A0, p.K0, p.M, p.lda0, p.batch, p.sA0, BK, BM, swz))) return r;
-  if ((r = make_map(&mB0, p.B0, p.K0, p.N, p.ldb0, p.batch, p.sB0, BK, BN, swz))) return r;
+  if ((r = make_map(&mB0, pre ? p.B0hi : p.B0, p.K0, p.N, p.ldb0, p.batch, p.sB0, BK, BN, swz))) return r;
+  mB0l = mB0;
+  if (pre && (r = make_map(&mB0l, p.B0lo, p.K0, p.N, p.ldb0, p.batch, p.sB0, BK, BN, swz))) return r;
   if (p.K1 > 0) {
     if ((r = make_map(&mA1, p.A1, p.K1, p.M, p.lda1, p.batch, p.sA1, BK, BM, swz))) return r;
-    if ((r = make_map(&mB1, p.B1, p.K1, p.N, p.ldb1, p.batch, p.sB1, BK, BN, swz))) return r;
+    if ((r = make_map(&mB1, pre ? p.B1hi : p.B1, p.K1, p.N, p.ldb1, p.batch, p.sB1, BK, BN, swz))) return r;
+    mB1l = mB1;
+    if (pre && (r = make_map(&mB1l, p.B1lo, p.K1, p.N, p.ldb1, p.batch, p.sB1, BK, BN, swz))) return r;
   } else {
-    mA1 = mA0; mB1 = mB0;
+    mA1 = mA0; mB1 = mB0; mB1l = mB0l;
   }
   KArgs a{};
   a.C = p.C; a.bias = p.bias; a.M = p.M; a.N = p.N; a.K0 = p.K0; a.K1 = p.K1;
@@ -1075,7 +1089,8 @@ int launch(const TcGemmP& p, cudaStream_t st) {
   ProfScope prof(st, PROF_TC_GEMM, 2.0 * p.M * p.N * (double)(p.K0 + p.K1) * p.batch);
   CUtensorMap mC = mA0;
   a.tma_store = make_c_map(&mC, p.C, p.N, p.M, p.ldc, p.batch, p.sC) ? 1 : 0;
-  NF_LAUNCH((k_tc_gemm<BN, STAGES, false, BK, EPI_NONE, TS>), grid, NTHREADS, S::TOTAL, st, mA0, mA1, mB0, mB1, mC, a);
+  a.b_presplit = pre ? 1 : 0;
+  NF_LAUNCH((k_tc_gemm<BN, STAGES, false, BK, EPI_NONE, TS>), grid, NTHREADS, S::TOTAL, st, mA0, mA1, mB0, mB1, mB0l, mB1l, mC, a);
   NF_LAUNCHED();
   return 0;
 }
@@ -1090,15 +1105,21 @@ int launch_epi(const TcGemmP& p, cudaStream_t st) {
     configured = true;
   }
   int r;
-  CUtensorMap mA0, mA1, mB0, mB1;
+  CUtensorMap mA0, mA1, mB0, mB1, mB0l, mB1l;
   const CUtensorMapSwizzle swz = BK == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  // pre-split weight tables (hi / lo) feed the TS form directly
+  const bool pre = TS && option(NF_OPT_PRESPLIT) != 0 && p.B0hi && p.B0lo && (p.K1 <= 0 || (p.B1hi && p.B1lo));
   if ((r = make_map(&mA0, p.A0, p.K0, p.M, p.lda0, p.batch, p.sA0, BK, BM, swz))) return r;
-  if ((r = make_map(&mB0, p.B0, p.K0, p.N, p.ldb0, p.batch, p.sB0, BK, BN, swz))) return r;
+  if ((r = make_map(&mB0, pre ? p.B0hi : p.B0, p.K0, p.N, p.ldb0, p.batch, p.sB0, BK, BN, swz))) return r;
+  mB0l = mB0;
+  if (pre && (r = make_map(&mB0l, p.B0lo, p.K0, p.N, p.ldb0, p.batch, p.sB0, BK, BN, swz))) return r;
   if (p.K1 > 0) {
     if ((r = make_map(&mA1, p.A1, p.K1, p.M, p.lda1, p.batch, p.sA1, BK, BM, swz))) return r;
-    if ((r = make_map(&mB1, p.B1, p.K1, p.N, p.ldb1, p.batch, p.sB1, BK, BN, swz))) return r;
+    if ((r = make_map(&mB1, pre ? p.B1hi : p.B1, p.K1, p.N, p.ldb1, p.batch, p.sB1, BK, BN, swz))) return r;
+    mB1l = mB1;
+    if (pre && (r = make_map(&mB1l, p.B1lo, p.K1, p.N, p.ldb1, p.batch, p.sB1, BK, BN, swz))) return r;
   } else {
-    mA1 = mA0; mB1 = mB0;
+    mA1 = mA0; mB1 = mB0; mB1l = mB0l;
   }
   KArgs a{};
   a.C = p.C; a.bias = p.bias; a.M = p.M; a.N = p.N; a.K0 = p.K0; a.K1 = p.K1;
@@ -1135,7 +1156,8 @@ int launch_epi(const TcGemmP& p, cudaStream_t st) {
   ProfScope prof(st, PROF_TC_GEMM, 2.0 * p.M * p.N * (double)(p.K0 + p.K1) * p.batch);
   CUtensorMap mC = mA0;
   a.tma_store = make_c_map(&mC, p.C, p.N, p.M, p.ldc, p.batch, p.sC) ? 1 : 0;
-  NF_CUDA(cudaLaunchKernelEx(&cfg, k_tc_gemm<BN, STAGES, false, BK, EPI, TS>, mA0, mA1, mB0, mB1, mC, a));
+  a.b_presplit = pre ? 1 : 0;
+  NF_CUDA(cudaLaunchKernelEx(&cfg, k_tc_gemm<BN, STAGES, false, BK, EPI, TS>, mA0, mA1, mB0, mB1, mB0l, mB1l, mC, a));
   NF_LAUNCHED();
   return 0;
 }
@@ -1196,7 +1218,7 @@ int launch_tn(const TcGemmTnP& p, cudaStream_t st) {
   ProfScope prof(st, PROF_TC_WGRAD, 2.0 * p.M * p.N * (double)p.K * p.batch);
   CUtensorMap mC = mA;
   a.tma_store = make_c_map(&mC, p.C, p.N, p.M, p.ldc, p.batch, p.sC) ? 1 : 0;
-  NF_LAUNCH((k_tc_gemm<BN, STAGES, true, BK, EPI_NONE, TS>), grid, NTHREADS, S::TOTAL, st, mA, mA, mB, mB, mC, a);
+  NF_LAUNCH((k_tc_gemm<BN, STAGES, true, BK, EPI_NONE, TS>), grid, NTHREADS, S::TOTAL, st, mA, mA, mB, mB, mB, mB, mC, a);
   NF_LAUNCHED();
   return 0;
 }

@@ -35,6 +35,9 @@ struct TcGemmP {
   // K-major operands; the reduction may be two segments (A0|A1) x (B0|B1)
   const float* A0 = nullptr; const float* A1 = nullptr;
   const float* B0 = nullptr; const float* B1 = nullptr;
+  // optional pre-split copies of the B segments (hi = rna_tf32(B), lo = B - hi, same pitches and strides): the
+  // TS kernels then load both with the TMA and the splitter threads only handle the A rows
+  const float* B0hi = nullptr; const float* B0lo = nullptr; const float* B1hi = nullptr; const float* B1lo = nullptr;
   float* C = nullptr;
   const float* bias = nullptr;
   int M = 0, N = 0, K0 = 0, K1 = 0;
