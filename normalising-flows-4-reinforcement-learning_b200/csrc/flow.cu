@@ -474,6 +474,15 @@ int nf_flow_prepare(const NfFlowDesc* desc, const float* params, void* packed_v,
   key.op = 1; key.desc = *desc; key.flags = what; key.ws_bytes = ws_bytes;
   key.ptr[0] = params; key.ptr[1] = packed_v; key.ptr[2] = workspace;
   auto body = [&](cudaStream_t st) -> int {
+  // three independent chains (PLU tables | folded LayerNorm + its transpose | first-layer packings) run as parallel
+  // branches; the hi/lo split of all tables joins them
+  SideStreams* ss = side_streams();
+  cudaStream_t s1 = ss ? ss->s1 : st, s2 = ss ? ss->s2 : st;
+  if (ss) {
+    NF_CUDA(cudaEventRecord(ss->evA, st));
+    NF_CUDA(cudaStreamWaitEvent(s1, ss->evA, 0));
+    NF_CUDA(cudaStreamWaitEvent(s2, ss->evA, 0));
+  }
   NF_TRY(plu_mask(params, pl, m, packed, kl, st));
   {  // PL = P @ Lh
     GemmP g;
@@ -488,13 +497,13 @@ int nf_flow_prepare(const NfFlowDesc* desc, const float* params, void* packed_v,
     g.C = packed + kl.W;
     NF_TRY(simt_gemm(g, st));
   }
-  NF_TRY(fold_ln_affine(params, pl, m, packed, kl, st));
+  NF_TRY(fold_ln_affine(params, pl, m, packed, kl, s1));
   // K-major B operands of the data-gradient GEMMs: W2f^T (H1,C) and W1^T (K1,H1), per net and block
   NF_TRY(transpose2d(packed + kl.net0 + kl.W2fT, m.C, kl.net_stride, kl.block_stride, packed + kl.net0 + kl.W2f,
-                     m.H1, kl.net_stride, kl.block_stride, m.C, m.H1, 2, m.n, st));
+                     m.H1, kl.net_stride, kl.block_stride, m.C, m.H1, 2, m.n, s1));
   NF_TRY(transpose2d(packed + kl.net0 + kl.W1T, m.H1, kl.net_stride, kl.block_stride,
-                     params + pl.slot_off[NF_P_W1], m.K1, pl.net_stride, pl.block_stride, m.H1, m.K1, 2, m.n, st));
-  NF_TRY(pack_w1(params, pl, m, packed, kl, st));
+                     params + pl.slot_off[NF_P_W1], m.K1, pl.net_stride, pl.block_stride, m.H1, m.K1, 2, m.n, s2));
+  NF_TRY(pack_w1(params, pl, m, packed, kl, s2));
   if (what & NF_PREP_INV) {
     const PrepWs w = carve_prep(m, workspace);
     NF_TRY(plu_tri_inverse(packed, kl, m, w.uinv, w.linv, st));
@@ -508,6 +517,12 @@ int nf_flow_prepare(const NfFlowDesc* desc, const float* params, void* packed_v,
     g.B0 = params + pl.slot_off[NF_P_PINV]; g.sB0 = pl.block_stride;
     g.C = packed + kl.Winv; g.sC = kl.block_stride;
     NF_TRY(simt_gemm(g, st));
+  }
+  if (ss) {
+    NF_CUDA(cudaEventRecord(ss->done1[0], s1));
+    NF_CUDA(cudaEventRecord(ss->done2[0], s2));
+    NF_CUDA(cudaStreamWaitEvent(st, ss->done1[0], 0));
+    NF_CUDA(cudaStreamWaitEvent(st, ss->done2[0], 0));
   }
   if (kl.hi_off) NF_TRY(split_tables(packed, kl.hi_off, kl.lo_off, (int64_t)m.n * kl.block_stride, st));
   return 0;
