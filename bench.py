@@ -318,7 +318,7 @@ def run_ours(args):
         # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the class's heaviest member, the fused
         # layer-2 Linear (M=4096, N=256, K=256, both nets) -- ncu --set full, profiles/r1_ncu_full_forward_block_C2a.txt
         # (cold cache under ncu; algorithmic bytes: 8.4 MB in + 0.5 MB weights + 8.4 MB out)
-        "traffic": 8.99e6 if cfgname == "C2a" and B == 4096 else None, "traffic_unit": "bytes/launch",
+        "traffic": 9.52e6 if cfgname == "C2a" and B == 4096 else None, "traffic_unit": "bytes/launch",
         "peak_source": peaks["source"] + ", dense bf16 burst",
         "note": (f"algorithmic FLOPs (2MNK per launch, split-precision passes NOT counted) / mean launch duration over "
                  f"{d_n} launches; the kernel issues {passes} kind::tf32 MMAs per product at half the bf16 rate, so the "
