@@ -128,6 +128,17 @@ NF_API int nf_flow_backward(const NfFlowDesc* desc, const float* params, const v
                      float* dx, float* dy, float* dparams,
                      void* workspace, int64_t ws_bytes, void* stream);
 
+/* The same backward, block range [block_begin, block_end) only (the full pass is the ranges from the top block
+ * down, in order, with the same workspace and no other call in between): data-parallel training all-reduces the
+ * gradient slice of one range while the next range computes.  dz is read by the range that ends at n_blocks, dx / dy
+ * are written by the range that begins at 0, dparams is written for the range's blocks only. */
+NF_API int nf_flow_backward_range(const NfFlowDesc* desc, const float* params, const void* packed,
+                           const void* stash, const float* y, int64_t B,
+                           const float* dz, const float* dlogdet,
+                           float* dx, float* dy, float* dparams,
+                           int32_t block_begin, int32_t block_end,
+                           void* workspace, int64_t ws_bytes, void* stream);
+
 /* Standalone affine coupling + log-det kernels (HBM-bound; torch_fcnf.py:101-104, :112-113).
  *   fwd: z[:, :dc] = xp[:, :dc];  z[:, dc:] = (xp[:, dc:] - t) * exp(-s);  logdet += c - sum_j s
  *   inv: xp[:, dc:] = z[:, dc:] * exp(s) + t;                              logdet += sum_j s - c

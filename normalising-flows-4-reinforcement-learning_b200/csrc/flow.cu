@@ -748,10 +748,15 @@ int nf_flow_inverse(const NfFlowDesc* desc, const float* params, const void* pac
   return 0;
 }
 
-int nf_flow_backward(const NfFlowDesc* desc, const float* params, const void* packed_v, const void* stash_v,
-                     const float* y, int64_t B, const float* dz, const float* dlogdet, float* dx, float* dy,
-                     float* dparams, void* workspace, int64_t ws_bytes, void* stream) {
+int nf_flow_backward_range(const NfFlowDesc* desc, const float* params, const void* packed_v, const void* stash_v,
+                           const float* y, int64_t B, const float* dz, const float* dlogdet, float* dx, float* dy,
+                           float* dparams, int32_t block_begin, int32_t block_end, void* workspace, int64_t ws_bytes,
+                           void* stream) {
   NF_TRY(check_desc(desc));
+  NF_CHECK_ARG(block_begin >= 0 && block_begin < block_end && block_end <= desc->n_blocks, NF_E_BADARG,
+               "block range [%d, %d) outside [0, %d)", block_begin, block_end, desc->n_blocks);
+  const bool first_range = block_end == desc->n_blocks, last_range = block_begin == 0;
+  const int nr = block_end - block_begin;
   NF_CHECK_ARG(B >= 0 && B < (int64_t(1) << 30), NF_E_BADARG, "B=%lld out of range", (long long)B);
   NF_TRY(check_ptr(params, "params", true));
   NF_TRY(check_ptr(packed_v, "packed", true));
@@ -761,7 +766,7 @@ int nf_flow_backward(const NfFlowDesc* desc, const float* params, const void* pa
   param_layout(m, &pl);
   cudaStream_t user_st = reinterpret_cast<cudaStream_t>(stream);
   if (B == 0) {
-    if (dparams) NF_TRY(fill_zero(dparams, pl.total, user_st));
+    if (dparams) NF_TRY(fill_zero(dparams + (int64_t)block_begin * pl.block_stride, (int64_t)nr * pl.block_stride, user_st));
     return 0;
   }
   NF_TRY(check_ptr(stash_v, "stash", true));
@@ -783,13 +788,13 @@ int nf_flow_backward(const NfFlowDesc* desc, const float* params, const void* pa
   GraphKey key;
   key.op = 4; key.desc = *desc; key.B = B; key.ws_bytes = ws_bytes;
   key.ptr[0] = params; key.ptr[1] = packed_v; key.ptr[2] = stash_v; key.ptr[8] = dparams; key.ptr[9] = workspace;
-  key.flags = (dz ? 1 : 0) | (dlogdet ? 2 : 0) | (dx ? 4 : 0) | (dy ? 8 : 0);
+  key.flags = (dz ? 1 : 0) | (dlogdet ? 2 : 0) | (dx ? 4 : 0) | (dy ? 8 : 0) | (block_begin << 8) | (block_end << 20);
   // cotangents in, dx / dy out through the workspace; y is the copy forward left in the stash
   float* const dx_user = dx;
   float* const dy_user = dy;
   {
     CopySegs c;
-    c.add(w.io_dz, dz, BD);
+    if (first_range) c.add(w.io_dz, dz, BD);       // later ranges continue from the workspace
     c.add(w.io_dld, dlogdet, B);
     NF_TRY(copy_segments(c, user_st));
   }
@@ -799,22 +804,24 @@ int nf_flow_backward(const NfFlowDesc* desc, const float* params, const void* pa
   if (dy) dy = w.io_dy;
   y = stash + sl.y;
   auto body = [&](cudaStream_t st) -> int {
-  if (dparams) NF_TRY(fill_zero(dparams, pl.total, st));
-  if (dy) NF_TRY(fill_zero(dy, B * m.R, st));
+  if (dparams) NF_TRY(fill_zero(dparams + (int64_t)block_begin * pl.block_stride, (int64_t)nr * pl.block_stride, st));
+  if (dy && first_range) NF_TRY(fill_zero(dy, B * m.R, st));
   if (dparams) {
-    NF_TRY(fill_zero(w.dWs, m.n * DD, st));
+    NF_TRY(fill_zero(w.dWs + (int64_t)block_begin * DD, nr * DD, st));
     if (dlogdet) NF_TRY(sum_vector(dlogdet, B, w.sumdld, st));
     else NF_TRY(fill_zero(w.sumdld, 4, st));
   }
-  const float* gcur = dz;  // NULL means zero (handled inside the kernels)
-  int pp = 0;
+  // block i < n-1 reads the gradient block i+1 left in d0 / d1 (alternating from the top block down), also across
+  // range calls; the top block reads dz (NULL means zero, handled inside the kernels)
+  int pp = (m.n - block_end) & 1;
+  const float* gcur = first_range ? dz : (pp ? w.d0 : w.d1);
   const bool fused = use_row_fused(m);
   const bool v2 = fused && row_v2_supported(m.D, m.C, m.H1);
   SideStreams* ss = (v2 && (dparams || dy)) ? side_streams() : nullptr;
   cudaStream_t s1 = ss ? ss->s1 : st, s2 = ss ? ss->s2 : st;
   bool used1[2] = {false, false}, used2[2] = {false, false};
   struct { float *dxp, *dout, *gA, *gB; } w2[2] = {{w.dxp, w.dout, w.gA, w.gB}, {w.dxp2, w.dout2, w.gA2, w.gB2}};
-  for (int i = m.n - 1; i >= 0; --i) {
+  for (int i = block_end - 1; i >= block_begin; --i) {
     const int par = ss ? ((m.n - 1 - i) & 1) : 0;
     const auto& wb = w2[par];   // this block's intermediate buffers
     if (ss) {   // the side work of block i+2 read this buffer set
@@ -1050,33 +1057,47 @@ int nf_flow_backward(const NfFlowDesc* desc, const float* params, const void* pa
   }
   if (dparams) {
     GemmP g;  // T1 = P^T dW
-    g.transA = 1; g.A0 = params + pl.slot_off[NF_P_P]; g.lda0 = m.D; g.sA0 = pl.block_stride; g.K0 = m.D;
-    g.B0 = w.dWs; g.ldb0 = m.D; g.sB0 = DD;
-    g.C = w.T1; g.ldc = m.D; g.sC = DD; g.M = m.D; g.N = m.D; g.batch = m.n;
+    const float* prm = params + (int64_t)block_begin * pl.block_stride;
+    const float* pck = packed + (int64_t)block_begin * kl.block_stride;
+    float* dWr = w.dWs + (int64_t)block_begin * DD;
+    Dims mr = m;
+    mr.n = nr;   // the parameter-sized kernels below run over this range's blocks only
+    g.transA = 1; g.A0 = prm + pl.slot_off[NF_P_P]; g.lda0 = m.D; g.sA0 = pl.block_stride; g.K0 = m.D;
+    g.B0 = dWr; g.ldb0 = m.D; g.sB0 = DD;
+    g.C = w.T1; g.ldc = m.D; g.sC = DD; g.M = m.D; g.N = m.D; g.batch = nr;
     NF_TRY(simt_gemm(g, st));
     GemmP h;  // dLh = T1 Uh^T
     h.A0 = w.T1; h.lda0 = m.D; h.sA0 = DD; h.K0 = m.D;
-    h.B0 = packed + kl.Uh; h.ldb0 = m.D; h.sB0 = kl.block_stride; h.transB = 1;
-    h.C = w.dLh; h.ldc = m.D; h.sC = DD; h.M = m.D; h.N = m.D; h.batch = m.n;
+    h.B0 = pck + kl.Uh; h.ldb0 = m.D; h.sB0 = kl.block_stride; h.transB = 1;
+    h.C = w.dLh; h.ldc = m.D; h.sC = DD; h.M = m.D; h.N = m.D; h.batch = nr;
     NF_TRY(simt_gemm(h, st));
     GemmP u;  // dUh = (P Lh)^T dW
-    u.transA = 1; u.A0 = packed + kl.PL; u.lda0 = m.D; u.sA0 = kl.block_stride; u.K0 = m.D;
-    u.B0 = w.dWs; u.ldb0 = m.D; u.sB0 = DD;
-    u.C = w.dUh; u.ldc = m.D; u.sC = DD; u.M = m.D; u.N = m.D; u.batch = m.n;
+    u.transA = 1; u.A0 = pck + kl.PL; u.lda0 = m.D; u.sA0 = kl.block_stride; u.K0 = m.D;
+    u.B0 = dWr; u.ldb0 = m.D; u.sB0 = DD;
+    u.C = w.dUh; u.ldc = m.D; u.sC = DD; u.M = m.D; u.N = m.D; u.batch = nr;
     NF_TRY(simt_gemm(u, st));
-    NF_TRY(plu_grad_finish(params, pl, m, w.dLh, w.dUh, w.sumdld, dparams, st));
-    NF_TRY(unfold_grads(params, pl, m, dparams, st));
+    float* dpr = dparams + (int64_t)block_begin * pl.block_stride;
+    NF_TRY(plu_grad_finish(prm, pl, mr, w.dLh, w.dUh, w.sumdld, dpr, st));
+    NF_TRY(unfold_grads(prm, pl, mr, dpr, st));
   }
   return 0;
   };
   NF_TRY(run_graphed(key, user_st, body));
-  {
+  if (last_range) {
     CopySegs c;
     c.add(dx_user, dx, BD);
     c.add(dy_user, dy, B * m.R);
     NF_TRY(copy_segments(c, user_st));
   }
   return 0;
+}
+
+int nf_flow_backward(const NfFlowDesc* desc, const float* params, const void* packed_v, const void* stash_v,
+                     const float* y, int64_t B, const float* dz, const float* dlogdet, float* dx, float* dy,
+                     float* dparams, void* workspace, int64_t ws_bytes, void* stream) {
+  NF_TRY(check_desc(desc));
+  return nf_flow_backward_range(desc, params, packed_v, stash_v, y, B, dz, dlogdet, dx, dy, dparams, 0, desc->n_blocks,
+                                workspace, ws_bytes, stream);
 }
 
 int nf_linear(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, float* C, int64_t ldc,
