@@ -291,11 +291,10 @@ def run_ours(args):
     prof = _lib.prof_collect()
     _lib.lib.nf_prof_enable(0)
 
-    if world > 1:
-        dist.barrier()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        # wait for rank 0 (CPU baseline, JSON line) and leave the process group together with it
+        dist.barrier()
+        dist.destroy_process_group()
         return
 
     peaks = load_peaks()
@@ -365,6 +364,7 @@ def run_ours(args):
     }
     print(json.dumps(out), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -429,13 +429,15 @@ class RealNVP(nn.Module):
             if need_p:
                 dflat = out if out is not None else torch.empty(self._layout.total, dtype=torch.float32, device=dev)
             ptr = lambda t: t.data_ptr() if t is not None else None
-            if need_p and self._dp_world > 1:
+            if need_p and self._dp_world > 1 and int(self.dp_bucket_blocks) > 0:
                 self._backward_overlapped(stash, packed, y, B, dz, dld, dx, dy, dflat, ws, dev)
             else:
                 _lib.check(lib.nf_flow_backward(
                     ctypes.byref(self._desc), self._flat.data_ptr(), packed.data_ptr(), stash.data_ptr(), y.data_ptr(),
                     B, ptr(dz), ptr(dld), ptr(dx), ptr(dy), ptr(dflat), ws.data_ptr(), ws.numel(), self._stream(dev)),
                     "nf_flow_backward")
+                if need_p and self._dp_world > 1:
+                    self._allreduce_grads(dflat)
         return dx, dy, dflat
 
     def _run_backward_fast(self, stash, packed, y, B, dz, dld, need_x, need_y, need_p):
@@ -510,7 +512,7 @@ class RealNVP(nn.Module):
         avg = dist.get_backend(self._dp_group) == "nccl"
         handles = []
         end = n
-        bucket = int(self.dp_bucket_blocks) if int(self.dp_bucket_blocks) > 0 else n
+        bucket = int(self.dp_bucket_blocks)
         while end > 0:
             begin = max(0, end - bucket)
             _lib.check(lib.nf_flow_backward_range(
