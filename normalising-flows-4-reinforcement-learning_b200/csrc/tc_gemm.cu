@@ -306,12 +306,15 @@ __device__ __forceinline__ float rna_tf32(float x) {
   return __uint_as_float(r);
 }
 
-template <int BN, int STAGES, int BK>
+template <int BN, int STAGES, int BK, bool TS = false>
 struct Smem {
   static constexpr int A_BYTES = BM * BK * 4;
   static constexpr int B_BYTES = BN * BK * 4;
   static constexpr int HALF = A_BYTES + B_BYTES;   // raw/hi tiles; the lo twins follow
-  static constexpr int STAGE = 2 * HALF;
+  // SS form: [A | B | A lo | B lo]; TS form: [A | B | B lo] (A's halves live in tensor memory), which buys two more
+  // stages of TMA prefetch in the same shared memory.  The lo twin of tile byte o sits at LO + o in both.
+  static constexpr int LO = TS ? B_BYTES : HALF;
+  static constexpr int STAGE = TS ? A_BYTES + 2 * B_BYTES : 2 * HALF;
   static constexpr int BARS = STAGES * STAGE;      // byte offset of the barrier block
   static constexpr int XCHG = BARS + 512;          // [kMaxCluster][128] float2 partial row statistics (epilogue kernels)
   static constexpr int TOTAL = BARS + 512 + 1024;  // + alignment slack
@@ -333,7 +336,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
           const __grid_constant__ CUtensorMap mB0, const __grid_constant__ CUtensorMap mB1,
           const __grid_constant__ CUtensorMap mB0l, const __grid_constant__ CUtensorMap mB1l,
           const __grid_constant__ CUtensorMap mC, const KArgs a) {
-  using S = Smem<BN, STAGES, BK>;
+  using S = Smem<BN, STAGES, BK, TS>;
   constexpr int A_BYTES = S::A_BYTES;
   constexpr int BOX = 32 * BK * 4;   // bytes of one 32-column MN-major TMA box
   extern __shared__ uint8_t smem_dyn[];
@@ -442,7 +445,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
             tma_load_3d(st, seg1 ? &mA1 : &mA0, &full[s], kk, m0, (seg1 ? a.zA1 : a.zA0) ? z : 0);
             tma_load_3d(st + A_BYTES, seg1 ? &mB1 : &mB0, &full[s], kk, n0, (seg1 ? a.zB1 : a.zB0) ? z : 0);
             if (TS && a.b_presplit)   // the lo tile lands where the in-kernel split would have put it
-              tma_load_3d(st + S::HALF + A_BYTES, seg1 ? &mB1l : &mB0l, &full[s], kk, n0, (seg1 ? a.zB1 : a.zB0) ? z : 0);
+              tma_load_3d(st + S::LO + A_BYTES, seg1 ? &mB1l : &mB0l, &full[s], kk, n0, (seg1 ? a.zB1 : a.zB0) ? z : 0);
           }
         }
         __syncwarp();
@@ -478,8 +481,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
           nks = kleft >= BK ? BK / 8 : (kleft + 7) / 8;
         }
         const uint32_t sa = (smem_u32(smem + s * S::STAGE) & 0x3FFFFu) >> 4;
-        uint32_t la_hi = dlo + sa, lb_hi = la_hi + (A_BYTES >> 4), la_lo = la_hi + (S::HALF >> 4),
-                 lb_lo = lb_hi + (S::HALF >> 4);
+        uint32_t la_hi = dlo + sa, lb_hi = la_hi + (A_BYTES >> 4), la_lo = la_hi + (S::LO >> 4),
+                 lb_lo = lb_hi + (S::LO >> 4);
         if (lane == 0) mbar_wait(&split[s], use & 1);
         __syncwarp();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -537,7 +540,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
       mbar_wait(&full[s], use & 1);
       if (threadIdx.x == 64 && it == 0) NF_TS(2);   // first operand tile landed
       float4* raw = reinterpret_cast<float4*>(smem + s * S::STAGE);
-      float4* lo = reinterpret_cast<float4*>(smem + s * S::STAGE + S::HALF);
+      float4* lo = reinterpret_cast<float4*>(smem + s * S::STAGE + S::LO);
       if constexpr (TS) {
         // B tile: split in shared memory as in the SS form; A tile: this thread's row -> tensor memory
         constexpr int A4 = A_BYTES / 16, PERB = S::B_BYTES / 16 / 128;
@@ -1039,7 +1042,7 @@ int pick_nacc(int total_k8) {
 
 template <int BN, int STAGES, int BK, bool TS = false>
 int launch(const TcGemmP& p, cudaStream_t st) {
-  using S = Smem<BN, STAGES, BK>;
+  using S = Smem<BN, STAGES, BK, TS>;
   int r;
   {
     static bool configured = false;
@@ -1097,7 +1100,7 @@ int launch(const TcGemmP& p, cudaStream_t st) {
 
 template <int BN, int STAGES, int BK, int EPI, bool TS = false>
 int launch_epi(const TcGemmP& p, cudaStream_t st) {
-  using S = Smem<BN, STAGES, BK>;
+  using S = Smem<BN, STAGES, BK, TS>;
   static bool configured = false;
   if (!configured) {
     NF_CUDA(cudaFuncSetAttribute(k_tc_gemm<BN, STAGES, false, BK, EPI, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1166,15 +1169,15 @@ template <int EPI>
 int launch_epi_pick(const TcGemmP& p, cudaStream_t st) {
   const bool ts = option(NF_OPT_TS) != 0;
   if (p.N % 128 == 0 && p.N / 128 <= kMaxCluster) {
-    if (ts) return launch_epi<128, 6, 16, EPI, true>(p, st);
+    if (ts) return launch_epi<128, 8, 16, EPI, true>(p, st);
     return launch_epi<128, 6, 16, EPI>(p, st);
   }
-  return ts ? launch_epi<64, 8, 16, EPI, true>(p, st) : launch_epi<64, 8, 16, EPI>(p, st);
+  return ts ? launch_epi<64, 12, 16, EPI, true>(p, st) : launch_epi<64, 8, 16, EPI>(p, st);
 }
 
 template <int BN, int STAGES, int BK, bool TS = false>
 int launch_tn(const TcGemmTnP& p, cudaStream_t st) {
-  using S = Smem<BN, STAGES, BK>;
+  using S = Smem<BN, STAGES, BK, TS>;
   int r;
   {
     static bool configured = false;
@@ -1285,10 +1288,10 @@ int tc_gemm(const TcGemmP& p, cudaStream_t st) {
   if (p.N > 128 && ctas256 >= 120) return launch<256, 4, 16>(p, st);
   const bool ts = option(NF_OPT_TS) != 0;
   if (p.N > 64) {
-    if (ts) return launch<128, 6, 16, true>(p, st);
+    if (ts) return launch<128, 8, 16, true>(p, st);
     return launch<128, 6, 16>(p, st);
   }
-  return ts ? launch<64, 8, 16, true>(p, st) : launch<64, 8, 16>(p, st);
+  return ts ? launch<64, 12, 16, true>(p, st) : launch<64, 8, 16>(p, st);
 }
 
 bool tc_gemm_tn_supported(const TcGemmTnP& p) {
@@ -1304,7 +1307,7 @@ int tc_gemm_tn(const TcGemmTnP& p, cudaStream_t st) {
   const int wide_ok = option(NF_OPT_BN256);
   if (wide_ok != 1) {
     if (p.bk == 32) return p.N > 64 ? launch_tn<128, 3, 32>(p, st) : launch_tn<64, 4, 32>(p, st);
-    if (option(NF_OPT_TS) != 0) return p.N > 64 ? launch_tn<128, 6, 16, true>(p, st) : launch_tn<64, 8, 16, true>(p, st);
+    if (option(NF_OPT_TS) != 0) return p.N > 64 ? launch_tn<128, 8, 16, true>(p, st) : launch_tn<64, 12, 16, true>(p, st);
     return p.N > 64 ? launch_tn<128, 6, 16>(p, st) : launch_tn<64, 8, 16>(p, st);
   }
   if (p.bk == 32) {
