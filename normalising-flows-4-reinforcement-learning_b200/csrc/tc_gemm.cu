@@ -330,8 +330,12 @@ struct Smem {
 // only the B operand comes from shared memory (64 KB per stage).  The ring takes 128 TMEM columns, so 128-wide
 // tiles rotate over two main accumulators instead of three (all golden cases, C5 with K = 1024 included, stay
 // inside the parity contract).
-template <int BN, int STAGES, bool MNMAJOR, int BK, int EPI = EPI_NONE, bool TS = false>
-__global__ void __launch_bounds__(NTHREADS, 1)
+// NSG = splitter groups of four warps.  One group needs ~1 100 cycles per 16-deep stage (wait for the tile 120, load +
+// split 320, wait for the TMEM slot 300, tcgen05.st + wait + fences + arrive 340 -- a chain of fixed latencies, measured
+// with clock64) against 384 cycles of MMAs, so the plain kernels run two groups on alternating stages; both groups
+// share the epilogue (alternating 32-column chunks).
+template <int BN, int STAGES, bool MNMAJOR, int BK, int EPI = EPI_NONE, bool TS = false, int NSG = 1>
+__global__ void __launch_bounds__(64 + 128 * NSG, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUtensorMap mA1,
           const __grid_constant__ CUtensorMap mB0, const __grid_constant__ CUtensorMap mB1,
           const __grid_constant__ CUtensorMap mB0l, const __grid_constant__ CUtensorMap mB1l,
@@ -468,25 +472,29 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
       const uint32_t rot_end = tmem_base + (uint32_t)nacc_rt * BN;
       uint32_t tmem_main = tmem_base, acc_c = 0, fresh = (uint32_t)nacc_rt;   // `fresh` mains not written yet
       const bool merge = a.merge_corr != 0, three = a.passes == 3;
+      // The tensor pipe accepts MMAs about as fast as it executes them (measured: 6 issues take 360-390 cycles, and
+      // with every wait removed a stage still took 690 cycles of which 330 were this loop's own bookkeeping), so
+      // whatever this warp does between two issue bursts is tensor-pipe idle time.  Everything is strength-reduced:
+      // stage index / phase / descriptor word / TMEM slot are wrapping counters, the K tail is a running remainder,
+      // the issuing lane is elected once.
+      const bool leader = elect_one();
+      const uint32_t lo0 = dlo + ((smem_u32(smem) & 0x3FFFFu) >> 4);          // descriptor low word of stage 0's A tile
+      uint32_t st_lo = lo0;
+      int s = 0;
+      uint32_t ph = 0;
+      uint32_t ta_slot = tmem_base + A_BASE;                                     // TS: first column of the current A slot
+      const uint32_t ta_end = tmem_base + A_BASE + kASlots * 2 * BK;
+      int aslot = 0;
+      int g = kc_begin;                                                           // global chunk index (K-major: over both segments)
+      int kleft = MNMAJOR ? (int)min((long long)a.K0 - (long long)kc_begin * BK, (long long)0x7fffffff)
+                          : (g >= nk0 ? a.K1 - (g - nk0) * BK : a.K0 - g * BK);
       for (int it = 0; it < nk; ++it) {
-        const int s = it % STAGES, use = it / STAGES;
-        int nks;
-        if (MNMAJOR) {
-          const long long kleft = (long long)a.K0 - (long long)(kc_begin + it) * BK;
-          nks = kleft >= BK ? BK / 8 : (int)((kleft + 7) / 8);
-        } else {
-          const int g = kc_begin + it;
-          const bool seg1 = g >= nk0;
-          const int kleft = (seg1 ? a.K1 - (g - nk0) * BK : a.K0 - g * BK);
-          nks = kleft >= BK ? BK / 8 : (kleft + 7) / 8;
-        }
-        const uint32_t sa = (smem_u32(smem + s * S::STAGE) & 0x3FFFFu) >> 4;
-        uint32_t la_hi = dlo + sa, lb_hi = la_hi + (A_BYTES >> 4), la_lo = la_hi + (S::LO >> 4),
-                 lb_lo = lb_hi + (S::LO >> 4);
-        if (lane == 0) mbar_wait(&split[s], use & 1);
+        const int nks = kleft >= BK ? BK / 8 : (kleft + 7) >> 3;
+        if (lane == 0) mbar_wait(&split[s], ph);
         __syncwarp();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const bool leader = elect_one();
+        uint32_t la_hi = st_lo, lb_hi = st_lo + (A_BYTES >> 4), la_lo = st_lo + (S::LO >> 4),
+                 lb_lo = st_lo + ((A_BYTES + S::LO) >> 4);
 #pragma unroll
         for (int ks = 0; ks < BK / 8; ++ks) {
           if (ks < nks) {
@@ -494,7 +502,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
             const uint64_t a_lo = (static_cast<uint64_t>(dhi) << 32) | la_lo, b_lo = (static_cast<uint64_t>(dhi) << 32) | lb_lo;
             uint32_t acc_m = fresh == 0 ? 1u : 0u;
             if constexpr (TS) {
-              const uint32_t ta_hi = tmem_base + A_BASE + (uint32_t)(it % kASlots) * 2 * BK + (uint32_t)ks * 8, ta_lo = ta_hi + BK;
+              const uint32_t ta_hi = ta_slot + (uint32_t)ks * 8, ta_lo = ta_hi + BK;
               if (leader) {
                 if (three) {
                   umma_tf32_ts(tmem_corr, ta_lo, b_hi, idesc, acc_c);
@@ -525,17 +533,25 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
         }
         if (leader) {
           umma_commit(&empty[s]);   // frees the stage once the MMAs above have read it
-          if (TS) umma_commit(&aempty[it % kASlots]);
+          if (TS) umma_commit(&aempty[aslot]);
         }
-        __syncwarp();
+        // next stage
+        kleft -= BK;
+        if (!MNMAJOR && ++g == nk0) kleft = a.K1;
+        st_lo += S::STAGE >> 4;
+        if (++s == STAGES) { s = 0; ph ^= 1u; st_lo = lo0; }
+        ta_slot += 2 * BK;
+        if (++aslot == kASlots) { aslot = 0; ta_slot = tmem_base + A_BASE; }
       }
+      (void)ta_end;
       if (elect_one()) umma_commit(accbar);        // accumulator complete
       __syncwarp();
     }
   } else {
     // ------------------------------------------------------------------ splitters, then epilogue
-    const int t = threadIdx.x - 64;  // 0..127
-    for (int it = 0; it < nk; ++it) {
+    const int t = (threadIdx.x - 64) & 127;       // 0..127 inside the splitter group
+    const int grp = (threadIdx.x - 64) >> 7;      // splitter group: takes the stages with it % NSG == grp
+    for (int it = grp; it < nk; it += NSG) {
       const int s = it % STAGES, use = it / STAGES;
       mbar_wait(&full[s], use & 1);
       if (threadIdx.x == 64 && it == 0) NF_TS(2);   // first operand tile landed
@@ -904,6 +920,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
     // bound by the 64 B/clk TMEM read path, not by the LSU; the fused epilogues keep the transposition)
     for (int c0 = 0; c0 < BN; c0 += 32) {
       if (n0 + c0 >= a.N) break;   // warp-uniform
+      if (NSG > 1 && ((c0 >> 5) % NSG) != grp) continue;   // the splitter groups share the epilogue chunk by chunk
       float rf[32];
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c0);
       tmem_ld_sum<BN, NACC>(taddr, nacc_used, with_corr, rf);
@@ -1043,11 +1060,12 @@ int pick_nacc(int total_k8) {
 template <int BN, int STAGES, int BK, bool TS = false>
 int launch(const TcGemmP& p, cudaStream_t st) {
   using S = Smem<BN, STAGES, BK, TS>;
+  constexpr int NSG = TS ? 2 : 1;
   int r;
   {
     static bool configured = false;
     if (!configured) {
-      NF_CUDA(cudaFuncSetAttribute(k_tc_gemm<BN, STAGES, false, BK, EPI_NONE, TS>,
+      NF_CUDA(cudaFuncSetAttribute(k_tc_gemm<BN, STAGES, false, BK, EPI_NONE, TS, NSG>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
       configured = true;
     }
@@ -1093,7 +1111,7 @@ int launch(const TcGemmP& p, cudaStream_t st) {
   CUtensorMap mC = mA0;
   a.tma_store = make_c_map(&mC, p.C, p.N, p.M, p.ldc, p.batch, p.sC) ? 1 : 0;
   a.b_presplit = pre ? 1 : 0;
-  NF_LAUNCH((k_tc_gemm<BN, STAGES, false, BK, EPI_NONE, TS>), grid, NTHREADS, S::TOTAL, st, mA0, mA1, mB0, mB1, mB0l, mB1l, mC, a);
+  NF_LAUNCH((k_tc_gemm<BN, STAGES, false, BK, EPI_NONE, TS, NSG>), grid, 64 + 128 * NSG, S::TOTAL, st, mA0, mA1, mB0, mB1, mB0l, mB1l, mC, a);
   NF_LAUNCHED();
   return 0;
 }
@@ -1178,11 +1196,12 @@ int launch_epi_pick(const TcGemmP& p, cudaStream_t st) {
 template <int BN, int STAGES, int BK, bool TS = false>
 int launch_tn(const TcGemmTnP& p, cudaStream_t st) {
   using S = Smem<BN, STAGES, BK, TS>;
+  constexpr int NSG = TS ? 2 : 1;
   int r;
   {
     static bool configured = false;
     if (!configured) {
-      NF_CUDA(cudaFuncSetAttribute(k_tc_gemm<BN, STAGES, true, BK, EPI_NONE, TS>,
+      NF_CUDA(cudaFuncSetAttribute(k_tc_gemm<BN, STAGES, true, BK, EPI_NONE, TS, NSG>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
       configured = true;
     }
@@ -1221,7 +1240,7 @@ int launch_tn(const TcGemmTnP& p, cudaStream_t st) {
   ProfScope prof(st, PROF_TC_WGRAD, 2.0 * p.M * p.N * (double)p.K * p.batch);
   CUtensorMap mC = mA;
   a.tma_store = make_c_map(&mC, p.C, p.N, p.M, p.ldc, p.batch, p.sC) ? 1 : 0;
-  NF_LAUNCH((k_tc_gemm<BN, STAGES, true, BK, EPI_NONE, TS>), grid, NTHREADS, S::TOTAL, st, mA, mA, mB, mB, mB, mB, mC, a);
+  NF_LAUNCH((k_tc_gemm<BN, STAGES, true, BK, EPI_NONE, TS, NSG>), grid, 64 + 128 * NSG, S::TOTAL, st, mA, mA, mB, mB, mB, mB, mC, a);
   NF_LAUNCHED();
   return 0;
 }

@@ -13,7 +13,7 @@ NAMES = ["prologue", "first tile", "mainloop(split)", "mma drain", "tmem->regs (
 def run(M, N, K, engine=4, reps=3):
     A = torch.randn(M, K, device=dev); W = torch.randn(N, K, device=dev) / K ** 0.5; C = torch.empty(M, N, device=dev)
     ctas = ((M + 127) // 128) * ((N + 127) // 128) * 4
-    buf = torch.zeros(ctas * 8, dtype=torch.int64, device=dev)
+    buf = torch.zeros(ctas * 16, dtype=torch.int64, device=dev)
     for _ in range(reps):
         lib.nf_linear(A.data_ptr(), K, W.data_ptr(), K, None, C.data_ptr(), N, M, N, K, engine, st)
     torch.cuda.synchronize()
@@ -23,9 +23,14 @@ def run(M, N, K, engine=4, reps=3):
     lib.nf_linear(A.data_ptr(), K, W.data_ptr(), K, None, C.data_ptr(), N, M, N, K, engine, st)
     e1.record(); torch.cuda.synchronize()
     lib.nf_debug_tc_timeline(None)
-    t = buf.view(-1, 8).cpu()
+    t = buf.view(-1, 16).cpu()
     t = t[t[:, 0] != 0]
-    d = (t[:, 1:] - t[:, :-1]).double()
+    d = (t[:, 1:8] - t[:, :7]).double()
+    if (t[:, 8] != 0).any():
+        names = ['mbar_wait(split)', 'syncwarp', 'fence + elect', '6 MMA issue', '2 commits + syncwarp', 'rest of loop (to next top)']
+        for i, nm in enumerate(names):
+            v = (t[:, 9 + i] - t[:, 8 + i]).double()
+            print(f'    MMA warp stage 8: {nm:36s} {v.mean():8.0f}  (min {v.min():6.0f} max {v.max():6.0f})')
     # plain epilogue: slots 5, 6 unused -> fold
     print(f"M={M} N={N} K={K}: {e0.elapsed_time(e1)*1e3:.1f} us event, {len(t)} CTAs; mean cycles per phase:")
     tot = (t[:, 7] - t[:, 0]).double()
@@ -37,6 +42,4 @@ def run(M, N, K, engine=4, reps=3):
     print(f"    {'total in CTA':18s} {tot.mean():9.0f} cycles = {tot.mean()/1.965e3:.2f} us at 1965 MHz")
 
 if __name__ == "__main__":
-    run(4096, 256, 256)
-    run(4096, 256, 72)
-    run(8192, 512, 512)
+    run(8192, 1024, 1024)
