@@ -488,13 +488,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
       int g = kc_begin;                                                           // global chunk index (K-major: over both segments)
       int kleft = MNMAJOR ? (int)min((long long)a.K0 - (long long)kc_begin * BK, (long long)0x7fffffff)
                           : (g >= nk0 ? a.K1 - (g - nk0) * BK : a.K0 - g * BK);
-      for (int it = 0; it < nk; ++it) {
-        const int nks = kleft >= BK ? BK / 8 : (kleft + 7) >> 3;
-        if (lane == 0) mbar_wait(&split[s], ph);
-        __syncwarp();
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        uint32_t la_hi = st_lo, lb_hi = st_lo + (A_BYTES >> 4), la_lo = st_lo + (S::LO >> 4),
-                 lb_lo = st_lo + ((A_BYTES + S::LO) >> 4);
+      // one stage worth of MMAs (3 per k8 step): lo*hi and hi*lo into corr, hi*hi into the rotating main accumulator
+      auto issue_stage = [&](uint32_t lo, uint32_t ta, int nks) {
+        uint32_t la_hi = lo, lb_hi = lo + (A_BYTES >> 4), la_lo = lo + (S::LO >> 4), lb_lo = lo + ((A_BYTES + S::LO) >> 4);
 #pragma unroll
         for (int ks = 0; ks < BK / 8; ++ks) {
           if (ks < nks) {
@@ -502,7 +498,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
             const uint64_t a_lo = (static_cast<uint64_t>(dhi) << 32) | la_lo, b_lo = (static_cast<uint64_t>(dhi) << 32) | lb_lo;
             uint32_t acc_m = fresh == 0 ? 1u : 0u;
             if constexpr (TS) {
-              const uint32_t ta_hi = ta_slot + (uint32_t)ks * 8, ta_lo = ta_hi + BK;
+              const uint32_t ta_hi = ta + (uint32_t)ks * 8, ta_lo = ta_hi + BK;
               if (leader) {
                 if (three) {
                   umma_tf32_ts(tmem_corr, ta_lo, b_hi, idesc, acc_c);
@@ -531,17 +527,54 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
             la_hi += kStep; lb_hi += kStep; la_lo += kStep; lb_lo += kStep;
           }
         }
+      };
+      // two stages per loop trip: both barriers are awaited first, then 12 MMAs go out back to back, so the fixed
+      // cost of a trip (barrier poll, warp sync, proxy fence, commits, counters) is paid once per 768 MMA cycles
+      for (int it = 0; it < nk; it += 2) {
+        const bool two = it + 1 < nk;
+        const int nks0 = kleft >= BK ? BK / 8 : (kleft + 7) >> 3;
+        int kleft1 = kleft - BK;
+        if (!MNMAJOR && g + 1 == nk0) kleft1 = a.K1;
+        const int nks1 = kleft1 >= BK ? BK / 8 : (kleft1 + 7) >> 3;
+        const bool wrap = s + 1 == STAGES;
+        const int s1 = wrap ? 0 : s + 1;
+        const uint32_t ph1 = wrap ? ph ^ 1u : ph;
+        const uint32_t lo1 = wrap ? lo0 : st_lo + (S::STAGE >> 4);
+        const bool awrap = aslot + 1 == kASlots;
+        const int aslot1 = awrap ? 0 : aslot + 1;
+        const uint32_t ta1 = awrap ? tmem_base + A_BASE : ta_slot + 2 * BK;
+        if (lane == 0) {
+          mbar_wait(&split[s], ph);
+          if (two) mbar_wait(&split[s1], ph1);
+        }
+        __syncwarp();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        issue_stage(st_lo, ta_slot, nks0);
         if (leader) {
           umma_commit(&empty[s]);   // frees the stage once the MMAs above have read it
           if (TS) umma_commit(&aempty[aslot]);
         }
-        // next stage
-        kleft -= BK;
-        if (!MNMAJOR && ++g == nk0) kleft = a.K1;
-        st_lo += S::STAGE >> 4;
-        if (++s == STAGES) { s = 0; ph ^= 1u; st_lo = lo0; }
-        ta_slot += 2 * BK;
-        if (++aslot == kASlots) { aslot = 0; ta_slot = tmem_base + A_BASE; }
+        if (two) {
+          issue_stage(lo1, ta1, nks1);
+          if (leader) {
+            umma_commit(&empty[s1]);
+            if (TS) umma_commit(&aempty[aslot1]);
+          }
+        }
+        // advance two stages
+        kleft = kleft1 - BK;
+        g += 2;
+        if (!MNMAJOR && g == nk0) kleft = a.K1;
+        s = s1; ph = ph1; st_lo = lo1; aslot = aslot1; ta_slot = ta1;
+        {
+          const bool w2 = s + 1 == STAGES;
+          st_lo = w2 ? lo0 : st_lo + (S::STAGE >> 4);
+          if (w2) ph ^= 1u;
+          s = w2 ? 0 : s + 1;
+          const bool aw2 = aslot + 1 == kASlots;
+          ta_slot = aw2 ? tmem_base + A_BASE : ta_slot + 2 * BK;
+          aslot = aw2 ? 0 : aslot + 1;
+        }
       }
       (void)ta_end;
       if (elect_one()) umma_commit(accbar);        // accumulator complete
