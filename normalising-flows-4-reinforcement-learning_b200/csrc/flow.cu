@@ -1113,13 +1113,11 @@ int nf_linear(const float* A, int64_t lda, const float* W, int64_t ldw, const fl
     g.C = C; g.ldc = (int)ldc; g.bias = bias; g.M = (int)M; g.N = N;
     return simt_gemm(g, st);
   }
-  NF_CHECK_ARG(engine == NF_PREC_TF32X3 || (engine >= 3 && engine <= 8), NF_E_UNSUPPORTED, "unknown engine %d", engine);
+  NF_CHECK_ARG(engine == NF_PREC_TF32X3 || (engine >= 3 && engine <= 6), NF_E_UNSUPPORTED, "unknown engine %d", engine);
   TcGemmP t;
   t.A0 = A; t.lda0 = lda; t.K0 = K; t.B0 = W; t.ldb0 = ldw; t.C = C; t.ldc = ldc; t.bias = bias;
   t.M = (int)M; t.N = N; t.passes = engine == 3 ? 1 : 3; t.raw_hi = (engine == 4 || engine == 6 || engine == 3);
   t.bk = (engine == 5 || engine == 6) ? 32 : 16;
-  if (engine == 7) { t.raw_hi = 0; t.lo_round = 1; }   // experiments: rounded lo
-  if (engine == 8) { t.raw_hi = 1; t.lo_round = 1; }
   return tc_gemm(t, st);
 }
 

@@ -1,19 +1,22 @@
 // tcgen05 / TMEM / TMA GEMM for the conditioner layers (sm_100a).  See tc_gemm.cuh.
 //
-// Roles inside one CTA (192 threads), one 128 x BN output tile per CTA:
-//   warp 0      TMA producer: fp32 operand tiles (128 B rows, SWIZZLE_128B) -> shared memory ring
-//   warps 2..5  splitters: hi = cvt.rna.tf32(x) written in place, lo = x - hi written to a twin
-//               buffer (same swizzled positions), then the epilogue (TMEM -> registers -> global)
-//   warp 1      MMA issuer: one thread issues tcgen05.mma kind::tf32 (lo*hi, hi*lo, hi*hi) with
-//               the fp32 accumulator in TMEM; owns tcgen05.alloc/dealloc
-// Pipelines: full[s] (TMA -> splitters), split[s] (splitters -> MMA), empty[s] (MMA commit ->
-// producer), acc (MMA commit -> epilogue).
-// Two fp32 accumulators live in TMEM: `main` takes only the hi*hi products, `corr` the two small
-// cross terms; the tensor core's accumulate step truncates, so keeping the 2^-11-sized terms out
-// of the main accumulator cuts the rounding drift of a long reduction by 3x.  They are summed in
-// the epilogue.
-// MNMAJOR = true is the weight-gradient form (both operands MN-major, reduction over batch rows,
-// split-K with red.global.add).
+// One 128 x BN output tile per CTA; fp32 parity through the 3xTF32 split (lo*hi, hi*lo, hi*hi).
+//   warp 0        TMA producer: operand tiles -> shared-memory ring (SWIZZLE_64B / 128B); pre-split weight
+//                 tables arrive as two tiles (hi, lo)
+//   warp 1        MMA issuer: the whole warp runs the loop with warp-uniform operands, one elected lane issues
+//                 tcgen05.mma kind::tf32 and the commits; owns tcgen05.alloc / dealloc
+//   warps 2..5    splitter group 0 (and 6..9 = group 1 in the plain TS kernels, alternating stages): thread = tile
+//                 row = TMEM lane.  TS form: reads its row of the A tile, writes hi / lo to a 4-slot TMEM ring
+//                 (tcgen05.st), splits B in shared memory only when it is not pre-split.  SS form: splits both
+//                 tiles in shared memory (hi in place, lo to a twin).  Then the epilogue.
+// Barriers: full[s] (TMA -> splitters), split[s] (splitters -> MMA), empty[s] (MMA commit -> producer),
+// aempty[i] (MMA commit -> splitters, TMEM A slot i), accbar (MMA commit -> epilogue), xbar / tbar (cluster).
+// Accumulators in TMEM: the hi*hi products rotate over NACC `main` accumulators, the cross terms go to `corr`
+// (the tensor core truncates when it accumulates: fewer sequential adds per accumulator = less drift); the
+// epilogue adds them with round-to-nearest.
+// Epilogues: plain (bias / accumulate / split-K reduce-add through bulk tensor stores), EPI_LN_FWD and
+// EPI_LN_BWD (LeakyReLU + LayerNorm forward / backward over a CTA cluster spanning the row, optional fused
+// flow tail).  MNMAJOR = true is the weight-gradient form (reduction over the batch rows, split-K).
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -36,8 +39,8 @@ struct KArgs {
   int M, N, K0, K1;
   long long ldc, sC, sBias;
   int zA0, zA1, zB0, zB1;  // 1: operand is batched over blockIdx.z, 0: shared
-  int accumulate, passes, raw_hi, lo_round;
-  int nacc, merge_corr;           // main accumulators in rotation (1..NACC); cross terms share the main accumulator
+  int accumulate, passes, raw_hi;
+  int nacc;                       // main accumulators in rotation, 0 = all NACC (option "nacc")
   int splitk, chunks_per_split;   // MN-major form only
   // row-wise epilogues over the cluster (EPI_LN_FWD / EPI_LN_BWD)
   float* rstd; long long sRstd;          // fwd: out (row), bwd: in
@@ -392,11 +395,11 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
     }
   }
   // Rotating over all NACC accumulators is also FASTER than using fewer (measured: 840 vs 940-1100 cycles per
-  // 16-deep stage): back-to-back MMAs into one accumulator serialise on it.  a.nacc / a.merge_corr stay as
-  // experiment knobs (NF_B200_NACC); the default is the full rotation with a separate corr accumulator.
+  // 16-deep stage): back-to-back MMAs into one accumulator serialise on it.  The "nacc" option
+  // (tests, experiments) can lower the count; the default is the full rotation with a separate corr accumulator.
   const int nacc_rt = a.nacc < 1 ? NACC : (a.nacc > NACC ? NACC : a.nacc);
   const int nacc_used = total_k8 < nacc_rt ? total_k8 : nacc_rt;
-  const bool with_corr = a.passes == 3 && !a.merge_corr;
+  const bool with_corr = a.passes == 3;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&mA0); prefetch_tmap(&mB0);
@@ -471,7 +474,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
       constexpr uint32_t kStep = MNMAJOR ? (1024u >> 4) : (32u >> 4);   // next k8 block inside a stage
       const uint32_t rot_end = tmem_base + (uint32_t)nacc_rt * BN;
       uint32_t tmem_main = tmem_base, acc_c = 0, fresh = (uint32_t)nacc_rt;   // `fresh` mains not written yet
-      const bool merge = a.merge_corr != 0, three = a.passes == 3;
+      const bool three = a.passes == 3;
       // The tensor pipe accepts MMAs about as fast as it executes them (measured: 6 issues take 360-390 cycles, and
       // with every wait removed a stage still took 690 cycles of which 330 were this loop's own bookkeeping), so
       // whatever this warp does between two issue bursts is tensor-pipe idle time.  Everything is strength-reduced:
@@ -509,14 +512,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
             } else
             if (leader) {
               if (three) {
-                if (merge) {
-                  umma_tf32(tmem_main, a_lo, b_hi, idesc, acc_m);
-                  umma_tf32(tmem_main, a_hi, b_lo, idesc, 1u);
-                  acc_m = 1;
-                } else {
-                  umma_tf32(tmem_corr, a_lo, b_hi, idesc, acc_c);
-                  umma_tf32(tmem_corr, a_hi, b_lo, idesc, 1u);
-                }
+                umma_tf32(tmem_corr, a_lo, b_hi, idesc, acc_c);
+                umma_tf32(tmem_corr, a_hi, b_lo, idesc, 1u);
               }
               umma_tf32(tmem_main, a_hi, b_hi, idesc, acc_m);
             }
@@ -669,7 +666,6 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
           raw[i] = h;
         }
         l.x = v[k].x - h.x; l.y = v[k].y - h.y; l.z = v[k].z - h.z; l.w = v[k].w - h.w;
-        if (a.lo_round) { l.x = rna_tf32(l.x); l.y = rna_tf32(l.y); l.z = rna_tf32(l.z); l.w = rna_tf32(l.w); }
         lo[i] = l;
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> UMMA reads
@@ -1082,13 +1078,7 @@ int set_smem() {
   return 0;
 }
 
-// accumulate-truncation budget: one main accumulator per 32 k8 steps (K = 256), at most 3; reductions of up to
-// 12 k8 steps (K <= 96) keep the cross terms in the main accumulator (3 truncations per step, still < 40)
-constexpr int kMergeCorrK8 = 12;
-int pick_nacc(int total_k8) {
-  (void)total_k8;
-  return option(NF_OPT_NACC);   // 0 = kernel default (all NACC accumulators)
-}
+int pick_nacc() { return option(NF_OPT_NACC); }   // 0 = kernel default (all NACC accumulators)
 
 template <int BN, int STAGES, int BK, bool TS = false>
 int launch(const TcGemmP& p, cudaStream_t st) {
@@ -1123,7 +1113,7 @@ int launch(const TcGemmP& p, cudaStream_t st) {
   a.C = p.C; a.bias = p.bias; a.M = p.M; a.N = p.N; a.K0 = p.K0; a.K1 = p.K1;
   a.ldc = p.ldc; a.sC = p.sC; a.sBias = p.sBias;
   a.zA0 = p.sA0 != 0; a.zA1 = p.sA1 != 0; a.zB0 = p.sB0 != 0; a.zB1 = p.sB1 != 0;
-  a.accumulate = p.accumulate; a.passes = p.passes; a.raw_hi = p.raw_hi; a.lo_round = p.lo_round;
+  a.accumulate = p.accumulate; a.passes = p.passes; a.raw_hi = p.raw_hi;
   // split the reduction over CTAs when the output is accumulated anyway (C already holds the base value) and
   // the tile grid leaves most of the 148 SMs idle: the dy GEMM of C2a (M = 4096, N = 64, K = 512) ran on 32
   // CTAs for 37 us
@@ -1138,7 +1128,7 @@ int launch(const TcGemmP& p, cudaStream_t st) {
   splitk = cdiv(nchunks, per);
   a.splitk = (int)splitk; a.chunks_per_split = (int)per;
   a.dbg = g_tc_dbg;
-  a.nacc = pick_nacc(0); a.merge_corr = 0;
+  a.nacc = pick_nacc();
   dim3 grid((unsigned)cdiv(p.M, BM), (unsigned)cdiv(p.N, BN), (unsigned)(p.batch * splitk));
   ProfScope prof(st, PROF_TC_GEMM, 2.0 * p.M * p.N * (double)(p.K0 + p.K1) * p.batch);
   CUtensorMap mC = mA0;
@@ -1179,13 +1169,10 @@ int launch_epi(const TcGemmP& p, cudaStream_t st) {
   a.C = p.C; a.bias = p.bias; a.M = p.M; a.N = p.N; a.K0 = p.K0; a.K1 = p.K1;
   a.ldc = p.ldc; a.sC = p.sC; a.sBias = p.sBias;
   a.zA0 = p.sA0 != 0; a.zA1 = p.sA1 != 0; a.zB0 = p.sB0 != 0; a.zB1 = p.sB1 != 0;
-  a.accumulate = 0; a.passes = p.passes; a.raw_hi = p.raw_hi; a.lo_round = p.lo_round;
+  a.accumulate = 0; a.passes = p.passes; a.raw_hi = p.raw_hi;
   a.splitk = 1; a.chunks_per_split = 0;
   a.dbg = g_tc_dbg;
-  {
-    const int total_k8 = (p.K0 + 7) / 8 + (p.K1 + 7) / 8;
-    a.nacc = pick_nacc(total_k8); a.merge_corr = 0 * (total_k8 <= kMergeCorrK8);
-  }
+  a.nacc = pick_nacc();
   a.rstd = p.epi.rstd; a.sRstd = p.epi.sRstd; a.mask = p.epi.mask; a.sMask = p.epi.sMask; a.mw = p.epi.mw;
   a.xh = p.epi.xh; a.ldxh = p.epi.ldxh; a.sXh = p.epi.sXh; a.eps = p.epi.eps;
   a.ncl = p.N / BN;
@@ -1262,13 +1249,10 @@ int launch_tn(const TcGemmTnP& p, cudaStream_t st) {
   a.K0 = (int)p.K; a.K1 = 0;
   a.ldc = p.ldc; a.sC = p.sC; a.sBias = 0;
   a.zA0 = p.sA != 0; a.zB0 = p.sB != 0; a.zA1 = a.zB1 = 0;
-  a.accumulate = 1; a.passes = p.passes; a.raw_hi = 0; a.lo_round = p.lo_round;
+  a.accumulate = 1; a.passes = p.passes; a.raw_hi = 0;
   a.splitk = (int)splitk; a.chunks_per_split = (int)per;
   a.dbg = g_tc_dbg;
-  {
-    const int total_k8 = (int)(per * BK / 8);
-    a.nacc = pick_nacc(total_k8); a.merge_corr = 0 * (total_k8 <= kMergeCorrK8);
-  }
+  a.nacc = pick_nacc();
   dim3 grid((unsigned)cdiv(p.M, BM), (unsigned)cdiv(p.N, BN), (unsigned)(splitk * p.batch));
   ProfScope prof(st, PROF_TC_WGRAD, 2.0 * p.M * p.N * (double)p.K * p.batch);
   CUtensorMap mC = mA;

@@ -48,7 +48,6 @@ struct TcGemmP {
   int passes = 3;       // 3 = 3xTF32 (fp32 parity), 1 = single TF32 pass
   int raw_hi = 1;       // feed the raw fp32 tile as the hi operand (the tensor core ignores the low 13 bits):
                         // lo = x - trunc_tf32(x); saves one shared-memory store per element (measured +10%)
-  int lo_round = 0;     // round lo to tf32 (nearest) instead of letting the tensor core truncate it
   int bk = 16;          // reduction elements per pipeline stage: 16 or 32
   TcEpi epi;            // optional fused row-wise epilogue (see tc_gemm_epi_supported)
 };
@@ -64,7 +63,6 @@ struct TcGemmTnP {
   int batch = 1;
   int splitk = 0;                            // 0 = choose
   int passes = 3;
-  int lo_round = 0;
   int bk = 16;
 };
 int tc_gemm_tn(const TcGemmTnP& p, cudaStream_t st);
