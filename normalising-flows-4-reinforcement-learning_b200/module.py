@@ -26,6 +26,24 @@ from . import _lib
 from ._lib import lib
 
 
+class _NoSwitch:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+_NO_SWITCH = _NoSwitch()
+
+
+def _on(dev):
+    """``torch.cuda.device(dev)`` only when ``dev`` is not already the current device."""
+    if dev.index is None or dev.index == torch.cuda.current_device():
+        return _NO_SWITCH
+    return torch.cuda.device(dev)
+
+
 def _dense(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
     """Contiguous and 16-byte aligned (the C ABI's contract); row slices of a tensor are contiguous
     but can start at any float, so those are copied."""
@@ -345,7 +363,10 @@ class RealNVP(nn.Module):
             raise RuntimeError("module parameters must be float32 on the same device as the inputs")
 
     def _stream(self, device):
-        return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+        # the raw handle of torch's current stream on that device (what current_stream().cuda_stream returns,
+        # without building a Stream object: this runs several times per step)
+        return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(device.index if device.index is not None
+                                                                  else torch.cuda.current_device()))
 
     def _workspace(self, B, device):
         need = lib.nf_flow_workspace_bytes(ctypes.byref(self._desc), B)
@@ -378,7 +399,7 @@ class RealNVP(nn.Module):
         B, D, n = x.shape[0], self.in_channels, self.n_layers
         x = _dense(x)
         y = _dense(y)
-        with torch.cuda.device(dev):
+        with _on(dev):
             packed = self._prepared(_lib.NF_PREP_FWD, dev)
             ws = self._workspace(B, dev)
             z = torch.empty((B, D), dtype=torch.float32, device=dev)
@@ -420,7 +441,7 @@ class RealNVP(nn.Module):
     def _run_backward(self, stash, packed, y, B, dz, dld, need_x, need_y, need_p, out=None):
         dev = y.device
         D, R = self.in_channels, self.cond_channels
-        with torch.cuda.device(dev):
+        with _on(dev):
             ws = self._workspace(B, dev)
             dz, dld, y = _dense(dz), _dense(dld), _dense(y)
             dx = torch.empty((B, D), dtype=torch.float32, device=dev) if need_x else None
@@ -552,7 +573,7 @@ class RealNVP(nn.Module):
         B, D, n = x.shape[0], self.in_channels, self.n_layers
         x = _dense(x.detach())
         y = _dense(y.detach())
-        with torch.cuda.device(dev):
+        with _on(dev):
             packed = self._prepared(_lib.NF_PREP_FWD | _lib.NF_PREP_INV, dev)
             ws = self._workspace(B, dev)
             out = torch.empty((B, D), dtype=torch.float32, device=dev)

@@ -17,6 +17,7 @@ import torch
 
 from . import _lib
 from ._lib import lib
+from .module import _on
 
 
 class FlatAdamW(torch.optim.Optimizer):
@@ -69,7 +70,7 @@ class FlatAdamW(torch.optim.Optimizer):
                         g[off:off + p.numel()].copy_(p.grad.reshape(-1))
             st = self._flow_state(flow)
             st["step"] += 1
-            with torch.cuda.device(flow._flat.device):
+            with _on(flow._flat.device):
                 _lib.check(lib.nf_adamw_step(
                     ctypes.byref(flow._desc), flow._flat.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(),
                     st["exp_avg_sq"].data_ptr(), st["mask"].data_ptr(), float(lr), float(b1), float(b2), float(eps),
