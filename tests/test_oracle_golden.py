@@ -86,3 +86,27 @@ def test_reverse_inverts_forward_and_reverse_logdet():
     xr, ldr = fo.flow_reverse(sd, n, z, y, return_logdet=True)
     assert np.max(np.abs(xr - x)) < 1e-9
     assert np.max(np.abs(ldr + ld)) < 1e-9
+
+
+@pytest.mark.parametrize("path", [p for p in CASES if "synth_C1a" in p or "synth_C2a" in p or "refinit_d9" in p],
+                         ids=lambda p: os.path.basename(p)[:-4])
+def test_torch_restatement_matches_reference(path):
+    """oracle/torch_flow.py (the stock-PyTorch bar of tools/eager_bar.py) against the same fixtures, in float64."""
+    import torch
+    from oracle.torch_flow import TorchFlow
+    cfg, sd, x, y, dz, dld, g = load_case(path)
+    m = TorchFlow(cfg["D"], cfg["C"], cfg["R"], cfg["n"], first_hidden=cfg.get("H1"), ln_eps=cfg.get("ln_eps", 1e-5))
+    m.load_state_dict({k: torch.tensor(v) for k, v in sd.items()})
+    m = m.double()
+    xt = torch.tensor(x, dtype=torch.float64, requires_grad=True)
+    yt = torch.tensor(y, dtype=torch.float64, requires_grad=True)
+    z, outs, ld = m(xt, yt)
+    ((z * torch.tensor(dz, dtype=torch.float64)).sum() + (ld * torch.tensor(dld, dtype=torch.float64)).sum()).backward()
+    assert rel_err(z.detach().numpy(), g["f64/z"]) <= 1e-10
+    assert rel_err(ld.detach().numpy(), g["f64/log_dets"]) <= 1e-10
+    assert rel_err(torch.stack(outs).detach().numpy(), g["f64/outputs"]) <= 1e-10
+    assert rel_err(xt.grad.numpy(), g["f64/dx"]) <= 1e-9
+    assert rel_err(yt.grad.numpy(), g["f64/dy"]) <= 1e-9
+    with torch.no_grad():
+        rev = m.reverse(torch.tensor(g["f64/z"]), yt)
+    assert rel_err(rev.numpy(), g["f64/rev"]) <= 1e-8
