@@ -184,6 +184,32 @@ NF_API int nf_adamw_step(const NfFlowDesc* desc, float* params, const float* gra
                          const unsigned char* slot_mask, float lr, float beta1, float beta2, float eps,
                          float weight_decay, int64_t step, void* stream);
 
+/* ---- conditioning encoder ---------------------------------------------------------
+ * The MLP that produces the flow's conditioning input y in every reference caller (GEncoder,
+ * torch_fcnf.py:154-190): n_hidden x [Linear -> LayerNorm(affine) -> SiLU] followed by one Linear.  The reference
+ * fixes hidden = 512 and n_hidden = 4; both are free here (hidden % 4 == 0, hidden <= 1024, n_hidden <= 8).
+ * Parameter arena (fp32, offsets from nf_encoder_param_layout, every slot 16-byte aligned): for hidden layer i
+ *   offs[4 i + 0] Linear weight (hidden, in_i) row-major (nn.Linear layout), offs[4 i + 1] Linear bias (hidden),
+ *   offs[4 i + 2] LayerNorm weight (hidden), offs[4 i + 3] LayerNorm bias (hidden);
+ * then offs[4 n_hidden] output weight (out_features, hidden) and offs[4 n_hidden + 1] output bias.
+ * Forward writes `out` (B, out_features) and, when `stash` is given, what backward needs.  Backward takes
+ * dout (B, out_features), writes dparams (same layout as params, overwritten) and optionally dg (B, in_features).
+ * Same conventions as the flow calls: caller-owned buffers, workspace passed in, asynchronous on `stream`. */
+typedef struct NfEncoderDesc {
+  int32_t in_features, hidden, out_features, n_hidden;
+  float ln_eps;      /* 1e-5 (torch) / 1e-6 (flax, nf.py:188-212) */
+  int32_t precision; /* NF_PREC_* */
+} NfEncoderDesc;
+#define NF_ENC_MAX_HIDDEN_LAYERS 8
+NF_API int64_t nf_encoder_param_layout(const NfEncoderDesc* desc, int64_t* offs);  /* returns total floats, < 0 on error */
+NF_API int64_t nf_encoder_stash_bytes(const NfEncoderDesc* desc, int64_t B);
+NF_API int64_t nf_encoder_workspace_bytes(const NfEncoderDesc* desc, int64_t B);
+NF_API int nf_encoder_forward(const NfEncoderDesc* desc, const float* params, const float* g, int64_t B, float* out,
+                              void* stash, void* workspace, int64_t ws_bytes, void* stream);
+NF_API int nf_encoder_backward(const NfEncoderDesc* desc, const float* params, const float* g, const void* stash,
+                               int64_t B, const float* dout, float* dg, float* dparams, void* workspace,
+                               int64_t ws_bytes, void* stream);
+
 /* Optional per-kernel-class timing (CUDA events on the launching stream; off by default).  Kinds:
  * 0 tcgen05 GEMM, 1 tcgen05 weight-gradient GEMM, 2 FFMA GEMM, 3 LeakyReLU+LayerNorm fwd, 4 its backward,
  * 5 affine coupling kernels, 6 parameter-sized kernels, 7 row-fused forward/inverse tail, 8 row-fused

@@ -25,6 +25,11 @@ class NfFlowDesc(Structure):
                 ("ln_eps", c_float), ("precision", c_int32), ("reserved", c_int32)]
 
 
+class NfEncoderDesc(Structure):
+    _fields_ = [("in_features", c_int32), ("hidden", c_int32), ("out_features", c_int32), ("n_hidden", c_int32),
+                ("ln_eps", c_float), ("precision", c_int32)]
+
+
 class NfParamLayout(Structure):
     _fields_ = [("slot_off", c_int64 * NF_P_SLOTS), ("slot_numel", c_int64 * NF_P_SLOTS),
                 ("block_stride", c_int64), ("net_stride", c_int64), ("total", c_int64)]
@@ -41,6 +46,7 @@ def _load():
         build()
     lib = ctypes.CDLL(LIB_PATH)
     D = POINTER(NfFlowDesc)
+    E = POINTER(NfEncoderDesc)
     fp, vp, i64 = c_void_p, c_void_p, c_int64   # device pointers are passed as integers
     sigs = {
         "nf_abi_version": (c_int, []),
@@ -66,6 +72,11 @@ def _load():
         "nf_nll_forward": (c_int, [fp, fp, i64, c_int32, fp, vp]),
         "nf_nll_cotangents": (c_int, [fp, fp, i64, c_int32, fp, fp, vp]),
         "nf_adamw_step": (c_int, [D, fp, fp, fp, fp, fp, c_float, c_float, c_float, c_float, c_float, i64, vp]),
+        "nf_encoder_param_layout": (c_int64, [E, POINTER(c_int64)]),
+        "nf_encoder_stash_bytes": (c_int64, [E, i64]),
+        "nf_encoder_workspace_bytes": (c_int64, [E, i64]),
+        "nf_encoder_forward": (c_int, [E, fp, fp, i64, fp, vp, vp, i64, vp]),
+        "nf_encoder_backward": (c_int, [E, fp, fp, vp, i64, fp, fp, fp, vp, i64, vp]),
         "nf_set_option": (c_int, [c_char_p, c_int]),
         "nf_get_option": (c_int, [c_char_p]),
         "nf_graphs_enable": (c_int, [c_int]),

@@ -36,6 +36,22 @@ int64_t& launch_counter();
     NF_CUDA(cudaPeekAtLastError());      \
   } while (0)
 
+#define NF_TRY(expr)            \
+  do {                          \
+    int _r = (expr);            \
+    if (_r != 0) return _r;     \
+  } while (0)
+
+// the C ABI's pointer contract: 16-byte aligned, NULL only where the argument is optional
+static inline int check_ptr(const void* p, const char* name, bool required) {
+  if (!p) {
+    NF_CHECK_ARG(!required, NF_E_BADARG, "%s is NULL", name);
+    return 0;
+  }
+  NF_CHECK_ARG((reinterpret_cast<uintptr_t>(p) & 15u) == 0, NF_E_ALIGN, "%s is not 16-byte aligned", name);
+  return 0;
+}
+
 // ---- run-time options (nf_set_option / NF_B200_<NAME> environment variables) ------------------------------
 enum NfOpt {
   NF_OPT_PDL = 0,        // programmatic dependent launch on every kernel                       (default 1)

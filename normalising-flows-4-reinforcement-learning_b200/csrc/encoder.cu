@@ -1,0 +1,407 @@
+// Conditioning encoder: n_hidden x [Linear -> LayerNorm(affine) -> SiLU] -> Linear, the
+// module that produces the flow's y in every reference caller (GEncoder, torch_fcnf.py:154-190; flax twin
+// nf.py:188-212 with eps 1e-6).  The Linears and their data / weight gradients go through the same dispatch as
+// the flow's conditioner layers (tcgen05 3xTF32, FFMA for odd pitches); the row-wise part is two kernels here:
+//   k_enc_ln_silu_fwd  x_hat = LN_noaffine(u), h = SiLU(gamma x_hat + beta)            (warp per row, 128-bit accesses)
+//   k_enc_ln_silu_bwd  du from dh, plus the column sums d gamma, d beta, d bias        (registers -> smem -> atomics)
+// SiLU follows the affine LayerNorm, so -- unlike the flow's LeakyReLU -> LN -> Linear -- gamma / beta cannot be
+// folded into the next Linear.
+#include <algorithm>
+
+#include "common.cuh"
+#include "elementwise.cuh"
+#include "linear.cuh"
+
+namespace nf {
+namespace {
+
+constexpr int kEncMaxV = 8;   // float4 per lane: hidden <= 1024
+
+struct EncDims {
+  int in, H, out, L, prec;
+  float eps;
+};
+
+int check_enc(const NfEncoderDesc* d) {
+  NF_CHECK_ARG(d != nullptr, NF_E_BADARG, "encoder desc is NULL");
+  NF_CHECK_ARG(d->in_features >= 1 && d->out_features >= 1, NF_E_BADARG, "encoder: in_features=%d out_features=%d",
+               d->in_features, d->out_features);
+  NF_CHECK_ARG(d->hidden >= 4 && d->hidden % 4 == 0 && d->hidden <= 128 * kEncMaxV, NF_E_UNSUPPORTED,
+               "encoder: hidden=%d must be a multiple of 4, at most %d", d->hidden, 128 * kEncMaxV);
+  NF_CHECK_ARG(d->n_hidden >= 1 && d->n_hidden <= NF_ENC_MAX_HIDDEN_LAYERS, NF_E_UNSUPPORTED,
+               "encoder: n_hidden=%d out of range", d->n_hidden);
+  NF_CHECK_ARG(d->ln_eps > 0.f, NF_E_BADARG, "encoder: ln_eps must be positive");
+  NF_CHECK_ARG(d->precision >= 0 && d->precision <= 1, NF_E_BADARG, "encoder: unknown precision %d", d->precision);
+  return 0;
+}
+
+EncDims enc_dims(const NfEncoderDesc* d) {
+  return EncDims{d->in_features, d->hidden, d->out_features, d->n_hidden, d->precision, d->ln_eps};
+}
+
+struct EncLayout {
+  int64_t w[NF_ENC_MAX_HIDDEN_LAYERS], b[NF_ENC_MAX_HIDDEN_LAYERS], lw[NF_ENC_MAX_HIDDEN_LAYERS],
+      lb[NF_ENC_MAX_HIDDEN_LAYERS];
+  int64_t wo, bo, total;
+};
+
+EncLayout enc_layout(const EncDims& m) {
+  EncLayout l{};
+  int64_t off = 0;
+  auto take = [&](int64_t n) { int64_t o = off; off += pad4(n); return o; };
+  for (int i = 0; i < m.L; ++i) {
+    l.w[i] = take((int64_t)m.H * (i == 0 ? m.in : m.H));
+    l.b[i] = take(m.H);
+    l.lw[i] = take(m.H);
+    l.lb[i] = take(m.H);
+  }
+  l.wo = take((int64_t)m.out * m.H);
+  l.bo = take(m.out);
+  l.total = off;
+  return l;
+}
+
+// stash: per hidden layer x_hat (B,H), h (B,H), rstd (B)
+struct EncStash {
+  int64_t xh, h, rstd, layer_stride, total;
+};
+EncStash enc_stash(const EncDims& m, int64_t B) {
+  EncStash s{};
+  s.xh = 0; s.h = B * m.H; s.rstd = 2 * B * m.H;
+  s.layer_stride = 2 * B * m.H + pad4(B);
+  s.total = s.layer_stride * m.L;
+  return s;
+}
+
+// workspace: two (B,H) activation buffers, one transposed weight
+struct EncWs {
+  int64_t a, b, wt, total;
+};
+EncWs enc_ws(const EncDims& m, int64_t B) {
+  EncWs w{};
+  w.a = 0; w.b = pad4(B * m.H); w.wt = 2 * pad4(B * m.H);
+  w.total = w.wt + pad4((int64_t)m.H * std::max(std::max(m.H, m.in), m.out));
+  return w;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// x_hat = (u - mean) / sqrt(var + eps) in place, h = SiLU(gamma x_hat + beta)     (torch_fcnf.py:172-174)
+template <int NV>
+__global__ void __launch_bounds__(256) k_enc_ln_silu_fwd(float* __restrict__ xh, float* __restrict__ h,
+                                                         float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, long long B, int H, float eps) {
+  NF_PDL_ENTRY();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long row = (long long)blockIdx.x * 8 + warp;
+  if (row >= B) return;
+  float4* xr = reinterpret_cast<float4*>(xh + row * H);
+  float4 v[NV];
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int c4 = lane + 32 * k;
+    v[k] = 4 * c4 < H ? xr[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+    sum += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+  }
+  const float mean = warp_sum(sum) / (float)H;
+  float m2 = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    if (4 * (lane + 32 * k) < H) {
+      const float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, d = v[k].w - mean;
+      m2 += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+  const float rs = 1.0f / sqrtf(warp_sum(m2) / (float)H + eps);
+  float4* hr = reinterpret_cast<float4*>(h + row * H);
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int c4 = lane + 32 * k;
+    if (4 * c4 < H) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+      float4 x, o;
+      x.x = (v[k].x - mean) * rs; x.y = (v[k].y - mean) * rs; x.z = (v[k].z - mean) * rs; x.w = (v[k].w - mean) * rs;
+      const float a0 = fmaf(x.x, g.x, b.x), a1 = fmaf(x.y, g.y, b.y), a2 = fmaf(x.z, g.z, b.z), a3 = fmaf(x.w, g.w, b.w);
+      o.x = a0 / (1.0f + expf(-a0)); o.y = a1 / (1.0f + expf(-a1));
+      o.z = a2 / (1.0f + expf(-a2)); o.w = a3 / (1.0f + expf(-a3));
+      xr[c4] = x;
+      hr[c4] = o;
+    }
+  }
+  if (lane == 0 && rstd) rstd[row] = rs;
+}
+
+// g: dh in, du out (in place).  a = gamma x_hat + beta, da = dh SiLU'(a), d x_hat = da gamma,
+// du = rstd (d x_hat - mean(d x_hat) - x_hat mean(d x_hat x_hat));  column sums over the CTA's rows:
+// dgamma += da x_hat, dbeta += da, dbias += du.
+template <int NV>
+__global__ void __launch_bounds__(256) k_enc_ln_silu_bwd(float* __restrict__ g, const float* __restrict__ xh,
+                                                         const float* __restrict__ rstd,
+                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                         float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                         float* __restrict__ dbias, long long B, int H, int rows_per_cta) {
+  extern __shared__ float red[];   // [3][H]
+  NF_PDL_ENTRY();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  float4 gm[NV], bt[NV], ag[NV], ab[NV], au[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int c4 = lane + 32 * k;
+    const bool ok = 4 * c4 < H;
+    gm[k] = ok ? __ldg(reinterpret_cast<const float4*>(gamma) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    bt[k] = ok ? __ldg(reinterpret_cast<const float4*>(beta) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    ag[k] = ab[k] = au[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const long long r0 = (long long)blockIdx.x * rows_per_cta;
+  const long long r1 = min(B, r0 + rows_per_cta);
+  const float invH = 1.0f / (float)H;
+  for (long long row = r0 + warp; row < r1; row += 8) {
+    float4* gr = reinterpret_cast<float4*>(g + row * H);
+    const float4* xr = reinterpret_cast<const float4*>(xh + row * H);
+    float4 dh[NV], x[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c4 = lane + 32 * k;
+      const bool ok = 4 * c4 < H;
+      dh[k] = ok ? gr[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+      x[k] = ok ? __ldg(xr + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float rs = rstd[row];
+    float s1 = 0.f, s2 = 0.f;
+    float4 da[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      auto one = [&](float d, float xx, float gg, float bb) {
+        const float a = fmaf(xx, gg, bb);
+        const float sg = 1.0f / (1.0f + expf(-a));
+        return d * sg * (1.0f + a * (1.0f - sg));
+      };
+      da[k].x = one(dh[k].x, x[k].x, gm[k].x, bt[k].x); da[k].y = one(dh[k].y, x[k].y, gm[k].y, bt[k].y);
+      da[k].z = one(dh[k].z, x[k].z, gm[k].z, bt[k].z); da[k].w = one(dh[k].w, x[k].w, gm[k].w, bt[k].w);
+      // d x_hat kept in dh
+      dh[k].x = da[k].x * gm[k].x; dh[k].y = da[k].y * gm[k].y; dh[k].z = da[k].z * gm[k].z; dh[k].w = da[k].w * gm[k].w;
+      s1 += (dh[k].x + dh[k].y) + (dh[k].z + dh[k].w);
+      s2 = fmaf(dh[k].x, x[k].x, fmaf(dh[k].y, x[k].y, fmaf(dh[k].z, x[k].z, fmaf(dh[k].w, x[k].w, s2))));
+    }
+    const float m1 = warp_sum(s1) * invH, m2 = warp_sum(s2) * invH;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c4 = lane + 32 * k;
+      float4 du;
+      du.x = rs * (dh[k].x - m1 - x[k].x * m2); du.y = rs * (dh[k].y - m1 - x[k].y * m2);
+      du.z = rs * (dh[k].z - m1 - x[k].z * m2); du.w = rs * (dh[k].w - m1 - x[k].w * m2);
+      if (4 * c4 < H) gr[c4] = du;
+      ag[k].x = fmaf(da[k].x, x[k].x, ag[k].x); ag[k].y = fmaf(da[k].y, x[k].y, ag[k].y);
+      ag[k].z = fmaf(da[k].z, x[k].z, ag[k].z); ag[k].w = fmaf(da[k].w, x[k].w, ag[k].w);
+      ab[k].x += da[k].x; ab[k].y += da[k].y; ab[k].z += da[k].z; ab[k].w += da[k].w;
+      au[k].x += du.x; au[k].y += du.y; au[k].z += du.z; au[k].w += du.w;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int c = 4 * (lane + 32 * k);
+    if (c < H) {
+      atomicAdd(&red[c], ag[k].x); atomicAdd(&red[c + 1], ag[k].y); atomicAdd(&red[c + 2], ag[k].z); atomicAdd(&red[c + 3], ag[k].w);
+      atomicAdd(&red[H + c], ab[k].x); atomicAdd(&red[H + c + 1], ab[k].y); atomicAdd(&red[H + c + 2], ab[k].z); atomicAdd(&red[H + c + 3], ab[k].w);
+      atomicAdd(&red[2 * H + c], au[k].x); atomicAdd(&red[2 * H + c + 1], au[k].y); atomicAdd(&red[2 * H + c + 2], au[k].z); atomicAdd(&red[2 * H + c + 3], au[k].w);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < H; i += blockDim.x) {
+    atomicAdd(&dgamma[i], red[i]);
+    atomicAdd(&dbeta[i], red[H + i]);
+    atomicAdd(&dbias[i], red[2 * H + i]);
+  }
+}
+
+// out[c] += sum over the CTA's rows of A[row][c]      (bias gradient of the output Linear)
+__global__ void __launch_bounds__(128) k_enc_colsum(const float* __restrict__ A, long long lda, long long B, int N,
+                                                    float* __restrict__ out, int rows_per_cta) {
+  NF_PDL_ENTRY();
+  const int c = blockIdx.y * 128 + threadIdx.x;
+  if (c >= N) return;
+  const long long r0 = (long long)blockIdx.x * rows_per_cta, r1 = min(B, r0 + rows_per_cta);
+  float acc = 0.f;
+  for (long long r = r0; r < r1; ++r) acc += A[r * lda + c];
+  atomicAdd(&out[c], acc);
+}
+
+int rows_per_cta_for(long long B) {
+  // enough CTAs for two waves on 148 SMs, at least 32 rows each (fewer global atomics per row)
+  long long rpc = cdiv(B, 296);
+  rpc = std::max<long long>(32, cdiv(rpc, 8) * 8);
+  return (int)rpc;
+}
+
+int ln_silu_fwd(float* xh, float* h, float* rstd, const float* gamma, const float* beta, long long B, int H, float eps,
+                cudaStream_t st) {
+  if (B <= 0) return 0;
+  const unsigned grid = (unsigned)cdiv(B, 8);
+  const int nv = (int)cdiv(H, 128);
+  switch (nv) {
+    case 1: NF_LAUNCH((k_enc_ln_silu_fwd<1>), grid, 256, 0, st, xh, h, rstd, gamma, beta, B, H, eps); break;
+    case 2: NF_LAUNCH((k_enc_ln_silu_fwd<2>), grid, 256, 0, st, xh, h, rstd, gamma, beta, B, H, eps); break;
+    case 3: case 4: NF_LAUNCH((k_enc_ln_silu_fwd<4>), grid, 256, 0, st, xh, h, rstd, gamma, beta, B, H, eps); break;
+    default: NF_LAUNCH((k_enc_ln_silu_fwd<kEncMaxV>), grid, 256, 0, st, xh, h, rstd, gamma, beta, B, H, eps); break;
+  }
+  NF_LAUNCHED();
+  return 0;
+}
+
+int ln_silu_bwd(float* g, const float* xh, const float* rstd, const float* gamma, const float* beta, float* dgamma,
+                float* dbeta, float* dbias, long long B, int H, cudaStream_t st) {
+  if (B <= 0) return 0;
+  const int rpc = rows_per_cta_for(B);
+  const unsigned grid = (unsigned)cdiv(B, rpc);
+  const size_t smem = (size_t)3 * H * sizeof(float);
+  const int nv = (int)cdiv(H, 128);
+  switch (nv) {
+    case 1: NF_LAUNCH((k_enc_ln_silu_bwd<1>), grid, 256, smem, st, g, xh, rstd, gamma, beta, dgamma, dbeta, dbias, B, H, rpc); break;
+    case 2: NF_LAUNCH((k_enc_ln_silu_bwd<2>), grid, 256, smem, st, g, xh, rstd, gamma, beta, dgamma, dbeta, dbias, B, H, rpc); break;
+    case 3: case 4: NF_LAUNCH((k_enc_ln_silu_bwd<4>), grid, 256, smem, st, g, xh, rstd, gamma, beta, dgamma, dbeta, dbias, B, H, rpc); break;
+    default: NF_LAUNCH((k_enc_ln_silu_bwd<kEncMaxV>), grid, 256, smem, st, g, xh, rstd, gamma, beta, dgamma, dbeta, dbias, B, H, rpc); break;
+  }
+  NF_LAUNCHED();
+  return 0;
+}
+
+int colsum(const float* A, long long lda, long long B, int N, float* out, cudaStream_t st) {
+  if (B <= 0 || N <= 0) return 0;
+  const int rpc = rows_per_cta_for(B);
+  NF_LAUNCH((k_enc_colsum), dim3((unsigned)cdiv(B, rpc), (unsigned)cdiv(N, 128)), 128, 0, st, A, lda, B, N, out, rpc);
+  NF_LAUNCHED();
+  return 0;
+}
+
+// C (B, N) = A (B, K) @ W (N, K)^T + bias
+int enc_linear(int prec, const float* A, int K, const float* W, const float* bias, float* C, int N, int64_t B,
+               cudaStream_t st) {
+  TcGemmP t;
+  t.A0 = A; t.lda0 = K; t.B0 = W; t.ldb0 = K; t.C = C; t.ldc = N; t.bias = bias;
+  t.M = (int)B; t.N = N; t.K0 = K;
+  return linear_nt(prec, t, st);
+}
+
+}  // namespace
+}  // namespace nf
+
+using namespace nf;
+
+extern "C" {
+
+NF_API int64_t nf_encoder_param_layout(const NfEncoderDesc* desc, int64_t* offs) {
+  if (check_enc(desc) != 0) return -1;
+  const EncDims m = enc_dims(desc);
+  const EncLayout l = enc_layout(m);
+  if (offs) {
+    for (int i = 0; i < m.L; ++i) {
+      offs[4 * i + 0] = l.w[i]; offs[4 * i + 1] = l.b[i]; offs[4 * i + 2] = l.lw[i]; offs[4 * i + 3] = l.lb[i];
+    }
+    offs[4 * m.L] = l.wo; offs[4 * m.L + 1] = l.bo;
+  }
+  return l.total;
+}
+
+NF_API int64_t nf_encoder_stash_bytes(const NfEncoderDesc* desc, int64_t B) {
+  if (check_enc(desc) != 0 || B < 0) return -1;
+  return std::max<int64_t>(16, enc_stash(enc_dims(desc), B).total * 4);
+}
+
+NF_API int64_t nf_encoder_workspace_bytes(const NfEncoderDesc* desc, int64_t B) {
+  if (check_enc(desc) != 0 || B < 0) return -1;
+  return std::max<int64_t>(16, enc_ws(enc_dims(desc), B).total * 4);
+}
+
+NF_API int nf_encoder_forward(const NfEncoderDesc* desc, const float* params, const float* g, int64_t B, float* out,
+                              void* stash, void* workspace, int64_t ws_bytes, void* stream) {
+  NF_TRY(check_enc(desc));
+  NF_CHECK_ARG(B >= 0 && B < (int64_t(1) << 30), NF_E_BADARG, "B=%lld out of range", (long long)B);
+  const EncDims m = enc_dims(desc);
+  const EncLayout l = enc_layout(m);
+  const EncStash sl = enc_stash(m, B);
+  const EncWs wl = enc_ws(m, B);
+  NF_TRY(check_ptr(params, "params", true));
+  if (B == 0) return 0;
+  NF_TRY(check_ptr(g, "g", true)); NF_TRY(check_ptr(out, "out", true));
+  NF_TRY(check_ptr(stash, "stash", false)); NF_TRY(check_ptr(workspace, "workspace", true));
+  NF_CHECK_ARG(ws_bytes >= wl.total * 4, NF_E_WORKSPACE, "workspace too small: %lld < %lld bytes", (long long)ws_bytes,
+               (long long)wl.total * 4);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* ws = static_cast<float*>(workspace);
+  float* sb = static_cast<float*>(stash);
+  const float* hin = g;
+  int K = m.in;
+  for (int i = 0; i < m.L; ++i) {
+    // with a stash every layer keeps its x_hat / h / rstd; without one the two workspace buffers alternate roles
+    float* xh = sb ? sb + i * sl.layer_stride + sl.xh : ws + wl.a;
+    float* h = sb ? sb + i * sl.layer_stride + sl.h : ws + wl.b;
+    float* rs = sb ? sb + i * sl.layer_stride + sl.rstd : nullptr;
+    NF_TRY(enc_linear(m.prec, hin, K, params + l.w[i], params + l.b[i], xh, m.H, B, st));        // fc_i   (:170)
+    NF_TRY(ln_silu_fwd(xh, h, rs, params + l.lw[i], params + l.lb[i], B, m.H, m.eps, st));       // norm_i, silu (:171-172)
+    hin = h; K = m.H;
+  }
+  return enc_linear(m.prec, hin, K, params + l.wo, params + l.bo, out, m.out, B, st);            // fc_out (:186)
+}
+
+NF_API int nf_encoder_backward(const NfEncoderDesc* desc, const float* params, const float* g, const void* stash,
+                               int64_t B, const float* dout, float* dg, float* dparams, void* workspace,
+                               int64_t ws_bytes, void* stream) {
+  NF_TRY(check_enc(desc));
+  NF_CHECK_ARG(B >= 0 && B < (int64_t(1) << 30), NF_E_BADARG, "B=%lld out of range", (long long)B);
+  const EncDims m = enc_dims(desc);
+  const EncLayout l = enc_layout(m);
+  const EncStash sl = enc_stash(m, B);
+  const EncWs wl = enc_ws(m, B);
+  NF_TRY(check_ptr(params, "params", true)); NF_TRY(check_ptr(dparams, "dparams", true));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  NF_TRY(fill_zero(dparams, l.total, st));
+  if (B == 0) return 0;
+  NF_TRY(check_ptr(g, "g", true)); NF_TRY(check_ptr(stash, "stash", true)); NF_TRY(check_ptr(dout, "dout", true));
+  NF_TRY(check_ptr(dg, "dg", false)); NF_TRY(check_ptr(workspace, "workspace", true));
+  NF_CHECK_ARG(ws_bytes >= wl.total * 4, NF_E_WORKSPACE, "workspace too small: %lld < %lld bytes", (long long)ws_bytes,
+               (long long)wl.total * 4);
+  float* ws = static_cast<float*>(workspace);
+  const float* sb = static_cast<const float*>(stash);
+  float* wt = ws + wl.wt;
+  auto layer = [&](int i, int64_t off) { return sb + i * sl.layer_stride + off; };
+
+  // output Linear: dW_out += dout^T h_L, db_out = colsum(dout), dh_L = dout W_out
+  {
+    TcGemmTnP w;
+    w.A = dout; w.lda = m.out; w.B = layer(m.L - 1, sl.h); w.ldb = m.H; w.C = dparams + l.wo; w.ldc = m.H;
+    w.M = m.out; w.N = m.H; w.K = B;
+    NF_TRY(wgrad_tn(m.prec, w, st));
+    NF_TRY(colsum(dout, m.out, B, m.out, dparams + l.bo, st));
+    NF_TRY(transpose2d(wt, m.out, 0, 0, params + l.wo, m.H, 0, 0, m.out, m.H, 1, 1, st));   // (out, H) -> (H, out)
+    NF_TRY(enc_linear(m.prec, dout, m.out, wt, nullptr, ws + wl.a, m.H, B, st));
+  }
+  float* cur = ws + wl.a;     // dh_i, then du_i in place
+  float* other = ws + wl.b;
+  for (int i = m.L - 1; i >= 0; --i) {
+    const int K = i == 0 ? m.in : m.H;
+    NF_TRY(ln_silu_bwd(cur, layer(i, sl.xh), layer(i, sl.rstd), params + l.lw[i], params + l.lb[i], dparams + l.lw[i],
+                       dparams + l.lb[i], dparams + l.b[i], B, m.H, st));
+    TcGemmTnP w;   // dW_i += du_i^T h_{i-1}
+    w.A = cur; w.lda = m.H; w.B = i == 0 ? g : layer(i - 1, sl.h); w.ldb = K; w.C = dparams + l.w[i]; w.ldc = K;
+    w.M = m.H; w.N = K; w.K = B;
+    NF_TRY(wgrad_tn(m.prec, w, st));
+    if (i > 0 || dg) {
+      // dh_{i-1} = du_i W_i : the K-major B operand is W_i^T (K, H)
+      NF_TRY(transpose2d(wt, m.H, 0, 0, params + l.w[i], K, 0, 0, m.H, K, 1, 1, st));
+      float* dst = i == 0 ? dg : other;
+      NF_TRY(enc_linear(m.prec, cur, m.H, wt, nullptr, dst, K, B, st));
+      std::swap(cur, other);
+    }
+  }
+  return 0;
+}
+
+}  // extern "C"

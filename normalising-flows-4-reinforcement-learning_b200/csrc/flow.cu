@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "elementwise.cuh"
 #include "graphs.cuh"
+#include "linear.cuh"
 #include "rowfused.cuh"
 #include "rowlocal.cuh"
 #include "simt_gemm.cuh"
@@ -259,24 +260,11 @@ static PrepWs carve_prep(const Dims& m, void* ws) {
   return w;
 }
 
-static int check_ptr(const void* p, const char* name, bool required) {
-  if (!p) {
-    NF_CHECK_ARG(!required, NF_E_BADARG, "%s is NULL", name);
-    return 0;
-  }
-  NF_CHECK_ARG((reinterpret_cast<uintptr_t>(p) & 15u) == 0, NF_E_ALIGN, "%s is not 16-byte aligned", name);
-  return 0;
-}
-#define NF_TRY(expr)            \
-  do {                          \
-    int _r = (expr);            \
-    if (_r != 0) return _r;     \
-  } while (0)
 
 // C[z] (M,N) (+)= [A0 | A1][z] (M,K0+K1) @ [B0 | B1][z] (N,K0+K1)^T : the Linear layers and their data
 // gradients.  precision 1 (3xTF32) runs on tcgen05 when the tile shapes make sense and TMA can
 // address the operands; everything else (tiny N or K, odd pitches) is exact-fp32 FFMA.
-static int linear_nt(int prec, const TcGemmP& t0, cudaStream_t st) {
+int linear_nt(int prec, const TcGemmP& t0, cudaStream_t st) {
   TcGemmP t = t0;
   // Truncating the hi operand (raw_hi) leaves a one-signed lo, so the dropped lo*lo products are a
   // systematic 2^-22-relative bias that grows with the reduction length; long reductions use the
@@ -294,7 +282,7 @@ static int linear_nt(int prec, const TcGemmP& t0, cudaStream_t st) {
 
 // C[z] (M,N) += A[z] (K,M)^T @ B[z] (K,N): weight gradients (reduction over the K = batch rows).
 // C must already hold the base value (the gradient arena is zero-filled first).
-static int wgrad_tn(int prec, const TcGemmTnP& t, cudaStream_t st) {
+int wgrad_tn(int prec, const TcGemmTnP& t, cudaStream_t st) {
   if (prec == NF_PREC_TF32X3 && t.M >= 32 && t.N >= 32 && tc_gemm_tn_supported(t)) return tc_gemm_tn(t, st);
   GemmP g;
   g.transA = 1; g.A0 = t.A; g.lda0 = (int)t.lda; g.sA0 = t.sA; g.K0 = (int)t.K;

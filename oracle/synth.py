@@ -122,3 +122,43 @@ def make_safe_inputs(sd, n, B, D, R, seed=1234, eps=1e-5, max_tries=400):
         if fo.min_abs_preactivation(sd64, n, x.astype(np.float64), y.astype(np.float64), eps) > KINK_MARGIN:
             return x, y, s
     raise RuntimeError("no kink-free input seed found")
+
+
+# ---------------------------------------------------------------------------- conditioning encoder (row f2)
+# (input_size, rep_size) of the reference callers: GCBC obs+goal (torch_nfgcbc.py:120), kitchen obs 60 x window 10
+# (torch_nfbc_kitchen.py:151), ant obs 29 x ... (SURVEY.md section 8 f2 quotes in = 4100).
+ENCODER_CONFIGS = {
+    "gcbc": dict(input_size=58, rep_size=64),
+    "kitchen": dict(input_size=600, rep_size=1024),
+    "ant": dict(input_size=4100, rep_size=256),
+}
+
+
+def make_encoder_state_dict(input_size: int, rep_size: int, seed: int = 0, hidden: int = 512, n_hidden: int = 4,
+                            dtype=np.float32) -> "OrderedDict[str, np.ndarray]":
+    """Weights with the reference GEncoder's key names (torch_fcnf.py:160-169): fc1..fcN, norm1..normN, fc_out."""
+    rs = np.random.RandomState(seed)
+    sd: "OrderedDict[str, np.ndarray]" = OrderedDict()
+
+    def uni(shape, fan_in):
+        k = 1.0 / math.sqrt(fan_in)
+        return rs.uniform(-k, k, size=shape)
+
+    fan = input_size
+    for i in range(1, n_hidden + 1):
+        sd[f"fc{i}.weight"] = uni((hidden, fan), fan)
+        sd[f"fc{i}.bias"] = uni((hidden,), fan)
+        sd[f"norm{i}.weight"] = 1.0 + 0.1 * rs.standard_normal(hidden)
+        sd[f"norm{i}.bias"] = 0.1 * rs.standard_normal(hidden)
+        fan = hidden
+    sd["fc_out.weight"] = uni((rep_size, hidden), hidden)
+    sd["fc_out.bias"] = uni((rep_size,), hidden)
+    return OrderedDict((k, np.ascontiguousarray(v, dtype=dtype)) for k, v in sd.items())
+
+
+def make_encoder_inputs(B: int, input_size: int, rep_size: int, seed: int = 77, dtype=np.float32):
+    """observations g ~ N(0,1) and an upstream gradient for the representation."""
+    rs = np.random.RandomState(seed)
+    g = rs.standard_normal((B, input_size))
+    dout = rs.standard_normal((B, rep_size))
+    return np.ascontiguousarray(g, dtype=dtype), np.ascontiguousarray(dout, dtype=dtype)
