@@ -192,8 +192,10 @@ NF_API int nf_adamw_step(const NfFlowDesc* desc, float* params, const float* gra
  *   offs[4 i + 0] Linear weight (hidden, in_i) row-major (nn.Linear layout), offs[4 i + 1] Linear bias (hidden),
  *   offs[4 i + 2] LayerNorm weight (hidden), offs[4 i + 3] LayerNorm bias (hidden);
  * then offs[4 n_hidden] output weight (out_features, hidden) and offs[4 n_hidden + 1] output bias.
- * Forward writes `out` (B, out_features) and, when `stash` is given, what backward needs.  Backward takes
- * dout (B, out_features), writes dparams (same layout as params, overwritten) and optionally dg (B, in_features).
+ * Forward writes `out` (B, out_features) and, when `stash` is given, what backward needs (a copy of g included).
+ * Backward takes dout (B, out_features), writes dparams (same layout as params, overwritten) and optionally dg
+ * (B, in_features).  Like the flow calls, both replay a cached launch graph keyed on (desc, B, params, stash,
+ * dparams, workspace); g / out / dout / dg are staged through the workspace and may change from call to call.
  * Same conventions as the flow calls: caller-owned buffers, workspace passed in, asynchronous on `stream`. */
 typedef struct NfEncoderDesc {
   int32_t in_features, hidden, out_features, n_hidden;
@@ -206,9 +208,9 @@ NF_API int64_t nf_encoder_stash_bytes(const NfEncoderDesc* desc, int64_t B);
 NF_API int64_t nf_encoder_workspace_bytes(const NfEncoderDesc* desc, int64_t B);
 NF_API int nf_encoder_forward(const NfEncoderDesc* desc, const float* params, const float* g, int64_t B, float* out,
                               void* stash, void* workspace, int64_t ws_bytes, void* stream);
-NF_API int nf_encoder_backward(const NfEncoderDesc* desc, const float* params, const float* g, const void* stash,
-                               int64_t B, const float* dout, float* dg, float* dparams, void* workspace,
-                               int64_t ws_bytes, void* stream);
+NF_API int nf_encoder_backward(const NfEncoderDesc* desc, const float* params, const void* stash, int64_t B,
+                               const float* dout, float* dg, float* dparams, void* workspace, int64_t ws_bytes,
+                               void* stream);
 
 /* Optional per-kernel-class timing (CUDA events on the launching stream; off by default).  Kinds:
  * 0 tcgen05 GEMM, 1 tcgen05 weight-gradient GEMM, 2 FFMA GEMM, 3 LeakyReLU+LayerNorm fwd, 4 its backward,

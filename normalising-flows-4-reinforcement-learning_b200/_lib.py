@@ -76,7 +76,7 @@ def _load():
         "nf_encoder_stash_bytes": (c_int64, [E, i64]),
         "nf_encoder_workspace_bytes": (c_int64, [E, i64]),
         "nf_encoder_forward": (c_int, [E, fp, fp, i64, fp, vp, vp, i64, vp]),
-        "nf_encoder_backward": (c_int, [E, fp, fp, vp, i64, fp, fp, fp, vp, i64, vp]),
+        "nf_encoder_backward": (c_int, [E, fp, vp, i64, fp, fp, fp, vp, i64, vp]),
         "nf_set_option": (c_int, [c_char_p, c_int]),
         "nf_get_option": (c_int, [c_char_p]),
         "nf_graphs_enable": (c_int, [c_int]),

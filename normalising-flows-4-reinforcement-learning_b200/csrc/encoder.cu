@@ -10,6 +10,7 @@
 
 #include "common.cuh"
 #include "elementwise.cuh"
+#include "graphs.cuh"
 #include "linear.cuh"
 
 namespace nf {
@@ -61,26 +62,33 @@ EncLayout enc_layout(const EncDims& m) {
   return l;
 }
 
-// stash: per hidden layer x_hat (B,H), h (B,H), rstd (B)
+// stash: a copy of the input g (B, in) -- forward's staging buffer, read again by the first layer's weight gradient --
+// then per hidden layer x_hat (B,H), h (B,H), rstd (B)
 struct EncStash {
-  int64_t xh, h, rstd, layer_stride, total;
+  int64_t g, layers, xh, h, rstd, layer_stride, total;
 };
 EncStash enc_stash(const EncDims& m, int64_t B) {
   EncStash s{};
+  s.g = 0; s.layers = pad4(B * m.in);
   s.xh = 0; s.h = B * m.H; s.rstd = 2 * B * m.H;
   s.layer_stride = 2 * B * m.H + pad4(B);
-  s.total = s.layer_stride * m.L;
+  s.total = s.layers + s.layer_stride * m.L;
   return s;
 }
 
-// workspace: two (B,H) activation buffers, one transposed weight
+// workspace: two (B,H) activation buffers, one transposed weight, and the I/O staging buffers that keep the cached
+// launch graphs independent of the caller's input / output pointers (graphs.cuh)
 struct EncWs {
-  int64_t a, b, wt, total;
+  int64_t a, b, wt, io_g, io_out, io_dg, total;
 };
 EncWs enc_ws(const EncDims& m, int64_t B) {
   EncWs w{};
-  w.a = 0; w.b = pad4(B * m.H); w.wt = 2 * pad4(B * m.H);
-  w.total = w.wt + pad4((int64_t)m.H * std::max(std::max(m.H, m.in), m.out));
+  int64_t off = 0;
+  auto take = [&](int64_t n) { int64_t o = off; off += pad4(n); return o; };
+  w.a = take(B * m.H); w.b = take(B * m.H);
+  w.wt = take((int64_t)m.H * std::max(std::max(m.H, m.in), m.out));
+  w.io_g = take(B * m.in); w.io_out = take(B * m.out); w.io_dg = take(B * m.in);
+  w.total = off;
   return w;
 }
 
@@ -281,12 +289,37 @@ int colsum(const float* A, long long lda, long long B, int N, float* out, cudaSt
   return 0;
 }
 
+// launch-sequence cache key (graphs.cuh): the encoder's descriptor folded into the flow descriptor's fields
+GraphKey enc_key(int op, const NfEncoderDesc* d, int64_t B, int64_t ws_bytes) {
+  GraphKey k;
+  k.op = op; k.B = B; k.ws_bytes = ws_bytes;
+  k.desc.D = d->in_features; k.desc.C = d->hidden; k.desc.H1 = d->n_hidden; k.desc.R = d->out_features;
+  k.desc.n_blocks = 0; k.desc.ln_eps = d->ln_eps; k.desc.precision = d->precision;
+  return k;
+}
+
+// C[r][c] = bias ? bias[c] : 0   (base value of a split-K accumulation)
+__global__ void __launch_bounds__(256) k_enc_fill_rows(float* __restrict__ C, long long n, int N,
+                                                       const float* __restrict__ bias) {
+  NF_PDL_ENTRY();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    C[i] = bias ? __ldg(bias + (int)(i % N)) : 0.f;
+}
+
 // C (B, N) = A (B, K) @ W (N, K)^T + bias
 int enc_linear(int prec, const float* A, int K, const float* W, const float* bias, float* C, int N, int64_t B,
                cudaStream_t st) {
   TcGemmP t;
   t.A0 = A; t.lda0 = K; t.B0 = W; t.ldb0 = K; t.C = C; t.ldc = N; t.bias = bias;
   t.M = (int)B; t.N = N; t.K0 = K;
+  // Few output tiles and a long reduction (the ant encoder's first layer at batch 256: 8 tiles, K = 4100): start C
+  // at the bias and accumulate, which lets the GEMM split the reduction over the idle SMs.
+  if (prec == NF_PREC_TF32X3 && K >= 512 && cdiv(B, 128) * cdiv(N, 128) * 2 <= 148 && tc_gemm_supported(t)) {
+    const long long n = B * N;
+    NF_LAUNCH((k_enc_fill_rows), (unsigned)std::min<long long>(cdiv(n, 256), 148 * 4), 256, 0, st, C, n, N, bias);
+    NF_LAUNCHED();
+    t.bias = nullptr; t.accumulate = 1;
+  }
   return linear_nt(prec, t, st);
 }
 
@@ -334,26 +367,41 @@ NF_API int nf_encoder_forward(const NfEncoderDesc* desc, const float* params, co
   NF_TRY(check_ptr(stash, "stash", false)); NF_TRY(check_ptr(workspace, "workspace", true));
   NF_CHECK_ARG(ws_bytes >= wl.total * 4, NF_E_WORKSPACE, "workspace too small: %lld < %lld bytes", (long long)ws_bytes,
                (long long)wl.total * 4);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaStream_t user_st = static_cast<cudaStream_t>(stream);
   float* ws = static_cast<float*>(workspace);
   float* sb = static_cast<float*>(stash);
-  const float* hin = g;
-  int K = m.in;
-  for (int i = 0; i < m.L; ++i) {
-    // with a stash every layer keeps its x_hat / h / rstd; without one the two workspace buffers alternate roles
-    float* xh = sb ? sb + i * sl.layer_stride + sl.xh : ws + wl.a;
-    float* h = sb ? sb + i * sl.layer_stride + sl.h : ws + wl.b;
-    float* rs = sb ? sb + i * sl.layer_stride + sl.rstd : nullptr;
-    NF_TRY(enc_linear(m.prec, hin, K, params + l.w[i], params + l.b[i], xh, m.H, B, st));        // fc_i   (:170)
-    NF_TRY(ln_silu_fwd(xh, h, rs, params + l.lw[i], params + l.lb[i], B, m.H, m.eps, st));       // norm_i, silu (:171-172)
-    hin = h; K = m.H;
+  float* g_in = sb ? sb + sl.g : ws + wl.io_g;
+  float* out_st = ws + wl.io_out;
+  {
+    CopySegs c;
+    c.add(g_in, g, B * m.in);
+    NF_TRY(copy_segments(c, user_st));
   }
-  return enc_linear(m.prec, hin, K, params + l.wo, params + l.bo, out, m.out, B, st);            // fc_out (:186)
+  GraphKey key = enc_key(20, desc, B, ws_bytes);
+  key.ptr[0] = params; key.ptr[1] = stash; key.ptr[2] = workspace;
+  auto body = [&](cudaStream_t st) -> int {
+    const float* hin = g_in;
+    int K = m.in;
+    for (int i = 0; i < m.L; ++i) {
+      // with a stash every layer keeps its x_hat / h / rstd; without one the two workspace buffers alternate roles
+      float* xh = sb ? sb + sl.layers + i * sl.layer_stride + sl.xh : ws + wl.a;
+      float* h = sb ? sb + sl.layers + i * sl.layer_stride + sl.h : ws + wl.b;
+      float* rs = sb ? sb + sl.layers + i * sl.layer_stride + sl.rstd : nullptr;
+      NF_TRY(enc_linear(m.prec, hin, K, params + l.w[i], params + l.b[i], xh, m.H, B, st));        // fc_i   (:170)
+      NF_TRY(ln_silu_fwd(xh, h, rs, params + l.lw[i], params + l.lb[i], B, m.H, m.eps, st));       // norm_i, silu (:171-172)
+      hin = h; K = m.H;
+    }
+    return enc_linear(m.prec, hin, K, params + l.wo, params + l.bo, out_st, m.out, B, st);         // fc_out (:186)
+  };
+  NF_TRY(run_graphed(key, user_st, body));
+  CopySegs c;
+  c.add(out, out_st, B * m.out);
+  return copy_segments(c, user_st);
 }
 
-NF_API int nf_encoder_backward(const NfEncoderDesc* desc, const float* params, const float* g, const void* stash,
-                               int64_t B, const float* dout, float* dg, float* dparams, void* workspace,
-                               int64_t ws_bytes, void* stream) {
+NF_API int nf_encoder_backward(const NfEncoderDesc* desc, const float* params, const void* stash, int64_t B,
+                               const float* dout, float* dg, float* dparams, void* workspace, int64_t ws_bytes,
+                               void* stream) {
   NF_TRY(check_enc(desc));
   NF_CHECK_ARG(B >= 0 && B < (int64_t(1) << 30), NF_E_BADARG, "B=%lld out of range", (long long)B);
   const EncDims m = enc_dims(desc);
@@ -361,47 +409,63 @@ NF_API int nf_encoder_backward(const NfEncoderDesc* desc, const float* params, c
   const EncStash sl = enc_stash(m, B);
   const EncWs wl = enc_ws(m, B);
   NF_TRY(check_ptr(params, "params", true)); NF_TRY(check_ptr(dparams, "dparams", true));
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  NF_TRY(fill_zero(dparams, l.total, st));
-  if (B == 0) return 0;
-  NF_TRY(check_ptr(g, "g", true)); NF_TRY(check_ptr(stash, "stash", true)); NF_TRY(check_ptr(dout, "dout", true));
+  cudaStream_t user_st = static_cast<cudaStream_t>(stream);
+  if (B == 0) return fill_zero(dparams, l.total, user_st);
+  NF_TRY(check_ptr(stash, "stash", true)); NF_TRY(check_ptr(dout, "dout", true));
   NF_TRY(check_ptr(dg, "dg", false)); NF_TRY(check_ptr(workspace, "workspace", true));
   NF_CHECK_ARG(ws_bytes >= wl.total * 4, NF_E_WORKSPACE, "workspace too small: %lld < %lld bytes", (long long)ws_bytes,
                (long long)wl.total * 4);
   float* ws = static_cast<float*>(workspace);
   const float* sb = static_cast<const float*>(stash);
-  float* wt = ws + wl.wt;
-  auto layer = [&](int i, int64_t off) { return sb + i * sl.layer_stride + off; };
-
-  // output Linear: dW_out += dout^T h_L, db_out = colsum(dout), dh_L = dout W_out
+  const float* g_in = sb + sl.g;
+  float* dout_st = ws + wl.io_out;      // forward's output staging is free by now
+  float* dg_st = ws + wl.io_dg;
   {
-    TcGemmTnP w;
-    w.A = dout; w.lda = m.out; w.B = layer(m.L - 1, sl.h); w.ldb = m.H; w.C = dparams + l.wo; w.ldc = m.H;
-    w.M = m.out; w.N = m.H; w.K = B;
-    NF_TRY(wgrad_tn(m.prec, w, st));
-    NF_TRY(colsum(dout, m.out, B, m.out, dparams + l.bo, st));
-    NF_TRY(transpose2d(wt, m.out, 0, 0, params + l.wo, m.H, 0, 0, m.out, m.H, 1, 1, st));   // (out, H) -> (H, out)
-    NF_TRY(enc_linear(m.prec, dout, m.out, wt, nullptr, ws + wl.a, m.H, B, st));
+    CopySegs c;
+    c.add(dout_st, dout, B * m.out);
+    NF_TRY(copy_segments(c, user_st));
   }
-  float* cur = ws + wl.a;     // dh_i, then du_i in place
-  float* other = ws + wl.b;
-  for (int i = m.L - 1; i >= 0; --i) {
-    const int K = i == 0 ? m.in : m.H;
-    NF_TRY(ln_silu_bwd(cur, layer(i, sl.xh), layer(i, sl.rstd), params + l.lw[i], params + l.lb[i], dparams + l.lw[i],
-                       dparams + l.lb[i], dparams + l.b[i], B, m.H, st));
-    TcGemmTnP w;   // dW_i += du_i^T h_{i-1}
-    w.A = cur; w.lda = m.H; w.B = i == 0 ? g : layer(i - 1, sl.h); w.ldb = K; w.C = dparams + l.w[i]; w.ldc = K;
-    w.M = m.H; w.N = K; w.K = B;
-    NF_TRY(wgrad_tn(m.prec, w, st));
-    if (i > 0 || dg) {
-      // dh_{i-1} = du_i W_i : the K-major B operand is W_i^T (K, H)
-      NF_TRY(transpose2d(wt, m.H, 0, 0, params + l.w[i], K, 0, 0, m.H, K, 1, 1, st));
-      float* dst = i == 0 ? dg : other;
-      NF_TRY(enc_linear(m.prec, cur, m.H, wt, nullptr, dst, K, B, st));
-      std::swap(cur, other);
+  GraphKey key = enc_key(21, desc, B, ws_bytes);
+  key.ptr[0] = params; key.ptr[1] = stash; key.ptr[2] = dparams; key.ptr[3] = workspace;
+  key.flags = dg ? 1 : 0;
+  auto body = [&](cudaStream_t st) -> int {
+    NF_TRY(fill_zero(dparams, l.total, st));
+    float* wt = ws + wl.wt;
+    auto layer = [&](int i, int64_t off) { return sb + sl.layers + i * sl.layer_stride + off; };
+    // output Linear: dW_out += dout^T h_L, db_out = colsum(dout), dh_L = dout W_out
+    {
+      TcGemmTnP w;
+      w.A = dout_st; w.lda = m.out; w.B = layer(m.L - 1, sl.h); w.ldb = m.H; w.C = dparams + l.wo; w.ldc = m.H;
+      w.M = m.out; w.N = m.H; w.K = B;
+      NF_TRY(wgrad_tn(m.prec, w, st));
+      NF_TRY(colsum(dout_st, m.out, B, m.out, dparams + l.bo, st));
+      NF_TRY(transpose2d(wt, m.out, 0, 0, params + l.wo, m.H, 0, 0, m.out, m.H, 1, 1, st));   // (out, H) -> (H, out)
+      NF_TRY(enc_linear(m.prec, dout_st, m.out, wt, nullptr, ws + wl.a, m.H, B, st));
     }
-  }
-  return 0;
+    float* cur = ws + wl.a;     // dh_i, then du_i in place
+    float* other = ws + wl.b;
+    for (int i = m.L - 1; i >= 0; --i) {
+      const int K = i == 0 ? m.in : m.H;
+      NF_TRY(ln_silu_bwd(cur, layer(i, sl.xh), layer(i, sl.rstd), params + l.lw[i], params + l.lb[i],
+                         dparams + l.lw[i], dparams + l.lb[i], dparams + l.b[i], B, m.H, st));
+      TcGemmTnP w;   // dW_i += du_i^T h_{i-1}
+      w.A = cur; w.lda = m.H; w.B = i == 0 ? g_in : layer(i - 1, sl.h); w.ldb = K; w.C = dparams + l.w[i]; w.ldc = K;
+      w.M = m.H; w.N = K; w.K = B;
+      NF_TRY(wgrad_tn(m.prec, w, st));
+      if (i > 0 || dg) {
+        // dh_{i-1} = du_i W_i : the K-major B operand is W_i^T (K, H)
+        NF_TRY(transpose2d(wt, m.H, 0, 0, params + l.w[i], K, 0, 0, m.H, K, 1, 1, st));
+        float* dst = i == 0 ? dg_st : other;
+        NF_TRY(enc_linear(m.prec, cur, m.H, wt, nullptr, dst, K, B, st));
+        std::swap(cur, other);
+      }
+    }
+    return 0;
+  };
+  NF_TRY(run_graphed(key, user_st, body));
+  CopySegs c;
+  c.add(dg, dg_st, B * m.in);
+  return copy_segments(c, user_st);
 }
 
 }  // extern "C"

@@ -17,14 +17,15 @@ from torch import nn
 
 from . import _lib
 from ._lib import lib
-from .module import _dense, _on
+from .module import _dense, _on, _SlotGuard, _StashSlot
 
 
 class _Encode(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model: "GEncoder", need_stash: bool, g, *params):
-        out, stash = model._run_forward(g, need_stash)
+        out, stash, slot = model._run_forward(g, need_stash)
         ctx.model, ctx.stash = model, stash
+        ctx.guard = _SlotGuard(slot) if slot is not None else None
         ctx.save_for_backward(g)
         return out
 
@@ -36,6 +37,8 @@ class _Encode(torch.autograd.Function):
         (g,) = ctx.saved_tensors
         dg, dflat = model._run_backward(g, ctx.stash, dout, ctx.needs_input_grad[2])
         ctx.stash = None
+        if ctx.guard is not None:
+            ctx.guard.release()      # the stash may be reused by the next forward
         views = model._grad_views(dflat)
         return (None, None, dg) + tuple(v if need else None for v, need in zip(views, ctx.needs_input_grad[3:]))
 
@@ -67,6 +70,7 @@ class GEncoder(nn.Module):
         self._offs, self._total = list(offs), int(total)
         self._flat = None
         self._ws = None
+        self._stash_pool = {}
         self._flatten()
         self.register_load_state_dict_post_hook(lambda module, keys: module._flatten())
 
@@ -95,6 +99,7 @@ class GEncoder(nn.Module):
         out = super()._apply(fn, recurse)
         self._flatten()
         self._ws = None
+        self._stash_pool = {}
         return out
 
     def _is_flat(self):
@@ -133,13 +138,31 @@ class GEncoder(nn.Module):
         with _on(dev):
             ws = self._workspace(B, dev)
             out = torch.empty((B, self.rep_size), dtype=torch.float32, device=dev)
-            stash = None
+            stash, slot = None, None
             if need_stash:
-                stash = torch.empty(lib.nf_encoder_stash_bytes(ctypes.byref(self._desc), B), dtype=torch.uint8, device=dev)
+                stash, slot = self._acquire_stash(B, dev)
             _lib.check(lib.nf_encoder_forward(ctypes.byref(self._desc), self._flat.data_ptr(), g.data_ptr(), B,
                                               out.data_ptr(), stash.data_ptr() if stash is not None else None,
                                               ws.data_ptr(), ws.numel(), self._stream(dev)), "nf_encoder_forward")
-        return out, stash
+        return out, stash, slot
+
+    _MAX_STASH_SLOTS = 4
+
+    def _acquire_stash(self, B, dev):
+        """A free persistent stash for batch size B (the library's launch graphs are keyed on it), or a fresh
+        unpooled one when all are in flight."""
+        pool = self._stash_pool.setdefault((B, dev), [])
+        for slot in pool:
+            if not slot.busy:
+                slot.busy = True
+                return slot.tensor, slot
+        t = torch.empty(lib.nf_encoder_stash_bytes(ctypes.byref(self._desc), B), dtype=torch.uint8, device=dev)
+        if len(pool) < self._MAX_STASH_SLOTS:
+            slot = _StashSlot(t)
+            slot.busy = True
+            pool.append(slot)
+            return t, slot
+        return t, None
 
     def _run_backward(self, g, stash, dout, need_dg):
         dev, B = g.device, g.shape[0]
@@ -148,7 +171,7 @@ class GEncoder(nn.Module):
             ws = self._workspace(B, dev)
             dg = torch.empty_like(g) if need_dg else None
             dflat = torch.empty(self._total, dtype=torch.float32, device=dev)
-            _lib.check(lib.nf_encoder_backward(ctypes.byref(self._desc), self._flat.data_ptr(), g.data_ptr(),
+            _lib.check(lib.nf_encoder_backward(ctypes.byref(self._desc), self._flat.data_ptr(),
                                                stash.data_ptr(), B, dout.data_ptr(),
                                                dg.data_ptr() if dg is not None else None, dflat.data_ptr(),
                                                ws.data_ptr(), ws.numel(), self._stream(dev)), "nf_encoder_backward")

@@ -93,3 +93,25 @@ class TorchFlow(nn.Module):
         for b in reversed(self.blocks):
             z = b.reverse(z, y)
         return z
+
+
+class TorchEncoder(nn.Module):
+    """Stock-PyTorch restatement of the reference conditioning encoder (torch_fcnf.py:154-190): n_hidden times
+    Linear -> LayerNorm -> SiLU, then Linear; same state_dict keys (fc1.., norm1.., fc_out)."""
+
+    def __init__(self, input_size, rep_size, hidden=512, n_hidden=4, ln_eps=1e-5):
+        super().__init__()
+        self.n_hidden = n_hidden
+        fan = input_size
+        for i in range(1, n_hidden + 1):
+            setattr(self, f"fc{i}", nn.Linear(fan, hidden))
+            fan = hidden
+        self.fc_out = nn.Linear(hidden, rep_size)
+        for i in range(1, n_hidden + 1):
+            setattr(self, f"norm{i}", nn.LayerNorm(hidden, eps=ln_eps))
+
+    def forward(self, g):
+        x = g
+        for i in range(1, self.n_hidden + 1):
+            x = nn.functional.silu(getattr(self, f"norm{i}")(getattr(self, f"fc{i}")(x)))
+        return self.fc_out(x)

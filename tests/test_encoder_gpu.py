@@ -42,9 +42,10 @@ def test_encoder_golden_forward_backward(path, precision):
     tol = max(2e-5, 2.0 * max(noise))
     for k, e in errs.items():
         assert e <= tol, (k, e, tol)
-    # inference path (no stash) gives the same output
+    # inference path (no stash) gives the same output (split-K partial sums are combined in arrival order, so the
+    # two runs may differ in the last bit)
     with torch.no_grad():
-        assert torch.equal(m(gt.detach()), out.detach())
+        assert rel_err(m(gt.detach()).cpu().numpy(), out.detach().cpu().numpy()) <= 1e-6
 
 
 @pytest.mark.parametrize("precision", PRECISIONS)

@@ -9,7 +9,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import nf_b200
 from oracle import synth
-from oracle.torch_flow import TorchFlow
+from oracle.torch_flow import TorchEncoder, TorchFlow
 
 BATCH = {"C2a": 4096, "C3": 16384, "C4": 8192, "C1a": 256, "C1c": 256, "C5": 8192}
 
@@ -63,7 +63,37 @@ def run(name, iters):
           f"sample eager {es:.3f} ms  nf_b200 {os_:.3f} ms  x{es / os_:.2f}", flush=True)
 
 
+def run_encoder(name, B, iters=30):
+    """encoder forward + backward (parameters and input gradients off: observations need none), eager vs nf_b200"""
+    cfg = synth.ENCODER_CONFIGS[name]
+    dev = torch.device("cuda:0")
+    sd = {k: torch.tensor(v) for k, v in synth.make_encoder_state_dict(cfg["input_size"], cfg["rep_size"]).items()}
+    ours = nf_b200.GEncoder(cfg["input_size"], cfg["rep_size"]); ours.load_state_dict(sd); ours = ours.to(dev)
+    eager = TorchEncoder(cfg["input_size"], cfg["rep_size"]); eager.load_state_dict(sd); eager = eager.to(dev)
+    g, dout = synth.make_encoder_inputs(B, cfg["input_size"], cfg["rep_size"])
+    g = torch.tensor(g, device=dev); dout = torch.tensor(dout, device=dev)
+    row = {}
+    for tag, m in (("eager", eager), ("nf_b200", ours)):
+        plist = list(m.parameters())
+
+        def train():
+            for p in plist:
+                p.grad = None
+            m(g).backward(dout)
+
+        def infer():
+            with torch.no_grad():
+                m(g)
+        row[tag] = (timed(train, iters), timed(infer, iters))
+    (et, ei), (ot, oi) = row["eager"], row["nf_b200"]
+    print(f"encoder {name} B={B}: fwd+bwd eager {et:.3f} ms  nf_b200 {ot:.3f} ms  x{et / ot:.2f} | "
+          f"fwd eager {ei:.3f} ms  nf_b200 {oi:.3f} ms  x{ei / oi:.2f}", flush=True)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "encoder":
+        run_encoder("gcbc", 4096); run_encoder("kitchen", 8192); run_encoder("ant", 256)
+        sys.exit(0)
     names = sys.argv[1].split(",") if len(sys.argv) > 1 else ["C2a", "C3", "C4", "C1a", "C5"]
     for nm in names:
         run(nm, 5 if nm == "C5" else 30)
