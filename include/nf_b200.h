@@ -55,7 +55,7 @@ extern "C" {
 #define NF_PREC_FP32_SIMT 0 /* FFMA, exact fp32 (checker / odd shapes)                         */
 #define NF_PREC_TF32X3    1 /* tcgen05 kind::tf32, 3-pass split operands, fp32 accumulate:     */
                             /* fp32-parity mode (<= 1e-5 vs the fp64 arbiter)                   */
-#define NF_PREC_BF16      2 /* tcgen05 kind::f16 (bf16 operands), 2e-2 contract                */
+#define NF_PREC_BF16      2 /* reserved (optional 2e-2 mode): not built, rejected with NF_E_UNSUPPORTED */
 
 typedef struct NfFlowDesc {
   int32_t D;        /* in_channels: flow dimension                                     */

@@ -64,6 +64,7 @@ int check_desc(const NfFlowDesc* d) {
   NF_CHECK_ARG(d->n_blocks >= 1 && d->n_blocks <= 4096, NF_E_BADARG, "n_blocks=%d out of range", d->n_blocks);
   NF_CHECK_ARG(d->ln_eps > 0.f, NF_E_BADARG, "ln_eps must be > 0");
   NF_CHECK_ARG(d->precision >= 0 && d->precision <= 2, NF_E_BADARG, "unknown precision %d", d->precision);
+  NF_CHECK_ARG(d->precision != NF_PREC_BF16, NF_E_UNSUPPORTED, "the bf16 mode is not built (use NF_PREC_TF32X3)");
   return 0;
 }
 

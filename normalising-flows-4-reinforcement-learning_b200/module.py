@@ -225,7 +225,7 @@ class RealNVP(nn.Module):
     Extra keyword arguments select the flax twin's semantics
     (/root/reference/unsupservised-gcrl/nf.py): ``first_hidden=channels+cond_channels`` (:94,101),
     ``ln_eps=1e-6`` (flax LayerNorm default), and ``precision``:
-    ``"fp32"`` (tcgen05 3xTF32, fp32-parity), ``"fp32_simt"`` (FFMA), ``"bf16"``.
+    ``"fp32"`` (tcgen05 3xTF32, fp32-parity) or ``"fp32_simt"`` (FFMA); the optional bf16 mode is not built.
 
     ``fast_param_grads`` (default on): ``loss.backward()`` writes all parameter gradients into one
     persistent flat arena with a single library call and points every ``p.grad`` at its view of that
