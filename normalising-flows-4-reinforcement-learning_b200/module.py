@@ -263,6 +263,7 @@ class RealNVP(nn.Module):
         self._gflat: Optional[torch.Tensor] = None
         self._gviews = None
         self._stash_pool = {}
+        self._neg_b = None
         self._xver = 0
         self._dp_group = None
         self._dp_world = 1
@@ -603,6 +604,37 @@ class RealNVP(nn.Module):
         if torch.is_grad_enabled() and (x.requires_grad or y.requires_grad or params):
             return _FlowNLL.apply(self, x, y, *params[:1])
         return -self.log_prob(x, y).mean()
+
+    def denoise(self, x, y, noise_std):
+        """One denoising step ``x + noise_std**2 * d/dx [log N(z; 0, I) + log_dets]`` -- the evaluation-time step of
+        torch_nfbc_ant.py:212-217 (clone, forward, ``autograd.grad(logprob.sum(), [action])``, in-place update) as one
+        call without an autograd graph: forward with a stash, the cotangents (dz = -z, dlogdet = 1) from the library's
+        NLL kernel, a backward that only produces dx (no parameter or y gradients), one axpy.  Returns a new tensor."""
+        self._check_inputs(x, y)
+        dev, B, D = x.device, x.shape[0], self.in_channels
+        x, y = _dense(x.detach()), _dense(y.detach())
+        if B == 0:
+            return x.clone()
+        z, logdet, _, stash, packed, slot = self._run_forward(x, y, True)
+        try:
+            with _on(dev):
+                # nf_nll_cotangents yields dz = g z / B, dlogdet = -g / B: g = -B gives the gradient of logprob.sum()
+                if self._neg_b is None or self._neg_b[0] != (B, dev):
+                    self._neg_b = ((B, dev), torch.full((4,), -float(B), dtype=torch.float32, device=dev))
+                g = self._neg_b[1]
+                dz = torch.empty_like(z)
+                dld = torch.empty((B,), dtype=torch.float32, device=dev)
+                _lib.check(lib.nf_nll_cotangents(z.data_ptr(), g.data_ptr(), B, D, dz.data_ptr(), dld.data_ptr(),
+                                                 self._stream(dev)), "nf_nll_cotangents")
+            dx, _, _ = self._run_backward(stash, packed, y, B, dz, dld, True, False, False)
+        finally:
+            if slot is not None:
+                slot.busy = False
+        return torch.add(x, dx, alpha=float(noise_std) ** 2)
+
+    def sample_denoised(self, y, noise_std, generator=None):
+        """``reverse(prior sample, y)`` followed by one ``denoise`` step (torch_nfbc_ant.py:207-217)."""
+        return self.denoise(self.sample(y, generator=generator), y, noise_std)
 
     def sample(self, y, generator=None):
         """reverse(prior sample, y) with a standard-normal prior (torch_nfbc_ant.py:209-210)."""

@@ -179,6 +179,51 @@ def test_denoise_step_input_gradient_only():
     assert rel_err(grad.cpu().numpy(), ref["dx"]) <= 2e-5
 
 
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_denoise_call_matches_the_reference_sequence(precision):
+    """RealNVP.denoise == the reference's clone / forward / autograd.grad / in-place update (torch_nfbc_ant.py:212-217),
+    with trainable parameters left alone (no gradients appear on them)."""
+    cfg = dict(D=9, C=64, R=24, n=3, B=50)
+    sd = synth.make_state_dict(9, 64, 24, 3, seed=4)
+    model = build_model(cfg, sd, precision)
+    x, y, _ = synth.make_safe_inputs(sd, 3, 50, 9, 24, seed=8)
+    noise_std = 0.1
+    out = model.denoise(t(x), t(y), noise_std)
+    assert all(p.grad is None for p in model.parameters())
+    sd64 = fo.cast_state_dict(sd, np.float64)
+    z64, _, _ = fo.flow_forward(sd64, 3, x.astype(np.float64), y.astype(np.float64))
+    ref = fo.flow_backward(sd64, 3, x.astype(np.float64), y.astype(np.float64), -z64, np.ones(50))
+    want = x.astype(np.float64) + noise_std ** 2 * ref["dx"]
+    assert rel_err(out.cpu().numpy(), want) <= 1e-5
+    # the same through autograd, as the reference script writes it
+    action = t(x).clone().requires_grad_(True)
+    z, _, ld = model(action, t(y))
+    (grad,) = torch.autograd.grad((-0.5 * (z * z).sum(1) + ld).sum(), [action])
+    assert rel_err(out.cpu().numpy(), (action.detach() + noise_std ** 2 * grad).cpu().numpy()) <= 1e-6
+    # sample + denoise stays close to the plain sample (a small step)
+    torch.manual_seed(0)
+    a = model.sample_denoised(t(y), noise_std)
+    assert a.shape == (50, 9) and torch.isfinite(a).all()
+
+
+def test_empty_batch():
+    """B = 0 (SURVEY section 8c edge cases): every call returns empty tensors and zero parameter gradients."""
+    cfg = dict(D=8, C=32, R=16, n=2, B=0)
+    sd = synth.make_state_dict(8, 32, 16, 2, seed=1)
+    model = build_model(cfg, sd, PRECISIONS[1])
+    x = torch.empty((0, 8), device="cuda:0", requires_grad=True)
+    y = torch.empty((0, 16), device="cuda:0")
+    z, outs, ld = model(x, y)
+    assert z.shape == (0, 8) and ld.shape == (0,) and len(outs) == 2 and outs[0].shape == (0, 8)
+    (z.sum() + ld.sum()).backward()
+    assert x.grad.shape == (0, 8)
+    for p in model.parameters():
+        if p.requires_grad:
+            assert p.grad is not None and float(p.grad.abs().max()) == 0.0
+    assert model.reverse(x.detach(), y).shape == (0, 8)
+    assert model.denoise(x.detach(), y, 0.1).shape == (0, 8)
+
+
 def test_standalone_affine_and_plu_kernels():
     lib = _lib.lib
     rs = np.random.RandomState(0)
