@@ -274,8 +274,9 @@ def run_ours(args):
                   for name, a, b in zip(("train", "sample", "e2e_train", "e2e_sample"), gstats[:-1], gstats[1:])}
     # the four timed legs above are short (tens of ms at the default K): keep the same kernels running until
     # nvidia-smi (100 ms period) has seen them under load; these extra steps are not part of any reported time
-    t_end = time.perf_counter() + 1.5
-    while time.perf_counter() < t_end:
+    # (a FIXED count derived from the max-reduced step time: with world > 1 every train_step contains the gradient
+    # all-reduce, so all ranks must run the same number of steps -- a wall-clock loop deadlocks the process group)
+    for _ in range(int(min(4000, max(10, 1500.0 / max(ms_train, 1e-3))))):
         train_step(x, y)
     torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
