@@ -196,6 +196,8 @@ def run_ours(args):
     model = model.to(dev)
     if world > 1:
         model.enable_data_parallel()
+        if os.environ.get("NF_B200_DP_BUCKET_BLOCKS"):     # experiment knob: overlapped bucketed all-reduce
+            model.dp_bucket_blocks = int(os.environ["NF_B200_DP_BUCKET_BLOCKS"])
     xh, yh = synth.make_inputs(B, D, R, seed=1234 + rank)
     x_pin, y_pin = torch.tensor(xh).pin_memory(), torch.tensor(yh).pin_memory()
     x, y = x_pin.to(dev), y_pin.to(dev)

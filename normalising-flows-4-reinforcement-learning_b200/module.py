@@ -267,6 +267,7 @@ class RealNVP(nn.Module):
         self._xver = 0
         self._dp_group = None
         self._dp_world = 1
+        self._dp_avg = False
         self._flatten()
         self.register_load_state_dict_post_hook(lambda module, keys: module._flatten())
 
@@ -510,12 +511,16 @@ class RealNVP(nn.Module):
         import torch.distributed as dist
         self._dp_group = process_group
         self._dp_world = dist.get_world_size(process_group)
+        self._dp_avg = dist.get_backend(process_group) == "nccl"     # NCCL averages inside the reduction
         return self
 
     def _allreduce_grads(self, dflat):
         import torch.distributed as dist
-        dist.all_reduce(dflat, op=dist.ReduceOp.SUM, group=self._dp_group)
-        dflat.mul_(1.0 / self._dp_world)
+        if self._dp_avg:
+            dist.all_reduce(dflat, op=dist.ReduceOp.AVG, group=self._dp_group)
+        else:
+            dist.all_reduce(dflat, op=dist.ReduceOp.SUM, group=self._dp_group)
+            dflat.mul_(1.0 / self._dp_world)
 
     # Blocks per gradient bucket of the overlapped all-reduce; 0 = one bucket (the whole arena after a single
     # backward call).  Measured on 2 B200s, C2a: per-block buckets cost more in launches (6 graph launches + 6 NCCL
