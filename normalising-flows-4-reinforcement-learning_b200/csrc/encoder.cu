@@ -6,6 +6,8 @@
 //   k_enc_ln_silu_bwd  du from dh, plus the column sums d gamma, d beta, d bias        (registers -> smem -> atomics)
 // SiLU follows the affine LayerNorm, so -- unlike the flow's LeakyReLU -> LN -> Linear -- gamma / beta cannot be
 // folded into the next Linear.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -148,26 +150,27 @@ __global__ void __launch_bounds__(256) k_enc_ln_silu_fwd(float* __restrict__ xh,
 // g: dh in, du out (in place).  a = gamma x_hat + beta, da = dh SiLU'(a), d x_hat = da gamma,
 // du = rstd (d x_hat - mean(d x_hat) - x_hat mean(d x_hat x_hat));  column sums over the CTA's rows:
 // dgamma += da x_hat, dbeta += da, dbias += du.
+// Warp per row, lane = NV float4 column groups.  Registers decide the occupancy here (the first version kept gamma,
+// beta and da live: 174 registers, one CTA per SM, 27 us for 8192 x 512 = 27 % of the HBM rate): gamma / beta are read
+// from shared memory, the column sums are accumulated as soon as their terms exist, and the eight warps' partial sums
+// are combined through shared memory (no shared atomics) before one global atomic per column per CTA.
 template <int NV>
-__global__ void __launch_bounds__(256) k_enc_ln_silu_bwd(float* __restrict__ g, const float* __restrict__ xh,
-                                                         const float* __restrict__ rstd,
-                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                         float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                         float* __restrict__ dbias, long long B, int H, int rows_per_cta) {
-  extern __shared__ float red[];   // [3][H]
+__global__ void __launch_bounds__(256, 2) k_enc_ln_silu_bwd(float* __restrict__ g, const float* __restrict__ xh,
+                                                            const float* __restrict__ rstd,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                            float* __restrict__ dbias, long long B, int H, int rows_per_cta) {
+  extern __shared__ float smem_f[];   // gamma [H], beta [H], then the flush area [8 warps][3][H]
   NF_PDL_ENTRY();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) red[i] = 0.f;
+  float* sg = smem_f;
+  float* sb = smem_f + H;
+  float* part = smem_f + 2 * H;
+  for (int i = threadIdx.x; i < H; i += blockDim.x) { sg[i] = __ldg(gamma + i); sb[i] = __ldg(beta + i); }
   __syncthreads();
-  float4 gm[NV], bt[NV], ag[NV], ab[NV], au[NV];
+  float4 ag[NV], ab[NV], au[NV];
 #pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    const int c4 = lane + 32 * k;
-    const bool ok = 4 * c4 < H;
-    gm[k] = ok ? __ldg(reinterpret_cast<const float4*>(gamma) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-    bt[k] = ok ? __ldg(reinterpret_cast<const float4*>(beta) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-    ag[k] = ab[k] = au[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
+  for (int k = 0; k < NV; ++k) ag[k] = ab[k] = au[k] = make_float4(0.f, 0.f, 0.f, 0.f);
   const long long r0 = (long long)blockIdx.x * rows_per_cta;
   const long long r1 = min(B, r0 + rows_per_cta);
   const float invH = 1.0f / (float)H;
@@ -184,18 +187,25 @@ __global__ void __launch_bounds__(256) k_enc_ln_silu_bwd(float* __restrict__ g, 
     }
     const float rs = rstd[row];
     float s1 = 0.f, s2 = 0.f;
-    float4 da[NV];
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
-      auto one = [&](float d, float xx, float gg, float bb) {
+      const int c4 = lane + 32 * k;
+      const bool ok = 4 * c4 < H;
+      const float4 gm = ok ? *reinterpret_cast<const float4*>(sg + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 bt = ok ? *reinterpret_cast<const float4*>(sb + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      // returns d x_hat; accumulates da x_hat and da
+      auto one = [&](float d, float xx, float gg, float bb, float& accg, float& accb) {
         const float a = fmaf(xx, gg, bb);
-        const float sg = 1.0f / (1.0f + expf(-a));
-        return d * sg * (1.0f + a * (1.0f - sg));
+        const float sgm = 1.0f / (1.0f + expf(-a));
+        const float da = d * sgm * (1.0f + a * (1.0f - sgm));
+        accg = fmaf(da, xx, accg);
+        accb += da;
+        return da * gg;
       };
-      da[k].x = one(dh[k].x, x[k].x, gm[k].x, bt[k].x); da[k].y = one(dh[k].y, x[k].y, gm[k].y, bt[k].y);
-      da[k].z = one(dh[k].z, x[k].z, gm[k].z, bt[k].z); da[k].w = one(dh[k].w, x[k].w, gm[k].w, bt[k].w);
-      // d x_hat kept in dh
-      dh[k].x = da[k].x * gm[k].x; dh[k].y = da[k].y * gm[k].y; dh[k].z = da[k].z * gm[k].z; dh[k].w = da[k].w * gm[k].w;
+      dh[k].x = one(dh[k].x, x[k].x, gm.x, bt.x, ag[k].x, ab[k].x);
+      dh[k].y = one(dh[k].y, x[k].y, gm.y, bt.y, ag[k].y, ab[k].y);
+      dh[k].z = one(dh[k].z, x[k].z, gm.z, bt.z, ag[k].z, ab[k].z);
+      dh[k].w = one(dh[k].w, x[k].w, gm.w, bt.w, ag[k].w, ab[k].w);
       s1 += (dh[k].x + dh[k].y) + (dh[k].z + dh[k].w);
       s2 = fmaf(dh[k].x, x[k].x, fmaf(dh[k].y, x[k].y, fmaf(dh[k].z, x[k].z, fmaf(dh[k].w, x[k].w, s2))));
     }
@@ -207,26 +217,27 @@ __global__ void __launch_bounds__(256) k_enc_ln_silu_bwd(float* __restrict__ g, 
       du.x = rs * (dh[k].x - m1 - x[k].x * m2); du.y = rs * (dh[k].y - m1 - x[k].y * m2);
       du.z = rs * (dh[k].z - m1 - x[k].z * m2); du.w = rs * (dh[k].w - m1 - x[k].w * m2);
       if (4 * c4 < H) gr[c4] = du;
-      ag[k].x = fmaf(da[k].x, x[k].x, ag[k].x); ag[k].y = fmaf(da[k].y, x[k].y, ag[k].y);
-      ag[k].z = fmaf(da[k].z, x[k].z, ag[k].z); ag[k].w = fmaf(da[k].w, x[k].w, ag[k].w);
-      ab[k].x += da[k].x; ab[k].y += da[k].y; ab[k].z += da[k].z; ab[k].w += da[k].w;
       au[k].x += du.x; au[k].y += du.y; au[k].z += du.z; au[k].w += du.w;
     }
   }
+  // flush: warp w writes its partial sums to part[w][3][H]; then every thread adds the eight partials of its outputs
+  float* mine = part + (size_t)warp * 3 * H;
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
     const int c = 4 * (lane + 32 * k);
     if (c < H) {
-      atomicAdd(&red[c], ag[k].x); atomicAdd(&red[c + 1], ag[k].y); atomicAdd(&red[c + 2], ag[k].z); atomicAdd(&red[c + 3], ag[k].w);
-      atomicAdd(&red[H + c], ab[k].x); atomicAdd(&red[H + c + 1], ab[k].y); atomicAdd(&red[H + c + 2], ab[k].z); atomicAdd(&red[H + c + 3], ab[k].w);
-      atomicAdd(&red[2 * H + c], au[k].x); atomicAdd(&red[2 * H + c + 1], au[k].y); atomicAdd(&red[2 * H + c + 2], au[k].z); atomicAdd(&red[2 * H + c + 3], au[k].w);
+      *reinterpret_cast<float4*>(mine + c) = ag[k];
+      *reinterpret_cast<float4*>(mine + H + c) = ab[k];
+      *reinterpret_cast<float4*>(mine + 2 * H + c) = au[k];
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < H; i += blockDim.x) {
-    atomicAdd(&dgamma[i], red[i]);
-    atomicAdd(&dbeta[i], red[H + i]);
-    atomicAdd(&dbias[i], red[2 * H + i]);
+  for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += part[(size_t)w * 3 * H + i];
+    float* dst = i < H ? dgamma + i : (i < 2 * H ? dbeta + (i - H) : dbias + (i - 2 * H));
+    atomicAdd(dst, v);
   }
 }
 
@@ -244,6 +255,8 @@ __global__ void __launch_bounds__(128) k_enc_colsum(const float* __restrict__ A,
 
 int rows_per_cta_for(long long B) {
   // enough CTAs for two waves on 148 SMs, at least 32 rows each (fewer global atomics per row)
+  static const int forced = [] { const char* e = getenv("NF_B200_ENC_RPC"); return e ? atoi(e) : 0; }();
+  if (forced > 0) return forced;
   long long rpc = cdiv(B, 296);
   rpc = std::max<long long>(32, cdiv(rpc, 8) * 8);
   return (int)rpc;
@@ -269,8 +282,19 @@ int ln_silu_bwd(float* g, const float* xh, const float* rstd, const float* gamma
   if (B <= 0) return 0;
   const int rpc = rows_per_cta_for(B);
   const unsigned grid = (unsigned)cdiv(B, rpc);
-  const size_t smem = (size_t)3 * H * sizeof(float);
+  const size_t smem = (size_t)(2 + 8 * 3) * H * sizeof(float);   // gamma, beta, 8 warps x 3 partial-sum rows
   const int nv = (int)cdiv(H, 128);
+  {
+    static bool configured = false;   // more than 48 KB of dynamic shared memory from hidden = 512 on
+    if (!configured) {
+      constexpr int kMax = (2 + 8 * 3) * 128 * kEncMaxV * (int)sizeof(float);
+      NF_CUDA(cudaFuncSetAttribute(k_enc_ln_silu_bwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax));
+      NF_CUDA(cudaFuncSetAttribute(k_enc_ln_silu_bwd<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax));
+      NF_CUDA(cudaFuncSetAttribute(k_enc_ln_silu_bwd<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax));
+      NF_CUDA(cudaFuncSetAttribute(k_enc_ln_silu_bwd<kEncMaxV>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax));
+      configured = true;
+    }
+  }
   switch (nv) {
     case 1: NF_LAUNCH((k_enc_ln_silu_bwd<1>), grid, 256, smem, st, g, xh, rstd, gamma, beta, dgamma, dbeta, dbias, B, H, rpc); break;
     case 2: NF_LAUNCH((k_enc_ln_silu_bwd<2>), grid, 256, smem, st, g, xh, rstd, gamma, beta, dgamma, dbeta, dbias, B, H, rpc); break;

@@ -92,7 +92,9 @@ def run_encoder(name, B, iters=30):
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "encoder":
-        run_encoder("gcbc", 4096); run_encoder("kitchen", 8192); run_encoder("ant", 256)
+        for nm, b in (("gcbc", 4096), ("kitchen", 8192), ("ant", 256)):
+            if len(sys.argv) < 3 or sys.argv[2] == nm:
+                run_encoder(nm, b)
         sys.exit(0)
     names = sys.argv[1].split(",") if len(sys.argv) > 1 else ["C2a", "C3", "C4", "C1a", "C5"]
     for nm in names:
