@@ -94,32 +94,41 @@ def config_of(name):
 
 
 # --------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference algorithm on the host cores
+# CPU arm: the reference's op sequence in stock PyTorch (oracle/torch_flow.py) on the host cores
 # --------------------------------------------------------------------------------------------------
+LOG2PI = float(np.log(2 * np.pi))
+
+
 def cpu_step_fn(cfgname, B, seed=0):
-    from oracle import flow_oracle as fo
+    """The reference's CPU path: oracle/torch_flow.py, the stock-PyTorch restatement of the reference module (the same
+    nn.Linear / LayerNorm / cat / exp ops + autograd; pinned to the reference-generated fixtures by
+    tests/test_oracle_golden.py), on all host threads.  (The numpy oracle is the parity checker, not the baseline: it is
+    ~6x slower than the reference's torch path on the same cores.)"""
+    import torch
     from oracle import synth
+    from oracle.torch_flow import TorchFlow
+    torch.set_num_threads(os.cpu_count())      # torchrun exports OMP_NUM_THREADS=1
     cfg = config_of(cfgname)
     sd = synth.make_state_dict(cfg["D"], cfg["C"], cfg["R"], cfg["n"], seed=seed, H1=cfg["H1"])
+    model = TorchFlow(cfg["D"], cfg["C"], cfg["R"], cfg["n"], first_hidden=cfg["H1"], ln_eps=cfg["ln_eps"])
+    model.load_state_dict({k: torch.tensor(v) for k, v in sd.items()})
     x, y = synth.make_inputs(B, cfg["D"], cfg["R"], seed=1234)
+    x, y = torch.tensor(x), torch.tensor(y)
     D = cfg["D"]
+    plist = [p for p in model.parameters() if p.requires_grad]
 
     def train():
-        z, _, ld = fo.flow_forward(sd, cfg["n"], x, y, cfg["ln_eps"])   # forward for the loss cotangents
-        dz = (z / B).astype(np.float32)
-        dld = np.full(B, -1.0 / B, dtype=np.float32)
-        fo.flow_backward(sd, cfg["n"], x, y, dz, dld, cfg["ln_eps"])     # forward (again, with caches) + backward
-
-    def train_once():
-        # one forward with caches + backward, like loss.backward() after a forward
-        dz = (x / B).astype(np.float32)
-        dld = np.full(B, -1.0 / B, dtype=np.float32)
-        fo.flow_backward(sd, cfg["n"], x, y, dz, dld, cfg["ln_eps"])
+        for p in plist:
+            p.grad = None
+        yy = y.detach().requires_grad_(True)
+        z, _, ld = model(x, yy)
+        (-((-0.5 * (z * z).sum(1) - 0.5 * D * LOG2PI) + ld).mean()).backward()
 
     def sample():
-        fo.flow_reverse(sd, cfg["n"], x, y, cfg["ln_eps"])
+        with torch.no_grad():
+            model.reverse(x, y)
 
-    return train_once, sample
+    return train, sample
 
 
 def time_cpu(fn, min_seconds, max_iters):
@@ -135,7 +144,7 @@ def time_cpu(fn, min_seconds, max_iters):
 
 
 def run_reference_arm(args):
-    """--impl reference: the reference's CPU path (oracle port, numpy + multithreaded BLAS)."""
+    """--impl reference: the reference's CPU path (stock-PyTorch restatement of the reference module, all host threads)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -159,8 +168,8 @@ def run_reference_arm(args):
         "config": {"workload": f"{cfgname} coupling flow, batch {B} per step on the host CPU", **config_of(cfgname)},
         "sampling": {"value": B / ts, "unit": "actions/s"},
         "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} steps of forward+backward at batch {B} (numpy oracle port, "
-                                   f"OpenBLAS threads = {cores})"},
+                         "sample": f"{args.steps} steps of forward+backward at batch {B} (oracle/torch_flow.py: the "
+                                   f"reference's op sequence in stock PyTorch on the host, {cores} threads)"},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(out), flush=True)
@@ -202,7 +211,6 @@ def run_ours(args):
     x_pin, y_pin = torch.tensor(xh).pin_memory(), torch.tensor(yh).pin_memory()
     x, y = x_pin.to(dev), y_pin.to(dev)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
-    LOG2PI = float(np.log(2 * np.pi))
 
     plist = [p for p in model.parameters() if p.requires_grad]
 
@@ -331,14 +339,18 @@ def run_ours(args):
         "breakdown": breakdown,
     }
 
-    # ---- CPU baseline: the oracle port on this box's host cores, bounded sample --------------------
-    Bc = min(B, 4096)
-    ctrain, csample = cpu_step_fn(cfgname, Bc)
-    per, iters = time_cpu(ctrain, 8.0, 40)
-    cores = os.cpu_count()
-    cpu_baseline = {"value": Bc / per, "unit": "samples/s", "cores": cores, "kind": "port",
-                    "sample": f"{iters} steps of forward+backward at batch {Bc} of the same config "
-                              f"(numpy oracle port, {cores} BLAS threads, {per * iters:.1f} s)"}
+    # ---- CPU baseline: the reference's op sequence in stock PyTorch on this box's host cores, bounded sample,
+    # at N = 1 only (the other ranks of a multi-GPU run would just wait for it) -----------------------------------
+    cpu_baseline = None
+    if world == 1:
+        Bc = min(B, 4096)
+        ctrain, csample = cpu_step_fn(cfgname, Bc)
+        per, iters = time_cpu(ctrain, 10.0, 200)
+        cores = os.cpu_count()
+        cpu_baseline = {"value": Bc / per, "unit": "samples/s", "cores": cores, "kind": "port",
+                        "sample": f"{iters} steps of forward+backward at batch {Bc} of the same config "
+                                  f"(oracle/torch_flow.py: the reference's op sequence in stock PyTorch on the host, "
+                                  f"{cores} threads, {per * iters:.1f} s)"}
 
     bytes_in = x_pin.numel() * 4 + y_pin.numel() * 4
     out = {
