@@ -153,7 +153,9 @@ def make_encoder_state_dict(input_size: int, rep_size: int, seed: int = 0, hidde
         fan = hidden
     sd["fc_out.weight"] = uni((rep_size, hidden), hidden)
     sd["fc_out.bias"] = uni((rep_size,), hidden)
-    return OrderedDict((k, np.ascontiguousarray(v, dtype=dtype)) for k, v in sd.items())
+    # the reference registers fc1..fcN, fc_out, then norm1..normN (torch_fcnf.py:160-169): same key order here
+    order = [k for k in sd if k.startswith("fc")] + [k for k in sd if k.startswith("norm")]
+    return OrderedDict((k, np.ascontiguousarray(sd[k], dtype=dtype)) for k in order)
 
 
 def make_encoder_inputs(B: int, input_size: int, rep_size: int, seed: int = 77, dtype=np.float32):

@@ -113,3 +113,49 @@ def test_flops_formula():
     assert abs(synth.flops_fwd_per_sample(**synth.CONFIGS["C2a"]) / 1e6 - 2.016) < 0.01
     assert abs(synth.flops_fwd_per_sample(**synth.CONFIGS["C4"]) / 1e6 - 37.97) < 0.05
     assert abs(synth.flops_fwd_per_sample(**synth.CONFIGS["C5"]) / 1e6 - 129.02) < 0.05
+
+
+# ------------------------------------------------------------------ conditioning encoder (row f2)
+@pytest.mark.parametrize("input_size,rep_size,hidden,n_hidden", [(58, 64, 512, 4), (29, 10, 64, 2), (600, 1024, 512, 4)])
+def test_encoder_layout_matches_reference_state_dict(input_size, rep_size, hidden, n_hidden):
+    m = nf_b200.GEncoder(input_size, rep_size, hidden=hidden, n_hidden=n_hidden)
+    ref_sd = synth.make_encoder_state_dict(input_size, rep_size, hidden=hidden, n_hidden=n_hidden)
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(ref_sd.keys())            # fc1.., fc_out, norm1..: the reference's order
+    for k in sd:
+        assert tuple(sd[k].shape) == ref_sd[k].shape, k
+    # slots are 16-byte aligned, disjoint, in arena order, and the parameters are views of the arena
+    end = 0
+    for p, off in m._slots:
+        assert off % 4 == 0 and off >= end
+        assert p.data_ptr() == m._flat.data_ptr() + 4 * off
+        end = off + p.numel()
+    assert end <= m._total
+    # load_state_dict keeps the views and copies the values
+    m.load_state_dict({k: torch.tensor(v) for k, v in ref_sd.items()})
+    assert m._is_flat()
+    np.testing.assert_array_equal(m.fc_out.weight.detach().numpy(), ref_sd["fc_out.weight"])
+    d = m._desc
+    assert _lib.lib.nf_encoder_stash_bytes(ctypes.byref(d), 100) >= 4 * (100 * input_size + n_hidden * 2 * 100 * hidden)
+    assert _lib.lib.nf_encoder_workspace_bytes(ctypes.byref(d), 100) >= 4 * 2 * 100 * hidden
+
+
+def test_encoder_bad_arguments():
+    bad = _lib.NfEncoderDesc(58, 510, 64, 4, 1e-5, 1)          # hidden not a multiple of 4
+    assert _lib.lib.nf_encoder_param_layout(ctypes.byref(bad), None) == -1
+    assert b"hidden" in _lib.lib.nf_last_error()
+    assert _lib.lib.nf_encoder_stash_bytes(ctypes.byref(bad), 8) == -1
+    deep = _lib.NfEncoderDesc(58, 512, 64, 9, 1e-5, 1)          # more hidden layers than the ABI allows
+    assert _lib.lib.nf_encoder_workspace_bytes(ctypes.byref(deep), 8) == -1
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        nf_b200.GEncoder(8, 4, hidden=16, n_hidden=1)(torch.zeros(2, 8))
+    with pytest.raises(ValueError):
+        nf_b200.GEncoder(8, 4, precision="bf16")
+
+
+def test_reduced_precision_mode_is_rejected_not_silently_downgraded():
+    with pytest.raises(ValueError):
+        nf_b200.RealNVP(8, 32, 16, 2, None, precision="bf16")
+    d = _lib.make_desc(8, 32, 32, 16, 2, 1e-5, 2)              # NF_PREC_BF16 through the raw ABI
+    out = _lib.NfParamLayout()
+    assert _lib.lib.nf_param_layout(ctypes.byref(d), ctypes.byref(out)) == -4   # NF_E_UNSUPPORTED
