@@ -71,6 +71,7 @@ class GEncoder(nn.Module):
         self._flat = None
         self._ws = None
         self._stash_pool = {}
+        self._dp_group, self._dp_world, self._dp_avg = None, 1, False
         self._flatten()
         self.register_load_state_dict_post_hook(lambda module, keys: module._flatten())
 
@@ -175,7 +176,27 @@ class GEncoder(nn.Module):
                                                stash.data_ptr(), B, dout.data_ptr(),
                                                dg.data_ptr() if dg is not None else None, dflat.data_ptr(),
                                                ws.data_ptr(), ws.numel(), self._stream(dev)), "nf_encoder_backward")
+            if self._dp_world > 1:
+                self._allreduce_grads(dflat)
         return dg, dflat
+
+    # ------------------------------------------------------------------ data parallel
+    def enable_data_parallel(self, process_group=None):
+        """Batch-sharded data parallel training, like ``RealNVP.enable_data_parallel``: backward averages the flat
+        gradient arena over the ranks of ``process_group`` (one all-reduce) before the views are handed to autograd."""
+        import torch.distributed as dist
+        self._dp_group = process_group
+        self._dp_world = dist.get_world_size(process_group)
+        self._dp_avg = dist.get_backend(process_group) == "nccl"
+        return self
+
+    def _allreduce_grads(self, dflat):
+        import torch.distributed as dist
+        if self._dp_avg:
+            dist.all_reduce(dflat, op=dist.ReduceOp.AVG, group=self._dp_group)
+        else:
+            dist.all_reduce(dflat, op=dist.ReduceOp.SUM, group=self._dp_group)
+            dflat.mul_(1.0 / self._dp_world)
 
     def forward(self, g: torch.Tensor) -> torch.Tensor:
         self._check(g)

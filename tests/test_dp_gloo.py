@@ -47,6 +47,13 @@ def _worker(rank, world, port, ret):
         flat = model._flat.clone()
         dist.all_reduce(flat)
         ok = ok and torch.allclose(flat, model._flat * world)
+        # the conditioning encoder averages its arena the same way
+        enc = nf_b200.GEncoder(12, 6, hidden=16, n_hidden=2).enable_data_parallel()
+        eflat = torch.full((enc._total,), float(rank + 1))
+        eviews = enc._grad_views(eflat)
+        enc._allreduce_grads(eflat)
+        ok = ok and torch.allclose(eflat, torch.full((enc._total,), sum(range(1, world + 1)) / world))
+        ok = ok and eviews[0].data_ptr() == eflat.data_ptr() + 4 * enc._slots[0][1]
         # rank-sharded synthetic inputs (bench.py uses seed 1234 + rank)
         x, _ = synth.make_inputs(8, 9, 16, seed=1234 + rank)
         xs = [torch.zeros(8, 9) for _ in range(world)]
