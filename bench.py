@@ -224,6 +224,16 @@ def run_ours(args):
         loss.backward()
         return loss
 
+    def train_step_nll(xd, yd):
+        # the same step with the library's fused loss (RealNVP.nll: SURVEY section 8 row f3) instead of the ~8 torch
+        # kernels + autograd nodes of the reference's loss expression
+        model._packed_key = None
+        for p in plist:
+            p.grad = None
+        loss = model.nll(xd, yd.detach().requires_grad_(True))
+        loss.backward()
+        return loss
+
     def sample_step(xd, yd):
         with torch.no_grad():
             return model.reverse(xd, yd)
@@ -280,6 +290,7 @@ def run_ours(args):
     gstats.append(_lib.graph_stats())
     ms_e2e_sample, _ = timed(sample_step, args.steps, args.warmup, e2e=True)
     gstats.append(_lib.graph_stats())
+    ms_e2e_nll, _ = timed(train_step_nll, args.steps, args.warmup, e2e=True)   # informational, not the headline
     leg_graphs = {name: dict(zip(("replays", "captures", "eager_calls"), (b[i] - a[i] for i in range(3))))
                   for name, a, b in zip(("train", "sample", "e2e_train", "e2e_sample"), gstats[:-1], gstats[1:])}
     # the four timed legs above are short (tens of ms at the default K): keep the same kernels running until
@@ -366,7 +377,11 @@ def run_ours(args):
         "e2e": {"value": total_B / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": bytes_in,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e, "ms_median_max": list(step_stats[2]),
                 "sampling": {"value": total_B / (ms_e2e_sample * 1e-3), "unit": "actions/s",
-                             "d2h_bytes_per_step": 4, "ms_median_max": list(step_stats[3])}},
+                             "d2h_bytes_per_step": 4, "ms_median_max": list(step_stats[3])},
+                "with_fused_loss": {"value": total_B / (ms_e2e_nll * 1e-3), "unit": "samples/s",
+                                    "ms_per_step": ms_e2e_nll,
+                                    "note": "same end-to-end step with loss = model.nll(x, y) (library NLL kernels) "
+                                            "instead of the reference's torch-side loss expression"}},
         "gpu_launches": int(launches * args.steps),
         "gpu_launches_per_step": int(launches),
         "launch_graphs": {"replays": replays, "captures": captures, "eager_calls": eager, "per_leg": leg_graphs,
