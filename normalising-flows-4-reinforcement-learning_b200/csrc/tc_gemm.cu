@@ -409,7 +409,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&split[s], 4); mbar_init(&empty[s], 1); }
     mbar_init(accbar, 1);
     if (TS) for (int i = 0; i < kASlots; ++i) mbar_init(&aempty[i], 1);
-    if (EPI != EPI_NONE) mbar_init(xbar, (uint32_t)a.ncl * 128u);
+    if (EPI != EPI_NONE) mbar_init(xbar, (uint32_t)a.ncl * 128u * NSG);
     if (EPI == EPI_LN_FWD) mbar_init(tbar, 2u * (uint32_t)a.ncl * 128u);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -689,11 +689,17 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
       //   EPI_LN_BWD: du = LeakyReLU'(mask) rstd (g - mean(g) - x_hat mean(g x_hat)),  g = acc
       const int rit = q * 32 + lane;
       const bool rowok = row < a.M;
-      float v[BN];
+      // the NSG splitter groups share the tile's columns: this thread owns columns [cg0, cg0 + CW) of its row (half
+      // the registers per thread, which is what lets the 320-thread kernel keep the row in registers without spills)
+      constexpr int CW = BN / NSG;
+      const int gq = NSG > 1 ? grp : 0;
+      const int cg0 = gq * CW;
+      const bool tail = NSG == 1 && a.tail;
+      float v[CW];
 #pragma unroll
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = 0; c0 < CW; c0 += 32) {
         float r[32];
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c0);
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(cg0 + c0);
         tmem_ld_sum<BN, NACC>(taddr, nacc_used, with_corr, r);
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[c0 + j] = r[j];
@@ -705,54 +711,55 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
       // LayerNorm exchange stays inside the net's ncl CTAs
       const uint32_t rank_base = (EPI == EPI_LN_FWD && a.tail) ? (uint32_t)z * (uint32_t)ncl : 0u;
       const uint32_t my_rank = cluster_ctarank() - rank_base;
-      float* sxh = reinterpret_cast<float*>(smem) + q * (32 * (BN + 4));              // bwd: this warp's x_hat tile
-      float* sx = reinterpret_cast<float*>(smem) + 4 * 32 * (BN + 4) + q * kXWarpFloats;   // 32 x 32 transposition buffer
-      float* cwarp = a.C + (long long)z * a.sC + (long long)(m0 + q * 32) * a.ldc + n0;
+      float* sxh = reinterpret_cast<float*>(smem) + (gq * 4 + q) * (32 * (CW + 4));   // bwd: this warp's x_hat tile
+      float* sx = reinterpret_cast<float*>(smem) + NSG * 4 * 32 * (CW + 4) + (gq * 4 + q) * kXWarpFloats;   // 32 x 32 transposition buffer
+      float* cwarp = a.C + (long long)z * a.sC + (long long)(m0 + q * 32) * a.ldc + n0 + cg0;
       const int rows_valid_w = a.M - (m0 + q * 32);
       // TMA-store boxes (4 KB each, 1024-byte aligned): after the x_hat tiles / transposition buffers
-      uint8_t* boxes = smem + ((4 * 32 * (BN + 4) * 4 + 4 * kXWarpFloats * 4 + 1023) & ~1023) + q * (BN / 32) * 4096;
-      float p0, p1;            // the two partial statistics of this CTA's BN columns
-      uint32_t mbits[BN / 32];
+      uint8_t* boxes = smem + ((NSG * 4 * 32 * (CW + 4) * 4 + NSG * 4 * kXWarpFloats * 4 + 1023) & ~1023) +
+                       (q * (BN / 32) + (cg0 >> 5)) * 4096;
+      float p0, p1;            // the two partial statistics of this thread's CW columns
+      uint32_t mbits[CW / 32];
       if constexpr (EPI == EPI_LN_FWD) {
-        const float* bias = a.bias ? a.bias + (long long)z * a.sBias + n0 : nullptr;
+        const float* bias = a.bias ? a.bias + (long long)z * a.sBias + n0 + cg0 : nullptr;
         float sum = 0.f;
 #pragma unroll
-        for (int c = 0; c < BN; ++c) {
+        for (int c = 0; c < CW; ++c) {
           const float pre = v[c] + (bias ? __ldg(bias + c) : 0.f);
           if ((c & 31) == 0) mbits[c >> 5] = 0u;
           if (pre > 0.f) mbits[c >> 5] |= 1u << (c & 31);
           v[c] = pre > 0.f ? pre : kLeakySlope * pre;
           sum += v[c];
         }
-        p0 = sum * (1.0f / BN);                     // local mean
+        p0 = sum * (1.0f / CW);                     // local mean
         float m2 = 0.f;
 #pragma unroll
-        for (int c = 0; c < BN; ++c) { const float d = v[c] - p0; m2 = fmaf(d, d, m2); }
+        for (int c = 0; c < CW; ++c) { const float d = v[c] - p0; m2 = fmaf(d, d, m2); }
         p1 = m2;                                    // local centred sum of squares
       } else {
         // x_hat tile of this warp's 32 rows -> shared memory with coalesced 128-bit loads (the operand
         // stages are free now); both passes then read the lane's own row from there
-        const float* xw = a.xh + (long long)z * a.sXh + (long long)(m0 + q * 32) * a.ldxh + n0;
+        const float* xw = a.xh + (long long)z * a.sXh + (long long)(m0 + q * 32) * a.ldxh + n0 + cg0;
         const int rows_valid = a.M - (m0 + q * 32);
 #pragma unroll 8
-        for (int idx = lane; idx < 32 * (BN / 4); idx += 32) {
-          const int r = idx / (BN / 4), c4 = idx % (BN / 4);
+        for (int idx = lane; idx < 32 * (CW / 4); idx += 32) {
+          const int r = idx / (CW / 4), c4 = idx % (CW / 4);
           const float4 t = r < rows_valid ? __ldg(reinterpret_cast<const float4*>(xw + (long long)r * a.ldxh) + c4)
                                           : make_float4(0.f, 0.f, 0.f, 0.f);
-          *reinterpret_cast<float4*>(sxh + r * (BN + 4) + 4 * c4) = t;
+          *reinterpret_cast<float4*>(sxh + r * (CW + 4) + 4 * c4) = t;
         }
         __syncwarp();
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-        for (int c = 0; c < BN; c += 4) {
-          const float4 x = *reinterpret_cast<const float4*>(sxh + lane * (BN + 4) + c);
+        for (int c = 0; c < CW; c += 4) {
+          const float4 x = *reinterpret_cast<const float4*>(sxh + lane * (CW + 4) + c);
           s1 += (v[c] + v[c + 1]) + (v[c + 2] + v[c + 3]);
           s2 = fmaf(v[c], x.x, fmaf(v[c + 1], x.y, fmaf(v[c + 2], x.z, fmaf(v[c + 3], x.w, s2))));
         }
         p0 = s1; p1 = s2;
       }
       // push to every CTA of the cluster (own included), then wait for everyone's partials
-      const uint32_t slot = smem_u32(&xchg[my_rank * 128 + rit]);
+      const uint32_t slot = smem_u32(&xchg[(my_rank * NSG + gq) * 128 + rit]);   // [rank][group][row in tile]
       const uint32_t xb = smem_u32(xbar);
       for (int pr = 0; pr < ncl; ++pr) {
         st_cluster_v2(mapa_u32(slot, rank_base + (uint32_t)pr), p0, p1);
@@ -760,17 +767,17 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
       }
       mbar_wait_cluster(xbar, 0);
       if (threadIdx.x == 64) NF_TS(6);   // statistics exchanged
-      float* crow = a.C + (long long)z * a.sC + (long long)row * a.ldc + n0;
+      float* crow = a.C + (long long)z * a.sC + (long long)row * a.ldc + n0 + cg0;
       if constexpr (EPI == EPI_LN_FWD) {
         // combine equal-sized groups (Chan et al.): mean = avg(mean_i), M2 = sum M2_i + BN sum (mean_i - mean)^2
         float mean = 0.f;
-        for (int pr = 0; pr < ncl; ++pr) mean += xchg[pr * 128 + rit].x;
-        mean /= (float)ncl;
+        for (int pr = 0; pr < ncl * NSG; ++pr) mean += xchg[pr * 128 + rit].x;
+        mean /= (float)(ncl * NSG);
         float m2 = 0.f;
-        for (int pr = 0; pr < ncl; ++pr) {
+        for (int pr = 0; pr < ncl * NSG; ++pr) {
           const float2 s = xchg[pr * 128 + rit];
           const float d = s.x - mean;
-          m2 += s.y + (float)BN * d * d;
+          m2 += s.y + (float)CW * d * d;
         }
         const float rstd = rsqrtf(m2 / (float)(ncl * BN) + a.eps);
         // fused tail: this CTA's slice of the folded last Linear, W3f[net][i][n0 .. n0 + BN), in shared memory
@@ -778,7 +785,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
         float* sW3 = reinterpret_cast<float*>(smem + 160 * 1024);          // [4][BN]
         float* sWm = sW3 + 4 * BN;                                          // [D][D] (leader)
         float part[4] = {0.f, 0.f, 0.f, 0.f};
-        if (a.tail) {
+        if (tail) {
           const int te = threadIdx.x - 64;
           for (int idx = te; idx < 4 * BN; idx += 128) {
             const int i = idx / BN, c = idx - i * BN;
@@ -789,11 +796,11 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
           asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps
         }
 #pragma unroll
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = 0; c0 < CW; c0 += 32) {
           float o[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) o[j] = (v[c0 + j] - mean) * rstd;
-          if (a.tail) {
+          if (tail) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
 #pragma unroll
@@ -809,7 +816,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
             box_put(box, lane, o);
             // one store per 32-column chunk: the TMA drains the box while the next chunk is computed (issuing
             // all stores of the tile at the end behind a single proxy fence measured 20 % slower)
-            if (elect_one()) { tma_store_3d(&mC, box, n0 + c0, m0 + q * 32, z); tma_store_commit(); }
+            if (elect_one()) { tma_store_3d(&mC, box, n0 + cg0 + c0, m0 + q * 32, z); tma_store_commit(); }
             __syncwarp();
           } else {
             xpose_put(sx, lane, o);
@@ -824,13 +831,13 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
         }
         if (rowok) {
           if (a.mask) {
-            uint32_t* mk = a.mask + (long long)z * a.sMask + (long long)row * a.mw + (n0 >> 5);
+            uint32_t* mk = a.mask + (long long)z * a.sMask + (long long)row * a.mw + ((n0 + cg0) >> 5);
 #pragma unroll
-            for (int w = 0; w < BN / 32; ++w) mk[w] = mbits[w];
+            for (int w = 0; w < CW / 32; ++w) mk[w] = mbits[w];
           }
-          if (a.rstd && my_rank == 0) a.rstd[(long long)z * a.sRstd + row] = rstd;
+          if (a.rstd && my_rank == 0 && cg0 == 0) a.rstd[(long long)z * a.sRstd + row] = rstd;
         }
-        if (a.tail) {
+        if (tail) {
           // partial last-Linear outputs of this CTA's columns -> the cluster's leader CTA (rank 0)
           float4* tpart = reinterpret_cast<float4*>(smem + S::TPART);     // [rank][row in tile]
           const uint32_t crank = cluster_ctarank();
@@ -898,23 +905,23 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
         }
       } else {
         float s1 = 0.f, s2 = 0.f;
-        for (int pr = 0; pr < ncl; ++pr) { const float2 s = xchg[pr * 128 + rit]; s1 += s.x; s2 += s.y; }
+        for (int pr = 0; pr < ncl * NSG; ++pr) { const float2 s = xchg[pr * 128 + rit]; s1 += s.x; s2 += s.y; }
         const float inv = 1.0f / (float)(ncl * BN);
         s1 *= inv; s2 *= inv;
         float rs_row = 0.f;
         if (rowok) {
           rs_row = a.rstd[(long long)z * a.sRstd + row];
-          const uint32_t* mk = a.mask + (long long)z * a.sMask + (long long)row * a.mw + (n0 >> 5);
+          const uint32_t* mk = a.mask + (long long)z * a.sMask + (long long)row * a.mw + ((n0 + cg0) >> 5);
 #pragma unroll
-          for (int w = 0; w < BN / 32; ++w) mbits[w] = mk[w];
+          for (int w = 0; w < CW / 32; ++w) mbits[w] = mk[w];
         }
 #pragma unroll
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = 0; c0 < CW; c0 += 32) {
           float o[32];
           const uint32_t bits = mbits[c0 >> 5];
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            const float4 x = *reinterpret_cast<const float4*>(sxh + lane * (BN + 4) + c0 + j);
+            const float4 x = *reinterpret_cast<const float4*>(sxh + lane * (CW + 4) + c0 + j);
             o[j] = rs_row * (v[c0 + j] - s1 - x.x * s2) * (((bits >> j) & 1u) ? 1.0f : kLeakySlope);
             o[j + 1] = rs_row * (v[c0 + j + 1] - s1 - x.y * s2) * (((bits >> (j + 1)) & 1u) ? 1.0f : kLeakySlope);
             o[j + 2] = rs_row * (v[c0 + j + 2] - s1 - x.z * s2) * (((bits >> (j + 2)) & 1u) ? 1.0f : kLeakySlope);
@@ -925,7 +932,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
             box_put(box, lane, o);
             // one store per 32-column chunk: the TMA drains the box while the next chunk is computed (issuing
             // all stores of the tile at the end behind a single proxy fence measured 20 % slower)
-            if (elect_one()) { tma_store_3d(&mC, box, n0 + c0, m0 + q * 32, z); tma_store_commit(); }
+            if (elect_one()) { tma_store_3d(&mC, box, n0 + cg0 + c0, m0 + q * 32, z); tma_store_commit(); }
             __syncwarp();
           } else {
             xpose_put(sx, lane, o);
@@ -1139,12 +1146,15 @@ int launch(const TcGemmP& p, cudaStream_t st) {
   return 0;
 }
 
-template <int BN, int STAGES, int BK, int EPI, bool TS = false>
+// NSG = 2 (TS only): two splitter groups on alternating stages; the row-wise epilogue then splits the tile's columns
+// between the groups (the fused flow tail needs the whole row in one thread and keeps NSG = 1)
+template <int BN, int STAGES, int BK, int EPI, bool TS = false, int NSG = 1>
 int launch_epi(const TcGemmP& p, cudaStream_t st) {
   using S = Smem<BN, STAGES, BK, TS>;
+  static_assert(NSG == 1 || (TS && (BN / NSG) % 32 == 0), "two splitter groups need the TS form and 32-column slices");
   static bool configured = false;
   if (!configured) {
-    NF_CUDA(cudaFuncSetAttribute(k_tc_gemm<BN, STAGES, false, BK, EPI, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    NF_CUDA(cudaFuncSetAttribute(k_tc_gemm<BN, STAGES, false, BK, EPI, TS, NSG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  S::TOTAL_EPI));
     configured = true;
   }
@@ -1185,7 +1195,7 @@ int launch_epi(const TcGemmP& p, cudaStream_t st) {
   a.t_out = t.out; a.t_out2 = t.out2; a.t_logdet = t.logdet; a.t_s_out = t.s_out;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)cdiv(p.M, BM), (unsigned)a.ncl, (unsigned)p.batch);
-  cfg.blockDim = dim3(NTHREADS);
+  cfg.blockDim = dim3(64 + 128 * NSG);
   cfg.dynamicSmemBytes = S::TOTAL_EPI;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
@@ -1198,7 +1208,7 @@ int launch_epi(const TcGemmP& p, cudaStream_t st) {
   CUtensorMap mC = mA0;
   a.tma_store = make_c_map(&mC, p.C, p.N, p.M, p.ldc, p.batch, p.sC) ? 1 : 0;
   a.b_presplit = pre ? 1 : 0;
-  NF_CUDA(cudaLaunchKernelEx(&cfg, k_tc_gemm<BN, STAGES, false, BK, EPI, TS>, mA0, mA1, mB0, mB1, mB0l, mB1l, mC, a));
+  NF_CUDA(cudaLaunchKernelEx(&cfg, k_tc_gemm<BN, STAGES, false, BK, EPI, TS, NSG>, mA0, mA1, mB0, mB1, mB0l, mB1l, mC, a));
   NF_LAUNCHED();
   return 0;
 }
@@ -1206,11 +1216,19 @@ int launch_epi(const TcGemmP& p, cudaStream_t st) {
 template <int EPI>
 int launch_epi_pick(const TcGemmP& p, cudaStream_t st) {
   const bool ts = option(NF_OPT_TS) != 0;
+  const bool tail = EPI == EPI_LN_FWD && p.epi.tail.on;
   if (p.N % 128 == 0 && p.N / 128 <= kMaxCluster) {
-    if (ts) return launch_epi<128, 8, 16, EPI, true>(p, st);
+    if (ts) {
+      if constexpr (EPI == EPI_LN_FWD) { if (tail) return launch_epi<128, 8, 16, EPI, true, 1>(p, st); }
+      return launch_epi<128, 8, 16, EPI, true, 2>(p, st);
+    }
     return launch_epi<128, 6, 16, EPI>(p, st);
   }
-  return ts ? launch_epi<64, 12, 16, EPI, true>(p, st) : launch_epi<64, 8, 16, EPI>(p, st);
+  if (ts) {
+    if constexpr (EPI == EPI_LN_FWD) { if (tail) return launch_epi<64, 12, 16, EPI, true, 1>(p, st); }
+    return launch_epi<64, 12, 16, EPI, true, 2>(p, st);
+  }
+  return launch_epi<64, 8, 16, EPI>(p, st);
 }
 
 template <int BN, int STAGES, int BK, bool TS = false>
