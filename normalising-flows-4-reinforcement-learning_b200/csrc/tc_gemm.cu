@@ -5,7 +5,7 @@
 //                 tables arrive as two tiles (hi, lo)
 //   warp 1        MMA issuer: the whole warp runs the loop with warp-uniform operands, one elected lane issues
 //                 tcgen05.mma kind::tf32 and the commits; owns tcgen05.alloc / dealloc
-//   warps 2..5    splitter group 0 (and 6..9 = group 1 in the plain TS kernels, alternating stages): thread = tile
+//   warps 2..5    splitter group 0 (and 6..9 = group 1 in the TS kernels, alternating stages): thread = tile
 //                 row = TMEM lane.  TS form: reads its row of the A tile, writes hi / lo to a 4-slot TMEM ring
 //                 (tcgen05.st), splits B in shared memory only when it is not pre-split.  SS form: splits both
 //                 tiles in shared memory (hi in place, lo to a twin).  Then the epilogue.
@@ -14,7 +14,7 @@
 // Accumulators in TMEM: the hi*hi products rotate over NACC `main` accumulators, the cross terms go to `corr`
 // (the tensor core truncates when it accumulates: fewer sequential adds per accumulator = less drift); the
 // epilogue adds them with round-to-nearest.
-// Epilogues: plain (bias / accumulate / split-K reduce-add through bulk tensor stores), EPI_LN_FWD and
+// Epilogues (the splitter groups share the tile's columns): plain (bias / accumulate / split-K reduce-add through bulk tensor stores), EPI_LN_FWD and
 // EPI_LN_BWD (LeakyReLU + LayerNorm forward / backward over a CTA cluster spanning the row, optional fused
 // flow tail).  MNMAJOR = true is the weight-gradient form (reduction over the batch rows, split-K).
 #include <cuda.h>
@@ -335,8 +335,9 @@ struct Smem {
 // inside the parity contract).
 // NSG = splitter groups of four warps.  One group needs ~1 100 cycles per 16-deep stage (wait for the tile 120, load +
 // split 320, wait for the TMEM slot 300, tcgen05.st + wait + fences + arrive 340 -- a chain of fixed latencies, measured
-// with clock64) against 384 cycles of MMAs, so the plain kernels run two groups on alternating stages; both groups
-// share the epilogue (alternating 32-column chunks).
+// with clock64) against 384 cycles of MMAs, so the TS kernels run two groups on alternating stages; both groups
+// share the epilogue (plain: alternating 32-column chunks; row-wise: each group owns half of the tile's columns, which
+// also halves the registers a thread needs for its row -- 320 threads leave 200 per thread).
 template <int BN, int STAGES, bool MNMAJOR, int BK, int EPI = EPI_NONE, bool TS = false, int NSG = 1>
 __global__ void __launch_bounds__(64 + 128 * NSG, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUtensorMap mA1,
