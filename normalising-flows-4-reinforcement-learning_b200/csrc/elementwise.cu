@@ -69,6 +69,133 @@ __global__ void __launch_bounds__(256) k_lrelu_ln_fwd(LnFwdP p) {
   if (p.rstd && lane == 0) p.rstd[net * p.rstd_net + row] = rstd;
 }
 
+// Vectorised single-pass versions of the two kernels around this comment (N % 4 == 0, N <= 1024, 16-byte aligned
+// rows): a warp keeps its row in registers as NV float4 per lane, so u / g / x_hat are read exactly once with 128-bit
+// accesses (the scalar kernels read u three times and g, x_hat twice; measured on C3, B = 16384, H1 = 320:
+// backward 119 us, forward 28 us for 126 / 84 MB of algorithmic traffic).
+template <int NV>
+__global__ void __launch_bounds__(256) k_lrelu_ln_fwd_v4(LnFwdP p) {
+  NF_PDL_ENTRY();
+  const int net = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= p.B) return;
+  const int N = p.N;
+  const float4* u = reinterpret_cast<const float4*>(p.u + net * p.u_net + row * N);
+  const float4* bias = p.bias ? reinterpret_cast<const float4*>(p.bias + net * p.bias_net) : nullptr;
+  float4* xh = reinterpret_cast<float4*>(p.xh + net * p.xh_net + row * N);
+  uint32_t* mask = p.mask ? p.mask + net * p.mask_net + row * p.mw : nullptr;
+  float4 v[NV];
+  uint32_t nib[NV];
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int c4 = lane + 32 * k;
+    nib[k] = 0u;
+    v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (4 * c4 < N) {
+      float4 t = u[c4];
+      if (bias) { const float4 b = __ldg(bias + c4); t.x += b.x; t.y += b.y; t.z += b.z; t.w += b.w; }
+      nib[k] = (t.x > 0.f ? 1u : 0u) | (t.y > 0.f ? 2u : 0u) | (t.z > 0.f ? 4u : 0u) | (t.w > 0.f ? 8u : 0u);
+      t.x = t.x > 0.f ? t.x : kLeakySlope * t.x; t.y = t.y > 0.f ? t.y : kLeakySlope * t.y;
+      t.z = t.z > 0.f ? t.z : kLeakySlope * t.z; t.w = t.w > 0.f ? t.w : kLeakySlope * t.w;
+      v[k] = t;
+      sum += (t.x + t.y) + (t.z + t.w);
+    }
+  }
+  const float mean = warp_sum(sum) / (float)N;
+  float sq = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    if (4 * (lane + 32 * k) < N) {
+      const float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, d = v[k].w - mean;
+      sq += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / (float)N + p.eps);
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int c4 = lane + 32 * k;
+    if (4 * c4 < N)
+      xh[c4] = make_float4((v[k].x - mean) * rstd, (v[k].y - mean) * rstd, (v[k].z - mean) * rstd, (v[k].w - mean) * rstd);
+    // sign mask: 8 consecutive lanes hold the 32 bits of word (lane >> 3) + 4 k
+    uint32_t w = nib[k] << ((lane & 7) * 4);
+    w |= __shfl_xor_sync(0xffffffffu, w, 1);
+    w |= __shfl_xor_sync(0xffffffffu, w, 2);
+    w |= __shfl_xor_sync(0xffffffffu, w, 4);
+    const int word = (lane >> 3) + 4 * k;
+    if (mask && (lane & 7) == 0 && 32 * word < N) mask[word] = w;
+  }
+  if (p.rstd && lane == 0) p.rstd[net * p.rstd_net + row] = rstd;
+}
+
+template <int NV>
+__global__ void __launch_bounds__(256, 2) k_ln_lrelu_bwd_v4(LnBwdP p, int rows_per_cta) {
+  extern __shared__ float s_part[];   // [8 warps][N] column sums
+  NF_PDL_ENTRY();
+  const int net = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int N = p.N;
+  float4 cs[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) cs[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const long long r0 = (long long)blockIdx.x * rows_per_cta;
+  const long long r1 = min(p.B, r0 + rows_per_cta);
+  const float invN = 1.0f / (float)N;
+  for (long long row = r0 + warp; row < r1; row += 8) {
+    float4* g = reinterpret_cast<float4*>(p.g + net * p.g_net + row * N);
+    const float4* xh = reinterpret_cast<const float4*>(p.xh + net * p.xh_net + row * N);
+    const uint32_t* mask = p.mask + net * p.mask_net + row * p.mw;
+    float4 gv[NV], xv[NV];
+    uint32_t mw[NV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c4 = lane + 32 * k;
+      const bool ok = 4 * c4 < N;
+      gv[k] = ok ? g[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+      xv[k] = ok ? __ldg(xh + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      mw[k] = ok ? __ldg(mask + (lane >> 3) + 4 * k) : 0u;
+    }
+    const float rstd = p.rstd[net * p.rstd_net + row];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      s1 += (gv[k].x + gv[k].y) + (gv[k].z + gv[k].w);
+      s2 = fmaf(gv[k].x, xv[k].x, fmaf(gv[k].y, xv[k].y, fmaf(gv[k].z, xv[k].z, fmaf(gv[k].w, xv[k].w, s2))));
+    }
+    const float m1 = warp_sum(s1) * invN, m2 = warp_sum(s2) * invN;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c4 = lane + 32 * k;
+      const uint32_t bits = mw[k] >> ((lane & 7) * 4);
+      float4 d;
+      d.x = rstd * (gv[k].x - m1 - xv[k].x * m2) * ((bits & 1u) ? 1.0f : kLeakySlope);
+      d.y = rstd * (gv[k].y - m1 - xv[k].y * m2) * ((bits & 2u) ? 1.0f : kLeakySlope);
+      d.z = rstd * (gv[k].z - m1 - xv[k].z * m2) * ((bits & 4u) ? 1.0f : kLeakySlope);
+      d.w = rstd * (gv[k].w - m1 - xv[k].w * m2) * ((bits & 8u) ? 1.0f : kLeakySlope);
+      if (4 * c4 < N) {
+        g[c4] = d;
+        cs[k].x += d.x; cs[k].y += d.y; cs[k].z += d.z; cs[k].w += d.w;
+      }
+    }
+  }
+  if (p.colsum) {   // uniform across the CTA
+    float* mine = s_part + (size_t)warp * N;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c = 4 * (lane + 32 * k);
+      if (c < N) *reinterpret_cast<float4*>(mine + c) = cs[k];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < N; c += blockDim.x) {
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) v += s_part[(size_t)w * N + c];
+      if (v != 0.f) atomicAdd(&p.colsum[net * p.colsum_net + c], v);
+    }
+  }
+}
+
 // d u = LeakyReLU'(u) * rstd * (g - mean(g) - x_hat * mean(g * x_hat)),  g = d x_hat
 // One warp owns kBwdRowsPerWarp rows: a statistics pass, then per 256-column chunk a pass that
 // writes d u and keeps the column sums (bias gradient) in registers; the warps of a CTA are
@@ -491,11 +618,23 @@ __global__ void k_transpose2d(float* dst, long long ldd, long long sd0, long lon
 // ------------------------------------------------------------------------------------------
 // host wrappers
 // ------------------------------------------------------------------------------------------
+static bool al16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; }
+
 int lrelu_ln_fwd(const LnFwdP& p, cudaStream_t st) {
   if (p.B <= 0) return 0;
   dim3 grid((unsigned)cdiv(p.B, 8), (unsigned)p.nets);
   ProfScope prof(st, PROF_LN_FWD, 8.0 * p.B * p.N * p.nets);   // read u, write x_hat
-  NF_LAUNCH((k_lrelu_ln_fwd), grid, 256, 0, st, p);
+  const bool v4 = !p.xh_lo && p.N % 4 == 0 && p.N <= 1024 && al16(p.u) && al16(p.xh) && al16(p.bias) &&
+                  p.u_net % 4 == 0 && p.xh_net % 4 == 0 && p.bias_net % 4 == 0;
+  if (v4) {
+    const int nv = (int)cdiv(p.N, 128);
+    if (nv <= 1) NF_LAUNCH((k_lrelu_ln_fwd_v4<1>), grid, 256, 0, st, p);
+    else if (nv <= 2) NF_LAUNCH((k_lrelu_ln_fwd_v4<2>), grid, 256, 0, st, p);
+    else if (nv <= 4) NF_LAUNCH((k_lrelu_ln_fwd_v4<4>), grid, 256, 0, st, p);
+    else NF_LAUNCH((k_lrelu_ln_fwd_v4<8>), grid, 256, 0, st, p);
+  } else {
+    NF_LAUNCH((k_lrelu_ln_fwd), grid, 256, 0, st, p);
+  }
   NF_LAUNCHED();
   return 0;
 }
@@ -508,7 +647,21 @@ int ln_lrelu_bwd(const LnBwdP& p, cudaStream_t st) {
   if (rpw > kBwdRowsPerWarp) rpw = kBwdRowsPerWarp;
   dim3 grid((unsigned)cdiv(p.B, kBwdWarps * rpw), (unsigned)p.nets);
   ProfScope prof(st, PROF_LN_BWD, 12.0 * p.B * p.N * p.nets);  // read g, x_hat; write du
-  NF_LAUNCH((k_ln_lrelu_bwd), grid, kBwdWarps * 32, 0, st, p, (int)rpw);
+  const bool v4 = p.N % 4 == 0 && p.N <= 1024 && al16(p.g) && al16(p.xh) && p.g_net % 4 == 0 && p.xh_net % 4 == 0;
+  if (v4) {
+    // two CTAs per SM, two waves; at least 32 rows per CTA (one global atomic per column and CTA)
+    long long rpc = cdiv(p.B * p.nets, 2 * 2 * 148);
+    rpc = std::max<long long>(32, cdiv(rpc, 8) * 8);
+    dim3 g2((unsigned)cdiv(p.B, rpc), (unsigned)p.nets);
+    const size_t smem = (size_t)8 * p.N * sizeof(float);
+    const int nv = (int)cdiv(p.N, 128);
+    if (nv <= 1) NF_LAUNCH((k_ln_lrelu_bwd_v4<1>), g2, 256, smem, st, p, (int)rpc);
+    else if (nv <= 2) NF_LAUNCH((k_ln_lrelu_bwd_v4<2>), g2, 256, smem, st, p, (int)rpc);
+    else if (nv <= 4) NF_LAUNCH((k_ln_lrelu_bwd_v4<4>), g2, 256, smem, st, p, (int)rpc);
+    else NF_LAUNCH((k_ln_lrelu_bwd_v4<8>), g2, 256, smem, st, p, (int)rpc);
+  } else {
+    NF_LAUNCH((k_ln_lrelu_bwd), grid, kBwdWarps * 32, 0, st, p, (int)rpw);
+  }
   NF_LAUNCHED();
   return 0;
 }
