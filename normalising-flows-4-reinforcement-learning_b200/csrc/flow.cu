@@ -191,6 +191,7 @@ static FwdWs carve_fwd(const Dims& m, int64_t B, void* ws) {
 struct BwdWs { float *d0, *d1, *dxp, *dout, *gA, *gB, *dWs, *T1, *dLh, *dUh, *sumdld;
                float *dxp2, *dout2, *gA2, *gB2;   // second set: blocks alternate so side streams can lag one block
                float *io_dz, *io_dld, *io_dy, *io_dx;   // staging of the caller's cotangents and of dx / dy (see FwdWs)
+               float *w3t[2];                           // generic path: W3f^T (2, C, dtp) of the current block (alternating)
                int64_t total; };
 static BwdWs carve_bwd(const Dims& m, int64_t B, void* ws) {
   Carver c(ws);
@@ -216,6 +217,8 @@ static BwdWs carve_bwd(const Dims& m, int64_t B, void* ws) {
   w.io_dld = c.take(B);
   w.io_dy = c.take(B * m.R);
   w.io_dx = c.take(B * m.D);
+  w.w3t[0] = c.take(2 * (int64_t)m.C * pad4(m.dt));
+  w.w3t[1] = c.take(2 * (int64_t)m.C * pad4(m.dt));
   w.total = c.off;
   return w;
 }
@@ -284,7 +287,7 @@ int linear_nt(int prec, const TcGemmP& t0, cudaStream_t st) {
 // C[z] (M,N) += A[z] (K,M)^T @ B[z] (K,N): weight gradients (reduction over the K = batch rows).
 // C must already hold the base value (the gradient arena is zero-filled first).
 int wgrad_tn(int prec, const TcGemmTnP& t, cudaStream_t st) {
-  if (prec == NF_PREC_TF32X3 && t.M >= 32 && t.N >= 32 && tc_gemm_tn_supported(t)) return tc_gemm_tn(t, st);
+  if (prec == NF_PREC_TF32X3 && t.M >= 16 && t.N >= 32 && tc_gemm_tn_supported(t)) return tc_gemm_tn(t, st);
   GemmP g;
   g.transA = 1; g.A0 = t.A; g.lda0 = (int)t.lda; g.sA0 = t.sA; g.K0 = (int)t.K;
   g.B0 = t.B; g.ldb0 = (int)t.ldb; g.sB0 = t.sB;
@@ -870,12 +873,27 @@ int nf_flow_backward_range(const NfFlowDesc* desc, const float* params, const vo
         NF_TRY(wgrad_tn(m.prec, g, st));
       }
       {  // c. d x_hat2 = dout W3f
-        GemmP g;
-        g.A0 = wb.dout; g.lda0 = m.dt; g.sA0 = B * m.dt; g.K0 = m.dt;
-        g.B0 = kb + kl.net0 + kl.W3f; g.ldb0 = m.C; g.sB0 = kl.net_stride;
-        g.C = wb.gA; g.ldc = m.C; g.sC = B * Hm;
-        g.M = (int)B; g.N = m.C; g.batch = 2;
-        NF_TRY(simt_gemm(g, st));
+        bool done = false;
+        if (m.prec == NF_PREC_TF32X3 && m.dt >= 16 && (m.dt & 3) == 0) {
+          // tensor-core form: the K-major B operand is W3f^T (C, dt), transposed per block into the workspace (the
+          // FFMA GEMM below took 44 us per block on C5 for what is a 67 MB store)
+          float* w3t = w.w3t[par];
+          NF_TRY(transpose2d(w3t, m.dt, (int64_t)m.C * m.dt, 0, kb + kl.net0 + kl.W3f, m.C, kl.net_stride, 0, m.dt, m.C, 2, 1, st));
+          TcGemmP t;
+          t.A0 = wb.dout; t.lda0 = m.dt; t.sA0 = B * m.dt; t.K0 = m.dt;
+          t.B0 = w3t; t.ldb0 = m.dt; t.sB0 = (int64_t)m.C * m.dt;
+          t.C = wb.gA; t.ldc = m.C; t.sC = B * Hm;
+          t.M = (int)B; t.N = m.C; t.batch = 2;
+          if (tc_gemm_supported(t)) { NF_TRY(tc_gemm(t, st)); done = true; }
+        }
+        if (!done) {
+          GemmP g;
+          g.A0 = wb.dout; g.lda0 = m.dt; g.sA0 = B * m.dt; g.K0 = m.dt;
+          g.B0 = kb + kl.net0 + kl.W3f; g.ldb0 = m.C; g.sB0 = kl.net_stride;
+          g.C = wb.gA; g.ldc = m.C; g.sC = B * Hm;
+          g.M = (int)B; g.N = m.C; g.batch = 2;
+          NF_TRY(simt_gemm(g, st));
+        }
       }
       {  // d. through LayerNorm + LeakyReLU (layer 2); column sums -> slot b2
         LnBwdP p{};
