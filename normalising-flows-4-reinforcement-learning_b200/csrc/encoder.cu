@@ -254,9 +254,8 @@ __global__ void __launch_bounds__(128) k_enc_colsum(const float* __restrict__ A,
 }
 
 int rows_per_cta_for(long long B) {
-  // enough CTAs for two waves on 148 SMs, at least 32 rows each (fewer global atomics per row)
-  static const int forced = [] { const char* e = getenv("NF_B200_ENC_RPC"); return e ? atoi(e) : 0; }();
-  if (forced > 0) return forced;
+  // enough CTAs for two waves on 148 SMs, at least 32 rows each (fewer global atomics per row; measured on the kitchen
+  // encoder, batch 8192: 16 rows 0.803 ms, 32 rows 0.790 ms, 64 rows 0.830 ms per forward + backward)
   long long rpc = cdiv(B, 296);
   rpc = std::max<long long>(32, cdiv(rpc, 8) * 8);
   return (int)rpc;
