@@ -145,7 +145,7 @@ class _Flow(torch.autograd.Function):
         ctx.stash = stash
         ctx.guard = _SlotGuard(slot) if slot is not None else None
         ctx.packed = packed
-        ctx.pver = model._params_version()
+        ctx.pver = model._pver_seen      # computed by _prepared inside _run_forward
         ctx.B = x.shape[0]
         ctx.save_for_backward(y)
         ctx.mark_non_differentiable(outs)
@@ -191,7 +191,7 @@ class _FlowNLL(torch.autograd.Function):
                                       loss.data_ptr(), model._stream(x.device)), "nf_nll_forward")
         ctx.model, ctx.stash, ctx.packed = model, stash, packed
         ctx.guard = _SlotGuard(slot) if slot is not None else None
-        ctx.pver = model._params_version()
+        ctx.pver = model._pver_seen      # computed by _prepared inside _run_forward
         ctx.B = x.shape[0]
         ctx.save_for_backward(y, z)
         return loss
@@ -264,6 +264,7 @@ class RealNVP(nn.Module):
         self._gviews = None
         self._stash_pool = {}
         self._neg_b = None
+        self._pver_seen = 0
         self._xver = 0
         self._dp_group = None
         self._dp_world = 1
@@ -380,7 +381,8 @@ class RealNVP(nn.Module):
         """Derived parameter tables (W, W^-1, folded LayerNorm affine, log|det|), rebuilt whenever a
         parameter changed (torch_fcnf.py:34-38, 45-54 redo this in every call).  The buffer is
         persistent, so the library's cached launch graphs keep seeing the same pointer."""
-        key = (self._params_version(), self._flat.data_ptr())
+        self._pver_seen = pver = self._params_version()   # (the autograd functions reuse it: one walk over the parameters per forward)
+        key = (pver, self._flat.data_ptr())
         have = self._packed_key
         if self._packed is not None and have is not None and have[0] == key and (have[1] & what) == what:
             return self._packed
