@@ -11,7 +11,7 @@ import nf_b200
 from oracle import synth
 from oracle.torch_flow import TorchEncoder, TorchFlow
 
-BATCH = {"C2a": 4096, "C3": 16384, "C4": 8192, "C1a": 256, "C1c": 256, "C5": 8192}
+BATCH = {"C2a": 4096, "C3": 16384, "C4": 8192, "C1a": 256, "C1b": 256, "C1c": 256, "C5": 8192}
 
 
 def timed(fn, iters, warm=5):
