@@ -97,6 +97,20 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   (void)nf::launch_pdl(kernel, dim3(grid), dim3(block), (size_t)(smem), st, __VA_ARGS__)
 #endif
 
+// cudaFuncSetAttribute is per device: a call site remembers which devices it has configured (the Python layer
+// runs modules on non-current devices too, so one process-wide flag would leave the second GPU without the
+// > 48 KB dynamic shared memory opt-in).
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool first() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+};
+
 static inline int64_t pad4(int64_t v) { return (v + 3) & ~int64_t(3); }
 static inline int64_t pad32(int64_t v) { return (v + 31) & ~int64_t(31); }
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }

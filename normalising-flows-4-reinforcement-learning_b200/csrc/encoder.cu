@@ -284,14 +284,13 @@ int ln_silu_bwd(float* g, const float* xh, const float* rstd, const float* gamma
   const size_t smem = (size_t)(2 + 8 * 3) * H * sizeof(float);   // gamma, beta, 8 warps x 3 partial-sum rows
   const int nv = (int)cdiv(H, 128);
   {
-    static bool configured = false;   // more than 48 KB of dynamic shared memory from hidden = 512 on
-    if (!configured) {
+    static PerDeviceOnce once;   // more than 48 KB of dynamic shared memory from hidden = 512 on
+    if (once.first()) {
       constexpr int kMax = (2 + 8 * 3) * 128 * kEncMaxV * (int)sizeof(float);
       NF_CUDA(cudaFuncSetAttribute(k_enc_ln_silu_bwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax));
       NF_CUDA(cudaFuncSetAttribute(k_enc_ln_silu_bwd<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax));
       NF_CUDA(cudaFuncSetAttribute(k_enc_ln_silu_bwd<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax));
       NF_CUDA(cudaFuncSetAttribute(k_enc_ln_silu_bwd<kEncMaxV>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax));
-      configured = true;
     }
   }
   switch (nv) {

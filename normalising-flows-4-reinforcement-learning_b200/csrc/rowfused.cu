@@ -383,12 +383,12 @@ int row_bwd_head(const BwdHeadP& p, cudaStream_t st) {
   const size_t smem = row_bwd_head_smem(p.D, p.C);
   ProfScope prof(st, PROF_ROW_HEAD, 4.0 * p.B * (4.0 * p.C + 4.0 * p.D));
   if (dt <= 4) {
-    static bool cfg = false;
-    if (!cfg) { NF_CUDA(cudaFuncSetAttribute(k_row_bwd_head<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cfg = true; }
+    static PerDeviceOnce once;
+    if (once.first()) { NF_CUDA(cudaFuncSetAttribute(k_row_bwd_head<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRowFusedSmemLimit)); }
     NF_LAUNCH((k_row_bwd_head<4>), grid, kWarps * 32, smem, st, p, rpw);
   } else {
-    static bool cfg = false;
-    if (!cfg) { NF_CUDA(cudaFuncSetAttribute(k_row_bwd_head<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cfg = true; }
+    static PerDeviceOnce once;
+    if (once.first()) { NF_CUDA(cudaFuncSetAttribute(k_row_bwd_head<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRowFusedSmemLimit)); }
     NF_LAUNCH((k_row_bwd_head<16>), grid, kWarps * 32, smem, st, p, rpw);
   }
   NF_LAUNCHED();
@@ -410,12 +410,12 @@ int row_bwd_tail(const BwdTailP& p, cudaStream_t st) {
   const size_t smem = row_bwd_tail_smem(p.D, p.H1);
   ProfScope prof(st, PROF_ROW_BTAIL, 4.0 * p.B * (4.0 * p.H1 + 4.0 * p.D));
   if (dc <= 8) {
-    static bool cfg = false;
-    if (!cfg) { NF_CUDA(cudaFuncSetAttribute(k_row_bwd_tail<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cfg = true; }
+    static PerDeviceOnce once;
+    if (once.first()) { NF_CUDA(cudaFuncSetAttribute(k_row_bwd_tail<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRowFusedSmemLimit)); }
     NF_LAUNCH((k_row_bwd_tail<8>), grid, kWarps * 32, smem, st, p, rpw);
   } else {
-    static bool cfg = false;
-    if (!cfg) { NF_CUDA(cudaFuncSetAttribute(k_row_bwd_tail<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cfg = true; }
+    static PerDeviceOnce once;
+    if (once.first()) { NF_CUDA(cudaFuncSetAttribute(k_row_bwd_tail<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRowFusedSmemLimit)); }
     NF_LAUNCH((k_row_bwd_tail<16>), grid, kWarps * 32, smem, st, p, rpw);
   }
   NF_LAUNCHED();

@@ -1077,11 +1077,10 @@ bool ok_operand(const float* p, long long ld, long long bstride) {
 
 template <int BN, int STAGES, bool MN, int BK>
 int set_smem() {
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     NF_CUDA(cudaFuncSetAttribute(k_tc_gemm<BN, STAGES, MN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  Smem<BN, STAGES, BK>::TOTAL));
-    configured = true;
   }
   return 0;
 }
@@ -1094,11 +1093,10 @@ int launch(const TcGemmP& p, cudaStream_t st) {
   constexpr int NSG = TS ? 2 : 1;
   int r;
   {
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce once;
+    if (once.first()) {
       NF_CUDA(cudaFuncSetAttribute(k_tc_gemm<BN, STAGES, false, BK, EPI_NONE, TS, NSG>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-      configured = true;
     }
   }
   CUtensorMap mA0, mA1, mB0, mB1, mB0l, mB1l;
@@ -1153,11 +1151,10 @@ template <int BN, int STAGES, int BK, int EPI, bool TS = false, int NSG = 1>
 int launch_epi(const TcGemmP& p, cudaStream_t st) {
   using S = Smem<BN, STAGES, BK, TS>;
   static_assert(NSG == 1 || (TS && (BN / NSG) % 32 == 0), "two splitter groups need the TS form and 32-column slices");
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     NF_CUDA(cudaFuncSetAttribute(k_tc_gemm<BN, STAGES, false, BK, EPI, TS, NSG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  S::TOTAL_EPI));
-    configured = true;
   }
   int r;
   CUtensorMap mA0, mA1, mB0, mB1, mB0l, mB1l;
@@ -1238,11 +1235,10 @@ int launch_tn(const TcGemmTnP& p, cudaStream_t st) {
   constexpr int NSG = TS ? 2 : 1;
   int r;
   {
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce once;
+    if (once.first()) {
       NF_CUDA(cudaFuncSetAttribute(k_tc_gemm<BN, STAGES, true, BK, EPI_NONE, TS, NSG>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-      configured = true;
     }
   }
   CUtensorMap mA, mB;

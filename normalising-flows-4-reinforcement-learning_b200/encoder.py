@@ -17,14 +17,14 @@ from torch import nn
 
 from . import _lib
 from ._lib import lib
-from .module import _dense, _on, _SlotGuard, _StashSlot
+from .module import _accumulate_nodes, _dense, _on, _param_grads_wanted, _SlotGuard, _StashSlot
 
 
 class _Encode(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, model: "GEncoder", need_stash: bool, g, *params):
+    def forward(ctx, model: "GEncoder", need_stash: bool, nodes, g, *params):
         out, stash, slot = model._run_forward(g, need_stash)
-        ctx.model, ctx.stash = model, stash
+        ctx.model, ctx.stash, ctx.nodes = model, stash, nodes
         ctx.guard = _SlotGuard(slot) if slot is not None else None
         ctx.save_for_backward(g)
         return out
@@ -35,12 +35,15 @@ class _Encode(torch.autograd.Function):
         if ctx.stash is None:
             raise RuntimeError("nf_b200: encoder backward without a stash (forward ran under no_grad, or backward twice)")
         (g,) = ctx.saved_tensors
-        dg, dflat = model._run_backward(g, ctx.stash, dout, ctx.needs_input_grad[2])
+        need_p = _param_grads_wanted(ctx.needs_input_grad[4:], ctx.nodes)
+        dg, dflat = model._run_backward(g, ctx.stash, dout, ctx.needs_input_grad[3], need_p)
         ctx.stash = None
         if ctx.guard is not None:
             ctx.guard.release()      # the stash may be reused by the next forward
+        if not need_p:
+            return (None, None, None, dg) + (None,) * (len(ctx.needs_input_grad) - 4)
         views = model._grad_views(dflat)
-        return (None, None, dg) + tuple(v if need else None for v, need in zip(views, ctx.needs_input_grad[3:]))
+        return (None, None, None, dg) + tuple(v if need else None for v, need in zip(views, ctx.needs_input_grad[4:]))
 
 
 class GEncoder(nn.Module):
@@ -165,7 +168,7 @@ class GEncoder(nn.Module):
             return t, slot
         return t, None
 
-    def _run_backward(self, g, stash, dout, need_dg):
+    def _run_backward(self, g, stash, dout, need_dg, need_p=True):
         dev, B = g.device, g.shape[0]
         g, dout = _dense(g), _dense(dout)
         with _on(dev):
@@ -176,7 +179,7 @@ class GEncoder(nn.Module):
                                                stash.data_ptr(), B, dout.data_ptr(),
                                                dg.data_ptr() if dg is not None else None, dflat.data_ptr(),
                                                ws.data_ptr(), ws.numel(), self._stream(dev)), "nf_encoder_backward")
-            if self._dp_world > 1:
+            if self._dp_world > 1 and need_p:     # (a rank-local evaluation must not enter the collective)
                 self._allreduce_grads(dflat)
         return dg, dflat
 
@@ -188,6 +191,12 @@ class GEncoder(nn.Module):
         self._dp_group = process_group
         self._dp_world = dist.get_world_size(process_group)
         self._dp_avg = dist.get_backend(process_group) == "nccl"
+        if self._dp_world > 1:      # replicas start from rank 0's parameters
+            if not self._is_flat():
+                self._flatten()
+            with torch.no_grad():
+                dist.broadcast(self._flat, src=dist.get_global_rank(process_group, 0) if process_group is not None else 0,
+                               group=process_group)
         return self
 
     def _allreduce_grads(self, dflat):
@@ -203,4 +212,5 @@ class GEncoder(nn.Module):
         params = [p for p, _ in self._slots]
         # (grad mode is off inside Function.forward, so whether a backward can follow is decided here)
         need_stash = torch.is_grad_enabled() and (g.requires_grad or any(p.requires_grad for p in params))
-        return _Encode.apply(self, need_stash, g, *params)
+        nodes = _accumulate_nodes([p for p in params if p.requires_grad]) if need_stash else []
+        return _Encode.apply(self, need_stash, nodes, g, *params)

@@ -130,6 +130,32 @@ class _SlotGuard:
         self.release()
 
 
+def _accumulate_nodes(params):
+    """AccumulateGrad nodes of `params` (call with grad mode on, outside Function.forward)."""
+    nodes = []
+    for p in params:
+        fn = p.view_as(p).grad_fn
+        if fn is not None:
+            nodes.append(fn.next_functions[0][0])
+    return nodes
+
+
+def _param_grads_wanted(needs, nodes):
+    """``ctx.needs_input_grad`` is fixed at forward time from ``requires_grad``; it does not know the ``inputs=`` of
+    ``torch.autograd.grad``.  The reference's evaluation-time denoise step (torch_nfbc_ant.py:212-217) differentiates
+    w.r.t. the action only while the parameters still require grad: ask the engine whether this backward pass will
+    run the parameters' AccumulateGrad nodes, so that step neither pays for the weight-gradient kernels nor leaves
+    ``p.grad`` behind (nor issues the data-parallel all-reduce on one rank only)."""
+    if not any(needs):
+        return False
+    if not nodes:
+        return True
+    try:
+        return any(torch._C._will_engine_execute_node(n) for n in nodes)
+    except RuntimeError:
+        return True      # autograd.grad with the parameters themselves as inputs: leaf queries are unsupported there
+
+
 class _Flow(torch.autograd.Function):
     """autograd bridge: forward = nf_flow_forward, backward = nf_flow_backward.
 
@@ -138,10 +164,11 @@ class _Flow(torch.autograd.Function):
     (``fast_param_grads=True``: backward writes the flat gradient arena and sets ``p.grad`` views itself)."""
 
     @staticmethod
-    def forward(ctx, model: "RealNVP", fast: bool, x, y, *params):
+    def forward(ctx, model: "RealNVP", fast: bool, nodes, x, y, *params):
         z, logdet, outs, stash, packed, slot = model._run_forward(x, y, True)
         ctx.model = model
         ctx.fast = fast
+        ctx.nodes = nodes
         ctx.stash = stash
         ctx.guard = _SlotGuard(slot) if slot is not None else None
         ctx.packed = packed
@@ -159,10 +186,10 @@ class _Flow(torch.autograd.Function):
         if ctx.pver != model._params_version():
             raise RuntimeError("nf_b200: parameters were modified between forward and backward")
         (y,) = ctx.saved_tensors
-        need_x = ctx.needs_input_grad[2]
-        need_y = ctx.needs_input_grad[3]
-        need_p = any(ctx.needs_input_grad[4:])
-        nparams = len(ctx.needs_input_grad) - 4
+        need_x = ctx.needs_input_grad[3]
+        need_y = ctx.needs_input_grad[4]
+        need_p = _param_grads_wanted(ctx.needs_input_grad[5:], ctx.nodes)
+        nparams = len(ctx.needs_input_grad) - 5
         if ctx.fast:
             dx, dy = model._run_backward_fast(ctx.stash, ctx.packed, y, ctx.B, dz, dld, need_x, need_y, need_p)
             pg = (None,) * nparams
@@ -170,13 +197,13 @@ class _Flow(torch.autograd.Function):
             dx, dy, dflat = model._run_backward(ctx.stash, ctx.packed, y, ctx.B, dz, dld, need_x, need_y, need_p)
             if need_p:
                 views = model._grad_views(dflat)
-                pg = tuple(v if need else None for v, need in zip(views, ctx.needs_input_grad[4:]))
+                pg = tuple(v if need else None for v, need in zip(views, ctx.needs_input_grad[5:]))
             else:
                 pg = (None,) * nparams
         ctx.stash = None
         if ctx.guard is not None:
             ctx.guard.release()      # the stash may be reused by the next forward
-        return (None, None, dx, dy) + pg
+        return (None, None, None, dx, dy) + pg
 
 
 class _FlowNLL(torch.autograd.Function):
@@ -184,8 +211,9 @@ class _FlowNLL(torch.autograd.Function):
     (nf_nll_forward / nf_nll_cotangents) instead of ~8 elementwise torch kernels either side of the flow."""
 
     @staticmethod
-    def forward(ctx, model: "RealNVP", x, y, *params):
-        z, logdet, _, stash, packed, slot = model._run_forward(x, y, True)
+    def forward(ctx, model: "RealNVP", nodes, x, y, *params):
+        z, logdet, _, stash, packed, slot = model._run_forward(x, y, True, want_outputs=False)
+        ctx.nodes = nodes
         loss = torch.empty((), dtype=torch.float32, device=x.device)
         _lib.check(lib.nf_nll_forward(z.data_ptr(), logdet.data_ptr(), x.shape[0], model.in_channels,
                                       loss.data_ptr(), model._stream(x.device)), "nf_nll_forward")
@@ -210,13 +238,13 @@ class _FlowNLL(torch.autograd.Function):
         g = _dense(g.reshape(1).to(torch.float32))
         _lib.check(lib.nf_nll_cotangents(z.data_ptr(), g.data_ptr(), B, D, dz.data_ptr(), dld.data_ptr(),
                                          model._stream(z.device)), "nf_nll_cotangents")
-        need_x, need_y = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
-        need_p = any(ctx.needs_input_grad[3:])
+        need_x, need_y = ctx.needs_input_grad[2], ctx.needs_input_grad[3]
+        need_p = _param_grads_wanted(ctx.needs_input_grad[4:], ctx.nodes)
         dx, dy = model._run_backward_fast(ctx.stash, ctx.packed, y, B, dz, dld, need_x, need_y, need_p)
         ctx.stash = None
         if ctx.guard is not None:
             ctx.guard.release()
-        return (None, dx, dy) + (None,) * (len(ctx.needs_input_grad) - 3)
+        return (None, None, dx, dy) + (None,) * (len(ctx.needs_input_grad) - 4)
 
 
 class RealNVP(nn.Module):
@@ -236,7 +264,7 @@ class RealNVP(nn.Module):
     """
 
     def __init__(self, in_channels, channels, cond_channels, n_layers, prior, *,
-                 first_hidden: Optional[int] = None, ln_eps: float = 1e-5, precision: str = "fp32_simt",
+                 first_hidden: Optional[int] = None, ln_eps: float = 1e-5, precision: str = "fp32",
                  fast_param_grads: bool = True):
         super().__init__()
         self.fast_param_grads = bool(fast_param_grads)
@@ -398,7 +426,7 @@ class RealNVP(nn.Module):
         self._packed_key = (key, what)
         return packed
 
-    def _run_forward(self, x, y, want_stash):
+    def _run_forward(self, x, y, want_stash, want_outputs=True):
         dev = x.device
         B, D, n = x.shape[0], self.in_channels, self.n_layers
         x = _dense(x)
@@ -411,11 +439,11 @@ class RealNVP(nn.Module):
             stash, slot = None, None
             if want_stash:
                 stash, slot = self._acquire_stash(B, dev)
-                # outputs alias the block-input region of the stash: xs[1:], (n, B, D); they stay valid until
-                # the backward of this forward has run (then the stash may be reused)
-                outs = stash[B * D:(n + 1) * B * D].view(n, B, D)
-                outs_ptr = None
-            else:
+            # `outputs` are independent tensors as in the reference (torch_fcnf.py:134-141): the pooled stash is
+            # reused by the next forward, so they are copied out by the library's trailing copy kernel (the one
+            # that also delivers z and log_dets -- no extra launch)
+            outs, outs_ptr = None, None
+            if want_outputs:
                 outs = torch.empty((n, B, D), dtype=torch.float32, device=dev)
                 outs_ptr = outs.data_ptr()
             _lib.check(lib.nf_flow_forward(
@@ -514,6 +542,15 @@ class RealNVP(nn.Module):
         self._dp_group = process_group
         self._dp_world = dist.get_world_size(process_group)
         self._dp_avg = dist.get_backend(process_group) == "nccl"     # NCCL averages inside the reduction
+        # replicas start from rank 0's parameters, like DistributedDataParallel's construction-time broadcast
+        if self._dp_world > 1:
+            if not self._is_flat():
+                self._flatten()
+            with torch.no_grad():
+                dist.broadcast(self._flat, src=dist.get_global_rank(process_group, 0) if process_group is not None else 0,
+                               group=process_group)
+            self._packed_key = None
+            self._bump_version()
         return self
 
     def _allreduce_grads(self, dflat):
@@ -566,9 +603,9 @@ class RealNVP(nn.Module):
         need_grad = torch.is_grad_enabled() and (x.requires_grad or y.requires_grad or len(params) > 0)
         if need_grad:
             if self.fast_param_grads:
-                z, logdet, outs = _Flow.apply(self, True, x, y, *params[:1])
+                z, logdet, outs = _Flow.apply(self, True, _accumulate_nodes(params[:1]), x, y, *params[:1])
             else:
-                z, logdet, outs = _Flow.apply(self, False, x, y, *params)
+                z, logdet, outs = _Flow.apply(self, False, _accumulate_nodes(params), x, y, *params)
         else:
             z, logdet, outs, _, _, _ = self._run_forward(x, y, False)
         return z, list(outs.unbind(0)), logdet
@@ -609,7 +646,7 @@ class RealNVP(nn.Module):
         self._check_inputs(x, y)
         params = [p for p in self._tparams if p.requires_grad] if torch.is_grad_enabled() else []
         if torch.is_grad_enabled() and (x.requires_grad or y.requires_grad or params):
-            return _FlowNLL.apply(self, x, y, *params[:1])
+            return _FlowNLL.apply(self, _accumulate_nodes(params[:1]), x, y, *params[:1])
         return -self.log_prob(x, y).mean()
 
     def denoise(self, x, y, noise_std):
@@ -622,7 +659,7 @@ class RealNVP(nn.Module):
         x, y = _dense(x.detach()), _dense(y.detach())
         if B == 0:
             return x.clone()
-        z, logdet, _, stash, packed, slot = self._run_forward(x, y, True)
+        z, logdet, _, stash, packed, slot = self._run_forward(x, y, True, want_outputs=False)
         try:
             with _on(dev):
                 # nf_nll_cotangents yields dz = g z / B, dlogdet = -g / B: g = -B gives the gradient of logprob.sum()

@@ -30,8 +30,24 @@ class FlatAdamW(torch.optim.Optimizer):
         flow_ids = set()
         for f in self._flows:
             flow_ids.update(id(p) for p in f.parameters())
-        self._other = [p for g in self.param_groups for p in g["params"] if id(p) not in flow_ids]
-        self._other_opt = torch.optim.AdamW(self._other, **defaults) if self._other else None
+        # parameters outside the flow arenas keep their param-group structure (and per-group hyper-parameters)
+        self._other_groups = []
+        for gi, g in enumerate(self.param_groups):
+            rest = [p for p in g["params"] if id(p) not in flow_ids]
+            if rest:
+                self._other_groups.append((gi, rest))
+        self._other_opt = (torch.optim.AdamW([dict(params=rest) for _, rest in self._other_groups], **defaults)
+                           if self._other_groups else None)
+        # a flow's arena is updated by one kernel with one set of hyper-parameters: all of its parameters must sit in
+        # the same param group (that group's lr / betas / eps / weight_decay apply)
+        self._flow_group = {}
+        for f in self._flows:
+            owners = {gi for gi, g in enumerate(self.param_groups) for p in g["params"]
+                      if any(p is q for q in f._tparams if q.requires_grad)}
+            if len(owners) != 1:
+                raise ValueError("FlatAdamW: the trainable parameters of a flow must all belong to exactly one "
+                                 f"param group (found {len(owners)})")
+            self._flow_group[id(f)] = owners.pop()
         self._fstate = {}     # id(flow) -> dict(step, exp_avg, exp_avg_sq, mask)
 
     def _flow_state(self, flow):
@@ -54,11 +70,13 @@ class FlatAdamW(torch.optim.Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
-        group = self.param_groups[0]
-        lr, (b1, b2), eps, wd = group["lr"], group["betas"], group["eps"], group["weight_decay"]
         for flow in self._flows:
+            group = self.param_groups[self._flow_group[id(flow)]]
+            lr, (b1, b2), eps, wd = group["lr"], group["betas"], group["eps"], group["weight_decay"]
             if not flow._is_flat():
                 flow._flatten()
+            if all(p.grad is None for p in flow._tparams if p.requires_grad):
+                continue          # torch.optim.AdamW skips parameters without a gradient (no decay, no moment update)
             g = flow._gflat
             views_ok = g is not None and all(
                 (not p.requires_grad) or (p.grad is not None and p.grad.data_ptr() == v.data_ptr())
@@ -78,10 +96,40 @@ class FlatAdamW(torch.optim.Optimizer):
             flow._packed_key = None           # parameters changed: rebuild the derived tables on the next call
             flow._bump_version()              # ... and make the change visible to the forward/backward version check
         if self._other_opt is not None:
-            for og in self._other_opt.param_groups:
-                og.update(lr=lr, betas=(b1, b2), eps=eps, weight_decay=wd)
+            for og, (gi, _) in zip(self._other_opt.param_groups, self._other_groups):
+                src = self.param_groups[gi]
+                og.update(lr=src["lr"], betas=src["betas"], eps=src["eps"], weight_decay=src["weight_decay"])
             self._other_opt.step()
         return loss
+
+    # ------------------------------------------------------------------ checkpointing
+    def state_dict(self):
+        """torch's format plus the flat moments of every flow and the delegate optimizer's state (the flow moments
+        live outside ``self.state``: one tensor per arena, not one per parameter)."""
+        sd = super().state_dict()
+        sd["nf_flows"] = [dict(step=st["step"], exp_avg=st["exp_avg"].clone(), exp_avg_sq=st["exp_avg_sq"].clone())
+                          if (st := self._fstate.get(id(f))) is not None else None for f in self._flows]
+        sd["nf_other"] = self._other_opt.state_dict() if self._other_opt is not None else None
+        return sd
+
+    def load_state_dict(self, state_dict):
+        state_dict = dict(state_dict)
+        flows = state_dict.pop("nf_flows", None)
+        other = state_dict.pop("nf_other", None)
+        super().load_state_dict(state_dict)
+        if flows is not None:
+            if len(flows) != len(self._flows):
+                raise ValueError("FlatAdamW.load_state_dict: number of flows differs")
+            for f, saved in zip(self._flows, flows):
+                if saved is None:
+                    self._fstate.pop(id(f), None)
+                    continue
+                st = self._flow_state(f)
+                st["step"] = int(saved["step"])
+                st["exp_avg"].copy_(saved["exp_avg"])
+                st["exp_avg_sq"].copy_(saved["exp_avg_sq"])
+        if other is not None and self._other_opt is not None:
+            self._other_opt.load_state_dict(other)
 
 
 class CosineLRSchedule(torch.nn.Module):
@@ -95,6 +143,12 @@ class CosineLRSchedule(torch.nn.Module):
         self.optimizer, self.min_lr, self.max_lr = optimizer, min_lr, max_lr
         self._n = 0
         self.set_lr(min_lr)
+        # resume: the reference reads the step count from the `counter` buffer (torch_utils.py:33-36), so a loaded
+        # checkpoint continues the schedule instead of restarting the warm-up
+        self.register_load_state_dict_post_hook(lambda module, keys: module._resync())
+
+    def _resync(self):
+        self._n = int(round(float(self.counter.item())))
 
     def set_lr(self, lr: float) -> float:
         if self.min_lr <= lr <= self.max_lr:

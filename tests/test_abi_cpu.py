@@ -89,15 +89,38 @@ def test_parameters_are_views_of_one_arena_and_survive_load_state_dict():
 
 
 def test_same_seed_gives_the_reference_initialisation():
-    """The containers are built with the same torch calls in the same order as
-    torch_fcnf.py:15-31,61-93, so a seed reproduces the reference's initial weights; the heads are
-    zero (s = t = 0 at init)."""
-    torch.manual_seed(0)
+    """The containers are built with the same torch calls in the same order as torch_fcnf.py:15-31,61-93, so a
+    seed reproduces the reference's initial weights BIT FOR BIT: the refinit fixtures hold the state_dict of the real
+    reference module built after torch.manual_seed(0) (tests/golden/make_golden.py:make_refinit perturbs only the
+    zero heads and the LayerNorm affine parameters afterwards).  The heads are zero (s = t = 0 at init)."""
+    import os
+    from tests.helpers import GOLDEN_DIR
+    for name in ("refinit_d9", "refinit_d2", "refinit_d8"):
+        g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+        D, C, R, n = [int(v) for v in g["cfg"][:4]]
+        torch.manual_seed(0)
+        m = nf_b200.RealNVP(D, C, R, n, None)
+        sd = m.state_dict()
+        checked = 0
+        for k in sd:
+            leaf = k.split(".", 2)[2]
+            if leaf.startswith("l.") or leaf[2:] in ("0.weight", "0.bias", "3.weight", "3.bias"):
+                np.testing.assert_array_equal(sd[k].numpy(), g["sd/" + k], err_msg=f"{name}: {k}")
+                checked += 1
+        assert checked == n * (5 + 8)
+        for blk in m.blocks:
+            assert float(blk.s[6].weight.abs().max()) == 0.0 and float(blk.t[6].bias.abs().max()) == 0.0
+            assert float((blk.s[2].weight - 1).abs().max()) == 0.0 and float(blk.t[5].bias.abs().max()) == 0.0
+            W = blk.l.P @ (torch.tril(blk.l.L, -1) + torch.eye(D)) @ (torch.triu(blk.l.U, 1) + torch.diag(blk.l.s))
+            assert torch.allclose(W @ W.T, torch.eye(D), atol=1e-5)   # orthogonal init
+
+
+def test_default_precision_is_the_tensor_core_path():
+    """A constructor call with the reference's exact positional signature (torch_nfbc_ant.py:147) must land on the
+    tcgen05 path, not on the FFMA checker."""
     m = nf_b200.RealNVP(8, 32, 16, 2, None)
-    for blk in m.blocks:
-        assert float(blk.s[6].weight.abs().max()) == 0.0 and float(blk.t[6].bias.abs().max()) == 0.0
-        W = blk.l.P @ (torch.tril(blk.l.L, -1) + torch.eye(8)) @ (torch.triu(blk.l.U, 1) + torch.diag(blk.l.s))
-        assert torch.allclose(W @ W.T, torch.eye(8), atol=1e-5)   # orthogonal init
+    assert m.precision == "fp32" and m._desc.precision == _lib.PREC["fp32"] == 1
+    assert nf_b200.GEncoder(8, 4, hidden=16, n_hidden=1).precision == "fp32"
 
 
 def test_cpu_tensors_are_refused():

@@ -1,0 +1,197 @@
+"""Full-size parity (run on the B200 box with `-m gpu`): the DEFAULT-dispatch tensor-core path (precision="fp32",
+every size-dependent choice of the dispatcher left on auto: fused LayerNorm epilogues, tile widths, split-K,
+rows per warp) against the float64 checker at every BASELINE.json config and its BASELINE batch size.
+
+Checker: oracle/torch_flow.py -- the reference module's op sequence in stock PyTorch, pinned in float64 to the
+fixtures generated from the real reference (tests/test_oracle_golden.py) -- run in float64 ON THE GPU in row chunks
+(rows are independent, torch_fcnf.py:134-141; parameter gradients add over chunks).  The same module in float32 is
+the "reference in its own precision" leg of the tolerance of BASELINE.md section 3:
+
+    err(ours, ref64) <= max(floor, 2 err(ref32, ref64)),   err = max|a - ref| / max|ref|
+    floor = 1e-5 for z / log_dets / dx / dy, 5e-5 for parameter gradients.
+
+LeakyReLU kinks: at these sizes (up to 6e9 pre-activations per pass) some pre-activations are within rounding of
+zero, where the derivative jumps from 0.01 to 1; whether the float32 and float64 runs land on the same side is a coin
+toss for the reference as well.  Rows whose float64 pre-activations come within `margin` of a kink get ZERO cotangents,
+so they take part in the forward comparison (all rows) but not in the gradient comparison; the count is printed.
+Nothing here reads /root/reference.
+"""
+import numpy as np
+import pytest
+import torch
+
+import nf_b200
+from oracle import synth
+from oracle.torch_flow import TorchFlow
+
+pytestmark = pytest.mark.gpu
+
+CHUNK = 8192
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def rel(a, ref):
+    scale = max(float(ref.abs().max()), 1e-30)
+    return float((a.double() - ref.double()).abs().max()) / scale
+
+
+class Checker:
+    """TorchFlow in `dtype` on the GPU, evaluated in row chunks."""
+
+    def __init__(self, cfg, sd, dtype):
+        self.cfg, self.dtype = cfg, dtype
+        m = TorchFlow(cfg["D"], cfg["C"], cfg["R"], cfg["n"], first_hidden=cfg["H1"], ln_eps=cfg["ln_eps"])
+        m.load_state_dict({k: torch.tensor(np.asarray(v)) for k, v in sd.items()})
+        self.m = m.to(dev()).to(dtype)
+        self.minabs = None
+        for mod in self.m.modules():
+            if isinstance(mod, torch.nn.LeakyReLU):
+                mod.register_forward_hook(self._hook)
+
+    def _hook(self, mod, inp, out):
+        if self.minabs is not None:
+            v = inp[0].detach().abs().amin(dim=1)
+            self.minabs[0] = v if self.minabs[0] is None else torch.minimum(self.minabs[0], v)
+
+    @torch.no_grad()
+    def forward(self, x, y, want_minabs=False):
+        zs, lds, mins = [], [], []
+        for i in range(0, x.shape[0], CHUNK):
+            self.minabs = [None] if want_minabs else None
+            z, _, ld = self.m(x[i:i + CHUNK].to(self.dtype), y[i:i + CHUNK].to(self.dtype))
+            zs.append(z); lds.append(ld)
+            if want_minabs:
+                mins.append(self.minabs[0])
+        self.minabs = None
+        return torch.cat(zs), torch.cat(lds), (torch.cat(mins) if want_minabs else None)
+
+    @torch.no_grad()
+    def reverse(self, z, y):
+        return torch.cat([self.m.reverse(z[i:i + CHUNK].to(self.dtype), y[i:i + CHUNK].to(self.dtype))
+                          for i in range(0, z.shape[0], CHUNK)])
+
+    def backward(self, x, y, dz, dld):
+        """-> dx, dy, {param: grad} of sum(z * dz) + sum(log_dets * dld)."""
+        for p in self.m.parameters():
+            p.grad = None
+        dxs, dys = [], []
+        for i in range(0, x.shape[0], CHUNK):
+            xc = x[i:i + CHUNK].to(self.dtype).requires_grad_(True)
+            yc = y[i:i + CHUNK].to(self.dtype).requires_grad_(True)
+            z, _, ld = self.m(xc, yc)
+            ((z * dz[i:i + CHUNK].to(self.dtype)).sum() + (ld * dld[i:i + CHUNK].to(self.dtype)).sum()).backward()
+            dxs.append(xc.grad); dys.append(yc.grad)
+        grads = {k: p.grad.clone() for k, p in self.m.named_parameters() if p.requires_grad}
+        return torch.cat(dxs), torch.cat(dys), grads
+
+
+def ours_of(cfg, sd, **kw):
+    m = nf_b200.RealNVP(cfg["D"], cfg["C"], cfg["R"], cfg["n"], None, first_hidden=cfg["H1"], ln_eps=cfg["ln_eps"], **kw)
+    m.load_state_dict({k: torch.tensor(np.asarray(v, dtype=np.float32)) for k, v in sd.items()})
+    return m.to(dev())
+
+
+def setup(cfgname, B):
+    cfg = dict(synth.CONFIGS[cfgname])
+    sd = synth.make_state_dict(cfg["D"], cfg["C"], cfg["R"], cfg["n"], seed=0, H1=cfg["H1"])
+    x, y = synth.make_inputs(B, cfg["D"], cfg["R"], seed=1234)
+    x, y = torch.tensor(x, device=dev()), torch.tensor(y, device=dev())
+    return cfg, sd, x, y
+
+
+# margin: distance of a float64 pre-activation from the LeakyReLU kink below which the row is kept out of the
+# gradient comparison; scaled with the depth/width of the config (deeper stacks drift further from float64)
+FULL = [("C1a", 256, 1e-5), ("C1b", 256, 1e-5), ("C1c", 256, 1e-5), ("C2a", 4096, 1e-5), ("C3", 16384, 1e-5),
+        ("C5", 8192, 4e-6), ("C5", 65536, 4e-6)]
+
+
+@pytest.mark.parametrize("cfgname,B,margin", FULL, ids=[f"{c}@{b}" for c, b, _ in FULL])
+def test_training_step_matches_float64_checker_at_full_size(cfgname, B, margin):
+    cfg, sd, x, y = setup(cfgname, B)
+    model = ours_of(cfg, sd)                       # default dispatch: precision="fp32" (tcgen05 3xTF32), options on auto
+    assert model.precision == "fp32"
+    c64, c32 = Checker(cfg, sd, torch.float64), Checker(cfg, sd, torch.float32)
+
+    z64, ld64, minabs = c64.forward(x, y, want_minabs=True)
+    z32, ld32, _ = c32.forward(x, y)
+    safe = minabs > margin
+    n_safe = int(safe.sum())
+    assert n_safe >= B // 3, f"only {n_safe} of {B} rows are kink-free at margin {margin}"
+
+    dz_h, dld_h = synth.make_cotangents(B, cfg["D"], seed=4321)
+    dz = torch.tensor(dz_h, device=dev()) * safe[:, None]
+    dld = torch.tensor(dld_h, device=dev()) * safe
+    dx64, dy64, g64 = c64.backward(x, y, dz, dld)
+    dx32, dy32, g32 = c32.backward(x, y, dz, dld)
+    del c64, c32
+
+    xt, yt = x.clone().requires_grad_(True), y.clone().requires_grad_(True)
+    z, outs, ld = model(xt, yt)
+    ((z * dz).sum() + (ld * dld).sum()).backward()
+    torch.cuda.synchronize()
+
+    report = {}
+
+    def check(name, ours, r32, r64, floor):
+        e, noise = rel(ours, r64), rel(r32, r64)
+        report[name] = (e, noise)
+        assert e <= max(floor, 2.0 * noise), (cfgname, B, name, e, noise)
+
+    check("z", z.detach(), z32, z64, 1e-5)
+    check("log_dets", ld.detach(), ld32, ld64, 1e-5)
+    assert torch.equal(outs[-1], z.detach())
+    check("dx", xt.grad, dx32, dx64, 1e-5)
+    check("dy", yt.grad, dy32, dy64, 1e-5)
+    worst = ("", 0.0, 0.0)
+    for k, p in model.named_parameters():
+        if not p.requires_grad:
+            continue
+        e, noise = rel(p.grad, g64[k]), rel(g32[k], g64[k])
+        if e - max(5e-5, 2 * noise) > worst[1] - max(5e-5, 2 * worst[2]) or not worst[0]:
+            worst = (k, e, noise)
+        assert e <= max(5e-5, 2.0 * noise), (cfgname, B, k, e, noise)
+    print(f"\n[full-size parity] {cfgname}@{B}: kink-free rows {n_safe}/{B}; "
+          + ", ".join(f"{k} {e:.2e} (ref32 {n:.2e})" for k, (e, n) in report.items())
+          + f"; worst parameter gradient {worst[0]} {worst[1]:.2e} (ref32 {worst[2]:.2e})")
+
+
+def test_sampling_and_denoise_match_float64_checker_at_full_size():
+    """C4 (kitchen NF-BC, 8192 envs per GPU): reverse(prior sample, y), then the denoise step x + sigma^2 dlogp/dx
+    (torch_nfbc_ant.py:207-217)."""
+    cfgname, B, margin, sigma = "C4", 8192, 1e-5, 0.1
+    cfg, sd, _, y = setup(cfgname, B)
+    model = ours_of(cfg, sd)
+    c64, c32 = Checker(cfg, sd, torch.float64), Checker(cfg, sd, torch.float32)
+    gen = torch.Generator(device=dev()).manual_seed(7)
+    eps = torch.randn((B, cfg["D"]), device=dev(), generator=gen)
+
+    with torch.no_grad():
+        a, rld = model.reverse(eps, y, return_logdet=True)
+    a64, a32 = c64.reverse(eps, y), c32.reverse(eps, y)
+    e, noise = rel(a, a64), rel(a32, a64)
+    assert e <= max(1e-5, 2.0 * noise), ("reverse", e, noise)
+    # forward of the sampled actions returns to the prior sample; reverse log-det = - forward log-det
+    z64, ld64, minabs = c64.forward(a64.float(), y, want_minabs=True)
+    assert rel(rld, -ld64) <= max(1e-5, 2.0 * rel(-c32.forward(a64.float(), y)[1], -ld64))
+
+    # denoise on the same actions for every implementation (the float64 sample rounded to float32)
+    act = a64.float().contiguous()
+    safe = minabs > margin
+    assert int(safe.sum()) >= B // 3
+    dz = -z64 * safe[:, None]
+    dld = torch.ones(B, device=dev(), dtype=torch.float64) * safe
+    dx64, _, _ = c64.backward(act, y, dz, dld)
+    dx32, _, _ = c32.backward(act, y, dz, dld)
+    out = model.denoise(act, y, sigma)
+    assert all(p.grad is None for p in model.parameters())
+    want64 = act.double() + sigma ** 2 * dx64
+    want32 = act.double() + sigma ** 2 * dx32.double()
+    step = (out.double() - act.double())[safe] / sigma ** 2
+    e, noise = rel(step, dx64[safe]), rel(dx32[safe], dx64[safe])
+    assert e <= max(1e-5, 2.0 * noise), ("denoise dlogp/dx", e, noise)
+    assert rel(out[safe], want64[safe]) <= max(1e-6, 2.0 * rel(want32[safe], want64[safe]))
+    print(f"\n[full-size parity] C4@{B}: reverse {rel(a, a64):.2e} (ref32 {rel(a32, a64):.2e}); "
+          f"denoise gradient {e:.2e} (ref32 {noise:.2e}); kink-free rows {int(safe.sum())}/{B}")
