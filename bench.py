@@ -1,19 +1,31 @@
 """Benchmark of the flow hot path (BASELINE.json metric), one process per GPU.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C2a] [--batch B]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--configs C1a,C2a,...]
 
 A step = one pass of the hot path over one batch of synthetic input:
     z, outputs, log_dets = model(x, y); loss = -(log N(z) + log_dets).mean(); loss.backward()
-(torch_nfbc_ant.py:267-272 without the optimizer; y requires grad like the encoder output it is in the
-reference, so dy is computed; data-parallel gradient all-reduce included when N > 1), and -- reported under "sampling" -- model.reverse(randn(B, D), y) (torch_nfbc_ant.py:209-210).
-Workload at N = 1: BASELINE.json configs[1] (goal-conditioned NF policy, obs+goal conditioning,
-action 8, batch 4096): D=8, C=256, R=64, n=6 ("C2a" in SURVEY.md section 8d); every rank runs the same
-per-GPU batch when N > 1 (weak scaling).  Prints ONE JSON line on rank 0.
+(torch_nfbc_ant.py:267-272 without the optimizer; y requires grad like the encoder output it is in the reference, so
+dy is computed; the data-parallel gradient all-reduce is included when N > 1) and -- reported under "sampling" --
+model.reverse(randn(B, D), y) (torch_nfbc_ant.py:209-210).
+
+Headline (`value`, `e2e`, `roofline`): BASELINE.json configs[1] (goal-conditioned NF policy, obs+goal conditioning,
+action 8, batch 4096): D=8, C=256, R=64, n=6 ("C2a" in SURVEY.md section 8d), 4096 rows per GPU (weak scaling),
+EXACTLY --steps timed steps.  `per_config` carries every BASELINE configuration at its BASELINE batch in the same
+JSON line (train / sampling / e2e / roofline per config; >= 100 timed steps for the small ones):
+    C1a, C1c  ant NF-BC flow (D = 8 / 400), batch 256 per GPU                                    weak
+    C2a       as the headline, 100 steps                                                         weak
+    C3        latent-actor flow of nf.py (H1 = C + R, eps 1e-6), 16384 per GPU, DP all-reduce    weak
+    C4        kitchen NF-BC sampling, 65536 parallel envs sharded over the GPUs (no collective)  strong
+    C5        stress flow (24 blocks, width 1024, D = 32), global batch 65536 sharded            strong
+Before anything is timed, one forward of every config is compared with the float64 checker (the reference's op
+sequence in stock PyTorch, oracle/torch_flow.py, on the GPU) and the run aborts on a mismatch.
+Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -27,7 +39,18 @@ if ROOT not in sys.path:
 import numpy as np
 
 METRIC = "flow train samples/sec (log_prob fwd+bwd) & sampled actions/sec, 1/2/4/8 B200"
-DEFAULT_BATCH = {"C1a": 256, "C1b": 256, "C1c": 256, "C2a": 4096, "C3": 16384, "C3t": 16384, "C4": 8192, "C5": 8192}
+HEADLINE = "C2a"
+# name -> (batch, "per_gpu" | "global", legs, timed steps: "K" = --steps, int = at least that many)
+PLAN = {
+    "C1a": dict(batch=256, shard="per_gpu", train=True, steps=100),
+    "C1c": dict(batch=256, shard="per_gpu", train=True, steps=100),
+    "C2a": dict(batch=4096, shard="per_gpu", train=True, steps=100),
+    "C3": dict(batch=16384, shard="per_gpu", train=True, steps=100),
+    "C4": dict(batch=65536, shard="global", train=False, steps="K"),
+    "C5": dict(batch=65536, shard="global", train=True, steps="K"),
+}
+CPU_SAMPLE_ROWS = {"C1a": 256, "C1c": 256, "C2a": 4096, "C3": 4096, "C4": 2048, "C5": 1024}
+LOG2PI = float(np.log(2 * np.pi))
 
 
 def load_peaks():
@@ -38,6 +61,16 @@ def load_peaks():
         return dict(hbm_gbs=p["hbm_gbs"], bf16_tflops=p["bf16_tflops"], bf16_sustained=p.get("bf16_tflops_sustained"),
                     source="measured (MEASURED_PEAKS.json)")
     return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+def load_traffic():
+    """dram bytes per launch of the dominant kernels, parsed from committed `ncu --set full` captures by
+    tools/ncu_traffic.py (profiles/ncu_traffic.json: {"<config>:<kernel class>": {"bytes": ..., "source": ...}})."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(path):
+        return {}
+    with open(path) as f:
+        return json.load(f)
 
 
 class ClockSampler:
@@ -83,22 +116,36 @@ class ClockSampler:
             for n, v in zip(names, f[2:6]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
-        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+        # median over the samples taken under load (an idle GPU between legs parks at a low clock)
+        busy = [v for v in sm if mx and v >= 0.6 * max(mx)] or sm
+        return dict(sm_mhz=float(np.median(busy)) if busy else None, sm_max_mhz=max(mx) if mx else None,
                     reasons=sorted(reasons), samples=len(sm))
 
 
 def config_of(name):
     from oracle import synth
-    cfg = dict(synth.CONFIGS[name])
-    return cfg
+    return dict(synth.CONFIGS[name])
+
+
+def batch_per_gpu(name, world):
+    p = PLAN[name]
+    return p["batch"] if p["shard"] == "per_gpu" else max(1, p["batch"] // world)
+
+
+def config_dict(name, world, precision="fp32"):
+    """The `config` object BOTH arms print for the headline (identical dicts; the reference arm describes its bounded
+    CPU sample in cpu_baseline.sample)."""
+    cfg = config_of(name)
+    B = batch_per_gpu(name, world)
+    return {"workload": f"{name}: coupling flow D={cfg['D']} C={cfg['C']} R={cfg['R']} n={cfg['n']} H1={cfg['H1']}, "
+                        f"batch {B} per GPU, log_prob forward+backward",
+            **cfg, "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
+            "l2": "flushed between timed iterations (256 MB write)", "precision": precision}
 
 
 # --------------------------------------------------------------------------------------------------
 # CPU arm: the reference's op sequence in stock PyTorch (oracle/torch_flow.py) on the host cores
 # --------------------------------------------------------------------------------------------------
-LOG2PI = float(np.log(2 * np.pi))
-
-
 def cpu_step_fn(cfgname, B, seed=0):
     """The reference's CPU path: oracle/torch_flow.py, the stock-PyTorch restatement of the reference module (the same
     nn.Linear / LayerNorm / cat / exp ops + autograd; pinned to the reference-generated fixtures by
@@ -146,12 +193,11 @@ def time_cpu(fn, min_seconds, max_iters):
 def run_reference_arm(args):
     """--impl reference: the reference's CPU path (stock-PyTorch restatement of the reference module, all host threads)."""
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    cfgname = args.config
-    B_full = args.batch or DEFAULT_BATCH[cfgname]
-    B = min(B_full, 4096)
-    train, sample = cpu_step_fn(cfgname, B)
+    B = min(batch_per_gpu(HEADLINE, world), 4096)
+    train, sample = cpu_step_fn(HEADLINE, B)
     for _ in range(args.warmup):
         train()
     t0 = time.perf_counter()
@@ -165,11 +211,12 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{cfgname} coupling flow, batch {B} per step on the host CPU", **config_of(cfgname)},
+        "config": config_dict(HEADLINE, world),
         "sampling": {"value": B / ts, "unit": "actions/s"},
         "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} steps of forward+backward at batch {B} (oracle/torch_flow.py: the "
-                                   f"reference's op sequence in stock PyTorch on the host, {cores} threads)"},
+                         "sample": f"{args.steps} steps of forward+backward at batch {B} on the host CPU "
+                                   f"(oracle/torch_flow.py: the reference's op sequence in stock PyTorch, {cores} threads; "
+                                   f"the reference is a Python module under /root/reference that cannot travel to this box)"},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(out), flush=True)
@@ -178,12 +225,177 @@ def run_reference_arm(args):
 # --------------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------------
+KERNEL_NAMES = {"tc_gemm": "k_tc_gemm<BN,STAGES,false> (tcgen05 Linear fwd/dgrad)",
+                "tc_wgrad": "k_tc_gemm<BN,STAGES,true> (tcgen05 weight gradient)",
+                "simt_gemm": "k_gemm (FFMA)"}
+
+
+class Runner:
+    """One BASELINE configuration on this rank's GPU."""
+
+    def __init__(self, name, precision, dev, rank, world, flush):
+        import torch
+        import nf_b200
+        from oracle import synth
+        self.torch, self.name, self.dev, self.rank, self.world, self.flush = torch, name, dev, rank, world, flush
+        self.cfg = cfg = config_of(name)
+        self.B = B = batch_per_gpu(name, world)
+        self.D, self.R = cfg["D"], cfg["R"]
+        self.sd = synth.make_state_dict(cfg["D"], cfg["C"], cfg["R"], cfg["n"], seed=0, H1=cfg["H1"])
+        model = nf_b200.RealNVP(cfg["D"], cfg["C"], cfg["R"], cfg["n"], None, first_hidden=cfg["H1"],
+                                ln_eps=cfg["ln_eps"], precision=precision)
+        model.load_state_dict({k: torch.tensor(v) for k, v in self.sd.items()})
+        self.model = model.to(dev)
+        if world > 1 and PLAN[name]["train"]:
+            self.model.enable_data_parallel()
+            if os.environ.get("NF_B200_DP_BUCKET_BLOCKS"):     # experiment knob: bucketed all-reduce
+                self.model.dp_bucket_blocks = int(os.environ["NF_B200_DP_BUCKET_BLOCKS"])
+        xh, yh = synth.make_inputs(B, cfg["D"], cfg["R"], seed=1234 + rank)
+        self.x_pin, self.y_pin = torch.tensor(xh).pin_memory(), torch.tensor(yh).pin_memory()
+        self.x, self.y = self.x_pin.to(dev), self.y_pin.to(dev)
+        self.plist = [p for p in self.model.parameters() if p.requires_grad]
+        self.step_stats = {}
+
+    # ---- the steps ----
+    def train_step(self, xd, yd):
+        model, D = self.model, self.D
+        model._packed_key = None          # parameters change every real training step: rebuild the tables
+        for p in self.plist:              # optimizer.zero_grad(set_to_none=True)
+            p.grad = None
+        yd = yd.detach().requires_grad_(True)   # y is the encoder output in the reference (torch_nfbc_ant.py:267)
+        z, _, ld = model(xd, yd)
+        loss = -((-0.5 * (z * z).sum(1) - 0.5 * D * LOG2PI) + ld).mean()
+        loss.backward()
+        return loss
+
+    def train_step_nll(self, xd, yd):
+        # the same step with the library's fused loss (RealNVP.nll: SURVEY section 8 row f3)
+        model = self.model
+        model._packed_key = None
+        for p in self.plist:
+            p.grad = None
+        loss = model.nll(xd, yd.detach().requires_grad_(True))
+        loss.backward()
+        return loss
+
+    def sample_step(self, xd, yd):
+        with self.torch.no_grad():
+            return self.model.reverse(xd, yd)
+
+    # ---- parity gate ----
+    def parity_check(self, rows=2048):
+        """One forward of this configuration against the float64 checker (oracle/torch_flow.py on the GPU) on the
+        first `rows` rows of the step's inputs; tolerance of BASELINE.md section 3."""
+        torch = self.torch
+        from oracle.torch_flow import TorchFlow
+        cfg, n = self.cfg, min(rows, self.B)
+        x, y = self.x[:n].contiguous(), self.y[:n].contiguous()
+        with torch.no_grad():
+            z, _, ld = self.model(x, y)
+        res = {}
+        ref = {}
+        for dt in (torch.float64, torch.float32):
+            m = TorchFlow(cfg["D"], cfg["C"], cfg["R"], cfg["n"], first_hidden=cfg["H1"], ln_eps=cfg["ln_eps"])
+            m.load_state_dict({k: torch.tensor(v) for k, v in self.sd.items()})
+            m = m.to(self.dev).to(dt)
+            with torch.no_grad():
+                zz, _, ll = m(x.to(dt), y.to(dt))
+            ref[dt] = (zz.double(), ll.double())
+            del m
+
+        def rel(a, b):
+            return float((a.double() - b).abs().max()) / max(float(b.abs().max()), 1e-30)
+        for name, ours, i in (("z", z, 0), ("log_dets", ld, 1)):
+            e, noise = rel(ours, ref[torch.float64][i]), rel(ref[torch.float32][i], ref[torch.float64][i])
+            res[name] = {"err": e, "ref32_err": noise, "tol": max(1e-5, 2 * noise)}
+            if not e <= max(1e-5, 2 * noise):
+                raise SystemExit(f"bench.py: parity check failed for {self.name} ({name}: {e:.3e} > {max(1e-5, 2 * noise):.3e})")
+        res["rows"] = n
+        return res
+
+    # ---- timing ----
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def timed(self, tag, fn, steps, warmup, e2e=False):
+        torch = self.torch
+
+        def one():
+            if e2e:
+                xd = self.x_pin.to(self.dev, non_blocking=True)   # H2D of this step's inputs from pinned memory
+                yd = self.y_pin.to(self.dev, non_blocking=True)
+                out = fn(xd, yd)
+                _ = float(out.reshape(-1)[0].item()) if out.dim() else float(out.item())   # D2H of the result
+            else:
+                fn(self.x, self.y)
+        for _ in range(warmup):                         # same code path as the timed steps
+            self.flush.zero_()
+            one()
+        self.barrier()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for a, b in ev:
+            self.flush.zero_()                          # evict L2 between timed iterations (outside the events)
+            a.record()
+            one()
+            b.record()
+        self.barrier()
+        per = [a.elapsed_time(b) for a, b in ev]
+        t = torch.tensor([sum(per)], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)    # max over ranks
+        self.step_stats[tag] = (float(np.median(per)), float(max(per)))
+        return t.item() / steps
+
+    def roofline(self, ms_step, peaks, traffic, train):
+        """Per-kernel-class CUDA-event timing inside the same step (profiling on: eager launches)."""
+        torch = self.torch
+        from nf_b200 import _lib
+        from oracle import synth
+        _lib.lib.nf_prof_enable(1)
+        _lib.prof_collect()
+        reps = 3
+        for _ in range(reps):
+            self.flush.zero_()
+            (self.train_step if train else self.sample_step)(self.x, self.y)
+        torch.cuda.synchronize()
+        prof = _lib.prof_collect()
+        _lib.lib.nf_prof_enable(0)
+        tot_ms = sum(v[0] for v in prof.values()) or 1.0
+        dom = max(("tc_gemm", "tc_wgrad", "simt_gemm"), key=lambda k: prof[k][0])
+        d_ms, d_work, d_n = prof[dom]
+        achieved = d_work / (d_ms * 1e-3) / 1e12 if d_ms > 0 else 0.0
+        F_fwd = synth.flops_fwd_per_sample(**self.cfg)
+        step_flops = (3 if train else 1) * F_fwd * self.B
+        tr = traffic.get(f"{self.name}:{dom}")
+        return {
+            "bound": "tensor", "kernel": KERNEL_NAMES[dom], "achieved": achieved, "peak": peaks["bf16_tflops"],
+            "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
+            "traffic": tr["bytes"] if tr else None, "traffic_unit": "bytes/launch",
+            "traffic_source": tr["source"] if tr else None,
+            "peak_source": peaks["source"] + ", dense bf16 burst",
+            "launches_timed": int(d_n), "share_of_step": d_ms / tot_ms,
+            "whole_step": {"achieved": step_flops / (ms_step * 1e-3) / 1e12, "unit": "TFLOP/s",
+                           "frac": step_flops / (ms_step * 1e-3) / 1e12 / peaks["bf16_tflops"],
+                           "what": "train step (3 F_fwd B)" if train else "sampling pass (F_fwd B)"},
+            "breakdown": {k: {"ms_per_step": v[0] / reps, "launches_per_step": v[2] // reps, "share": v[0] / tot_ms}
+                          for k, v in prof.items() if v[2]},
+        }
+
+    def free(self):
+        self.model = None
+        self.x = self.y = self.x_pin = self.y_pin = None
+        self.torch.cuda.empty_cache()
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    import nf_b200
+    import nf_b200                                        # noqa: F401
     from nf_b200 import _lib
-    from oracle import synth
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -193,125 +405,76 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-
-    cfgname = args.config
-    cfg = config_of(cfgname)
-    B = args.batch or DEFAULT_BATCH[cfgname]
-    D, R = cfg["D"], cfg["R"]
-    sd = synth.make_state_dict(D, cfg["C"], R, cfg["n"], seed=0, H1=cfg["H1"])
-    model = nf_b200.RealNVP(D, cfg["C"], R, cfg["n"], None, first_hidden=cfg["H1"], ln_eps=cfg["ln_eps"],
-                            precision=args.precision)
-    model.load_state_dict({k: torch.tensor(v) for k, v in sd.items()})
-    model = model.to(dev)
-    if world > 1:
-        model.enable_data_parallel()
-        if os.environ.get("NF_B200_DP_BUCKET_BLOCKS"):     # experiment knob: overlapped bucketed all-reduce
-            model.dp_bucket_blocks = int(os.environ["NF_B200_DP_BUCKET_BLOCKS"])
-    xh, yh = synth.make_inputs(B, D, R, seed=1234 + rank)
-    x_pin, y_pin = torch.tensor(xh).pin_memory(), torch.tensor(yh).pin_memory()
-    x, y = x_pin.to(dev), y_pin.to(dev)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
+    peaks, traffic = load_peaks(), load_traffic()
+    K, W = args.steps, args.warmup
+    passes = 3 if args.precision in ("fp32", "tf32x3") else 1
 
-    plist = [p for p in model.parameters() if p.requires_grad]
-
-    def train_step(xd, yd):
-        model._packed_key = None          # parameters change every real training step: rebuild the tables
-        for p in plist:                   # optimizer.zero_grad(set_to_none=True)
-            p.grad = None
-        yd = yd.detach().requires_grad_(True)   # y is the encoder output in the reference (torch_nfbc_ant.py:267): dy is part of the step
-        z, _, ld = model(xd, yd)
-        loss = -((-0.5 * (z * z).sum(1) - 0.5 * D * LOG2PI) + ld).mean()
-        loss.backward()
-        return loss
-
-    def train_step_nll(xd, yd):
-        # the same step with the library's fused loss (RealNVP.nll: SURVEY section 8 row f3) instead of the ~8 torch
-        # kernels + autograd nodes of the reference's loss expression
-        model._packed_key = None
-        for p in plist:
-            p.grad = None
-        loss = model.nll(xd, yd.detach().requires_grad_(True))
-        loss.backward()
-        return loss
-
-    def sample_step(xd, yd):
-        with torch.no_grad():
-            return model.reverse(xd, yd)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps, warmup, e2e=False):
-        def one():
-            if e2e:
-                xd = x_pin.to(dev, non_blocking=True)   # H2D of this step's inputs from pinned memory
-                yd = y_pin.to(dev, non_blocking=True)
-                out = fn(xd, yd)
-                _ = float(out.reshape(-1)[0].item()) if out.dim() else float(out.item())   # D2H of the result
-            else:
-                fn(x, y)
-        for _ in range(warmup):                         # same code path as the timed steps
-            flush.zero_()
-            one()
-        barrier()
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        wall0 = time.perf_counter()
-        for a, b in ev:
-            flush.zero_()                               # evict L2 between timed iterations (outside the events)
-            a.record()
-            one()
-            b.record()
-        barrier()
-        wall = time.perf_counter() - wall0
-        per = [a.elapsed_time(b) for a, b in ev]
-        ms = sum(per)
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)    # max over ranks
-        step_stats.append((float(np.median(per)), float(max(per))))
-        if os.environ.get("BENCH_DEBUG"):
-            print("per-step ms:", " ".join(f"{v:.3f}" for v in per), file=sys.stderr, flush=True)
-        return t.item() / steps, wall
-
-    step_stats = []
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+
+    # ------------------------------------------------------------------ headline: C2a, exactly K timed steps
+    r = Runner(HEADLINE, args.precision, dev, rank, world, flush)
+    parity = {HEADLINE: r.parity_check()}
     _lib.lib.nf_launch_count(1)
     gstats = [_lib.graph_stats()]
-    ms_train, _ = timed(train_step, args.steps, args.warmup)
-    launches = _lib.lib.nf_launch_count(1) // (args.steps + args.warmup)
+    ms_train = r.timed("train", r.train_step, K, W)
+    launches = _lib.lib.nf_launch_count(1) // (K + W)
     gstats.append(_lib.graph_stats())
-    ms_sample, _ = timed(sample_step, args.steps, args.warmup)
+    ms_sample = r.timed("sample", r.sample_step, K, W)
     gstats.append(_lib.graph_stats())
-    ms_e2e, _ = timed(train_step, args.steps, args.warmup, e2e=True)
+    ms_e2e = r.timed("e2e_train", r.train_step, K, W, e2e=True)
     gstats.append(_lib.graph_stats())
-    ms_e2e_sample, _ = timed(sample_step, args.steps, args.warmup, e2e=True)
+    ms_e2e_sample = r.timed("e2e_sample", r.sample_step, K, W, e2e=True)
     gstats.append(_lib.graph_stats())
-    ms_e2e_nll, _ = timed(train_step_nll, args.steps, args.warmup, e2e=True)   # informational, not the headline
+    ms_e2e_nll = r.timed("e2e_nll", r.train_step_nll, K, W, e2e=True)   # informational, not the headline
     leg_graphs = {name: dict(zip(("replays", "captures", "eager_calls"), (b[i] - a[i] for i in range(3))))
                   for name, a, b in zip(("train", "sample", "e2e_train", "e2e_sample"), gstats[:-1], gstats[1:])}
-    # the four timed legs above are short (tens of ms at the default K): keep the same kernels running until
-    # nvidia-smi (100 ms period) has seen them under load; these extra steps are not part of any reported time
-    # (a FIXED count derived from the max-reduced step time: with world > 1 every train_step contains the gradient
-    # all-reduce, so all ranks must run the same number of steps -- a wall-clock loop deadlocks the process group)
+    # The timed legs above are short (tens of ms at the default K): keep the same kernels running until nvidia-smi
+    # (100 ms period) has seen them under load; these extra steps are not part of any reported time.  A FIXED count
+    # derived from the max-reduced step time: with world > 1 every train_step contains the gradient all-reduce, so
+    # all ranks must run the same number of steps.
     for _ in range(int(min(4000, max(10, 1500.0 / max(ms_train, 1e-3))))):
-        train_step(x, y)
+        r.train_step(r.x, r.y)
     torch.cuda.synchronize()
+    head_roof = r.roofline(ms_train, peaks, traffic, True)
+    head_stats = dict(r.step_stats)
+    B_head = r.B
+    bytes_in = r.x_pin.numel() * 4 + r.y_pin.numel() * 4
+    r.free()
+
+    # ------------------------------------------------------------------ every BASELINE configuration
+    per_config = {}
+    names = [c for c in args.configs.split(",") if c]
+    for name in names:
+        plan = PLAN[name]
+        steps = K if plan["steps"] == "K" else max(K, int(plan["steps"]))
+        r = Runner(name, args.precision, dev, rank, world, flush)
+        parity[name] = r.parity_check()
+        entry = {"config": config_dict(name, world, args.precision), "scaling": "weak" if plan["shard"] == "per_gpu" else "strong",
+                 "steps": steps, "warmup": W}
+        total_B = r.B * world
+        if plan["train"]:
+            ms = r.timed("train", r.train_step, steps, W)
+            entry["train"] = {"value": total_B / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms,
+                              "ms_median_max": list(r.step_stats["train"])}
+        ms_s = r.timed("sample", r.sample_step, steps, W)
+        entry["sampling"] = {"value": total_B / (ms_s * 1e-3), "unit": "actions/s", "ms_per_step": ms_s,
+                             "ms_median_max": list(r.step_stats["sample"])}
+        e2e = {"h2d_bytes_per_step": r.x_pin.numel() * 4 + r.y_pin.numel() * 4, "d2h_bytes_per_step": 4}
+        if plan["train"]:
+            ms_e = r.timed("e2e_train", r.train_step, steps, W, e2e=True)
+            e2e["train"] = {"value": total_B / (ms_e * 1e-3), "unit": "samples/s", "ms_per_step": ms_e}
+        ms_es = r.timed("e2e_sample", r.sample_step, steps, W, e2e=True)
+        e2e["sampling"] = {"value": total_B / (ms_es * 1e-3), "unit": "actions/s", "ms_per_step": ms_es}
+        entry["e2e"] = e2e
+        entry["roofline"] = r.roofline(ms if plan["train"] else ms_s, peaks, traffic, plan["train"])
+        per_config[name] = entry
+        r.free()
+
     clocks = sampler.stop() if rank == 0 else None
     replays, captures, eager = _lib.graph_stats()
-
-    # ---- roofline pass: per-kernel-class CUDA-event timing inside the same step (profiling on) ----
-    _lib.lib.nf_prof_enable(1)
-    _lib.prof_collect()
-    for _ in range(3):
-        flush.zero_()
-        train_step(x, y)
-    torch.cuda.synchronize()
-    prof = _lib.prof_collect()
-    _lib.lib.nf_prof_enable(0)
 
     if rank != 0:
         # wait for rank 0 (CPU baseline, JSON line) and leave the process group together with it
@@ -319,87 +482,68 @@ def run_ours(args):
         dist.destroy_process_group()
         return
 
-    peaks = load_peaks()
-    F_fwd = synth.flops_fwd_per_sample(**cfg)
-    total_B = B * world
-    value = total_B / (ms_train * 1e-3)
-    tot_ms = sum(v[0] for v in prof.values()) or 1.0
-    dom = max(("tc_gemm", "tc_wgrad", "simt_gemm"), key=lambda k: prof[k][0])
-    d_ms, d_work, d_n = prof[dom]
-    achieved = d_work / (d_ms * 1e-3) / 1e12 if d_ms > 0 else 0.0
-    breakdown = {k: {"ms_per_step": v[0] / 3, "launches_per_step": v[2] // 3,
-                     "share": v[0] / tot_ms} for k, v in prof.items() if v[2]}
-    passes = 3 if args.precision in ("fp32", "tf32x3") else 1
-    roofline = {
-        "bound": "tensor", "kernel": {"tc_gemm": "k_tc_gemm<BN,STAGES,false> (tcgen05 Linear fwd/dgrad)",
-                                      "tc_wgrad": "k_tc_gemm<BN,STAGES,true> (tcgen05 weight gradient)",
-                                      "simt_gemm": "k_gemm (FFMA)"}[dom],
-        "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-        "frac": achieved / peaks["bf16_tflops"],
-        # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the class's heaviest member, the fused
-        # layer-2 Linear (M=4096, N=256, K=256, both nets) -- ncu --set full, profiles/r1_ncu_full_forward_block_C2a.txt
-        # (cold cache under ncu; algorithmic bytes: 8.4 MB in + 0.5 MB weights + 8.4 MB out)
-        "traffic": 9.52e6 if cfgname == "C2a" and B == 4096 else None, "traffic_unit": "bytes/launch",
-        "peak_source": peaks["source"] + ", dense bf16 burst",
-        "note": (f"algorithmic FLOPs (2MNK per launch, split-precision passes NOT counted) / mean launch duration over "
-                 f"{d_n} launches; the kernel issues {passes} kind::tf32 MMAs per product at half the bf16 rate, so the "
-                 f"tensor-pipe-equivalent rate is {achieved * passes * 2:.0f} TFLOP/s bf16-equivalent"),
-        "share_of_step": d_ms / tot_ms,
-        "whole_step": {"achieved": 3 * F_fwd * B / (ms_train * 1e-3) / 1e12, "unit": "TFLOP/s",
-                       "frac": 3 * F_fwd * B / (ms_train * 1e-3) / 1e12 / peaks["bf16_tflops"]},
-        "breakdown": breakdown,
-    }
-
-    # ---- CPU baseline: the reference's op sequence in stock PyTorch on this box's host cores, bounded sample,
+    # ---- CPU baseline: the reference's op sequence in stock PyTorch on this box's host cores, bounded samples,
     # at N = 1 only (the other ranks of a multi-GPU run would just wait for it) -----------------------------------
     cpu_baseline = None
     if world == 1:
-        Bc = min(B, 4096)
-        ctrain, csample = cpu_step_fn(cfgname, Bc)
-        per, iters = time_cpu(ctrain, 10.0, 200)
         cores = os.cpu_count()
+        Bc = min(B_head, 4096)
+        ctrain, csample = cpu_step_fn(HEADLINE, Bc)
+        per, iters = time_cpu(ctrain, 10.0, 200)
         cpu_baseline = {"value": Bc / per, "unit": "samples/s", "cores": cores, "kind": "port",
                         "sample": f"{iters} steps of forward+backward at batch {Bc} of the same config "
                                   f"(oracle/torch_flow.py: the reference's op sequence in stock PyTorch on the host, "
                                   f"{cores} threads, {per * iters:.1f} s)"}
+        for name in names:
+            if name == HEADLINE:
+                per_config[name]["cpu_baseline"] = dict(cpu_baseline)
+                continue
+            Bc = min(batch_per_gpu(name, 1), CPU_SAMPLE_ROWS[name])
+            ctrain, csample = cpu_step_fn(name, Bc)
+            fn, unit = (ctrain, "samples/s") if PLAN[name]["train"] else (csample, "actions/s")
+            per, iters = time_cpu(fn, 2.5, 20)
+            per_config[name]["cpu_baseline"] = {
+                "value": Bc / per, "unit": unit, "cores": cores, "kind": "port",
+                "sample": f"{iters} {'train steps' if PLAN[name]['train'] else 'reverse passes'} at batch {Bc} "
+                          f"(oracle/torch_flow.py on the host, {cores} threads, {per * iters:.1f} s)"}
 
-    bytes_in = x_pin.numel() * 4 + y_pin.numel() * 4
+    total_B = B_head * world
+    head_roof["note"] = (f"algorithmic FLOPs (2MNK per launch, split-precision passes NOT counted) / mean launch duration "
+                         f"over {head_roof['launches_timed']} launches; the kernel issues {passes} kind::tf32 MMAs per "
+                         f"product at half the bf16 rate, so the tensor-pipe-equivalent rate is "
+                         f"{head_roof['achieved'] * passes * 2:.0f} TFLOP/s bf16-equivalent")
     out = {
-        "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_train, "higher_is_better": True, "scaling": "weak",
+        "metric": METRIC, "value": total_B / (ms_train * 1e-3), "unit": "samples/s", "n_gpus": world, "steps": K,
+        "warmup": W, "ms_per_step": ms_train, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32 (tcgen05 3xTF32 split, fp32 accumulate)" if passes == 3 else args.precision,
         "data": "synthetic",
-        "config": {"workload": f"{cfgname}: coupling flow D={D} C={cfg['C']} R={R} n={cfg['n']} H1={cfg['H1']}, "
-                               f"batch {B} per GPU, log_prob forward+backward",
-                   "global_batch": total_batch_str(total_B), "parallelism": f"dp{world}",
-                   "l2": "flushed between timed iterations (256 MB write)", "precision": args.precision},
+        "config": config_dict(HEADLINE, world, args.precision),
         "sampling": {"value": total_B / (ms_sample * 1e-3), "unit": "actions/s", "ms_per_step": ms_sample},
         "e2e": {"value": total_B / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": bytes_in,
-                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e, "ms_median_max": list(step_stats[2]),
+                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e, "ms_median_max": list(head_stats["e2e_train"]),
                 "sampling": {"value": total_B / (ms_e2e_sample * 1e-3), "unit": "actions/s",
-                             "d2h_bytes_per_step": 4, "ms_median_max": list(step_stats[3])},
+                             "d2h_bytes_per_step": 4, "ms_median_max": list(head_stats["e2e_sample"])},
                 "with_fused_loss": {"value": total_B / (ms_e2e_nll * 1e-3), "unit": "samples/s",
                                     "ms_per_step": ms_e2e_nll,
                                     "note": "same end-to-end step with loss = model.nll(x, y) (library NLL kernels) "
                                             "instead of the reference's torch-side loss expression"}},
-        "gpu_launches": int(launches * args.steps),
+        "gpu_launches": int(launches * K),
         "gpu_launches_per_step": int(launches),
         "launch_graphs": {"replays": replays, "captures": captures, "eager_calls": eager, "per_leg": leg_graphs,
                           "note": "the library replays its kernel sequence as a cached CUDA graph; gpu_launches "
                                   "counts the library's kernels inside the replayed graphs"},
-        "train_ms_median_max": list(step_stats[0]),
+        "train_ms_median_max": list(head_stats["train"]),
         "clocks": clocks,
-        "roofline": roofline,
+        "roofline": head_roof,
         "cpu_baseline": cpu_baseline,
+        "parity_check": {"checker": "oracle/torch_flow.py in float64 on the GPU, first rows of each config's inputs; "
+                                    "err = max|a-ref|/max|ref| <= max(1e-5, 2 err(ref32, ref64))", **parity},
+        "per_config": per_config,
     }
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-
-
-def total_batch_str(n):
-    return int(n)
 
 
 def main():
@@ -408,8 +552,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="C2a")
-    ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--configs", default="C1a,C1c,C2a,C3,C4,C5",
+                    help="comma-separated configurations of the per_config table (empty: headline only)")
     ap.add_argument("--precision", default="fp32", choices=["fp32", "fp32_simt"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
