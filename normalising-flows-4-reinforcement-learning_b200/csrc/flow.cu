@@ -37,6 +37,7 @@ const OptDef kOpts[NF_OPT_COUNT] = {
     {"pdl", "NF_B200_PDL", 1},           {"streams", "NF_B200_STREAMS", 1},       {"tma_store", "NF_B200_TMA_STORE", 1},
     {"nacc", "NF_B200_NACC", 0},         {"fused_ln", "NF_B200_FUSED_LN", -1},    {"fused_tail", "NF_B200_FUSED_TAIL", 0},
     {"bn256", "NF_B200_BN256", 0},       {"ts", "NF_B200_TS", 1},                 {"presplit", "NF_B200_PRESPLIT", 1},
+    {"whatif", "NF_B200_WHATIF", 0},
 };
 int g_opt[NF_OPT_COUNT];
 bool g_opt_init = false;
@@ -809,6 +810,7 @@ int nf_flow_backward_range(const NfFlowDesc* desc, const float* params, const vo
   const float* gcur = first_range ? dz : (pp ? w.d0 : w.d1);
   const bool fused = use_row_fused(m);
   const bool v2 = fused && row_v2_supported(m.D, m.C, m.H1);
+  const int whatif = option(NF_OPT_WHATIF);
   SideStreams* ss = (v2 && (dparams || dy)) ? side_streams() : nullptr;
   cudaStream_t s1 = ss ? ss->s1 : st, s2 = ss ? ss->s2 : st;
   bool used1[2] = {false, false}, used2[2] = {false, false};
@@ -912,7 +914,7 @@ int nf_flow_backward_range(const NfFlowDesc* desc, const float* params, const vo
       g.B = sb + sl.xh1; g.ldb = m.H1; g.sB = sl.net_stride;
       g.C = dn + pl.slot_off[NF_P_W2]; g.ldc = m.H1; g.sC = pl.net_stride;
       g.M = m.C; g.N = m.H1; g.K = B; g.batch = 2;
-      NF_TRY(wgrad_tn(m.prec, g, s1));
+      if (!(whatif & 2)) NF_TRY(wgrad_tn(m.prec, g, s1));
     }
     bool ln1_fused = false;
     {  // f. d x_hat1 = du2 W2f   (K-major B operand = W2f^T)
@@ -959,7 +961,7 @@ int nf_flow_backward_range(const NfFlowDesc* desc, const float* params, const vo
       if (m.R > 0) {
         g.B = y; g.ldb = m.R;
         g.C = dn + pl.slot_off[NF_P_W1] + m.dc; g.N = m.R;
-        NF_TRY(wgrad_tn(m.prec, g, s2));
+        if (!(whatif & 2)) NF_TRY(wgrad_tn(m.prec, g, s2));
       }
     }
     {  // i. d h0 = du1_t W1_t + du1_s W1_s : first dc columns -> dxp, the rest -> dy  (B operand = W1^T)
@@ -974,7 +976,7 @@ int nf_flow_backward_range(const NfFlowDesc* desc, const float* params, const vo
         g.B0 += (int64_t)m.dc * m.H1; g.B1 += (int64_t)m.dc * m.H1;
         if (kl.hi_off) { g.B0hi = g.B0 + kl.hi_off; g.B0lo = g.B0 + kl.lo_off; g.B1hi = g.B1 + kl.hi_off; g.B1lo = g.B1 + kl.lo_off; }
         g.C = dy; g.ldc = m.R; g.N = m.R;
-        NF_TRY(linear_nt(m.prec, g, s2));
+        if (!(whatif & 4)) NF_TRY(linear_nt(m.prec, g, s2));
       }
     }
     float* dst = (i > 0 || dx) ? ((i == 0) ? dx : (pp ? w.d1 : w.d0)) : nullptr;
@@ -1011,7 +1013,8 @@ int nf_flow_backward_range(const NfFlowDesc* desc, const float* params, const vo
         jobs[2].coef = xin; jobs[2].ldcf = m.D; jobs[2].m = m.D;
         jobs[2].out = w.dWs + (int64_t)i * DD; jobs[2].so_i = m.D; jobs[2].so_c = 1;
         jobs[2].batch = 1;
-        if (ss) {
+        if (whatif & 1) {
+        } else if (ss) {
           NF_CUDA(cudaEventRecord(ss->evC, st));
           NF_TRY(col_reduce(&jobs[0], 1, B, s1));
           NF_CUDA(cudaStreamWaitEvent(s1, ss->evC, 0));   // dxp is final after the tail kernel
