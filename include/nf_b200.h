@@ -139,6 +139,30 @@ NF_API int nf_flow_backward_range(const NfFlowDesc* desc, const float* params, c
                            int32_t block_begin, int32_t block_end,
                            void* workspace, int64_t ws_bytes, void* stream);
 
+/* ---- data parallel (SURVEY section 8 row e) --------------------------------------------------------------
+ * One process per GPU, batch-sharded, full weight replica; the one exchange step is the average of the gradient
+ * arena over the ranks.  The library owns an NCCL communicator per device (NCCL is bound at run time with
+ * dlopen("libnccl.so.2"), i.e. the build the host process already uses) so that the all-reduce is issued from inside
+ * the backward launch sequence and captured into its CUDA graph:
+ *   nf_dp_unique_id   rank 0 fills a 128-byte ncclUniqueId; the host distributes it (torch.distributed, MPI, a file)
+ *   nf_dp_init        every rank, with its CUDA device current (collective: ncclCommInitRank)
+ *   nf_dp_allreduce   in-place sum or average of a device buffer (standalone use: the encoder's arena)
+ *   nf_dp_broadcast   in-place broadcast from `root` (initial parameter replica)
+ *   nf_flow_backward_dp  nf_flow_backward + the averaged gradient arena: blocks are processed from the top down in
+ *                     buckets of `bucket_blocks` blocks; each finished bucket (one contiguous slice of the arena) is
+ *                     all-reduced on a side stream while the next bucket computes.  dparams must not be NULL. */
+NF_API int nf_dp_unique_id(void* id128);
+NF_API int nf_dp_init(const void* id128, int32_t rank, int32_t world);
+NF_API int nf_dp_world(void);
+NF_API int nf_dp_allreduce(float* buf, int64_t n, int32_t average, void* stream);
+NF_API int nf_dp_broadcast(float* buf, int64_t n, int32_t root, void* stream);
+NF_API int nf_dp_shutdown(void);
+NF_API int nf_flow_backward_dp(const NfFlowDesc* desc, const float* params, const void* packed,
+                        const void* stash, const float* y, int64_t B,
+                        const float* dz, const float* dlogdet,
+                        float* dx, float* dy, float* dparams, int32_t bucket_blocks,
+                        void* workspace, int64_t ws_bytes, void* stream);
+
 /* Standalone affine coupling + log-det kernels (HBM-bound; torch_fcnf.py:101-104, :112-113).
  *   fwd: z[:, :dc] = xp[:, :dc];  z[:, dc:] = (xp[:, dc:] - t) * exp(-s);  logdet += c - sum_j s
  *   inv: xp[:, dc:] = z[:, dc:] * exp(s) + t;                              logdet += sum_j s - c
@@ -232,7 +256,8 @@ NF_API int nf_graphs_stats(int64_t* replays, int64_t* captures, int64_t* eager);
 /* Run-time options, by name (also NF_B200_<NAME> in the environment, read once): "pdl" (programmatic dependent
  * launch, 1), "streams" (backward on three streams, 1), "tma_store" (bulk-tensor-store epilogues, 1), "nacc" (main
  * accumulators in rotation, 0 = 3), "fused_ln" (LayerNorm in the GEMM epilogue: -1 auto / 0 / 1), "fused_tail"
- * (flow tail in the layer-2 GEMM, 0), "bn256" (256-wide tiles: 0 auto / 1 / 2 never).  Every setting computes the
+ * (flow tail in the layer-2 GEMM, 0), "bn256" (256-wide tiles: 0 auto / 1 / 2 never), "stack" (persistent whole-stack
+ * forward / inverse kernel: -1 auto / 0 / 1), "whatif" (experiments only: skips backward work, wrong gradients).  Every setting computes the
  * same function (tests/test_flow_gpu.py::test_options_are_equivalent); setting one clears the launch graphs. */
 NF_API int nf_set_option(const char* name, int value);
 NF_API int nf_get_option(const char* name);

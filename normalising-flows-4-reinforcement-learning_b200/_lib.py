@@ -60,6 +60,13 @@ def _load():
         "nf_flow_inverse": (c_int, [D, fp, vp, fp, fp, i64, fp, fp, fp, vp, i64, vp]),
         "nf_flow_backward": (c_int, [D, fp, vp, vp, fp, i64, fp, fp, fp, fp, fp, vp, i64, vp]),
         "nf_flow_backward_range": (c_int, [D, fp, vp, vp, fp, i64, fp, fp, fp, fp, fp, c_int32, c_int32, vp, i64, vp]),
+        "nf_flow_backward_dp": (c_int, [D, fp, vp, vp, fp, i64, fp, fp, fp, fp, fp, c_int32, vp, i64, vp]),
+        "nf_dp_unique_id": (c_int, [vp]),
+        "nf_dp_init": (c_int, [vp, c_int32, c_int32]),
+        "nf_dp_world": (c_int, []),
+        "nf_dp_allreduce": (c_int, [fp, i64, c_int32, vp]),
+        "nf_dp_broadcast": (c_int, [fp, i64, c_int32, vp]),
+        "nf_dp_shutdown": (c_int, []),
         "nf_affine_logdet_fwd": (c_int, [fp, fp, fp, fp, fp, c_float, i64, c_int32, fp, fp, fp, vp]),
         "nf_affine_logdet_inv": (c_int, [fp, fp, fp, fp, fp, c_float, i64, c_int32, fp, fp, vp]),
         "nf_affine_logdet_bwd": (c_int, [fp, fp, fp, fp, i64, c_int32, fp, fp, fp, vp]),

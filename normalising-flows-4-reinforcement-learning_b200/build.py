@@ -44,7 +44,8 @@ def build(force=False, verbose=False):
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libnf_b200.so")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB + ".tmp"] + sources()
+    extra = os.environ.get("NF_B200_NVCC_FLAGS", "").split()     # experiments (e.g. -DNF_ASLOTS64=4)
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB + ".tmp"] + sources()
     # No -lcuda: the few driver entry points (cuTensorMapEncodeTiled) are fetched at run time with
     # cudaGetDriverEntryPoint, so the library loads (and exports its symbols) on hosts without a driver.
     res = subprocess.run(cmd, capture_output=True, text=True)

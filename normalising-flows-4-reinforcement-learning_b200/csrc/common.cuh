@@ -63,6 +63,8 @@ enum NfOpt {
   NF_OPT_BN256,          // 256-wide GEMM tiles: 0 auto (K <= 256), 1 always, 2 never           (default 0)
   NF_OPT_TS,             // A operand of the K-major GEMMs from tensor memory                   (default 1)
   NF_OPT_PRESPLIT,       // weight operands split into hi / lo once per parameter update        (default 1)
+  NF_OPT_STACK,          // persistent whole-stack forward / inverse kernel: -1 auto (small grids), 0 never, 1 always (default -1)
+  NF_OPT_STACK_NSG,      // splitter groups of the whole-stack kernel: 1 or 2 (default 2)
   NF_OPT_WHATIF,         // EXPERIMENTS ONLY (wrong gradients): bit 0 skip column reductions, 1 skip weight-gradient
                          // GEMMs, 2 skip the dy GEMM -- upper bounds for what removing that work could buy (default 0)
   NF_OPT_COUNT

@@ -6,7 +6,9 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "dp.cuh"
 #include "elementwise.cuh"
+#include "flow_stack.cuh"
 #include "graphs.cuh"
 #include "linear.cuh"
 #include "rowfused.cuh"
@@ -37,7 +39,7 @@ const OptDef kOpts[NF_OPT_COUNT] = {
     {"pdl", "NF_B200_PDL", 1},           {"streams", "NF_B200_STREAMS", 1},       {"tma_store", "NF_B200_TMA_STORE", 1},
     {"nacc", "NF_B200_NACC", 0},         {"fused_ln", "NF_B200_FUSED_LN", -1},    {"fused_tail", "NF_B200_FUSED_TAIL", 0},
     {"bn256", "NF_B200_BN256", 0},       {"ts", "NF_B200_TS", 1},                 {"presplit", "NF_B200_PRESPLIT", 1},
-    {"whatif", "NF_B200_WHATIF", 0},
+    {"stack", "NF_B200_STACK", -1},      {"stack_nsg", "NF_B200_STACK_NSG", 2},   {"whatif", "NF_B200_WHATIF", 0},
 };
 int g_opt[NF_OPT_COUNT];
 bool g_opt_init = false;
@@ -233,19 +235,21 @@ static BwdWs carve_bwd(const Dims& m, int64_t B, void* ws) {
 // graph), so the critical path per block is 3 kernels instead of 8.  Blocks alternate between two sets of
 // intermediate buffers and the main stream waits for the side work of block i+2 before it overwrites them.
 struct SideStreams {
-  cudaStream_t s1 = nullptr, s2 = nullptr;
+  cudaStream_t s1 = nullptr, s2 = nullptr, s3 = nullptr;   // s3: gradient all-reduce of finished buckets (data parallel)
   cudaEvent_t evA = nullptr, evB = nullptr, evC = nullptr, done1[2] = {nullptr, nullptr}, done2[2] = {nullptr, nullptr};
+  cudaEvent_t evD = nullptr, done3 = nullptr;
   bool ok = false;
 };
-static SideStreams* side_streams() {
+static SideStreams* side_streams(bool force = false) {
   static SideStreams per_dev[64];
   int dev = 0;
-  if (!option(NF_OPT_STREAMS) || cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if ((!force && !option(NF_OPT_STREAMS)) || cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
   SideStreams& s = per_dev[dev];
   if (!s.ok) {
     bool good = cudaStreamCreateWithFlags(&s.s1, cudaStreamNonBlocking) == cudaSuccess &&
-                cudaStreamCreateWithFlags(&s.s2, cudaStreamNonBlocking) == cudaSuccess;
-    cudaEvent_t* evs[] = {&s.evA, &s.evB, &s.evC, &s.done1[0], &s.done1[1], &s.done2[0], &s.done2[1]};
+                cudaStreamCreateWithFlags(&s.s2, cudaStreamNonBlocking) == cudaSuccess &&
+                cudaStreamCreateWithFlags(&s.s3, cudaStreamNonBlocking) == cudaSuccess;
+    cudaEvent_t* evs[] = {&s.evA, &s.evB, &s.evC, &s.done1[0], &s.done1[1], &s.done2[0], &s.done2[1], &s.evD, &s.done3};
     for (cudaEvent_t* e : evs) good = good && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess;
     if (!good) { cudaGetLastError(); return nullptr; }
     s.ok = true;
@@ -381,6 +385,28 @@ static int conditioners(const Dims& m, const NfParamLayout& pl, const PackedLayo
     NF_TRY(linear_nt(m.prec, g, st));
   }
   return 0;
+}
+
+// The persistent whole-stack kernel (flow_stack.cuh) replaces the per-layer launches of a forward / inverse pass when
+// the flow is narrow (D <= 9), both hidden widths are equal multiples of 128 and the grid is small enough to be
+// latency-bound (at most two waves of CTAs; larger batches keep the per-layer kernels, whose epilogues overlap with
+// other tiles' MMAs).
+static bool stack_params(const Dims& m, const NfParamLayout& pl, const PackedLayout& kl, const float* params,
+                         const float* packed, int64_t B, StackP* out) {
+  const int mode = option(NF_OPT_STACK);
+  if (mode == 0 || m.prec != NF_PREC_TF32X3 || m.H1 != m.C || !kl.hi_off) return false;
+  StackP p;
+  p.B = B; p.D = m.D; p.H = m.C; p.R = m.R; p.n = m.n; p.eps = m.eps;
+  p.raw_hi = (m.dc + m.R >= 512 || m.C >= 512) ? 0 : 1;
+  p.W1p = packed + kl.net0 + kl.W1p; p.K1p = kl.K1p; p.dcp = kl.dcp;
+  p.W2f = packed + kl.net0 + kl.W2f;
+  p.w_net = kl.net_stride; p.w_blk = kl.block_stride; p.hi_off = kl.hi_off; p.lo_off = kl.lo_off;
+  p.b1 = params + pl.slot_off[NF_P_B1]; p.b1_net = pl.net_stride; p.b1_blk = pl.block_stride;
+  p.b2f = packed + kl.net0 + kl.b2f; p.W3f = packed + kl.net0 + kl.W3f; p.b3f = packed + kl.net0 + kl.b3f;
+  p.cdev = packed + kl.logdet_c;
+  if (mode != 1 && cdiv(B, 128) * 2 * (m.C / 128) > 2 * 148) return false;
+  *out = p;
+  return true;
 }
 
 }  // namespace nf
@@ -576,6 +602,35 @@ int nf_flow_forward(const NfFlowDesc* desc, const float* params, const void* pac
   NF_CUDA(cudaMemsetAsync(logdet, 0, B * sizeof(float), st));
   const float* cur = x_in;
   const bool fused = use_row_fused(m);
+  StackP sp;
+  if (fused && stack_params(m, pl, kl, params, packed, B, &sp)) {
+    sp.inverse = 0;
+    sp.cur = w.xp; sp.cur_w = w.xp; sp.ld_cur = w.Dp; sp.y = y;
+    sp.Wmat = packed + kl.W;
+    if (stash) {
+      float* sb = stash + sl.blocks;
+      sp.xh1 = sb + sl.xh1; sp.xh2 = sb + sl.xh2; sp.xh_net = sl.net_stride; sp.xh_blk = sl.block_stride;
+      sp.store_xh2 = 1;
+      sp.rstd1 = sb + sl.r1; sp.rstd2 = sb + sl.r2;
+      sp.mask1 = reinterpret_cast<uint32_t*>(sb + sl.m1); sp.mask2 = reinterpret_cast<uint32_t*>(sb + sl.m2);
+      sp.mw = sl.mw1;
+      sp.out = stash + sl.xs + BD; sp.out_blk = BD;
+      sp.s_out = stash + sl.ss; sp.s_blk = B * m.dt;
+    } else {
+      sp.xh1 = w.xh1; sp.xh2 = w.xh2; sp.xh_net = B * m.C; sp.xh_blk = 0;
+      if (outputs) { sp.out = outputs; sp.out_blk = BD; }
+      else { sp.out = z; sp.out_blk = 0; }
+    }
+    sp.logdet = logdet;
+    if (flow_stack_supported(sp)) {
+      GemmP g;   // xp = x @ W_0   (torch_fcnf.py:40); later blocks: the previous block's tail
+      g.A0 = cur; g.lda0 = m.D; g.K0 = m.D;
+      g.B0 = packed + kl.W; g.ldb0 = m.D;
+      g.C = w.xp; g.ldc = w.Dp; g.M = (int)B; g.N = m.D;
+      NF_TRY(simt_gemm(g, st));
+      return flow_stack(sp, st);
+    }
+  }
   for (int i = 0; i < m.n; ++i) {
     const float* pb = params + (int64_t)i * pl.block_stride;
     const float* kb = packed + (int64_t)i * kl.block_stride;
@@ -692,6 +747,16 @@ int nf_flow_inverse(const NfFlowDesc* desc, const float* params, const void* pac
   }
   int step = 0;
   const bool fused = use_row_fused(m);
+  StackP sp;
+  if (fused && !seq && stack_params(m, pl, kl, params, packed, B, &sp)) {
+    sp.inverse = 1;
+    sp.cur = cur; sp.cur_w = const_cast<float*>(cur); sp.ld_cur = ldcur; sp.y = y;   // (a workspace copy of z: updated in place)
+    sp.Wmat = packed + kl.Winv;
+    sp.xh1 = w.xh1; sp.xh2 = w.xh2; sp.xh_net = B * m.C; sp.xh_blk = 0;
+    sp.logdet = logdet;
+    sp.final_out = x; sp.ld_final = m.D;
+    if (flow_stack_supported(sp)) return flow_stack(sp, st);
+  }
   for (int i = m.n - 1; i >= 0; --i, ++step) {
     const float* pb = params + (int64_t)i * pl.block_stride;
     const float* kb = packed + (int64_t)i * kl.block_stride;
@@ -741,15 +806,21 @@ int nf_flow_inverse(const NfFlowDesc* desc, const float* params, const void* pac
   return 0;
 }
 
-int nf_flow_backward_range(const NfFlowDesc* desc, const float* params, const void* packed_v, const void* stash_v,
-                           const float* y, int64_t B, const float* dz, const float* dlogdet, float* dx, float* dy,
-                           float* dparams, int32_t block_begin, int32_t block_end, void* workspace, int64_t ws_bytes,
-                           void* stream) {
+// dp_bucket > 0: data-parallel backward -- the call's block range is processed in sub-ranges of dp_bucket blocks from
+// the top block down and the finished gradient slice of every sub-range is averaged over the ranks (NCCL, the
+// library's communicator) on a third side stream while the next sub-range computes; everything is part of the one
+// launch graph of the call.
+static int backward_impl(const NfFlowDesc* desc, const float* params, const void* packed_v, const void* stash_v,
+                         const float* y, int64_t B, const float* dz, const float* dlogdet, float* dx, float* dy,
+                         float* dparams, int32_t block_begin, int32_t block_end, int32_t dp_bucket, void* workspace,
+                         int64_t ws_bytes, void* stream) {
   NF_TRY(check_desc(desc));
   NF_CHECK_ARG(block_begin >= 0 && block_begin < block_end && block_end <= desc->n_blocks, NF_E_BADARG,
                "block range [%d, %d) outside [0, %d)", block_begin, block_end, desc->n_blocks);
   const bool first_range = block_end == desc->n_blocks, last_range = block_begin == 0;
-  const int nr = block_end - block_begin;
+  const int nr_all = block_end - block_begin;
+  if (dp_bucket > 0) NF_CHECK_ARG(dp_world() > 1 && dparams != nullptr, NF_E_BADARG,
+                                  "data-parallel backward needs nf_dp_init (world > 1) and a gradient arena");
   NF_CHECK_ARG(B >= 0 && B < (int64_t(1) << 30), NF_E_BADARG, "B=%lld out of range", (long long)B);
   NF_TRY(check_ptr(params, "params", true));
   NF_TRY(check_ptr(packed_v, "packed", true));
@@ -759,7 +830,9 @@ int nf_flow_backward_range(const NfFlowDesc* desc, const float* params, const vo
   param_layout(m, &pl);
   cudaStream_t user_st = reinterpret_cast<cudaStream_t>(stream);
   if (B == 0) {
-    if (dparams) NF_TRY(fill_zero(dparams + (int64_t)block_begin * pl.block_stride, (int64_t)nr * pl.block_stride, user_st));
+    if (dparams) NF_TRY(fill_zero(dparams + (int64_t)block_begin * pl.block_stride, (int64_t)nr_all * pl.block_stride, user_st));
+    // (an empty shard still takes part in the collective)
+    if (dp_bucket > 0) NF_TRY(dp_allreduce(dparams + (int64_t)block_begin * pl.block_stride, (int64_t)nr_all * pl.block_stride, true, user_st));
     return 0;
   }
   NF_TRY(check_ptr(stash_v, "stash", true));
@@ -782,6 +855,7 @@ int nf_flow_backward_range(const NfFlowDesc* desc, const float* params, const vo
   key.op = 4; key.desc = *desc; key.B = B; key.ws_bytes = ws_bytes;
   key.ptr[0] = params; key.ptr[1] = packed_v; key.ptr[2] = stash_v; key.ptr[8] = dparams; key.ptr[9] = workspace;
   key.flags = (dz ? 1 : 0) | (dlogdet ? 2 : 0) | (dx ? 4 : 0) | (dy ? 8 : 0) | (block_begin << 8) | (block_end << 20);
+  key.ptr[10] = reinterpret_cast<const void*>((uintptr_t)(dp_bucket > 0 ? dp_bucket : 0));
   // cotangents in, dx / dy out through the workspace; y is the copy forward left in the stash
   float* const dx_user = dx;
   float* const dy_user = dy;
@@ -797,10 +871,10 @@ int nf_flow_backward_range(const NfFlowDesc* desc, const float* params, const vo
   if (dy) dy = w.io_dy;
   y = stash + sl.y;
   auto body = [&](cudaStream_t st) -> int {
-  if (dparams) NF_TRY(fill_zero(dparams + (int64_t)block_begin * pl.block_stride, (int64_t)nr * pl.block_stride, st));
+  if (dparams) NF_TRY(fill_zero(dparams + (int64_t)block_begin * pl.block_stride, (int64_t)nr_all * pl.block_stride, st));
   if (dy && first_range) NF_TRY(fill_zero(dy, B * m.R, st));
   if (dparams) {
-    NF_TRY(fill_zero(w.dWs + (int64_t)block_begin * DD, nr * DD, st));
+    NF_TRY(fill_zero(w.dWs + (int64_t)block_begin * DD, nr_all * DD, st));
     if (dlogdet) NF_TRY(sum_vector(dlogdet, B, w.sumdld, st));
     else NF_TRY(fill_zero(w.sumdld, 4, st));
   }
@@ -812,10 +886,16 @@ int nf_flow_backward_range(const NfFlowDesc* desc, const float* params, const vo
   const bool v2 = fused && row_v2_supported(m.D, m.C, m.H1);
   const int whatif = option(NF_OPT_WHATIF);
   SideStreams* ss = (v2 && (dparams || dy)) ? side_streams() : nullptr;
+  SideStreams* sar = dp_bucket > 0 ? side_streams(true) : nullptr;     // all-reduce stream
+  NF_CHECK_ARG(dp_bucket <= 0 || sar != nullptr, NF_E_UNSUPPORTED, "could not create the all-reduce stream");
   cudaStream_t s1 = ss ? ss->s1 : st, s2 = ss ? ss->s2 : st;
-  bool used1[2] = {false, false}, used2[2] = {false, false};
   struct { float *dxp, *dout, *gA, *gB; } w2[2] = {{w.dxp, w.dout, w.gA, w.gB}, {w.dxp2, w.dout2, w.gA2, w.gB2}};
-  for (int i = block_end - 1; i >= block_begin; --i) {
+  bool any_ar = false;
+  for (int sub_end = block_end; sub_end > block_begin;) {
+  const int sub_begin = dp_bucket > 0 ? std::max(block_begin, sub_end - dp_bucket) : block_begin;
+  const int nr = sub_end - sub_begin;
+  bool used1[2] = {false, false}, used2[2] = {false, false};
+  for (int i = sub_end - 1; i >= sub_begin; --i) {
     const int par = ss ? ((m.n - 1 - i) & 1) : 0;
     const auto& wb = w2[par];   // this block's intermediate buffers
     if (ss) {   // the side work of block i+2 read this buffer set
@@ -1067,9 +1147,9 @@ int nf_flow_backward_range(const NfFlowDesc* desc, const float* params, const vo
   }
   if (dparams) {
     GemmP g;  // T1 = P^T dW
-    const float* prm = params + (int64_t)block_begin * pl.block_stride;
-    const float* pck = packed + (int64_t)block_begin * kl.block_stride;
-    float* dWr = w.dWs + (int64_t)block_begin * DD;
+    const float* prm = params + (int64_t)sub_begin * pl.block_stride;
+    const float* pck = packed + (int64_t)sub_begin * kl.block_stride;
+    float* dWr = w.dWs + (int64_t)sub_begin * DD;
     Dims mr = m;
     mr.n = nr;   // the parameter-sized kernels below run over this range's blocks only
     g.transA = 1; g.A0 = prm + pl.slot_off[NF_P_P]; g.lda0 = m.D; g.sA0 = pl.block_stride; g.K0 = m.D;
@@ -1086,9 +1166,21 @@ int nf_flow_backward_range(const NfFlowDesc* desc, const float* params, const vo
     u.B0 = dWr; u.ldb0 = m.D; u.sB0 = DD;
     u.C = w.dUh; u.ldc = m.D; u.sC = DD; u.M = m.D; u.N = m.D; u.batch = nr;
     NF_TRY(simt_gemm(u, st));
-    float* dpr = dparams + (int64_t)block_begin * pl.block_stride;
+    float* dpr = dparams + (int64_t)sub_begin * pl.block_stride;
     NF_TRY(plu_grad_finish(prm, pl, mr, w.dLh, w.dUh, w.sumdld, dpr, st));
     NF_TRY(unfold_grads(prm, pl, mr, dpr, st));
+    if (sar) {   // this sub-range's gradients are final: average them over the ranks while the next sub-range computes
+      NF_CUDA(cudaEventRecord(sar->evD, st));
+      NF_CUDA(cudaStreamWaitEvent(sar->s3, sar->evD, 0));
+      NF_TRY(dp_allreduce(dpr, (int64_t)nr * pl.block_stride, true, sar->s3));
+      any_ar = true;
+    }
+  }
+  sub_end = sub_begin;
+  }   // sub-ranges
+  if (any_ar) {
+    NF_CUDA(cudaEventRecord(sar->done3, sar->s3));
+    NF_CUDA(cudaStreamWaitEvent(st, sar->done3, 0));
   }
   return 0;
   };
@@ -1102,12 +1194,29 @@ int nf_flow_backward_range(const NfFlowDesc* desc, const float* params, const vo
   return 0;
 }
 
+int nf_flow_backward_range(const NfFlowDesc* desc, const float* params, const void* packed_v, const void* stash_v,
+                           const float* y, int64_t B, const float* dz, const float* dlogdet, float* dx, float* dy,
+                           float* dparams, int32_t block_begin, int32_t block_end, void* workspace, int64_t ws_bytes,
+                           void* stream) {
+  return backward_impl(desc, params, packed_v, stash_v, y, B, dz, dlogdet, dx, dy, dparams, block_begin, block_end, 0,
+                       workspace, ws_bytes, stream);
+}
+
 int nf_flow_backward(const NfFlowDesc* desc, const float* params, const void* packed_v, const void* stash_v,
                      const float* y, int64_t B, const float* dz, const float* dlogdet, float* dx, float* dy,
                      float* dparams, void* workspace, int64_t ws_bytes, void* stream) {
   NF_TRY(check_desc(desc));
-  return nf_flow_backward_range(desc, params, packed_v, stash_v, y, B, dz, dlogdet, dx, dy, dparams, 0, desc->n_blocks,
-                                workspace, ws_bytes, stream);
+  return backward_impl(desc, params, packed_v, stash_v, y, B, dz, dlogdet, dx, dy, dparams, 0, desc->n_blocks, 0,
+                       workspace, ws_bytes, stream);
+}
+
+int nf_flow_backward_dp(const NfFlowDesc* desc, const float* params, const void* packed_v, const void* stash_v,
+                        const float* y, int64_t B, const float* dz, const float* dlogdet, float* dx, float* dy,
+                        float* dparams, int32_t bucket_blocks, void* workspace, int64_t ws_bytes, void* stream) {
+  NF_TRY(check_desc(desc));
+  NF_CHECK_ARG(bucket_blocks >= 1, NF_E_BADARG, "bucket_blocks must be >= 1");
+  return backward_impl(desc, params, packed_v, stash_v, y, B, dz, dlogdet, dx, dy, dparams, 0, desc->n_blocks,
+                       bucket_blocks, workspace, ws_bytes, stream);
 }
 
 int nf_linear(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, float* C, int64_t ldc,

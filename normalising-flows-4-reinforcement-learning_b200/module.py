@@ -156,6 +156,30 @@ def _param_grads_wanted(needs, nodes):
         return True      # autograd.grad with the parameters themselves as inputs: leaf queries are unsupported there
 
 
+_LIB_COMM = {}     # (device index, group id) -> world size of the library's NCCL communicator
+
+
+def _init_library_comm(process_group, device):
+    """Open the library's own NCCL communicator on `device` for the ranks of `process_group` (once per process)."""
+    import torch.distributed as dist
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    world, rank = dist.get_world_size(process_group), dist.get_rank(process_group)
+    if _LIB_COMM.get(key) == world and lib.nf_dp_world() == world:
+        return
+    with _on(device):
+        ident = torch.zeros(128, dtype=torch.uint8, device=device)
+        if rank == 0:
+            buf = ctypes.create_string_buffer(128)
+            _lib.check(lib.nf_dp_unique_id(buf), "nf_dp_unique_id")
+            ident.copy_(torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8))
+        dist.broadcast(ident, src=dist.get_global_rank(process_group, 0) if process_group is not None else 0,
+                       group=process_group)
+        raw = bytes(ident.cpu().numpy().tobytes())
+        torch.cuda.synchronize(device)
+        _lib.check(lib.nf_dp_init(ctypes.c_char_p(raw), rank, world), "nf_dp_init")
+    _LIB_COMM[key] = world
+
+
 class _Flow(torch.autograd.Function):
     """autograd bridge: forward = nf_flow_forward, backward = nf_flow_backward.
 
@@ -297,6 +321,7 @@ class RealNVP(nn.Module):
         self._dp_group = None
         self._dp_world = 1
         self._dp_avg = False
+        self._dp_in_graph = False
         self._flatten()
         self.register_load_state_dict_post_hook(lambda module, keys: module._flatten())
 
@@ -482,7 +507,13 @@ class RealNVP(nn.Module):
             if need_p:
                 dflat = out if out is not None else torch.empty(self._layout.total, dtype=torch.float32, device=dev)
             ptr = lambda t: t.data_ptr() if t is not None else None
-            if need_p and self._dp_world > 1 and int(self.dp_bucket_blocks) > 0:
+            if need_p and self._dp_world > 1 and getattr(self, "_dp_in_graph", False):
+                bucket = int(self.dp_bucket_blocks) or max(1, -(-self.n_layers // 3))    # default: three buckets
+                _lib.check(lib.nf_flow_backward_dp(
+                    ctypes.byref(self._desc), self._flat.data_ptr(), packed.data_ptr(), stash.data_ptr(), y.data_ptr(),
+                    B, ptr(dz), ptr(dld), ptr(dx), ptr(dy), dflat.data_ptr(), bucket, ws.data_ptr(), ws.numel(),
+                    self._stream(dev)), "nf_flow_backward_dp")
+            elif need_p and self._dp_world > 1 and int(self.dp_bucket_blocks) > 0:
                 self._backward_overlapped(stash, packed, y, B, dz, dld, dx, dy, dflat, ws, dev)
             else:
                 _lib.check(lib.nf_flow_backward(
@@ -535,17 +566,27 @@ class RealNVP(nn.Module):
         return dx, dy
 
     # ------------------------------------------------------------------ data parallel
-    def enable_data_parallel(self, process_group=None):
-        """Batch-sharded data parallel training: gradients of the flat arena are averaged over the
-        ranks of `process_group` (NCCL over NVLink on the GPU box) inside backward."""
+    def enable_data_parallel(self, process_group=None, in_graph=None):
+        """Batch-sharded data parallel training: gradients of the flat arena are averaged over the ranks of
+        `process_group` inside backward.
+
+        With the NCCL backend on CUDA the library opens its own communicator (``nf_dp_init``; the 128-byte unique id
+        travels through ``torch.distributed``) and the averaging runs INSIDE the backward launch graph
+        (``nf_flow_backward_dp``): blocks finish from the top down, every bucket of ``dp_bucket_blocks`` blocks is
+        all-reduced on a side stream while the next bucket computes.  Other backends (gloo on CPU tests) use one
+        ``torch.distributed.all_reduce`` after the backward call.  Replicas start from rank 0's parameters."""
         import torch.distributed as dist
         self._dp_group = process_group
         self._dp_world = dist.get_world_size(process_group)
         self._dp_avg = dist.get_backend(process_group) == "nccl"     # NCCL averages inside the reduction
-        # replicas start from rank 0's parameters, like DistributedDataParallel's construction-time broadcast
+        self._dp_in_graph = False
         if self._dp_world > 1:
             if not self._is_flat():
                 self._flatten()
+            want = self._dp_avg and self._flat.is_cuda if in_graph is None else bool(in_graph)
+            if want:
+                _init_library_comm(process_group, self._flat.device)
+                self._dp_in_graph = True
             with torch.no_grad():
                 dist.broadcast(self._flat, src=dist.get_global_rank(process_group, 0) if process_group is not None else 0,
                                group=process_group)
@@ -561,10 +602,10 @@ class RealNVP(nn.Module):
             dist.all_reduce(dflat, op=dist.ReduceOp.SUM, group=self._dp_group)
             dflat.mul_(1.0 / self._dp_world)
 
-    # Blocks per gradient bucket of the overlapped all-reduce; 0 = one bucket (the whole arena after a single
-    # backward call).  Measured on 2 B200s, C2a: per-block buckets cost more in launches (6 graph launches + 6 NCCL
-    # calls) than the 4 MB all-reduce they hide (1.08 vs 0.85 ms/step); worth it only for flows whose gradient
-    # arena is large against one block's backward.
+    # Blocks per gradient bucket.  In-graph path (NCCL): 0 = three buckets.  torch.distributed path: 0 = one
+    # all-reduce of the whole arena after the backward call; > 0 = one range call + one asynchronous all-reduce per
+    # bucket (measured on 2 B200s, C2a: per-block buckets cost more in launches -- 6 graph launches + 6 NCCL calls --
+    # than the 4 MB all-reduce they hide: 1.08 vs 0.85 ms/step; the in-graph path has no per-bucket host work).
     dp_bucket_blocks = 0
 
     def _backward_overlapped(self, stash, packed, y, B, dz, dld, dx, dy, dflat, ws, dev):

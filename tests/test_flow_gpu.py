@@ -418,7 +418,8 @@ def test_launch_graph_replay_is_bit_identical(precision):
 
 
 OPTION_SETTINGS = [("pdl", 0), ("streams", 0), ("tma_store", 0), ("fused_ln", 0), ("fused_ln", 1), ("fused_tail", 1),
-                   ("nacc", 1), ("bn256", 2), ("bn256", 1), ("ts", 0), ("presplit", 0)]
+                   ("nacc", 1), ("bn256", 2), ("bn256", 1), ("ts", 0), ("presplit", 0),
+                   ("stack", 0), ("stack", 1), ("stack_nsg", 1)]
 
 
 @pytest.mark.parametrize("name,value", OPTION_SETTINGS, ids=[f"{n}={v}" for n, v in OPTION_SETTINGS])
@@ -450,13 +451,17 @@ def test_options_are_equivalent(name, value):
         return outs
 
     default = _lib.get_option(name)
-    ref = run()
+    ref = run()                              # library defaults (forward / inverse: the persistent whole-stack kernel)
+    stack_default = _lib.get_option("stack")
+    if not name.startswith("stack"):
+        _lib.set_option("stack", 0)          # the per-layer kernels are what these options change
     _lib.set_option(name, value)
     try:
         assert _lib.get_option(name) == value
         got = run()
     finally:
         _lib.set_option(name, default)
+        _lib.set_option("stack", stack_default)
     tol = 1e-5 if name == "nacc" else 3e-6   # one accumulator instead of three: the truncation noise itself changes
     for a, b, nm in zip(ref, got, ("z", "ld", "dx", "dy", "dparams", "rev")):
         assert rel_err(b, a) <= tol, (name, value, nm, rel_err(b, a))

@@ -32,7 +32,7 @@ def run(M, N, K, engine=4, reps=3):
             v = (t[:, 9 + i] - t[:, 8 + i]).double()
             print(f'    MMA warp stage 8: {nm:36s} {v.mean():8.0f}  (min {v.min():6.0f} max {v.max():6.0f})')
     # plain epilogue: slots 5, 6 unused -> fold
-    print(f"M={M} N={N} K={K}: {e0.elapsed_time(e1)*1e3:.1f} us event, {len(t)} CTAs; mean cycles per phase:")
+    print(f"engine={engine} M={M} N={N} K={K}: {e0.elapsed_time(e1)*1e3:.1f} us event, {len(t)} CTAs; mean cycles per phase:")
     tot = (t[:, 7] - t[:, 0]).double()
     for i, n in enumerate(NAMES):
         v = d[:, i]
@@ -42,4 +42,10 @@ def run(M, N, K, engine=4, reps=3):
     print(f"    {'total in CTA':18s} {tot.mean():9.0f} cycles = {tot.mean()/1.965e3:.2f} us at 1965 MHz")
 
 if __name__ == "__main__":
-    run(8192, 1024, 1024)
+    if len(sys.argv) > 1:
+        for spec in sys.argv[1:]:
+            parts = [int(v) for v in spec.split("x")]
+            M, N, K = parts[:3]
+            run(M, N, K, engine=parts[3] if len(parts) > 3 else 4)
+    else:
+        run(8192, 1024, 1024)
