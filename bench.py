@@ -247,7 +247,8 @@ class Runner:
         model.load_state_dict({k: torch.tensor(v) for k, v in self.sd.items()})
         self.model = model.to(dev)
         if world > 1 and PLAN[name]["train"]:
-            self.model.enable_data_parallel()
+            ig = os.environ.get("NF_B200_DP_IN_GRAPH")          # experiment knob: 0 = torch.distributed after backward
+            self.model.enable_data_parallel(in_graph=None if ig is None else bool(int(ig)))
             if os.environ.get("NF_B200_DP_BUCKET_BLOCKS"):     # experiment knob: bucketed all-reduce
                 self.model.dp_bucket_blocks = int(os.environ["NF_B200_DP_BUCKET_BLOCKS"])
         xh, yh = synth.make_inputs(B, cfg["D"], cfg["R"], seed=1234 + rank)

@@ -508,7 +508,9 @@ class RealNVP(nn.Module):
                 dflat = out if out is not None else torch.empty(self._layout.total, dtype=torch.float32, device=dev)
             ptr = lambda t: t.data_ptr() if t is not None else None
             if need_p and self._dp_world > 1 and getattr(self, "_dp_in_graph", False):
-                bucket = int(self.dp_bucket_blocks) or max(1, -(-self.n_layers // 3))    # default: three buckets
+                bucket = int(self.dp_bucket_blocks)
+                if bucket <= 0:    # default: one bucket while the all-reduce is latency-bound, four for large arenas
+                    bucket = self.n_layers if self._layout.total * 4 < (32 << 20) else max(1, -(-self.n_layers // 4))
                 _lib.check(lib.nf_flow_backward_dp(
                     ctypes.byref(self._desc), self._flat.data_ptr(), packed.data_ptr(), stash.data_ptr(), y.data_ptr(),
                     B, ptr(dz), ptr(dld), ptr(dx), ptr(dy), dflat.data_ptr(), bucket, ws.data_ptr(), ws.numel(),
@@ -602,10 +604,12 @@ class RealNVP(nn.Module):
             dist.all_reduce(dflat, op=dist.ReduceOp.SUM, group=self._dp_group)
             dflat.mul_(1.0 / self._dp_world)
 
-    # Blocks per gradient bucket.  In-graph path (NCCL): 0 = three buckets.  torch.distributed path: 0 = one
-    # all-reduce of the whole arena after the backward call; > 0 = one range call + one asynchronous all-reduce per
-    # bucket (measured on 2 B200s, C2a: per-block buckets cost more in launches -- 6 graph launches + 6 NCCL calls --
-    # than the 4 MB all-reduce they hide: 1.08 vs 0.85 ms/step; the in-graph path has no per-bucket host work).
+    # Blocks per gradient bucket; 0 = one bucket = one all-reduce of the whole arena at the end of backward.
+    # Measured on 2 B200s (bench.py, C2a, 4096 rows per GPU, single-GPU step 0.72 ms): in-graph, one bucket 0.783 ms;
+    # in-graph, 2 / 3 buckets 0.81 / 0.85 ms; torch.distributed.all_reduce after the backward call 0.80 ms; per-block
+    # buckets through range calls 1.08 ms.  A 4 MB all-reduce is latency-bound (~0.06 ms), so the LAST bucket's
+    # all-reduce is exposed at full price however the arena is cut, and every earlier one competes with the backward
+    # kernels for SMs: overlap only pays for arenas large against the all-reduce latency (C5: 259 MB).
     dp_bucket_blocks = 0
 
     def _backward_overlapped(self, stash, packed, y, B, dz, dld, dx, dy, dflat, ws, dev):
