@@ -102,7 +102,11 @@ NF_API int64_t nf_flow_workspace_bytes(const NfFlowDesc* desc, int64_t B);
 NF_API int nf_flow_prepare(const NfFlowDesc* desc, const float* params, void* packed, int what,
                     void* workspace, int64_t ws_bytes, void* stream);
 
-/* z (B,D), logdet (B,), outputs (n_blocks,B,D) or NULL.  `stash` (nf_flow_stash_bytes) receives
+/* y == NULL in nf_flow_forward / nf_flow_inverse / nf_flow_backward means "the conditioning input is identically zero"
+ * (train_auto_NF_rl.py:328-339 evaluates the flow 1 M times with cond = 0): the y segment of the first Linear's
+ * reduction, the dy GEMM and the y columns of dW1 are skipped (dy, if given, is zero-filled).
+ *
+ * z (B,D), logdet (B,), outputs (n_blocks,B,D) or NULL.  `stash` (nf_flow_stash_bytes) receives
  * what nf_flow_backward needs; pass NULL for an inference-only forward. */
 NF_API int nf_flow_forward(const NfFlowDesc* desc, const float* params, const void* packed,
                     const float* x, const float* y, int64_t B,
@@ -127,6 +131,17 @@ NF_API int nf_flow_backward(const NfFlowDesc* desc, const float* params, const v
                      const float* dz, const float* dlogdet,
                      float* dx, float* dy, float* dparams,
                      void* workspace, int64_t ws_bytes, void* stream);
+
+/* Backward of the REVERSE direction x = nf_flow_inverse(z, y) (with its log-det), for callers that differentiate
+ * through sampling (flax nf.py:131-148 as used by offline-rl/agents/vinf.py:50,68).  `stash` is the one
+ * nf_flow_forward(x = the reverse output, y) leaves (the intermediate values of reverse(z) are those of forward(x)).
+ * dx (B,D) / dlogdet (B,) are the cotangents of the reverse output and of the reverse log-det (either may be NULL);
+ * outputs: dz (B,D) or NULL, dy (B,R) or NULL, dparams (flat arena, fully overwritten) or NULL. */
+NF_API int nf_flow_inverse_backward(const NfFlowDesc* desc, const float* params, const void* packed,
+                             const void* stash, const float* y, int64_t B,
+                             const float* dx, const float* dlogdet,
+                             float* dz, float* dy, float* dparams,
+                             void* workspace, int64_t ws_bytes, void* stream);
 
 /* The same backward, block range [block_begin, block_end) only (the full pass is the ranges from the top block
  * down, in order, with the same workspace and no other call in between): data-parallel training all-reduces the

@@ -60,6 +60,7 @@ def _load():
         "nf_flow_inverse": (c_int, [D, fp, vp, fp, fp, i64, fp, fp, fp, vp, i64, vp]),
         "nf_flow_backward": (c_int, [D, fp, vp, vp, fp, i64, fp, fp, fp, fp, fp, vp, i64, vp]),
         "nf_flow_backward_range": (c_int, [D, fp, vp, vp, fp, i64, fp, fp, fp, fp, fp, c_int32, c_int32, vp, i64, vp]),
+        "nf_flow_inverse_backward": (c_int, [D, fp, vp, vp, fp, i64, fp, fp, fp, fp, fp, vp, i64, vp]),
         "nf_flow_backward_dp": (c_int, [D, fp, vp, vp, fp, i64, fp, fp, fp, fp, fp, c_int32, vp, i64, vp]),
         "nf_dp_unique_id": (c_int, [vp]),
         "nf_dp_init": (c_int, [vp, c_int32, c_int32]),

@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(256) k_affine_bwd(const float* __restrict__ dz
                                                     const float* __restrict__ sfull, const float* __restrict__ dld,
                                                     long long B, int D, float* __restrict__ dxp,
                                                     float* __restrict__ ds, float* __restrict__ dtt,
-                                                    float* g3s, float* g3t) {
+                                                    float* g3s, float* g3t, int inverse) {
   NF_PDL_ENTRY();
   extern __shared__ float sh[];  // 2*dt partial column sums
   const int dc = (D + 1) / 2, dt = D / 2;
@@ -375,15 +375,25 @@ __global__ void __launch_bounds__(256) k_affine_bwd(const float* __restrict__ dz
     } else {
       const int jt = j - dc;
       const float sv = sfull[row * dt + jt];
-      const float e = expf(-sv);
-      const float ge = g * e;
-      dxp[idx] = ge;
-      const float dsv = -g * z[idx] - (dld ? dld[row] : 0.f);
+      float dsv, dtv;
+      if (inverse) {
+        // reverse direction (torch_fcnf.py:112-113): xp_t = z_t e^s + t, logdet += sum s.  `dz` is the cotangent of
+        // xp, `z` the block's z:  dz_t = g e^s, ds = g z_t e^s + dlogdet, dt = g
+        const float ge = g * expf(sv);
+        dxp[idx] = ge;
+        dsv = ge * z[idx] + (dld ? dld[row] : 0.f);
+        dtv = g;
+      } else {
+        const float ge = g * expf(-sv);
+        dxp[idx] = ge;
+        dsv = -g * z[idx] - (dld ? dld[row] : 0.f);
+        dtv = -ge;
+      }
       ds[row * dt + jt] = dsv;
-      dtt[row * dt + jt] = -ge;
+      dtt[row * dt + jt] = dtv;
       if (g3s) {
         atomicAdd(&sh[jt], dsv);
-        atomicAdd(&sh[dt + jt], -ge);
+        atomicAdd(&sh[dt + jt], dtv);
       }
     }
   }
@@ -546,14 +556,14 @@ __global__ void k_unfold(const float* params, NfParamLayout pl, Dims m, float* d
 
 // dL = tril(dLh,-1), dU = triu(dUh,1), ds = diag(dUh) + sum(dlogdet)/s
 __global__ void k_plu_grad_finish(const float* params, NfParamLayout pl, int D, const float* dLh, const float* dUh,
-                                  const float* sum_dld, float* dparams) {
+                                  const float* sum_dld, float* dparams, float ld_sign) {
   NF_PDL_ENTRY();
   const int b = blockIdx.y;
   const float* pb = params + (long long)b * pl.block_stride;
   float* db = dparams + (long long)b * pl.block_stride;
   const float* dl = dLh + (long long)b * D * D;
   const float* du = dUh + (long long)b * D * D;
-  const float sd = sum_dld ? *sum_dld : 0.f;
+  const float sd = sum_dld ? ld_sign * *sum_dld : 0.f;   // reverse direction: log-det = -sum log|s| per block
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < D * D; idx += gridDim.x * blockDim.x) {
     const int i = idx / D, j = idx % D;
     db[pl.slot_off[NF_P_L] + idx] = i > j ? dl[idx] : 0.f;
@@ -700,14 +710,14 @@ int affine_inv(const float* z, int ld_in, const float* s, const float* t, const 
 }
 
 int affine_bwd(const float* dz, const float* z, const float* s_full, const float* dlogdet, long long B, int D,
-               float* dxp, float* ds, float* dt, float* g3s, float* g3t, cudaStream_t st) {
+               float* dxp, float* ds, float* dt, float* g3s, float* g3t, cudaStream_t st, int inverse) {
   if (B <= 0) return 0;
   const long long total = B * D;
   long long blocks = cdiv(total, 256 * 4);
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
   ProfScope prof(st, PROF_AFFINE, 4.0 * B * (3.0 * D + 3.0 * (D / 2) + 1.0));
-  NF_LAUNCH((k_affine_bwd), (unsigned)blocks, 256, 2 * (D / 2) * sizeof(float) + 16, st, dz, z, s_full, dlogdet, B, D, dxp,                                                                               ds, dt, g3s, g3t);
+  NF_LAUNCH((k_affine_bwd), (unsigned)blocks, 256, 2 * (D / 2) * sizeof(float) + 16, st, dz, z, s_full, dlogdet, B, D, dxp, ds, dt, g3s, g3t, inverse);
   NF_LAUNCHED();
   return 0;
 }
@@ -757,9 +767,9 @@ int unfold_grads(const float* params, const NfParamLayout& pl, const Dims& m, fl
 }
 
 int plu_grad_finish(const float* params, const NfParamLayout& pl, const Dims& m, const float* dLh, const float* dUh,
-                    const float* sum_dld, float* dparams, cudaStream_t st) {
+                    const float* sum_dld, float* dparams, cudaStream_t st, float ld_sign) {
   dim3 grid((unsigned)std::min<int64_t>(cdiv((int64_t)m.D * m.D, 256), 64), (unsigned)m.n);
-  NF_LAUNCH((k_plu_grad_finish), grid, 256, 0, st, params, pl, m.D, dLh, dUh, sum_dld, dparams);
+  NF_LAUNCH((k_plu_grad_finish), grid, 256, 0, st, params, pl, m.D, dLh, dUh, sum_dld, dparams, ld_sign);
   NF_LAUNCHED();
   return 0;
 }

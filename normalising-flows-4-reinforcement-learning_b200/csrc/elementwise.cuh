@@ -40,7 +40,7 @@ int affine_inv(const float* z, int ld_in, const float* s, const float* t, const 
                float* xp, int ld_out, float* logdet, cudaStream_t st);
 // ds/dt are (B,dt) each; g3s/g3t (dt) receive column sums of ds/dt (atomic), may be null.
 int affine_bwd(const float* dz, const float* z, const float* s_full, const float* dlogdet, long long B, int D,
-               float* dxp, float* ds, float* dt, float* g3s, float* g3t, cudaStream_t st);
+               float* dxp, float* ds, float* dt, float* g3s, float* g3t, cudaStream_t st, int inverse = 0);
 
 // ---- parameter-sized kernels ---------------------------------------------------------------
 int plu_mask(const float* params, const NfParamLayout& pl, const Dims& m, float* packed,
@@ -53,7 +53,7 @@ int pack_w1(const float* params, const NfParamLayout& pl, const Dims& m, float* 
             cudaStream_t st);
 int unfold_grads(const float* params, const NfParamLayout& pl, const Dims& m, float* dparams, cudaStream_t st);
 int plu_grad_finish(const float* params, const NfParamLayout& pl, const Dims& m, const float* dLh,
-                    const float* dUh, const float* sum_dld, float* dparams, cudaStream_t st);
+                    const float* dUh, const float* sum_dld, float* dparams, cudaStream_t st, float ld_sign = 1.0f);
 int sum_vector(const float* v, long long n, float* out, cudaStream_t st);  // out[0] = sum(v)
 int fill_zero(float* p, long long n, cudaStream_t st);
 // hi[i] = rna_tf32(t[i]), lo[i] = t[i] - hi[i] for the first n floats of the packed tables (hi = t + hi_off, ...)

@@ -362,11 +362,14 @@ static int conditioners(const Dims& m, const NfParamLayout& pl, const PackedLayo
   {  // layer 1: [x_cond | y] W1^T + b1
     TcGemmP g;
     g.A0 = xc; g.lda0 = ldxc; g.K0 = m.dc;
-    if (m.R > 0) { g.A1 = y; g.lda1 = m.R; g.K1 = m.R; }
+    // y == NULL: the conditioning input is identically zero (train_auto_NF_rl.py:328-339 evaluates the flow 1 M times
+    // with cond = 0): the first Linear reduces to x_cond W1[:, :dc]^T + b1, the y segment of the reduction is skipped
+    const bool has_y = m.R > 0 && y != nullptr;
+    if (has_y) { g.A1 = y; g.lda1 = m.R; g.K1 = m.R; }
     // W1p: W1 with the y columns moved to the 16-byte aligned column dcp (TMA operand)
     g.B0 = kb + kl.net0 + kl.W1p; g.ldb0 = kl.K1p; g.sB0 = kl.net_stride;
-    if (m.R > 0) { g.B1 = g.B0 + kl.dcp; g.ldb1 = kl.K1p; g.sB1 = kl.net_stride; }
-    if (kl.hi_off) { g.B0hi = g.B0 + kl.hi_off; g.B0lo = g.B0 + kl.lo_off; if (m.R > 0) { g.B1hi = g.B1 + kl.hi_off; g.B1lo = g.B1 + kl.lo_off; } }
+    if (has_y) { g.B1 = g.B0 + kl.dcp; g.ldb1 = kl.K1p; g.sB1 = kl.net_stride; }
+    if (kl.hi_off) { g.B0hi = g.B0 + kl.hi_off; g.B0lo = g.B0 + kl.lo_off; if (has_y) { g.B1hi = g.B1 + kl.hi_off; g.B1lo = g.B1 + kl.lo_off; } }
     NF_TRY(linear_lrelu_ln(g, m.H1, pb + pl.slot_off[NF_P_B1], pl.net_stride, xh1, xh1_net, r1, m1, mw1, nullptr));
   }
   {  // layer 2: x_hat1 W2f^T + b2f
@@ -558,7 +561,7 @@ int nf_flow_forward(const NfFlowDesc* desc, const float* params, const void* pac
   NF_TRY(check_ptr(packed_v, "packed", true));
   if (B == 0) return 0;
   NF_TRY(check_ptr(x, "x", true));
-  NF_TRY(check_ptr(y, "y", desc->R > 0));
+  NF_TRY(check_ptr(y, "y", false));     // NULL: y == 0 (fast path, see conditioners())
   NF_TRY(check_ptr(z, "z", true));
   NF_TRY(check_ptr(logdet, "logdet", true));
   NF_TRY(check_ptr(outputs, "outputs", false));
@@ -580,7 +583,7 @@ int nf_flow_forward(const NfFlowDesc* desc, const float* params, const void* pac
   GraphKey key;
   key.op = 2; key.desc = *desc; key.B = B; key.ws_bytes = ws_bytes;
   key.ptr[0] = params; key.ptr[1] = packed_v; key.ptr[7] = stash_v; key.ptr[8] = workspace;
-  key.flags = (outputs ? 1 : 0) | (stash ? 2 : 0);
+  key.flags = (outputs ? 1 : 0) | (stash ? 2 : 0) | (y ? 4 : 0);
   // inputs -> persistent staging (the stash keeps x and y for backward anyway)
   float* x_in = stash ? stash + sl.xs : w.io_x;
   float* y_in = stash ? stash + sl.y : w.io_y;
@@ -593,7 +596,7 @@ int nf_flow_forward(const NfFlowDesc* desc, const float* params, const void* pac
     c.add(y_in, y, B * m.R);
     NF_TRY(copy_segments(c, user_st));
   }
-  y = y_in;
+  if (y) y = y_in;
   logdet = w.io_ld;
   z = w.io_z;
   if (outputs && !stash) outputs = w.io_outs;
@@ -705,7 +708,7 @@ int nf_flow_inverse(const NfFlowDesc* desc, const float* params, const void* pac
   NF_TRY(check_ptr(packed_v, "packed", true));
   if (B == 0) return 0;
   NF_TRY(check_ptr(z, "z", true));
-  NF_TRY(check_ptr(y, "y", desc->R > 0));
+  NF_TRY(check_ptr(y, "y", false));     // NULL: y == 0
   NF_TRY(check_ptr(x, "x", true));
   NF_TRY(check_ptr(logdet, "logdet", false));
   NF_TRY(check_ptr(seq, "seq", false));
@@ -724,7 +727,7 @@ int nf_flow_inverse(const NfFlowDesc* desc, const float* params, const void* pac
   GraphKey key;
   key.op = 3; key.desc = *desc; key.B = B; key.ws_bytes = ws_bytes;
   key.ptr[0] = params; key.ptr[1] = packed_v; key.ptr[6] = seq; key.ptr[7] = workspace;
-  key.flags = logdet ? 1 : 0;
+  key.flags = (logdet ? 1 : 0) | (y ? 2 : 0);
   float* const x_user = x;
   float* const logdet_user = logdet;
   {
@@ -733,7 +736,7 @@ int nf_flow_inverse(const NfFlowDesc* desc, const float* params, const void* pac
     c.add(w.io_y, y, B * m.R);
     NF_TRY(copy_segments(c, user_st));
   }
-  z = w.io_x; y = w.io_y; x = w.io_z;
+  z = w.io_x; if (y) y = w.io_y; x = w.io_z;
   if (logdet) logdet = w.io_ld;
   auto body = [&](cudaStream_t st) -> int {
   if (logdet) NF_CUDA(cudaMemsetAsync(logdet, 0, B * sizeof(float), st));
@@ -836,7 +839,7 @@ static int backward_impl(const NfFlowDesc* desc, const float* params, const void
     return 0;
   }
   NF_TRY(check_ptr(stash_v, "stash", true));
-  NF_TRY(check_ptr(y, "y", desc->R > 0));
+  NF_TRY(check_ptr(y, "y", false));       // NULL: the forward ran with y == 0 (no dy, no y columns in dW1)
   NF_TRY(check_ptr(dz, "dz", false));
   NF_TRY(check_ptr(dlogdet, "dlogdet", false));
   NF_TRY(check_ptr(dx, "dx", false));
@@ -854,7 +857,12 @@ static int backward_impl(const NfFlowDesc* desc, const float* params, const void
   GraphKey key;
   key.op = 4; key.desc = *desc; key.B = B; key.ws_bytes = ws_bytes;
   key.ptr[0] = params; key.ptr[1] = packed_v; key.ptr[2] = stash_v; key.ptr[8] = dparams; key.ptr[9] = workspace;
-  key.flags = (dz ? 1 : 0) | (dlogdet ? 2 : 0) | (dx ? 4 : 0) | (dy ? 8 : 0) | (block_begin << 8) | (block_end << 20);
+  const bool has_y = y != nullptr && m.R > 0;
+  if (!has_y && dy) {   // y == 0 was not an input: its gradient is reported as zero
+    NF_TRY(fill_zero(dy, B * m.R, user_st));
+    dy = nullptr;
+  }
+  key.flags = (dz ? 1 : 0) | (dlogdet ? 2 : 0) | (dx ? 4 : 0) | (dy ? 8 : 0) | (has_y ? 16 : 0) | (block_begin << 8) | (block_end << 20);
   key.ptr[10] = reinterpret_cast<const void*>((uintptr_t)(dp_bucket > 0 ? dp_bucket : 0));
   // cotangents in, dx / dy out through the workspace; y is the copy forward left in the stash
   float* const dx_user = dx;
@@ -1038,7 +1046,7 @@ static int backward_impl(const NfFlowDesc* desc, const float* params, const void
       g.C = dn + pl.slot_off[NF_P_W1]; g.ldc = m.K1; g.sC = pl.net_stride;
       g.M = m.H1; g.N = m.dc; g.K = B; g.batch = 2;
       if (!fused) NF_TRY(wgrad_tn(m.prec, g, st));
-      if (m.R > 0) {
+      if (has_y) {
         g.B = y; g.ldb = m.R;
         g.C = dn + pl.slot_off[NF_P_W1] + m.dc; g.N = m.R;
         if (!(whatif & 2)) NF_TRY(wgrad_tn(m.prec, g, s2));
@@ -1052,7 +1060,7 @@ static int backward_impl(const NfFlowDesc* desc, const float* params, const void
       g.B1 = g.B0 + kl.net_stride; g.ldb1 = m.H1;
       g.C = wb.dxp; g.ldc = m.D; g.M = (int)B; g.N = m.dc; g.accumulate = 1;
       if (!fused) NF_TRY(linear_nt(m.prec, g, st));
-      if (dy && m.R > 0) {
+      if (dy && has_y) {
         g.B0 += (int64_t)m.dc * m.H1; g.B1 += (int64_t)m.dc * m.H1;
         if (kl.hi_off) { g.B0hi = g.B0 + kl.hi_off; g.B0lo = g.B0 + kl.lo_off; g.B1hi = g.B1 + kl.hi_off; g.B1lo = g.B1 + kl.lo_off; }
         g.C = dy; g.ldc = m.R; g.N = m.R;
@@ -1217,6 +1225,219 @@ int nf_flow_backward_dp(const NfFlowDesc* desc, const float* params, const void*
   NF_CHECK_ARG(bucket_blocks >= 1, NF_E_BADARG, "bucket_blocks must be >= 1");
   return backward_impl(desc, params, packed_v, stash_v, y, B, dz, dlogdet, dx, dy, dparams, 0, desc->n_blocks,
                        bucket_blocks, workspace, ws_bytes, stream);
+}
+
+// Backward of the REVERSE direction (x = reverse(z, y), optionally with its log-det; flax nf.py:131-148, used
+// differentiably by offline-rl/agents/vinf.py:50,68).  The intermediate values of reverse(z) are those of forward(x)
+// (block i's forward input is its reverse output), so the stash is the one nf_flow_forward(x = reverse output) leaves.
+// Per block, in forward block order i = 0 .. n-1 (the reverse pass ran n-1 .. 0), with g the cotangent of the block's
+// reverse output x_i:
+//   g_xp = g W_i^-T ;  dW_i = -x_i^T g_xp          (x_i = xp W^-1  =>  dW^-1 = xp^T g,  dW = -W^-T dW^-1 W^-T)
+//   dz_t = g_xp_t e^s ;  ds = g_xp_t z_t e^s + dlogdet ;  dt = g_xp_t ;  dz_c = g_xp_c + (conditioner input gradient)
+// and the conditioner backward (last Linear, LayerNorm / LeakyReLU, the two wide Linears, dy) is the forward
+// direction's.  This is the general path (plain GEMM + row kernels), not a tuned one.
+int nf_flow_inverse_backward(const NfFlowDesc* desc, const float* params, const void* packed_v, const void* stash_v,
+                             const float* y, int64_t B, const float* dx, const float* dlogdet, float* dz, float* dy,
+                             float* dparams, void* workspace, int64_t ws_bytes, void* stream) {
+  NF_TRY(check_desc(desc));
+  NF_CHECK_ARG(B >= 0 && B < (int64_t(1) << 30), NF_E_BADARG, "B=%lld out of range", (long long)B);
+  NF_TRY(check_ptr(params, "params", true));
+  NF_TRY(check_ptr(packed_v, "packed", true));
+  NF_TRY(check_ptr(dparams, "dparams", false));
+  const Dims m = dims_of(desc);
+  NfParamLayout pl;
+  param_layout(m, &pl);
+  cudaStream_t user_st = reinterpret_cast<cudaStream_t>(stream);
+  if (B == 0) {
+    if (dparams) NF_TRY(fill_zero(dparams, pl.total, user_st));
+    return 0;
+  }
+  NF_TRY(check_ptr(stash_v, "stash", true));
+  NF_TRY(check_ptr(y, "y", false));
+  NF_TRY(check_ptr(dx, "dx", false)); NF_TRY(check_ptr(dlogdet, "dlogdet", false));
+  NF_TRY(check_ptr(dz, "dz", false)); NF_TRY(check_ptr(dy, "dy", false));
+  NF_TRY(check_ptr(workspace, "workspace", true));
+  const PackedLayout kl = packed_layout(m);
+  const StashLayout sl = stash_layout(m, B);
+  const BwdWs w = carve_bwd(m, B, workspace);
+  NF_CHECK_ARG(ws_bytes >= w.total * (int64_t)sizeof(float), NF_E_WORKSPACE, "workspace too small: %lld < %lld",
+               (long long)ws_bytes, (long long)(w.total * sizeof(float)));
+  const float* packed = reinterpret_cast<const float*>(packed_v);
+  const float* stash = reinterpret_cast<const float*>(stash_v);
+  const int64_t BD = B * m.D, Hm = std::max(m.H1, m.C), DD = (int64_t)m.D * m.D;
+  const bool has_y = y != nullptr && m.R > 0;
+
+  GraphKey key;
+  key.op = 6; key.desc = *desc; key.B = B; key.ws_bytes = ws_bytes;
+  key.ptr[0] = params; key.ptr[1] = packed_v; key.ptr[2] = stash_v; key.ptr[8] = dparams; key.ptr[9] = workspace;
+  key.flags = (dx ? 1 : 0) | (dlogdet ? 2 : 0) | (dz ? 4 : 0) | (dy ? 8 : 0) | (has_y ? 16 : 0);
+  float* const dz_user = dz;
+  float* const dy_user = dy;
+  {
+    CopySegs c;
+    c.add(w.io_dz, dx, BD);
+    c.add(w.io_dld, dlogdet, B);
+    NF_TRY(copy_segments(c, user_st));
+  }
+  if (dx) dx = w.io_dz;
+  if (dlogdet) dlogdet = w.io_dld;
+  if (dz) dz = w.io_dx;
+  if (dy) dy = w.io_dy;
+  y = has_y ? stash + sl.y : nullptr;
+  auto body = [&](cudaStream_t st) -> int {
+  if (dparams) {
+    NF_TRY(fill_zero(dparams, pl.total, st));
+    NF_TRY(fill_zero(w.dWs, m.n * DD, st));
+    if (dlogdet) NF_TRY(sum_vector(dlogdet, B, w.sumdld, st));
+    else NF_TRY(fill_zero(w.sumdld, 4, st));
+  }
+  if (dy) NF_TRY(fill_zero(dy, B * m.R, st));
+  if (!dx) NF_TRY(fill_zero(w.io_dz, BD, st));
+  const float* gcur = dx ? dx : w.io_dz;
+  struct { float *dxp, *dout, *gA, *gB; } w2[2] = {{w.dxp, w.dout, w.gA, w.gB}, {w.dxp2, w.dout2, w.gA2, w.gB2}};
+  for (int i = 0; i < m.n; ++i) {
+    const auto& wb = w2[i & 1];
+    const float* kb = packed + (int64_t)i * kl.block_stride;
+    float* dn = dparams ? dparams + (int64_t)i * pl.block_stride : nullptr;
+    const float* xin = stash + sl.xs + (int64_t)i * BD;          // reverse output of block i
+    const float* zi = stash + sl.xs + (int64_t)(i + 1) * BD;     // reverse input of block i
+    const float* si = stash + sl.ss + (int64_t)i * B * m.dt;
+    const float* sb = stash + sl.blocks + (int64_t)i * sl.block_stride;
+    const uint32_t* m1 = reinterpret_cast<const uint32_t*>(sb + sl.m1);
+    const uint32_t* m2 = reinterpret_cast<const uint32_t*>(sb + sl.m2);
+    {  // g_xp = g W^-T  -> d0 (scratch)
+      GemmP g;
+      g.A0 = gcur; g.lda0 = m.D; g.K0 = m.D;
+      g.B0 = kb + kl.Winv; g.ldb0 = m.D; g.transB = 1;
+      g.C = w.d0; g.ldc = m.D; g.M = (int)B; g.N = m.D;
+      NF_TRY(simt_gemm(g, st));
+    }
+    if (dn) {  // dW = -x_in^T g_xp
+      GemmP g;
+      g.transA = 1; g.A0 = xin; g.lda0 = m.D; g.K0 = (int)B;
+      g.B0 = w.d0; g.ldb0 = m.D;
+      g.C = w.dWs + (int64_t)i * DD; g.ldc = m.D; g.M = m.D; g.N = m.D;
+      g.splitk = pick_splitk(g.M, g.N, B, 1);
+      g.alpha = -1.0f;
+      NF_TRY(simt_gemm(g, st));
+    }
+    // affine coupling, reverse direction: dxp := [g_xp_c, g_xp_t e^s] (= dz of this block before the conditioner term)
+    NF_TRY(affine_bwd(w.d0, zi, si, dlogdet, B, m.D, wb.dxp, wb.dout + B * m.dt, wb.dout,
+                      dn ? dn + pl.net_stride + pl.slot_off[NF_P_B3] : nullptr,
+                      dn ? dn + pl.slot_off[NF_P_B3] : nullptr, st, 1));
+    if (dn) {  // G3 = dout^T x_hat2
+      TcGemmTnP g;
+      g.A = wb.dout; g.lda = m.dt; g.sA = B * m.dt;
+      g.B = sb + sl.xh2; g.ldb = m.C; g.sB = sl.net_stride;
+      g.C = dn + pl.slot_off[NF_P_W3]; g.ldc = m.C; g.sC = pl.net_stride;
+      g.M = m.dt; g.N = m.C; g.K = B; g.batch = 2;
+      NF_TRY(wgrad_tn(m.prec, g, st));
+    }
+    {  // d x_hat2 = dout W3f
+      GemmP g;
+      g.A0 = wb.dout; g.lda0 = m.dt; g.sA0 = B * m.dt; g.K0 = m.dt;
+      g.B0 = kb + kl.net0 + kl.W3f; g.ldb0 = m.C; g.sB0 = kl.net_stride;
+      g.C = wb.gA; g.ldc = m.C; g.sC = B * Hm;
+      g.M = (int)B; g.N = m.C; g.batch = 2;
+      NF_TRY(simt_gemm(g, st));
+    }
+    {  // through LayerNorm + LeakyReLU (layer 2); column sums -> slot b2
+      LnBwdP p{};
+      p.g = wb.gA; p.g_net = B * Hm;
+      p.xh = sb + sl.xh2; p.xh_net = sl.net_stride;
+      p.rstd = sb + sl.r2; p.rstd_net = sl.net_stride;
+      p.mask = m2; p.mask_net = sl.net_stride; p.mw = sl.mw2;
+      p.colsum = dn ? dn + pl.slot_off[NF_P_B2] : nullptr; p.colsum_net = pl.net_stride;
+      p.N = m.C; p.nets = 2; p.B = B;
+      NF_TRY(ln_lrelu_bwd(p, st));
+    }
+    if (dn) {  // G2 = du2^T x_hat1
+      TcGemmTnP g;
+      g.A = wb.gA; g.lda = m.C; g.sA = B * Hm;
+      g.B = sb + sl.xh1; g.ldb = m.H1; g.sB = sl.net_stride;
+      g.C = dn + pl.slot_off[NF_P_W2]; g.ldc = m.H1; g.sC = pl.net_stride;
+      g.M = m.C; g.N = m.H1; g.K = B; g.batch = 2;
+      NF_TRY(wgrad_tn(m.prec, g, st));
+    }
+    {  // d x_hat1 = du2 W2f
+      TcGemmP g;
+      g.A0 = wb.gA; g.lda0 = m.C; g.sA0 = B * Hm; g.K0 = m.C;
+      g.B0 = kb + kl.net0 + kl.W2fT; g.ldb0 = m.C; g.sB0 = kl.net_stride;
+      g.C = wb.gB; g.ldc = m.H1; g.sC = B * Hm;
+      g.M = (int)B; g.N = m.H1; g.batch = 2;
+      if (kl.hi_off) { g.B0hi = g.B0 + kl.hi_off; g.B0lo = g.B0 + kl.lo_off; }
+      NF_TRY(linear_nt(m.prec, g, st));
+    }
+    {  // through LayerNorm + LeakyReLU (layer 1); column sums -> slot b1
+      LnBwdP p{};
+      p.g = wb.gB; p.g_net = B * Hm;
+      p.xh = sb + sl.xh1; p.xh_net = sl.net_stride;
+      p.rstd = sb + sl.r1; p.rstd_net = sl.net_stride;
+      p.mask = m1; p.mask_net = sl.net_stride; p.mw = sl.mw1;
+      p.colsum = dn ? dn + pl.slot_off[NF_P_B1] : nullptr; p.colsum_net = pl.net_stride;
+      p.N = m.H1; p.nets = 2; p.B = B;
+      NF_TRY(ln_lrelu_bwd(p, st));
+    }
+    if (dn) {  // dW1 = du1^T [z_c | y]
+      TcGemmTnP g;
+      g.A = wb.gB; g.lda = m.H1; g.sA = B * Hm;
+      g.B = zi; g.ldb = m.D; g.sB = 0;
+      g.C = dn + pl.slot_off[NF_P_W1]; g.ldc = m.K1; g.sC = pl.net_stride;
+      g.M = m.H1; g.N = m.dc; g.K = B; g.batch = 2;
+      NF_TRY(wgrad_tn(m.prec, g, st));
+      if (has_y) {
+        g.B = y; g.ldb = m.R;
+        g.C = dn + pl.slot_off[NF_P_W1] + m.dc; g.N = m.R;
+        NF_TRY(wgrad_tn(m.prec, g, st));
+      }
+    }
+    {  // d h0 = du1_t W1_t + du1_s W1_s : first dc columns -> dz_c, the rest -> dy
+      TcGemmP g;
+      g.A0 = wb.gB; g.lda0 = m.H1; g.K0 = m.H1;
+      g.A1 = wb.gB + B * Hm; g.lda1 = m.H1; g.K1 = m.H1;
+      g.B0 = kb + kl.net0 + kl.W1T; g.ldb0 = m.H1;
+      g.B1 = g.B0 + kl.net_stride; g.ldb1 = m.H1;
+      g.C = wb.dxp; g.ldc = m.D; g.M = (int)B; g.N = m.dc; g.accumulate = 1;
+      NF_TRY(linear_nt(m.prec, g, st));
+      if (dy && has_y) {
+        g.B0 += (int64_t)m.dc * m.H1; g.B1 += (int64_t)m.dc * m.H1;
+        if (kl.hi_off) { g.B0hi = g.B0 + kl.hi_off; g.B0lo = g.B0 + kl.lo_off; g.B1hi = g.B1 + kl.hi_off; g.B1lo = g.B1 + kl.lo_off; }
+        g.C = dy; g.ldc = m.R; g.N = m.R;
+        NF_TRY(linear_nt(m.prec, g, st));
+      }
+    }
+    gcur = wb.dxp;
+  }
+  if (dz) NF_CUDA(cudaMemcpyAsync(dz, gcur, BD * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (dparams) {
+    GemmP g;  // T1 = P^T dW
+    g.transA = 1; g.A0 = params + pl.slot_off[NF_P_P]; g.lda0 = m.D; g.sA0 = pl.block_stride; g.K0 = m.D;
+    g.B0 = w.dWs; g.ldb0 = m.D; g.sB0 = DD;
+    g.C = w.T1; g.ldc = m.D; g.sC = DD; g.M = m.D; g.N = m.D; g.batch = m.n;
+    NF_TRY(simt_gemm(g, st));
+    GemmP h;  // dLh = T1 Uh^T
+    h.A0 = w.T1; h.lda0 = m.D; h.sA0 = DD; h.K0 = m.D;
+    h.B0 = packed + kl.Uh; h.ldb0 = m.D; h.sB0 = kl.block_stride; h.transB = 1;
+    h.C = w.dLh; h.ldc = m.D; h.sC = DD; h.M = m.D; h.N = m.D; h.batch = m.n;
+    NF_TRY(simt_gemm(h, st));
+    GemmP u;  // dUh = (P Lh)^T dW
+    u.transA = 1; u.A0 = packed + kl.PL; u.lda0 = m.D; u.sA0 = kl.block_stride; u.K0 = m.D;
+    u.B0 = w.dWs; u.ldb0 = m.D; u.sB0 = DD;
+    u.C = w.dUh; u.ldc = m.D; u.sC = DD; u.M = m.D; u.N = m.D; u.batch = m.n;
+    NF_TRY(simt_gemm(u, st));
+    NF_TRY(plu_grad_finish(params, pl, m, w.dLh, w.dUh, w.sumdld, dparams, st, -1.0f));
+    NF_TRY(unfold_grads(params, pl, m, dparams, st));
+  }
+  return 0;
+  };
+  NF_TRY(run_graphed(key, user_st, body));
+  {
+    CopySegs c;
+    c.add(dz_user, dz, BD);
+    c.add(dy_user, dy, B * m.R);
+    NF_TRY(copy_segments(c, user_st));
+  }
+  return 0;
 }
 
 int nf_linear(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, float* C, int64_t ldc,

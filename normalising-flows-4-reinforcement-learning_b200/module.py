@@ -198,7 +198,8 @@ class _Flow(torch.autograd.Function):
         ctx.packed = packed
         ctx.pver = model._pver_seen      # computed by _prepared inside _run_forward
         ctx.B = x.shape[0]
-        ctx.save_for_backward(y)
+        ctx.has_y = y is not None
+        ctx.save_for_backward(*([y] if y is not None else []))
         ctx.mark_non_differentiable(outs)
         return z, logdet, outs
 
@@ -209,7 +210,7 @@ class _Flow(torch.autograd.Function):
             raise RuntimeError("nf_b200: backward called twice on the same forward (the stash is freed after use)")
         if ctx.pver != model._params_version():
             raise RuntimeError("nf_b200: parameters were modified between forward and backward")
-        (y,) = ctx.saved_tensors
+        y = ctx.saved_tensors[0] if ctx.has_y else None
         need_x = ctx.needs_input_grad[3]
         need_y = ctx.needs_input_grad[4]
         need_p = _param_grads_wanted(ctx.needs_input_grad[5:], ctx.nodes)
@@ -230,6 +231,53 @@ class _Flow(torch.autograd.Function):
         return (None, None, None, dx, dy) + pg
 
 
+class _FlowReverse(torch.autograd.Function):
+    """autograd bridge of the sampling direction: forward = nf_flow_inverse; backward = nf_flow_forward on the result
+    (for the stash) followed by nf_flow_inverse_backward."""
+
+    @staticmethod
+    def forward(ctx, model: "RealNVP", fast: bool, nodes, want_logdet: bool, z, y, *params):
+        out, logdet, _ = model._run_inverse(z, y, want_logdet)
+        ctx.model, ctx.fast, ctx.nodes = model, fast, nodes
+        ctx.pver = model._pver_seen
+        ctx.has_y = y is not None
+        ctx.save_for_backward(out, *([y] if y is not None else []))
+        if logdet is None:
+            logdet = out.new_zeros(())
+            ctx.mark_non_differentiable(logdet)
+        return out, logdet
+
+    @staticmethod
+    def backward(ctx, dx, dld):
+        model = ctx.model
+        if ctx.pver != model._params_version():
+            raise RuntimeError("nf_b200: parameters were modified between reverse() and its backward")
+        saved = ctx.saved_tensors
+        out, y = saved[0], (saved[1] if ctx.has_y else None)
+        B = out.shape[0]
+        if dld is not None and dld.dim() == 0:
+            dld = None
+        need_z, need_y = ctx.needs_input_grad[4], ctx.needs_input_grad[5]
+        need_p = _param_grads_wanted(ctx.needs_input_grad[6:], ctx.nodes)
+        nparams = len(ctx.needs_input_grad) - 6
+        _, _, _, stash, packed, slot = model._run_forward(out, y, True, want_outputs=False)
+        try:
+            if ctx.fast:
+                dz, dy = model._run_backward_fast(stash, packed, y, B, dx, dld, need_z, need_y, need_p, inverse=True)
+                pg = (None,) * nparams
+            else:
+                dz, dy, dflat = model._run_backward(stash, packed, y, B, dx, dld, need_z, need_y, need_p, inverse=True)
+                if need_p:
+                    views = model._grad_views(dflat)
+                    pg = tuple(v if need else None for v, need in zip(views, ctx.needs_input_grad[6:]))
+                else:
+                    pg = (None,) * nparams
+        finally:
+            if slot is not None:
+                slot.busy = False
+        return (None, None, None, None, dz, dy) + pg
+
+
 class _FlowNLL(torch.autograd.Function):
     """loss = -mean(log N(z; 0, I) + log_dets) with the loss and its cotangents computed by the library
     (nf_nll_forward / nf_nll_cotangents) instead of ~8 elementwise torch kernels either side of the flow."""
@@ -245,7 +293,8 @@ class _FlowNLL(torch.autograd.Function):
         ctx.guard = _SlotGuard(slot) if slot is not None else None
         ctx.pver = model._pver_seen      # computed by _prepared inside _run_forward
         ctx.B = x.shape[0]
-        ctx.save_for_backward(y, z)
+        ctx.has_y = y is not None
+        ctx.save_for_backward(z, *([y] if y is not None else []))
         return loss
 
     @staticmethod
@@ -255,7 +304,8 @@ class _FlowNLL(torch.autograd.Function):
             raise RuntimeError("nf_b200: backward called twice on the same forward (the stash is freed after use)")
         if ctx.pver != model._params_version():
             raise RuntimeError("nf_b200: parameters were modified between forward and backward")
-        y, z = ctx.saved_tensors
+        z = ctx.saved_tensors[0]
+        y = ctx.saved_tensors[1] if ctx.has_y else None
         B, D = ctx.B, model.in_channels
         dz = torch.empty_like(z)
         dld = torch.empty((B,), dtype=torch.float32, device=z.device)
@@ -404,14 +454,17 @@ class RealNVP(nn.Module):
 
     # ------------------------------------------------------------------ plumbing
     def _check_inputs(self, x, y):
-        if not (x.is_cuda and y.is_cuda):
+        """``y=None`` means "the conditioning input is identically zero" (the fast path of
+        unsupservised-gcrl/train_auto_NF_rl.py:328-339, which evaluates the flow with ``y = zeros`` a million times
+        per actor step): the y part of the first Linear is skipped instead of multiplying zeros."""
+        if not (x.is_cuda and (y is None or y.is_cuda)):
             raise RuntimeError("nf_b200.RealNVP runs on CUDA only (sm_100a kernels, no CPU fallback); "
                                "move the module and its inputs to a B200")
         if x.dim() != 2 or x.shape[1] != self.in_channels:
             raise ValueError(f"x must be (B, {self.in_channels}), got {tuple(x.shape)}")
-        if y.dim() != 2 or y.shape[1] != self.cond_channels or y.shape[0] != x.shape[0]:
+        if y is not None and (y.dim() != 2 or y.shape[1] != self.cond_channels or y.shape[0] != x.shape[0]):
             raise ValueError(f"y must be ({x.shape[0]}, {self.cond_channels}), got {tuple(y.shape)}")
-        if x.dtype != torch.float32 or y.dtype != torch.float32:
+        if x.dtype != torch.float32 or (y is not None and y.dtype != torch.float32):
             raise TypeError("nf_b200 computes in float32: x and y must be float32")
         if not self._is_flat():
             self._flatten()
@@ -456,6 +509,7 @@ class RealNVP(nn.Module):
         B, D, n = x.shape[0], self.in_channels, self.n_layers
         x = _dense(x)
         y = _dense(y)
+        yp = y.data_ptr() if y is not None else None
         with _on(dev):
             packed = self._prepared(_lib.NF_PREP_FWD, dev)
             ws = self._workspace(B, dev)
@@ -472,7 +526,7 @@ class RealNVP(nn.Module):
                 outs = torch.empty((n, B, D), dtype=torch.float32, device=dev)
                 outs_ptr = outs.data_ptr()
             _lib.check(lib.nf_flow_forward(
-                ctypes.byref(self._desc), self._flat.data_ptr(), packed.data_ptr(), x.data_ptr(), y.data_ptr(), B,
+                ctypes.byref(self._desc), self._flat.data_ptr(), packed.data_ptr(), x.data_ptr(), yp, B,
                 z.data_ptr(), logdet.data_ptr(), outs_ptr, stash.data_ptr() if stash is not None else None,
                 ws.data_ptr(), ws.numel(), self._stream(dev)), "nf_flow_forward")
         return z, logdet, outs, stash, packed, slot
@@ -495,9 +549,12 @@ class RealNVP(nn.Module):
             return t, slot
         return t, None
 
-    def _run_backward(self, stash, packed, y, B, dz, dld, need_x, need_y, need_p, out=None):
-        dev = y.device
+    def _run_backward(self, stash, packed, y, B, dz, dld, need_x, need_y, need_p, out=None, inverse=False):
+        """``inverse=True``: backward of the reverse direction (nf_flow_inverse_backward); dz / dld are then the
+        cotangents of the reverse output and reverse log-det, and the returned dx is the gradient w.r.t. its input."""
+        dev = stash.device
         D, R = self.in_channels, self.cond_channels
+        need_y = need_y and y is not None
         with _on(dev):
             ws = self._workspace(B, dev)
             dz, dld, y = _dense(dz), _dense(dld), _dense(y)
@@ -507,31 +564,41 @@ class RealNVP(nn.Module):
             if need_p:
                 dflat = out if out is not None else torch.empty(self._layout.total, dtype=torch.float32, device=dev)
             ptr = lambda t: t.data_ptr() if t is not None else None
-            if need_p and self._dp_world > 1 and getattr(self, "_dp_in_graph", False):
+            if inverse:
+                _lib.check(lib.nf_flow_inverse_backward(
+                    ctypes.byref(self._desc), self._flat.data_ptr(), packed.data_ptr(), stash.data_ptr(), ptr(y),
+                    B, ptr(dz), ptr(dld), ptr(dx), ptr(dy), ptr(dflat), ws.data_ptr(), ws.numel(), self._stream(dev)),
+                    "nf_flow_inverse_backward")
+                if need_p and self._dp_world > 1:
+                    if getattr(self, "_dp_in_graph", False):
+                        _lib.check(lib.nf_dp_allreduce(dflat.data_ptr(), dflat.numel(), 1, self._stream(dev)), "nf_dp_allreduce")
+                    else:
+                        self._allreduce_grads(dflat)
+            elif need_p and self._dp_world > 1 and getattr(self, "_dp_in_graph", False):
                 bucket = int(self.dp_bucket_blocks)
                 if bucket <= 0:    # default: one bucket while the all-reduce is latency-bound, four for large arenas
                     bucket = self.n_layers if self._layout.total * 4 < (32 << 20) else max(1, -(-self.n_layers // 4))
                 _lib.check(lib.nf_flow_backward_dp(
-                    ctypes.byref(self._desc), self._flat.data_ptr(), packed.data_ptr(), stash.data_ptr(), y.data_ptr(),
+                    ctypes.byref(self._desc), self._flat.data_ptr(), packed.data_ptr(), stash.data_ptr(), ptr(y),
                     B, ptr(dz), ptr(dld), ptr(dx), ptr(dy), dflat.data_ptr(), bucket, ws.data_ptr(), ws.numel(),
                     self._stream(dev)), "nf_flow_backward_dp")
             elif need_p and self._dp_world > 1 and int(self.dp_bucket_blocks) > 0:
                 self._backward_overlapped(stash, packed, y, B, dz, dld, dx, dy, dflat, ws, dev)
             else:
                 _lib.check(lib.nf_flow_backward(
-                    ctypes.byref(self._desc), self._flat.data_ptr(), packed.data_ptr(), stash.data_ptr(), y.data_ptr(),
+                    ctypes.byref(self._desc), self._flat.data_ptr(), packed.data_ptr(), stash.data_ptr(), ptr(y),
                     B, ptr(dz), ptr(dld), ptr(dx), ptr(dy), ptr(dflat), ws.data_ptr(), ws.numel(), self._stream(dev)),
                     "nf_flow_backward")
                 if need_p and self._dp_world > 1:
                     self._allreduce_grads(dflat)
         return dx, dy, dflat
 
-    def _run_backward_fast(self, stash, packed, y, B, dz, dld, need_x, need_y, need_p):
+    def _run_backward_fast(self, stash, packed, y, B, dz, dld, need_x, need_y, need_p, inverse=False):
         """Backward with the parameter gradients written straight into the persistent flat arena."""
-        dev = y.device
+        dev = stash.device
         tp = self._tparams
         if not need_p:
-            dx, dy, _ = self._run_backward(stash, packed, y, B, dz, dld, need_x, need_y, False)
+            dx, dy, _ = self._run_backward(stash, packed, y, B, dz, dld, need_x, need_y, False, inverse=inverse)
             return dx, dy
         if self._gflat is None or self._gflat.device != dev:
             self._gflat = torch.zeros(self._layout.total, dtype=torch.float32, device=dev)
@@ -550,7 +617,7 @@ class RealNVP(nn.Module):
             else:
                 ours = False
         target = self._gflat if fresh else None
-        dx, dy, dflat = self._run_backward(stash, packed, y, B, dz, dld, need_x, need_y, True, out=target)
+        dx, dy, dflat = self._run_backward(stash, packed, y, B, dz, dld, need_x, need_y, True, out=target, inverse=inverse)
         if fresh:
             for p, v in zip(tp, views):
                 if p.requires_grad:
@@ -627,7 +694,7 @@ class RealNVP(nn.Module):
         while end > 0:
             begin = max(0, end - bucket)
             _lib.check(lib.nf_flow_backward_range(
-                ctypes.byref(self._desc), self._flat.data_ptr(), packed.data_ptr(), stash.data_ptr(), y.data_ptr(), B,
+                ctypes.byref(self._desc), self._flat.data_ptr(), packed.data_ptr(), stash.data_ptr(), ptr(y), B,
                 ptr(dz), ptr(dld), ptr(dx), ptr(dy), dflat.data_ptr(), begin, end, ws.data_ptr(), ws.numel(),
                 self._stream(dev)), "nf_flow_backward_range")
             seg = dflat[begin * stride:end * stride]
@@ -640,12 +707,12 @@ class RealNVP(nn.Module):
             dflat.mul_(1.0 / self._dp_world)
 
     # ------------------------------------------------------------------ reference API
-    def forward(self, x, y):
+    def forward(self, x, y=None):
         """-> (z, outputs, log_dets): torch_fcnf.py:134-141.  ``outputs`` (list of n_layers (B, D)
-        tensors, the block outputs logged at torch_nfbc_ant.py:286-287) are not differentiable."""
+        tensors, the block outputs logged at torch_nfbc_ant.py:286-287) are not differentiable.  ``y=None``: y == 0."""
         self._check_inputs(x, y)
         params = [p for p in self._tparams if p.requires_grad] if torch.is_grad_enabled() else []
-        need_grad = torch.is_grad_enabled() and (x.requires_grad or y.requires_grad or len(params) > 0)
+        need_grad = torch.is_grad_enabled() and (x.requires_grad or (y is not None and y.requires_grad) or len(params) > 0)
         if need_grad:
             if self.fast_param_grads:
                 z, logdet, outs = _Flow.apply(self, True, _accumulate_nodes(params[:1]), x, y, *params[:1])
@@ -655,42 +722,63 @@ class RealNVP(nn.Module):
             z, logdet, outs, _, _, _ = self._run_forward(x, y, False)
         return z, list(outs.unbind(0)), logdet
 
-    def reverse(self, x, y, return_sequence=False, return_logdet=False):
-        """torch_fcnf.py:143-152 (sampling direction; not differentiable).  With
-        ``return_logdet=True`` also returns the flax-style reverse log-det (nf.py:131-148)."""
-        self._check_inputs(x, y)
+    def _run_inverse(self, x, y, want_logdet, want_seq=False):
         dev = x.device
         B, D, n = x.shape[0], self.in_channels, self.n_layers
         x = _dense(x.detach())
-        y = _dense(y.detach())
+        y = _dense(y.detach()) if y is not None else None
         with _on(dev):
             packed = self._prepared(_lib.NF_PREP_FWD | _lib.NF_PREP_INV, dev)
             ws = self._workspace(B, dev)
             out = torch.empty((B, D), dtype=torch.float32, device=dev)
-            logdet = torch.empty((B,), dtype=torch.float32, device=dev) if return_logdet else None
-            seq = torch.empty((n + 1, B, D), dtype=torch.float32, device=dev) if return_sequence else None
+            logdet = torch.empty((B,), dtype=torch.float32, device=dev) if want_logdet else None
+            seq = torch.empty((n + 1, B, D), dtype=torch.float32, device=dev) if want_seq else None
             _lib.check(lib.nf_flow_inverse(
-                ctypes.byref(self._desc), self._flat.data_ptr(), packed.data_ptr(), x.data_ptr(), y.data_ptr(), B,
+                ctypes.byref(self._desc), self._flat.data_ptr(), packed.data_ptr(), x.data_ptr(),
+                y.data_ptr() if y is not None else None, B,
                 out.data_ptr(), logdet.data_ptr() if logdet is not None else None,
                 seq.data_ptr() if seq is not None else None, ws.data_ptr(), ws.numel(), self._stream(dev)),
                 "nf_flow_inverse")
+        return out, logdet, seq
+
+    def reverse(self, x, y=None, return_sequence=False, return_logdet=False):
+        """torch_fcnf.py:143-152 (sampling direction).  With ``return_logdet=True`` also returns the flax-style
+        reverse log-det (nf.py:131-148).  ``y=None``: y == 0.
+
+        Differentiable like the reference's (w.r.t. the input, ``y`` and every trainable parameter; both directions
+        are differentiated by offline-rl/agents/vinf.py:50,68): when gradients are enabled and something requires
+        them, the result carries an autograd node whose backward re-runs the forward direction on the result to obtain
+        the activations (the intermediate values of reverse(z) are those of forward(x)) and then the reverse-direction
+        backward (nf_flow_inverse_backward).  The sampling call itself costs the same either way; under
+        ``torch.no_grad()`` (the reference's evaluation loops, torch_nfbc_ant.py:207-210) no node is created.
+        ``return_sequence=True`` results are not differentiable."""
+        self._check_inputs(x, y)
+        params = [p for p in self._tparams if p.requires_grad] if torch.is_grad_enabled() else []
+        need_grad = (torch.is_grad_enabled() and not return_sequence and x.shape[0] > 0
+                     and (x.requires_grad or (y is not None and y.requires_grad) or len(params) > 0))
+        if need_grad:
+            carrier = params[:1] if self.fast_param_grads else params
+            out, logdet = _FlowReverse.apply(self, self.fast_param_grads, _accumulate_nodes(carrier), return_logdet,
+                                             x, y, *carrier)
+            return (out, logdet) if return_logdet else out
+        out, logdet, seq = self._run_inverse(x, y, return_logdet, return_sequence)
         res = list(seq.unbind(0)) if return_sequence else out
         return (res, logdet) if return_logdet else res
 
     # ------------------------------------------------------------------ extras
-    def log_prob(self, x, y):
+    def log_prob(self, x, y=None):
         """log N(z; 0, I) + log_dets -- what the callers assemble from ``prior.log_prob(z) + logdets``
         (torch_nfbc_ant.py:269) for the standard-normal prior, without the O(D^2) Mahalanobis path."""
         z, _, logdet = self.forward(x, y)
         return -0.5 * (z * z).sum(dim=1) - 0.5 * self.in_channels * math.log(2.0 * math.pi) + logdet
 
-    def nll(self, x, y):
+    def nll(self, x, y=None):
         """-mean(log N(z; 0, I) + log_dets): the training loss of torch_nfbc_ant.py:269-270 for the standard-normal
         prior, with the loss reduction and its cotangents fused into two library kernels.  Parameter gradients
         go to the flat gradient arena (``fast_param_grads`` semantics)."""
         self._check_inputs(x, y)
         params = [p for p in self._tparams if p.requires_grad] if torch.is_grad_enabled() else []
-        if torch.is_grad_enabled() and (x.requires_grad or y.requires_grad or params):
+        if torch.is_grad_enabled() and (x.requires_grad or (y is not None and y.requires_grad) or params):
             return _FlowNLL.apply(self, _accumulate_nodes(params[:1]), x, y, *params[:1])
         return -self.log_prob(x, y).mean()
 
@@ -701,7 +789,7 @@ class RealNVP(nn.Module):
         NLL kernel, a backward that only produces dx (no parameter or y gradients), one axpy.  Returns a new tensor."""
         self._check_inputs(x, y)
         dev, B, D = x.device, x.shape[0], self.in_channels
-        x, y = _dense(x.detach()), _dense(y.detach())
+        x, y = _dense(x.detach()), (_dense(y.detach()) if y is not None else None)
         if B == 0:
             return x.clone()
         z, logdet, _, stash, packed, slot = self._run_forward(x, y, True, want_outputs=False)

@@ -66,11 +66,12 @@ class _Block(nn.Module):
         s, t = self.s(h), self.t(h)
         return torch.cat([xc, (xt - t) * torch.exp(-s)], 1), self.l.logdet() - s.sum(1)
 
-    def reverse(self, z, y):     # torch_fcnf.py:108-117
+    def reverse(self, z, y, with_logdet=False):     # torch_fcnf.py:108-117; log-det: flax nf.py:131-148
         zc, zt = z[:, :self.dc], z[:, self.dc:]
         h = torch.cat([zc, y], 1)
         s, t = self.s(h), self.t(h)
-        return torch.cat([zc, zt * torch.exp(s) + t], 1) @ self.l.weight_inv()
+        x = torch.cat([zc, zt * torch.exp(s) + t], 1) @ self.l.weight_inv()
+        return (x, s.sum(1) - self.l.logdet()) if with_logdet else x
 
 
 class TorchFlow(nn.Module):
@@ -89,10 +90,15 @@ class TorchFlow(nn.Module):
             outs.append(x)
         return x, outs, logdets
 
-    def reverse(self, z, y):
+    def reverse(self, z, y, return_logdet=False):
+        logdets = torch.zeros(z.shape[0], dtype=z.dtype, device=z.device)
         for b in reversed(self.blocks):
-            z = b.reverse(z, y)
-        return z
+            if return_logdet:
+                z, ld = b.reverse(z, y, True)
+                logdets = logdets + ld
+            else:
+                z = b.reverse(z, y)
+        return (z, logdets) if return_logdet else z
 
 
 class TorchEncoder(nn.Module):

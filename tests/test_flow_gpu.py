@@ -610,3 +610,82 @@ def test_reference_constructor_call_runs_on_the_tensor_cores():
     prof = _lib.prof_collect()
     _lib.lib.nf_prof_enable(0)
     assert prof["tc_gemm"][2] >= 2 * n and prof["tc_wgrad"][2] >= n, prof
+
+
+def _torch_checker(cfg, sd, H1=None, eps=1e-5, dtype=torch.float64):
+    from oracle.torch_flow import TorchFlow
+    m = TorchFlow(cfg["D"], cfg["C"], cfg["R"], cfg["n"], first_hidden=H1, ln_eps=eps)
+    m.load_state_dict({k: torch.tensor(np.asarray(v)) for k, v in sd.items()})
+    return m.to(dev()).to(dtype)
+
+
+@pytest.mark.parametrize("fast", [True, False])
+@pytest.mark.parametrize("D,C,R,n,H1,eps,B", [(8, 128, 32, 3, None, 1e-5, 300), (9, 64, 24, 3, None, 1e-5, 50),
+                                              (2, 32, 8, 2, 40, 1e-6, 257), (40, 64, 16, 2, None, 1e-5, 64)])
+def test_reverse_is_differentiable(D, C, R, n, H1, eps, B, fast):
+    """the sampling direction with its log-det, differentiated w.r.t. its input, y and every
+    parameter (both directions are differentiated by offline-rl/agents/vinf.py:50,68; flax nf.py:131-148) -- against
+    autograd through the float64 checker (oracle/torch_flow.py)."""
+    sd = synth.make_state_dict(D, C, R, n, seed=21, H1=H1)
+    cfg = dict(D=D, C=C, R=R, n=n, B=B)
+    model = build_model(cfg, sd, "fp32", first_hidden=H1, ln_eps=eps, fast_param_grads=fast)
+    ref = _torch_checker(cfg, sd, H1, eps)
+    # a latent whose reverse lands on kink-free activations: z = forward(x) of safe inputs
+    x0, y, _ = synth.make_safe_inputs(sd, n, B, D, R, seed=300 + B, eps=eps)
+    with torch.no_grad():
+        z64, _, _ = ref(t(x0).double(), t(y).double())
+    cx, cl = synth.make_cotangents(B, D, seed=B + 7)
+    zt, yt = z64.float().clone().requires_grad_(True), t(y).requires_grad_(True)
+    xr, ld = model.reverse(zt, yt, return_logdet=True)
+    assert xr.requires_grad and ld.requires_grad
+    ((xr * t(cx)).sum() + (ld * t(cl)).sum()).backward()
+    zr, yr = z64.float().double().clone().requires_grad_(True), t(y).double().requires_grad_(True)
+    xr64, ld64 = ref.reverse(zr, yr, return_logdet=True)
+    ((xr64 * t(cx).double()).sum() + (ld64 * t(cl).double()).sum()).backward()
+    tol = 1e-4   # the reference's own float32 round trip is 3e-5 .. 1.7e-2 (SURVEY section 4)
+    assert rel_err(xr.detach().cpu().numpy(), xr64.detach().cpu().numpy()) <= tol
+    assert rel_err(ld.detach().cpu().numpy(), ld64.detach().cpu().numpy()) <= tol
+    assert rel_err(zt.grad.cpu().numpy(), zr.grad.cpu().numpy()) <= tol
+    assert rel_err(yt.grad.cpu().numpy(), yr.grad.cpu().numpy()) <= tol
+    refg = dict(ref.named_parameters())
+    for k, p in model.named_parameters():
+        if p.requires_grad:
+            assert p.grad is not None, k
+            assert rel_err(p.grad.cpu().numpy(), refg[k].grad.cpu().numpy()) <= 2e-4, k
+    # without the log-det, and under no_grad, nothing is recorded
+    for p in model.parameters():
+        p.grad = None
+    x2 = model.reverse(zt.detach().requires_grad_(True), yt.detach())
+    assert x2.requires_grad and torch.allclose(x2, xr.detach())
+    with torch.no_grad():
+        assert not model.reverse(zt, yt).requires_grad
+
+
+@pytest.mark.parametrize("D,C,R,n,H1,B", [(2, 256, 64, 2, 320, 1000), (8, 128, 32, 3, None, 300), (40, 64, 16, 2, None, 64)])
+def test_zero_conditioning_fast_path(D, C, R, n, H1, B):
+    """y=None (train_auto_NF_rl.py:328-339 evaluates the flow with cond == 0) computes what
+    y = zeros computes -- forward, log-det, gradients, reverse -- without the y part of the first Linear."""
+    sd = synth.make_state_dict(D, C, R, n, seed=31, H1=H1)
+    cfg = dict(D=D, C=C, R=R, n=n, B=B)
+    x, _ = synth.make_inputs(B, D, R, seed=5)
+    y0 = torch.zeros(B, R, device=dev())
+    dz, dld = synth.make_cotangents(B, D, seed=6)
+    res = []
+    for yy in (y0, None):
+        model = build_model(cfg, sd, "fp32", first_hidden=H1)
+        xt = t(x).requires_grad_(True)
+        z, outs, ld = model(xt, yy)
+        ((z * t(dz)).sum() + (ld * t(dld)).sum()).backward()
+        with torch.no_grad():
+            xr, rld = model.reverse(z.detach(), yy, return_logdet=True)
+            lp = model.log_prob(t(x), yy)
+        g = torch.cat([p.grad.reshape(-1) for p in model.parameters() if p.requires_grad])
+        res.append([v.detach().cpu().numpy() for v in (z, ld, xt.grad, g, xr, rld, lp)])
+        if yy is None:   # the y columns of the first Linear's weight gradient are exactly zero
+            dc = (D + 1) // 2
+            assert float(model.blocks[0].s[0].weight.grad[:, dc:].abs().max()) == 0.0
+    for a, b, nm in zip(res[0], res[1], ("z", "ld", "dx", "dparams", "rev", "rev_ld", "log_prob")):
+        assert rel_err(b, a) <= 5e-6, (nm, rel_err(b, a))
+    sd64 = fo.cast_state_dict(sd, np.float64)
+    ref = fo.flow_forward(sd64, n, x.astype(np.float64), np.zeros((B, R)), eps=1e-5)
+    assert rel_err(res[1][0], ref[0]) <= 2e-5
