@@ -55,7 +55,11 @@ extern "C" {
 #define NF_PREC_FP32_SIMT 0 /* FFMA, exact fp32 (checker / odd shapes)                         */
 #define NF_PREC_TF32X3    1 /* tcgen05 kind::tf32, 3-pass split operands, fp32 accumulate:     */
                             /* fp32-parity mode (<= 1e-5 vs the fp64 arbiter)                   */
-#define NF_PREC_BF16      2 /* reserved (optional 2e-2 mode): not built, rejected with NF_E_UNSUPPORTED */
+#define NF_PREC_BF16      2 /* reserved: not built, rejected with NF_E_UNSUPPORTED                */
+#define NF_PREC_TF32      3 /* optional reduced-precision mode: ONE kind::tf32 pass on the raw fp32 operands (10-bit
+                             * mantissa, fp32 accumulate), no operand splitting; contract 2e-2 relative on z / log_prob
+                             * for D <= 64, n_blocks <= 12 (BASELINE north_star's optional fast mode; errors grow with
+                             * depth: measured values in DESIGN.md) */
 
 typedef struct NfFlowDesc {
   int32_t D;        /* in_channels: flow dimension                                     */

@@ -9,7 +9,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int6
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libnf_b200.so")
 
-PREC = {"fp32_simt": 0, "fp32": 1, "tf32x3": 1}
+PREC = {"fp32_simt": 0, "fp32": 1, "tf32x3": 1, "tf32": 3}
 
 NF_P_SLOTS = 25
 NF_P_NET_SLOTS = 10

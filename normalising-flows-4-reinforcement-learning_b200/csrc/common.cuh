@@ -136,6 +136,9 @@ static inline Dims dims_of(const NfFlowDesc* d) {
   return m;
 }
 
+// precision modes that run the contractions on the tensor cores; the reduced mode issues one raw TF32 pass
+static inline bool prec_tc(int prec) { return prec == NF_PREC_TF32X3 || prec == NF_PREC_TF32; }
+
 int check_desc(const NfFlowDesc* d);
 void param_layout(const Dims& m, NfParamLayout* out);
 

@@ -336,7 +336,7 @@ int enc_linear(int prec, const float* A, int K, const float* W, const float* bia
   t.M = (int)B; t.N = N; t.K0 = K;
   // Few output tiles and a long reduction (the ant encoder's first layer at batch 256: 8 tiles, K = 4100): start C
   // at the bias and accumulate, which lets the GEMM split the reduction over the idle SMs.
-  if (prec == NF_PREC_TF32X3 && K >= 512 && cdiv(B, 128) * cdiv(N, 128) * 2 <= 148 && tc_gemm_supported(t)) {
+  if (prec_tc(prec) && K >= 512 && cdiv(B, 128) * cdiv(N, 128) * 2 <= 148 && tc_gemm_supported(t)) {
     const long long n = B * N;
     NF_LAUNCH((k_enc_fill_rows), (unsigned)std::min<long long>(cdiv(n, 256), 148 * 4), 256, 0, st, C, n, N, bias);
     NF_LAUNCHED();

@@ -66,7 +66,7 @@ int check_desc(const NfFlowDesc* d) {
   NF_CHECK_ARG(d->R >= 0 && d->R <= 65536, NF_E_BADARG, "R=%d out of range", d->R);
   NF_CHECK_ARG(d->n_blocks >= 1 && d->n_blocks <= 4096, NF_E_BADARG, "n_blocks=%d out of range", d->n_blocks);
   NF_CHECK_ARG(d->ln_eps > 0.f, NF_E_BADARG, "ln_eps must be > 0");
-  NF_CHECK_ARG(d->precision >= 0 && d->precision <= 2, NF_E_BADARG, "unknown precision %d", d->precision);
+  NF_CHECK_ARG(d->precision >= 0 && d->precision <= 3, NF_E_BADARG, "unknown precision %d", d->precision);
   NF_CHECK_ARG(d->precision != NF_PREC_BF16, NF_E_UNSUPPORTED, "the bf16 mode is not built (use NF_PREC_TF32X3)");
   return 0;
 }
@@ -279,7 +279,8 @@ int linear_nt(int prec, const TcGemmP& t0, cudaStream_t st) {
   // systematic 2^-22-relative bias that grows with the reduction length; long reductions use the
   // round-to-nearest split (zero-mean lo) -- measured on C5 (K = 1024, 24 blocks): dy error 1.08e-5 -> inside 1e-5.
   if (t.K0 + t.K1 >= 512) t.raw_hi = 0;
-  if (prec == NF_PREC_TF32X3 && t.N >= 16 && (t.K0 + t.K1) >= 32 && tc_gemm_supported(t)) return tc_gemm(t, st);
+  if (prec == NF_PREC_TF32) { t.passes = 1; t.raw_hi = 1; t.B0hi = t.B0lo = t.B1hi = t.B1lo = nullptr; }
+  if (prec_tc(prec) && t.N >= 16 && (t.K0 + t.K1) >= 32 && tc_gemm_supported(t)) return tc_gemm(t, st);
   GemmP g;
   g.A0 = t.A0; g.A1 = t.A1; g.B0 = t.B0; g.B1 = t.B1; g.C = t.C; g.bias = t.bias;
   g.M = t.M; g.N = t.N; g.K0 = t.K0; g.K1 = t.K1;
@@ -291,8 +292,10 @@ int linear_nt(int prec, const TcGemmP& t0, cudaStream_t st) {
 
 // C[z] (M,N) += A[z] (K,M)^T @ B[z] (K,N): weight gradients (reduction over the K = batch rows).
 // C must already hold the base value (the gradient arena is zero-filled first).
-int wgrad_tn(int prec, const TcGemmTnP& t, cudaStream_t st) {
-  if (prec == NF_PREC_TF32X3 && t.M >= 16 && t.N >= 32 && tc_gemm_tn_supported(t)) return tc_gemm_tn(t, st);
+int wgrad_tn(int prec, const TcGemmTnP& t0, cudaStream_t st) {
+  TcGemmTnP t = t0;
+  if (prec == NF_PREC_TF32) t.passes = 1;
+  if (prec_tc(prec) && t.M >= 16 && t.N >= 32 && tc_gemm_tn_supported(t)) return tc_gemm_tn(t, st);
   GemmP g;
   g.transA = 1; g.A0 = t.A; g.lda0 = (int)t.lda; g.sA0 = t.sA; g.K0 = (int)t.K;
   g.B0 = t.B; g.ldb0 = (int)t.ldb; g.sB0 = t.sB;
@@ -330,11 +333,12 @@ static int conditioners(const Dims& m, const NfParamLayout& pl, const PackedLayo
                              float* r, uint32_t* mk, int mw, const TailP* tl) -> int {
     g.M = (int)B; g.N = N; g.batch = 2;
     if (g.K0 + g.K1 >= 512) g.raw_hi = 0;
+    if (m.prec == NF_PREC_TF32) { g.passes = 1; g.raw_hi = 1; g.B0hi = g.B0lo = g.B1hi = g.B1lo = nullptr; }
     TcGemmP f = g;
     f.C = xh; f.ldc = N; f.sC = xh_net; f.bias = bias; f.sBias = bias_net;
     f.epi.kind = TC_EPI_LN_FWD; f.epi.eps = m.eps;
     f.epi.rstd = r; f.epi.sRstd = r_net; f.epi.mask = mk; f.epi.sMask = m_net; f.epi.mw = mk ? mw : 0;
-    if (m.prec == NF_PREC_TF32X3 && (g.K0 + g.K1) >= 32 && tc_gemm_epi_supported(f)) {
+    if (prec_tc(m.prec) && (g.K0 + g.K1) >= 32 && tc_gemm_epi_supported(f)) {
       if (tl && tc_gemm_tail_supported(f, tl->D)) {
         // the whole rest of the block (last Linear, affine coupling, log-det, neighbouring PLU matmul) rides on
         // this launch: the cluster holds both nets, its leader CTA finishes the rows
@@ -964,7 +968,7 @@ static int backward_impl(const NfFlowDesc* desc, const float* params, const void
       }
       {  // c. d x_hat2 = dout W3f
         bool done = false;
-        if (m.prec == NF_PREC_TF32X3 && m.dt >= 16 && (m.dt & 3) == 0) {
+        if (prec_tc(m.prec) && m.dt >= 16 && (m.dt & 3) == 0) {
           // tensor-core form: the K-major B operand is W3f^T (C, dt), transposed per block into the workspace (the
           // FFMA GEMM below took 44 us per block on C5 for what is a 67 MB store)
           float* w3t = w.w3t[par];
@@ -974,6 +978,7 @@ static int backward_impl(const NfFlowDesc* desc, const float* params, const void
           t.B0 = w3t; t.ldb0 = m.dt; t.sB0 = (int64_t)m.C * m.dt;
           t.C = wb.gA; t.ldc = m.C; t.sC = B * Hm;
           t.M = (int)B; t.N = m.C; t.batch = 2;
+          if (m.prec == NF_PREC_TF32) { t.passes = 1; t.raw_hi = 1; }
           if (tc_gemm_supported(t)) { NF_TRY(tc_gemm(t, st)); done = true; }
         }
         if (!done) {
@@ -1012,11 +1017,12 @@ static int backward_impl(const NfFlowDesc* desc, const float* params, const void
       g.C = wb.gB; g.ldc = m.H1; g.sC = B * Hm;
       g.M = (int)B; g.N = m.H1; g.batch = 2;
       if (kl.hi_off) { g.B0hi = g.B0 + kl.hi_off; g.B0lo = g.B0 + kl.lo_off; }
-      if (v2 && m.prec == NF_PREC_TF32X3 && m.C >= 32) {
+      if (v2 && prec_tc(m.prec) && m.C >= 32) {
         // f + g in one kernel: LayerNorm-1 / LeakyReLU-1 backward as the GEMM's row-wise epilogue; the bias
         // gradient (column sums of du1) is taken by the block's column-reduction launch
         TcGemmP f = g;
         if (f.K0 >= 512) f.raw_hi = 0;
+        if (m.prec == NF_PREC_TF32) { f.passes = 1; f.raw_hi = 1; f.B0hi = f.B0lo = nullptr; }
         f.epi.kind = TC_EPI_LN_BWD;
         f.epi.xh = sb + sl.xh1; f.epi.ldxh = m.H1; f.epi.sXh = sl.net_stride;
         f.epi.rstd = const_cast<float*>(sb + sl.r1); f.epi.sRstd = sl.net_stride;
@@ -1453,11 +1459,12 @@ int nf_linear(const float* A, int64_t lda, const float* W, int64_t ldw, const fl
     g.C = C; g.ldc = (int)ldc; g.bias = bias; g.M = (int)M; g.N = N;
     return simt_gemm(g, st);
   }
-  NF_CHECK_ARG(engine == NF_PREC_TF32X3 || (engine >= 3 && engine <= 6), NF_E_UNSUPPORTED, "unknown engine %d", engine);
+  NF_CHECK_ARG(engine == NF_PREC_TF32X3 || (engine >= 3 && engine <= 7), NF_E_UNSUPPORTED, "unknown engine %d", engine);
   TcGemmP t;
   t.A0 = A; t.lda0 = lda; t.K0 = K; t.B0 = W; t.ldb0 = ldw; t.C = C; t.ldc = ldc; t.bias = bias;
-  t.M = (int)M; t.N = N; t.passes = engine == 3 ? 1 : 3; t.raw_hi = (engine == 4 || engine == 6 || engine == 3);
-  t.bk = (engine == 5 || engine == 6) ? 32 : 16;
+  t.M = (int)M; t.N = N; t.passes = (engine == 3 || engine == 7) ? 1 : 3;
+  t.raw_hi = (engine == 4 || engine == 6 || engine == 3 || engine == 7);
+  t.bk = (engine == 5 || engine == 6 || engine == 7) ? 32 : 16;
   return tc_gemm(t, st);
 }
 

@@ -63,15 +63,17 @@ struct KArgs {
 };
 constexpr int EPI_NONE = 0, EPI_LN_FWD = 1, EPI_LN_BWD = 2;
 
-template <int BN, int STAGES, int BK, bool TS = false>
+// NS = true ("no split"): single TF32 pass on the raw fp32 tiles, SS form -- a stage is just [A | B], so twice as many
+// stages are in flight in the same shared memory (the loop is bound by bytes in flight / round-trip latency).
+template <int BN, int STAGES, int BK, bool TS = false, bool NS = false>
 struct Smem {
   static constexpr int A_BYTES = BM * BK * 4;
   static constexpr int B_BYTES = BN * BK * 4;
   static constexpr int HALF = A_BYTES + B_BYTES;   // raw/hi tiles; the lo twins follow
   // SS form: [A | B | A lo | B lo]; TS form: [A | B | B lo] (A's halves live in tensor memory), which buys two more
   // stages of TMA prefetch in the same shared memory.  The lo twin of tile byte o sits at LO + o in both.
-  static constexpr int LO = TS ? B_BYTES : HALF;
-  static constexpr int STAGE = TS ? A_BYTES + 2 * B_BYTES : 2 * HALF;
+  static constexpr int LO = NS ? 0 : (TS ? B_BYTES : HALF);
+  static constexpr int STAGE = NS ? HALF : (TS ? A_BYTES + 2 * B_BYTES : 2 * HALF);
   static constexpr int BARS = STAGES * STAGE;      // byte offset of the barrier block
   static constexpr int XCHG = BARS + 512;          // [kMaxCluster][128] float2 partial row statistics (epilogue kernels)
   static constexpr int TOTAL = BARS + 512 + 1024;  // + alignment slack
@@ -92,13 +94,14 @@ struct Smem {
 // with clock64) against 384 cycles of MMAs, so the TS kernels run two groups on alternating stages; both groups
 // share the epilogue (plain: alternating 32-column chunks; row-wise: each group owns half of the tile's columns, which
 // also halves the registers a thread needs for its row -- 320 threads leave 200 per thread).
-template <int BN, int STAGES, bool MNMAJOR, int BK, int EPI = EPI_NONE, bool TS = false, int NSG = 1>
+template <int BN, int STAGES, bool MNMAJOR, int BK, int EPI = EPI_NONE, bool TS = false, int NSG = 1, bool NS = false>
 __global__ void __launch_bounds__(64 + 128 * NSG, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUtensorMap mA1,
           const __grid_constant__ CUtensorMap mB0, const __grid_constant__ CUtensorMap mB1,
           const __grid_constant__ CUtensorMap mB0l, const __grid_constant__ CUtensorMap mB1l,
           const __grid_constant__ CUtensorMap mC, const KArgs a) {
-  using S = Smem<BN, STAGES, BK, TS>;
+  using S = Smem<BN, STAGES, BK, TS, NS>;
+  static_assert(!NS || !TS, "the no-split form feeds both operands from shared memory");
   constexpr int A_BYTES = S::A_BYTES;
   constexpr int BOX = 32 * BK * 4;   // bytes of one 32-column MN-major TMA box
   extern __shared__ uint8_t smem_dyn[];
@@ -162,7 +165,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
   // (tests, experiments) can lower the count; the default is the full rotation with a separate corr accumulator.
   const int nacc_rt = a.nacc < 1 ? NACC : (a.nacc > NACC ? NACC : a.nacc);
   const int nacc_used = total_k8 < nacc_rt ? total_k8 : nacc_rt;
-  const bool with_corr = a.passes == 3;
+  const bool with_corr = !NS && a.passes == 3;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&mA0); prefetch_tmap(&mB0);
@@ -237,7 +240,10 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
       constexpr uint32_t kStep = MNMAJOR ? (1024u >> 4) : (32u >> 4);   // next k8 block inside a stage
       const uint32_t rot_end = tmem_base + (uint32_t)nacc_rt * BN;
       uint32_t tmem_main = tmem_base, acc_c = 0, fresh = (uint32_t)nacc_rt;   // `fresh` mains not written yet
-      const bool three = a.passes == 3;
+      const bool three = !NS && a.passes == 3;
+      // single TF32 pass on the raw fp32 tiles (the tensor core ignores the low 13 mantissa bits): nothing to split, the
+      // MMAs consume the TMA tiles directly -- TMA -> full barrier -> MMA, no thread in between
+      uint64_t* ready = (NS || (!TS && a.passes == 1 && a.raw_hi)) ? full : split;
       // The tensor pipe accepts MMAs about as fast as it executes them (measured: 6 issues take 360-390 cycles, and
       // with every wait removed a stage still took 690 cycles of which 330 were this loop's own bookkeeping), so
       // whatever this warp does between two issue bursts is tensor-pipe idle time.  Everything is strength-reduced:
@@ -304,8 +310,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
         const int aslot1 = awrap ? 0 : aslot + 1;
         const uint32_t ta1 = awrap ? tmem_base + A_BASE : ta_slot + 2 * BK;
         if (lane == 0) {
-          mbar_wait(&split[s], ph);
-          if (two) mbar_wait(&split[s1], ph1);
+          mbar_wait(&ready[s], ph);
+          if (two) mbar_wait(&ready[s1], ph1);
         }
         __syncwarp();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -344,7 +350,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
     // ------------------------------------------------------------------ splitters, then epilogue
     const int t = (threadIdx.x - 64) & 127;       // 0..127 inside the splitter group
     const int grp = (threadIdx.x - 64) >> 7;      // splitter group: takes the stages with it % NSG == grp
-    for (int it = grp; it < nk; it += NSG) {
+    const bool nosplit = NS || (!TS && a.passes == 1 && a.raw_hi);
+    for (int it = grp; it < nk && !nosplit; it += NSG) {
       const int s = it % STAGES, use = it / STAGES;
       mbar_wait(&full[s], use & 1);
       if (threadIdx.x == 64 && it == 0) NF_TS(2);   // first operand tile landed
@@ -849,15 +856,15 @@ int set_smem() {
 
 int pick_nacc() { return option(NF_OPT_NACC); }   // 0 = kernel default (all NACC accumulators)
 
-template <int BN, int STAGES, int BK, bool TS = false>
+template <int BN, int STAGES, int BK, bool TS = false, bool NS = false>
 int launch(const TcGemmP& p, cudaStream_t st) {
-  using S = Smem<BN, STAGES, BK, TS>;
+  using S = Smem<BN, STAGES, BK, TS, NS>;
   constexpr int NSG = TS ? 2 : 1;
   int r;
   {
     static PerDeviceOnce once;
     if (once.first()) {
-      NF_CUDA(cudaFuncSetAttribute(k_tc_gemm<BN, STAGES, false, BK, EPI_NONE, TS, NSG>,
+      NF_CUDA(cudaFuncSetAttribute((k_tc_gemm<BN, STAGES, false, BK, EPI_NONE, TS, NSG, NS>),
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     }
   }
@@ -902,20 +909,20 @@ int launch(const TcGemmP& p, cudaStream_t st) {
   CUtensorMap mC = mA0;
   a.tma_store = make_c_map(&mC, p.C, p.N, p.M, p.ldc, p.batch, p.sC) ? 1 : 0;
   a.b_presplit = pre ? 1 : 0;
-  NF_LAUNCH((k_tc_gemm<BN, STAGES, false, BK, EPI_NONE, TS, NSG>), grid, 64 + 128 * NSG, S::TOTAL, st, mA0, mA1, mB0, mB1, mB0l, mB1l, mC, a);
+  NF_LAUNCH((k_tc_gemm<BN, STAGES, false, BK, EPI_NONE, TS, NSG, NS>), grid, 64 + 128 * NSG, S::TOTAL, st, mA0, mA1, mB0, mB1, mB0l, mB1l, mC, a);
   NF_LAUNCHED();
   return 0;
 }
 
 // NSG = 2 (TS only): two splitter groups on alternating stages; the row-wise epilogue then splits the tile's columns
 // between the groups (the fused flow tail needs the whole row in one thread and keeps NSG = 1)
-template <int BN, int STAGES, int BK, int EPI, bool TS = false, int NSG = 1>
+template <int BN, int STAGES, int BK, int EPI, bool TS = false, int NSG = 1, bool NS = false>
 int launch_epi(const TcGemmP& p, cudaStream_t st) {
-  using S = Smem<BN, STAGES, BK, TS>;
+  using S = Smem<BN, STAGES, BK, TS, NS>;
   static_assert(NSG == 1 || (TS && (BN / NSG) % 32 == 0), "two splitter groups need the TS form and 32-column slices");
   static PerDeviceOnce once;
   if (once.first()) {
-    NF_CUDA(cudaFuncSetAttribute(k_tc_gemm<BN, STAGES, false, BK, EPI, TS, NSG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    NF_CUDA(cudaFuncSetAttribute((k_tc_gemm<BN, STAGES, false, BK, EPI, TS, NSG, NS>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  S::TOTAL_EPI));
   }
   int r;
@@ -968,13 +975,17 @@ int launch_epi(const TcGemmP& p, cudaStream_t st) {
   CUtensorMap mC = mA0;
   a.tma_store = make_c_map(&mC, p.C, p.N, p.M, p.ldc, p.batch, p.sC) ? 1 : 0;
   a.b_presplit = pre ? 1 : 0;
-  NF_CUDA(cudaLaunchKernelEx(&cfg, k_tc_gemm<BN, STAGES, false, BK, EPI, TS, NSG>, mA0, mA1, mB0, mB1, mB0l, mB1l, mC, a));
+  NF_CUDA(cudaLaunchKernelEx(&cfg, k_tc_gemm<BN, STAGES, false, BK, EPI, TS, NSG, NS>, mA0, mA1, mB0, mB1, mB0l, mB1l, mC, a));
   NF_LAUNCHED();
   return 0;
 }
 
 template <int EPI>
 int launch_epi_pick(const TcGemmP& p, cudaStream_t st) {
+  if (p.passes == 1 && p.raw_hi && !(EPI == EPI_LN_FWD && p.epi.tail.on)) {   // single raw TF32 pass: no-split form
+    if (p.N % 128 == 0 && p.N / 128 <= kMaxCluster) return launch_epi<128, 11, 16, EPI, false, 1, true>(p, st);
+    return launch_epi<64, 14, 16, EPI, false, 1, true>(p, st);
+  }
   const bool ts = option(NF_OPT_TS) != 0;
   const bool tail = EPI == EPI_LN_FWD && p.epi.tail.on;
   if (p.N % 128 == 0 && p.N / 128 <= kMaxCluster) {
@@ -991,15 +1002,15 @@ int launch_epi_pick(const TcGemmP& p, cudaStream_t st) {
   return launch_epi<64, 8, 16, EPI>(p, st);
 }
 
-template <int BN, int STAGES, int BK, bool TS = false>
+template <int BN, int STAGES, int BK, bool TS = false, bool NS = false>
 int launch_tn(const TcGemmTnP& p, cudaStream_t st) {
-  using S = Smem<BN, STAGES, BK, TS>;
+  using S = Smem<BN, STAGES, BK, TS, NS>;
   constexpr int NSG = TS ? 2 : 1;
   int r;
   {
     static PerDeviceOnce once;
     if (once.first()) {
-      NF_CUDA(cudaFuncSetAttribute(k_tc_gemm<BN, STAGES, true, BK, EPI_NONE, TS, NSG>,
+      NF_CUDA(cudaFuncSetAttribute((k_tc_gemm<BN, STAGES, true, BK, EPI_NONE, TS, NSG, NS>),
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     }
   }
@@ -1026,7 +1037,7 @@ int launch_tn(const TcGemmTnP& p, cudaStream_t st) {
   a.K0 = (int)p.K; a.K1 = 0;
   a.ldc = p.ldc; a.sC = p.sC; a.sBias = 0;
   a.zA0 = p.sA != 0; a.zB0 = p.sB != 0; a.zA1 = a.zB1 = 0;
-  a.accumulate = 1; a.passes = p.passes; a.raw_hi = 0;
+  a.accumulate = 1; a.passes = p.passes; a.raw_hi = NS ? 1 : 0;
   a.splitk = (int)splitk; a.chunks_per_split = (int)per;
   a.dbg = g_tc_dbg;
   a.nacc = pick_nacc();
@@ -1034,7 +1045,7 @@ int launch_tn(const TcGemmTnP& p, cudaStream_t st) {
   ProfScope prof(st, PROF_TC_WGRAD, 2.0 * p.M * p.N * (double)p.K * p.batch);
   CUtensorMap mC = mA;
   a.tma_store = make_c_map(&mC, p.C, p.N, p.M, p.ldc, p.batch, p.sC) ? 1 : 0;
-  NF_LAUNCH((k_tc_gemm<BN, STAGES, true, BK, EPI_NONE, TS, NSG>), grid, 64 + 128 * NSG, S::TOTAL, st, mA, mA, mB, mB, mB, mB, mC, a);
+  NF_LAUNCH((k_tc_gemm<BN, STAGES, true, BK, EPI_NONE, TS, NSG, NS>), grid, 64 + 128 * NSG, S::TOTAL, st, mA, mA, mB, mB, mB, mB, mC, a);
   NF_LAUNCHED();
   return 0;
 }
@@ -1112,6 +1123,8 @@ int tc_gemm(const TcGemmP& p, cudaStream_t st) {
   // small problems: prefer more, smaller CTAs (3 pipeline stages) over filling TMEM
   // BN = 256 fills TMEM with one main + one corr accumulator; BN <= 128 leaves room for the three rotating
   // main accumulators that keep long reductions inside fp32 parity, so 256 is only used while one accumulator is enough (K <= 256, pick_nacc).
+  if (p.passes == 1 && p.raw_hi && p.bk != 32)   // single raw TF32 pass: no-split form, 12 stages in flight
+    return p.N > 64 ? launch<128, 12, 16, false, true>(p, st) : launch<64, 16, 16, false, true>(p, st);
   const int wide_ok = option(NF_OPT_BN256);
   const long long ctas256 = (wide_ok == 1 || (wide_ok == 0 && p.K0 + p.K1 <= 256))
                                 ? cdiv(p.M, BM) * cdiv(p.N, 256) * p.batch : 0;
@@ -1140,6 +1153,8 @@ int tc_gemm_tn(const TcGemmTnP& p, cudaStream_t st) {
   if (p.M <= 0 || p.N <= 0 || p.batch <= 0 || p.K <= 0) return 0;
   NF_CHECK_ARG(tc_gemm_tn_supported(p), NF_E_UNSUPPORTED,
                "tc_gemm_tn: operands must be 16-byte aligned with row pitches that are multiples of 4 floats");
+  if (p.passes == 1 && p.bk != 32)   // single raw TF32 pass: no-split form
+    return p.N > 64 ? launch_tn<128, 12, 16, false, true>(p, st) : launch_tn<64, 16, 16, false, true>(p, st);
   const int wide_ok = option(NF_OPT_BN256);
   if (wide_ok != 1) {
     if (p.bk == 32) return p.N > 64 ? launch_tn<128, 3, 32>(p, st) : launch_tn<64, 4, 32>(p, st);

@@ -53,8 +53,8 @@ class GEncoder(nn.Module):
     def __init__(self, input_size, rep_size, *, hidden: int = 512, n_hidden: int = 4, ln_eps: float = 1e-5,
                  precision: str = "fp32"):
         super().__init__()
-        if precision not in ("fp32", "tf32x3", "fp32_simt"):
-            raise ValueError("precision must be 'fp32' or 'fp32_simt'")
+        if precision not in ("fp32", "tf32x3", "fp32_simt", "tf32"):
+            raise ValueError("precision must be 'fp32', 'fp32_simt' or 'tf32'")
         self.input_size, self.rep_size = int(input_size), int(rep_size)
         self.hidden, self.n_hidden, self.ln_eps, self.precision = int(hidden), int(n_hidden), float(ln_eps), precision
         fan = self.input_size

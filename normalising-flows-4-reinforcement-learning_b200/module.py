@@ -327,7 +327,9 @@ class RealNVP(nn.Module):
     Extra keyword arguments select the flax twin's semantics
     (/root/reference/unsupservised-gcrl/nf.py): ``first_hidden=channels+cond_channels`` (:94,101),
     ``ln_eps=1e-6`` (flax LayerNorm default), and ``precision``:
-    ``"fp32"`` (tcgen05 3xTF32, fp32-parity) or ``"fp32_simt"`` (FFMA); the optional bf16 mode is not built.
+    ``"fp32"`` (tcgen05 3xTF32, fp32-parity, the default), ``"fp32_simt"`` (FFMA checker) or ``"tf32"`` -- the optional
+    reduced-precision mode: one TF32 tensor-core pass on the raw fp32 operands (10-bit mantissa, fp32 accumulation),
+    contract 2e-2 relative on z / log_prob for D <= 64 and n_layers <= 12.  A bf16 mode is not built.
 
     ``fast_param_grads`` (default on): ``loss.backward()`` writes all parameter gradients into one
     persistent flat arena with a single library call and points every ``p.grad`` at its view of that

@@ -689,3 +689,35 @@ def test_zero_conditioning_fast_path(D, C, R, n, H1, B):
     sd64 = fo.cast_state_dict(sd, np.float64)
     ref = fo.flow_forward(sd64, n, x.astype(np.float64), np.zeros((B, R)), eps=1e-5)
     assert rel_err(res[1][0], ref[0]) <= 2e-5
+
+
+@pytest.mark.parametrize("name", ["synth_C2a", "synth_C1a", "synth_C1b", "synth_C3t"])
+def test_reduced_precision_mode_contract(name):
+    """The optional reduced-precision mode (precision="tf32": one TF32 tensor-core pass on the raw fp32 operands):
+    z and log_prob within 2e-2 relative of the float64 reference on the configs inside the stated envelope
+    (D <= 64, n_layers <= 12; BASELINE.json north_star), gradients and the inverse stay usable."""
+    path = [p for p in CASES if os.path.basename(p) == name + ".npz"][0]
+    cfg, sd, x, y, dz, dld, g = load_case(path)
+    assert cfg["D"] <= 64 and cfg["n"] <= 12
+    model = build_model(cfg, sd, "tf32")
+    xt, yt = t(x).requires_grad_(True), t(y).requires_grad_(True)
+    _lib.lib.nf_prof_enable(1)
+    _lib.prof_collect()
+    z, outputs, ld = model(xt, yt)
+    (z * t(dz)).sum().add((ld * t(dld)).sum()).backward()
+    torch.cuda.synchronize()
+    prof = _lib.prof_collect()
+    _lib.lib.nf_prof_enable(0)
+    assert prof["tc_gemm"][2] > 0 and prof["tc_wgrad"][2] > 0     # the tensor-core kernels ran
+    errs = {"z": rel_err(z.detach().cpu().numpy(), g["f64/z"]),
+            "log_dets": rel_err(ld.detach().cpu().numpy(), g["f64/log_dets"]),
+            "dx": rel_err(xt.grad.cpu().numpy(), g["f64/dx"]), "dy": rel_err(yt.grad.cpu().numpy(), g["f64/dy"])}
+    with torch.no_grad():
+        nll = -model.log_prob(t(x), t(y)).mean().item()
+        rev = model.reverse(t(g["f32/z"]), t(y))
+    errs["nll"] = abs(nll - float(g["f64/nll"])) / max(1.0, abs(float(g["f64/nll"])))
+    errs["rev"] = rel_err(rev.cpu().numpy(), g["f64/rev"])
+    print(f"\n[tf32 mode] {name}: " + ", ".join(f"{k} {v:.2e}" for k, v in errs.items()))
+    assert errs["z"] <= 2e-2 and errs["log_dets"] <= 2e-2 and errs["nll"] <= 2e-2, errs
+    assert errs["dx"] <= 1e-1 and errs["dy"] <= 1e-1 and errs["rev"] <= 1e-1, errs
+    assert errs["z"] > 1e-6     # ... and it really is the reduced mode
