@@ -69,8 +69,10 @@ typedef struct NfFlowDesc {
   int32_t n_blocks; /* n_layers                                                         */
   float   ln_eps;   /* 1e-5 (torch nn.LayerNorm) or 1e-6 (flax nn.LayerNorm)            */
   int32_t precision;/* NF_PREC_*                                                        */
-  int32_t reserved;
+  int32_t reserved; /* flags: NF_FLAG_*                                                 */
 } NfFlowDesc;
+/* flax nn.LayerNorm (nf.py:94-104) computes var = max(0, E[x^2] - E[x]^2); torch nn.LayerNorm the centred variance */
+#define NF_FLAG_LN_FAST_VARIANCE 1
 
 /* Per-block slots of the flat parameter arena, in order.  Offsets are in floats, every slot
  * starts on a multiple of 4 floats.  Net 0 is `t`, net 1 is `s` (state_dict order). */
@@ -221,6 +223,11 @@ NF_API int nf_linear_wgrad(const float* dY, int64_t lddy, const float* X, int64_
  *   nf_adamw_step     one torch.optim.AdamW step (torch_nfbc_ant.py:150-155) over the flat parameter arena in one
  *                     launch; exp_avg / exp_avg_sq are arenas of the same layout, slot_mask (n_blocks * NF_P_SLOTS
  *                     bytes on the device, 1 = update) leaves P / P_inv and frozen parameters alone; step >= 1. */
+/*   nf_noise_augment  out[i] = x[i] + std * N(0, 1): the training-time noise augmentation of torch_nfbc_ant.py:264-265 as
+ *                     one kernel (counter-based Philox4x32-10 + Box-Muller; the normal at index i is a pure function of
+ *                     (seed, offset + i / 4, i % 4), so a caller advances `offset` by ceil(n / 4) per call); out may
+ *                     alias x. */
+NF_API int nf_noise_augment(const float* x, int64_t n, float std_, uint64_t seed, uint64_t offset, float* out, void* stream);
 NF_API int nf_nll_forward(const float* z, const float* logdet, int64_t B, int32_t D, float* loss, void* stream);
 NF_API int nf_nll_cotangents(const float* z, const float* g, int64_t B, int32_t D, float* dz, float* dld, void* stream);
 NF_API int nf_adamw_step(const NfFlowDesc* desc, float* params, const float* grads, float* exp_avg, float* exp_avg_sq,

@@ -77,6 +77,7 @@ def _load():
         "nf_prof_enable": (c_int, [c_int]),
         "nf_prof_collect": (c_int, [POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(c_int64), c_int]),
         "nf_launch_count": (c_int64, [c_int]),
+        "nf_noise_augment": (c_int, [fp, i64, c_float, ctypes.c_uint64, ctypes.c_uint64, fp, vp]),
         "nf_nll_forward": (c_int, [fp, fp, i64, c_int32, fp, vp]),
         "nf_nll_cotangents": (c_int, [fp, fp, i64, c_int32, fp, fp, vp]),
         "nf_adamw_step": (c_int, [D, fp, fp, fp, fp, fp, c_float, c_float, c_float, c_float, c_float, i64, vp]),
@@ -107,8 +108,11 @@ def check(rc: int, what: str):
         raise NfError(f"{what} failed (code {rc}): {msg}")
 
 
-def make_desc(D, C, H1, R, n, ln_eps, precision) -> NfFlowDesc:
-    return NfFlowDesc(int(D), int(C), int(H1), int(R), int(n), float(ln_eps), int(precision), 0)
+NF_FLAG_LN_FAST_VARIANCE = 1
+
+
+def make_desc(D, C, H1, R, n, ln_eps, precision, flags=0) -> NfFlowDesc:
+    return NfFlowDesc(int(D), int(C), int(H1), int(R), int(n), float(ln_eps), int(precision), int(flags))
 
 
 def param_layout(desc: NfFlowDesc) -> NfParamLayout:

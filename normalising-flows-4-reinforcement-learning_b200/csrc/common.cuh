@@ -123,6 +123,7 @@ struct Dims {
   int D, C, H1, R, n, dc, dt, K1;
   float eps;
   int prec;
+  int fastvar;   // NF_FLAG_LN_FAST_VARIANCE
 };
 
 static inline Dims dims_of(const NfFlowDesc* d) {
@@ -133,6 +134,7 @@ static inline Dims dims_of(const NfFlowDesc* d) {
   m.K1 = m.dc + d->R;
   m.eps = d->ln_eps;
   m.prec = d->precision;
+  m.fastvar = (d->reserved & NF_FLAG_LN_FAST_VARIANCE) ? 1 : 0;
   return m;
 }
 

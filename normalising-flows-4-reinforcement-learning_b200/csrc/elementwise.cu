@@ -42,10 +42,11 @@ __global__ void __launch_bounds__(256) k_lrelu_ln_fwd(LnFwdP p) {
   for (int c = lane; c < N; c += 32) {
     float v = u[c] + (bias ? bias[c] : 0.f);
     v = v > 0.f ? v : kLeakySlope * v;
-    const float d = v - mean;
+    const float d = p.fast_var ? v : v - mean;
     sq = fmaf(d, d, sq);
   }
-  const float var = warp_sum(sq) / (float)N;
+  float var = warp_sum(sq) / (float)N;
+  if (p.fast_var) var = fmaxf(var - mean * mean, 0.f);   // flax: E[x^2] - E[x]^2, clipped at 0
   const float rstd = rsqrtf(var + p.eps);
   uint32_t* mask = p.mask ? p.mask + net * p.mask_net + row * p.mw : nullptr;
   for (int c0 = 0; c0 < N; c0 += 32) {
@@ -108,11 +109,14 @@ __global__ void __launch_bounds__(256) k_lrelu_ln_fwd_v4(LnFwdP p) {
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
     if (4 * (lane + 32 * k) < N) {
-      const float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, d = v[k].w - mean;
+      const float sh = p.fast_var ? 0.f : mean;
+      const float a = v[k].x - sh, b = v[k].y - sh, c = v[k].z - sh, d = v[k].w - sh;
       sq += (a * a + b * b) + (c * c + d * d);
     }
   }
-  const float rstd = rsqrtf(warp_sum(sq) / (float)N + p.eps);
+  float var = warp_sum(sq) / (float)N;
+  if (p.fast_var) var = fmaxf(var - mean * mean, 0.f);   // flax: E[x^2] - E[x]^2, clipped at 0
+  const float rstd = rsqrtf(var + p.eps);
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
     const int c4 = lane + 32 * k;
@@ -915,6 +919,66 @@ int nll_cotangents(const float* z, const float* g, long long B, int D, float* dz
   if (B <= 0) return 0;
   const long long blocks = std::min<long long>(cdiv(B * D, 256), 148 * 8);
   NF_LAUNCH((k_nll_cot), (unsigned)blocks, 256, 0, st, z, g, B, D, dz, dld);
+  NF_LAUNCHED();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// noise augmentation  out = x + std * N(0, 1)   (torch_nfbc_ant.py:264-265: naction + 0.1 * randn_like(naction))
+// ------------------------------------------------------------------------------------------
+// Counter-based Philox4x32-10 (Salmon et al. 2011; the generator behind torch.randn on CUDA): element group g = i / 4
+// uses counter (offset + g) and key `seed`, so the stream is a pure function of (seed, offset, index) -- independent of
+// the grid -- and a training loop advances `offset` by the number of groups it consumed.  Four uniforms -> two
+// Box-Muller pairs -> four normals, one 128-bit load and store per thread.
+namespace {
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, c[0]), lo0 = M0 * c[0];
+    const uint32_t hi1 = __umulhi(M1, c[2]), lo1 = M1 * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+    c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+    k0 += W0; k1 += W1;
+  }
+}
+__device__ __forceinline__ float u01(uint32_t r) { return (float)(r >> 8) * (1.0f / 16777216.0f) + (0.5f / 16777216.0f); }
+
+__global__ void __launch_bounds__(256) k_noise_augment(const float* __restrict__ x, long long n, float std_,
+                                                       unsigned long long seed, unsigned long long offset,
+                                                       float* __restrict__ out) {
+  NF_PDL_ENTRY();
+  const long long groups = (n + 3) >> 2;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (long long)gridDim.x * blockDim.x) {
+    const unsigned long long ctr = offset + (unsigned long long)g;
+    uint32_t c[4] = {(uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    float z[4];
+    {
+      const float r0 = sqrtf(-2.0f * __logf(u01(c[0]))), r1 = sqrtf(-2.0f * __logf(u01(c[2])));
+      float s0, c0, s1, c1;
+      __sincosf(6.2831853071795865f * u01(c[1]), &s0, &c0);
+      __sincosf(6.2831853071795865f * u01(c[3]), &s1, &c1);
+      z[0] = r0 * c0; z[1] = r0 * s0; z[2] = r1 * c1; z[3] = r1 * s1;
+    }
+    const long long i = g << 2;
+    if (i + 3 < n) {
+      const float4 v = *reinterpret_cast<const float4*>(x + i);
+      *reinterpret_cast<float4*>(out + i) = make_float4(fmaf(std_, z[0], v.x), fmaf(std_, z[1], v.y), fmaf(std_, z[2], v.z),
+                                                        fmaf(std_, z[3], v.w));
+    } else {
+      for (int k = 0; k < 4 && i + k < n; ++k) out[i + k] = fmaf(std_, z[k], x[i + k]);
+    }
+  }
+}
+}  // namespace
+
+int noise_augment(const float* x, long long n, float std_, unsigned long long seed, unsigned long long offset, float* out,
+                  cudaStream_t st) {
+  if (n <= 0) return 0;
+  const long long blocks = std::min<long long>(cdiv(cdiv(n, 4), 256), 148 * 8);
+  ProfScope prof(st, PROF_AFFINE, 8.0 * n);
+  NF_LAUNCH((k_noise_augment), (unsigned)blocks, 256, 0, st, x, n, std_, seed, offset, out);
   NF_LAUNCHED();
   return 0;
 }

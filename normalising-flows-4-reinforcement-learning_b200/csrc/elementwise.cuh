@@ -16,6 +16,7 @@ struct LnFwdP {
   int mw, N, nets;
   long long B;
   float eps;
+  int fast_var;   // flax nn.LayerNorm: var = max(0, E[x^2] - E[x]^2) instead of the centred two-pass variance
 };
 int lrelu_ln_fwd(const LnFwdP& p, cudaStream_t st);
 
@@ -65,6 +66,8 @@ int nll_forward(const float* z, const float* logdet, long long B, int D, float* 
 int nll_cotangents(const float* z, const float* g, long long B, int D, float* dz, float* dld, cudaStream_t st);
 // one AdamW step (torch.optim.AdamW semantics, torch_nfbc_ant.py:150-155) over the flat parameter arena; slot_mask
 // (n_blocks * NF_P_SLOTS bytes on the device) selects the trainable slots
+int noise_augment(const float* x, long long n, float std_, unsigned long long seed, unsigned long long offset, float* out,
+                  cudaStream_t st);   // out = x + std * N(0, 1), Philox4x32-10 keyed by (seed, offset + i / 4)
 struct AdamWP {
   float* params; const float* grads; float* exp_avg; float* exp_avg_sq;
   const unsigned char* slot_mask;

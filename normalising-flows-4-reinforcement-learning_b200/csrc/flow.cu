@@ -336,7 +336,7 @@ static int conditioners(const Dims& m, const NfParamLayout& pl, const PackedLayo
     if (m.prec == NF_PREC_TF32) { g.passes = 1; g.raw_hi = 1; g.B0hi = g.B0lo = g.B1hi = g.B1lo = nullptr; }
     TcGemmP f = g;
     f.C = xh; f.ldc = N; f.sC = xh_net; f.bias = bias; f.sBias = bias_net;
-    f.epi.kind = TC_EPI_LN_FWD; f.epi.eps = m.eps;
+    f.epi.kind = TC_EPI_LN_FWD; f.epi.eps = m.eps; f.epi.fast_var = m.fastvar;
     f.epi.rstd = r; f.epi.sRstd = r_net; f.epi.mask = mk; f.epi.sMask = m_net; f.epi.mw = mk ? mw : 0;
     if (prec_tc(m.prec) && (g.K0 + g.K1) >= 32 && tc_gemm_epi_supported(f)) {
       if (tl && tc_gemm_tail_supported(f, tl->D)) {
@@ -360,7 +360,7 @@ static int conditioners(const Dims& m, const NfParamLayout& pl, const PackedLayo
     p.xh = xh; p.xh_net = xh_net;
     p.rstd = r; p.rstd_net = r_net;
     p.mask = mk; p.mask_net = m_net; p.mw = mw;
-    p.N = N; p.nets = 2; p.B = B; p.eps = m.eps;
+    p.N = N; p.nets = 2; p.B = B; p.eps = m.eps; p.fast_var = m.fastvar;
     return lrelu_ln_fwd(p, st);
   };
   {  // layer 1: [x_cond | y] W1^T + b1
@@ -403,7 +403,7 @@ static bool stack_params(const Dims& m, const NfParamLayout& pl, const PackedLay
   const int mode = option(NF_OPT_STACK);
   if (mode == 0 || m.prec != NF_PREC_TF32X3 || m.H1 != m.C || !kl.hi_off) return false;
   StackP p;
-  p.B = B; p.D = m.D; p.H = m.C; p.R = m.R; p.n = m.n; p.eps = m.eps;
+  p.B = B; p.D = m.D; p.H = m.C; p.R = m.R; p.n = m.n; p.eps = m.eps; p.fast_var = m.fastvar;
   p.raw_hi = (m.dc + m.R >= 512 || m.C >= 512) ? 0 : 1;
   p.W1p = packed + kl.net0 + kl.W1p; p.K1p = kl.K1p; p.dcp = kl.dcp;
   p.W2f = packed + kl.net0 + kl.W2f;
@@ -1527,6 +1527,12 @@ int nf_nll_cotangents(const float* z, const float* g, int64_t B, int32_t D, floa
   NF_CHECK_ARG(D >= 1 && B >= 0, NF_E_BADARG, "bad shape B=%lld D=%d", (long long)B, D);
   NF_TRY(check_ptr(z, "z", B > 0)); NF_TRY(check_ptr(dz, "dz", B > 0)); NF_TRY(check_ptr(dld, "dld", B > 0));
   return nll_cotangents(z, g, B, D, dz, dld, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int nf_noise_augment(const float* x, int64_t n, float std_, uint64_t seed, uint64_t offset, float* out, void* stream) {
+  NF_CHECK_ARG(n >= 0, NF_E_BADARG, "n=%lld out of range", (long long)n);
+  NF_TRY(check_ptr(x, "x", n > 0)); NF_TRY(check_ptr(out, "out", n > 0));
+  return noise_augment(x, n, std_, seed, offset, out, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int nf_adamw_step(const NfFlowDesc* desc, float* params, const float* grads, float* exp_avg, float* exp_avg_sq,

@@ -33,7 +33,7 @@ constexpr uint32_t A_BASE = (NACC + 1) * BN;      // first TMEM column of the A 
 constexpr uint32_t TMEM_COLS = 512;
 
 struct StackArgs {
-  int M, D, dc, dt, H, R, n, inverse, raw_hi, ncl, xh_slots;
+  int M, D, dc, dt, H, R, n, inverse, raw_hi, ncl, xh_slots, fast_var;
   float eps;
   const float* b1; long long b1_net, b1_blk;
   const float* b2f; const float* W3f; const float* b3f; const float* Wmat; long long w_net, w_blk;
@@ -346,8 +346,9 @@ k_flow_stack(const __grid_constant__ CUtensorMap mX, const __grid_constant__ CUt
       }
       const float p0 = sum * (1.0f / CW);
       float p1 = 0.f;
+      const float sh = a.fast_var ? 0.f : p0;
 #pragma unroll
-      for (int c = 0; c < CW; ++c) { const float d = v[c] - p0; p1 = fmaf(d, d, p1); }
+      for (int c = 0; c < CW; ++c) { const float d = v[c] - sh; p1 = fmaf(d, d, p1); }
       {
         const uint32_t slot = smem_u32(&xchg[(my_rank * NSG + gq) * 128 + rit]);
         const uint32_t xb = smem_u32(xbar);
@@ -363,9 +364,11 @@ k_flow_stack(const __grid_constant__ CUtensorMap mX, const __grid_constant__ CUt
       for (int pr = 0; pr < ncl * NSG; ++pr) {
         const float2 sx = xchg[pr * 128 + rit];
         const float d = sx.x - mean;
-        m2 += sx.y + (float)CW * d * d;
+        m2 += a.fast_var ? sx.y : sx.y + (float)CW * d * d;
       }
-      const float rstd = rsqrtf(m2 / (float)(ncl * BN) + a.eps);
+      float var = m2 / (float)(ncl * BN);
+      if (a.fast_var) var = fmaxf(var - mean * mean, 0.f);
+      const float rstd = rsqrtf(var + a.eps);
       const bool tail = phase == 1;
       const bool store_c = phase == 0 || a.store_xh2;
       float part[4] = {0.f, 0.f, 0.f, 0.f};
@@ -546,7 +549,7 @@ int launch_stack(const StackP& p, cudaStream_t st) {
   NF_TRY(tc_make_map4(&mXh2_st, p.xh2, H, B, H, 2, p.xh_net, slots, p.xh_blk, 32, 32, s128));
   StackArgs a{};
   a.M = (int)B; a.D = p.D; a.dc = dc; a.dt = dt; a.H = H; a.R = p.R; a.n = p.n; a.inverse = p.inverse;
-  a.raw_hi = p.raw_hi; a.ncl = H / BN; a.xh_slots = slots; a.eps = p.eps;
+  a.raw_hi = p.raw_hi; a.ncl = H / BN; a.xh_slots = slots; a.eps = p.eps; a.fast_var = p.fast_var;
   a.b1 = p.b1; a.b1_net = p.b1_net; a.b1_blk = p.b1_blk;
   a.b2f = p.b2f; a.W3f = p.W3f; a.b3f = p.b3f; a.Wmat = p.Wmat; a.w_net = p.w_net; a.w_blk = p.w_blk;
   a.cdev = p.cdev; a.cur = p.cur; a.cur_w = p.cur_w; a.ld_cur = p.ld_cur;

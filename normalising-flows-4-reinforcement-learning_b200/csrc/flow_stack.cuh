@@ -20,6 +20,7 @@ struct StackP {
   int D = 0, H = 0, R = 0, n = 0;      // H = H1 = C (the kernel needs equal hidden widths)
   int inverse = 0;
   float eps = 1e-5f;
+  int fast_var = 0;     // flax LayerNorm variance
   int raw_hi = 1;
   // operands (all fp32, 16-byte aligned)
   const float* cur = nullptr; int ld_cur = 0;       // (B, ld_cur) running buffer: forward x W_0 on entry; inverse z on entry

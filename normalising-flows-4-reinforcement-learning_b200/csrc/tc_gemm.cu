@@ -48,6 +48,7 @@ struct KArgs {
   uint32_t* mask; long long sMask; int mw;   // fwd: out, bwd: in; mw words per row
   const float* xh; long long ldxh, sXh;  // bwd: normalised activations of the layer (stash)
   float eps;
+  int fast_var;                          // LayerNorm variance as E[x^2] - E[x]^2 (flax)
   int ncl;                               // CTAs per cluster = N / BN (the cluster spans the whole row)
   long long* dbg;                        // optional: 8 clock64 timestamps per CTA (nf_debug_tc_timeline)
   int tma_store;                         // mC is valid: write the output tile with bulk tensor stores
@@ -503,9 +504,10 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
         }
         p0 = sum * (1.0f / CW);                     // local mean
         float m2 = 0.f;
+        const float sh = a.fast_var ? 0.f : p0;
 #pragma unroll
-        for (int c = 0; c < CW; ++c) { const float d = v[c] - p0; m2 = fmaf(d, d, m2); }
-        p1 = m2;                                    // local centred sum of squares
+        for (int c = 0; c < CW; ++c) { const float d = v[c] - sh; m2 = fmaf(d, d, m2); }
+        p1 = m2;                                    // local centred sum of squares (fast_var: plain sum of squares)
       } else {
         // x_hat tile of this warp's 32 rows -> shared memory with coalesced 128-bit loads (the operand
         // stages are free now); both passes then read the lane's own row from there
@@ -547,9 +549,11 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
         for (int pr = 0; pr < ncl * NSG; ++pr) {
           const float2 s = xchg[pr * 128 + rit];
           const float d = s.x - mean;
-          m2 += s.y + (float)CW * d * d;
+          m2 += a.fast_var ? s.y : s.y + (float)CW * d * d;
         }
-        const float rstd = rsqrtf(m2 / (float)(ncl * BN) + a.eps);
+        float var = m2 / (float)(ncl * BN);
+        if (a.fast_var) var = fmaxf(var - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + a.eps);
         // fused tail: this CTA's slice of the folded last Linear, W3f[net][i][n0 .. n0 + BN), in shared memory
         const int dt = a.t_D >> 1;
         float* sW3 = reinterpret_cast<float*>(smem + 160 * 1024);          // [4][BN]
@@ -951,7 +955,7 @@ int launch_epi(const TcGemmP& p, cudaStream_t st) {
   a.dbg = g_tc_dbg;
   a.nacc = pick_nacc();
   a.rstd = p.epi.rstd; a.sRstd = p.epi.sRstd; a.mask = p.epi.mask; a.sMask = p.epi.sMask; a.mw = p.epi.mw;
-  a.xh = p.epi.xh; a.ldxh = p.epi.ldxh; a.sXh = p.epi.sXh; a.eps = p.epi.eps;
+  a.xh = p.epi.xh; a.ldxh = p.epi.ldxh; a.sXh = p.epi.sXh; a.eps = p.epi.eps; a.fast_var = p.epi.fast_var;
   a.ncl = p.N / BN;
   const TcEpi::Tail& t = p.epi.tail;
   a.tail = (EPI == EPI_LN_FWD && t.on) ? 1 : 0;

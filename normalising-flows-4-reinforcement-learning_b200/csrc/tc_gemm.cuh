@@ -20,6 +20,7 @@ struct TcEpi {
   uint32_t* mask = nullptr; long long sMask = 0; int mw = 0;
   const float* xh = nullptr; long long ldxh = 0, sXh = 0;
   float eps = 1e-5f;
+  int fast_var = 0;   // TC_EPI_LN_FWD: flax variance E[x^2] - E[x]^2 (see LnFwdP)
   // TC_EPI_LN_FWD only: finish the flow block inside the same kernel (see tc_gemm_tail_supported).  Same
   // contract as TailP / row_tail2 (rowfused.cuh); store_c = 0 skips writing C (x_hat) altogether.
   struct Tail {

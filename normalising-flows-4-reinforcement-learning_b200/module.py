@@ -189,7 +189,9 @@ class _Flow(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, model: "RealNVP", fast: bool, nodes, x, y, *params):
-        z, logdet, outs, stash, packed, slot = model._run_forward(x, y, True)
+        z, logdet, outs, stash, packed, slot = model._run_forward(x, y, True, want_outputs=model.return_outputs)
+        if outs is None:
+            outs = z.new_zeros(())
         ctx.model = model
         ctx.fast = fast
         ctx.nodes = nodes
@@ -326,7 +328,9 @@ class RealNVP(nn.Module):
 
     Extra keyword arguments select the flax twin's semantics
     (/root/reference/unsupservised-gcrl/nf.py): ``first_hidden=channels+cond_channels`` (:94,101),
-    ``ln_eps=1e-6`` (flax LayerNorm default), and ``precision``:
+    ``ln_eps=1e-6`` (flax LayerNorm default), ``ln_fast_variance=True`` (flax computes the LayerNorm variance as
+    ``max(0, E[x^2] - E[x]^2)``), ``return_outputs=False`` (``forward`` returns the 2-tuple ``(z, log_dets)`` of
+    nf.py:174-179 and no per-block outputs are materialised), and ``precision``:
     ``"fp32"`` (tcgen05 3xTF32, fp32-parity, the default), ``"fp32_simt"`` (FFMA checker) or ``"tf32"`` -- the optional
     reduced-precision mode: one TF32 tensor-core pass on the raw fp32 operands (10-bit mantissa, fp32 accumulation),
     contract 2e-2 relative on z / log_prob for D <= 64 and n_layers <= 12.  A bf16 mode is not built.
@@ -341,9 +345,11 @@ class RealNVP(nn.Module):
 
     def __init__(self, in_channels, channels, cond_channels, n_layers, prior, *,
                  first_hidden: Optional[int] = None, ln_eps: float = 1e-5, precision: str = "fp32",
-                 fast_param_grads: bool = True):
+                 fast_param_grads: bool = True, ln_fast_variance: bool = False, return_outputs: bool = True):
         super().__init__()
         self.fast_param_grads = bool(fast_param_grads)
+        self.ln_fast_variance = bool(ln_fast_variance)
+        self.return_outputs = bool(return_outputs)
         self.in_channels = int(in_channels)
         self.channels = int(channels)
         self.cond_channels = int(cond_channels)
@@ -358,7 +364,8 @@ class RealNVP(nn.Module):
         self.prior = prior
 
         self._desc = _lib.make_desc(self.in_channels, self.channels, self.first_hidden, self.cond_channels,
-                                    self.n_layers, self.ln_eps, _lib.PREC[precision])
+                                    self.n_layers, self.ln_eps, _lib.PREC[precision],
+                                    _lib.NF_FLAG_LN_FAST_VARIANCE if self.ln_fast_variance else 0)
         self._layout = _lib.param_layout(self._desc)
         self._flat: Optional[torch.Tensor] = None
         self._packed: Optional[torch.Tensor] = None
@@ -374,6 +381,7 @@ class RealNVP(nn.Module):
         self._dp_world = 1
         self._dp_avg = False
         self._dp_in_graph = False
+        self._noise_offset = {}
         self._flatten()
         self.register_load_state_dict_post_hook(lambda module, keys: module._flatten())
 
@@ -721,7 +729,9 @@ class RealNVP(nn.Module):
             else:
                 z, logdet, outs = _Flow.apply(self, False, _accumulate_nodes(params), x, y, *params)
         else:
-            z, logdet, outs, _, _, _ = self._run_forward(x, y, False)
+            z, logdet, outs, _, _, _ = self._run_forward(x, y, False, want_outputs=self.return_outputs)
+        if not self.return_outputs:
+            return z, logdet                     # flax signature (nf.py:174-179)
         return z, list(outs.unbind(0)), logdet
 
     def _run_inverse(self, x, y, want_logdet, want_seq=False):
@@ -771,13 +781,34 @@ class RealNVP(nn.Module):
     def log_prob(self, x, y=None):
         """log N(z; 0, I) + log_dets -- what the callers assemble from ``prior.log_prob(z) + logdets``
         (torch_nfbc_ant.py:269) for the standard-normal prior, without the O(D^2) Mahalanobis path."""
-        z, _, logdet = self.forward(x, y)
+        res = self.forward(x, y)
+        z, logdet = res[0], res[-1]
         return -0.5 * (z * z).sum(dim=1) - 0.5 * self.in_channels * math.log(2.0 * math.pi) + logdet
 
-    def nll(self, x, y=None):
+    def augment(self, x, noise_std, seed=0):
+        """``x + noise_std * randn_like(x)`` -- the training-time noise augmentation of torch_nfbc_ant.py:264-265 -- as
+        one library kernel (nf_noise_augment: counter-based Philox4x32-10 + Box-Muller).  The module keeps a running
+        counter, so successive calls with the same ``seed`` draw fresh noise; the stream is reproducible from
+        (seed, call order).  Not differentiated through (the reference adds the noise to the data, outside autograd)."""
+        if not x.is_cuda or x.dtype != torch.float32:
+            raise RuntimeError("nf_b200.RealNVP.augment needs a float32 CUDA tensor")
+        xd = _dense(x.detach())
+        out = torch.empty_like(xd)
+        n = xd.numel()
+        off = self._noise_offset.get(int(seed), 0)
+        with _on(xd.device):
+            _lib.check(lib.nf_noise_augment(xd.data_ptr(), n, float(noise_std), int(seed) & (2**64 - 1), off,
+                                            out.data_ptr(), self._stream(xd.device)), "nf_noise_augment")
+        self._noise_offset[int(seed)] = off + (n + 3) // 4
+        return out
+
+    def nll(self, x, y=None, noise_std=0.0, seed=0):
         """-mean(log N(z; 0, I) + log_dets): the training loss of torch_nfbc_ant.py:269-270 for the standard-normal
         prior, with the loss reduction and its cotangents fused into two library kernels.  Parameter gradients
-        go to the flat gradient arena (``fast_param_grads`` semantics)."""
+        go to the flat gradient arena (``fast_param_grads`` semantics).  ``noise_std > 0`` first applies the
+        reference's noise augmentation (:264-265) with the library's Philox kernel (``augment``)."""
+        if noise_std:
+            x = self.augment(x, noise_std, seed)
         self._check_inputs(x, y)
         params = [p for p in self._tparams if p.requires_grad] if torch.is_grad_enabled() else []
         if torch.is_grad_enabled() and (x.requires_grad or (y is not None and y.requires_grad) or params):

@@ -58,10 +58,20 @@ def leaky_relu(u):
     return np.where(u > 0, u, LEAKY_SLOPE * u)
 
 
+# flax nn.LayerNorm (unsupservised-gcrl/nf.py:94-104; flax 0.8.3 default use_fast_variance=True) computes the variance
+# as max(0, E[x^2] - E[x]^2); torch nn.LayerNorm (torch_fcnf.py:75) the centred form.  The two are the same function
+# (and have the same derivative); they differ in rounding only.  Tests switch this flag to check the product's
+# `ln_fast_variance` option against the matching formula (parity unpinned: no jax in this image).
+LN_FAST_VARIANCE = False
+
+
 def layer_norm_stats(v, eps):
-    """nn.LayerNorm(C) statistics: biased variance over the last dim (torch_fcnf.py:75)."""
+    """mean and 1/sqrt(var + eps) over the last axis (biased variance, as both frameworks use)."""
     mu = v.mean(axis=1, keepdims=True)
-    var = ((v - mu) ** 2).mean(axis=1, keepdims=True)
+    if LN_FAST_VARIANCE:
+        var = np.maximum((v * v).mean(axis=1, keepdims=True) - mu * mu, 0)
+    else:
+        var = ((v - mu) ** 2).mean(axis=1, keepdims=True)
     rstd = 1.0 / np.sqrt(var + v.dtype.type(eps))
     return mu, rstd
 

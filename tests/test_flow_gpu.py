@@ -723,3 +723,67 @@ def test_reduced_precision_mode_contract(name):
     # still for the 64-dimensional flow whose reference float32 inverse is itself only good to ~1e-3)
     assert errs["dx"] <= 1e-1 and errs["dy"] <= 1e-1 and errs["rev"] <= (1e-1 if cfg["D"] <= 9 else 5e-1), errs
     assert errs["z"] > 1e-6     # ... and it really is the reduced mode
+
+
+def test_noise_augmentation_kernel_matches_the_philox_oracle():
+    """x + 0.1 * randn (torch_nfbc_ant.py:264-265) with the library's Philox4x32-10 kernel: the normals are the ones
+    the known-answer-pinned restatement (oracle/philox.py) produces for (seed, offset), odd sizes included; the
+    module-level call advances the counter between calls."""
+    from oracle import philox
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for n, seed, offset in [(4096 * 8, 3, 0), (1001, 2 ** 40 + 5, 123456789), (3, 9, 2 ** 33)]:
+        x = torch.linspace(-1, 1, n, device=dev())
+        out = torch.empty_like(x)
+        _lib.check(_lib.lib.nf_noise_augment(x.data_ptr(), n, 0.1, seed, offset, out.data_ptr(), st), "nf_noise_augment")
+        z = ((out.double() - x.double()) / 0.1).cpu().numpy()
+        ref = philox.normals(n, seed, offset)
+        assert np.max(np.abs(z - ref)) <= 2e-4, (n, np.max(np.abs(z - ref)))    # fast log / sincos + the fp32 add
+    model = build_model(dict(D=8, C=32, R=16, n=2, B=0), synth.make_state_dict(8, 32, 16, 2, seed=1), "fp32")
+    x = torch.zeros(512, 8, device=dev())
+    a, b = model.augment(x, 0.1, seed=11), model.augment(x, 0.1, seed=11)
+    assert not torch.equal(a, b)                                    # fresh noise per call ...
+    ref = philox.normals(2 * 4096, 11)
+    assert np.max(np.abs(torch.cat([a, b]).reshape(-1).double().cpu().numpy() / 0.1 - ref)) <= 2e-4   # ... one stream
+    assert abs(float(a.std()) / 0.1 - 1.0) < 0.05
+    # the fused-loss entry point takes the augmentation as an argument
+    y = torch.zeros(512, 16, device=dev())
+    l0, l1 = model.nll(x, y), model.nll(x, y, noise_std=0.1, seed=11)
+    assert torch.isfinite(l1) and float(l0) != float(l1)
+
+
+@pytest.mark.parametrize("D,C,R,n,B", [(2, 256, 64, 2, 300), (8, 64, 16, 3, 50), (2, 192, 64, 2, 1000)])
+def test_flax_semantics_flags(D, C, R, n, B):
+    """The flax twin (unsupservised-gcrl/nf.py): first hidden width C + R, eps 1e-6, LayerNorm variance as
+    max(0, E[x^2] - E[x]^2), forward -> (z, log_dets), reverse -> (x, log_det).  Parity unpinned upstream (no jax in the
+    image): checked against the numpy oracle with the matching variance formula."""
+    H1, eps = C + R, 1e-6
+    sd = synth.make_state_dict(D, C, R, n, seed=51, H1=H1)
+    x, y, _ = synth.make_safe_inputs(sd, n, B, D, R, seed=52, eps=eps)
+    dz, dld = synth.make_cotangents(B, D, seed=53)
+    m = nf_b200.RealNVP(D, C, R, n, None, first_hidden=H1, ln_eps=eps, ln_fast_variance=True, return_outputs=False)
+    m.load_state_dict({k: torch.tensor(v) for k, v in sd.items()})
+    m = m.to(dev())
+    xt, yt = t(x).requires_grad_(True), t(y).requires_grad_(True)
+    res = m(xt, yt)
+    assert isinstance(res, tuple) and len(res) == 2            # nf.py:174-179
+    z, ld = res
+    (z * t(dz)).sum().add((ld * t(dld)).sum()).backward()
+    sd64 = fo.cast_state_dict(sd, np.float64)
+    fo.LN_FAST_VARIANCE = True
+    try:
+        ref = fo.flow_backward(sd64, n, x.astype(np.float64), y.astype(np.float64), dz.astype(np.float64),
+                               dld.astype(np.float64), eps=eps)
+        rx, rld = fo.flow_reverse(sd64, n, ref["z"], y.astype(np.float64), eps=eps, return_logdet=True)
+    finally:
+        fo.LN_FAST_VARIANCE = False
+    assert rel_err(z.detach().cpu().numpy(), ref["z"]) <= 2e-5
+    assert rel_err(ld.detach().cpu().numpy(), ref["log_dets"]) <= 2e-5
+    assert rel_err(xt.grad.cpu().numpy(), ref["dx"]) <= 2e-5 and rel_err(yt.grad.cpu().numpy(), ref["dy"]) <= 2e-5
+    for k, p in m.named_parameters():
+        if p.requires_grad:
+            assert rel_err(p.grad.cpu().numpy(), ref["grads"][k]) <= 5e-5, k
+    with torch.no_grad():
+        xr, rl = m.reverse(z.detach(), t(y), return_logdet=True)   # nf.py:131-148: reverse returns its log-det
+        z2, ld2 = m(t(x), t(y))
+    assert rel_err(xr.cpu().numpy(), rx) <= 1e-4 and rel_err(rl.cpu().numpy(), rld) <= 1e-4
+    assert torch.allclose(z2, z.detach(), atol=1e-6) and torch.allclose(ld2, ld.detach(), atol=1e-5)
