@@ -151,6 +151,7 @@ void param_layout(const Dims& m, NfParamLayout* out);
 // After all blocks: logdet_c (n floats, sum log|s| per block) and logdet_total (1 float).
 struct PackedLayout {
   int64_t W, Winv, Lh, Uh, PL;
+  int64_t WT, WinvT;     // transposes of W / W^-1: the K-major B operands of x @ W and xp @ W^-1 on the tensor cores
   int64_t net0;          // offset of net t tables inside a block
   int64_t W2f, b2f, W3f, b3f, W2fT, W1T, W1p;  // offsets inside a net
   int dcp, K1p;  // W1p: (H1, K1p) copy of W1 whose y columns start at the 16-byte aligned column dcp

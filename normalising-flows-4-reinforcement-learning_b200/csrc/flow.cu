@@ -103,6 +103,8 @@ PackedLayout packed_layout(const Dims& m) {
   k.Lh = off; off += DD;
   k.Uh = off; off += DD;
   k.PL = off; off += DD;
+  k.WT = off; off += DD;
+  k.WinvT = off; off += DD;
   k.net0 = off;
   int64_t n = 0;
   k.W2f = n; n += pad4((int64_t)m.C * m.H1);
@@ -303,6 +305,28 @@ int wgrad_tn(int prec, const TcGemmTnP& t0, cudaStream_t st) {
   g.M = t.M; g.N = t.N; g.batch = t.batch;
   g.splitk = pick_splitk(g.M, g.N, t.K, t.batch);
   if (g.splitk == 1) g.accumulate = 1;
+  return simt_gemm(g, st);
+}
+
+// C (B, D) = A (B, D) @ Bk^T with Bk a (D, D) table of the packed block (so its hi / lo copies exist): the
+// invertible-linear matmuls x @ W (Bk = W^T), xp @ W^-1 (Bk = W^-T), dxp @ W^T (Bk = W), g @ W^-T (Bk = W^-1).
+// Wide flows run them on the tensor cores (measured: the FFMA GEMM took 46 us per launch on the D = 400 ant flow,
+// 47 % of its training step); narrow or unaligned ones stay FFMA.
+static int plu_matmul(const Dims& m, const PackedLayout& kl, const float* A, int lda, const float* Bk, float* C, int ldc,
+                      int64_t B, cudaStream_t st) {
+  if (prec_tc(m.prec) && m.D >= 32 && (m.D & 3) == 0 && (lda & 3) == 0 && (ldc & 3) == 0) {
+    TcGemmP t;
+    t.A0 = A; t.lda0 = lda; t.K0 = m.D;
+    t.B0 = Bk; t.ldb0 = m.D;
+    if (kl.hi_off) { t.B0hi = Bk + kl.hi_off; t.B0lo = Bk + kl.lo_off; }
+    t.C = C; t.ldc = ldc; t.M = (int)B; t.N = m.D;
+    t.raw_hi = 0;   // round-to-nearest split: the truncating one biases |z| low by ~1e-5 of the D = 400 log-prob sum
+    return linear_nt(m.prec, t, st);
+  }
+  GemmP g;
+  g.A0 = A; g.lda0 = lda; g.K0 = m.D;
+  g.B0 = Bk; g.ldb0 = m.D; g.transB = 1;
+  g.C = C; g.ldc = ldc; g.M = (int)B; g.N = m.D;
   return simt_gemm(g, st);
 }
 
@@ -522,6 +546,7 @@ int nf_flow_prepare(const NfFlowDesc* desc, const float* params, void* packed_v,
     g.B0 = packed + kl.Uh;
     g.C = packed + kl.W;
     NF_TRY(simt_gemm(g, st));
+    NF_TRY(transpose2d(packed + kl.WT, m.D, kl.block_stride, 0, packed + kl.W, m.D, kl.block_stride, 0, m.D, m.D, m.n, 1, st));
   }
   NF_TRY(fold_ln_affine(params, pl, m, packed, kl, s1));
   // K-major B operands of the data-gradient GEMMs: W2f^T (H1,C) and W1^T (K1,H1), per net and block
@@ -543,6 +568,7 @@ int nf_flow_prepare(const NfFlowDesc* desc, const float* params, void* packed_v,
     g.B0 = params + pl.slot_off[NF_P_PINV]; g.sB0 = pl.block_stride;
     g.C = packed + kl.Winv; g.sC = kl.block_stride;
     NF_TRY(simt_gemm(g, st));
+    NF_TRY(transpose2d(packed + kl.WinvT, m.D, kl.block_stride, 0, packed + kl.Winv, m.D, kl.block_stride, 0, m.D, m.D, m.n, 1, st));
   }
   if (ss) {
     NF_CUDA(cudaEventRecord(ss->done1[0], s1));
@@ -641,13 +667,8 @@ int nf_flow_forward(const NfFlowDesc* desc, const float* params, const void* pac
   for (int i = 0; i < m.n; ++i) {
     const float* pb = params + (int64_t)i * pl.block_stride;
     const float* kb = packed + (int64_t)i * kl.block_stride;
-    if (!fused || i == 0) {  // xp = cur @ W   (torch_fcnf.py:40); fused: done by the previous block's tail
-      GemmP g;
-      g.A0 = cur; g.lda0 = m.D; g.K0 = m.D;
-      g.B0 = kb + kl.W; g.ldb0 = m.D;
-      g.C = w.xp; g.ldc = w.Dp; g.M = (int)B; g.N = m.D;
-      NF_TRY(simt_gemm(g, st));
-    }
+    if (!fused || i == 0)   // xp = cur @ W   (torch_fcnf.py:40); fused: done by the previous block's tail
+      NF_TRY(plu_matmul(m, kl, cur, m.D, kb + kl.WT, w.xp, w.Dp, B, st));
     float *xh1 = w.xh1, *xh2 = w.xh2, *r1 = nullptr, *r2 = nullptr;
     uint32_t *m1 = nullptr, *m2 = nullptr;
     int64_t xh1_net = B * m.H1, xh2_net = B * m.C, r_net = 0, m_net = 0;
@@ -791,11 +812,7 @@ int nf_flow_inverse(const NfFlowDesc* desc, const float* params, const void* pac
     } else {
       NF_TRY(affine_inv(cur, ldcur, w.o + B * m.dt, w.o, kb + kl.net0 + kl.net_stride + kl.b3f, kb + kl.net0 + kl.b3f,
                         packed + kl.logdet_c + i, 0.f, B, m.D, w.xp, w.Dp, logdet, st));
-      GemmP g;
-      g.A0 = w.xp; g.lda0 = w.Dp; g.K0 = m.D;
-      g.B0 = kb + kl.Winv; g.ldb0 = m.D;
-      g.C = next; g.ldc = ldnext; g.M = (int)B; g.N = m.D;
-      NF_TRY(simt_gemm(g, st));
+      NF_TRY(plu_matmul(m, kl, w.xp, w.Dp, kb + kl.WinvT, next, ldnext, B, st));
     }
     if (seq && w.Dp != m.D) NF_TRY(copy2d(seq + (int64_t)(step + 1) * BD, m.D, next, ldnext, B, m.D, st));
     cur = next; ldcur = ldnext;
@@ -1135,21 +1152,14 @@ static int backward_impl(const NfFlowDesc* desc, const float* params, const void
       t.B = B; t.D = m.D; t.H1 = m.H1;
       NF_TRY(row_bwd_tail(t, st));
     } else {
-      if (dn) {  // j. dW = x_in^T dxp
-        GemmP g;
-        g.transA = 1; g.A0 = xin; g.lda0 = m.D; g.K0 = (int)B;
-        g.B0 = wb.dxp; g.ldb0 = m.D;
-        g.C = w.dWs + (int64_t)i * DD; g.ldc = m.D; g.M = m.D; g.N = m.D;
-        g.splitk = pick_splitk(g.M, g.N, B, 1);
-        NF_TRY(simt_gemm(g, st));
+      if (dn) {  // j. dW = x_in^T dxp   (tensor cores for wide flows; dWs was zero-filled)
+        TcGemmTnP g;
+        g.A = xin; g.lda = m.D; g.B = wb.dxp; g.ldb = m.D;
+        g.C = w.dWs + (int64_t)i * DD; g.ldc = m.D; g.M = m.D; g.N = m.D; g.K = B;
+        NF_TRY(wgrad_tn(m.D >= 32 ? m.prec : NF_PREC_FP32_SIMT, g, st));
       }
-      if (dst) {  // k. d x_in = dxp W^T
-        GemmP g;
-        g.A0 = wb.dxp; g.lda0 = m.D; g.K0 = m.D;
-        g.B0 = kb + kl.W; g.ldb0 = m.D; g.transB = 1;
-        g.C = dst; g.ldc = m.D; g.M = (int)B; g.N = m.D;
-        NF_TRY(simt_gemm(g, st));
-      }
+      if (dst)   // k. d x_in = dxp W^T
+        NF_TRY(plu_matmul(m, kl, wb.dxp, m.D, kb + kl.W, dst, m.D, B, st));
     }
     if (dst) { gcur = dst; pp ^= 1; }
   }
@@ -1311,13 +1321,7 @@ int nf_flow_inverse_backward(const NfFlowDesc* desc, const float* params, const 
     const float* sb = stash + sl.blocks + (int64_t)i * sl.block_stride;
     const uint32_t* m1 = reinterpret_cast<const uint32_t*>(sb + sl.m1);
     const uint32_t* m2 = reinterpret_cast<const uint32_t*>(sb + sl.m2);
-    {  // g_xp = g W^-T  -> d0 (scratch)
-      GemmP g;
-      g.A0 = gcur; g.lda0 = m.D; g.K0 = m.D;
-      g.B0 = kb + kl.Winv; g.ldb0 = m.D; g.transB = 1;
-      g.C = w.d0; g.ldc = m.D; g.M = (int)B; g.N = m.D;
-      NF_TRY(simt_gemm(g, st));
-    }
+    NF_TRY(plu_matmul(m, kl, gcur, m.D, kb + kl.Winv, w.d0, m.D, B, st));   // g_xp = g W^-T  -> d0 (scratch)
     if (dn) {  // dW = -x_in^T g_xp
       GemmP g;
       g.transA = 1; g.A0 = xin; g.lda0 = m.D; g.K0 = (int)B;

@@ -42,6 +42,8 @@ def run(name, B, precision, iters=10):
 
 if __name__ == "__main__":
     precs = sys.argv[1].split(",") if len(sys.argv) > 1 else ["fp32_simt"]
+    specs = sys.argv[2:] or ["C2a:4096", "C3:16384", "C4:8192", "C1a:256", "C5:8192"]
     for prec in precs:
-        run("C2a", 4096, prec); run("C3", 16384, prec); run("C4", 8192, prec); run("C1a", 256, prec)
-        run("C5", 8192, prec, iters=3)
+        for spec in specs:
+            name, B = spec.split(":")
+            run(name, int(B), prec, iters=3 if name == "C5" else 10)
