@@ -262,6 +262,46 @@ NF_API int nf_encoder_backward(const NfEncoderDesc* desc, const float* params, c
                                const float* dout, float* dg, float* dparams, void* workspace, int64_t ws_bytes,
                                void* stream);
 
+/* Causal-transformer flow: the model `il-and-cil/torch_nfgcbc.py:27,119` imports from the
+ * absent `utils/torch_networks.py` -- RealNVP(input_dims, channels, rep_dim, head_dim, blocks, layers_per_block, prior),
+ * model(actions (B, A, 1), cond (B, 1, rep)) -> (z, outputs, logdets) (:136-142), model.reverse(z, cond)
+ * (utils/torch_evaluations.py:79-82).  PARITY UNPINNED upstream; the arithmetic is the published TarFlow meta block as
+ * restated in oracle/torch_tarflow.py (the checker): T = A tokens (the conditioning token, then action dimensions
+ * 0 .. A-2), n_layers x [pre-LN causal attention + GELU MLP], token t yields (xa_t, xb_t), z_t = (x_t - xb_t) exp(-xa_t),
+ * logdet = -sum_t xa_t; odd blocks run on the reversed dimension order.  Parameters live in one flat arena
+ * (nf_tarflow_param_layout); forward keeps what backward needs in `stash` (NULL = inference); inverse is the
+ * autoregressive loop over the A dimensions with the per-layer K / V rows cached in the workspace.  x, z, dz, dx are
+ * (B, A); y, dy are (B, R); logdet, dlogdet are (B).  outputs (n_blocks, B, A) is optional.  Conventions as the flow. */
+typedef struct NfTarflowDesc {
+  int32_t A;          /* action dimensions (tokens), 1 .. 32                                  */
+  int32_t C;          /* channels, multiple of 4, <= 1024                                     */
+  int32_t R;          /* rep_dim of the conditioning vector                                   */
+  int32_t head_dim;   /* 32, 64 or 128; divides C                                             */
+  int32_t n_blocks;
+  int32_t n_layers;   /* layers per block                                                     */
+  int32_t expansion;  /* MLP width = expansion * C                                            */
+  float   ln_eps;
+  float   logscale_clamp; /* c > 0: xa = c tanh(raw / c); 0: raw                              */
+  int32_t precision;  /* NF_PREC_FP32_SIMT or NF_PREC_TF32X3                                  */
+} NfTarflowDesc;
+/* offs[22] (floats): block_stride, then offsets inside a block: pos_embed (A, C), proj_in.weight (C), proj_in.bias (C),
+ * cond_proj.weight (C, R), cond_proj.bias (C), layers, layer_stride, then inside a layer: attn.norm.{weight,bias},
+ * attn.qkv.{weight (3C, C),bias}, attn.proj.{weight,bias}, mlp.norm.{weight,bias}, mlp.fc1.{weight (EC, C),bias},
+ * mlp.fc2.{weight (C, EC),bias}; then inside the block again: proj_out.weight (2, C), proj_out.bias (2).
+ * Returns the arena size in floats (< 0 on error). */
+#define NF_TARFLOW_LAYOUT_SLOTS 22
+NF_API int64_t nf_tarflow_param_layout(const NfTarflowDesc* desc, int64_t* offs);
+NF_API int64_t nf_tarflow_stash_bytes(const NfTarflowDesc* desc, int64_t B);
+NF_API int64_t nf_tarflow_workspace_bytes(const NfTarflowDesc* desc, int64_t B);
+NF_API int nf_tarflow_forward(const NfTarflowDesc* desc, const float* params, const float* x, const float* y, int64_t B,
+                              float* z, float* logdet, float* outputs, void* stash, void* workspace, int64_t ws_bytes,
+                              void* stream);
+NF_API int nf_tarflow_inverse(const NfTarflowDesc* desc, const float* params, const float* z, const float* y, int64_t B,
+                              float* x, float* logdet, void* workspace, int64_t ws_bytes, void* stream);
+NF_API int nf_tarflow_backward(const NfTarflowDesc* desc, const float* params, const void* stash, int64_t B,
+                               const float* dz, const float* dlogdet, float* dx, float* dy, float* dparams,
+                               void* workspace, int64_t ws_bytes, void* stream);
+
 /* Optional per-kernel-class timing (CUDA events on the launching stream; off by default).  Kinds:
  * 0 tcgen05 GEMM, 1 tcgen05 weight-gradient GEMM, 2 FFMA GEMM, 3 LeakyReLU+LayerNorm fwd, 4 its backward,
  * 5 affine coupling kernels, 6 parameter-sized kernels, 7 row-fused forward/inverse tail, 8 row-fused
@@ -283,7 +323,9 @@ NF_API int nf_graphs_stats(int64_t* replays, int64_t* captures, int64_t* eager);
  * launch, 1), "streams" (backward on three streams, 1), "tma_store" (bulk-tensor-store epilogues, 1), "nacc" (main
  * accumulators in rotation, 0 = 3), "fused_ln" (LayerNorm in the GEMM epilogue: -1 auto / 0 / 1), "fused_tail"
  * (flow tail in the layer-2 GEMM, 0), "bn256" (256-wide tiles: 0 auto / 1 / 2 never), "stack" (persistent whole-stack
- * forward / inverse kernel: -1 auto / 0 / 1), "whatif" (experiments only: skips backward work, wrong gradients).  Every setting computes the
+ * forward / inverse kernel: -1 auto / 0 / 1), "ride" (bias / x_cond weight gradients
+ * taken along by the weight-gradient GEMMs instead of a column-reduction pass, 1), "whatif" (experiments only: skips
+ * backward work, wrong gradients).  Every setting computes the
  * same function (tests/test_flow_gpu.py::test_options_are_equivalent); setting one clears the launch graphs. */
 NF_API int nf_set_option(const char* name, int value);
 NF_API int nf_get_option(const char* name);

@@ -7,5 +7,7 @@ reference's ``RealNVP`` / ``MetaBlock`` / ``InvertiblePLU`` interface).
 from .module import InvertiblePLU, MetaBlock, RealNVP, count_parameters  # noqa: F401
 from .optim import CosineLRSchedule, FlatAdamW  # noqa: F401
 from .encoder import GEncoder  # noqa: F401
+from .tarflow import TransformerMetaBlock, TransformerRealNVP  # noqa: F401
 
-__all__ = ["RealNVP", "MetaBlock", "InvertiblePLU", "count_parameters", "FlatAdamW", "CosineLRSchedule"]
+__all__ = ["RealNVP", "MetaBlock", "InvertiblePLU", "count_parameters", "FlatAdamW", "CosineLRSchedule", "GEncoder",
+           "TransformerRealNVP", "TransformerMetaBlock"]

@@ -30,6 +30,15 @@ class NfEncoderDesc(Structure):
                 ("ln_eps", c_float), ("precision", c_int32)]
 
 
+class NfTarflowDesc(Structure):
+    _fields_ = [("A", c_int32), ("C", c_int32), ("R", c_int32), ("head_dim", c_int32), ("n_blocks", c_int32),
+                ("n_layers", c_int32), ("expansion", c_int32), ("ln_eps", c_float), ("logscale_clamp", c_float),
+                ("precision", c_int32)]
+
+
+NF_TARFLOW_LAYOUT_SLOTS = 22
+
+
 class NfParamLayout(Structure):
     _fields_ = [("slot_off", c_int64 * NF_P_SLOTS), ("slot_numel", c_int64 * NF_P_SLOTS),
                 ("block_stride", c_int64), ("net_stride", c_int64), ("total", c_int64)]
@@ -47,6 +56,7 @@ def _load():
     lib = ctypes.CDLL(LIB_PATH)
     D = POINTER(NfFlowDesc)
     E = POINTER(NfEncoderDesc)
+    T = POINTER(NfTarflowDesc)
     fp, vp, i64 = c_void_p, c_void_p, c_int64   # device pointers are passed as integers
     sigs = {
         "nf_abi_version": (c_int, []),
@@ -86,6 +96,12 @@ def _load():
         "nf_encoder_workspace_bytes": (c_int64, [E, i64]),
         "nf_encoder_forward": (c_int, [E, fp, fp, i64, fp, vp, vp, i64, vp]),
         "nf_encoder_backward": (c_int, [E, fp, vp, i64, fp, fp, fp, vp, i64, vp]),
+        "nf_tarflow_param_layout": (c_int64, [T, POINTER(c_int64)]),
+        "nf_tarflow_stash_bytes": (c_int64, [T, i64]),
+        "nf_tarflow_workspace_bytes": (c_int64, [T, i64]),
+        "nf_tarflow_forward": (c_int, [T, fp, fp, fp, i64, fp, fp, fp, vp, vp, i64, vp]),
+        "nf_tarflow_inverse": (c_int, [T, fp, fp, fp, i64, fp, fp, vp, i64, vp]),
+        "nf_tarflow_backward": (c_int, [T, fp, vp, i64, fp, fp, fp, fp, fp, vp, i64, vp]),
         "nf_set_option": (c_int, [c_char_p, c_int]),
         "nf_get_option": (c_int, [c_char_p]),
         "nf_graphs_enable": (c_int, [c_int]),

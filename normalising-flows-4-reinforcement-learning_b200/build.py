@@ -39,21 +39,48 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
+    """One object per .cu (compiled in parallel, rebuilt only when the source or a header is newer), then one link."""
     if not force and not needs_build():
         return LIB
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libnf_b200.so")
     extra = os.environ.get("NF_B200_NVCC_FLAGS", "").split()     # experiments (e.g. -DNF_ASLOTS64=4)
-    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB + ".tmp"] + sources()
+    objdir = os.path.join(HERE, "_build")
+    os.makedirs(objdir, exist_ok=True)
+    headers = glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(HERE, "..", "include", "*.h"))
+    hdr_t = max(os.path.getmtime(h) for h in headers)
+    flags = [f for f in NVCC_FLAGS if f != "-shared"] + extra + (["-Xptxas", "-v"] if verbose else [])
+    stamp = os.path.join(objdir, "flags.txt")
+    if not os.path.exists(stamp) or open(stamp).read() != " ".join(flags):
+        force = True
+    jobs = []
+    objs = []
+    for src in sources():
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_t):
+            jobs.append((src, subprocess.Popen([nvcc] + flags + ["-c", "-o", obj, src], stdout=subprocess.PIPE,
+                                               stderr=subprocess.PIPE, text=True)))
+    failed = False
+    for src, proc in jobs:
+        out, err = proc.communicate()
+        if proc.returncode != 0:
+            sys.stderr.write(out + err)
+            failed = True
+        elif verbose:
+            sys.stderr.write(err)
+    if failed:
+        raise RuntimeError("nvcc failed")
+    with open(stamp, "w") as f:
+        f.write(" ".join(flags))
     # No -lcuda: the few driver entry points (cuTensorMapEncodeTiled) are fetched at run time with
     # cudaGetDriverEntryPoint, so the library loads (and exports its symbols) on hosts without a driver.
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    res = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB + ".tmp"] + objs,
+                         capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError("nvcc failed")
-    if verbose:
-        sys.stderr.write(res.stderr)
+        raise RuntimeError("nvcc link failed")
     os.replace(LIB + ".tmp", LIB)
     return LIB
 

@@ -40,6 +40,7 @@ const OptDef kOpts[NF_OPT_COUNT] = {
     {"nacc", "NF_B200_NACC", 0},         {"fused_ln", "NF_B200_FUSED_LN", -1},    {"fused_tail", "NF_B200_FUSED_TAIL", 0},
     {"bn256", "NF_B200_BN256", 0},       {"ts", "NF_B200_TS", 1},                 {"presplit", "NF_B200_PRESPLIT", 1},
     {"stack", "NF_B200_STACK", -1},      {"stack_nsg", "NF_B200_STACK_NSG", 2},   {"whatif", "NF_B200_WHATIF", 0},
+    {"ride", "NF_B200_RIDE", 1},
 };
 int g_opt[NF_OPT_COUNT];
 bool g_opt_init = false;
@@ -290,6 +291,11 @@ int linear_nt(int prec, const TcGemmP& t0, cudaStream_t st) {
   g.sA0 = t.sA0; g.sA1 = t.sA1; g.sB0 = t.sB0; g.sB1 = t.sB1; g.sC = t.sC; g.sBias = t.sBias;
   g.batch = t.batch; g.transB = 1; g.accumulate = t.accumulate;
   return simt_gemm(g, st);
+}
+
+// true when wgrad_tn(prec, t) will run a kernel that can take colsum / skinny reductions along (option "ride")
+bool rides_ok(int prec, const TcGemmTnP& t) {
+  return option(NF_OPT_RIDE) != 0 && prec == NF_PREC_TF32X3 && t.M >= 16 && t.N >= 32 && tc_gemm_tn_rides_supported(t);
 }
 
 // C[z] (M,N) += A[z] (K,M)^T @ B[z] (K,N): weight gradients (reduction over the K = batch rows).
@@ -1018,12 +1024,17 @@ static int backward_impl(const NfFlowDesc* desc, const float* params, const void
         NF_TRY(ln_lrelu_bwd(p, st));
       }
     }
+    bool fold_e = false, fold_h = false;   // batch-row reductions taken by the weight-gradient GEMMs (tc_gemm.cuh)
     if (dn) {  // e. G2 = du2^T x_hat1 -> slot W2
       TcGemmTnP g;
       g.A = wb.gA; g.lda = m.C; g.sA = B * Hm;
       g.B = sb + sl.xh1; g.ldb = m.H1; g.sB = sl.net_stride;
       g.C = dn + pl.slot_off[NF_P_W2]; g.ldc = m.H1; g.sC = pl.net_stride;
       g.M = m.C; g.N = m.H1; g.K = B; g.batch = 2;
+      if (fused && v2 && rides_ok(m.prec, g)) {   // gb2 = colsum(du2) rides on this GEMM's A operand
+        g.colsum = dn + pl.slot_off[NF_P_B2]; g.sColsum = pl.net_stride;
+        fold_e = true;
+      }
       if (!(whatif & 2)) NF_TRY(wgrad_tn(m.prec, g, s1));
     }
     bool ln1_fused = false;
@@ -1072,6 +1083,13 @@ static int backward_impl(const NfFlowDesc* desc, const float* params, const void
       if (has_y) {
         g.B = y; g.ldb = m.R;
         g.C = dn + pl.slot_off[NF_P_W1] + m.dc; g.N = m.R;
+        if (fused && v2 && m.dc <= 16 && rides_ok(m.prec, g)) {
+          // G1[:, :dc] = du1^T x_cond and gb1 = colsum(du1) ride on this GEMM's A operand (du1)
+          g.xc = zi; g.ldxc = m.D; g.nxc = m.dc;
+          g.skinny = dn + pl.slot_off[NF_P_W1]; g.ldsk = m.K1; g.sSk = pl.net_stride;
+          if (ln1_fused) { g.colsum = dn + pl.slot_off[NF_P_B1]; g.sColsum = pl.net_stride; }
+          fold_h = true;
+        }
         if (!(whatif & 2)) NF_TRY(wgrad_tn(m.prec, g, s2));
       }
     }
@@ -1106,8 +1124,10 @@ static int backward_impl(const NfFlowDesc* desc, const float* params, const void
         jobs[0].A = sb + sl.xh2; jobs[0].lda = m.C; jobs[0].sA = sl.net_stride; jobs[0].N = m.C;
         jobs[0].coef = wb.dout; jobs[0].ldcf = m.dt; jobs[0].sCf = B * m.dt; jobs[0].m = m.dt;
         jobs[0].out = dn + pl.slot_off[NF_P_W3]; jobs[0].so_i = m.C; jobs[0].so_c = 1; jobs[0].sOut = pl.net_stride;
-        jobs[0].A2 = wb.gA; jobs[0].lda2 = m.C; jobs[0].sA2 = B * Hm;
-        jobs[0].out2 = dn + pl.slot_off[NF_P_B2]; jobs[0].sOut2 = pl.net_stride;
+        if (!fold_e) {
+          jobs[0].A2 = wb.gA; jobs[0].lda2 = m.C; jobs[0].sA2 = B * Hm;
+          jobs[0].out2 = dn + pl.slot_off[NF_P_B2]; jobs[0].sOut2 = pl.net_stride;
+        }
         jobs[0].out3 = dn + pl.slot_off[NF_P_B3]; jobs[0].sOut3 = pl.net_stride;
         jobs[0].batch = 2;
         // G1[:, :dc] = du1^T x_cond   (x_cond = z[:, :dc])
@@ -1129,10 +1149,11 @@ static int backward_impl(const NfFlowDesc* desc, const float* params, const void
           NF_CUDA(cudaEventRecord(ss->evC, st));
           NF_TRY(col_reduce(&jobs[0], 1, B, s1));
           NF_CUDA(cudaStreamWaitEvent(s1, ss->evC, 0));   // dxp is final after the tail kernel
-          NF_TRY(col_reduce(&jobs[2], 1, B, s1));
-          NF_TRY(col_reduce(&jobs[1], 1, B, s2));
+          NF_TRY(xtg_small(xin, wb.dxp, w.dWs + (int64_t)i * DD, B, m.D, s1));
+          if (!fold_h) NF_TRY(col_reduce(&jobs[1], 1, B, s2));
         } else {
-          NF_TRY(col_reduce(jobs, 3, B, st));
+          NF_TRY(col_reduce(jobs, fold_h ? 1 : 2, B, st));
+          NF_TRY(xtg_small(xin, wb.dxp, w.dWs + (int64_t)i * DD, B, m.D, st));
         }
       }
       if (ss) {

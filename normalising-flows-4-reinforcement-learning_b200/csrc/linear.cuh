@@ -10,4 +10,7 @@ int linear_nt(int prec, const TcGemmP& t, cudaStream_t st);
 // C[z] (M,N) += A[z] (K,M)^T @ B[z] (K,N); C must hold the base value
 int wgrad_tn(int prec, const TcGemmTnP& t, cudaStream_t st);
 
+// true when wgrad_tn(prec, t) runs a kernel whose splitter threads can take t.colsum / t.skinny along (tc_gemm.cuh)
+bool rides_ok(int prec, const TcGemmTnP& t);
+
 }  // namespace nf

@@ -64,5 +64,7 @@ struct ColJob {
 };
 constexpr int kColMaxJobs = 4;
 int col_reduce(const ColJob* jobs, int njobs, long long B, cudaStream_t st);
+// dW (D, D) += X (B, D)^T G (B, D), dense rows, D <= 32
+int xtg_small(const float* X, const float* G, float* dW, long long B, int D, cudaStream_t st);
 
 }  // namespace nf

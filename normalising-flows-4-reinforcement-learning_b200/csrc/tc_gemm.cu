@@ -43,6 +43,13 @@ struct KArgs {
   int accumulate, passes, raw_hi;
   int nacc;                       // main accumulators in rotation, 0 = all NACC (option "nacc")
   int splitk, chunks_per_split;   // MN-major form only
+  // MN-major TS form, blockIdx.y == 0 CTAs only: the splitter threads already hold every element of their A column
+  // (thread = output row m, elements = the batch rows of the stage), so the reductions over the batch rows that share
+  // this operand ride along: colsum[z][m] += sum_k A[k, m] (the bias gradient) and skinny[z][m, j] += sum_k A[k, m] *
+  // xc[k, j], j < nxc <= 16 (the x_cond columns of dW1) -- instead of a separate column-reduction pass over A
+  float* colsum; long long sColsum;
+  const float* xc; long long ldxc; int nxc;
+  float* skinny; long long ldsk, sSk;
   // row-wise epilogues over the cluster (EPI_LN_FWD / EPI_LN_BWD)
   float* rstd; long long sRstd;          // fwd: out (row), bwd: in
   uint32_t* mask; long long sMask; int mw;   // fwd: out, bwd: in; mw words per row
@@ -352,6 +359,11 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
     const int t = (threadIdx.x - 64) & 127;       // 0..127 inside the splitter group
     const int grp = (threadIdx.x - 64) >> 7;      // splitter group: takes the stages with it % NSG == grp
     const bool nosplit = NS || (!TS && a.passes == 1 && a.raw_hi);
+    constexpr int kMaxXc = 16;
+    const bool ride = MNMAJOR && TS && blockIdx.y == 0 && (a.colsum != nullptr || a.skinny != nullptr);
+    float csum = 0.f, sk[kMaxXc];
+#pragma unroll
+    for (int j = 0; j < kMaxXc; ++j) sk[j] = 0.f;
     for (int it = grp; it < nk && !nosplit; it += NSG) {
       const int s = it % STAGES, use = it / STAGES;
       mbar_wait(&full[s], use & 1);
@@ -370,6 +382,25 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
 #pragma unroll
           for (int c = 0; c < 4; ++c)
             av[c] = make_float4(boxf[(4 * c) * 32], boxf[(4 * c + 1) * 32], boxf[(4 * c + 2) * 32], boxf[(4 * c + 3) * 32]);
+          if (ride) {   // rows past K are zero-filled by the TMA, so they add nothing
+            csum += ((av[0].x + av[0].y) + (av[0].z + av[0].w)) + ((av[1].x + av[1].y) + (av[1].z + av[1].w)) +
+                    ((av[2].x + av[2].y) + (av[2].z + av[2].w)) + ((av[3].x + av[3].y) + (av[3].z + av[3].w));
+            if (a.skinny) {
+              const long long k0 = (long long)(kc_begin + it) * BK;
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const float e4[4] = {av[c].x, av[c].y, av[c].z, av[c].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const long long kr = min(k0 + 4 * c + e, (long long)a.K0 - 1);
+                  const float* xr = a.xc + kr * a.ldxc;      // same address in every lane: one broadcast transaction
+#pragma unroll
+                  for (int j = 0; j < kMaxXc; ++j)
+                    if (j < a.nxc) sk[j] = fmaf(e4[e], __ldg(xr + j), sk[j]);
+                }
+              }
+            }
+          }
         } else {
           const int sw = (r >> 1) & 3;                               // SWIZZLE_64B: 16-byte chunk c sits at c ^ ((row >> 1) & 3)
 #pragma unroll
@@ -443,6 +474,18 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&split[s]);
+    }
+    if (ride) {   // one atomic per output element, CTA and splitter group
+      const int mrow = m0 + (warp & 3) * 32 + lane;
+      if (mrow < a.M) {
+        if (a.colsum) atomicAdd(a.colsum + (long long)z * a.sColsum + mrow, csum);
+        if (a.skinny) {
+          float* o = a.skinny + (long long)z * a.sSk + (long long)mrow * a.ldsk;
+#pragma unroll
+          for (int j = 0; j < kMaxXc; ++j)
+            if (j < a.nxc) atomicAdd(o + j, sk[j]);
+        }
+      }
     }
     // epilogue: this warp may only touch TMEM lanes 32*(warp%4) .. +31; thread = one output row
     if (threadIdx.x == 64) NF_TS(3);   // last tile split
@@ -1045,6 +1088,13 @@ int launch_tn(const TcGemmTnP& p, cudaStream_t st) {
   a.splitk = (int)splitk; a.chunks_per_split = (int)per;
   a.dbg = g_tc_dbg;
   a.nacc = pick_nacc();
+  if (p.colsum || p.skinny) {
+    NF_CHECK_ARG(TS, NF_E_UNSUPPORTED, "tc_gemm_tn: column sums ride only on the TS weight-gradient kernels");
+    NF_CHECK_ARG(!p.skinny || (p.xc && p.nxc >= 1 && p.nxc <= 16), NF_E_BADARG, "tc_gemm_tn: 1..16 skinny columns, got %d", p.nxc);
+    a.colsum = p.colsum; a.sColsum = p.sColsum;
+    a.xc = p.xc; a.ldxc = p.ldxc; a.nxc = p.skinny ? p.nxc : 0;
+    a.skinny = p.skinny; a.ldsk = p.ldsk; a.sSk = p.sSk;
+  }
   dim3 grid((unsigned)cdiv(p.M, BM), (unsigned)cdiv(p.N, BN), (unsigned)(splitk * p.batch));
   ProfScope prof(st, PROF_TC_WGRAD, 2.0 * p.M * p.N * (double)p.K * p.batch);
   CUtensorMap mC = mA;
@@ -1151,6 +1201,11 @@ bool tc_gemm_tn_supported(const TcGemmTnP& p) {
   if (p.M <= 0 || p.N <= 0 || p.K <= 0 || p.K >= (1ll << 31) || p.batch <= 0) return false;
   if (!ok_operand(p.A, p.lda, p.sA) || !ok_operand(p.B, p.ldb, p.sB) || !p.C) return false;
   return encode_fn() != nullptr;
+}
+
+bool tc_gemm_tn_rides_supported(const TcGemmTnP& p) {
+  // mirrors the dispatch below: the TS kernels (3 passes, 16-deep stages) are the ones with splitter threads on A
+  return tc_gemm_tn_supported(p) && p.passes == 3 && p.bk != 32 && option(NF_OPT_BN256) != 1 && option(NF_OPT_TS) != 0;
 }
 
 int tc_gemm_tn(const TcGemmTnP& p, cudaStream_t st) {

@@ -65,7 +65,14 @@ struct TcGemmTnP {
   int splitk = 0;                            // 0 = choose
   int passes = 3;
   int bk = 16;
+  // reductions over the batch rows that share the A operand, taken by the kernel's splitter threads (TS kernels only,
+  // see tc_gemm_tn_rides_supported; outputs are accumulated with atomics and must hold the base value on entry):
+  //   colsum[z][m] += sum_k A[z][k, m];   skinny[z][m, j] += sum_k A[z][k, m] * xc[k, j], j < nxc <= 16 (xc shared by z)
+  float* colsum = nullptr; long long sColsum = 0;
+  const float* xc = nullptr; long long ldxc = 0; int nxc = 0;
+  float* skinny = nullptr; long long ldsk = 0, sSk = 0;
 };
+bool tc_gemm_tn_rides_supported(const TcGemmTnP& p);
 int tc_gemm_tn(const TcGemmTnP& p, cudaStream_t st);
 bool tc_gemm_tn_supported(const TcGemmTnP& p);
 

@@ -43,7 +43,10 @@ KEEP = [
 def main():
     rep, out = sys.argv[1], sys.argv[2]
     note = sys.argv[3] if len(sys.argv) > 3 else ""
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    # a .csv is the raw page already exported on the GPU box (`ncu -i x.ncu-rep --page raw --csv > x.csv`: full
+    # reports of a whole step exceed what gpurun copies back)
+    raw = open(rep).read() if rep.endswith(".csv") else \
+        subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     lines = [f"# ncu --set full summary of {rep}", f"# {note}" if note else "#",

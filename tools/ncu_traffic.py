@@ -21,7 +21,10 @@ TUNIT = {"ns": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "msecond": 1e3, "nsec
 
 def main():
     rep, key, pattern, source = sys.argv[1:5]
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    # a .csv is the raw page already exported on the GPU box (`ncu -i x.ncu-rep --page raw --csv > x.csv`: full
+    # reports of a whole step exceed what gpurun copies back)
+    raw = open(rep).read() if rep.endswith(".csv") else \
+        subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     u = dict(zip(hdr, units))
