@@ -17,6 +17,7 @@ JSON line (train / sampling / e2e / roofline per config; >= 100 timed steps for 
     C3        latent-actor flow of nf.py (H1 = C + R, eps 1e-6), 16384 per GPU, DP all-reduce    weak
     C4        kitchen NF-BC sampling, 65536 parallel envs sharded over the GPUs (no collective)  strong
     C5        stress flow (24 blocks, width 1024, D = 32), global batch 65536 sharded            strong
+    C2t       causal-transformer flow (torch_nfgcbc.py:119 shape: 8 tokens, width 256, 4 x 4 layers), batch 4096   weak
 Before anything is timed, one forward of every config is compared with the float64 checker (the reference's op
 sequence in stock PyTorch, oracle/torch_flow.py, on the GPU) and the run aborts on a mismatch.
 Prints ONE JSON line on rank 0.
@@ -392,6 +393,151 @@ class Runner:
         self.torch.cuda.empty_cache()
 
 
+# --------------------------------------------------------------------------------------------------
+# causal-transformer flow: the transformer shape of BASELINE configs[1]
+# --------------------------------------------------------------------------------------------------
+TARFLOW = dict(A=8, C=256, R=64, hd=64, nb=4, L=4, E=4, batch=4096)     # torch_nfgcbc.py:74-82 defaults, batch of configs[1]
+
+
+def tarflow_flops_fwd(c):
+    A, C, R, H, E = c["A"], c["C"], c["R"], c["C"] // c["hd"], c["E"]
+    layer = A * (2 * C * 3 * C + 2 * C * C + 2 * 2 * C * E * C) + H * 2 * 2 * c["hd"] * A * (A + 1) // 2
+    return c["nb"] * (2 * R * C + c["L"] * layer + A * 2 * 2 * C)
+
+
+def tarflow_models(c, seed=0):
+    import torch
+    from oracle import torch_tarflow as tt
+    torch.manual_seed(seed)
+    ref = tt.RealNVP(c["A"], c["C"], c["R"], c["hd"], c["nb"], c["L"], None, expansion=c["E"])
+    tt.perturb_output_heads(ref, seed=seed + 1)
+    return ref
+
+
+class TarflowRunner(Runner):
+    """The transformer flow on this rank's GPU; same timing / e2e machinery as the coupling-flow configurations."""
+
+    def __init__(self, dev, rank, world, flush):
+        import torch
+        import nf_b200
+        c = TARFLOW
+        self.torch, self.name, self.dev, self.rank, self.world, self.flush = torch, "C2t", dev, rank, world, flush
+        self.c, self.B, self.D, self.R = c, c["batch"], c["A"], c["R"]
+        self.ref = tarflow_models(c)
+        model = nf_b200.TransformerRealNVP(c["A"], c["C"], c["R"], c["hd"], c["nb"], c["L"], None, expansion=c["E"])
+        model.load_state_dict(self.ref.state_dict())
+        self.model = model.to(dev)
+        if world > 1:
+            self.model.enable_data_parallel()
+        g = torch.Generator().manual_seed(1234 + rank)
+        B = self.B
+        xh = torch.rand(B, c["A"], 1, generator=g) * 2 - 1 + 0.1 * torch.randn(B, c["A"], 1, generator=g)
+        yh = torch.randn(B, 1, c["R"], generator=g)
+        self.x_pin, self.y_pin = xh.pin_memory(), yh.pin_memory()
+        self.x, self.y = self.x_pin.to(dev), self.y_pin.to(dev)
+        self.plist = [p for p in self.model.parameters() if p.requires_grad]
+        self.step_stats = {}
+
+    def config(self):
+        c = self.c
+        return {"workload": f"C2t: causal-transformer flow (torch_nfgcbc.py:119 shape) A={c['A']} channels={c['C']} "
+                            f"rep={c['R']} head_dim={c['hd']} blocks={c['nb']} layers_per_block={c['L']}, batch {self.B} per GPU, "
+                            f"log_prob forward+backward; sampling = the autoregressive inverse",
+                **{k: v for k, v in c.items() if k != "batch"}, "batch_per_gpu": self.B, "global_batch": self.B * self.world,
+                "parallelism": f"dp{self.world}", "l2": "flushed between timed iterations (256 MB write)",
+                "precision": "fp32", "parity": "unpinned upstream (source absent); checker oracle/torch_tarflow.py"}
+
+    def train_step(self, xd, yd):
+        model, D = self.model, self.D
+        for p in self.plist:
+            p.grad = None
+        yd = yd.detach().requires_grad_(True)       # the encoder output (torch_nfgcbc.py:141)
+        z, _, ld = model(xd, yd)
+        loss = -((-0.5 * (z * z).sum((1, 2)) - 0.5 * D * LOG2PI) + ld).mean()       # torch_nfgcbc.py:142
+        loss.backward()
+        return loss
+
+    def parity_check(self, rows=512, gate=True):
+        import copy
+        torch = self.torch
+        n = min(rows, self.B)
+        x, y = self.x[:n].contiguous(), self.y[:n].contiguous()
+        with torch.no_grad():
+            z, _, ld = self.model(x, y)
+        ref = {}
+        for dt in (torch.float64, torch.float32):
+            m = copy.deepcopy(self.ref).to(self.dev).to(dt)
+            with torch.no_grad():
+                zz, _, ll = m(x.to(dt), y.to(dt))
+            ref[dt] = (zz.double(), ll.double())
+
+        def rel(a, b):
+            return float((a.double() - b).abs().max()) / max(float(b.abs().max()), 1e-30)
+        res = {"rows": n}
+        for name, ours, i in (("z", z, 0), ("log_dets", ld, 1)):
+            e, noise = rel(ours, ref[torch.float64][i]), rel(ref[torch.float32][i], ref[torch.float64][i])
+            res[name] = {"err": e, "ref32_err": noise, "tol": max(1e-5, 2 * noise)}
+            if gate and not e <= max(1e-5, 2 * noise):
+                raise SystemExit(f"bench.py: parity check failed for C2t ({name}: {e:.3e})")
+        return res
+
+    def roofline(self, ms_step, peaks, traffic, train):
+        torch = self.torch
+        from nf_b200 import _lib
+        _lib.lib.nf_prof_enable(1)
+        _lib.prof_collect()
+        reps = 3
+        for _ in range(reps):
+            self.flush.zero_()
+            (self.train_step if train else self.sample_step)(self.x, self.y)
+        torch.cuda.synchronize()
+        prof = _lib.prof_collect()
+        _lib.lib.nf_prof_enable(0)
+        tot_ms = sum(v[0] for v in prof.values()) or 1.0
+        dom = max(("tc_gemm", "tc_wgrad", "simt_gemm"), key=lambda k: prof[k][0])
+        d_ms, d_work, d_n = prof[dom]
+        achieved = d_work / (d_ms * 1e-3) / 1e12 if d_ms > 0 else 0.0
+        step_flops = (3 if train else 1) * tarflow_flops_fwd(self.c) * self.B
+        return {"bound": "tensor", "kernel": KERNEL_NAMES[dom], "achieved": achieved, "peak": peaks["bf16_tflops"],
+                "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"], "traffic": None,
+                "launches_timed": int(d_n),
+                "gemm_share_of_profiled_kernels": d_ms / tot_ms,
+                "note": "only the GEMM classes are profiled; the transformer flow's row kernels (LayerNorm, attention, "
+                        "GELU, tail) are outside the per-class profiler",
+                "whole_step": {"achieved": step_flops / (ms_step * 1e-3) / 1e12, "unit": "TFLOP/s",
+                               "frac": step_flops / (ms_step * 1e-3) / 1e12 / peaks["bf16_tflops"],
+                               "what": "train step (3 F_fwd B)" if train else "sampling pass (F_fwd B)"}}
+
+
+def tarflow_cpu_baseline(Bc=256):
+    """The checker (stock PyTorch, all host threads) as the CPU baseline of the transformer flow."""
+    import torch
+    torch.set_num_threads(os.cpu_count())
+    c = TARFLOW
+    m = tarflow_models(c)
+    g = torch.Generator().manual_seed(1234)
+    x = torch.rand(Bc, c["A"], 1, generator=g) * 2 - 1
+    y = torch.randn(Bc, 1, c["R"], generator=g)
+    plist = list(m.parameters())
+
+    def train():
+        for p in plist:
+            p.grad = None
+        z, _, ld = m(x, y.detach().requires_grad_(True))
+        (-((-0.5 * (z * z).sum((1, 2)) - 0.5 * c["A"] * LOG2PI) + ld).mean()).backward()
+
+    def sample():
+        with torch.no_grad():
+            m.reverse(x, y)
+    per, iters = time_cpu(train, 2.5, 20)
+    per_s, iters_s = time_cpu(sample, 2.5, 10)
+    cores = os.cpu_count()
+    return {"value": Bc / per, "unit": "samples/s", "cores": cores, "kind": "port",
+            "sampling": {"value": Bc / per_s, "unit": "actions/s"},
+            "sample": f"{iters} train steps and {iters_s} reverse passes at batch {Bc} (oracle/torch_tarflow.py on the host, "
+                      f"{cores} threads; its reverse recomputes the full causal pass per dimension, there is no K/V cache)"}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -489,6 +635,29 @@ def run_ours(args):
             entry["tf32"] = red
             r.free()
 
+    if args.tarflow:
+        r = TarflowRunner(dev, rank, world, flush)
+        parity["C2t"] = r.parity_check()
+        steps = max(K, 50)
+        entry = {"config": r.config(), "scaling": "weak", "steps": steps, "warmup": W}
+        total_B = r.B * world
+        _lib.lib.nf_launch_count(1)
+        ms = r.timed("train", r.train_step, steps, W)
+        entry["gpu_launches_per_step"] = int(_lib.lib.nf_launch_count(1) // (steps + W))
+        entry["train"] = {"value": total_B / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms,
+                          "ms_median_max": list(r.step_stats["train"])}
+        ms_s = r.timed("sample", r.sample_step, steps, W)
+        entry["sampling"] = {"value": total_B / (ms_s * 1e-3), "unit": "actions/s", "ms_per_step": ms_s,
+                             "ms_median_max": list(r.step_stats["sample"])}
+        ms_e = r.timed("e2e_train", r.train_step, steps, W, e2e=True)
+        ms_es = r.timed("e2e_sample", r.sample_step, steps, W, e2e=True)
+        entry["e2e"] = {"h2d_bytes_per_step": r.x_pin.numel() * 4 + r.y_pin.numel() * 4, "d2h_bytes_per_step": 4,
+                        "train": {"value": total_B / (ms_e * 1e-3), "unit": "samples/s", "ms_per_step": ms_e},
+                        "sampling": {"value": total_B / (ms_es * 1e-3), "unit": "actions/s", "ms_per_step": ms_es}}
+        entry["roofline"] = r.roofline(ms, peaks, traffic, True)
+        per_config["C2t"] = entry
+        r.free()
+
     clocks = sampler.stop() if rank == 0 else None
     replays, captures, eager = _lib.graph_stats()
 
@@ -522,6 +691,9 @@ def run_ours(args):
                 "value": Bc / per, "unit": unit, "cores": cores, "kind": "port",
                 "sample": f"{iters} {'train steps' if PLAN[name]['train'] else 'reverse passes'} at batch {Bc} "
                           f"(oracle/torch_flow.py on the host, {cores} threads, {per * iters:.1f} s)"}
+
+        if "C2t" in per_config:
+            per_config["C2t"]["cpu_baseline"] = tarflow_cpu_baseline()
 
     total_B = B_head * world
     head_roof["note"] = (f"algorithmic FLOPs (2MNK per launch, split-precision passes NOT counted) / mean launch duration "
@@ -574,6 +746,8 @@ def main():
     ap.add_argument("--reduced", default="C4,C5",
                     help="configurations additionally timed in the optional reduced-precision mode (precision='tf32'), "
                          "reported under per_config[...]['tf32'] -- never the headline (the reference is fp32)")
+    ap.add_argument("--tarflow", type=int, default=1,
+                    help="1: also time the causal-transformer flow (per_config['C2t'], SURVEY section 8 row f1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

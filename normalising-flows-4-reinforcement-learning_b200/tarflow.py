@@ -117,6 +117,7 @@ class TransformerRealNVP(nn.Module):
             raise _lib.NfError("nf_tarflow_param_layout: " + lib.nf_last_error().decode(errors="replace"))
         self._offs, self._total = list(offs), int(total)
         self._flat, self._ws, self._stash_pool = None, None, {}
+        self._dp_group, self._dp_world, self._dp_avg = None, 1, False
         self._flatten()
         self.register_load_state_dict_post_hook(lambda module, keys: module._flatten())
 
@@ -234,7 +235,33 @@ class TransformerRealNVP(nn.Module):
             _lib.check(lib.nf_tarflow_backward(ctypes.byref(self._desc), self._flat.data_ptr(), stash.data_ptr(), B,
                                                p(dz), p(dld), p(dx), p(dy), p(dflat), ws.data_ptr(), ws.numel(),
                                                self._stream(dev)), "nf_tarflow_backward")
+            if self._dp_world > 1 and need_p:     # (a rank-local evaluation must not enter the collective)
+                self._allreduce_grads(dflat)
         return dx, dy, dflat
+
+    # ------------------------------------------------------------------ data parallel
+    def enable_data_parallel(self, process_group=None):
+        """Batch-sharded data parallel training (rows are independent): parameters are broadcast from rank 0 and
+        backward averages the flat gradient arena over the ranks (one NCCL all-reduce) before autograd sees the views."""
+        import torch.distributed as dist
+        self._dp_group = process_group
+        self._dp_world = dist.get_world_size(process_group)
+        self._dp_avg = dist.get_backend(process_group) == "nccl"
+        if self._dp_world > 1:
+            if not self._is_flat():
+                self._flatten()
+            with torch.no_grad():
+                dist.broadcast(self._flat, src=dist.get_global_rank(process_group, 0) if process_group is not None else 0,
+                               group=process_group)
+        return self
+
+    def _allreduce_grads(self, dflat):
+        import torch.distributed as dist
+        if self._dp_avg:
+            dist.all_reduce(dflat, op=dist.ReduceOp.AVG, group=self._dp_group)
+        else:
+            dist.all_reduce(dflat, op=dist.ReduceOp.SUM, group=self._dp_group)
+            dflat.mul_(1.0 / self._dp_world)
 
     # ------------------------------------------------------------------ the reference's call sites
     def forward(self, x: torch.Tensor, cond: torch.Tensor):

@@ -77,8 +77,17 @@ def test_forward_backward_reverse_match_the_checker(name, precision):
         for i, o in enumerate(outs):
             e = rel_err(o.detach().cpu().numpy(), r64["outs"][i])
             assert e <= max(1e-5, 2.0 * rel_err(r32["outs"][i], r64["outs"][i])), (name, "outputs", i, e)
-        # the inverse of z is x (round trip) and equals the checker's reverse of its own z
-        assert rel_err(xr.cpu().numpy(), x.numpy()) <= max(2e-5, 4.0 * rel_err(r32["rev"], x.numpy())), (name, "round trip")
+        # the inverse, isolated: our reverse of our z against the float64 checker's reverse of the same z; the noise
+        # floor is the float32 checker's reverse of that z (the autoregressive loop feeds every rounding error of
+        # dimension t into dimensions t+1.., so the inverse is noisier than the forward in any float32 implementation)
+        if it == 0:
+            zc = z.detach().cpu()
+            with torch.no_grad():
+                want = copy.deepcopy(ref).double().reverse(zc.double(), y.detach().double()).numpy()
+                noise = rel_err(ref.reverse(zc, y.detach()).numpy(), want)
+            e = rel_err(xr.cpu().numpy(), want)
+            assert e <= max(2e-5, 3.0 * noise), (name, precision, "reverse", e, noise)
+            assert rel_err(xr.cpu().numpy(), x.detach().numpy()) <= max(5e-5, 6.0 * noise), (name, "round trip")
         assert torch.equal(xr, xr2)
         assert rel_err(ldr.cpu().numpy(), -r64["ld"]) <= max(2e-5, 4.0 * rel_err(r32["ld"], r64["ld"])), (name, "reverse logdet")
         for k, p in ours.named_parameters():
