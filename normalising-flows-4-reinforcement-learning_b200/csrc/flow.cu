@@ -40,7 +40,7 @@ const OptDef kOpts[NF_OPT_COUNT] = {
     {"nacc", "NF_B200_NACC", 0},         {"fused_ln", "NF_B200_FUSED_LN", -1},    {"fused_tail", "NF_B200_FUSED_TAIL", 0},
     {"bn256", "NF_B200_BN256", 0},       {"ts", "NF_B200_TS", 1},                 {"presplit", "NF_B200_PRESPLIT", 1},
     {"stack", "NF_B200_STACK", -1},      {"stack_nsg", "NF_B200_STACK_NSG", 2},   {"whatif", "NF_B200_WHATIF", 0},
-    {"ride", "NF_B200_RIDE", 1},
+    {"ride", "NF_B200_RIDE", 1},         {"defer_wgrad", "NF_B200_DEFER_WGRAD", -1},
 };
 int g_opt[NF_OPT_COUNT];
 bool g_opt_init = false;
@@ -198,7 +198,17 @@ struct BwdWs { float *d0, *d1, *dxp, *dout, *gA, *gB, *dWs, *T1, *dLh, *dUh, *su
                float *dxp2, *dout2, *gA2, *gB2;   // second set: blocks alternate so side streams can lag one block
                float *io_dz, *io_dld, *io_dy, *io_dx;   // staging of the caller's cotangents and of dx / dy (see FwdWs)
                float *w3t[2];                           // generic path: W3f^T (2, C, dtp) of the current block (alternating)
+               float *gAall, *gBall;                    // du2 / du1 of EVERY block (n, 2, B, Hm) when the weight gradients are deferred
                int64_t total; };
+// The conditioner weight gradients of a block only consume du2 / du1.  While the flow is small enough to keep those for
+// every block (2 x n x 2 x B x Hm floats), backward skips the per-block weight-gradient GEMMs and runs TWO batched
+// launches after the block loop (batch = blocks x nets): 12 launches of 15-16 us with 36-74-way split-K become 2 with a
+// 4-6-way split (C2a).  Larger flows keep the per-block launches, which overlap the data-gradient chain on side streams.
+constexpr int64_t kDeferWgradMaxBytes = int64_t(640) << 20;
+static bool defer_fits(const Dims& m, int64_t B) {
+  const int64_t Hm = std::max(m.H1, m.C);
+  return (int64_t)m.n * 2 * 2 * B * Hm * 4 <= kDeferWgradMaxBytes;
+}
 static BwdWs carve_bwd(const Dims& m, int64_t B, void* ws) {
   Carver c(ws);
   BwdWs w;
@@ -225,6 +235,11 @@ static BwdWs carve_bwd(const Dims& m, int64_t B, void* ws) {
   w.io_dx = c.take(B * m.D);
   w.w3t[0] = c.take(2 * (int64_t)m.C * pad4(m.dt));
   w.w3t[1] = c.take(2 * (int64_t)m.C * pad4(m.dt));
+  w.gAall = w.gBall = nullptr;
+  if (defer_fits(m, B)) {     // (sized by shape alone, so the workspace size does not depend on run-time options)
+    w.gAall = c.take((int64_t)m.n * 2 * B * Hm);
+    w.gBall = c.take((int64_t)m.n * 2 * B * Hm);
+  }
   w.total = c.off;
   return w;
 }
@@ -925,6 +940,22 @@ static int backward_impl(const NfFlowDesc* desc, const float* params, const void
   NF_CHECK_ARG(dp_bucket <= 0 || sar != nullptr, NF_E_UNSUPPORTED, "could not create the all-reduce stream");
   cudaStream_t s1 = ss ? ss->s1 : st, s2 = ss ? ss->s2 : st;
   struct { float *dxp, *dout, *gA, *gB; } w2[2] = {{w.dxp, w.dout, w.gA, w.gB}, {w.dxp2, w.dout2, w.gA2, w.gB2}};
+  // deferred, batched conditioner weight gradients (see defer_fits): both GEMMs must be the TS kernels that take the
+  // bias / x_cond reductions along
+  bool defer = false, ln1_fused_any = false;
+  // auto: only where it was measured to win -- the data-gradient chain fills the machine about once per kernel (C2a:
+  // 128 CTAs), so per-block weight gradients on the side streams compete with it: train step 0.658 -> 0.628 ms.  Smaller
+  // grids leave idle SMs that absorb the side work for free (C1a, B = 256: 1.152 -> 1.202 ms when deferred) and on
+  // multi-wave grids the per-block launches fill the tails of the waves (C3, B = 16384: 2.218 -> 2.260 ms).
+  const int64_t chain_ctas = cdiv(B, 128) * 2 * cdiv(m.H1, 128);
+  const int dw = option(NF_OPT_DEFER_WGRAD);
+  if (v2 && dparams && has_y && w.gAall && m.dc <= 16 && (dw == 1 || (dw < 0 && chain_ctas >= 96 && chain_ctas <= 192))) {
+    TcGemmTnP e, h;
+    e.A = w.gAall; e.lda = m.C; e.sA = B * Hm; e.B = stash + sl.blocks + sl.xh1; e.ldb = m.H1; e.sB = sl.net_stride;
+    e.C = dparams; e.ldc = m.H1; e.M = m.C; e.N = m.H1; e.K = B; e.batch = 2;
+    h = e; h.A = w.gBall; h.lda = m.H1; h.B = y; h.ldb = m.R; h.sB = 0; h.ldc = m.K1; h.M = m.H1; h.N = m.R;
+    defer = rides_ok(m.prec, e) && rides_ok(m.prec, h);
+  }
   bool any_ar = false;
   for (int sub_end = block_end; sub_end > block_begin;) {
   const int sub_begin = dp_bucket > 0 ? std::max(block_begin, sub_end - dp_bucket) : block_begin;
@@ -933,6 +964,8 @@ static int backward_impl(const NfFlowDesc* desc, const float* params, const void
   for (int i = sub_end - 1; i >= sub_begin; --i) {
     const int par = ss ? ((m.n - 1 - i) & 1) : 0;
     const auto& wb = w2[par];   // this block's intermediate buffers
+    float* const gA = defer ? w.gAall + (int64_t)i * 2 * B * Hm : wb.gA;   // du2 (deferred weight gradients: kept per block)
+    float* const gB = defer ? w.gBall + (int64_t)i * 2 * B * Hm : wb.gB;   // du1
     if (ss) {   // the side work of block i+2 read this buffer set
       if (used1[par]) NF_CUDA(cudaStreamWaitEvent(st, ss->done1[par], 0));
       if (used2[par]) NF_CUDA(cudaStreamWaitEvent(st, ss->done2[par], 0));
@@ -956,7 +989,7 @@ static int backward_impl(const NfFlowDesc* desc, const float* params, const void
       h.mask = m2; h.mask_net = sl.net_stride; h.mw = sl.mw2;
       h.W3f = kb + kl.net0 + kl.W3f; h.w_net = kl.net_stride;
       h.dxp = wb.dxp; h.dout = wb.dout; h.dout_net = B * m.dt;
-      h.du2 = wb.gA; h.du2_net = B * Hm;
+      h.du2 = gA; h.du2_net = B * Hm;
       h.B = B; h.D = m.D; h.C = m.C;
       NF_TRY(row_bwd_head2(h, st));
       if (ss) { NF_CUDA(cudaEventRecord(ss->evA, st)); NF_CUDA(cudaStreamWaitEvent(s1, ss->evA, 0)); }
@@ -969,7 +1002,7 @@ static int backward_impl(const NfFlowDesc* desc, const float* params, const void
       h.rstd = sb + sl.r2; h.rstd_net = sl.net_stride;
       h.mask = m2; h.mask_net = sl.net_stride; h.mw = sl.mw2;
       h.W3f = kb + kl.net0 + kl.W3f; h.w_net = kl.net_stride;
-      h.dxp = wb.dxp; h.du2 = wb.gA; h.du2_net = B * Hm;
+      h.dxp = wb.dxp; h.du2 = gA; h.du2_net = B * Hm;
       h.G3 = dn ? dn + pl.slot_off[NF_P_W3] : nullptr;
       h.g3 = dn ? dn + pl.slot_off[NF_P_B3] : nullptr;
       h.gb2 = dn ? dn + pl.slot_off[NF_P_B2] : nullptr;
@@ -999,7 +1032,7 @@ static int backward_impl(const NfFlowDesc* desc, const float* params, const void
           TcGemmP t;
           t.A0 = wb.dout; t.lda0 = m.dt; t.sA0 = B * m.dt; t.K0 = m.dt;
           t.B0 = w3t; t.ldb0 = m.dt; t.sB0 = (int64_t)m.C * m.dt;
-          t.C = wb.gA; t.ldc = m.C; t.sC = B * Hm;
+          t.C = gA; t.ldc = m.C; t.sC = B * Hm;
           t.M = (int)B; t.N = m.C; t.batch = 2;
           if (m.prec == NF_PREC_TF32) { t.passes = 1; t.raw_hi = 1; }
           if (tc_gemm_supported(t)) { NF_TRY(tc_gemm(t, st)); done = true; }
@@ -1008,14 +1041,14 @@ static int backward_impl(const NfFlowDesc* desc, const float* params, const void
           GemmP g;
           g.A0 = wb.dout; g.lda0 = m.dt; g.sA0 = B * m.dt; g.K0 = m.dt;
           g.B0 = kb + kl.net0 + kl.W3f; g.ldb0 = m.C; g.sB0 = kl.net_stride;
-          g.C = wb.gA; g.ldc = m.C; g.sC = B * Hm;
+          g.C = gA; g.ldc = m.C; g.sC = B * Hm;
           g.M = (int)B; g.N = m.C; g.batch = 2;
           NF_TRY(simt_gemm(g, st));
         }
       }
       {  // d. through LayerNorm + LeakyReLU (layer 2); column sums -> slot b2
         LnBwdP p{};
-        p.g = wb.gA; p.g_net = B * Hm;
+        p.g = gA; p.g_net = B * Hm;
         p.xh = sb + sl.xh2; p.xh_net = sl.net_stride;
         p.rstd = sb + sl.r2; p.rstd_net = sl.net_stride;
         p.mask = m2; p.mask_net = sl.net_stride; p.mw = sl.mw2;
@@ -1027,7 +1060,7 @@ static int backward_impl(const NfFlowDesc* desc, const float* params, const void
     bool fold_e = false, fold_h = false;   // batch-row reductions taken by the weight-gradient GEMMs (tc_gemm.cuh)
     if (dn) {  // e. G2 = du2^T x_hat1 -> slot W2
       TcGemmTnP g;
-      g.A = wb.gA; g.lda = m.C; g.sA = B * Hm;
+      g.A = gA; g.lda = m.C; g.sA = B * Hm;
       g.B = sb + sl.xh1; g.ldb = m.H1; g.sB = sl.net_stride;
       g.C = dn + pl.slot_off[NF_P_W2]; g.ldc = m.H1; g.sC = pl.net_stride;
       g.M = m.C; g.N = m.H1; g.K = B; g.batch = 2;
@@ -1035,14 +1068,14 @@ static int backward_impl(const NfFlowDesc* desc, const float* params, const void
         g.colsum = dn + pl.slot_off[NF_P_B2]; g.sColsum = pl.net_stride;
         fold_e = true;
       }
-      if (!(whatif & 2)) NF_TRY(wgrad_tn(m.prec, g, s1));
+      if (!(whatif & 2) && !defer) NF_TRY(wgrad_tn(m.prec, g, s1));
     }
     bool ln1_fused = false;
     {  // f. d x_hat1 = du2 W2f   (K-major B operand = W2f^T)
       TcGemmP g;
-      g.A0 = wb.gA; g.lda0 = m.C; g.sA0 = B * Hm; g.K0 = m.C;
+      g.A0 = gA; g.lda0 = m.C; g.sA0 = B * Hm; g.K0 = m.C;
       g.B0 = kb + kl.net0 + kl.W2fT; g.ldb0 = m.C; g.sB0 = kl.net_stride;
-      g.C = wb.gB; g.ldc = m.H1; g.sC = B * Hm;
+      g.C = gB; g.ldc = m.H1; g.sC = B * Hm;
       g.M = (int)B; g.N = m.H1; g.batch = 2;
       if (kl.hi_off) { g.B0hi = g.B0 + kl.hi_off; g.B0lo = g.B0 + kl.lo_off; }
       if (v2 && prec_tc(m.prec) && m.C >= 32) {
@@ -1062,9 +1095,10 @@ static int backward_impl(const NfFlowDesc* desc, const float* params, const void
       }
       if (!ln1_fused) NF_TRY(linear_nt(m.prec, g, st));
     }
+    ln1_fused_any = ln1_fused;
     if (!ln1_fused) {  // g. through LayerNorm + LeakyReLU (layer 1); column sums -> slot b1
       LnBwdP p{};
-      p.g = wb.gB; p.g_net = B * Hm;
+      p.g = gB; p.g_net = B * Hm;
       p.xh = sb + sl.xh1; p.xh_net = sl.net_stride;
       p.rstd = sb + sl.r1; p.rstd_net = sl.net_stride;
       p.mask = m1; p.mask_net = sl.net_stride; p.mw = sl.mw1;
@@ -1075,7 +1109,7 @@ static int backward_impl(const NfFlowDesc* desc, const float* params, const void
     if (ss) { NF_CUDA(cudaEventRecord(ss->evB, st)); NF_CUDA(cudaStreamWaitEvent(s2, ss->evB, 0)); }
     if (dn) {  // h. dW1 = du1^T [x_cond | y]   (fused path: the x_cond columns come from the tail kernel)
       TcGemmTnP g;
-      g.A = wb.gB; g.lda = m.H1; g.sA = B * Hm;
+      g.A = gB; g.lda = m.H1; g.sA = B * Hm;
       g.B = zi; g.ldb = m.D; g.sB = 0;
       g.C = dn + pl.slot_off[NF_P_W1]; g.ldc = m.K1; g.sC = pl.net_stride;
       g.M = m.H1; g.N = m.dc; g.K = B; g.batch = 2;
@@ -1090,13 +1124,13 @@ static int backward_impl(const NfFlowDesc* desc, const float* params, const void
           if (ln1_fused) { g.colsum = dn + pl.slot_off[NF_P_B1]; g.sColsum = pl.net_stride; }
           fold_h = true;
         }
-        if (!(whatif & 2)) NF_TRY(wgrad_tn(m.prec, g, s2));
+        if (!(whatif & 2) && !defer) NF_TRY(wgrad_tn(m.prec, g, s2));
       }
     }
     {  // i. d h0 = du1_t W1_t + du1_s W1_s : first dc columns -> dxp, the rest -> dy  (B operand = W1^T)
       TcGemmP g;
-      g.A0 = wb.gB; g.lda0 = m.H1; g.K0 = m.H1;
-      g.A1 = wb.gB + B * Hm; g.lda1 = m.H1; g.K1 = m.H1;
+      g.A0 = gB; g.lda0 = m.H1; g.K0 = m.H1;
+      g.A1 = gB + B * Hm; g.lda1 = m.H1; g.K1 = m.H1;
       g.B0 = kb + kl.net0 + kl.W1T; g.ldb0 = m.H1;
       g.B1 = g.B0 + kl.net_stride; g.ldb1 = m.H1;
       g.C = wb.dxp; g.ldc = m.D; g.M = (int)B; g.N = m.dc; g.accumulate = 1;
@@ -1112,7 +1146,7 @@ static int backward_impl(const NfFlowDesc* desc, const float* params, const void
     if (fused && v2) {
       // i (x_cond part) and k per row, then every reduction over the batch rows of this block in one launch
       BwdTail2P t{};
-      t.du1 = wb.gB; t.du1_net = B * Hm;
+      t.du1 = gB; t.du1_net = B * Hm;
       t.W1T = kb + kl.net0 + kl.W1T; t.w_net = kl.net_stride;
       t.W = kb + kl.W;
       t.dxp = wb.dxp; t.dxin = dst; t.ld_dxin = m.D;
@@ -1125,17 +1159,17 @@ static int backward_impl(const NfFlowDesc* desc, const float* params, const void
         jobs[0].coef = wb.dout; jobs[0].ldcf = m.dt; jobs[0].sCf = B * m.dt; jobs[0].m = m.dt;
         jobs[0].out = dn + pl.slot_off[NF_P_W3]; jobs[0].so_i = m.C; jobs[0].so_c = 1; jobs[0].sOut = pl.net_stride;
         if (!fold_e) {
-          jobs[0].A2 = wb.gA; jobs[0].lda2 = m.C; jobs[0].sA2 = B * Hm;
+          jobs[0].A2 = gA; jobs[0].lda2 = m.C; jobs[0].sA2 = B * Hm;
           jobs[0].out2 = dn + pl.slot_off[NF_P_B2]; jobs[0].sOut2 = pl.net_stride;
         }
         jobs[0].out3 = dn + pl.slot_off[NF_P_B3]; jobs[0].sOut3 = pl.net_stride;
         jobs[0].batch = 2;
         // G1[:, :dc] = du1^T x_cond   (x_cond = z[:, :dc])
-        jobs[1].A = wb.gB; jobs[1].lda = m.H1; jobs[1].sA = B * Hm; jobs[1].N = m.H1;
+        jobs[1].A = gB; jobs[1].lda = m.H1; jobs[1].sA = B * Hm; jobs[1].N = m.H1;
         jobs[1].coef = zi; jobs[1].ldcf = m.D; jobs[1].sCf = 0; jobs[1].m = m.dc;
         jobs[1].out = dn + pl.slot_off[NF_P_W1]; jobs[1].so_i = 1; jobs[1].so_c = m.K1; jobs[1].sOut = pl.net_stride;
         if (ln1_fused) {   // gb1 = colsum(du1): same array as A, loaded once
-          jobs[1].A2 = wb.gB; jobs[1].lda2 = m.H1; jobs[1].sA2 = B * Hm;
+          jobs[1].A2 = gB; jobs[1].lda2 = m.H1; jobs[1].sA2 = B * Hm;
           jobs[1].out2 = dn + pl.slot_off[NF_P_B1]; jobs[1].sOut2 = pl.net_stride;
         }
         jobs[1].batch = 2;
@@ -1164,7 +1198,7 @@ static int backward_impl(const NfFlowDesc* desc, const float* params, const void
     } else if (fused) {
       // i (x_cond part), j, k in one kernel
       BwdTailP t{};
-      t.du1 = wb.gB; t.du1_net = B * Hm;
+      t.du1 = gB; t.du1_net = B * Hm;
       t.W1T = kb + kl.net0 + kl.W1T; t.w_net = kl.net_stride;
       t.z = zi; t.xin = xin; t.W = kb + kl.W;
       t.dxp = wb.dxp; t.dxin = dst; t.ld_dxin = m.D;
@@ -1189,6 +1223,25 @@ static int backward_impl(const NfFlowDesc* desc, const float* params, const void
       if (used1[par]) NF_CUDA(cudaStreamWaitEvent(st, ss->done1[par], 0));
       if (used2[par]) NF_CUDA(cudaStreamWaitEvent(st, ss->done2[par], 0));
     }
+  }
+  if (defer && !(whatif & 2)) {
+    float* dpr = dparams + (int64_t)sub_begin * pl.block_stride;
+    TcGemmTnP g;   // e. G2 = du2^T x_hat1 and gb2 = colsum(du2) of every block and net of the range
+    g.A = w.gAall + (int64_t)sub_begin * 2 * B * Hm; g.lda = m.C; g.sA = B * Hm;
+    g.B = stash + sl.blocks + (int64_t)sub_begin * sl.block_stride + sl.xh1; g.ldb = m.H1; g.sB = sl.net_stride;
+    g.C = dpr + pl.slot_off[NF_P_W2]; g.ldc = m.H1; g.sC = pl.net_stride; g.sC2 = pl.block_stride;
+    g.M = m.C; g.N = m.H1; g.K = B; g.batch = 2 * nr; g.inner = 2;
+    g.colsum = dpr + pl.slot_off[NF_P_B2]; g.sColsum = pl.net_stride; g.sColsum2 = pl.block_stride;
+    NF_TRY(wgrad_tn(m.prec, g, st));
+    TcGemmTnP h;   // h. dW1 = du1^T [x_cond | y] and gb1 = colsum(du1)
+    h.A = w.gBall + (int64_t)sub_begin * 2 * B * Hm; h.lda = m.H1; h.sA = B * Hm;
+    h.B = y; h.ldb = m.R; h.sB = 0;
+    h.C = dpr + pl.slot_off[NF_P_W1] + m.dc; h.ldc = m.K1; h.sC = pl.net_stride; h.sC2 = pl.block_stride;
+    h.M = m.H1; h.N = m.R; h.K = B; h.batch = 2 * nr; h.inner = 2;
+    h.xc = stash + sl.xs + (int64_t)(sub_begin + 1) * BD; h.ldxc = m.D; h.nxc = m.dc; h.sXc2 = BD;
+    h.skinny = dpr + pl.slot_off[NF_P_W1]; h.ldsk = m.K1; h.sSk = pl.net_stride; h.sSk2 = pl.block_stride;
+    if (ln1_fused_any) { h.colsum = dpr + pl.slot_off[NF_P_B1]; h.sColsum = pl.net_stride; h.sColsum2 = pl.block_stride; }
+    NF_TRY(wgrad_tn(m.prec, h, st));
   }
   if (dparams) {
     GemmP g;  // T1 = P^T dW

@@ -50,6 +50,9 @@ struct KArgs {
   float* colsum; long long sColsum;
   const float* xc; long long ldxc; int nxc;
   float* skinny; long long ldsk, sSk;
+  // MN-major form, two-level batch (zin > 0): z = zo * zin + zi; A / B keep one uniform stride (TMA coordinate z), the
+  // outputs live at zo * s?2 + zi * s? (the per-block / per-net slots of the gradient arena) and xc at zo * sXc2
+  int zin; long long sC2, sColsum2, sSk2, sXc2;
   // row-wise epilogues over the cluster (EPI_LN_FWD / EPI_LN_BWD)
   float* rstd; long long sRstd;          // fwd: out (row), bwd: in
   uint32_t* mask; long long sMask; int mw;   // fwd: out, bwd: in; mw words per row
@@ -130,6 +133,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
 #define NF_TS(i) do { if (dbg) dbg[i] = clock64(); } while (0)
   if (threadIdx.x == 64) NF_TS(0);
   const int z = blockIdx.z / a.splitk;
+  // output offsets of this batch entry (two-level in the batched weight-gradient launches)
+  const int z_o = (MNMAJOR && a.zin > 0) ? z / a.zin : 0, z_i = (MNMAJOR && a.zin > 0) ? z % a.zin : z;
+  const long long c_off = (long long)z_o * a.sC2 + (long long)z_i * a.sC;
   const int nk0 = (a.K0 + BK - 1) / BK, nk1 = (a.K1 + BK - 1) / BK;
   // chunk range of this CTA: everything (K-major form) or one split of the batch rows (MN-major form)
   // both forms can split the reduction over CTAs (partial tiles are combined with red.global.add)
@@ -393,7 +399,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   const long long kr = min(k0 + 4 * c + e, (long long)a.K0 - 1);
-                  const float* xr = a.xc + kr * a.ldxc;      // same address in every lane: one broadcast transaction
+                  const float* xr = a.xc + (long long)z_o * a.sXc2 + kr * a.ldxc;      // same address in every lane: one broadcast transaction
 #pragma unroll
                   for (int j = 0; j < kMaxXc; ++j)
                     if (j < a.nxc) sk[j] = fmaf(e4[e], __ldg(xr + j), sk[j]);
@@ -478,9 +484,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
     if (ride) {   // one atomic per output element, CTA and splitter group
       const int mrow = m0 + (warp & 3) * 32 + lane;
       if (mrow < a.M) {
-        if (a.colsum) atomicAdd(a.colsum + (long long)z * a.sColsum + mrow, csum);
+        if (a.colsum) atomicAdd(a.colsum + (long long)z_o * a.sColsum2 + (long long)z_i * a.sColsum + mrow, csum);
         if (a.skinny) {
-          float* o = a.skinny + (long long)z * a.sSk + (long long)mrow * a.ldsk;
+          float* o = a.skinny + (long long)z_o * a.sSk2 + (long long)z_i * a.sSk + (long long)mrow * a.ldsk;
 #pragma unroll
           for (int j = 0; j < kMaxXc; ++j)
             if (j < a.nxc) atomicAdd(o + j, sk[j]);
@@ -527,7 +533,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
       const uint32_t my_rank = cluster_ctarank() - rank_base;
       float* sxh = reinterpret_cast<float*>(smem) + (gq * 4 + q) * (32 * (CW + 4));   // bwd: this warp's x_hat tile
       float* sx = reinterpret_cast<float*>(smem) + NSG * 4 * 32 * (CW + 4) + (gq * 4 + q) * kXWarpFloats;   // 32 x 32 transposition buffer
-      float* cwarp = a.C + (long long)z * a.sC + (long long)(m0 + q * 32) * a.ldc + n0 + cg0;
+      float* cwarp = a.C + c_off + (long long)(m0 + q * 32) * a.ldc + n0 + cg0;
       const int rows_valid_w = a.M - (m0 + q * 32);
       // TMA-store boxes (4 KB each, 1024-byte aligned): after the x_hat tiles / transposition buffers
       uint8_t* boxes = smem + ((NSG * 4 * 32 * (CW + 4) * 4 + NSG * 4 * kXWarpFloats * 4 + 1023) & ~1023) +
@@ -582,7 +588,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
       }
       mbar_wait_cluster(xbar, 0);
       if (threadIdx.x == 64) NF_TS(6);   // statistics exchanged
-      float* crow = a.C + (long long)z * a.sC + (long long)row * a.ldc + n0 + cg0;
+      float* crow = a.C + c_off + (long long)row * a.ldc + n0 + cg0;
       if constexpr (EPI == EPI_LN_FWD) {
         // combine equal-sized groups (Chan et al.): mean = avg(mean_i), M2 = sum M2_i + BN sum (mean_i - mean)^2
         float mean = 0.f;
@@ -767,8 +773,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
     } else {
     const bool red = MNMAJOR || a.splitk > 1;   // partial tile: combine with red.global.add
     const float* bias = (a.bias && kc_begin == 0) ? a.bias + (long long)z * a.sBias : nullptr;
-    const bool vec_ok = (a.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.C) + (size_t)z * a.sC * 4) & 15) == 0;
-    float* crow = a.C + (long long)z * a.sC + (long long)row * a.ldc;
+    const bool vec_ok = (a.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.C) + (size_t)c_off * 4) & 15) == 0;
+    float* crow = a.C + c_off + (long long)row * a.ldc;
     // (a shared-memory transposition for fully coalesced stores was measured SLOWER here: this epilogue is
     // bound by the 64 B/clk TMEM read path, not by the LSU; the fused epilogues keep the transposition)
     for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -903,10 +909,10 @@ int set_smem() {
 
 int pick_nacc() { return option(NF_OPT_NACC); }   // 0 = kernel default (all NACC accumulators)
 
-template <int BN, int STAGES, int BK, bool TS = false, bool NS = false>
+template <int BN, int STAGES, int BK, bool TS = false, bool NS = false, int NSG_ = 0>
 int launch(const TcGemmP& p, cudaStream_t st) {
   using S = Smem<BN, STAGES, BK, TS, NS>;
-  constexpr int NSG = TS ? 2 : 1;
+  constexpr int NSG = NSG_ ? NSG_ : (TS ? 2 : 1);
   int r;
   {
     static PerDeviceOnce once;
@@ -1049,10 +1055,10 @@ int launch_epi_pick(const TcGemmP& p, cudaStream_t st) {
   return launch_epi<64, 8, 16, EPI>(p, st);
 }
 
-template <int BN, int STAGES, int BK, bool TS = false, bool NS = false>
+template <int BN, int STAGES, int BK, bool TS = false, bool NS = false, int NSG_ = 0>
 int launch_tn(const TcGemmTnP& p, cudaStream_t st) {
   using S = Smem<BN, STAGES, BK, TS, NS>;
-  constexpr int NSG = TS ? 2 : 1;
+  constexpr int NSG = NSG_ ? NSG_ : (TS ? 2 : 1);
   int r;
   {
     static PerDeviceOnce once;
@@ -1074,6 +1080,17 @@ int launch_tn(const TcGemmTnP& p, cudaStream_t st) {
   // accumulate-truncation bound (see the kernel): at most kMaxRowsPerSplit batch rows per CTA
   constexpr long long kMaxRowsPerSplit = TS ? 1024 : 1536;   // two rotating accumulators in the TS form
   if (p.splitk <= 0 && splitk < cdiv(p.K, kMaxRowsPerSplit)) splitk = cdiv(p.K, kMaxRowsPerSplit);
+  if (p.splitk <= 0 && p.inner > 0 && tiles < 148) {
+    // batched launch over several blocks: pick the split with the fewest (waves x stages per CTA), a fixed ~8 stages of
+    // prologue / epilogue per CTA included, among the splits that respect the rows-per-CTA bound
+    const long long smin = std::max<long long>(1, cdiv(p.K, kMaxRowsPerSplit));
+    long long best = smin, best_cost = -1;
+    for (long long s_ = smin; s_ <= std::max<long long>(smin, 24); ++s_) {
+      const long long cost = cdiv(tiles * s_, 148) * (cdiv(nk, s_) + 8);
+      if (best_cost < 0 || cost < best_cost) { best = s_; best_cost = cost; }
+    }
+    splitk = best;
+  }
   if (splitk > nk) splitk = nk;
   if (splitk < 1) splitk = 1;
   const long long per = cdiv(nk, splitk);
@@ -1095,10 +1112,15 @@ int launch_tn(const TcGemmTnP& p, cudaStream_t st) {
     a.xc = p.xc; a.ldxc = p.ldxc; a.nxc = p.skinny ? p.nxc : 0;
     a.skinny = p.skinny; a.ldsk = p.ldsk; a.sSk = p.sSk;
   }
+  if (p.inner > 0) {
+    NF_CHECK_ARG(p.batch % p.inner == 0, NF_E_BADARG, "tc_gemm_tn: batch %d is not a multiple of the inner batch %d", p.batch, p.inner);
+    a.zin = p.inner; a.sC2 = p.sC2; a.sColsum2 = p.sColsum2; a.sSk2 = p.sSk2; a.sXc2 = p.sXc2;
+  }
   dim3 grid((unsigned)cdiv(p.M, BM), (unsigned)cdiv(p.N, BN), (unsigned)(splitk * p.batch));
   ProfScope prof(st, PROF_TC_WGRAD, 2.0 * p.M * p.N * (double)p.K * p.batch);
   CUtensorMap mC = mA;
-  a.tma_store = make_c_map(&mC, p.C, p.N, p.M, p.ldc, p.batch, p.sC) ? 1 : 0;
+  // (the bulk-tensor-store epilogue addresses C through a 3-d map with one batch stride: two-level batches store directly)
+  a.tma_store = (p.inner <= 0 && make_c_map(&mC, p.C, p.N, p.M, p.ldc, p.batch, p.sC)) ? 1 : 0;
   NF_LAUNCH((k_tc_gemm<BN, STAGES, true, BK, EPI_NONE, TS, NSG, NS>), grid, 64 + 128 * NSG, S::TOTAL, st, mA, mA, mB, mB, mB, mB, mC, a);
   NF_LAUNCHED();
   return 0;

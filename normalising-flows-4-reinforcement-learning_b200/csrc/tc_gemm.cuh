@@ -71,6 +71,9 @@ struct TcGemmTnP {
   float* colsum = nullptr; long long sColsum = 0;
   const float* xc = nullptr; long long ldxc = 0; int nxc = 0;
   float* skinny = nullptr; long long ldsk = 0, sSk = 0;
+  // two-level batch (inner > 0): z = zo * inner + zi.  A and B still advance by sA / sB per z; the outputs live at
+  // zo * s?2 + zi * s? and xc at zo * sXc2 (one launch for the weight gradients of several blocks x 2 nets)
+  int inner = 0; long long sC2 = 0, sColsum2 = 0, sSk2 = 0, sXc2 = 0;
 };
 bool tc_gemm_tn_rides_supported(const TcGemmTnP& p);
 int tc_gemm_tn(const TcGemmTnP& p, cudaStream_t st);
