@@ -501,9 +501,9 @@ class TarflowRunner(Runner):
         return {"bound": "tensor", "kernel": KERNEL_NAMES[dom], "achieved": achieved, "peak": peaks["bf16_tflops"],
                 "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"], "traffic": None,
                 "launches_timed": int(d_n),
-                "gemm_share_of_profiled_kernels": d_ms / tot_ms,
-                "note": "only the GEMM classes are profiled; the transformer flow's row kernels (LayerNorm, attention, "
-                        "GELU, tail) are outside the per-class profiler",
+                "share_of_step": d_ms / tot_ms,
+                "breakdown": {k: {"ms_per_step": v[0] / reps, "launches_per_step": v[2] // reps, "share": v[0] / tot_ms}
+                              for k, v in prof.items() if v[2]},
                 "whole_step": {"achieved": step_flops / (ms_step * 1e-3) / 1e12, "unit": "TFLOP/s",
                                "frac": step_flops / (ms_step * 1e-3) / 1e12 / peaks["bf16_tflops"],
                                "what": "train step (3 F_fwd B)" if train else "sampling pass (F_fwd B)"}}

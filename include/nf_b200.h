@@ -305,9 +305,10 @@ NF_API int nf_tarflow_backward(const NfTarflowDesc* desc, const float* params, c
 /* Optional per-kernel-class timing (CUDA events on the launching stream; off by default).  Kinds:
  * 0 tcgen05 GEMM, 1 tcgen05 weight-gradient GEMM, 2 FFMA GEMM, 3 LeakyReLU+LayerNorm fwd, 4 its backward,
  * 5 affine coupling kernels, 6 parameter-sized kernels, 7 row-fused forward/inverse tail, 8 row-fused
- * backward head, 9 row-fused backward tail, 10 column reductions over the batch rows.  nf_prof_collect sums and clears the records:
+ * backward head, 9 row-fused backward tail, 10 column reductions over the batch rows, 11 transformer-flow row kernels, 12 transformer-flow
+ * attention.  nf_prof_collect sums and clears the records:
  * ms[k] total milliseconds, work[k] algorithmic FLOPs (GEMMs) or bytes (row kernels), launches[k]. */
-#define NF_PROF_KINDS 11
+#define NF_PROF_KINDS 13
 NF_API int nf_prof_enable(int on);
 NF_API int nf_prof_collect(double* ms, double* work, int64_t* launches, int nkinds);
 

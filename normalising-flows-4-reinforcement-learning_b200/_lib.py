@@ -153,7 +153,7 @@ def graph_stats():
 
 
 PROF_KINDS = ["tc_gemm", "tc_wgrad", "simt_gemm", "ln_fwd", "ln_bwd", "affine", "param", "row_tail", "row_bwd_head",
-              "row_bwd_tail", "col_reduce"]
+              "row_bwd_tail", "col_reduce", "tf_row", "tf_attn"]
 
 
 def prof_collect():

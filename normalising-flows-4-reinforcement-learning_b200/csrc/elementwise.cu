@@ -357,6 +357,108 @@ __global__ void __launch_bounds__(256) k_affine_rowwarp(const float* __restrict_
   }
 }
 
+// Vectorised form for D % 8 == 0 (both halves are whole float4 chunks): G = 2^k lanes share a row (G >= chunks per half,
+// capped at 32), a warp covers 32 / G consecutive rows, every access is a 128-bit load / store that is contiguous across the
+// lanes of a row (and across rows for s / t), the row sum of s is an xor-shuffle reduction inside the lane group.
+// Replaces row-per-thread (D <= 64: a warp instruction touched 32 different lines) and scalar warp-per-row (D > 64).
+template <int G, bool INVERSE>
+__global__ void __launch_bounds__(256) k_affine_vec(const float* __restrict__ in, const float* __restrict__ s,
+                                                    const float* __restrict__ t, const float* __restrict__ bs,
+                                                    const float* __restrict__ bt, const float* cdev, float chost,
+                                                    long long B, int D, int ldi, int ldo, float* __restrict__ out,
+                                                    float* __restrict__ logdet, float* __restrict__ s_out) {
+  NF_PDL_ENTRY();
+  constexpr int RPW = 32 / G;                     // rows per warp
+  const int lane = threadIdx.x & 31, g = lane % G;
+  const long long row = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + lane / G;
+  const bool ok = row < B;
+  const int h4 = D >> 3;                          // float4 chunks per half (dc == dt)
+  float ssum = 0.f;
+  if (ok) {
+    const float4* xi = reinterpret_cast<const float4*>(in + row * ldi);
+    float4* xo = reinterpret_cast<float4*>(out + row * ldo);
+    const float4* sr = reinterpret_cast<const float4*>(s + row * (D >> 1));
+    const float4* tr = reinterpret_cast<const float4*>(t + row * (D >> 1));
+    float4* so = s_out ? reinterpret_cast<float4*>(s_out + row * (D >> 1)) : nullptr;
+    // two chunks per trip, all eight loads issued before the first use (D = 400: 50 chunks per half over 32 lanes)
+    for (int c = g; c < h4; c += 2 * G) {
+      const int c2 = c + G;
+      const bool two = c2 < h4;
+      const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 xc0 = xi[c], xv0 = xi[h4 + c];
+      float4 sv0 = sr[c], tv0 = tr[c];
+      const float4 xc1 = two ? xi[c2] : zero, xv1 = two ? xi[h4 + c2] : zero;
+      float4 sv1 = two ? sr[c2] : zero, tv1 = two ? tr[c2] : zero;
+      auto one = [&](int cc, const float4& xc, const float4& xv, float4& sv, float4& tv) {
+        if (bs) { const float4 b = __ldg(reinterpret_cast<const float4*>(bs) + cc); sv.x += b.x; sv.y += b.y; sv.z += b.z; sv.w += b.w; }
+        if (bt) { const float4 b = __ldg(reinterpret_cast<const float4*>(bt) + cc); tv.x += b.x; tv.y += b.y; tv.z += b.z; tv.w += b.w; }
+        float4 o;
+        if (!INVERSE) {
+          o.x = (xv.x - tv.x) * expf(-sv.x); o.y = (xv.y - tv.y) * expf(-sv.y);
+          o.z = (xv.z - tv.z) * expf(-sv.z); o.w = (xv.w - tv.w) * expf(-sv.w);
+        } else {
+          o.x = fmaf(xv.x, expf(sv.x), tv.x); o.y = fmaf(xv.y, expf(sv.y), tv.y);
+          o.z = fmaf(xv.z, expf(sv.z), tv.z); o.w = fmaf(xv.w, expf(sv.w), tv.w);
+        }
+        ssum += (sv.x + sv.y) + (sv.z + sv.w);
+        xo[cc] = xc;
+        xo[h4 + cc] = o;
+        if (so) so[cc] = sv;
+      };
+      one(c, xc0, xv0, sv0, tv0);
+      if (two) one(c2, xc1, xv1, sv1, tv1);
+    }
+  }
+#pragma unroll
+  for (int o = G >> 1; o > 0; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
+  if (ok && g == 0 && logdet) {
+    const float c = chost + (cdev ? *cdev : 0.f);
+    logdet[row] += INVERSE ? (ssum - c) : (c - ssum);
+  }
+}
+
+// backward, same lane grouping (no column sums): dxp_c = g_c; forward: dxp_t = g e^-s, ds = -g z_t - dld, dt = -g e^-s;
+// reverse direction: dxp_t = g e^s, ds = g z_t e^s + dld, dt = g
+template <int G>
+__global__ void __launch_bounds__(256) k_affine_bwd_vec(const float* __restrict__ dz, const float* __restrict__ z,
+                                                        const float* __restrict__ sfull, const float* __restrict__ dld,
+                                                        long long B, int D, float* __restrict__ dxp,
+                                                        float* __restrict__ ds, float* __restrict__ dtt, int inverse) {
+  NF_PDL_ENTRY();
+  constexpr int RPW = 32 / G;
+  const int lane = threadIdx.x & 31, g = lane % G;
+  const long long row = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + lane / G;
+  if (row >= B) return;
+  const int h4 = D >> 3;
+  const float4* gr = dz ? reinterpret_cast<const float4*>(dz + row * D) : nullptr;
+  const float4* zr = reinterpret_cast<const float4*>(z + row * D);
+  const float4* sr = reinterpret_cast<const float4*>(sfull + row * (D >> 1));
+  float4* xo = reinterpret_cast<float4*>(dxp + row * D);
+  float4* dso = reinterpret_cast<float4*>(ds + row * (D >> 1));
+  float4* dto = reinterpret_cast<float4*>(dtt + row * (D >> 1));
+  const float gl = dld ? dld[row] : 0.f;
+#pragma unroll 2
+  for (int c = g; c < h4; c += G) {
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 gc = gr ? gr[c] : zero, gt = gr ? gr[h4 + c] : zero;
+    const float4 zt = zr[h4 + c], sv = sr[c];
+    float4 ox, od, ot;
+    if (inverse) {
+      ox.x = gt.x * expf(sv.x); ox.y = gt.y * expf(sv.y); ox.z = gt.z * expf(sv.z); ox.w = gt.w * expf(sv.w);
+      od.x = fmaf(ox.x, zt.x, gl); od.y = fmaf(ox.y, zt.y, gl); od.z = fmaf(ox.z, zt.z, gl); od.w = fmaf(ox.w, zt.w, gl);
+      ot = gt;
+    } else {
+      ox.x = gt.x * expf(-sv.x); ox.y = gt.y * expf(-sv.y); ox.z = gt.z * expf(-sv.z); ox.w = gt.w * expf(-sv.w);
+      od.x = -gt.x * zt.x - gl; od.y = -gt.y * zt.y - gl; od.z = -gt.z * zt.z - gl; od.w = -gt.w * zt.w - gl;
+      ot.x = -ox.x; ot.y = -ox.y; ot.z = -ox.z; ot.w = -ox.w;
+    }
+    xo[c] = gc;
+    xo[h4 + c] = ox;
+    dso[c] = od;
+    dto[c] = ot;
+  }
+}
+
 // backward of the affine coupling: per element, plus column sums of ds/dt (last-layer bias grads)
 __global__ void __launch_bounds__(256) k_affine_bwd(const float* __restrict__ dz, const float* __restrict__ z,
                                                     const float* __restrict__ sfull, const float* __restrict__ dld,
@@ -687,6 +789,19 @@ static int affine_launch(const float* in, int ldi, const float* s, const float* 
   if (B <= 0) return 0;
   // algorithmic bytes: read xp (D), s, t (D/2 each), logdet; write z (D), logdet  
   ProfScope prof(st, PROF_AFFINE, 4.0 * B * (2.0 * D + 2.0 * (D / 2) + 2.0));
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  if (D % 8 == 0 && ldi % 4 == 0 && ldo % 4 == 0 && al16(in) && al16(out) && al16(s) && al16(t) && al16(s_out) &&
+      al16(bs) && al16(bt) && in != out) {
+    const int h4 = D / 8;
+#define NF_AFF(G)                                                                                                   \
+    NF_LAUNCH((k_affine_vec<G, INV>), (unsigned)cdiv(B, 8 * (32 / G)), 256, 0, st, in, s, t, bs, bt, cdev, chost, B, D, ldi, \
+              ldo, out, logdet, s_out)
+    if (h4 <= 1) NF_AFF(1); else if (h4 <= 2) NF_AFF(2); else if (h4 <= 4) NF_AFF(4); else if (h4 <= 8) NF_AFF(8);
+    else if (h4 <= 16) NF_AFF(16); else NF_AFF(32);
+#undef NF_AFF
+    NF_LAUNCHED();
+    return 0;
+  }
   if (D <= 64) {
     const bool vec = (D % 8 == 0) && (ldi % 4 == 0) && (ldo % 4 == 0);
     dim3 grid((unsigned)cdiv(B, 256));
@@ -721,6 +836,17 @@ int affine_bwd(const float* dz, const float* z, const float* s_full, const float
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
   ProfScope prof(st, PROF_AFFINE, 4.0 * B * (3.0 * D + 3.0 * (D / 2) + 1.0));
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  if (!g3s && !g3t && D % 8 == 0 && al16(dz) && al16(z) && al16(s_full) && al16(dxp) && al16(ds) && al16(dt)) {
+    const int h4 = D / 8;
+#define NF_AFFB(G) \
+    NF_LAUNCH((k_affine_bwd_vec<G>), (unsigned)cdiv(B, 8 * (32 / G)), 256, 0, st, dz, z, s_full, dlogdet, B, D, dxp, ds, dt, inverse)
+    if (h4 <= 1) NF_AFFB(1); else if (h4 <= 2) NF_AFFB(2); else if (h4 <= 4) NF_AFFB(4); else if (h4 <= 8) NF_AFFB(8);
+    else if (h4 <= 16) NF_AFFB(16); else NF_AFFB(32);
+#undef NF_AFFB
+    NF_LAUNCHED();
+    return 0;
+  }
   NF_LAUNCH((k_affine_bwd), (unsigned)blocks, 256, 2 * (D / 2) * sizeof(float) + 16, st, dz, z, s_full, dlogdet, B, D, dxp, ds, dt, g3s, g3t, inverse);
   NF_LAUNCHED();
   return 0;

@@ -342,7 +342,10 @@ static int plu_matmul(const Dims& m, const PackedLayout& kl, const float* A, int
     if (kl.hi_off) { t.B0hi = Bk + kl.hi_off; t.B0lo = Bk + kl.lo_off; }
     t.C = C; t.ldc = ldc; t.M = (int)B; t.N = m.D;
     t.raw_hi = 0;   // round-to-nearest split: the truncating one biases |z| low by ~1e-5 of the D = 400 log-prob sum
-    return linear_nt(m.prec, t, st);
+    // The invertible linear layer is the flow's own transform, not a conditioner: in the reduced-precision mode it stays
+    // at 3xTF32 (a single TF32 pass here put its 1e-3 rounding straight into z and the inverse: C5 z error 1.4e-3 -> 1.7e-2
+    // when this matmul first moved to the tensor cores) -- it is 1-12 % of a block's FLOPs.
+    return linear_nt(m.prec == NF_PREC_TF32 ? NF_PREC_TF32X3 : m.prec, t, st);
   }
   GemmP g;
   g.A0 = A; g.lda0 = lda; g.K0 = m.D;

@@ -19,7 +19,9 @@ enum ProfKind {
   PROF_ROW_HEAD = 8,    // row-fused backward head
   PROF_ROW_BTAIL = 9,   // row-fused backward tail
   PROF_COL_REDUCE = 10, // multi-job column reduction over the batch rows (skinny weight/bias gradients)
-  PROF_NKINDS = 11
+  PROF_TF_ROW = 11,     // transformer flow: row kernels (embedding, residual + LayerNorm, GELU, tail, column sums); work = bytes
+  PROF_TF_ATTN = 12,    // transformer flow: causal attention forward / backward; work = FLOPs
+  PROF_NKINDS = 13
 };
 
 bool prof_enabled();

@@ -26,6 +26,7 @@
 #include "elementwise.cuh"
 #include "graphs.cuh"
 #include "linear.cuh"
+#include "prof.cuh"
 
 namespace nf {
 namespace {
@@ -699,6 +700,7 @@ int rows_per_cta_for(long long rows) {
 
 int tf_embed(const float* x, const float* cproj, const float* win, const float* bin, const float* pos, float* h,
              long long B, const TfDims& m, int t0, int t1, int flip, cudaStream_t st) {
+  ProfScope prof(st, PROF_TF_ROW, 4.0 * B * (t1 - t0) * m.C);
   const long long n = B * (t1 - t0) * (m.C / 4);
   if (n <= 0) return 0;
   NF_LAUNCH((k_tf_embed), (unsigned)std::min<long long>(cdiv(n, 256), 148 * 8), 256, 0, st, x, cproj, win, bin, pos, h, B,
@@ -709,6 +711,7 @@ int tf_embed(const float* x, const float* cproj, const float* win, const float* 
 
 int tf_add_ln(const float* h_in, const float* r, float* h_out, float* a, float* stats, const float* gamma,
               const float* beta, long long rows, const TfDims& m, cudaStream_t st) {
+  ProfScope prof(st, PROF_TF_ROW, 4.0 * rows * m.C * (r ? 4 : 3));
   if (rows <= 0) return 0;
   const unsigned grid = (unsigned)cdiv(rows, 8);
   TF_NV_SWITCH(m.C, NF_LAUNCH((k_tf_add_ln<NV>), grid, 256, 0, st, h_in, r, h_out, a, reinterpret_cast<float2*>(stats),
@@ -719,6 +722,7 @@ int tf_add_ln(const float* h_in, const float* r, float* h_out, float* a, float* 
 
 int tf_ln_bwd(const float* da, const float* h, const float* stats, const float* gamma, const float* dres, float* dh_out,
               float* dgamma, float* dbeta, long long rows, const TfDims& m, cudaStream_t st) {
+  ProfScope prof(st, PROF_TF_ROW, 4.0 * rows * m.C * (dres ? 4 : 3));
   if (rows <= 0) return 0;
   const int rpc = rows_per_cta_for(rows);
   const unsigned grid = (unsigned)cdiv(rows, rpc);
@@ -740,6 +744,7 @@ int tf_ln_bwd(const float* da, const float* h, const float* stats, const float* 
 }
 
 int tf_attn_fwd(const float* qkv, float* o, float* P, long long B, const TfDims& m, int t0, int t1, cudaStream_t st) {
+  ProfScope prof(st, PROF_TF_ATTN, 4.0 * B * m.C * 0.5 * (t1 - t0) * (t0 + t1 + 1));
   if (B <= 0) return 0;
   const unsigned grid = (unsigned)cdiv(B * m.H, 4);
   const float scale = 1.0f / sqrtf((float)m.hd);
@@ -765,6 +770,7 @@ int tf_attn_bwd_t(const float* qkv, const float* o, const float* P, const float*
 }
 int tf_attn_bwd(const float* qkv, const float* o, const float* P, const float* d_o, float* dqkv, long long B,
                 const TfDims& m, cudaStream_t st) {
+  ProfScope prof(st, PROF_TF_ATTN, 8.0 * B * m.C * 0.5 * m.T * (m.T + 1));
   if (B <= 0) return 0;
   switch (m.hd / 32) {
     case 1: return tf_attn_bwd_t<1>(qkv, o, P, d_o, dqkv, B, m, st);
@@ -774,6 +780,7 @@ int tf_attn_bwd(const float* qkv, const float* o, const float* P, const float* d
 }
 
 int tf_gelu(const float* u, float* g, long long n, cudaStream_t st) {
+  ProfScope prof(st, PROF_TF_ROW, 8.0 * n);
   if (n <= 0) return 0;
   NF_LAUNCH((k_tf_gelu), (unsigned)std::min<long long>(cdiv(n / 4, 256), 148 * 16), 256, 0, st,
             reinterpret_cast<const float4*>(u), reinterpret_cast<float4*>(g), n / 4);
@@ -781,6 +788,7 @@ int tf_gelu(const float* u, float* g, long long n, cudaStream_t st) {
   return 0;
 }
 int tf_gelu_bwd(float* dg, const float* u, long long n, cudaStream_t st) {
+  ProfScope prof(st, PROF_TF_ROW, 12.0 * n);
   if (n <= 0) return 0;
   NF_LAUNCH((k_tf_gelu_bwd), (unsigned)std::min<long long>(cdiv(n / 4, 256), 148 * 16), 256, 0, st,
             reinterpret_cast<float4*>(dg), reinterpret_cast<const float4*>(u), n / 4);
@@ -794,6 +802,7 @@ struct TailArgs {
   const float* win = nullptr; const float* bin = nullptr; const float* pos = nullptr; float* hnext = nullptr;
 };
 int tf_tail(const TailArgs& a, long long B, const TfDims& m, cudaStream_t st) {
+  ProfScope prof(st, PROF_TF_ROW, 4.0 * B * (a.t1 - a.t0) * m.C * (a.r ? 2 : 1));
   if (B <= 0) return 0;
   const unsigned grid = (unsigned)cdiv(B, 8);
   TF_NV_SWITCH(m.C, NF_LAUNCH((k_tf_tail<NV>), grid, 256, 0, st, a.h, a.r, a.wout, a.bout, a.in, a.out, a.logdet, a.xa_out, B,
@@ -804,6 +813,7 @@ int tf_tail(const TailArgs& a, long long B, const TfDims& m, cudaStream_t st) {
 
 int tf_tail_bwd(const float* dz, const float* dld, const float* z, const float* xa, const float* hf, const float* wout,
                 float* dh, float* dx, float* dwout, float* dbout, long long B, const TfDims& m, int flip, cudaStream_t st) {
+  ProfScope prof(st, PROF_TF_ROW, 8.0 * B * m.A * m.C);
   if (B <= 0) return 0;
   const int rpc = rows_per_cta_for(B);
   const size_t smem = ((size_t)8 * 2 * m.C + 16) * sizeof(float);
@@ -825,6 +835,7 @@ int tf_tail_bwd(const float* dz, const float* dld, const float* z, const float* 
 
 int tf_embed_bwd(const float* dh0, const float* x, const float* win, float* dx, float* dwin, long long B, const TfDims& m,
                  int flip, cudaStream_t st) {
+  ProfScope prof(st, PROF_TF_ROW, 4.0 * B * m.A * m.C);
   if (B <= 0 || m.A < 2) return 0;
   const int rpc = rows_per_cta_for(B);
   const size_t smem = (size_t)8 * m.C * sizeof(float);
@@ -835,6 +846,7 @@ int tf_embed_bwd(const float* dh0, const float* x, const float* win, float* dx, 
 }
 
 int tf_colsum(const float* X, long long ld, long long rows, int N, float* out, cudaStream_t st) {
+  ProfScope prof(st, PROF_TF_ROW, 4.0 * rows * N);
   if (rows <= 0 || N <= 0) return 0;
   const int rpc = rows_per_cta_for(rows);
   NF_LAUNCH((k_tf_colsum), dim3((unsigned)cdiv(rows, rpc), (unsigned)cdiv(N, 128)), 128, 0, st, X, ld, rows, N, out, rpc);

@@ -49,6 +49,7 @@ struct KArgs {
   // xc[k, j], j < nxc <= 16 (the x_cond columns of dW1) -- instead of a separate column-reduction pass over A
   float* colsum; long long sColsum;
   const float* xc; long long ldxc; int nxc;
+  int xc_vec;                            // xc rows may be read as float4 chunks (aligned, 4 ceil(nxc / 4) <= row length)
   float* skinny; long long ldsk, sSk;
   // MN-major form, two-level batch (zin > 0): z = zo * zin + zi; A / B keep one uniform stride (TMA coordinate z), the
   // outputs live at zo * s?2 + zi * s? (the per-block / per-net slots of the gradient arena) and xc at zo * sXc2
@@ -365,7 +366,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
     const int t = (threadIdx.x - 64) & 127;       // 0..127 inside the splitter group
     const int grp = (threadIdx.x - 64) >> 7;      // splitter group: takes the stages with it % NSG == grp
     const bool nosplit = NS || (!TS && a.passes == 1 && a.raw_hi);
-    constexpr int kMaxXc = 16;
+    constexpr int kMaxXc = 16, kVecXc = 8;   // (the 128-bit path keeps 4 rows x kVecXc columns in registers)
     const bool ride = MNMAJOR && TS && blockIdx.y == 0 && (a.colsum != nullptr || a.skinny != nullptr);
     float csum = 0.f, sk[kMaxXc];
 #pragma unroll
@@ -393,16 +394,45 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
                     ((av[2].x + av[2].y) + (av[2].z + av[2].w)) + ((av[3].x + av[3].y) + (av[3].z + av[3].w));
             if (a.skinny) {
               const long long k0 = (long long)(kc_begin + it) * BK;
+              const float* xbase = a.xc + (long long)z_o * a.sXc2;
+              if (a.xc_vec) {
+                // rows of xc as 128-bit loads (same address in every lane: one broadcast transaction each), four rows
+                // in flight at a time -- as scalar loads this rode at 3 100 cycles per stage (ncu, C2a batched dW1)
 #pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                const float e4[4] = {av[c].x, av[c].y, av[c].z, av[c].w};
+                for (int c = 0; c < 4; ++c) {
+                  const float e4[4] = {av[c].x, av[c].y, av[c].z, av[c].w};
+                  float4 xv[4][kVecXc / 4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const long long kr = min(k0 + 4 * c + e, (long long)a.K0 - 1);
-                  const float* xr = a.xc + (long long)z_o * a.sXc2 + kr * a.ldxc;      // same address in every lane: one broadcast transaction
+                  for (int e = 0; e < 4; ++e) {
+                    const long long kr = min(k0 + 4 * c + e, (long long)a.K0 - 1);
+                    const float4* xr = reinterpret_cast<const float4*>(xbase + kr * a.ldxc);
 #pragma unroll
-                  for (int j = 0; j < kMaxXc; ++j)
-                    if (j < a.nxc) sk[j] = fmaf(e4[e], __ldg(xr + j), sk[j]);
+                    for (int j4 = 0; j4 < kVecXc / 4; ++j4)
+                      xv[e][j4] = 4 * j4 < a.nxc ? __ldg(xr + j4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                  }
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+#pragma unroll
+                    for (int j4 = 0; j4 < kVecXc / 4; ++j4) {
+                      if (4 * j4 < a.nxc) {
+                        sk[4 * j4] = fmaf(e4[e], xv[e][j4].x, sk[4 * j4]); sk[4 * j4 + 1] = fmaf(e4[e], xv[e][j4].y, sk[4 * j4 + 1]);
+                        sk[4 * j4 + 2] = fmaf(e4[e], xv[e][j4].z, sk[4 * j4 + 2]); sk[4 * j4 + 3] = fmaf(e4[e], xv[e][j4].w, sk[4 * j4 + 3]);
+                      }
+                    }
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                  const float e4[4] = {av[c].x, av[c].y, av[c].z, av[c].w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const long long kr = min(k0 + 4 * c + e, (long long)a.K0 - 1);
+                    const float* xr = xbase + kr * a.ldxc;      // same address in every lane: one broadcast transaction
+#pragma unroll
+                    for (int j = 0; j < kMaxXc; ++j)
+                      if (j < a.nxc) sk[j] = fmaf(e4[e], __ldg(xr + j), sk[j]);
+                  }
                 }
               }
             }
@@ -1110,6 +1140,8 @@ int launch_tn(const TcGemmTnP& p, cudaStream_t st) {
     NF_CHECK_ARG(!p.skinny || (p.xc && p.nxc >= 1 && p.nxc <= 16), NF_E_BADARG, "tc_gemm_tn: 1..16 skinny columns, got %d", p.nxc);
     a.colsum = p.colsum; a.sColsum = p.sColsum;
     a.xc = p.xc; a.ldxc = p.ldxc; a.nxc = p.skinny ? p.nxc : 0;
+    a.xc_vec = p.skinny && (p.ldxc & 3) == 0 && (reinterpret_cast<uintptr_t>(p.xc) & 15u) == 0 && (p.sXc2 & 3) == 0 &&
+               4 * ((p.nxc + 3) / 4) <= p.ldxc && p.nxc <= 8;
     a.skinny = p.skinny; a.ldsk = p.ldsk; a.sSk = p.sSk;
   }
   if (p.inner > 0) {

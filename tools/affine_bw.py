@@ -1,5 +1,6 @@
 """Achieved HBM bandwidth of the standalone affine / log-det kernels of the C ABI (SURVEY section 8d:
-4*(2D + 2dt + 2) algorithmic bytes per row) and of the row tail at a streaming batch size."""
+4*(2D + 2dt + 2) algorithmic bytes per row forward / inverse; backward reads dz (D), z_t, s (dt each), dlogdet and writes dxp
+(D), ds, dt: 4*(2D + 4dt + 1)) and of the row tail at a streaming batch size."""
 import sys, os, ctypes, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -23,7 +24,7 @@ for D, B in ((8, 1 << 23), (32, 1 << 22), (400, 1 << 18)):
     def inv(): lib.nf_affine_logdet_inv(z.data_ptr(), s.data_ptr(), t.data_ptr(), None, None, 0.0, B, D, xp.data_ptr(), ld.data_ptr(), st)
     def bwd(): lib.nf_affine_logdet_bwd(dz.data_ptr(), z.data_ptr(), s.data_ptr(), dld.data_ptr(), B, D, dxp.data_ptr(), ds.data_ptr(), dtt.data_ptr(), st)
     for name, fn, nbytes in (("fwd", fwd, 4 * (2 * D + 2 * dt + 2) * B), ("inv", inv, 4 * (2 * D + 2 * dt + 2) * B),
-                             ("bwd", bwd, 4 * (3 * D + 3 * dt + 1) * B)):
+                             ("bwd", bwd, 4 * (2 * D + 4 * dt + 1) * B)):
         for _ in range(3): fn()
         ms = []
         for _ in range(5):
