@@ -227,6 +227,11 @@ NF_API int nf_linear_wgrad(const float* dY, int64_t lddy, const float* X, int64_
  *                     one kernel (counter-based Philox4x32-10 + Box-Muller; the normal at index i is a pure function of
  *                     (seed, offset + i / 4, i % 4), so a caller advances `offset` by ceil(n / 4) per call); out may
  *                     alias x. */
+/*   nf_logprob_group_argmin  per group g of N candidates: n* = argmin_n [log N(z_gn; 0, I) + logdet_gn] (ties: smaller n),
+ *                     out_x[g] = x[g, n*], out_idx[g] = n*, out_lp[g] = the minimum (each output optional): the exploration-goal
+ *                     selection of unsupservised-gcrl/train_auto_NF_rl.py:328-333 without the (G, N) round trip. */
+NF_API int nf_logprob_group_argmin(const float* z, const float* logdet, const float* x, int64_t G, int64_t N, int32_t D,
+                                   float* out_x, int64_t* out_idx, float* out_lp, void* stream);
 NF_API int nf_noise_augment(const float* x, int64_t n, float std_, uint64_t seed, uint64_t offset, float* out, void* stream);
 NF_API int nf_nll_forward(const float* z, const float* logdet, int64_t B, int32_t D, float* loss, void* stream);
 NF_API int nf_nll_cotangents(const float* z, const float* g, int64_t B, int32_t D, float* dz, float* dld, void* stream);

@@ -1050,6 +1050,70 @@ int nll_cotangents(const float* z, const float* g, long long B, int D, float* dz
 }
 
 // ------------------------------------------------------------------------------------------
+// Group-wise argmin of the log-probability (unsupservised-gcrl/train_auto_NF_rl.py:328-333: for every environment the
+// candidate goal with the LOWEST log N(z) + logdet among its N candidates is the next exploration goal): one CTA per group
+// computes lp[n] = -0.5 |z_n|^2 - D/2 log(2 pi) + logdet[n], reduces (value, index) with ties to the smaller index
+// (jnp.argmin), and copies the winning candidate row.  Replaces log_prob -> argmin -> gather (and the (G, N) round trip).
+// ------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) k_group_argmin_logp(const float* __restrict__ z, const float* __restrict__ logdet,
+                                                           const float* __restrict__ x, long long N, int D,
+                                                           float* __restrict__ out_x, long long* __restrict__ out_idx,
+                                                           float* __restrict__ out_lp) {
+  NF_PDL_ENTRY();
+  __shared__ float s_v[8];
+  __shared__ long long s_i[8];
+  const long long g = blockIdx.x;
+  const float c = -0.5f * (float)D * 1.8378770664093453f;
+  float best = INFINITY;
+  long long bi = 0x7fffffffffffffffll;
+  for (long long n = threadIdx.x; n < N; n += blockDim.x) {
+    const float* zr = z + (g * N + n) * D;
+    float ss = 0.f;
+    for (int j = 0; j < D; ++j) ss = fmaf(zr[j], zr[j], ss);
+    const float lp = fmaf(-0.5f, ss, c) + logdet[g * N + n];
+    if (lp < best || (lp == best && n < bi)) { best = lp; bi = n; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov < best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { s_v[threadIdx.x >> 5] = best; s_i[threadIdx.x >> 5] = bi; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    best = threadIdx.x < (blockDim.x >> 5) ? s_v[threadIdx.x] : INFINITY;
+    bi = threadIdx.x < (blockDim.x >> 5) ? s_i[threadIdx.x] : 0x7fffffffffffffffll;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov < best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (threadIdx.x == 0) { s_v[0] = best; s_i[0] = bi; }
+  }
+  __syncthreads();
+  bi = s_i[0];
+  if (bi >= N) bi = 0;      // every candidate NaN / +inf: fall back to the first one
+  if (threadIdx.x == 0) {
+    if (out_idx) out_idx[g] = bi;
+    if (out_lp) out_lp[g] = s_v[0];
+  }
+  if (out_x && x)
+    for (int j = threadIdx.x; j < D; j += blockDim.x) out_x[g * D + j] = x[(g * N + bi) * D + j];
+}
+}  // namespace
+
+int group_argmin_logp(const float* z, const float* logdet, const float* x, long long G, long long N, int D, float* out_x,
+                      long long* out_idx, float* out_lp, cudaStream_t st) {
+  if (G <= 0 || N <= 0) return 0;
+  NF_LAUNCH((k_group_argmin_logp), (unsigned)G, 256, 0, st, z, logdet, x, N, D, out_x, out_idx, out_lp);
+  NF_LAUNCHED();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
 // noise augmentation  out = x + std * N(0, 1)   (torch_nfbc_ant.py:264-265: naction + 0.1 * randn_like(naction))
 // ------------------------------------------------------------------------------------------
 // Counter-based Philox4x32-10 (Salmon et al. 2011; the generator behind torch.randn on CUDA): element group g = i / 4

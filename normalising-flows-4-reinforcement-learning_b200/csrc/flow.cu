@@ -1610,6 +1610,16 @@ int nf_nll_cotangents(const float* z, const float* g, int64_t B, int32_t D, floa
   return nll_cotangents(z, g, B, D, dz, dld, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int nf_logprob_group_argmin(const float* z, const float* logdet, const float* x, int64_t G, int64_t N, int32_t D,
+                            float* out_x, int64_t* out_idx, float* out_lp, void* stream) {
+  NF_CHECK_ARG(D >= 1 && G >= 0 && N >= 1 && G <= 0x7fffffff, NF_E_BADARG, "bad shape G=%lld N=%lld D=%d", (long long)G,
+               (long long)N, D);
+  NF_TRY(check_ptr(z, "z", G > 0)); NF_TRY(check_ptr(logdet, "logdet", G > 0)); NF_TRY(check_ptr(x, "x", out_x != nullptr));
+  static_assert(sizeof(long long) == sizeof(int64_t), "index type");
+  return group_argmin_logp(z, logdet, x, G, N, D, out_x, reinterpret_cast<long long*>(out_idx), out_lp,
+                           reinterpret_cast<cudaStream_t>(stream));
+}
+
 int nf_noise_augment(const float* x, int64_t n, float std_, uint64_t seed, uint64_t offset, float* out, void* stream) {
   NF_CHECK_ARG(n >= 0, NF_E_BADARG, "n=%lld out of range", (long long)n);
   NF_TRY(check_ptr(x, "x", n > 0)); NF_TRY(check_ptr(out, "out", n > 0));

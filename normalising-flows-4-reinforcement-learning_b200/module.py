@@ -785,6 +785,27 @@ class RealNVP(nn.Module):
         z, logdet = res[0], res[-1]
         return -0.5 * (z * z).sum(dim=1) - 0.5 * self.in_channels * math.log(2.0 * math.pi) + logdet
 
+    @torch.no_grad()
+    def argmin_log_prob(self, x, y=None, return_index=False):
+        """For candidates ``x (G, N, D)`` (conditioning ``y (G, N, R)`` or ``None`` = the masked, all-zero conditioning of
+        the caller): the candidate with the LOWEST log-probability of every group, ``(G, D)`` -- the exploration-goal
+        selection ``rg[argmin(prior.log_prob(z) + logdets)]`` of unsupservised-gcrl/train_auto_NF_rl.py:328-333, vmapped
+        over the groups.  One flow forward over the G * N rows (``y = None`` takes the y == 0 fast path) and one reduction
+        kernel (``nf_logprob_group_argmin``); ties go to the smaller index like ``jnp.argmin``."""
+        if x.dim() != 3 or x.shape[2] != self.in_channels:
+            raise ValueError(f"x must be (G, N, {self.in_channels}), got {tuple(x.shape)}")
+        G, N, D = x.shape
+        xf = _dense(x.reshape(G * N, D))
+        yf = _dense(y.reshape(G * N, -1)) if y is not None else None
+        res = self.forward(xf, yf)
+        z, logdet = _dense(res[0]), _dense(res[-1])
+        out = torch.empty((G, D), dtype=torch.float32, device=x.device)
+        idx = torch.empty((G,), dtype=torch.int64, device=x.device)
+        with _on(x.device):
+            _lib.check(lib.nf_logprob_group_argmin(z.data_ptr(), logdet.data_ptr(), xf.data_ptr(), G, N, D, out.data_ptr(),
+                                                   idx.data_ptr(), None, self._stream(x.device)), "nf_logprob_group_argmin")
+        return (out, idx) if return_index else out
+
     def augment(self, x, noise_std, seed=0):
         """``x + noise_std * randn_like(x)`` -- the training-time noise augmentation of torch_nfbc_ant.py:264-265 -- as
         one library kernel (nf_noise_augment: counter-based Philox4x32-10 + Box-Muller).  The module keeps a running

@@ -787,3 +787,32 @@ def test_flax_semantics_flags(D, C, R, n, B):
         z2, ld2 = m(t(x), t(y))
     assert rel_err(xr.cpu().numpy(), rx) <= 1e-4 and rel_err(rl.cpu().numpy(), rld) <= 1e-4
     assert torch.allclose(z2, z.detach(), atol=1e-6) and torch.allclose(ld2, ld.detach(), atol=1e-5)
+
+
+def test_group_argmin_of_log_prob_matches_the_oracle():
+    """The exploration-goal selection of unsupservised-gcrl/train_auto_NF_rl.py:328-333 -- for every group of N candidate
+    goals the one with the lowest log N(z) + logdet under masked (all-zero) conditioning -- as one forward + one reduction
+    kernel: indices and rows equal argmin over the float64 oracle's log-probabilities (flax-variant network: H1 = C + R,
+    eps 1e-6; D = 2 like the goal xy of the reference)."""
+    D, C, R, n, G, N = 2, 64, 16, 3, 37, 50
+    sd = synth.make_state_dict(D, C, R, n, seed=71, H1=C + R)
+    rs = np.random.RandomState(72)
+    x = rs.uniform(-1, 1, size=(G, N, D)).astype(np.float32)
+    model = nf_b200.RealNVP(D, C, R, n, None, first_hidden=C + R, ln_eps=1e-6)
+    model.load_state_dict({k: torch.tensor(v) for k, v in sd.items()})
+    model = model.to(dev())
+    sd64 = fo.cast_state_dict(sd, np.float64)
+    z, _, ld = fo.flow_forward(sd64, n, x.reshape(G * N, D).astype(np.float64), np.zeros((G * N, R)), eps=1e-6)[:3]
+    lp = (-0.5 * (z * z).sum(1) - 0.5 * D * np.log(2 * np.pi) + ld).reshape(G, N)
+    want = lp.argmin(1)
+    for yy in (None, torch.zeros(G, N, R, device=dev())):
+        got, idx = model.argmin_log_prob(t(x), yy, return_index=True)
+        idx = idx.cpu().numpy()
+        # (a float32 near-tie may pick the runner-up: accept it when the two log-probabilities agree to 1e-5)
+        for g in range(G):
+            assert idx[g] == want[g] or abs(lp[g, idx[g]] - lp[g, want[g]]) <= 1e-5 * max(1.0, abs(lp[g, want[g]])), (g, idx[g], want[g])
+        assert np.array_equal(got.cpu().numpy(), x[np.arange(G), idx])
+    # ties go to the smaller index (jnp.argmin): identical candidates
+    xt = t(np.repeat(x[:, :1], 4, axis=1).copy())
+    _, idx = model.argmin_log_prob(xt, None, return_index=True)
+    assert int(idx.abs().max()) == 0
