@@ -331,7 +331,8 @@ NF_API int nf_graphs_stats(int64_t* replays, int64_t* captures, int64_t* eager);
  * (flow tail in the layer-2 GEMM, 0), "bn256" (256-wide tiles: 0 auto / 1 / 2 never), "stack" (persistent whole-stack
  * forward / inverse kernel: -1 auto / 0 / 1), "ride" (bias / x_cond weight gradients
  * taken along by the weight-gradient GEMMs instead of a column-reduction pass, 1), "defer_wgrad" (conditioner weight
- * gradients of all blocks in two batched launches after the block loop: -1 auto while the flow is small / 0 / 1), "whatif" (experiments only: skips
+ * gradients of all blocks in two batched launches after the block loop: -1 auto while the flow is small / 0 / 1), "mcast"
+ * (weight tiles of the large conditioner GEMMs multicast over CTA pairs: -1 auto / 0 / 1), "whatif" (experiments only: skips
  * backward work, wrong gradients).  Every setting computes the
  * same function (tests/test_flow_gpu.py::test_options_are_equivalent); setting one clears the launch graphs. */
 NF_API int nf_set_option(const char* name, int value);

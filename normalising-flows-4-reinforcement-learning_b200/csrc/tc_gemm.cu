@@ -106,7 +106,12 @@ struct Smem {
 // with clock64) against 384 cycles of MMAs, so the TS kernels run two groups on alternating stages; both groups
 // share the epilogue (plain: alternating 32-column chunks; row-wise: each group owns half of the tile's columns, which
 // also halves the registers a thread needs for its row -- 320 threads leave 200 per thread).
-template <int BN, int STAGES, bool MNMAJOR, int BK, int EPI = EPI_NONE, bool TS = false, int NSG = 1, bool NS = false>
+// MC = true (K-major TS form with pre-split weights, plain epilogue): the two CTAs of a (2, 1, 1) cluster compute
+// neighbouring row tiles of the same output columns, i.e. they consume the SAME weight tiles.  Each loads half of every B
+// tile (hi and lo) and the TMA multicasts it into both CTAs' stage, so a weight tile leaves L2 once per CTA pair (16 KB ->
+// 8 KB per stage and CTA, section 8 of DESIGN.md).  A stage may be refilled only when BOTH CTAs' MMAs have read it: the
+// MMA commits arrive on the empty barrier of both CTAs (count 2).
+template <int BN, int STAGES, bool MNMAJOR, int BK, int EPI = EPI_NONE, bool TS = false, int NSG = 1, bool NS = false, bool MC = false>
 __global__ void __launch_bounds__(64 + 128 * NSG, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUtensorMap mA1,
           const __grid_constant__ CUtensorMap mB0, const __grid_constant__ CUtensorMap mB1,
@@ -114,6 +119,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
           const __grid_constant__ CUtensorMap mC, const KArgs a) {
   using S = Smem<BN, STAGES, BK, TS, NS>;
   static_assert(!NS || !TS, "the no-split form feeds both operands from shared memory");
+  static_assert(!MC || (TS && !MNMAJOR && EPI == EPI_NONE), "weight-tile multicast: K-major TS form, plain epilogue");
   constexpr int A_BYTES = S::A_BYTES;
   constexpr int BOX = 32 * BK * 4;   // bytes of one 32-column MN-major TMA box
   extern __shared__ uint8_t smem_dyn[];
@@ -187,7 +193,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
     if (a.tma_store) prefetch_tmap(&mC);
     if (TS && a.b_presplit) { prefetch_tmap(&mB0l); if (nk1) prefetch_tmap(&mB1l); }
     if (nk1) { prefetch_tmap(&mA1); prefetch_tmap(&mB1); }
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&split[s], 4); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&split[s], 4); mbar_init(&empty[s], MC ? 2 : 1); }
     mbar_init(accbar, 1);
     if (TS) for (int i = 0; i < kASlots; ++i) mbar_init(&aempty[i], 1);
     if (EPI != EPI_NONE) mbar_init(xbar, (uint32_t)a.ncl * 128u * NSG);
@@ -201,7 +207,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (EPI != EPI_NONE) cluster_sync_all();   // every CTA's exchange barrier is initialised before a peer arrives on it
+  if (EPI != EPI_NONE || MC) cluster_sync_all();   // every CTA's barriers are initialised before a peer arrives on them
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
   // everything above (barrier init, TMEM allocation, tensor-map prefetch) overlaps the previous kernel
@@ -231,9 +237,17 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
             const bool seg1 = g >= nk0;
             const int kk = (seg1 ? g - nk0 : g) * BK;
             tma_load_3d(st, seg1 ? &mA1 : &mA0, &full[s], kk, m0, (seg1 ? a.zA1 : a.zA0) ? z : 0);
+            if constexpr (MC) {
+              // this CTA's half of the weight tile (BN / 2 rows of hi and of lo), delivered to both CTAs of the pair
+              const int half = (int)cluster_ctarank() * (BN / 2);
+              const int zb = (seg1 ? a.zB1 : a.zB0) ? z : 0;
+              tma_load_3d_mc(st + A_BYTES + half * BK * 4, seg1 ? &mB1 : &mB0, &full[s], kk, n0 + half, zb, (uint16_t)3);
+              tma_load_3d_mc(st + S::LO + A_BYTES + half * BK * 4, seg1 ? &mB1l : &mB0l, &full[s], kk, n0 + half, zb, (uint16_t)3);
+            } else {
             tma_load_3d(st + A_BYTES, seg1 ? &mB1 : &mB0, &full[s], kk, n0, (seg1 ? a.zB1 : a.zB0) ? z : 0);
             if (TS && a.b_presplit)   // the lo tile lands where the in-kernel split would have put it
               tma_load_3d(st + S::LO + A_BYTES, seg1 ? &mB1l : &mB0l, &full[s], kk, n0, (seg1 ? a.zB1 : a.zB0) ? z : 0);
+            }
           }
         }
         __syncwarp();
@@ -332,13 +346,15 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         issue_stage(st_lo, ta_slot, nks0);
         if (leader) {
-          umma_commit(&empty[s]);   // frees the stage once the MMAs above have read it
+          if constexpr (MC) umma_commit_mc(&empty[s], (uint16_t)3);   // both CTAs of the pair refill this stage's weights
+          else umma_commit(&empty[s]);   // frees the stage once the MMAs above have read it
           if (TS) umma_commit(&aempty[aslot]);
         }
         if (two) {
           issue_stage(lo1, ta1, nks1);
           if (leader) {
-            umma_commit(&empty[s1]);
+            if constexpr (MC) umma_commit_mc(&empty[s1], (uint16_t)3);
+            else umma_commit(&empty[s1]);
             if (TS) umma_commit(&aempty[aslot1]);
           }
         }
@@ -870,6 +886,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
 #undef NF_TS
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (MC) cluster_sync_all();   // the peer may still multicast into this CTA's stages / arrive on its barriers
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
@@ -939,7 +956,7 @@ int set_smem() {
 
 int pick_nacc() { return option(NF_OPT_NACC); }   // 0 = kernel default (all NACC accumulators)
 
-template <int BN, int STAGES, int BK, bool TS = false, bool NS = false, int NSG_ = 0>
+template <int BN, int STAGES, int BK, bool TS = false, bool NS = false, int NSG_ = 0, bool MC = false>
 int launch(const TcGemmP& p, cudaStream_t st) {
   using S = Smem<BN, STAGES, BK, TS, NS>;
   constexpr int NSG = NSG_ ? NSG_ : (TS ? 2 : 1);
@@ -947,7 +964,7 @@ int launch(const TcGemmP& p, cudaStream_t st) {
   {
     static PerDeviceOnce once;
     if (once.first()) {
-      NF_CUDA(cudaFuncSetAttribute((k_tc_gemm<BN, STAGES, false, BK, EPI_NONE, TS, NSG, NS>),
+      NF_CUDA(cudaFuncSetAttribute((k_tc_gemm<BN, STAGES, false, BK, EPI_NONE, TS, NSG, NS, MC>),
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     }
   }
@@ -956,14 +973,16 @@ int launch(const TcGemmP& p, cudaStream_t st) {
   // pre-split weight tables (hi / lo) feed the TS form directly
   const bool pre = TS && option(NF_OPT_PRESPLIT) != 0 && p.B0hi && p.B0lo && (p.K1 <= 0 || (p.B1hi && p.B1lo));
   if ((r = make_map(&mA0, p.A0, p.K0, p.M, p.lda0, p.batch, p.sA0, BK, BM, swz))) return r;
-  if ((r = make_map(&mB0, pre ? p.B0hi : p.B0, p.K0, p.N, p.ldb0, p.batch, p.sB0, BK, BN, swz))) return r;
+  constexpr int BROWS = MC ? BN / 2 : BN;     // rows of one weight box (multicast: each CTA of the pair loads half a tile)
+  NF_CHECK_ARG(!MC || pre, NF_E_UNSUPPORTED, "tc_gemm: the multicast form needs pre-split weights");
+  if ((r = make_map(&mB0, pre ? p.B0hi : p.B0, p.K0, p.N, p.ldb0, p.batch, p.sB0, BK, BROWS, swz))) return r;
   mB0l = mB0;
-  if (pre && (r = make_map(&mB0l, p.B0lo, p.K0, p.N, p.ldb0, p.batch, p.sB0, BK, BN, swz))) return r;
+  if (pre && (r = make_map(&mB0l, p.B0lo, p.K0, p.N, p.ldb0, p.batch, p.sB0, BK, BROWS, swz))) return r;
   if (p.K1 > 0) {
     if ((r = make_map(&mA1, p.A1, p.K1, p.M, p.lda1, p.batch, p.sA1, BK, BM, swz))) return r;
-    if ((r = make_map(&mB1, pre ? p.B1hi : p.B1, p.K1, p.N, p.ldb1, p.batch, p.sB1, BK, BN, swz))) return r;
+    if ((r = make_map(&mB1, pre ? p.B1hi : p.B1, p.K1, p.N, p.ldb1, p.batch, p.sB1, BK, BROWS, swz))) return r;
     mB1l = mB1;
-    if (pre && (r = make_map(&mB1l, p.B1lo, p.K1, p.N, p.ldb1, p.batch, p.sB1, BK, BN, swz))) return r;
+    if (pre && (r = make_map(&mB1l, p.B1lo, p.K1, p.N, p.ldb1, p.batch, p.sB1, BK, BROWS, swz))) return r;
   } else {
     mA1 = mA0; mB1 = mB0; mB1l = mB0l;
   }
@@ -992,7 +1011,23 @@ int launch(const TcGemmP& p, cudaStream_t st) {
   CUtensorMap mC = mA0;
   a.tma_store = make_c_map(&mC, p.C, p.N, p.M, p.ldc, p.batch, p.sC) ? 1 : 0;
   a.b_presplit = pre ? 1 : 0;
-  NF_LAUNCH((k_tc_gemm<BN, STAGES, false, BK, EPI_NONE, TS, NSG, NS>), grid, 64 + 128 * NSG, S::TOTAL, st, mA0, mA1, mB0, mB1, mB0l, mB1l, mC, a);
+  if constexpr (MC) {
+    NF_CHECK_ARG(splitk == 1, NF_E_UNSUPPORTED, "tc_gemm: the multicast form does not split the reduction");
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((grid.x + 1u) & ~1u, grid.y, grid.z);      // whole pairs: an odd last row tile gets an idle partner
+    cfg.blockDim = dim3(64 + 128 * NSG);
+    cfg.dynamicSmemBytes = S::TOTAL;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    NF_CUDA(cudaLaunchKernelEx(&cfg, k_tc_gemm<BN, STAGES, false, BK, EPI_NONE, TS, NSG, NS, MC>, mA0, mA1, mB0, mB1, mB0l, mB1l, mC, a));
+  } else {
+  NF_LAUNCH((k_tc_gemm<BN, STAGES, false, BK, EPI_NONE, TS, NSG, NS, MC>), grid, 64 + 128 * NSG, S::TOTAL, st, mA0, mA1, mB0, mB1, mB0l, mB1l, mC, a);
+  }
   NF_LAUNCHED();
   return 0;
 }
@@ -1009,19 +1044,22 @@ int launch_epi(const TcGemmP& p, cudaStream_t st) {
                                  S::TOTAL_EPI));
   }
   int r;
+  constexpr bool MC = false;   // (the fused-epilogue kernels keep their own cluster along N: no weight-tile multicast)
   CUtensorMap mA0, mA1, mB0, mB1, mB0l, mB1l;
   const CUtensorMapSwizzle swz = BK == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   // pre-split weight tables (hi / lo) feed the TS form directly
   const bool pre = TS && option(NF_OPT_PRESPLIT) != 0 && p.B0hi && p.B0lo && (p.K1 <= 0 || (p.B1hi && p.B1lo));
   if ((r = make_map(&mA0, p.A0, p.K0, p.M, p.lda0, p.batch, p.sA0, BK, BM, swz))) return r;
-  if ((r = make_map(&mB0, pre ? p.B0hi : p.B0, p.K0, p.N, p.ldb0, p.batch, p.sB0, BK, BN, swz))) return r;
+  constexpr int BROWS = MC ? BN / 2 : BN;     // rows of one weight box (multicast: each CTA of the pair loads half a tile)
+  NF_CHECK_ARG(!MC || pre, NF_E_UNSUPPORTED, "tc_gemm: the multicast form needs pre-split weights");
+  if ((r = make_map(&mB0, pre ? p.B0hi : p.B0, p.K0, p.N, p.ldb0, p.batch, p.sB0, BK, BROWS, swz))) return r;
   mB0l = mB0;
-  if (pre && (r = make_map(&mB0l, p.B0lo, p.K0, p.N, p.ldb0, p.batch, p.sB0, BK, BN, swz))) return r;
+  if (pre && (r = make_map(&mB0l, p.B0lo, p.K0, p.N, p.ldb0, p.batch, p.sB0, BK, BROWS, swz))) return r;
   if (p.K1 > 0) {
     if ((r = make_map(&mA1, p.A1, p.K1, p.M, p.lda1, p.batch, p.sA1, BK, BM, swz))) return r;
-    if ((r = make_map(&mB1, pre ? p.B1hi : p.B1, p.K1, p.N, p.ldb1, p.batch, p.sB1, BK, BN, swz))) return r;
+    if ((r = make_map(&mB1, pre ? p.B1hi : p.B1, p.K1, p.N, p.ldb1, p.batch, p.sB1, BK, BROWS, swz))) return r;
     mB1l = mB1;
-    if (pre && (r = make_map(&mB1l, p.B1lo, p.K1, p.N, p.ldb1, p.batch, p.sB1, BK, BN, swz))) return r;
+    if (pre && (r = make_map(&mB1l, p.B1lo, p.K1, p.N, p.ldb1, p.batch, p.sB1, BK, BROWS, swz))) return r;
   } else {
     mA1 = mA0; mB1 = mB0; mB1l = mB0l;
   }
@@ -1245,7 +1283,20 @@ int tc_gemm(const TcGemmP& p, cudaStream_t st) {
   const bool ts = option(NF_OPT_TS) != 0;
   if (p.N > 64) {
     if (option(NF_OPT_TS) == 2) return launch<128, 4, 16, true>(p, st);   // experiment: half the stage ring
-    if (ts) return launch<128, 8, 16, true>(p, st);
+    if (ts) {
+      // weight-tile multicast over CTA pairs: large grids only (several waves of tiles: the L2 fabric is the shared
+      // resource there), pre-split weights, no split-K (option "mcast": -1 auto, 0 never, 1 whenever possible)
+      const int mc = option(NF_OPT_MCAST);
+      const bool pre = option(NF_OPT_PRESPLIT) != 0 && p.B0hi && p.B0lo && (p.K1 <= 0 || (p.B1hi && p.B1lo));
+      const long long tiles = cdiv(p.M, BM) * cdiv(p.N, 128) * p.batch;
+      const bool nosplit = !(p.accumulate && tiles * 2 <= 148);
+      // measured (tools/quick_time.py, B = 8192 / 16384): C4 (N = 512) forward 3.169 -> 3.001 ms, C3 (N = 256 / 320) 0.793 ->
+      // 0.777 ms, but C5 (N = 1024, K = 1024) 9.48 -> 9.78 ms -- pairing two CTAs couples their pipelines, and with eight
+      // column tiles per row tile the A tiles already share L2 well; auto therefore stops at N = 512
+      if (mc != 0 && pre && nosplit && p.M > BM && p.N % 64 == 0 && (mc == 1 || (tiles >= 2 * 148 && p.N <= 512)))
+        return launch<128, 8, 16, true, false, 0, true>(p, st);
+      return launch<128, 8, 16, true>(p, st);
+    }
     return launch<128, 6, 16>(p, st);
   }
   return ts ? launch<64, 12, 16, true>(p, st) : launch<64, 8, 16>(p, st);
