@@ -147,6 +147,34 @@ def config_dict(name, world, precision="fp32"):
 # --------------------------------------------------------------------------------------------------
 # CPU arm: the reference's op sequence in stock PyTorch (oracle/torch_flow.py) on the host cores
 # --------------------------------------------------------------------------------------------------
+def reference_module():
+    """The UNMODIFIED reference file il-and-cil/utils/torch_fcnf.py, staged by __graft_entry__.build() into the git-ignored
+    oracle/_ref/ (it travels with the gpurun snapshot; /root/reference does not exist on the GPU box).  None when absent."""
+    path = os.path.join(ROOT, "oracle", "_ref", "torch_fcnf.py")
+    if not os.path.exists(path):
+        return None
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("nf_reference_torch_fcnf", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def cpu_kind(cfgname):
+    """"reference" when the CPU arm of this configuration runs the staged reference file itself (torch widths and eps only:
+    the flax twin's H1 = C + R / eps 1e-6 network exists upstream only in JAX), else "port" (oracle/torch_flow.py)."""
+    cfg = config_of(cfgname)
+    return "reference" if (cfg["H1"] == cfg["C"] and cfg["ln_eps"] == 1e-5 and reference_module() is not None) else "port"
+
+
+def cpu_what(cfgname):
+    if cpu_kind(cfgname) == "reference":
+        return ("the unmodified reference module il-and-cil/utils/torch_fcnf.py staged in oracle/_ref/ by build(), with the "
+                "scripts' MultivariateNormal prior and loss line")
+    return ("oracle/torch_flow.py, the reference's op sequence restated in stock PyTorch: the staged reference file is "
+            "absent or this configuration uses the flax twin's widths")
+
+
 def cpu_step_fn(cfgname, B, seed=0):
     """The reference's CPU path: oracle/torch_flow.py, the stock-PyTorch restatement of the reference module (the same
     nn.Linear / LayerNorm / cat / exp ops + autograd; pinned to the reference-generated fixtures by
@@ -158,11 +186,19 @@ def cpu_step_fn(cfgname, B, seed=0):
     torch.set_num_threads(os.cpu_count())      # torchrun exports OMP_NUM_THREADS=1
     cfg = config_of(cfgname)
     sd = synth.make_state_dict(cfg["D"], cfg["C"], cfg["R"], cfg["n"], seed=seed, H1=cfg["H1"])
-    model = TorchFlow(cfg["D"], cfg["C"], cfg["R"], cfg["n"], first_hidden=cfg["H1"], ln_eps=cfg["ln_eps"])
+    D = cfg["D"]
+    use_ref = cpu_kind(cfgname) == "reference"
+    if use_ref:
+        # the reference's own module and its own loss line: model.prior is the full-covariance MultivariateNormal the
+        # scripts build (torch_nfbc_ant.py:146-147, 267-270)
+        ref = reference_module()
+        prior = torch.distributions.MultivariateNormal(torch.zeros(D), torch.eye(D))
+        model = ref.RealNVP(D, cfg["C"], cfg["R"], cfg["n"], prior)
+    else:
+        model = TorchFlow(cfg["D"], cfg["C"], cfg["R"], cfg["n"], first_hidden=cfg["H1"], ln_eps=cfg["ln_eps"])
     model.load_state_dict({k: torch.tensor(v) for k, v in sd.items()})
     x, y = synth.make_inputs(B, cfg["D"], cfg["R"], seed=1234)
     x, y = torch.tensor(x), torch.tensor(y)
-    D = cfg["D"]
     plist = [p for p in model.parameters() if p.requires_grad]
 
     def train():
@@ -170,7 +206,10 @@ def cpu_step_fn(cfgname, B, seed=0):
             p.grad = None
         yy = y.detach().requires_grad_(True)
         z, _, ld = model(x, yy)
-        (-((-0.5 * (z * z).sum(1) - 0.5 * D * LOG2PI) + ld).mean()).backward()
+        if use_ref:
+            (-(model.prior.log_prob(z) + ld).mean()).backward()          # torch_nfbc_ant.py:269-271
+        else:
+            (-((-0.5 * (z * z).sum(1) - 0.5 * D * LOG2PI) + ld).mean()).backward()
 
     def sample():
         with torch.no_grad():
@@ -214,10 +253,9 @@ def run_reference_arm(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": config_dict(HEADLINE, world),
         "sampling": {"value": B / ts, "unit": "actions/s"},
-        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} steps of forward+backward at batch {B} on the host CPU "
-                                   f"(oracle/torch_flow.py: the reference's op sequence in stock PyTorch, {cores} threads; "
-                                   f"the reference is a Python module under /root/reference that cannot travel to this box)"},
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": cpu_kind(HEADLINE),
+                         "sample": f"{args.steps} steps of forward+backward at batch {B} on the host CPU, {cores} threads ("
+                                   + cpu_what(HEADLINE) + ")"},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(out), flush=True)
@@ -675,10 +713,9 @@ def run_ours(args):
         Bc = min(B_head, 4096)
         ctrain, csample = cpu_step_fn(HEADLINE, Bc)
         per, iters = time_cpu(ctrain, 10.0, 200)
-        cpu_baseline = {"value": Bc / per, "unit": "samples/s", "cores": cores, "kind": "port",
-                        "sample": f"{iters} steps of forward+backward at batch {Bc} of the same config "
-                                  f"(oracle/torch_flow.py: the reference's op sequence in stock PyTorch on the host, "
-                                  f"{cores} threads, {per * iters:.1f} s)"}
+        cpu_baseline = {"value": Bc / per, "unit": "samples/s", "cores": cores, "kind": cpu_kind(HEADLINE),
+                        "sample": f"{iters} steps of forward+backward at batch {Bc} of the same config on the host, "
+                                  f"{cores} threads, {per * iters:.1f} s ({cpu_what(HEADLINE)})"}
         for name in names:
             if name == HEADLINE:
                 per_config[name]["cpu_baseline"] = dict(cpu_baseline)
@@ -688,9 +725,9 @@ def run_ours(args):
             fn, unit = (ctrain, "samples/s") if PLAN[name]["train"] else (csample, "actions/s")
             per, iters = time_cpu(fn, 2.5, 20)
             per_config[name]["cpu_baseline"] = {
-                "value": Bc / per, "unit": unit, "cores": cores, "kind": "port",
+                "value": Bc / per, "unit": unit, "cores": cores, "kind": cpu_kind(name),
                 "sample": f"{iters} {'train steps' if PLAN[name]['train'] else 'reverse passes'} at batch {Bc} "
-                          f"(oracle/torch_flow.py on the host, {cores} threads, {per * iters:.1f} s)"}
+                          f"on the host, {cores} threads, {per * iters:.1f} s ({cpu_what(name)})"}
 
         if "C2t" in per_config:
             per_config["C2t"]["cpu_baseline"] = tarflow_cpu_baseline()
