@@ -148,16 +148,22 @@ def config_dict(name, world, precision="fp32"):
 # CPU arm: the reference's op sequence in stock PyTorch (oracle/torch_flow.py) on the host cores
 # --------------------------------------------------------------------------------------------------
 def reference_module():
-    """The UNMODIFIED reference file il-and-cil/utils/torch_fcnf.py, staged by __graft_entry__.build() into the git-ignored
-    oracle/_ref/ (it travels with the gpurun snapshot; /root/reference does not exist on the GPU box).  None when absent."""
-    path = os.path.join(ROOT, "oracle", "_ref", "torch_fcnf.py")
+    """The UNMODIFIED reference module il-and-cil/utils/torch_fcnf.py, compiled to bytecode by __graft_entry__.build() into
+    the git-ignored oracle/_ref/ (build outputs only; it travels with the gpurun snapshot -- /root/reference does not exist
+    on the GPU box).  None when absent."""
+    path = os.path.join(ROOT, "oracle", "_ref", "torch_fcnf.pyc")
     if not os.path.exists(path):
         return None
+    import importlib.machinery
     import importlib.util
-    spec = importlib.util.spec_from_file_location("nf_reference_torch_fcnf", path)
-    mod = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(mod)
-    return mod
+    try:
+        loader = importlib.machinery.SourcelessFileLoader("nf_reference_torch_fcnf", path)
+        spec = importlib.util.spec_from_loader("nf_reference_torch_fcnf", loader)
+        mod = importlib.util.module_from_spec(spec)
+        loader.exec_module(mod)
+        return mod
+    except Exception:       # bytecode of another interpreter version: fall back to the port
+        return None
 
 
 def cpu_kind(cfgname):
@@ -169,7 +175,7 @@ def cpu_kind(cfgname):
 
 def cpu_what(cfgname):
     if cpu_kind(cfgname) == "reference":
-        return ("the unmodified reference module il-and-cil/utils/torch_fcnf.py staged in oracle/_ref/ by build(), with the "
+        return ("the unmodified reference module il-and-cil/utils/torch_fcnf.py compiled into oracle/_ref/ by build(), with the "
                 "scripts' MultivariateNormal prior and loss line")
     return ("oracle/torch_flow.py, the reference's op sequence restated in stock PyTorch: the staged reference file is "
             "absent or this configuration uses the flax twin's widths")
