@@ -70,6 +70,8 @@ enum NfOpt {
   NF_OPT_RIDE,           // bias / x_cond weight gradients taken along by the weight-gradient GEMMs          (default 1)
   NF_OPT_DEFER_WGRAD,    // conditioner weight gradients of all blocks in two batched launches after the block loop: -1 auto (small flows), 0, 1 (default -1)
   NF_OPT_MCAST,          // weight tiles of the large K-major GEMMs multicast over CTA pairs: -1 auto, 0 never, 1 whenever possible (default -1)
+  NF_OPT_BN64,           // 64-wide tiles for K-major GEMMs whose 128-wide grid fills at most half the SMs (default 1)
+  NF_OPT_TF_AR,          // transformer flow: persistent autoregressive-inverse kernel for B <= 128: -1 auto, 0 never (default -1)
   NF_OPT_COUNT
 };
 int option(int id);

@@ -41,7 +41,8 @@ const OptDef kOpts[NF_OPT_COUNT] = {
     {"bn256", "NF_B200_BN256", 0},       {"ts", "NF_B200_TS", 1},                 {"presplit", "NF_B200_PRESPLIT", 1},
     {"stack", "NF_B200_STACK", -1},      {"stack_nsg", "NF_B200_STACK_NSG", 2},   {"whatif", "NF_B200_WHATIF", 0},
     {"ride", "NF_B200_RIDE", 1},         {"defer_wgrad", "NF_B200_DEFER_WGRAD", -1},
-    {"mcast", "NF_B200_MCAST", -1},
+    {"mcast", "NF_B200_MCAST", -1},      {"bn64", "NF_B200_BN64", 1},
+    {"tf_ar", "NF_B200_TF_AR", -1},
 };
 int g_opt[NF_OPT_COUNT];
 bool g_opt_init = false;

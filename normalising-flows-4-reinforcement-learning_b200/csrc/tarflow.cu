@@ -27,6 +27,7 @@
 #include "graphs.cuh"
 #include "linear.cuh"
 #include "prof.cuh"
+#include "tarflow_ar.cuh"
 
 namespace nf {
 namespace {
@@ -116,7 +117,7 @@ TfStash tf_stash(const TfDims& m, int64_t B) {
 // ---- workspace ---------------------------------------------------------------------------------------------------------
 struct TfWs {
   int64_t io_x, io_y, io_z, io_ld, io_dz, io_dld, io_dx, io_dy, x0, x1, xa, cproj;
-  int64_t tmp, bufA, bufB, bufO, big, big2, qkv, kv, wT, total;
+  int64_t tmp, bufA, bufB, bufO, big, big2, qkv, kv, wT, bars, total;
   int64_t t_qkv, t_proj, t_w1, t_w2, t_layer_stride, t_wc, t_block_stride;   // transposed weights inside wT
 };
 TfWs tf_ws(const TfDims& m, int64_t B) {
@@ -136,6 +137,7 @@ TfWs tf_ws(const TfDims& m, int64_t B) {
   w.t_wc = w.t_layer_stride * m.L;
   w.t_block_stride = w.t_wc + pad4(C * (int64_t)m.R);
   w.wT = take(w.t_block_stride * m.nb);
+  w.bars = take(64);                    // grid-barrier counters of the persistent inverse kernel (one per block)
   w.total = off;
   return w;
 }
@@ -1051,13 +1053,34 @@ NF_API int nf_tarflow_inverse(const NfTarflowDesc* desc, const float* params, co
   GraphKey key = tf_key(31, desc, B, ws_bytes);
   key.ptr[0] = params; key.ptr[2] = workspace;
   key.flags = (logdet ? 1 : 0);
+  // evaluation-sized batches: one persistent cooperative kernel per block runs the whole autoregressive loop
+  // (tarflow_ar.cu; option "tf_ar": -1 auto = whenever the shape is supported, 0 never)
+  const ArShape shape{(int)std::min<int64_t>(B, 1 << 20), m.A, m.C, m.EC, m.L, m.hd};
+  const bool persistent = option(NF_OPT_TF_AR) != 0 && m.nb <= 64 && tf_ar_plan(shape, nullptr, nullptr);
+  key.flags |= persistent ? 2 : 0;
   auto body = [&](cudaStream_t st) -> int {
     const float* cur = ws + wl.io_z;
+    if (persistent) NF_TRY(fill_zero(ws + wl.bars, 64, st));
     for (int i = m.nb - 1; i >= 0; --i) {
       const float* bp = params + (int64_t)i * pl.block_stride;
       const int flip = i & 1;
       float* nxt = i == 0 ? ws + wl.io_x : ws + ((i & 1) ? wl.x1 : wl.x0);
       NF_TRY(tf_linear(m.prec, ws + wl.io_y, m.R, bp + pl.wc, m.R, bp + pl.bc, ws + wl.cproj, m.C, m.C, B, 0, st));
+      if (persistent) {
+        ArP a{};
+        a.pos = bp + pl.pos; a.win = bp + pl.win; a.bin = bp + pl.bin; a.wout = bp + pl.wout; a.bout = bp + pl.bout;
+        a.layers = bp + pl.layers; a.layer_stride = pl.layer_stride;
+        a.o_ln1w = pl.ln1w; a.o_ln1b = pl.ln1b; a.o_wqkv = pl.wqkv; a.o_bqkv = pl.bqkv; a.o_wproj = pl.wproj; a.o_bproj = pl.bproj;
+        a.o_ln2w = pl.ln2w; a.o_ln2b = pl.ln2b; a.o_w1 = pl.w1; a.o_b1 = pl.b1; a.o_w2 = pl.w2; a.o_b2 = pl.b2;
+        a.A = m.A; a.C = m.C; a.H = m.H; a.hd = m.hd; a.L = m.L; a.EC = m.EC; a.B = (int)B; a.flip = flip;
+        a.ld_first = i == m.nb - 1; a.eps = m.eps; a.clamp = m.clamp;
+        a.zin = cur; a.xout = nxt; a.logdet = logdet ? ws + wl.io_ld : nullptr; a.cproj = ws + wl.cproj;
+        a.qkv = ws + wl.kv; a.o = ws + wl.bufO; a.h = ws + wl.bufA; a.h2 = ws + wl.bufB; a.g = ws + wl.big;
+        a.bar = reinterpret_cast<unsigned*>(ws + wl.bars) + i;
+        NF_TRY(tf_ar_block(a, st));
+        cur = nxt;
+        continue;
+      }
       PassBufs bf{};
       bf.h = ws + wl.bufA; bf.a = ws + wl.bufB; bf.o = ws + wl.bufO; bf.tmp = ws + wl.tmp; bf.big = ws + wl.big;
       bf.qkv0 = ws + wl.kv; bf.qkv_layer = 3 * B * m.T * m.C;

@@ -1281,6 +1281,11 @@ int tc_gemm(const TcGemmP& p, cudaStream_t st) {
   }
   if (p.N > 128 && ctas256 >= 120) return launch<256, 4, 16>(p, st);
   const bool ts = option(NF_OPT_TS) != 0;
+  // under-filled grids of 128-wide tiles (the per-token GEMMs of the autoregressive inverse: M = 4096, N = 256 is 64 CTAs on
+  // 148 SMs): 64-wide tiles double the CTAs; the launch is latency-bound, the narrower MMA does not matter (option "bn64": 0 off)
+  if (ts && option(NF_OPT_BN64) != 0 && p.N > 64 && p.N % 64 == 0 && !p.accumulate &&
+      cdiv(p.M, BM) * cdiv(p.N, 128) * p.batch <= 74)
+    return launch<64, 12, 16, true>(p, st);
   if (p.N > 64) {
     if (option(NF_OPT_TS) == 2) return launch<128, 4, 16, true>(p, st);   // experiment: half the stage ring
     if (ts) {

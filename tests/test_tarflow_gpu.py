@@ -139,3 +139,33 @@ def test_rows_are_independent_and_batches_ragged():
         xr = ours.reverse(z[:1], y[:1].cuda())
     assert rel_err(z1.cpu().numpy(), z[:129].cpu().numpy()) <= 2e-6 and rel_err(ld1.cpu().numpy(), ld[:129].cpu().numpy()) <= 2e-6
     assert rel_err(xr.cpu().numpy(), x[:1].numpy()) <= 5e-5
+
+
+def test_persistent_inverse_kernel_agrees_with_the_per_token_path():
+    """Evaluation-sized batches (B <= 128) run the autoregressive inverse as ONE cooperative kernel per block
+    (csrc/tarflow_ar.cu); larger ones launch the per-token kernel sequence.  Same function: both against the float64
+    checker, and against each other, at the reference script's shape with 20 environments (torch_evaluations.py:79-82)."""
+    c = dict(CASES["gcbc"], B=20)
+    ref, ours, x, y, dz, dld = build(c, "fp32")
+    with torch.no_grad():
+        z = ours(x.cuda(), y.cuda())[0]
+        want = copy.deepcopy(ref).double().reverse(z.cpu().double(), y.double()).numpy()
+        noise = rel_err(ref.reverse(z.cpu(), y).numpy(), want)
+        res = {}
+        for v in (-1, 0):
+            _lib.set_option("tf_ar", v)
+            try:
+                for _ in range(3):      # eager, capture, replay
+                    xr, ldr = ours.reverse(z, y.cuda(), return_logdet=True)
+                res[v] = (xr.cpu().numpy(), ldr.cpu().numpy())
+            finally:
+                _lib.set_option("tf_ar", -1)
+    for v in (-1, 0):
+        assert rel_err(res[v][0], want) <= max(2e-5, 3.0 * noise), (v, rel_err(res[v][0], want), noise)
+    assert rel_err(res[-1][0], res[0][0]) <= max(2e-5, 3.0 * noise)
+    assert rel_err(res[-1][1], res[0][1]) <= 2e-5
+    # the kernel count shows which path ran
+    _lib.lib.nf_launch_count(1)
+    with torch.no_grad():
+        ours.reverse(z, y.cuda())
+    assert _lib.lib.nf_launch_count(1) <= 4 * c["nb"] + 4
