@@ -699,6 +699,21 @@ def run_ours(args):
                         "train": {"value": total_B / (ms_e * 1e-3), "unit": "samples/s", "ms_per_step": ms_e},
                         "sampling": {"value": total_B / (ms_es * 1e-3), "unit": "actions/s", "ms_per_step": ms_es}}
         entry["roofline"] = r.roofline(ms, peaks, traffic, True)
+        # the evaluation loop's batch (20 parallel environments, utils/torch_evaluations.py:79-82): the autoregressive inverse
+        # runs as one persistent cooperative kernel per block there (csrc/tarflow_ar.cu)
+        xe, ye = r.x[:20].contiguous(), r.y[:20].contiguous()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(20)]
+        for _ in range(W):
+            r.sample_step(xe, ye)
+        for a, b in ev:
+            flush.zero_()
+            a.record()
+            r.sample_step(xe, ye)
+            b.record()
+        torch.cuda.synchronize()
+        ms_eval = sum(a.elapsed_time(b) for a, b in ev) / len(ev)
+        entry["sampling_eval_batch"] = {"batch": 20, "ms_per_call": ms_eval, "value": 20 / (ms_eval * 1e-3), "unit": "actions/s",
+                                        "note": "per rank, not aggregated; persistent autoregressive-inverse kernel"}
         per_config["C2t"] = entry
         r.free()
 
