@@ -151,7 +151,7 @@ def reference_module():
     """The UNMODIFIED reference module il-and-cil/utils/torch_fcnf.py, compiled to bytecode by __graft_entry__.build() into
     the git-ignored oracle/_ref/ (build outputs only; it travels with the gpurun snapshot -- /root/reference does not exist
     on the GPU box).  None when absent."""
-    path = os.path.join(ROOT, "oracle", "_ref", "torch_fcnf.pyc")
+    path = os.path.join(ROOT, "oracle", "_ref", "torch_fcnf.bytecode")
     if not os.path.exists(path):
         return None
     import importlib.machinery

@@ -19,7 +19,7 @@ def test_reference_arm_prints_the_contract_line():
     assert d["value"] > 0 and d["steps"] == 1 and d["n_gpus"] == 1
     # "reference" when __graft_entry__.build() has compiled the unmodified reference module into oracle/_ref/ (the build
     # container, and the GPU box through the snapshot), "port" (oracle/torch_flow.py) otherwise
-    staged = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "torch_fcnf.pyc"))
+    staged = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "torch_fcnf.bytecode"))
     assert d["cpu_baseline"]["kind"] == ("reference" if staged else "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "C2a" in d["config"]["workload"]
