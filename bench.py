@@ -3,7 +3,7 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--configs C1a,C2a,...]
 
 A step = one pass of the hot path over one batch of synthetic input:
-    z, outputs, log_dets = model(x, y); loss = -(log N(z) + log_dets).mean(); loss.backward()
+    z, outputs, log_dets = model(x, y); loss = -(model.prior.log_prob(z) + log_dets).mean(); loss.backward()
 (torch_nfbc_ant.py:267-272 without the optimizer; y requires grad like the encoder output it is in the reference, so
 dy is computed; the data-parallel gradient all-reduce is included when N > 1) and -- reported under "sampling" --
 model.reverse(randn(B, D), y) (torch_nfbc_ant.py:209-210).
@@ -287,8 +287,9 @@ class Runner:
         self.B = B = batch_per_gpu(name, world)
         self.D, self.R = cfg["D"], cfg["R"]
         self.sd = synth.make_state_dict(cfg["D"], cfg["C"], cfg["R"], cfg["n"], seed=0, H1=cfg["H1"])
-        model = nf_b200.RealNVP(cfg["D"], cfg["C"], cfg["R"], cfg["n"], None, first_hidden=cfg["H1"],
-                                ln_eps=cfg["ln_eps"], precision=precision)
+        # the prior the scripts pass to the constructor (torch_nfbc_ant.py:146-147), as the library's one-kernel N(0, I)
+        model = nf_b200.RealNVP(cfg["D"], cfg["C"], cfg["R"], cfg["n"], nf_b200.StandardNormal(cfg["D"], dev),
+                                first_hidden=cfg["H1"], ln_eps=cfg["ln_eps"], precision=precision)
         model.load_state_dict({k: torch.tensor(v) for k, v in self.sd.items()})
         self.model = model.to(dev)
         if world > 1 and PLAN[name]["train"]:
@@ -310,7 +311,7 @@ class Runner:
             p.grad = None
         yd = yd.detach().requires_grad_(True)   # y is the encoder output in the reference (torch_nfbc_ant.py:267)
         z, _, ld = model(xd, yd)
-        loss = -((-0.5 * (z * z).sum(1) - 0.5 * D * LOG2PI) + ld).mean()
+        loss = -(model.prior.log_prob(z) + ld).mean()          # the reference's loss line, torch_nfbc_ant.py:269-270
         loss.backward()
         return loss
 
@@ -468,7 +469,8 @@ class TarflowRunner(Runner):
         self.torch, self.name, self.dev, self.rank, self.world, self.flush = torch, "C2t", dev, rank, world, flush
         self.c, self.B, self.D, self.R = c, c["batch"], c["A"], c["R"]
         self.ref = tarflow_models(c)
-        model = nf_b200.TransformerRealNVP(c["A"], c["C"], c["R"], c["hd"], c["nb"], c["L"], None, expansion=c["E"])
+        model = nf_b200.TransformerRealNVP(c["A"], c["C"], c["R"], c["hd"], c["nb"], c["L"],
+                                           nf_b200.StandardNormal(c["A"], dev), expansion=c["E"])
         model.load_state_dict(self.ref.state_dict())
         self.model = model.to(dev)
         if world > 1:
@@ -497,7 +499,7 @@ class TarflowRunner(Runner):
             p.grad = None
         yd = yd.detach().requires_grad_(True)       # the encoder output (torch_nfgcbc.py:141)
         z, _, ld = model(xd, yd)
-        loss = -((-0.5 * (z * z).sum((1, 2)) - 0.5 * D * LOG2PI) + ld).mean()       # torch_nfgcbc.py:142
+        loss = -(model.prior.log_prob(z.squeeze(-1)) + ld).mean()                   # torch_nfgcbc.py:142
         loss.backward()
         return loss
 

@@ -227,6 +227,11 @@ NF_API int nf_linear_wgrad(const float* dY, int64_t lddy, const float* X, int64_
  *                     one kernel (counter-based Philox4x32-10 + Box-Muller; the normal at index i is a pure function of
  *                     (seed, offset + i / 4, i % 4), so a caller advances `offset` by ceil(n / 4) per call); out may
  *                     alias x. */
+/*   nf_stdnormal_logprob  lp[b] = log N(z_b; 0, I) = -0.5 |z_b|^2 - D/2 log 2 pi: `model.prior.log_prob(z)` of the reference's
+ *                     loss line for its MultivariateNormal(0, I) prior (torch_nfbc_ant.py:146,269) as one kernel;
+ *   nf_stdnormal_logprob_bwd  dz[b, j] = -g[b] z[b, j]. */
+NF_API int nf_stdnormal_logprob(const float* z, int64_t B, int32_t D, float* lp, void* stream);
+NF_API int nf_stdnormal_logprob_bwd(const float* z, const float* g, int64_t B, int32_t D, float* dz, void* stream);
 /*   nf_logprob_group_argmin  per group g of N candidates: n* = argmin_n [log N(z_gn; 0, I) + logdet_gn] (ties: smaller n),
  *                     out_x[g] = x[g, n*], out_idx[g] = n*, out_lp[g] = the minimum (each output optional): the exploration-goal
  *                     selection of unsupservised-gcrl/train_auto_NF_rl.py:328-333 without the (G, N) round trip. */

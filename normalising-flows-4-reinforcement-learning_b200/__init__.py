@@ -8,6 +8,7 @@ from .module import InvertiblePLU, MetaBlock, RealNVP, count_parameters  # noqa:
 from .optim import CosineLRSchedule, FlatAdamW  # noqa: F401
 from .encoder import GEncoder  # noqa: F401
 from .tarflow import TransformerMetaBlock, TransformerRealNVP  # noqa: F401
+from .prior import StandardNormal  # noqa: F401
 
 __all__ = ["RealNVP", "MetaBlock", "InvertiblePLU", "count_parameters", "FlatAdamW", "CosineLRSchedule", "GEncoder",
-           "TransformerRealNVP", "TransformerMetaBlock"]
+           "TransformerRealNVP", "TransformerMetaBlock", "StandardNormal"]

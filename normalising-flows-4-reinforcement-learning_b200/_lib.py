@@ -87,6 +87,8 @@ def _load():
         "nf_prof_enable": (c_int, [c_int]),
         "nf_prof_collect": (c_int, [POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(c_int64), c_int]),
         "nf_launch_count": (c_int64, [c_int]),
+        "nf_stdnormal_logprob": (c_int, [fp, i64, c_int32, fp, vp]),
+        "nf_stdnormal_logprob_bwd": (c_int, [fp, fp, i64, c_int32, fp, vp]),
         "nf_logprob_group_argmin": (c_int, [fp, fp, fp, i64, i64, c_int32, fp, fp, fp, vp]),
         "nf_noise_augment": (c_int, [fp, i64, c_float, ctypes.c_uint64, ctypes.c_uint64, fp, vp]),
         "nf_nll_forward": (c_int, [fp, fp, i64, c_int32, fp, vp]),

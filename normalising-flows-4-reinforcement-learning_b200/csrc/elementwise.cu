@@ -1050,6 +1050,61 @@ int nll_cotangents(const float* z, const float* g, long long B, int D, float* dz
 }
 
 // ------------------------------------------------------------------------------------------
+// log-density of the standard-normal prior, the `model.prior.log_prob(z)` of the reference's loss line
+// (torch_nfbc_ant.py:146,269: MultivariateNormal(0, I), evaluated there through a Cholesky / Mahalanobis path of ~10 kernels):
+//   lp[b] = -0.5 |z_b|^2 - D/2 log(2 pi);   backward  dz[b, j] = -g[b] z[b, j]
+// One warp per row group: G = 2^k lanes share a row (D / 4 chunks when D % 4 == 0, scalar otherwise), like k_affine_vec.
+// ------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) k_stdnormal_logprob(const float* __restrict__ z, long long B, int D,
+                                                           float* __restrict__ lp) {
+  NF_PDL_ENTRY();
+  const int lane = threadIdx.x & 31;
+  const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const float c = -0.5f * (float)D * 1.8378770664093453f;
+  if (D <= 32) {                      // a warp takes 32 / G rows, G lanes per row
+    int G = 1;
+    while (G < D) G <<= 1;
+    const int rpw = 32 / G, g = lane % G;
+    const long long row = w * rpw + lane / G;
+    float s = 0.f;
+    if (row < B && g < D) { const float v = z[row * D + g]; s = v * v; }
+    for (int o = G >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (row < B && g == 0) lp[row] = fmaf(-0.5f, s, c);
+  } else {                            // warp per row
+    if (w >= B) return;
+    float s = 0.f;
+    for (int j = lane; j < D; j += 32) { const float v = z[w * D + j]; s = fmaf(v, v, s); }
+    s = warp_sum(s);
+    if (lane == 0) lp[w] = fmaf(-0.5f, s, c);
+  }
+}
+__global__ void __launch_bounds__(256) k_stdnormal_logprob_bwd(const float* __restrict__ z, const float* __restrict__ g,
+                                                               long long B, int D, float* __restrict__ dz) {
+  NF_PDL_ENTRY();
+  const long long n = B * D;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dz[i] = -g[i / D] * z[i];
+}
+}  // namespace
+
+int stdnormal_logprob(const float* z, long long B, int D, float* lp, cudaStream_t st) {
+  if (B <= 0) return 0;
+  int G = 1;
+  while (G < D && G < 32) G <<= 1;
+  const long long rows_per_warp = D <= 32 ? 32 / G : 1;
+  NF_LAUNCH((k_stdnormal_logprob), (unsigned)cdiv(B, 8 * rows_per_warp), 256, 0, st, z, B, D, lp);
+  NF_LAUNCHED();
+  return 0;
+}
+int stdnormal_logprob_bwd(const float* z, const float* g, long long B, int D, float* dz, cudaStream_t st) {
+  if (B <= 0) return 0;
+  NF_LAUNCH((k_stdnormal_logprob_bwd), (unsigned)std::min<long long>(cdiv(B * D, 256), 148 * 8), 256, 0, st, z, g, B, D, dz);
+  NF_LAUNCHED();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
 // Group-wise argmin of the log-probability (unsupservised-gcrl/train_auto_NF_rl.py:328-333: for every environment the
 // candidate goal with the LOWEST log N(z) + logdet among its N candidates is the next exploration goal): one CTA per group
 // computes lp[n] = -0.5 |z_n|^2 - D/2 log(2 pi) + logdet[n], reduces (value, index) with ties to the smaller index

@@ -66,6 +66,9 @@ int nll_forward(const float* z, const float* logdet, long long B, int D, float* 
 int nll_cotangents(const float* z, const float* g, long long B, int D, float* dz, float* dld, cudaStream_t st);
 // one AdamW step (torch.optim.AdamW semantics, torch_nfbc_ant.py:150-155) over the flat parameter arena; slot_mask
 // (n_blocks * NF_P_SLOTS bytes on the device) selects the trainable slots
+// lp[b] = log N(z_b; 0, I) and its backward dz = -g[b] z   (the prior term of the reference's loss line)
+int stdnormal_logprob(const float* z, long long B, int D, float* lp, cudaStream_t st);
+int stdnormal_logprob_bwd(const float* z, const float* g, long long B, int D, float* dz, cudaStream_t st);
 // per group g of N candidate rows: argmin_n of -0.5 |z|^2 - D/2 log 2 pi + logdet (ties: smaller index); out_x (G, D) =
 // the winning row of x, out_idx (G) its index, out_lp (G) its log-probability (each optional)
 int group_argmin_logp(const float* z, const float* logdet, const float* x, long long G, long long N, int D, float* out_x,

@@ -1612,6 +1612,18 @@ int nf_nll_cotangents(const float* z, const float* g, int64_t B, int32_t D, floa
   return nll_cotangents(z, g, B, D, dz, dld, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int nf_stdnormal_logprob(const float* z, int64_t B, int32_t D, float* lp, void* stream) {
+  NF_CHECK_ARG(D >= 1 && B >= 0, NF_E_BADARG, "bad shape B=%lld D=%d", (long long)B, D);
+  NF_TRY(check_ptr(z, "z", B > 0)); NF_TRY(check_ptr(lp, "lp", B > 0));
+  return stdnormal_logprob(z, B, D, lp, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int nf_stdnormal_logprob_bwd(const float* z, const float* g, int64_t B, int32_t D, float* dz, void* stream) {
+  NF_CHECK_ARG(D >= 1 && B >= 0, NF_E_BADARG, "bad shape B=%lld D=%d", (long long)B, D);
+  NF_TRY(check_ptr(z, "z", B > 0)); NF_TRY(check_ptr(g, "g", B > 0)); NF_TRY(check_ptr(dz, "dz", B > 0));
+  return stdnormal_logprob_bwd(z, g, B, D, dz, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int nf_logprob_group_argmin(const float* z, const float* logdet, const float* x, int64_t G, int64_t N, int32_t D,
                             float* out_x, int64_t* out_idx, float* out_lp, void* stream) {
   NF_CHECK_ARG(D >= 1 && G >= 0 && N >= 1 && G <= 0x7fffffff, NF_E_BADARG, "bad shape G=%lld N=%lld D=%d", (long long)G,

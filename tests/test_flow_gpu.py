@@ -816,3 +816,28 @@ def test_group_argmin_of_log_prob_matches_the_oracle():
     xt = t(np.repeat(x[:, :1], 4, axis=1).copy())
     _, idx = model.argmin_log_prob(xt, None, return_index=True)
     assert int(idx.abs().max()) == 0
+
+
+@pytest.mark.parametrize("D,B", [(2, 1000), (8, 4096), (9, 257), (32, 300), (400, 50)])
+def test_standard_normal_prior_matches_multivariate_normal(D, B):
+    """``nf_b200.StandardNormal(D).log_prob`` (one kernel forward, one backward) against the prior the reference's scripts
+    build, ``MultivariateNormal(zeros(D), eye(D))`` (torch_nfbc_ant.py:146), values and gradient, in the loss line's form."""
+    rs = np.random.RandomState(D)
+    z = torch.tensor(rs.randn(B, D).astype(np.float32), device=dev())
+    w = torch.tensor(rs.randn(B).astype(np.float32), device=dev())
+    ref_prior = torch.distributions.MultivariateNormal(torch.zeros(D, dtype=torch.float64, device=dev()),
+                                                       torch.eye(D, dtype=torch.float64, device=dev()))
+    z64 = z.double().requires_grad_(True)
+    lp64 = ref_prior.log_prob(z64)
+    (lp64 * w.double()).sum().backward()
+    zz = z.clone().requires_grad_(True)
+    prior = nf_b200.StandardNormal(D, dev())
+    lp = prior.log_prob(zz)
+    (lp * w).sum().backward()
+    assert lp.shape == (B,)
+    assert rel_err(lp.detach().cpu().numpy(), lp64.detach().cpu().numpy()) <= 2e-6
+    assert rel_err(zz.grad.cpu().numpy(), z64.grad.cpu().numpy()) <= 2e-6
+    assert prior.sample((7,)).shape == (7, D) and prior.sample((7,)).device.type == "cuda"
+    # leading batch dimensions and a view with an offset (rows of a larger tensor)
+    lp3 = prior.log_prob(z[1:].reshape(1, B - 1, D))
+    assert lp3.shape == (1, B - 1) and torch.allclose(lp3[0], lp[1:].detach(), rtol=1e-6, atol=1e-6)
