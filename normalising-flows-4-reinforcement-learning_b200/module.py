@@ -199,6 +199,7 @@ class _Flow(torch.autograd.Function):
         ctx.guard = _SlotGuard(slot) if slot is not None else None
         ctx.packed = packed
         ctx.pver = model._pver_seen      # computed by _prepared inside _run_forward
+        ctx.cver = model._quick_version()
         ctx.B = x.shape[0]
         ctx.has_y = y is not None
         ctx.save_for_backward(*([y] if y is not None else []))
@@ -210,7 +211,9 @@ class _Flow(torch.autograd.Function):
         model = ctx.model
         if ctx.stash is None:
             raise RuntimeError("nf_b200: backward called twice on the same forward (the stash is freed after use)")
-        if ctx.pver != model._params_version():
+        # (an optimizer step between forward and backward touches every trainable parameter, the first one included: one
+        # version read instead of a second walk over all of them)
+        if ctx.cver != model._quick_version():
             raise RuntimeError("nf_b200: parameters were modified between forward and backward")
         y = ctx.saved_tensors[0] if ctx.has_y else None
         need_x = ctx.needs_input_grad[3]
@@ -429,6 +432,9 @@ class RealNVP(nn.Module):
             sizes.append(self._layout.total - pos)
         self._split_sizes, self._split_picks = sizes, picks
         self._tparams = [p for p, _ in self._trainable]
+        self._carrier_cache = [None, None]    # [carrier parameter, its AccumulateGrad nodes] (a list: nn.Module would
+                                              # register a Parameter assigned as an attribute)
+        self._ws_need = {}
         self._packed = None
         self._packed_key = None
         self._gflat = None
@@ -452,11 +458,34 @@ class RealNVP(nn.Module):
         """Called by code that updates the arena outside torch's version counters (FlatAdamW)."""
         self._xver += 1
 
+    def _quick_version(self):
+        tp = self._tparams
+        return self._xver + (tp[0]._version + tp[-1]._version if tp else 0)
+
     def _params_version(self):
         v = self._xver
         for p in self._tparams:
             v += p._version
         return v
+
+    def _grad_carriers(self):
+        """The trainable parameters handed to the autograd function: all of them, or -- ``fast_param_grads`` -- only the
+        first one (the carrier whose AccumulateGrad node tells backward whether parameter gradients are wanted).  The
+        carrier is cached and re-validated with one attribute read instead of a walk over ~150 parameters per forward;
+        its AccumulateGrad node is cached too (holding it keeps it the node autograd uses)."""
+        if not self.fast_param_grads:
+            params = [p for p in self._tparams if p.requires_grad]
+            return params, _accumulate_nodes(params)
+        cache = self._carrier_cache
+        c = cache[0]
+        if c is None or not c.requires_grad:
+            c = cache[0] = next((p for p in self._tparams if p.requires_grad), None)
+            cache[1] = None
+        if c is None:
+            return [], []
+        if cache[1] is None:
+            cache[1] = _accumulate_nodes([c])
+        return [c], cache[1]
 
     def _grad_views(self, dflat):
         chunks = dflat.split_with_sizes(self._split_sizes)
@@ -488,7 +517,9 @@ class RealNVP(nn.Module):
                                                                   else torch.cuda.current_device()))
 
     def _workspace(self, B, device):
-        need = lib.nf_flow_workspace_bytes(ctypes.byref(self._desc), B)
+        need = self._ws_need.get(B)
+        if need is None:
+            need = self._ws_need[B] = lib.nf_flow_workspace_bytes(ctypes.byref(self._desc), B)
         if self._ws is None or self._ws.numel() < need or self._ws.device != device:
             self._ws = torch.empty(need, dtype=torch.uint8, device=device)
         return self._ws
@@ -721,13 +752,10 @@ class RealNVP(nn.Module):
         """-> (z, outputs, log_dets): torch_fcnf.py:134-141.  ``outputs`` (list of n_layers (B, D)
         tensors, the block outputs logged at torch_nfbc_ant.py:286-287) are not differentiable.  ``y=None``: y == 0."""
         self._check_inputs(x, y)
-        params = [p for p in self._tparams if p.requires_grad] if torch.is_grad_enabled() else []
+        params, nodes = self._grad_carriers() if torch.is_grad_enabled() else ([], [])
         need_grad = torch.is_grad_enabled() and (x.requires_grad or (y is not None and y.requires_grad) or len(params) > 0)
         if need_grad:
-            if self.fast_param_grads:
-                z, logdet, outs = _Flow.apply(self, True, _accumulate_nodes(params[:1]), x, y, *params[:1])
-            else:
-                z, logdet, outs = _Flow.apply(self, False, _accumulate_nodes(params), x, y, *params)
+            z, logdet, outs = _Flow.apply(self, self.fast_param_grads, nodes, x, y, *params)
         else:
             z, logdet, outs, _, _, _ = self._run_forward(x, y, False, want_outputs=self.return_outputs)
         if not self.return_outputs:
