@@ -15,6 +15,8 @@ include/nf_b200.h; there is no CPU or PyTorch-eager fallback -- CPU tensors rais
 from __future__ import annotations
 
 import ctypes
+import itertools
+import operator
 import math
 from typing import List, Optional
 
@@ -24,6 +26,9 @@ from torch import nn
 
 from . import _lib
 from ._lib import lib
+
+
+_get_grad = operator.attrgetter("grad")
 
 
 class _NoSwitch:
@@ -645,18 +650,20 @@ class RealNVP(nn.Module):
             self._gflat = torch.zeros(self._layout.total, dtype=torch.float32, device=dev)
             self._gviews = self._grad_views(self._gflat)
         views = self._gviews
-        fresh = True          # every p.grad is None: write the arena in place and hand out the views
-        ours = True           # every p.grad already is our view: accumulate with one flat add
-        for p, v in zip(tp, views):
-            if not p.requires_grad:
-                continue
-            g = p.grad
-            if g is not None:
-                fresh = False
-                if g.data_ptr() != v.data_ptr() or g.shape != v.shape:
-                    ours = False
-            else:
-                ours = False
+        # Which state are the .grad fields in?  fresh: every one is None (after zero_grad(set_to_none=True): write the arena
+        # in place and hand out the views); ours: every one already is our view (accumulate with one flat add); anything
+        # else goes parameter by parameter.  Both common states are recognised with C-level identity tests -- a Python
+        # loop over ~150 parameters with two attribute reads each was 30 us of host time per step.
+        grads = list(map(_get_grad, tp))
+        n_none = sum(map(operator.is_, grads, itertools.repeat(None)))
+        fresh = n_none == len(grads)
+        ours = False
+        if not fresh and n_none == 0:
+            ours = sum(map(operator.is_, grads, views)) == len(grads)
+            if not ours:      # same storage through another Python object?
+                ours = all(g.data_ptr() == v.data_ptr() and g.shape == v.shape for g, v in zip(grads, views))
+        if any(not p.requires_grad for p in tp) and not fresh:
+            ours = False      # parameters frozen after construction: take the per-parameter path
         target = self._gflat if fresh else None
         dx, dy, dflat = self._run_backward(stash, packed, y, B, dz, dld, need_x, need_y, True, out=target, inverse=inverse)
         if fresh:
