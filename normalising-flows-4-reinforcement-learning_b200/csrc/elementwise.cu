@@ -546,6 +546,89 @@ __global__ void k_logdet_total(float* packed, PackedLayout kl, int n) {
   }
 }
 
+// Small flow dimensions (D <= 32): the whole chain  mask -> PL = P Lh -> W = PL Uh -> W^T  plus the block's log|det| in ONE
+// kernel, one CTA per block with the five D x D matrices in shared memory (as five launches this chain was the critical
+// path of nf_flow_prepare: ~20 us per training step on C2a, where the parameters change every step).
+__global__ void __launch_bounds__(256) k_plu_build_small(const float* __restrict__ params, NfParamLayout pl, int D,
+                                                         float* __restrict__ packed, PackedLayout kl) {
+  NF_PDL_ENTRY();
+  __shared__ float sP[1024], sLh[1024], sUh[1024], sPL[1024];
+  const int b = blockIdx.x, DD = D * D;
+  const float* pb = params + (long long)b * pl.block_stride;
+  float* kb = packed + (long long)b * kl.block_stride;
+  const float* L = pb + pl.slot_off[NF_P_L];
+  const float* U = pb + pl.slot_off[NF_P_U];
+  const float* s = pb + pl.slot_off[NF_P_S];
+  const float* P = pb + pl.slot_off[NF_P_P];
+  for (int idx = threadIdx.x; idx < DD; idx += blockDim.x) {
+    const int i = idx / D, j = idx % D;
+    const float lh = i > j ? L[idx] : (i == j ? 1.f : 0.f);
+    const float uh = i < j ? U[idx] : (i == j ? s[i] : 0.f);
+    sP[idx] = P[idx]; sLh[idx] = lh; sUh[idx] = uh;
+    kb[kl.Lh + idx] = lh; kb[kl.Uh + idx] = uh;
+  }
+  if (threadIdx.x < 32) {
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < D; i += 32) acc += logf(fabsf(s[i]));
+    acc = warp_sum(acc);
+    if (threadIdx.x == 0) packed[kl.logdet_c + b] = acc;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < DD; idx += blockDim.x) {
+    const int i = idx / D, j = idx % D;
+    float acc = 0.f;
+    for (int k = 0; k < D; ++k) acc = fmaf(sP[i * D + k], sLh[k * D + j], acc);
+    sPL[idx] = acc;
+    kb[kl.PL + idx] = acc;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < DD; idx += blockDim.x) {
+    const int i = idx / D, j = idx % D;
+    float acc = 0.f;
+    for (int k = 0; k < D; ++k) acc = fmaf(sPL[i * D + k], sUh[k * D + j], acc);
+    kb[kl.W + idx] = acc;
+    kb[kl.WT + j * D + i] = acc;
+  }
+}
+
+// Small flow dimensions: T1 = P^T dW, dLh = T1 Uh^T, dUh = (P Lh)^T dW and the masking / diagonal terms of
+// k_plu_grad_finish in one kernel, one CTA per block (three FFMA GEMM launches + the finish kernel before).
+__global__ void __launch_bounds__(256) k_plu_grad_small(const float* __restrict__ params, NfParamLayout pl, int D,
+                                                        const float* __restrict__ packed, PackedLayout kl,
+                                                        const float* __restrict__ dW, const float* __restrict__ sum_dld,
+                                                        float* __restrict__ dparams, float ld_sign) {
+  NF_PDL_ENTRY();
+  __shared__ float sP[1024], sUh[1024], sPL[1024], sdW[1024], sT1[1024];
+  const int b = blockIdx.x, DD = D * D;
+  const float* pb = params + (long long)b * pl.block_stride;
+  const float* kb = packed + (long long)b * kl.block_stride;
+  float* db = dparams + (long long)b * pl.block_stride;
+  for (int idx = threadIdx.x; idx < DD; idx += blockDim.x) {
+    sP[idx] = pb[pl.slot_off[NF_P_P] + idx];
+    sUh[idx] = kb[kl.Uh + idx];
+    sPL[idx] = kb[kl.PL + idx];
+    sdW[idx] = dW[(long long)b * DD + idx];
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < DD; idx += blockDim.x) {     // T1 = P^T dW
+    const int i = idx / D, j = idx % D;
+    float acc = 0.f;
+    for (int k = 0; k < D; ++k) acc = fmaf(sP[k * D + i], sdW[k * D + j], acc);
+    sT1[idx] = acc;
+  }
+  __syncthreads();
+  const float sd = sum_dld ? ld_sign * *sum_dld : 0.f;
+  for (int idx = threadIdx.x; idx < DD; idx += blockDim.x) {
+    const int i = idx / D, j = idx % D;
+    float dl = 0.f, du = 0.f;
+    if (i > j) for (int k = 0; k < D; ++k) dl = fmaf(sT1[i * D + k], sUh[j * D + k], dl);       // dLh = T1 Uh^T
+    if (i <= j) for (int k = 0; k < D; ++k) du = fmaf(sPL[k * D + i], sdW[k * D + j], du);      // dUh = PL^T dW
+    db[pl.slot_off[NF_P_L] + idx] = i > j ? dl : 0.f;
+    db[pl.slot_off[NF_P_U] + idx] = i < j ? du : 0.f;
+    if (i == j) db[pl.slot_off[NF_P_S] + i] = du + sd / pb[pl.slot_off[NF_P_S] + i];
+  }
+}
+
 // Triangular inverses by substitution against the identity, one thread per column
 // (torch.linalg.solve_triangular(..., eye), torch_fcnf.py:49-52).
 __global__ void k_tri_inverse(const float* packed, PackedLayout kl, int D, float* uinv, float* linv) {
@@ -858,6 +941,25 @@ int plu_mask(const float* params, const NfParamLayout& pl, const Dims& m, float*
   NF_LAUNCH((k_plu_mask), grid, 256, 0, st, params, pl, m.D, packed, kl);
   NF_LAUNCHED();
   NF_LAUNCH((k_logdet_total), 1, 32, 0, st, packed, kl, m.n);
+  NF_LAUNCHED();
+  return 0;
+}
+
+int plu_build_small(const float* params, const NfParamLayout& pl, const Dims& m, float* packed, const PackedLayout& kl,
+                    cudaStream_t st) {
+  NF_CHECK_ARG(m.D <= 32, NF_E_UNSUPPORTED, "plu_build_small: D=%d", m.D);
+  NF_LAUNCH((k_plu_build_small), (unsigned)m.n, 256, 0, st, params, pl, m.D, packed, kl);
+  NF_LAUNCHED();
+  NF_LAUNCH((k_logdet_total), 1, 32, 0, st, packed, kl, m.n);
+  NF_LAUNCHED();
+  return 0;
+}
+
+int plu_grad_small(const float* params, const NfParamLayout& pl, const Dims& m, const float* packed, const PackedLayout& kl,
+                   const float* dW, const float* sum_dld, float* dparams, cudaStream_t st, float ld_sign) {
+  NF_CHECK_ARG(m.D <= 32, NF_E_UNSUPPORTED, "plu_grad_small: D=%d", m.D);
+  if (m.n <= 0) return 0;
+  NF_LAUNCH((k_plu_grad_small), (unsigned)m.n, 256, 0, st, params, pl, m.D, packed, kl, dW, sum_dld, dparams, ld_sign);
   NF_LAUNCHED();
   return 0;
 }

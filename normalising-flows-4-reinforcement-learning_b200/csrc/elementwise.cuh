@@ -46,6 +46,12 @@ int affine_bwd(const float* dz, const float* z, const float* s_full, const float
 // ---- parameter-sized kernels ---------------------------------------------------------------
 int plu_mask(const float* params, const NfParamLayout& pl, const Dims& m, float* packed,
              const PackedLayout& kl, cudaStream_t st);
+// D <= 32: mask + PL + W + W^T + log|det| of every block in one kernel; the PLU parameter gradients (the three small GEMMs
+// and plu_grad_finish) in one kernel
+int plu_build_small(const float* params, const NfParamLayout& pl, const Dims& m, float* packed, const PackedLayout& kl,
+                    cudaStream_t st);
+int plu_grad_small(const float* params, const NfParamLayout& pl, const Dims& m, const float* packed, const PackedLayout& kl,
+                   const float* dW, const float* sum_dld, float* dparams, cudaStream_t st, float ld_sign = 1.0f);
 int plu_tri_inverse(const float* packed, const PackedLayout& kl, const Dims& m, float* uinv, float* linv,
                     cudaStream_t st);
 int fold_ln_affine(const float* params, const NfParamLayout& pl, const Dims& m, float* packed,

@@ -559,20 +559,24 @@ int nf_flow_prepare(const NfFlowDesc* desc, const float* params, void* packed_v,
     NF_CUDA(cudaStreamWaitEvent(s1, ss->evA, 0));
     NF_CUDA(cudaStreamWaitEvent(s2, ss->evA, 0));
   }
-  NF_TRY(plu_mask(params, pl, m, packed, kl, st));
-  {  // PL = P @ Lh
-    GemmP g;
-    g.A0 = params + pl.slot_off[NF_P_P]; g.lda0 = m.D; g.K0 = m.D; g.sA0 = pl.block_stride;
-    g.B0 = packed + kl.Lh; g.ldb0 = m.D; g.sB0 = kl.block_stride;
-    g.C = packed + kl.PL; g.ldc = m.D; g.sC = kl.block_stride;
-    g.M = m.D; g.N = m.D; g.batch = m.n;
-    NF_TRY(simt_gemm(g, st));
-    // W = PL @ Uh
-    g.A0 = packed + kl.PL; g.sA0 = kl.block_stride;
-    g.B0 = packed + kl.Uh;
-    g.C = packed + kl.W;
-    NF_TRY(simt_gemm(g, st));
-    NF_TRY(transpose2d(packed + kl.WT, m.D, kl.block_stride, 0, packed + kl.W, m.D, kl.block_stride, 0, m.D, m.D, m.n, 1, st));
+  if (m.D <= 32) {
+    NF_TRY(plu_build_small(params, pl, m, packed, kl, st));   // mask, PL, W, W^T, log|det| in one kernel
+  } else {
+    NF_TRY(plu_mask(params, pl, m, packed, kl, st));
+    {  // PL = P @ Lh
+      GemmP g;
+      g.A0 = params + pl.slot_off[NF_P_P]; g.lda0 = m.D; g.K0 = m.D; g.sA0 = pl.block_stride;
+      g.B0 = packed + kl.Lh; g.ldb0 = m.D; g.sB0 = kl.block_stride;
+      g.C = packed + kl.PL; g.ldc = m.D; g.sC = kl.block_stride;
+      g.M = m.D; g.N = m.D; g.batch = m.n;
+      NF_TRY(simt_gemm(g, st));
+      // W = PL @ Uh
+      g.A0 = packed + kl.PL; g.sA0 = kl.block_stride;
+      g.B0 = packed + kl.Uh;
+      g.C = packed + kl.W;
+      NF_TRY(simt_gemm(g, st));
+      NF_TRY(transpose2d(packed + kl.WT, m.D, kl.block_stride, 0, packed + kl.W, m.D, kl.block_stride, 0, m.D, m.D, m.n, 1, st));
+    }
   }
   NF_TRY(fold_ln_affine(params, pl, m, packed, kl, s1));
   // K-major B operands of the data-gradient GEMMs: W2f^T (H1,C) and W1^T (K1,H1), per net and block
@@ -1249,12 +1253,16 @@ static int backward_impl(const NfFlowDesc* desc, const float* params, const void
     NF_TRY(wgrad_tn(m.prec, h, st));
   }
   if (dparams) {
-    GemmP g;  // T1 = P^T dW
     const float* prm = params + (int64_t)sub_begin * pl.block_stride;
     const float* pck = packed + (int64_t)sub_begin * kl.block_stride;
     float* dWr = w.dWs + (int64_t)sub_begin * DD;
     Dims mr = m;
     mr.n = nr;   // the parameter-sized kernels below run over this range's blocks only
+    float* dpr = dparams + (int64_t)sub_begin * pl.block_stride;
+    if (m.D <= 32) {
+      NF_TRY(plu_grad_small(prm, pl, mr, pck, kl, dWr, w.sumdld, dpr, st));
+    } else {
+    GemmP g;  // T1 = P^T dW
     g.transA = 1; g.A0 = prm + pl.slot_off[NF_P_P]; g.lda0 = m.D; g.sA0 = pl.block_stride; g.K0 = m.D;
     g.B0 = dWr; g.ldb0 = m.D; g.sB0 = DD;
     g.C = w.T1; g.ldc = m.D; g.sC = DD; g.M = m.D; g.N = m.D; g.batch = nr;
@@ -1269,8 +1277,8 @@ static int backward_impl(const NfFlowDesc* desc, const float* params, const void
     u.B0 = dWr; u.ldb0 = m.D; u.sB0 = DD;
     u.C = w.dUh; u.ldc = m.D; u.sC = DD; u.M = m.D; u.N = m.D; u.batch = nr;
     NF_TRY(simt_gemm(u, st));
-    float* dpr = dparams + (int64_t)sub_begin * pl.block_stride;
     NF_TRY(plu_grad_finish(prm, pl, mr, w.dLh, w.dUh, w.sumdld, dpr, st));
+    }
     NF_TRY(unfold_grads(prm, pl, mr, dpr, st));
     if (sar) {   // this sub-range's gradients are final: average them over the ranks while the next sub-range computes
       NF_CUDA(cudaEventRecord(sar->evD, st));
@@ -1499,6 +1507,9 @@ int nf_flow_inverse_backward(const NfFlowDesc* desc, const float* params, const 
   }
   if (dz) NF_CUDA(cudaMemcpyAsync(dz, gcur, BD * sizeof(float), cudaMemcpyDeviceToDevice, st));
   if (dparams) {
+    if (m.D <= 32) {
+      NF_TRY(plu_grad_small(params, pl, m, packed, kl, w.dWs, w.sumdld, dparams, st, -1.0f));
+    } else {
     GemmP g;  // T1 = P^T dW
     g.transA = 1; g.A0 = params + pl.slot_off[NF_P_P]; g.lda0 = m.D; g.sA0 = pl.block_stride; g.K0 = m.D;
     g.B0 = w.dWs; g.ldb0 = m.D; g.sB0 = DD;
@@ -1515,6 +1526,7 @@ int nf_flow_inverse_backward(const NfFlowDesc* desc, const float* params, const 
     u.C = w.dUh; u.ldc = m.D; u.sC = DD; u.M = m.D; u.N = m.D; u.batch = m.n;
     NF_TRY(simt_gemm(u, st));
     NF_TRY(plu_grad_finish(params, pl, m, w.dLh, w.dUh, w.sumdld, dparams, st, -1.0f));
+    }
     NF_TRY(unfold_grads(params, pl, m, dparams, st));
   }
   return 0;
