@@ -169,6 +169,14 @@ NF_API int nf_flow_backward_range(const NfFlowDesc* desc, const float* params, c
  *   nf_dp_init        every rank, with its CUDA device current (collective: ncclCommInitRank)
  *   nf_dp_allreduce   in-place sum or average of a device buffer (standalone use: the encoder's arena)
  *   nf_dp_broadcast   in-place broadcast from `root` (initial parameter replica)
+ *   nf_dp_p2p_alloc / nf_dp_p2p_connect / nf_dp_p2p_enable / nf_dp_p2p_status
+ *                     all-reduce over NVLink peer memory for the ranks of one box (2..8): every rank allocates its
+ *                     exchange buffer (`max_floats` = largest arena to take this path) and gets a 64-byte CUDA IPC
+ *                     handle; the host gathers the handles of all ranks in rank order and every rank connects; once
+ *                     ALL ranks have connected (the host agrees on that), nf_dp_p2p_enable(1) routes nf_dp_allreduce
+ *                     and nf_flow_backward_dp of arenas up to max_floats through one peer-store kernel per rank (sum in
+ *                     rank order: bit-identical on every replica) instead of NCCL.  status: 1 active, 0 off, -1 a peer
+ *                     did not arrive within the kernel's time-out.
  *   nf_flow_backward_dp  nf_flow_backward + the averaged gradient arena: blocks are processed from the top down in
  *                     buckets of `bucket_blocks` blocks; each finished bucket (one contiguous slice of the arena) is
  *                     all-reduced on a side stream while the next bucket computes.  dparams must not be NULL. */
@@ -177,6 +185,11 @@ NF_API int nf_dp_init(const void* id128, int32_t rank, int32_t world);
 NF_API int nf_dp_world(void);
 NF_API int nf_dp_allreduce(float* buf, int64_t n, int32_t average, void* stream);
 NF_API int nf_dp_broadcast(float* buf, int64_t n, int32_t root, void* stream);
+NF_API int nf_dp_p2p_alloc(int64_t max_floats, void* handle64);
+NF_API int nf_dp_p2p_connect(const void* handles, int32_t rank, int32_t world);
+NF_API int nf_dp_p2p_enable(int32_t on);
+NF_API int nf_dp_p2p_status(void);
+NF_API int nf_dp_p2p_timeline(uint64_t* ns6);   /* debug: CTA 0's phase boundaries of the last call, %globaltimer ns */
 NF_API int nf_dp_shutdown(void);
 NF_API int nf_flow_backward_dp(const NfFlowDesc* desc, const float* params, const void* packed,
                         const void* stash, const float* y, int64_t B,

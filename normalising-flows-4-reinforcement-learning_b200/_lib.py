@@ -77,6 +77,11 @@ def _load():
         "nf_dp_world": (c_int, []),
         "nf_dp_allreduce": (c_int, [fp, i64, c_int32, vp]),
         "nf_dp_broadcast": (c_int, [fp, i64, c_int32, vp]),
+        "nf_dp_p2p_alloc": (c_int, [i64, vp]),
+        "nf_dp_p2p_connect": (c_int, [vp, c_int32, c_int32]),
+        "nf_dp_p2p_enable": (c_int, [c_int32]),
+        "nf_dp_p2p_status": (c_int, []),
+        "nf_dp_p2p_timeline": (c_int, [vp]),
         "nf_dp_shutdown": (c_int, []),
         "nf_affine_logdet_fwd": (c_int, [fp, fp, fp, fp, fp, c_float, i64, c_int32, fp, fp, fp, vp]),
         "nf_affine_logdet_inv": (c_int, [fp, fp, fp, fp, fp, c_float, i64, c_int32, fp, fp, vp]),

@@ -15,6 +15,7 @@ include/nf_b200.h; there is no CPU or PyTorch-eager fallback -- CPU tensors rais
 from __future__ import annotations
 
 import ctypes
+import os
 import itertools
 import operator
 import math
@@ -182,7 +183,39 @@ def _init_library_comm(process_group, device):
         raw = bytes(ident.cpu().numpy().tobytes())
         torch.cuda.synchronize(device)
         _lib.check(lib.nf_dp_init(ctypes.c_char_p(raw), rank, world), "nf_dp_init")
+        _connect_peer_memory(process_group, device, rank, world)
     _LIB_COMM[key] = world
+
+
+# Largest gradient arena (bytes) averaged by the library's peer-memory kernel instead of NCCL; 0 turns the path off.
+_P2P_MAX_BYTES = int(os.environ.get("NF_B200_DP_P2P_MAX_BYTES", str(16 << 20)))
+
+
+def _connect_peer_memory(process_group, device, rank, world):
+    """All-reduce over NVLink peer memory (csrc/dp.cu): every rank allocates its exchange buffer, the 64-byte CUDA IPC
+    handles travel through ``torch.distributed``, every rank maps its peers' buffers.  The path is switched on only when
+    ALL ranks connected; otherwise (more than 8 ranks, ranks on different boxes, IPC refused) NCCL keeps the job."""
+    import torch.distributed as dist
+    if _P2P_MAX_BYTES <= 0 or world < 2 or world > 8:
+        return False
+    mine = torch.zeros(65, dtype=torch.uint8, device=device)
+    buf = ctypes.create_string_buffer(64)
+    if lib.nf_dp_p2p_alloc(_P2P_MAX_BYTES // 4, buf) == 0:
+        mine[:64].copy_(torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8))
+        mine[64] = 1
+    everyone = torch.zeros(world, 65, dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(everyone, mine, group=process_group)
+    everyone = everyone.cpu()
+    ok = bool(everyone[:, 64].min().item())
+    if ok:
+        handles = everyone[:, :64].contiguous().numpy().tobytes()
+        ok = lib.nf_dp_p2p_connect(ctypes.c_char_p(handles), rank, world) == 0
+    agreed = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(agreed, op=dist.ReduceOp.MIN, group=process_group)
+    ok = bool(agreed.item())
+    if ok:
+        _lib.check(lib.nf_dp_p2p_enable(1), "nf_dp_p2p_enable")
+    return ok
 
 
 class _Flow(torch.autograd.Function):

@@ -62,5 +62,12 @@ if rank == 0:
     (g,) = torch.autograd.grad((-0.5 * (z * z).sum(1) + ld).sum(), [a])
     torch.cuda.synchronize()
     print("rank-local input gradient ok", tuple(g.shape), flush=True)
+if world <= 8:
+    # the flow's arena went through the library's peer-memory kernel (csrc/dp.cu), and no peer ever timed out
+    from nf_b200 import _lib
+    status = _lib.lib.nf_dp_p2p_status()
+    if rank == 0:
+        print("peer-memory all-reduce status:", status, flush=True)
+    assert status == 1 or int(os.environ.get("NF_B200_DP_P2P_MAX_BYTES", "1")) == 0, status
 dist.barrier()
 dist.destroy_process_group()
