@@ -307,11 +307,11 @@ class Runner:
     def train_step(self, xd, yd):
         model, D = self.model, self.D
         model._packed_key = None          # parameters change every real training step: rebuild the tables
-        for p in self.plist:              # optimizer.zero_grad(set_to_none=True)
-            p.grad = None
         yd = yd.detach().requires_grad_(True)   # y is the encoder output in the reference (torch_nfbc_ant.py:267)
         z, _, ld = model(xd, yd)
         loss = -(model.prior.log_prob(z) + ld).mean()          # the reference's loss line, torch_nfbc_ant.py:269-270
+        for p in self.plist:              # optimizer.zero_grad(set_to_none=True): between the loss and backward(),
+            p.grad = None                 # where the reference has it (torch_nfbc_ant.py:272)
         loss.backward()
         return loss
 
@@ -319,9 +319,9 @@ class Runner:
         # the same step with the library's fused loss (RealNVP.nll: SURVEY section 8 row f3)
         model = self.model
         model._packed_key = None
+        loss = model.nll(xd, yd.detach().requires_grad_(True))
         for p in self.plist:
             p.grad = None
-        loss = model.nll(xd, yd.detach().requires_grad_(True))
         loss.backward()
         return loss
 
@@ -495,11 +495,11 @@ class TarflowRunner(Runner):
 
     def train_step(self, xd, yd):
         model, D = self.model, self.D
-        for p in self.plist:
-            p.grad = None
         yd = yd.detach().requires_grad_(True)       # the encoder output (torch_nfgcbc.py:141)
         z, _, ld = model(xd, yd)
         loss = -(model.prior.log_prob(z.squeeze(-1)) + ld).mean()                   # torch_nfgcbc.py:142
+        for p in self.plist:                        # optimizer.zero_grad() sits between loss and backward()
+            p.grad = None
         loss.backward()
         return loss
 
