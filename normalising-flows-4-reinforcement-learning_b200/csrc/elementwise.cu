@@ -591,6 +591,175 @@ __global__ void __launch_bounds__(256) k_plu_build_small(const float* __restrict
   }
 }
 
+// ---- all derived tables of the forward direction in ONE kernel (D <= 32) ---------------------------------------
+// nf_flow_prepare(NF_PREP_FWD) was a graph of 9 kernels in three branches joined by the hi/lo split (critical path
+// fold -> transpose -> split, ~24 us on C2a, in front of every training step because the parameters change every
+// step).  Every table is a pure function of the parameters, so each CTA of this kernel produces its tables directly --
+// value, rounded-to-tf32 `hi` and residual `lo` in the same store -- and nothing waits for another CTA:
+//   blockIdx.z = block * 2 + net, blockIdx.x = job -- every job is one load -> store pass, no loop-carried latency:
+//     32 x 32 tile of W2:   W2f = W2 diag(gamma1) and its transpose W2fT
+//     8 rows of W2:         b2f = b2 + W2 beta1 (one warp per row);   one more job: W3f = W3 diag(gamma2), b3f = b3 + W3 beta2
+//     32 x 32 tile of W1:   W1T (transpose)
+//     8 rows of W1:         W1p (y columns moved to the aligned column dcp)
+//     last job, net 0 only: the PLU tables of the block (k_plu_build_small's body) and, in block 0, the total log|det|
+__device__ __forceinline__ void put3(float* packed, long long off, float v, long long hi_off, long long lo_off) {
+  packed[off] = v;
+  if (hi_off) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    const float h = __uint_as_float(r);
+    packed[off + hi_off] = h;
+    packed[off + lo_off] = v - h;
+  }
+}
+
+struct PrepJobs { int tF, rB, tW, rP; };   // job counts: W2 tiles, W2 row groups (+1: W3), W1 tiles, W1 row groups (+1: PLU)
+
+__global__ void __launch_bounds__(256) k_prepare_fwd(const float* __restrict__ params, NfParamLayout pl, Dims m,
+                                                     float* __restrict__ packed, PackedLayout kl, PrepJobs J) {
+  NF_PDL_ENTRY();
+  __shared__ float tile[32][33];
+  __shared__ float sP[1024], sLh[1024], sUh[1024], sPL[1024];
+  const int b = blockIdx.z >> 1, net = blockIdx.z & 1;
+  int job = blockIdx.x;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  const float* pn = params + (long long)b * pl.block_stride + net * pl.net_stride;
+  const long long kn = (long long)b * kl.block_stride + kl.net0 + net * kl.net_stride;   // offset of this net's tables
+  const long long HI = kl.hi_off, LO = kl.lo_off;
+  if (job < J.tF) {
+    const float* W = pn + pl.slot_off[NF_P_W2];
+    const int tk = (m.H1 + 31) / 32, r0 = (job / tk) * 32, k0 = (job % tk) * 32, K = m.H1;
+    const int k = k0 + tx;
+    const float g = k < K ? pn[pl.slot_off[NF_P_G1] + k] : 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int r = r0 + ty + 8 * q;
+      float v = 0.f;
+      if (r < m.C && k < K) {
+        v = W[(long long)r * K + k] * g;
+        put3(packed, kn + kl.W2f + (long long)r * K + k, v, HI, LO);
+      }
+      tile[ty + 8 * q][tx] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {                  // W2fT[k, r]: row k0 + ty + 8q, column r0 + tx
+      const int kk = k0 + ty + 8 * q, r = r0 + tx;
+      if (kk < K && r < m.C) put3(packed, kn + kl.W2fT + (long long)kk * m.C + r, tile[tx][ty + 8 * q], HI, LO);
+    }
+    return;
+  }
+  job -= J.tF;
+  if (job < J.rB) {                                // b2f: one warp per row, lane-strided like k_fold (same summation order)
+    const int r = job * 8 + ty, K = m.H1;
+    if (r >= m.C) return;
+    const float* W = pn + pl.slot_off[NF_P_W2] + (long long)r * K;
+    const float* bet = pn + pl.slot_off[NF_P_BE1];
+    float acc = 0.f;
+    for (int k = tx; k < K; k += 32) acc = fmaf(W[k], bet[k], acc);
+    acc = warp_sum(acc);
+    if (tx == 0) put3(packed, kn + kl.b2f + r, pn[pl.slot_off[NF_P_B2] + r] + acc, HI, LO);
+    return;
+  }
+  job -= J.rB;
+  if (job == 0) {
+    const float* W = pn + pl.slot_off[NF_P_W3];
+    const float* gam = pn + pl.slot_off[NF_P_G2];
+    const float* bet = pn + pl.slot_off[NF_P_BE2];
+    for (int r = ty; r < m.dt; r += 8) {
+      float acc = 0.f;
+      for (int k = tx; k < m.C; k += 32) {
+        const float w = W[(long long)r * m.C + k];
+        put3(packed, kn + kl.W3f + (long long)r * m.C + k, w * gam[k], HI, LO);
+        acc = fmaf(w, bet[k], acc);
+      }
+      acc = warp_sum(acc);
+      if (tx == 0) put3(packed, kn + kl.b3f + r, pn[pl.slot_off[NF_P_B3] + r] + acc, HI, LO);
+    }
+    return;
+  }
+  job -= 1;
+  if (job < J.tW) {                                // W1T[c, r] = W1[r, c]
+    const float* W = pn + pl.slot_off[NF_P_W1];
+    const int tc = (m.K1 + 31) / 32, r0 = (job / tc) * 32, c0 = (job % tc) * 32;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int r = r0 + ty + 8 * q, c = c0 + tx;
+      tile[ty + 8 * q][tx] = (r < m.H1 && c < m.K1) ? W[(long long)r * m.K1 + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int c = c0 + ty + 8 * q, r = r0 + tx;
+      if (c < m.K1 && r < m.H1) put3(packed, kn + kl.W1T + (long long)c * m.H1 + r, tile[tx][ty + 8 * q], HI, LO);
+    }
+    return;
+  }
+  job -= J.tW;
+  if (job < J.rP) {                                // W1p rows
+    const float* W = pn + pl.slot_off[NF_P_W1];
+    const int r = job * 8 + ty;
+    if (r >= m.H1) return;
+    for (int c = tx; c < kl.K1p; c += 32) {
+      float v = 0.f;
+      if (c < m.dc) v = W[(long long)r * m.K1 + c];
+      else if (c >= kl.dcp && c - kl.dcp < m.R) v = W[(long long)r * m.K1 + m.dc + c - kl.dcp];
+      put3(packed, kn + kl.W1p + (long long)r * kl.K1p + c, v, HI, LO);
+    }
+    return;
+  }
+  if (net == 0) {
+    const int D = m.D, DD = D * D;
+    const float* pb = params + (long long)b * pl.block_stride;
+    const long long kb = (long long)b * kl.block_stride;
+    const float* L = pb + pl.slot_off[NF_P_L];
+    const float* U = pb + pl.slot_off[NF_P_U];
+    const float* sv = pb + pl.slot_off[NF_P_S];
+    const float* P = pb + pl.slot_off[NF_P_P];
+    for (int idx = threadIdx.x; idx < DD; idx += blockDim.x) {
+      const int i = idx / D, j = idx % D;
+      const float lh = i > j ? L[idx] : (i == j ? 1.f : 0.f);
+      const float uh = i < j ? U[idx] : (i == j ? sv[i] : 0.f);
+      sP[idx] = P[idx]; sLh[idx] = lh; sUh[idx] = uh;
+      put3(packed, kb + kl.Lh + idx, lh, HI, LO);
+      put3(packed, kb + kl.Uh + idx, uh, HI, LO);
+    }
+    if (threadIdx.x < 32) {                           // log|det| of this block; block 0 also writes the total over the blocks
+      float acc = 0.f;
+      for (int i = threadIdx.x; i < D; i += 32) acc += logf(fabsf(sv[i]));
+      acc = warp_sum(acc);
+      if (threadIdx.x == 0) packed[kl.logdet_c + b] = acc;
+      if (b == 0) {
+        float tot = 0.f;
+        for (int bb = 0; bb < m.n; ++bb) {            // same order and arithmetic as k_plu_mask + k_logdet_total
+          const float* sb = params + (long long)bb * pl.block_stride + pl.slot_off[NF_P_S];
+          float a = 0.f;
+          for (int i = threadIdx.x; i < D; i += 32) a += logf(fabsf(sb[i]));
+          a = warp_sum(a);
+          tot += a;
+        }
+        if (threadIdx.x == 0) packed[kl.logdet_total] = tot;
+      }
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < DD; idx += blockDim.x) {
+      const int i = idx / D, j = idx % D;
+      float acc = 0.f;
+      for (int k = 0; k < D; ++k) acc = fmaf(sP[i * D + k], sLh[k * D + j], acc);
+      sPL[idx] = acc;
+      put3(packed, kb + kl.PL + idx, acc, HI, LO);
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < DD; idx += blockDim.x) {
+      const int i = idx / D, j = idx % D;
+      float acc = 0.f;
+      for (int k = 0; k < D; ++k) acc = fmaf(sPL[i * D + k], sUh[k * D + j], acc);
+      put3(packed, kb + kl.W + idx, acc, HI, LO);
+      put3(packed, kb + kl.WT + j * D + i, acc, HI, LO);
+    }
+  }
+}
+
 // Small flow dimensions: T1 = P^T dW, dLh = T1 Uh^T, dUh = (P Lh)^T dW and the masking / diagonal terms of
 // k_plu_grad_finish in one kernel, one CTA per block (three FFMA GEMM launches + the finish kernel before).
 __global__ void __launch_bounds__(256) k_plu_grad_small(const float* __restrict__ params, NfParamLayout pl, int D,
@@ -726,18 +895,30 @@ __global__ void k_unfold(const float* params, NfParamLayout pl, Dims m, float* d
   float* dn = dparams + (long long)b * pl.block_stride + net * pl.net_stride;
   const int sw = layer == 0 ? NF_P_W2 : NF_P_W3, sb = layer == 0 ? NF_P_B2 : NF_P_B3;
   const int sg = layer == 0 ? NF_P_G1 : NF_P_G2, sbe = layer == 0 ? NF_P_BE1 : NF_P_BE2;
-  const float* W = pn + pl.slot_off[sw];
-  float* G = dn + pl.slot_off[sw];
-  const float* g = dn + pl.slot_off[sb];
+  const float* __restrict__ W = pn + pl.slot_off[sw];
+  float* __restrict__ G = dn + pl.slot_off[sw];
+  const float* __restrict__ g = dn + pl.slot_off[sb];
   const float gam = pn[pl.slot_off[sg] + col], bet = pn[pl.slot_off[sbe] + col];
   float dgam = 0.f, dbet = 0.f;
   const int n1 = min(rows, n0 + kUnfoldRows);
-  for (int n = n0; n < n1; ++n) {
+  // all loads of the strip first (the in-place store to G made every iteration wait for the one before it: this
+  // kernel is the tail of the backward pass, 12.8 us on C2a for 4 MB of gradients)
+  float Gv[kUnfoldRows], wv[kUnfoldRows], gn[kUnfoldRows];
+#pragma unroll
+  for (int i = 0; i < kUnfoldRows; ++i) {
+    const int n = n0 + i;
+    const bool ok = n < n1;
     const long long idx = (long long)n * K + col;
-    const float Gv = G[idx], w = W[idx], gn = g[n];
-    dgam = fmaf(Gv, w, dgam);
-    dbet = fmaf(gn, w, dbet);
-    G[idx] = fmaf(Gv, gam, gn * bet);
+    Gv[i] = ok ? G[idx] : 0.f;
+    wv[i] = ok ? W[idx] : 0.f;
+    gn[i] = ok ? g[n] : 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < kUnfoldRows; ++i) {
+    const int n = n0 + i;
+    dgam = fmaf(Gv[i], wv[i], dgam);
+    dbet = fmaf(gn[i], wv[i], dbet);
+    if (n < n1) G[(long long)n * K + col] = fmaf(Gv[i], gam, gn[i] * bet);
   }
   atomicAdd(&dn[pl.slot_off[sg] + col], dgam);    // the gamma / beta slots are zero on entry
   atomicAdd(&dn[pl.slot_off[sbe] + col], dbet);
@@ -951,6 +1132,19 @@ int plu_build_small(const float* params, const NfParamLayout& pl, const Dims& m,
   NF_LAUNCH((k_plu_build_small), (unsigned)m.n, 256, 0, st, params, pl, m.D, packed, kl);
   NF_LAUNCHED();
   NF_LAUNCH((k_logdet_total), 1, 32, 0, st, packed, kl, m.n);
+  NF_LAUNCHED();
+  return 0;
+}
+
+int prepare_fwd_fused(const float* params, const NfParamLayout& pl, const Dims& m, float* packed, const PackedLayout& kl,
+                      cudaStream_t st) {
+  NF_CHECK_ARG(m.D <= 32, NF_E_UNSUPPORTED, "prepare_fwd_fused: D=%d", m.D);
+  PrepJobs J;
+  J.tF = (int)(cdiv(m.C, 32) * cdiv(m.H1, 32)); J.rB = (int)cdiv(m.C, 8);
+  J.tW = (int)(cdiv(m.H1, 32) * cdiv(m.K1, 32)); J.rP = (int)cdiv(m.H1, 8);
+  dim3 grid((unsigned)(J.tF + J.rB + 1 + J.tW + J.rP + 1), 1, (unsigned)(2 * m.n));
+  ProfScope prof(st, PROF_PARAM, 0.0);
+  NF_LAUNCH((k_prepare_fwd), grid, 256, 0, st, params, pl, m, packed, kl, J);
   NF_LAUNCHED();
   return 0;
 }

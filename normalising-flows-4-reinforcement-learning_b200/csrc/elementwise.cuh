@@ -50,6 +50,10 @@ int plu_mask(const float* params, const NfParamLayout& pl, const Dims& m, float*
 // and plu_grad_finish) in one kernel
 int plu_build_small(const float* params, const NfParamLayout& pl, const Dims& m, float* packed, const PackedLayout& kl,
                     cudaStream_t st);
+// D <= 32: every derived table of the forward direction (PLU tables, folded LayerNorm affine and its transpose, first-layer
+// packings, total log|det|) with their hi / lo copies, in one kernel with no dependency between CTAs
+int prepare_fwd_fused(const float* params, const NfParamLayout& pl, const Dims& m, float* packed, const PackedLayout& kl,
+                      cudaStream_t st);
 int plu_grad_small(const float* params, const NfParamLayout& pl, const Dims& m, const float* packed, const PackedLayout& kl,
                    const float* dW, const float* sum_dld, float* dparams, cudaStream_t st, float ld_sign = 1.0f);
 int plu_tri_inverse(const float* packed, const PackedLayout& kl, const Dims& m, float* uinv, float* linv,

@@ -42,7 +42,7 @@ const OptDef kOpts[NF_OPT_COUNT] = {
     {"stack", "NF_B200_STACK", -1},      {"stack_nsg", "NF_B200_STACK_NSG", 2},   {"whatif", "NF_B200_WHATIF", 0},
     {"ride", "NF_B200_RIDE", 1},         {"defer_wgrad", "NF_B200_DEFER_WGRAD", -1},
     {"mcast", "NF_B200_MCAST", -1},      {"bn64", "NF_B200_BN64", 1},
-    {"tf_ar", "NF_B200_TF_AR", -1},
+    {"tf_ar", "NF_B200_TF_AR", -1},      {"prep_fused", "NF_B200_PREP_FUSED", 1},
 };
 int g_opt[NF_OPT_COUNT];
 bool g_opt_init = false;
@@ -550,6 +550,8 @@ int nf_flow_prepare(const NfFlowDesc* desc, const float* params, void* packed_v,
   key.op = 1; key.desc = *desc; key.flags = what; key.ws_bytes = ws_bytes;
   key.ptr[0] = params; key.ptr[1] = packed_v; key.ptr[2] = workspace;
   auto body = [&](cudaStream_t st) -> int {
+  // forward-direction tables of a small flow dimension: one kernel, no dependent launches (elementwise.cu)
+  if (!(what & NF_PREP_INV) && m.D <= 32 && option(NF_OPT_PREP_FUSED)) return prepare_fwd_fused(params, pl, m, packed, kl, st);
   // three independent chains (PLU tables | folded LayerNorm + its transpose | first-layer packings) run as parallel
   // branches; the hi/lo split of all tables joins them
   SideStreams* ss = side_streams();

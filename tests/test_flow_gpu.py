@@ -419,7 +419,8 @@ def test_launch_graph_replay_is_bit_identical(precision):
 
 OPTION_SETTINGS = [("pdl", 0), ("streams", 0), ("tma_store", 0), ("fused_ln", 0), ("fused_ln", 1), ("fused_tail", 1),
                    ("nacc", 1), ("bn256", 2), ("bn256", 1), ("ts", 0), ("presplit", 0),
-                   ("stack", 0), ("stack", 1), ("stack_nsg", 1), ("ride", 0), ("defer_wgrad", 0), ("defer_wgrad", 1), ("mcast", 0), ("mcast", 1)]
+                   ("stack", 0), ("stack", 1), ("stack_nsg", 1), ("ride", 0), ("defer_wgrad", 0), ("defer_wgrad", 1), ("mcast", 0), ("mcast", 1),
+                   ("prep_fused", 0)]
 
 
 @pytest.mark.parametrize("name,value", OPTION_SETTINGS, ids=[f"{n}={v}" for n, v in OPTION_SETTINGS])
@@ -465,6 +466,36 @@ def test_options_are_equivalent(name, value):
     tol = 1e-5 if name == "nacc" else 3e-6   # one accumulator instead of three: the truncation noise itself changes
     for a, b, nm in zip(ref, got, ("z", "ld", "dx", "dy", "dparams", "rev")):
         assert rel_err(b, a) <= tol, (name, value, nm, rel_err(b, a))
+
+
+@pytest.mark.parametrize("shape", [dict(D=8, C=256, R=64, n=3, H1=256), dict(D=2, C=256, R=64, n=2, H1=320),
+                                   dict(D=9, C=128, R=37 * 4, n=2, H1=128), dict(D=32, C=64, R=16, n=2, H1=96)],
+                         ids=["C2a-like", "C3-like", "odd-D", "D32"])
+def test_one_kernel_prepare_writes_the_same_tables(shape):
+    """nf_flow_prepare(NF_PREP_FWD) for D <= 32 is one kernel that writes every derived table with its hi / lo copies
+    directly (k_prepare_fwd); the graph of separate kernels it replaces (option prep_fused = 0) must produce the same
+    bytes -- same products, same summation order."""
+    D, C, R, n, H1 = shape["D"], shape["C"], shape["R"], shape["n"], shape["H1"]
+    sd = synth.make_state_dict(D, C, R, n, seed=77, H1=H1)
+    model = build_model(dict(D=D, C=C, R=R, n=n, B=64, H1=H1), sd, "fp32", first_hidden=H1)
+    x, y = synth.make_inputs(8, D, R, seed=3)
+    with torch.no_grad():
+        model(t(x), t(y))                    # allocates the table buffer
+    tables = []
+    default = _lib.get_option("prep_fused")
+    try:
+        for v in (1, 0):
+            _lib.set_option("prep_fused", v)
+            model._packed.zero_()
+            model._packed_key = None
+            model._prepared(_lib.NF_PREP_FWD, model._flat.device)
+            torch.cuda.synchronize()
+            tables.append(model._packed.clone())
+    finally:
+        _lib.set_option("prep_fused", default)
+    a, b = (v.view(torch.float32) for v in tables)
+    assert float(a.abs().max()) > 0
+    assert torch.equal(a, b), int((a != b).sum())
 
 
 def test_fused_nll_and_flat_adamw_match_the_torch_training_step():
