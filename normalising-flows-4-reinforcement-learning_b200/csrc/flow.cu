@@ -42,7 +42,7 @@ const OptDef kOpts[NF_OPT_COUNT] = {
     {"stack", "NF_B200_STACK", -1},      {"stack_nsg", "NF_B200_STACK_NSG", 2},   {"whatif", "NF_B200_WHATIF", 0},
     {"ride", "NF_B200_RIDE", 1},         {"defer_wgrad", "NF_B200_DEFER_WGRAD", -1},
     {"mcast", "NF_B200_MCAST", -1},      {"bn64", "NF_B200_BN64", 1},
-    {"tf_ar", "NF_B200_TF_AR", -1},      {"prep_fused", "NF_B200_PREP_FUSED", 1},
+    {"tf_ar", "NF_B200_TF_AR", -1},      {"prep_fused", "NF_B200_PREP_FUSED", 1}, {"defer_dy", "NF_B200_DEFER_DY", 1},
 };
 int g_opt[NF_OPT_COUNT];
 bool g_opt_init = false;
@@ -967,6 +967,16 @@ static int backward_impl(const NfFlowDesc* desc, const float* params, const void
     h = e; h.A = w.gBall; h.lda = m.H1; h.B = y; h.ldb = m.R; h.sB = 0; h.ldc = m.K1; h.M = m.H1; h.N = m.R;
     defer = rides_ok(m.prec, e) && rides_ok(m.prec, h);
   }
+  // with du1 of every block kept, the dy GEMMs of the blocks (M = B, N = R, K = 2 H1 each; C2a: 6 launches of 11 us beside
+  // the chain) are ONE launch after the loop whose batch entries accumulate into dy with red.add
+  bool defer_dy = false;
+  if (defer && dy && has_y && ss && prec_tc(m.prec) && m.R >= 16 && option(NF_OPT_DEFER_DY)) {
+    TcGemmP t;
+    t.A0 = w.gBall; t.lda0 = m.H1; t.K0 = m.H1; t.A1 = w.gBall + B * Hm; t.lda1 = m.H1; t.K1 = m.H1;
+    t.B0 = packed + kl.net0 + kl.W1T + (int64_t)m.dc * m.H1; t.ldb0 = m.H1; t.B1 = t.B0 + kl.net_stride; t.ldb1 = m.H1;
+    t.C = dy; t.ldc = m.R; t.M = (int)B; t.N = m.R; t.accumulate = 1;
+    defer_dy = tc_gemm_supported(t);
+  }
   bool any_ar = false;
   for (int sub_end = block_end; sub_end > block_begin;) {
   const int sub_begin = dp_bucket > 0 ? std::max(block_begin, sub_end - dp_bucket) : block_begin;
@@ -1150,7 +1160,7 @@ static int backward_impl(const NfFlowDesc* desc, const float* params, const void
         g.B0 += (int64_t)m.dc * m.H1; g.B1 += (int64_t)m.dc * m.H1;
         if (kl.hi_off) { g.B0hi = g.B0 + kl.hi_off; g.B0lo = g.B0 + kl.lo_off; g.B1hi = g.B1 + kl.hi_off; g.B1lo = g.B1 + kl.lo_off; }
         g.C = dy; g.ldc = m.R; g.N = m.R;
-        if (!(whatif & 4)) NF_TRY(linear_nt(m.prec, g, s2));
+        if (!(whatif & 4) && !defer_dy) NF_TRY(linear_nt(m.prec, g, s2));
       }
     }
     float* dst = (i > 0 || dx) ? ((i == 0) ? dx : (pp ? w.d1 : w.d0)) : nullptr;
@@ -1235,6 +1245,20 @@ static int backward_impl(const NfFlowDesc* desc, const float* params, const void
       if (used2[par]) NF_CUDA(cudaStreamWaitEvent(st, ss->done2[par], 0));
     }
   }
+  cudaStream_t tail_st = st;
+  if (defer_dy && !(whatif & 4)) {
+    NF_CUDA(cudaEventRecord(ss->evA, st));
+    NF_CUDA(cudaStreamWaitEvent(s2, ss->evA, 0));
+    TcGemmP g;
+    g.A0 = w.gBall + (int64_t)sub_begin * 2 * B * Hm; g.lda0 = m.H1; g.K0 = m.H1; g.sA0 = 2 * B * Hm;
+    g.A1 = g.A0 + B * Hm; g.lda1 = m.H1; g.K1 = m.H1; g.sA1 = 2 * B * Hm;
+    g.B0 = packed + (int64_t)sub_begin * kl.block_stride + kl.net0 + kl.W1T + (int64_t)m.dc * m.H1; g.ldb0 = m.H1;
+    g.B1 = g.B0 + kl.net_stride; g.ldb1 = m.H1; g.sB0 = g.sB1 = kl.block_stride;
+    if (kl.hi_off) { g.B0hi = g.B0 + kl.hi_off; g.B0lo = g.B0 + kl.lo_off; g.B1hi = g.B1 + kl.hi_off; g.B1lo = g.B1 + kl.lo_off; }
+    g.C = dy; g.ldc = m.R; g.sC = 0; g.M = (int)B; g.N = m.R; g.batch = nr; g.accumulate = 1;
+    NF_TRY(linear_nt(m.prec, g, s2));
+    NF_CUDA(cudaEventRecord(ss->done2[0], s2));
+  }
   if (defer && !(whatif & 2)) {
     float* dpr = dparams + (int64_t)sub_begin * pl.block_stride;
     TcGemmTnP g;   // e. G2 = du2^T x_hat1 and gb2 = colsum(du2) of every block and net of the range
@@ -1244,6 +1268,11 @@ static int backward_impl(const NfFlowDesc* desc, const float* params, const void
     g.M = m.C; g.N = m.H1; g.K = B; g.batch = 2 * nr; g.inner = 2;
     g.colsum = dpr + pl.slot_off[NF_P_B2]; g.sColsum = pl.net_stride; g.sColsum2 = pl.block_stride;
     NF_TRY(wgrad_tn(m.prec, g, st));
+    if (ss && dparams) {   // the parameter-sized tail (PLU gradients, un-folding) needs nothing of dW1: it runs beside it
+      NF_CUDA(cudaEventRecord(ss->evC, st));
+      NF_CUDA(cudaStreamWaitEvent(s1, ss->evC, 0));
+      tail_st = s1;
+    }
     TcGemmTnP h;   // h. dW1 = du1^T [x_cond | y] and gb1 = colsum(du1)
     h.A = w.gBall + (int64_t)sub_begin * 2 * B * Hm; h.lda = m.H1; h.sA = B * Hm;
     h.B = y; h.ldb = m.R; h.sB = 0;
@@ -1262,26 +1291,30 @@ static int backward_impl(const NfFlowDesc* desc, const float* params, const void
     mr.n = nr;   // the parameter-sized kernels below run over this range's blocks only
     float* dpr = dparams + (int64_t)sub_begin * pl.block_stride;
     if (m.D <= 32) {
-      NF_TRY(plu_grad_small(prm, pl, mr, pck, kl, dWr, w.sumdld, dpr, st));
+      NF_TRY(plu_grad_small(prm, pl, mr, pck, kl, dWr, w.sumdld, dpr, tail_st));
     } else {
     GemmP g;  // T1 = P^T dW
     g.transA = 1; g.A0 = prm + pl.slot_off[NF_P_P]; g.lda0 = m.D; g.sA0 = pl.block_stride; g.K0 = m.D;
     g.B0 = dWr; g.ldb0 = m.D; g.sB0 = DD;
     g.C = w.T1; g.ldc = m.D; g.sC = DD; g.M = m.D; g.N = m.D; g.batch = nr;
-    NF_TRY(simt_gemm(g, st));
+    NF_TRY(simt_gemm(g, tail_st));
     GemmP h;  // dLh = T1 Uh^T
     h.A0 = w.T1; h.lda0 = m.D; h.sA0 = DD; h.K0 = m.D;
     h.B0 = pck + kl.Uh; h.ldb0 = m.D; h.sB0 = kl.block_stride; h.transB = 1;
     h.C = w.dLh; h.ldc = m.D; h.sC = DD; h.M = m.D; h.N = m.D; h.batch = nr;
-    NF_TRY(simt_gemm(h, st));
+    NF_TRY(simt_gemm(h, tail_st));
     GemmP u;  // dUh = (P Lh)^T dW
     u.transA = 1; u.A0 = pck + kl.PL; u.lda0 = m.D; u.sA0 = kl.block_stride; u.K0 = m.D;
     u.B0 = dWr; u.ldb0 = m.D; u.sB0 = DD;
     u.C = w.dUh; u.ldc = m.D; u.sC = DD; u.M = m.D; u.N = m.D; u.batch = nr;
-    NF_TRY(simt_gemm(u, st));
-    NF_TRY(plu_grad_finish(prm, pl, mr, w.dLh, w.dUh, w.sumdld, dpr, st));
+    NF_TRY(simt_gemm(u, tail_st));
+    NF_TRY(plu_grad_finish(prm, pl, mr, w.dLh, w.dUh, w.sumdld, dpr, tail_st));
     }
-    NF_TRY(unfold_grads(prm, pl, mr, dpr, st));
+    NF_TRY(unfold_grads(prm, pl, mr, dpr, tail_st));
+    if (tail_st != st) {
+      NF_CUDA(cudaEventRecord(ss->done1[0], tail_st));
+      NF_CUDA(cudaStreamWaitEvent(st, ss->done1[0], 0));
+    }
     if (sar) {   // this sub-range's gradients are final: average them over the ranks while the next sub-range computes
       NF_CUDA(cudaEventRecord(sar->evD, st));
       NF_CUDA(cudaStreamWaitEvent(sar->s3, sar->evD, 0));
@@ -1289,6 +1322,7 @@ static int backward_impl(const NfFlowDesc* desc, const float* params, const void
       any_ar = true;
     }
   }
+  if (defer_dy && !(whatif & 4)) NF_CUDA(cudaStreamWaitEvent(st, ss->done2[0], 0));
   sub_end = sub_begin;
   }   // sub-ranges
   if (any_ar) {

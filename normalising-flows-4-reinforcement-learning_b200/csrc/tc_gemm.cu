@@ -43,6 +43,7 @@ struct KArgs {
   int accumulate, passes, raw_hi;
   int nacc;                       // main accumulators in rotation, 0 = all NACC (option "nacc")
   int splitk, chunks_per_split;   // MN-major form only
+  int shared_c;                   // K-major form: the batch entries accumulate into ONE output (red.add), e.g. dy over blocks
   // MN-major TS form, blockIdx.y == 0 CTAs only: the splitter threads already hold every element of their A column
   // (thread = output row m, elements = the batch rows of the stage), so the reductions over the batch rows that share
   // this operand ride along: colsum[z][m] += sum_k A[k, m] (the bias gradient) and skinny[z][m, j] += sum_k A[k, m] *
@@ -817,7 +818,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
       }
       if (a.tma_store) tma_store_wait_all();   // (only the electing lanes have groups in flight)
     } else {
-    const bool red = MNMAJOR || a.splitk > 1;   // partial tile: combine with red.global.add
+    const bool red = MNMAJOR || a.splitk > 1 || a.shared_c;   // partial tile: combine with red.global.add
     const float* bias = (a.bias && kc_begin == 0) ? a.bias + (long long)z * a.sBias : nullptr;
     const bool vec_ok = (a.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.C) + (size_t)c_off * 4) & 15) == 0;
     float* crow = a.C + c_off + (long long)row * a.ldc;
@@ -838,7 +839,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
         uint8_t* box = smem + (q * (BN / 32) + (c0 >> 5)) * 4096;
         box_put(box, lane, rf);
         if (elect_one()) {
-          if (red || a.accumulate) tma_reduce_add_3d(&mC, box, n0 + c0, m0 + q * 32, z);
+          if (red || a.accumulate) tma_reduce_add_3d(&mC, box, n0 + c0, m0 + q * 32, a.shared_c ? 0 : z);
           else tma_store_3d(&mC, box, n0 + c0, m0 + q * 32, z);
           tma_store_commit();
         }
@@ -1009,7 +1010,10 @@ int launch(const TcGemmP& p, cudaStream_t st) {
   dim3 grid((unsigned)cdiv(p.M, BM), (unsigned)cdiv(p.N, BN), (unsigned)(p.batch * splitk));
   ProfScope prof(st, PROF_TC_GEMM, 2.0 * p.M * p.N * (double)(p.K0 + p.K1) * p.batch);
   CUtensorMap mC = mA0;
-  a.tma_store = make_c_map(&mC, p.C, p.N, p.M, p.ldc, p.batch, p.sC) ? 1 : 0;
+  a.shared_c = (p.batch > 1 && p.sC == 0) ? 1 : 0;
+  NF_CHECK_ARG(!a.shared_c || (p.accumulate && p.epi.kind == TC_EPI_NONE && !p.bias), NF_E_BADARG,
+               "tc_gemm: a batch that shares its output must accumulate (no bias, no fused epilogue)");
+  a.tma_store = make_c_map(&mC, p.C, p.N, p.M, p.ldc, a.shared_c ? 1 : p.batch, p.sC) ? 1 : 0;
   a.b_presplit = pre ? 1 : 0;
   if constexpr (MC) {
     NF_CHECK_ARG(splitk == 1, NF_E_UNSUPPORTED, "tc_gemm: the multicast form does not split the reduction");
