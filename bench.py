@@ -721,6 +721,9 @@ def run_ours(args):
 
     clocks = sampler.stop() if rank == 0 else None
     replays, captures, eager = _lib.graph_stats()
+    p2p_status = _lib.lib.nf_dp_p2p_status() if world > 1 else 0     # 1: peer-memory all-reduce in use, 0: NCCL only
+    if p2p_status < 0:
+        raise SystemExit("bench.py: the peer-memory all-reduce timed out waiting for a rank (results are invalid)")
 
     if rank != 0:
         # wait for rank 0 (CPU baseline, JSON line) and leave the process group together with it
@@ -780,6 +783,9 @@ def run_ours(args):
         "launch_graphs": {"replays": replays, "captures": captures, "eager_calls": eager, "per_leg": leg_graphs,
                           "note": "the library replays its kernel sequence as a cached CUDA graph; gpu_launches "
                                   "counts the library's kernels inside the replayed graphs"},
+        "allreduce": ("none (one GPU)" if world == 1 else
+                      "peer-memory kernel over NVLink for arenas <= %d MB (csrc/dp.cu), NCCL above" % (nf_b200.module._P2P_MAX_BYTES >> 20)
+                      if p2p_status == 1 else "NCCL"),
         "train_ms_median_max": list(head_stats["train"]),
         "clocks": clocks,
         "roofline": head_roof,

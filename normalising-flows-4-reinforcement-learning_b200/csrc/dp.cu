@@ -115,7 +115,7 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 // The CTA barrier orders every thread's peer stores before thread p's release store (system scope, cumulative) of this
 // CTA's flag of `phase` on peer p -- one fence per flag, not one per thread (a membar.sys in all 32 K threads cost
 // ~12 us per phase); thread s then waits for peer s's flag of the same CTA index.  A peer that never arrives (a rank
-// that skipped the call) ends the wait after ~60 s with the error word set instead of hanging the device.
+// that skipped the call) ends the wait after ~5 min with the error word set instead of hanging the device.
 __device__ __forceinline__ void p2p_exchange_flags(const P2pPeers& pp, int rank, int world, int phase, uint32_t epoch,
                                                    int* err) {
   __syncthreads();
@@ -126,7 +126,7 @@ __device__ __forceinline__ void p2p_exchange_flags(const P2pPeers& pp, int rank,
     const uint32_t* f = pp.flags[rank] + (phase * kP2pMaxWorld + t) * kP2pCtas + blockIdx.x;
     const long long t0 = clock64();
     while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) {
-      if (clock64() - t0 > 120000000000LL) { *err = 1; break; }
+      if (clock64() - t0 > 600000000000LL) { *err = 1; break; }
     }
   }
   __syncthreads();
