@@ -932,17 +932,6 @@ static int backward_impl(const NfFlowDesc* desc, const float* params, const void
   if (dy) dy = w.io_dy;
   y = stash + sl.y;
   auto body = [&](cudaStream_t st) -> int {
-  if (dparams) NF_TRY(fill_zero(dparams + (int64_t)block_begin * pl.block_stride, (int64_t)nr_all * pl.block_stride, st));
-  if (dy && first_range) NF_TRY(fill_zero(dy, B * m.R, st));
-  if (dparams) {
-    NF_TRY(fill_zero(w.dWs + (int64_t)block_begin * DD, nr_all * DD, st));
-    if (dlogdet) NF_TRY(sum_vector(dlogdet, B, w.sumdld, st));
-    else NF_TRY(fill_zero(w.sumdld, 4, st));
-  }
-  // block i < n-1 reads the gradient block i+1 left in d0 / d1 (alternating from the top block down), also across
-  // range calls; the top block reads dz (NULL means zero, handled inside the kernels)
-  int pp = (m.n - block_end) & 1;
-  const float* gcur = first_range ? dz : (pp ? w.d0 : w.d1);
   const bool fused = use_row_fused(m);
   const bool v2 = fused && row_v2_supported(m.D, m.C, m.H1);
   const int whatif = option(NF_OPT_WHATIF);
@@ -950,6 +939,23 @@ static int backward_impl(const NfFlowDesc* desc, const float* params, const void
   SideStreams* sar = dp_bucket > 0 ? side_streams(true) : nullptr;     // all-reduce stream
   NF_CHECK_ARG(dp_bucket <= 0 || sar != nullptr, NF_E_UNSUPPORTED, "could not create the all-reduce stream");
   cudaStream_t s1 = ss ? ss->s1 : st, s2 = ss ? ss->s2 : st;
+  if (ss) {   // what only the side streams consume is prepared there, off the chain: dy (written by the dy GEMMs on s2) and
+              // the sum of the log-det cotangents (read by the PLU gradient kernel at the very end)
+    NF_CUDA(cudaEventRecord(ss->evB, st));
+    NF_CUDA(cudaStreamWaitEvent(s1, ss->evB, 0));
+    NF_CUDA(cudaStreamWaitEvent(s2, ss->evB, 0));
+  }
+  if (dparams) NF_TRY(fill_zero(dparams + (int64_t)block_begin * pl.block_stride, (int64_t)nr_all * pl.block_stride, st));
+  if (dy && first_range) NF_TRY(fill_zero(dy, B * m.R, s2));
+  if (dparams) {
+    NF_TRY(fill_zero(w.dWs + (int64_t)block_begin * DD, nr_all * DD, st));
+    if (dlogdet) NF_TRY(sum_vector(dlogdet, B, w.sumdld, s1));
+    else NF_TRY(fill_zero(w.sumdld, 4, s1));
+  }
+  // block i < n-1 reads the gradient block i+1 left in d0 / d1 (alternating from the top block down), also across
+  // range calls; the top block reads dz (NULL means zero, handled inside the kernels)
+  int pp = (m.n - block_end) & 1;
+  const float* gcur = first_range ? dz : (pp ? w.d0 : w.d1);
   struct { float *dxp, *dout, *gA, *gB; } w2[2] = {{w.dxp, w.dout, w.gA, w.gB}, {w.dxp2, w.dout2, w.gA2, w.gB2}};
   // deferred, batched conditioner weight gradients (see defer_fits): both GEMMs must be the TS kernels that take the
   // bias / x_cond reductions along
