@@ -74,6 +74,7 @@ enum NfOpt {
   NF_OPT_TF_AR,          // transformer flow: persistent autoregressive-inverse kernel for B <= 128: -1 auto, 0 never (default -1)
   NF_OPT_PREP_FUSED,     // D <= 32: forward-direction tables of nf_flow_prepare in one kernel (default 1)
   NF_OPT_DEFER_DY,       // with deferred weight gradients: the dy GEMMs of all blocks as one batched launch after the loop (default 1)
+  NF_OPT_DEFER_COLS,     // with deferred weight gradients: the remaining column reductions of all blocks as one launch each after the loop (default 1)
   NF_OPT_COUNT
 };
 int option(int id);

@@ -9,6 +9,7 @@
 #include "dp.cuh"
 #include "elementwise.cuh"
 #include "flow_stack.cuh"
+#include <vector>
 #include "graphs.cuh"
 #include "linear.cuh"
 #include "rowfused.cuh"
@@ -43,6 +44,7 @@ const OptDef kOpts[NF_OPT_COUNT] = {
     {"ride", "NF_B200_RIDE", 1},         {"defer_wgrad", "NF_B200_DEFER_WGRAD", -1},
     {"mcast", "NF_B200_MCAST", -1},      {"bn64", "NF_B200_BN64", 1},
     {"tf_ar", "NF_B200_TF_AR", -1},      {"prep_fused", "NF_B200_PREP_FUSED", 1}, {"defer_dy", "NF_B200_DEFER_DY", 1},
+    {"defer_cols", "NF_B200_DEFER_COLS", 1},
 };
 int g_opt[NF_OPT_COUNT];
 bool g_opt_init = false;
@@ -200,6 +202,7 @@ struct BwdWs { float *d0, *d1, *dxp, *dout, *gA, *gB, *dWs, *T1, *dLh, *dUh, *su
                float *dxp2, *dout2, *gA2, *gB2;   // second set: blocks alternate so side streams can lag one block
                float *io_dz, *io_dld, *io_dy, *io_dx;   // staging of the caller's cotangents and of dx / dy (see FwdWs)
                float *w3t[2];                           // generic path: W3f^T (2, C, dtp) of the current block (alternating)
+               float *doutAll, *dxpAll;                 // dout / dxp of every block (deferred column reductions)
                float *gAall, *gBall;                    // du2 / du1 of EVERY block (n, 2, B, Hm) when the weight gradients are deferred
                int64_t total; };
 // The conditioner weight gradients of a block only consume du2 / du1.  While the flow is small enough to keep those for
@@ -237,10 +240,12 @@ static BwdWs carve_bwd(const Dims& m, int64_t B, void* ws) {
   w.io_dx = c.take(B * m.D);
   w.w3t[0] = c.take(2 * (int64_t)m.C * pad4(m.dt));
   w.w3t[1] = c.take(2 * (int64_t)m.C * pad4(m.dt));
-  w.gAall = w.gBall = nullptr;
+  w.gAall = w.gBall = w.doutAll = w.dxpAll = nullptr;
   if (defer_fits(m, B)) {     // (sized by shape alone, so the workspace size does not depend on run-time options)
     w.gAall = c.take((int64_t)m.n * 2 * B * Hm);
     w.gBall = c.take((int64_t)m.n * 2 * B * Hm);
+    w.doutAll = c.take((int64_t)m.n * 2 * B * m.dt);
+    w.dxpAll = c.take((int64_t)m.n * B * m.D);
   }
   w.total = c.off;
   return w;
@@ -983,6 +988,10 @@ static int backward_impl(const NfFlowDesc* desc, const float* params, const void
     t.C = dy; t.ldc = m.R; t.M = (int)B; t.N = m.R; t.accumulate = 1;
     defer_dy = tc_gemm_supported(t);
   }
+  // ... and what is left of the column reductions (G3 = dout^T x_hat2 with colsum(dout), dW = x_in^T dxp): with dout / dxp
+  // of every block kept they are one launch each after the loop (C2a: 12 launches of 5-11 us beside the chain -> 2)
+  const bool defer_cols = defer && ss && w.doutAll && option(NF_OPT_DEFER_COLS) != 0;
+  std::vector<char> cols_later((size_t)m.n, 0);
   bool any_ar = false;
   for (int sub_end = block_end; sub_end > block_begin;) {
   const int sub_begin = dp_bucket > 0 ? std::max(block_begin, sub_end - dp_bucket) : block_begin;
@@ -990,7 +999,8 @@ static int backward_impl(const NfFlowDesc* desc, const float* params, const void
   bool used1[2] = {false, false}, used2[2] = {false, false};
   for (int i = sub_end - 1; i >= sub_begin; --i) {
     const int par = ss ? ((m.n - 1 - i) & 1) : 0;
-    const auto& wb = w2[par];   // this block's intermediate buffers
+    auto wb = w2[par];          // this block's intermediate buffers
+    if (defer_cols) { wb.dout = w.doutAll + (int64_t)i * 2 * B * m.dt; wb.dxp = w.dxpAll + (int64_t)i * BD; }
     float* const gA = defer ? w.gAall + (int64_t)i * 2 * B * Hm : wb.gA;   // du2 (deferred weight gradients: kept per block)
     float* const gB = defer ? w.gBall + (int64_t)i * 2 * B * Hm : wb.gB;   // du1
     if (ss) {   // the side work of block i+2 read this buffer set
@@ -1206,6 +1216,8 @@ static int backward_impl(const NfFlowDesc* desc, const float* params, const void
         jobs[2].out = w.dWs + (int64_t)i * DD; jobs[2].so_i = m.D; jobs[2].so_c = 1;
         jobs[2].batch = 1;
         if (whatif & 1) {
+        } else if (defer_cols && fold_e && fold_h) {
+          cols_later[i] = 1;
         } else if (ss) {
           NF_CUDA(cudaEventRecord(ss->evC, st));
           NF_TRY(col_reduce(&jobs[0], 1, B, s1));
@@ -1252,6 +1264,35 @@ static int backward_impl(const NfFlowDesc* desc, const float* params, const void
     }
   }
   cudaStream_t tail_st = st;
+  if (defer_cols) {   // on s1, beside the batched weight-gradient GEMMs; the un-folding kernel (s1 as well) comes after them
+    NF_CUDA(cudaEventRecord(ss->evC, st));
+    NF_CUDA(cudaStreamWaitEvent(s1, ss->evC, 0));
+    ColJob jobs[kColMaxJobs];
+    int nj = 0, first = -1, last = -1;
+    for (int i = sub_begin; i < sub_end; ++i) {
+      if (!cols_later[i]) continue;
+      if (first < 0) first = i;
+      last = i;
+      float* dn = dparams + (int64_t)i * pl.block_stride;
+      const float* sb = stash + sl.blocks + (int64_t)i * sl.block_stride;
+      ColJob& j = jobs[nj++];
+      j = ColJob();
+      j.A = sb + sl.xh2; j.lda = m.C; j.sA = sl.net_stride; j.N = m.C;
+      j.coef = w.doutAll + (int64_t)i * 2 * B * m.dt; j.ldcf = m.dt; j.sCf = B * m.dt; j.m = m.dt;
+      j.out = dn + pl.slot_off[NF_P_W3]; j.so_i = m.C; j.so_c = 1; j.sOut = pl.net_stride;
+      j.out3 = dn + pl.slot_off[NF_P_B3]; j.sOut3 = pl.net_stride;
+      j.batch = 2;
+      if (nj == kColMaxJobs) { NF_TRY(col_reduce(jobs, nj, B, s1)); nj = 0; }
+    }
+    if (nj) NF_TRY(col_reduce(jobs, nj, B, s1));
+    if (first >= 0) {   // (every block of the range takes the same path: same shapes, same options)
+      NF_CHECK_ARG(last - first + 1 == nr, NF_E_UNSUPPORTED, "deferred column reductions: mixed blocks");
+      NF_TRY(xtg_small(stash + sl.xs + (int64_t)first * BD, w.dxpAll + (int64_t)first * BD, w.dWs + (int64_t)first * DD, B, m.D,
+                       s1, nr, BD, BD, DD));
+    }
+    NF_CUDA(cudaEventRecord(ss->done1[0], s1));
+    used1[0] = true;
+  }
   if (defer_dy && !(whatif & 4)) {
     NF_CUDA(cudaEventRecord(ss->evA, st));
     NF_CUDA(cudaStreamWaitEvent(s2, ss->evA, 0));

@@ -422,8 +422,10 @@ __global__ void __launch_bounds__(256) k_col_reduce(const __grid_constant__ ColA
 // As a col_reduce job this took 12.9 us on C2a (32 CTAs, 2 useful lanes per warp); this kernel is bound by its launch.
 constexpr int kXtgRows = 64;
 __global__ void __launch_bounds__(256) k_xtg_small(const float* __restrict__ X, const float* __restrict__ G,
-                                                   float* __restrict__ dW, long long B, int D, int rows_per_cta) {
+                                                   float* __restrict__ dW, long long B, int D, int rows_per_cta,
+                                                   long long sX, long long sG, long long sW) {
   NF_PDL_ENTRY();
+  X += blockIdx.y * sX; G += blockIdx.y * sG; dW += blockIdx.y * sW;   // blockIdx.y: flow block (batched launch)
   __shared__ float sx[kXtgRows * 32], sg[kXtgRows * 32];
   const int DD = D * D;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -453,13 +455,14 @@ __global__ void __launch_bounds__(256) k_xtg_small(const float* __restrict__ X, 
 
 }  // namespace
 
-int xtg_small(const float* X, const float* G, float* dW, long long B, int D, cudaStream_t st) {
-  if (B <= 0) return 0;
+int xtg_small(const float* X, const float* G, float* dW, long long B, int D, cudaStream_t st, int batch, long long sX,
+              long long sG, long long sW) {
+  if (B <= 0 || batch <= 0) return 0;
   NF_CHECK_ARG(D >= 1 && D <= 32, NF_E_UNSUPPORTED, "xtg_small: D=%d", D);
   long long rpc = cdiv(cdiv(B, 296), kXtgRows) * kXtgRows;
   if (rpc < kXtgRows) rpc = kXtgRows;
-  ProfScope prof(st, PROF_COL_REDUCE, 8.0 * B * D);
-  NF_LAUNCH((k_xtg_small), (unsigned)cdiv(B, rpc), 256, 0, st, X, G, dW, B, D, (int)rpc);
+  ProfScope prof(st, PROF_COL_REDUCE, 8.0 * B * D * batch);
+  NF_LAUNCH((k_xtg_small), dim3((unsigned)cdiv(B, rpc), (unsigned)batch), 256, 0, st, X, G, dW, B, D, (int)rpc, sX, sG, sW);
   NF_LAUNCHED();
   return 0;
 }

@@ -62,9 +62,11 @@ struct ColJob {
   float* out3 = nullptr; long long sOut3 = 0;
   int N = 0, batch = 1;
 };
-constexpr int kColMaxJobs = 4;
+constexpr int kColMaxJobs = 8;
 int col_reduce(const ColJob* jobs, int njobs, long long B, cudaStream_t st);
 // dW (D, D) += X (B, D)^T G (B, D), dense rows, D <= 32
-int xtg_small(const float* X, const float* G, float* dW, long long B, int D, cudaStream_t st);
+// (batch > 1: one launch for several flow blocks, operands `s?` floats apart)
+int xtg_small(const float* X, const float* G, float* dW, long long B, int D, cudaStream_t st, int batch = 1, long long sX = 0,
+              long long sG = 0, long long sW = 0);
 
 }  // namespace nf
