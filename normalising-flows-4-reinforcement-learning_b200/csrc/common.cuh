@@ -75,6 +75,7 @@ enum NfOpt {
   NF_OPT_PREP_FUSED,     // D <= 32: forward-direction tables of nf_flow_prepare in one kernel (default 1)
   NF_OPT_DEFER_DY,       // with deferred weight gradients: the dy GEMMs of all blocks as one batched launch after the loop (default 1)
   NF_OPT_DEFER_COLS,     // with deferred weight gradients: the remaining column reductions of all blocks as one launch each after the loop (default 1)
+  NF_OPT_DEFER_SKINNY,   // with deferred column reductions: the x_cond columns of dW1 as column-reduction jobs instead of riding on the dW1 GEMM (default 0: measured 7 us slower on C2a)
   NF_OPT_COUNT
 };
 int option(int id);

@@ -44,7 +44,7 @@ const OptDef kOpts[NF_OPT_COUNT] = {
     {"ride", "NF_B200_RIDE", 1},         {"defer_wgrad", "NF_B200_DEFER_WGRAD", -1},
     {"mcast", "NF_B200_MCAST", -1},      {"bn64", "NF_B200_BN64", 1},
     {"tf_ar", "NF_B200_TF_AR", -1},      {"prep_fused", "NF_B200_PREP_FUSED", 1}, {"defer_dy", "NF_B200_DEFER_DY", 1},
-    {"defer_cols", "NF_B200_DEFER_COLS", 1},
+    {"defer_cols", "NF_B200_DEFER_COLS", 1}, {"defer_skinny", "NF_B200_DEFER_SKINNY", 0},
 };
 int g_opt[NF_OPT_COUNT];
 bool g_opt_init = false;
@@ -1264,11 +1264,15 @@ static int backward_impl(const NfFlowDesc* desc, const float* params, const void
     }
   }
   cudaStream_t tail_st = st;
+  bool skinny_cols = false;
   if (defer_cols) {   // on s1, beside the batched weight-gradient GEMMs; the un-folding kernel (s1 as well) comes after them
     NF_CUDA(cudaEventRecord(ss->evC, st));
     NF_CUDA(cudaStreamWaitEvent(s1, ss->evC, 0));
     ColJob jobs[kColMaxJobs];
     int nj = 0, first = -1, last = -1;
+    bool all_later = true;
+    for (int i = sub_begin; i < sub_end; ++i) all_later = all_later && cols_later[i];
+    skinny_cols = all_later && option(NF_OPT_DEFER_SKINNY) != 0 && !(whatif & 2);
     for (int i = sub_begin; i < sub_end; ++i) {
       if (!cols_later[i]) continue;
       if (first < 0) first = i;
@@ -1283,6 +1287,15 @@ static int backward_impl(const NfFlowDesc* desc, const float* params, const void
       j.out3 = dn + pl.slot_off[NF_P_B3]; j.sOut3 = pl.net_stride;
       j.batch = 2;
       if (nj == kColMaxJobs) { NF_TRY(col_reduce(jobs, nj, B, s1)); nj = 0; }
+      if (skinny_cols) {   // G1[:, :dc] = du1^T x_cond here instead of on the dW1 GEMM's splitter threads
+        ColJob& k = jobs[nj++];
+        k = ColJob();
+        k.A = w.gBall + (int64_t)i * 2 * B * Hm; k.lda = m.H1; k.sA = B * Hm; k.N = m.H1;
+        k.coef = stash + sl.xs + (int64_t)(i + 1) * BD; k.ldcf = m.D; k.sCf = 0; k.m = m.dc;
+        k.out = dn + pl.slot_off[NF_P_W1]; k.so_i = 1; k.so_c = m.K1; k.sOut = pl.net_stride;
+        k.batch = 2;
+        if (nj == kColMaxJobs) { NF_TRY(col_reduce(jobs, nj, B, s1)); nj = 0; }
+      }
     }
     if (nj) NF_TRY(col_reduce(jobs, nj, B, s1));
     if (first >= 0) {   // (every block of the range takes the same path: same shapes, same options)
@@ -1325,8 +1338,10 @@ static int backward_impl(const NfFlowDesc* desc, const float* params, const void
     h.B = y; h.ldb = m.R; h.sB = 0;
     h.C = dpr + pl.slot_off[NF_P_W1] + m.dc; h.ldc = m.K1; h.sC = pl.net_stride; h.sC2 = pl.block_stride;
     h.M = m.H1; h.N = m.R; h.K = B; h.batch = 2 * nr; h.inner = 2;
-    h.xc = stash + sl.xs + (int64_t)(sub_begin + 1) * BD; h.ldxc = m.D; h.nxc = m.dc; h.sXc2 = BD;
-    h.skinny = dpr + pl.slot_off[NF_P_W1]; h.ldsk = m.K1; h.sSk = pl.net_stride; h.sSk2 = pl.block_stride;
+    if (!skinny_cols) {
+      h.xc = stash + sl.xs + (int64_t)(sub_begin + 1) * BD; h.ldxc = m.D; h.nxc = m.dc; h.sXc2 = BD;
+      h.skinny = dpr + pl.slot_off[NF_P_W1]; h.ldsk = m.K1; h.sSk = pl.net_stride; h.sSk2 = pl.block_stride;
+    }
     if (ln1_fused_any) { h.colsum = dpr + pl.slot_off[NF_P_B1]; h.sColsum = pl.net_stride; h.sColsum2 = pl.block_stride; }
     NF_TRY(wgrad_tn(m.prec, h, st));
   }

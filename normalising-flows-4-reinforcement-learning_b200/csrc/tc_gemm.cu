@@ -388,8 +388,22 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
     float csum = 0.f, sk[kMaxXc];
 #pragma unroll
     for (int j = 0; j < kMaxXc; ++j) sk[j] = 0.f;
+    // riding skinny reduction: lane l fetches float4 (l & 1) of row (l >> 1) of the stage's xc tile one stage ahead
+    const bool xc_pre = ride && a.skinny != nullptr && a.xc_vec && BK == 16;
+    float4 xc_next = make_float4(0.f, 0.f, 0.f, 0.f), xc_cur = xc_next, av_r[4];
+    auto xc_fetch = [&](int it_) -> float4 {
+      const long long kr = min((long long)(kc_begin + it_) * BK + (lane >> 1), (long long)a.K0 - 1);
+      const int j4 = lane & 1;
+      if (4 * j4 >= a.nxc) return make_float4(0.f, 0.f, 0.f, 0.f);
+      return __ldg(reinterpret_cast<const float4*>(a.xc + (long long)z_o * a.sXc2 + kr * a.ldxc) + j4);
+    };
+    if (xc_pre && grp < nk) xc_next = xc_fetch(grp);
     for (int it = grp; it < nk && !nosplit; it += NSG) {
       const int s = it % STAGES, use = it / STAGES;
+      if (xc_pre) {
+        xc_cur = xc_next;
+        if (it + NSG < nk) xc_next = xc_fetch(it + NSG);   // in flight across the wait below
+      }
       mbar_wait(&full[s], use & 1);
       if (threadIdx.x == 64 && it == 0) NF_TS(2);   // first operand tile landed
       float4* raw = reinterpret_cast<float4*>(smem + s * S::STAGE);
@@ -412,7 +426,11 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
             if (a.skinny) {
               const long long k0 = (long long)(kc_begin + it) * BK;
               const float* xbase = a.xc + (long long)z_o * a.sXc2;
-              if (a.xc_vec) {
+              if (xc_pre) {
+                // (done after this stage's operands have been handed to the MMA warp, see the end of the iteration)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) av_r[c] = av[c];
+              } else if (a.xc_vec) {
                 // rows of xc as 128-bit loads (same address in every lane: one broadcast transaction each), four rows
                 // in flight at a time -- as scalar loads this rode at 3 100 cycles per stage (ncu, C2a batched dW1)
 #pragma unroll
@@ -527,6 +545,44 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&split[s]);
+      if constexpr (TS && MNMAJOR) {
+        if (xc_pre) {   // riding skinny reduction, in the shadow of this stage's MMAs (the operands are already handed over)
+        // The stage's xc tile (BK rows x <= 8 columns = 32 float4) was fetched one float4 per lane BEFORE the
+        // wait for the operand tile (xc_cur); the warp passes it round through its 512 B of shared memory and
+        // every lane reads the 16 rows back as broadcasts.  (Loading the rows after the wait -- 16 dependent 128-bit
+        // loads in four rounds -- made the main loop of C2a's batched dW1 GEMM 64.6 K cycles per CTA; this form: 46.9 K;
+        // without the riding reduction: 27 K.  What-if runs: the prefetch load alone costs 6 K, the FMAs 9 K, the
+        // hand-over through shared memory 9 K -- the two splitter groups are a latency chain, every instruction added
+        // to an iteration delays the group's next stage.  A dedicated rider warp is the next step, not taken.)
+        float4* xs = reinterpret_cast<float4*>(smem + S::BARS + 512) + (warp - 2) * 32;
+        xs[lane] = xc_cur;
+        __syncwarp();
+        // (two batches of eight broadcast loads, all issued before the FMAs that use them)
+        const float ar[16] = {av_r[0].x, av_r[0].y, av_r[0].z, av_r[0].w, av_r[1].x, av_r[1].y, av_r[1].z, av_r[1].w,
+                              av_r[2].x, av_r[2].y, av_r[2].z, av_r[2].w, av_r[3].x, av_r[3].y, av_r[3].z, av_r[3].w};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float4 v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = xs[2 * (8 * h + e)];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            sk[0] = fmaf(ar[8 * h + e], v[e].x, sk[0]); sk[1] = fmaf(ar[8 * h + e], v[e].y, sk[1]);
+            sk[2] = fmaf(ar[8 * h + e], v[e].z, sk[2]); sk[3] = fmaf(ar[8 * h + e], v[e].w, sk[3]);
+          }
+          if (a.nxc > 4) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = xs[2 * (8 * h + e) + 1];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              sk[4] = fmaf(ar[8 * h + e], v[e].x, sk[4]); sk[5] = fmaf(ar[8 * h + e], v[e].y, sk[5]);
+              sk[6] = fmaf(ar[8 * h + e], v[e].z, sk[6]); sk[7] = fmaf(ar[8 * h + e], v[e].w, sk[7]);
+            }
+          }
+        }
+        __syncwarp();
+        }
+      }
     }
     if (ride) {   // one atomic per output element, CTA and splitter group
       const int mrow = m0 + (warp & 3) * 32 + lane;
@@ -1131,12 +1187,13 @@ template <int BN, int STAGES, int BK, bool TS = false, bool NS = false, int NSG_
 int launch_tn(const TcGemmTnP& p, cudaStream_t st) {
   using S = Smem<BN, STAGES, BK, TS, NS>;
   constexpr int NSG = NSG_ ? NSG_ : (TS ? 2 : 1);
+  constexpr int kXcBytes = TS ? 4 * NSG * 512 : 0;   // per splitter warp: the stage's xc tile (riding skinny reduction), after the barrier block
   int r;
   {
     static PerDeviceOnce once;
     if (once.first()) {
       NF_CUDA(cudaFuncSetAttribute((k_tc_gemm<BN, STAGES, true, BK, EPI_NONE, TS, NSG, NS>),
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL + kXcBytes));
     }
   }
   CUtensorMap mA, mB;
@@ -1195,7 +1252,7 @@ int launch_tn(const TcGemmTnP& p, cudaStream_t st) {
   CUtensorMap mC = mA;
   // (the bulk-tensor-store epilogue addresses C through a 3-d map with one batch stride: two-level batches store directly)
   a.tma_store = (p.inner <= 0 && make_c_map(&mC, p.C, p.N, p.M, p.ldc, p.batch, p.sC)) ? 1 : 0;
-  NF_LAUNCH((k_tc_gemm<BN, STAGES, true, BK, EPI_NONE, TS, NSG, NS>), grid, 64 + 128 * NSG, S::TOTAL, st, mA, mA, mB, mB, mB, mB, mC, a);
+  NF_LAUNCH((k_tc_gemm<BN, STAGES, true, BK, EPI_NONE, TS, NSG, NS>), grid, 64 + 128 * NSG, S::TOTAL + kXcBytes, st, mA, mA, mB, mB, mB, mB, mC, a);
   NF_LAUNCHED();
   return 0;
 }

@@ -420,7 +420,7 @@ def test_launch_graph_replay_is_bit_identical(precision):
 OPTION_SETTINGS = [("pdl", 0), ("streams", 0), ("tma_store", 0), ("fused_ln", 0), ("fused_ln", 1), ("fused_tail", 1),
                    ("nacc", 1), ("bn256", 2), ("bn256", 1), ("ts", 0), ("presplit", 0),
                    ("stack", 0), ("stack", 1), ("stack_nsg", 1), ("ride", 0), ("defer_wgrad", 0), ("defer_wgrad", 1), ("mcast", 0), ("mcast", 1),
-                   ("prep_fused", 0), ("defer_dy", 0), ("defer_cols", 0)]
+                   ("prep_fused", 0), ("defer_dy", 0), ("defer_cols", 0), ("defer_skinny", 1)]
 
 
 @pytest.mark.parametrize("name,value", OPTION_SETTINGS, ids=[f"{n}={v}" for n, v in OPTION_SETTINGS])
