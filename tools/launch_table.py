@@ -1,10 +1,14 @@
 """Aggregate an `ncu --metrics gpu__time_duration.sum --csv` launch list: per kernel (name, grid) count / mean / total
-for the LAST training step in the file (from the last launch of the marker kernel on; default k_plu_mask)."""
+for the LAST training step in the file (from the last launch of the marker kernel on; default: k_prepare_fwd, the one-kernel table build, else k_plu_mask)."""
 import csv, collections, sys
 path = sys.argv[1]
 rows = list(csv.DictReader(l for l in open(path) if l.startswith('"')))
-marker = sys.argv[2] if len(sys.argv) > 2 else 'k_plu_mask'   # first kernel of a step
-idx = [i for i, r in enumerate(rows) if marker in r['Kernel Name']]
+marker = sys.argv[2] if len(sys.argv) > 2 else None   # first kernel of a step
+idx = []
+for mk in ([marker] if marker else ['k_prepare_fwd', 'k_plu_mask']):
+    idx = [i for i, r in enumerate(rows) if mk in r['Kernel Name']]
+    if idx:
+        break
 last = rows[idx[-1]:] if idx else rows
 agg = collections.OrderedDict()
 for r in last:
