@@ -25,6 +25,7 @@ Prints ONE JSON line on rank 0.
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import math
 import os
@@ -383,11 +384,18 @@ class Runner:
             one()
         self.barrier()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        for a, b in ev:
-            self.flush.zero_()                          # evict L2 between timed iterations (outside the events)
-            a.record()
-            one()
-            b.record()
+        # the step is short enough (0.6 ms) that a cyclic-GC pass of the interpreter in the middle of the host's issue loop
+        # shows up as a device-idle gap inside the events (seen as single 0.9 ms steps): collect before, not during
+        gc.collect()
+        gc.disable()
+        try:
+            for a, b in ev:
+                self.flush.zero_()                          # evict L2 between timed iterations (outside the events)
+                a.record()
+                one()
+                b.record()
+        finally:
+            gc.enable()
         self.barrier()
         per = [a.elapsed_time(b) for a, b in ev]
         t = torch.tensor([sum(per)], dtype=torch.float64, device=self.dev)

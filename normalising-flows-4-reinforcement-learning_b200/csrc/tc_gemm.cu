@@ -389,13 +389,21 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
 #pragma unroll
     for (int j = 0; j < kMaxXc; ++j) sk[j] = 0.f;
     // riding skinny reduction: lane l fetches float4 (l & 1) of row (l >> 1) of the stage's xc tile one stage ahead
-    const bool xc_pre = ride && a.skinny != nullptr && a.xc_vec && BK == 16;
+    // (any xc with at most 8 columns: 128-bit loads when its rows allow them, else up to four scalar loads per lane)
+    const bool xc_pre = ride && a.skinny != nullptr && a.nxc <= 8 && BK == 16;
     float4 xc_next = make_float4(0.f, 0.f, 0.f, 0.f), xc_cur = xc_next, av_r[4];
     auto xc_fetch = [&](int it_) -> float4 {
       const long long kr = min((long long)(kc_begin + it_) * BK + (lane >> 1), (long long)a.K0 - 1);
-      const int j4 = lane & 1;
-      if (4 * j4 >= a.nxc) return make_float4(0.f, 0.f, 0.f, 0.f);
-      return __ldg(reinterpret_cast<const float4*>(a.xc + (long long)z_o * a.sXc2 + kr * a.ldxc) + j4);
+      const int j0 = 4 * (lane & 1);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (j0 >= a.nxc) return v;
+      const float* xr = a.xc + (long long)z_o * a.sXc2 + kr * a.ldxc + j0;
+      if (a.xc_vec) return __ldg(reinterpret_cast<const float4*>(xr));
+      v.x = __ldg(xr);
+      if (j0 + 1 < a.nxc) v.y = __ldg(xr + 1);
+      if (j0 + 2 < a.nxc) v.z = __ldg(xr + 2);
+      if (j0 + 3 < a.nxc) v.w = __ldg(xr + 3);
+      return v;
     };
     if (xc_pre && grp < nk) xc_next = xc_fetch(grp);
     for (int it = grp; it < nk && !nosplit; it += NSG) {
