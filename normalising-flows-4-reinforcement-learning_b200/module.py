@@ -30,6 +30,8 @@ from ._lib import lib
 
 
 _get_grad = operator.attrgetter("grad")
+_get_requires_grad = operator.attrgetter("requires_grad")
+_get_version = operator.attrgetter("_version")
 
 
 class _NoSwitch:
@@ -501,10 +503,7 @@ class RealNVP(nn.Module):
         return self._xver + (tp[0]._version + tp[-1]._version if tp else 0)
 
     def _params_version(self):
-        v = self._xver
-        for p in self._tparams:
-            v += p._version
-        return v
+        return self._xver + sum(map(_get_version, self._tparams))     # (C-level walk: ~150 parameters per forward)
 
     def _grad_carriers(self):
         """The trainable parameters handed to the autograd function: all of them, or -- ``fast_param_grads`` -- only the
@@ -695,13 +694,14 @@ class RealNVP(nn.Module):
             ours = sum(map(operator.is_, grads, views)) == len(grads)
             if not ours:      # same storage through another Python object?
                 ours = all(g.data_ptr() == v.data_ptr() and g.shape == v.shape for g, v in zip(grads, views))
-        if any(not p.requires_grad for p in tp) and not fresh:
+        all_trainable = sum(map(_get_requires_grad, tp)) == len(tp)
+        if not all_trainable and not fresh:
             ours = False      # parameters frozen after construction: take the per-parameter path
         target = self._gflat if fresh else None
         dx, dy, dflat = self._run_backward(stash, packed, y, B, dz, dld, need_x, need_y, True, out=target, inverse=inverse)
         if fresh:
             for p, v in zip(tp, views):
-                if p.requires_grad:
+                if all_trainable or p.requires_grad:
                     p.grad = v
         elif ours:
             self._gflat.add_(dflat)
