@@ -25,7 +25,6 @@ Prints ONE JSON line on rank 0.
 from __future__ import annotations
 
 import argparse
-import gc
 import json
 import math
 import os
@@ -86,7 +85,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", os.environ.get("NF_B200_SMI_MS", "100")],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -382,20 +381,15 @@ class Runner:
         for _ in range(warmup):                         # same code path as the timed steps
             self.flush.zero_()
             one()
-        self.barrier()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        # the step is short enough (0.6 ms) that a cyclic-GC pass of the interpreter in the middle of the host's issue loop
-        # shows up as a device-idle gap inside the events (seen as single 0.9 ms steps): collect before, not during
-        gc.collect()
-        gc.disable()
-        try:
-            for a, b in ev:
-                self.flush.zero_()                          # evict L2 between timed iterations (outside the events)
-                a.record()
-                one()
-                b.record()
-        finally:
-            gc.enable()
+        self.barrier()
+        # (no work between the barrier and the first timed step: a pause there -- a gc.collect() was tried -- lets the
+        # idle GPU fall back and the first step then takes twice as long)
+        for a, b in ev:
+            self.flush.zero_()                          # evict L2 between timed iterations (outside the events)
+            a.record()
+            one()
+            b.record()
         self.barrier()
         per = [a.elapsed_time(b) for a, b in ev]
         t = torch.tensor([sum(per)], dtype=torch.float64, device=self.dev)
