@@ -211,6 +211,7 @@ struct P2pState {
   int rank = 0, world = 0;
   bool connected = false;
   int64_t max_floats = 0;          // arenas up to this size take the peer-memory path
+  int64_t min_floats = 0;          // ... and at least this size when fewer than 8 ranks take part (see nf_dp_p2p_alloc)
 };
 P2pState g_p2p[64];
 
@@ -240,7 +241,7 @@ int dp_allreduce(float* buf, int64_t n, bool average, cudaStream_t st) {
   NF_CHECK_ARG(c && c->comm, NF_E_BADARG, "nf_dp_init has not been called on this device");
   if (n <= 0) return 0;
   P2pState* s = p2p_current();
-  if (s && s->connected && s->world == c->world && n <= s->max_floats) {
+  if (s && s->connected && s->world == c->world && n <= s->max_floats && (s->world >= 8 || n >= s->min_floats)) {
     const int64_t slice = (cdiv(n, (int64_t)s->world) + 3) & ~int64_t(3);
     uint32_t* epochs = reinterpret_cast<uint32_t*>(s->base) + 2 * kP2pMaxWorld * kP2pCtas;
     int* err = reinterpret_cast<int*>(epochs + kP2pCtas);
@@ -332,6 +333,11 @@ int nf_dp_p2p_alloc(int64_t max_floats, void* handle64) {
   NF_CUDA(cudaIpcGetMemHandle(&h, s->base));
   memcpy(handle64, &h, sizeof(h));
   s->max_floats = max_floats;
+  // Measured against NCCL 2.28 on the same buffers (profiles/r2_p2p_allreduce.txt): at 8 ranks the kernel wins at every size
+  // (0.25 MB: 27 vs 30 us, 4 MB: 34 vs 44 us); at 2 and 4 ranks NCCL's low-latency protocol is ahead up to 1 MB (2 ranks,
+  // 1 MB: 16 vs 20 us) and behind from 4 MB on (24 vs 37 us).  NF_B200_DP_P2P_MIN_BYTES moves the switch-over.
+  const char* e = getenv("NF_B200_DP_P2P_MIN_BYTES");
+  s->min_floats = (e ? atoll(e) : (2ll << 20)) / 4;
   return 0;
 }
 

@@ -5,6 +5,7 @@ and device-timed latency of both paths per arena size.
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/dp_p2p_check.py
 """
 import ctypes, os, sys
+os.environ.setdefault("NF_B200_DP_P2P_MIN_BYTES", "0")      # exercise the kernel at every size, whatever the world size
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import torch.distributed as dist
