@@ -19,7 +19,8 @@ pytestmark = [pytest.mark.gpu,
 def _torchrun(script, port):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
            "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tools", script)]
-    return subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=300)
+    env = dict(os.environ, NF_B200_DP_P2P_MIN_BYTES="0")     # small arenas through the peer-memory kernel too
+    return subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=300, env=env)
 
 
 def test_peer_memory_allreduce_matches_nccl():
