@@ -50,7 +50,8 @@ struct KArgs {
   // xc[k, j], j < nxc <= 16 (the x_cond columns of dW1) -- instead of a separate column-reduction pass over A
   float* colsum; long long sColsum;
   const float* xc; long long ldxc; int nxc;
-  int xc_vec;                            // xc rows may be read as float4 chunks (aligned, 4 ceil(nxc / 4) <= row length)
+  int xc_vec;                            // xc rows may be read as float4 chunks (aligned, 4 ceil(nxc / 4) <= row length), nxc <= 8
+  int xc_al;                             // the same without the column limit (prefetched form, up to 16 columns)
   float* skinny; long long ldsk, sSk;
   // MN-major form, two-level batch (zin > 0): z = zo * zin + zi; A / B keep one uniform stride (TMA coordinate z), the
   // outputs live at zo * s?2 + zi * s? (the per-block / per-net slots of the gradient arena) and xc at zo * sXc2
@@ -390,27 +391,34 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
     for (int j = 0; j < kMaxXc; ++j) sk[j] = 0.f;
     // riding skinny reduction: lane l fetches float4 (l & 1) of row (l >> 1) of the stage's xc tile one stage ahead
     // (any xc with at most 8 columns: 128-bit loads when its rows allow them, else up to four scalar loads per lane)
-    const bool xc_pre = ride && a.skinny != nullptr && a.nxc <= 8 && BK == 16;
-    float4 xc_next = make_float4(0.f, 0.f, 0.f, 0.f), xc_cur = xc_next, av_r[4];
-    auto xc_fetch = [&](int it_) -> float4 {
+    const bool xc_pre = ride && a.skinny != nullptr && a.nxc <= 16 && BK == 16;
+    const bool xc_wide = xc_pre && a.nxc > 8;     // columns 8..15: a second float4 per lane (C5: 16 x_cond columns)
+    float4 xc_next = make_float4(0.f, 0.f, 0.f, 0.f), xc_cur = xc_next, xc_next2 = xc_next, xc_cur2 = xc_next, av_r[4];
+    auto xc_fetch = [&](int it_, int half) -> float4 {
       const long long kr = min((long long)(kc_begin + it_) * BK + (lane >> 1), (long long)a.K0 - 1);
-      const int j0 = 4 * (lane & 1);
+      const int j0 = 8 * half + 4 * (lane & 1);
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (j0 >= a.nxc) return v;
       const float* xr = a.xc + (long long)z_o * a.sXc2 + kr * a.ldxc + j0;
-      if (a.xc_vec) return __ldg(reinterpret_cast<const float4*>(xr));
+      if (a.xc_al) return __ldg(reinterpret_cast<const float4*>(xr));
       v.x = __ldg(xr);
       if (j0 + 1 < a.nxc) v.y = __ldg(xr + 1);
       if (j0 + 2 < a.nxc) v.z = __ldg(xr + 2);
       if (j0 + 3 < a.nxc) v.w = __ldg(xr + 3);
       return v;
     };
-    if (xc_pre && grp < nk) xc_next = xc_fetch(grp);
+    if (xc_pre && grp < nk) {
+      xc_next = xc_fetch(grp, 0);
+      if (xc_wide) xc_next2 = xc_fetch(grp, 1);
+    }
     for (int it = grp; it < nk && !nosplit; it += NSG) {
       const int s = it % STAGES, use = it / STAGES;
       if (xc_pre) {
-        xc_cur = xc_next;
-        if (it + NSG < nk) xc_next = xc_fetch(it + NSG);   // in flight across the wait below
+        xc_cur = xc_next; xc_cur2 = xc_next2;
+        if (it + NSG < nk) {                               // in flight across the wait below
+          xc_next = xc_fetch(it + NSG, 0);
+          if (xc_wide) xc_next2 = xc_fetch(it + NSG, 1);
+        }
       }
       mbar_wait(&full[s], use & 1);
       if (threadIdx.x == 64 && it == 0) NF_TS(2);   // first operand tile landed
@@ -556,14 +564,16 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
       if constexpr (TS && MNMAJOR) {
         if (xc_pre) {   // riding skinny reduction, in the shadow of this stage's MMAs (the operands are already handed over)
         // The stage's xc tile (BK rows x <= 8 columns = 32 float4) was fetched one float4 per lane BEFORE the
-        // wait for the operand tile (xc_cur); the warp passes it round through its 512 B of shared memory and
+        // wait for the operand tile (xc_cur); the warp passes it round through its 512 B (1 KB for 9..16 columns) of shared memory and
         // every lane reads the 16 rows back as broadcasts.  (Loading the rows after the wait -- 16 dependent 128-bit
         // loads in four rounds -- made the main loop of C2a's batched dW1 GEMM 64.6 K cycles per CTA; this form: 46.9 K;
         // without the riding reduction: 27 K.  What-if runs: the prefetch load alone costs 6 K, the FMAs 9 K, the
         // hand-over through shared memory 9 K -- the two splitter groups are a latency chain, every instruction added
         // to an iteration delays the group's next stage.  A dedicated rider warp is the next step, not taken.)
-        float4* xs = reinterpret_cast<float4*>(smem + S::BARS + 512) + (warp - 2) * 32;
+        float4* xs = reinterpret_cast<float4*>(smem + S::BARS + 512) + (warp - 2) * 64;
+        float4* xs2 = xs + 32;                          // columns 8..15
         xs[lane] = xc_cur;
+        if (xc_wide) xs2[lane] = xc_cur2;
         __syncwarp();
         // (two batches of eight broadcast loads, all issued before the FMAs that use them)
         const float ar[16] = {av_r[0].x, av_r[0].y, av_r[0].z, av_r[0].w, av_r[1].x, av_r[1].y, av_r[1].z, av_r[1].w,
@@ -585,6 +595,24 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
             for (int e = 0; e < 8; ++e) {
               sk[4] = fmaf(ar[8 * h + e], v[e].x, sk[4]); sk[5] = fmaf(ar[8 * h + e], v[e].y, sk[5]);
               sk[6] = fmaf(ar[8 * h + e], v[e].z, sk[6]); sk[7] = fmaf(ar[8 * h + e], v[e].w, sk[7]);
+            }
+          }
+          if (xc_wide) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = xs2[2 * (8 * h + e)];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              sk[8] = fmaf(ar[8 * h + e], v[e].x, sk[8]); sk[9] = fmaf(ar[8 * h + e], v[e].y, sk[9]);
+              sk[10] = fmaf(ar[8 * h + e], v[e].z, sk[10]); sk[11] = fmaf(ar[8 * h + e], v[e].w, sk[11]);
+            }
+            if (a.nxc > 12) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = xs2[2 * (8 * h + e) + 1];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                sk[12] = fmaf(ar[8 * h + e], v[e].x, sk[12]); sk[13] = fmaf(ar[8 * h + e], v[e].y, sk[13]);
+                sk[14] = fmaf(ar[8 * h + e], v[e].z, sk[14]); sk[15] = fmaf(ar[8 * h + e], v[e].w, sk[15]);
+              }
             }
           }
         }
@@ -1195,7 +1223,7 @@ template <int BN, int STAGES, int BK, bool TS = false, bool NS = false, int NSG_
 int launch_tn(const TcGemmTnP& p, cudaStream_t st) {
   using S = Smem<BN, STAGES, BK, TS, NS>;
   constexpr int NSG = NSG_ ? NSG_ : (TS ? 2 : 1);
-  constexpr int kXcBytes = TS ? 4 * NSG * 512 : 0;   // per splitter warp: the stage's xc tile (riding skinny reduction), after the barrier block
+  constexpr int kXcBytes = TS ? 4 * NSG * 1024 : 0;   // per splitter warp: the stage's xc tile (riding skinny reduction), after the barrier block
   int r;
   {
     static PerDeviceOnce once;
@@ -1247,8 +1275,9 @@ int launch_tn(const TcGemmTnP& p, cudaStream_t st) {
     NF_CHECK_ARG(!p.skinny || (p.xc && p.nxc >= 1 && p.nxc <= 16), NF_E_BADARG, "tc_gemm_tn: 1..16 skinny columns, got %d", p.nxc);
     a.colsum = p.colsum; a.sColsum = p.sColsum;
     a.xc = p.xc; a.ldxc = p.ldxc; a.nxc = p.skinny ? p.nxc : 0;
-    a.xc_vec = p.skinny && (p.ldxc & 3) == 0 && (reinterpret_cast<uintptr_t>(p.xc) & 15u) == 0 && (p.sXc2 & 3) == 0 &&
-               4 * ((p.nxc + 3) / 4) <= p.ldxc && p.nxc <= 8;
+    a.xc_al = p.skinny && (p.ldxc & 3) == 0 && (reinterpret_cast<uintptr_t>(p.xc) & 15u) == 0 && (p.sXc2 & 3) == 0 &&
+              4 * ((p.nxc + 3) / 4) <= p.ldxc;
+    a.xc_vec = a.xc_al && p.nxc <= 8;
     a.skinny = p.skinny; a.ldsk = p.ldsk; a.sSk = p.sSk;
   }
   if (p.inner > 0) {
