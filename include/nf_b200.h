@@ -175,8 +175,10 @@ NF_API int nf_flow_backward_range(const NfFlowDesc* desc, const float* params, c
  *                     handle; the host gathers the handles of all ranks in rank order and every rank connects; once
  *                     ALL ranks have connected (the host agrees on that), nf_dp_p2p_enable(1) routes nf_dp_allreduce
  *                     and nf_flow_backward_dp of arenas up to max_floats through one peer-store kernel per rank (sum in
- *                     rank order: bit-identical on every replica) instead of NCCL.  status: 1 active, 0 off, -1 a peer
- *                     did not arrive within the kernel's time-out.
+ *                     rank order: bit-identical on every replica) instead of NCCL; with fewer than 8 ranks only arenas of
+ *                     at least NF_B200_DP_P2P_MIN_BYTES (default 2 MB: below that NCCL's low-latency protocol measured
+ *                     faster at 2 and 4 ranks).  status: 1 active, 0 off, -1 a peer did not arrive within the kernel's
+ *                     time-out (~5 min).
  *   nf_flow_backward_dp  nf_flow_backward + the averaged gradient arena: blocks are processed from the top down in
  *                     buckets of `bucket_blocks` blocks; each finished bucket (one contiguous slice of the arena) is
  *                     all-reduced on a side stream while the next bucket computes.  dparams must not be NULL. */
