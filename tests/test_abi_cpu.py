@@ -182,3 +182,16 @@ def test_reduced_precision_mode_is_rejected_not_silently_downgraded():
     d = _lib.make_desc(8, 32, 32, 16, 2, 1e-5, 2)              # NF_PREC_BF16 through the raw ABI
     out = _lib.NfParamLayout()
     assert _lib.lib.nf_param_layout(ctypes.byref(d), ctypes.byref(out)) == -4   # NF_E_UNSUPPORTED
+
+
+def test_peer_memory_allreduce_entry_points_without_a_gpu():
+    """The peer-memory all-reduce (csrc/dp.cu) is for 2..8 ranks of one box: the host side declines anything else
+    before it touches CUDA or the process group, and the C ABI rejects bad arguments with an error code."""
+    from nf_b200.module import _connect_peer_memory
+    cpu = torch.device("cpu")
+    assert _connect_peer_memory(None, cpu, 0, 1) is False      # single process: nothing to exchange
+    assert _connect_peer_memory(None, cpu, 0, 9) is False      # more ranks than one NVSwitch box: NCCL keeps the job
+    assert _lib.lib.nf_dp_p2p_alloc(0, None) < 0               # bad arguments: error code, nothing thrown
+    assert _lib.lib.nf_dp_p2p_connect(None, 0, 2) < 0
+    assert _lib.lib.nf_dp_p2p_connect(ctypes.c_char_p(b"\0" * 64 * 9), 0, 9) < 0
+    assert b"2..8" in _lib.lib.nf_last_error()
